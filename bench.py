@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — CLEVR questions/sec of the module-network hot path on B200 (BASELINE.json metric).
+
+One step = one pass of the hot path over one CLEVR-shaped batch (default 64 questions,
+10x15x512 pool5 grid, T=20 layout tokens, expert-layout mix): host layout compile (C++) ->
+table upload -> text projection -> tcgen05 conv_image contraction with fused Find epilogue ->
+tree kernel -> scores [64,28] on device. Inputs come from a pool of distinct batches resident in
+HBM that is larger than L2, walked round-robin, so no step re-reads a cached batch.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
+    python bench.py --impl reference ...                           # CPU arm (the oracle restatement)
+
+Under torchrun every rank owns one GPU and its own shard of the questions (weak scaling, no
+data-path collective: questions are independent); timing is CUDA events between
+barriers, max over ranks; rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W, D, T_DEC, C, TEXT_DIM = 10, 15, 512, 20, 28, 300
+METRIC = 'clevr_questions_per_sec'
+UNIT = 'questions/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=64, help='questions per GPU per step')
+    ap.add_argument('--layouts', default='expert', choices=['expert', 'random', 'deep'])
+    ap.add_argument('--pool', type=int, default=10, help='distinct resident batches (x19.7 MB)')
+    ap.add_argument('--cpu-seconds', type=float, default=12.0, help='cpu_baseline sample budget')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--wave', action='store_true', help='depth-bucketed wave executor')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d['hbm_gbs'], bf16_tflops=d['bf16_tflops'],
+                    bf16_sustained=d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_sustained=1400.0,
+                source='fallback (B200_PROFILING.md)')
+
+
+def make_tokens(asm, kind, n, seed):
+    from n2nmn_b200 import synth
+    if kind == 'expert':
+        toks = synth.expert_mix_tokens(asm, n, T_DEC)
+        rng = np.random.RandomState(seed)          # same mix, different question order per batch
+        return np.ascontiguousarray(toks[:, rng.permutation(n)])
+    if kind == 'random':
+        return synth.random_valid_tokens(asm, n, T_DEC, seed=seed)
+    return synth.random_valid_tokens(asm, n, T_DEC, seed=seed, ans_weight=0.15, min_depth=3,
+                                     max_depth=12)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._th = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._th:
+            self._th.join(timeout=6)
+        sm = [float(r[1]) for r in self.rows if r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace('.', '').isdigit()]
+        reasons = []
+        for name, col in (('hw_slowdown', 4), ('hw_thermal_slowdown', 5),
+                          ('sw_thermal_slowdown', 6), ('sw_power_cap', 7)):
+            if any(len(r) > col and r[col].lower().startswith('active') for r in self.rows):
+                reasons.append(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(self.rows)}
+
+
+def cpu_reference_qps(feat, word_vecs, weights, tokens_list, budget_s, min_batches=2):
+    """Times the oracle restatement of the reference path (Assembler.assemble + TF-Fold-style
+    depth-batched module calls, numpy/OpenBLAS fp32) on a bounded sample of the workload."""
+    from n2nmn_b200 import synth
+    from n2nmn_b200.assembler import Assembler
+    from oracle.nmn_oracle import OracleModules, run_depth_batched
+    asm = Assembler(synth.vocab_file('clevr'))
+    m = OracleModules(feat, word_vecs, C, weights, family='clevr')
+    exprs, _ = asm.assemble(tokens_list[0])
+    run_depth_batched(m, exprs)                       # warm-up (BLAS threads, caches)
+    n_q, t0, k = 0, time.perf_counter(), 0
+    while True:
+        tok = tokens_list[k % len(tokens_list)]
+        exprs, _ = asm.assemble(tok)
+        run_depth_batched(m, exprs)
+        n_q += tok.shape[1]
+        k += 1
+        el = time.perf_counter() - t0
+        if k >= min_batches and el >= budget_s:
+            break
+    return n_q / el, k, el
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the CPU restatement (oracle) of the reference's TF1 path on host cores;
+    TF 1.0 + TF Fold cannot be installed here. Rank 0 only."""
+    if rank != 0:
+        return
+    from n2nmn_b200 import synth, weights as wts
+    from n2nmn_b200.assembler import Assembler
+    asm = Assembler(synth.vocab_file('clevr'))
+    feat, word_vecs = synth.make_inputs(args.batch, H, W, D, T_DEC, seed=1234)
+    weights = wts.init_weights('clevr', H, W, D, C, seed=0, bias_std=0.1)
+    toks = [make_tokens(asm, args.layouts, args.batch, seed=100 + i) for i in range(4)]
+    from oracle.nmn_oracle import OracleModules, run_depth_batched
+    m = OracleModules(feat, word_vecs, C, weights, family='clevr')
+    for i in range(max(args.warmup, 1)):
+        run_depth_batched(m, asm.assemble(toks[i % 4])[0])
+    steps = min(args.steps, 400)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        run_depth_batched(m, asm.assemble(toks[i % 4])[0])
+    el = time.perf_counter() - t0
+    qps = steps * args.batch / el
+    threads = os.cpu_count()
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': qps, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * el / steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': 'CLEVR gt-layout eval, batch=%d, 10x15x512 pool5, %s layouts, T=%d'
+                   % (args.batch, args.layouts, T_DEC), 'global_batch': args.batch},
+        'cpu_baseline': {'value': qps, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                         'sample': '%d batches of %d questions (oracle/nmn_oracle.py: numpy + '
+                                   'OpenBLAS, Assembler.assemble included)' % (steps, args.batch)},
+        'e2e': {'value': qps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from n2nmn_b200 import _lib, synth, weights as wts
+    from n2nmn_b200.assembler import Assembler
+    from n2nmn_b200.executor import LayoutExecutor
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device. The product path has no CPU fallback.')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    B, P = args.batch, args.pool
+    asm = Assembler(synth.vocab_file('clevr'))
+    weights = wts.init_weights('clevr', H, W, D, C, seed=0, bias_std=0.1)
+    # pool of distinct batches (per-rank seeds = per-rank shard of the global question stream)
+    feats, wvs, toks = [], [], []
+    for i in range(P):
+        f, w = synth.make_inputs(B, H, W, D, T_DEC, seed=1234 + 1000 * rank + i)
+        feats.append(torch.from_numpy(f).to(dev))
+        wvs.append(torch.from_numpy(w).to(dev))
+        toks.append(make_tokens(asm, args.layouts, B, seed=100 + 1000 * rank + i))
+    flags = _lib.FLAG_WAVE_EXECUTOR if args.wave else 0
+    ex = LayoutExecutor('clevr', feats[0], wvs[0], C, asm, weights=weights, flags=flags,
+                        max_batch=B, max_T=T_DEC)
+    scores = torch.empty((B, C), dtype=torch.float32, device=dev)
+
+    def step(i):
+        k = i % P
+        ex.bind(feats[k], wvs[k])
+        cb = ex.compile_tokens(toks[k])
+        ex.run(cb, out=scores)
+        return cb
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ex.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        cb = step(args.warmup + i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ex.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max * 1e-3)
+
+    # ---- e2e: host (pinned) buffers in, host scores out, every step (n2nmn_forward_host)
+    e2e = None
+    if not args.no_e2e:
+        hp = min(P, 4)
+        hf = [feats[i].cpu().pin_memory() for i in range(hp)]
+        hw = [wvs[i].cpu().pin_memory() for i in range(hp)]
+        hs = torch.empty((B, C), dtype=torch.float32).pin_memory()
+        for i in range(3):
+            ex.forward_host(hf[i % hp], hw[i % hp], toks[i % hp], hs)
+        k_e2e = max(10, min(args.steps, 100))
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(k_e2e):
+            ex.forward_host(hf[i % hp], hw[i % hp], toks[i % hp], hs)
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        te = torch.tensor([el], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {'value': world * B * k_e2e / float(te.item()), 'unit': UNIT,
+               'h2d_bytes_per_step': int(hf[0].numel() * 4 + hw[0].numel() * 4 + 65536),
+               'd2h_bytes_per_step': int(hs.numel() * 4), 'steps': k_e2e,
+               'how': 'n2nmn_forward_host: pinned host features+word_vecs -> H2D -> compile -> '
+                      'kernels -> D2H scores, synchronous per step, wall clock'}
+
+    # ---- roofline of the dominant kernel: per-launch CUDA events, separate pass of the same steps
+    roof, kernel_us = None, {}
+    if rank == 0:
+        pk = peaks()
+        ex.set_profiling(True)
+        acc, bytes_acc, flops_acc, n = {}, 0, 0, 0
+        for i in range(min(args.steps, 50)):
+            cb = step(i)
+            for name, us in ex.launch_times():
+                acc.setdefault(name, []).append(us)
+            bytes_acc += cb.info['kernel_bytes'][1]
+            flops_acc += cb.info['kernel_flops'][1]
+            n += 1
+        ex.set_profiling(False)
+        kernel_us = {k: float(np.mean(v)) for k, v in acc.items()}
+        proj = 'proj_umma_kernel'
+        if proj in kernel_us and n:
+            dur = kernel_us[proj] * 1e-6
+            gbs = bytes_acc / n / dur / 1e9
+            tfs = flops_acc / n / dur / 1e12
+            tf32_peak = pk['bf16_tflops'] / 2
+            hbm_frac, tc_frac = gbs / pk['hbm_gbs'], tfs / tf32_peak
+            bound = 'hbm' if hbm_frac >= tc_frac else 'tensor'
+            roof = {'kernel': proj, 'bound': bound,
+                    'achieved': gbs if bound == 'hbm' else tfs,
+                    'peak': pk['hbm_gbs'] if bound == 'hbm' else tf32_peak,
+                    'unit': 'GB/s' if bound == 'hbm' else 'TFLOP/s',
+                    'frac': max(hbm_frac, tc_frac), 'traffic': None,
+                    'hbm_frac': hbm_frac, 'tensor_frac_of_tf32_peak': tc_frac,
+                    'avg_launch_us': kernel_us[proj],
+                    'algorithmic_bytes_per_launch': bytes_acc / n,
+                    'flops_per_launch': flops_acc / n,
+                    'peak_source': pk['source'] + '; TF32 peak taken as bf16 burst / 2',
+                    'share_of_step': kernel_us[proj] / max(sum(kernel_us.values()), 1e-9)}
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        f0, w0 = feats[0].cpu().numpy(), wvs[0].cpu().numpy()
+        qps, nb, el = cpu_reference_qps(f0, w0, weights, toks[:4], args.cpu_seconds)
+        cpu = {'value': qps, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+               'sample': '%d batches of %d questions in %.1f s (oracle/nmn_oracle.py: numpy+OpenBLAS '
+                         'fp32 depth-batched restatement, Assembler.assemble included)' % (nb, B, el)}
+
+    if rank == 0:
+        info = cb.info
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_max / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32 (fp32 in/out, fp32 accumulate)',
+            'data': 'synthetic',
+            'config': {'workload': 'CLEVR gt-layout eval, batch=%d/GPU, 10x15x512 pool5, %s '
+                                   'layouts depth<=12, T=%d' % (B, args.layouts, T_DEC),
+                       'global_batch': B * world, 'parallelism': 'dp%d (question shards, no '
+                       'collective)' % world,
+                       'cache': 'inputs larger than L2: %d distinct resident batches (%.0f MB) '
+                                'walked round-robin' % (P, P * B * H * W * D * 4 / 1e6),
+                       'executor': 'wave' if args.wave else 'tree',
+                       'nodes_per_batch': info['num_nodes'], 'max_depth': info['max_depth']},
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
+            'roofline': roof, 'cpu_baseline': cpu, 'kernel_us': kernel_us,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

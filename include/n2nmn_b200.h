@@ -1,0 +1,197 @@
+/*
+ * n2nmn_b200 — C ABI of the B200-native N2NMN module-network hot path.
+ *
+ * The reference (ronghanghu/n2nmn) has no FFI of its own: its hot path is a chain of TensorFlow
+ * graph calls made from Python. Each entry point below therefore names the reference *Python*
+ * interface it replaces (paths under the reference repo); INTEGRATION.md shows the ctypes stubs a
+ * maintainer of the reference would add to `models_clevr/nmn3_modules.py` / `nmn3_model.py`.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative n2nmn_status otherwise; the message of the
+ *     last failure on the calling thread is available from n2nmn_last_error(); nothing throws
+ *     across this boundary;
+ *   - "dev" pointers are CUDA device pointers to contiguous row-major fp32 (NHWC) / int32 data
+ *     owned by the caller and valid until the work enqueued on `stream` has finished;
+ *     "host" pointers are ordinary host memory read/written before the call returns unless
+ *     stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream). All device work is
+ *     enqueued on it; no call synchronises the device except where documented;
+ *   - a ctx is not thread-safe: one ctx per GPU per host thread.
+ *   - the library runs on sm_100a only and fails with N2NMN_ERR_DEVICE elsewhere. There is no
+ *     CPU fallback.
+ */
+#ifndef N2NMN_B200_H_
+#define N2NMN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define N2NMN_ABI_VERSION 1
+
+typedef struct n2nmn_ctx n2nmn_ctx;
+typedef struct n2nmn_sched n2nmn_sched;
+
+enum n2nmn_status {
+  N2NMN_OK = 0,
+  N2NMN_ERR_ARG = -1,      /* bad argument / shape */
+  N2NMN_ERR_CUDA = -2,     /* a CUDA call failed */
+  N2NMN_ERR_DEVICE = -3,   /* not an sm_100 device */
+  N2NMN_ERR_STATE = -4,    /* weights / inputs not bound yet */
+  N2NMN_ERR_CAPACITY = -5  /* batch / T / node count exceeds what the ctx was created for */
+};
+
+/* Model families = the three near-identical packages of the reference
+ * (models_clevr/, models_shapes/, models_vqa/). */
+enum n2nmn_family { N2NMN_CLEVR = 0, N2NMN_SHAPES = 1, N2NMN_VQA = 2 };
+
+/* Module opcodes. One per method of `class Modules`
+ * (models_clevr/nmn3_modules.py:60-495). VQA `_Transform` is N2NMN_OP_FIND_SAME_PROPERTY with the
+ * TransformModule weights (models_vqa/nmn3_modules.py:123-171); SHAPES `_Answer` is
+ * N2NMN_OP_EXIST with the AnswerModule weights (models_shapes/nmn3_modules.py:123-150). */
+enum n2nmn_op {
+  N2NMN_OP_SCENE = 0,
+  N2NMN_OP_FIND = 1,
+  N2NMN_OP_FILTER = 2,
+  N2NMN_OP_FIND_SAME_PROPERTY = 3,
+  N2NMN_OP_TRANSFORM = 4,
+  N2NMN_OP_AND = 5,
+  N2NMN_OP_OR = 6,
+  N2NMN_OP_EXIST = 7,
+  N2NMN_OP_COUNT = 8,
+  N2NMN_OP_EQUAL_NUM = 9,
+  N2NMN_OP_MORE_NUM = 10,
+  N2NMN_OP_LESS_NUM = 11,
+  N2NMN_OP_SAME_PROPERTY = 12,
+  N2NMN_OP_DESCRIBE = 13,
+  N2NMN_NUM_OPS = 14
+};
+
+enum n2nmn_flags {
+  /* Compute the conv_image contraction with the fp32 CUDA-core kernel instead of the tcgen05
+   * TF32 tensor-core kernel. Verification aid (bit-compatible with nothing, but free of TF32
+   * rounding); never the default. */
+  N2NMN_FLAG_PROJ_FP32_SIMT = 1,
+  /* Execute the layout as depth-bucketed waves (one launch per tree depth over all questions)
+   * instead of the default one-CTA-per-question tree walk. Same results. */
+  N2NMN_FLAG_WAVE_EXECUTOR = 2
+};
+
+typedef struct n2nmn_config {
+  int32_t abi_version;   /* N2NMN_ABI_VERSION */
+  int32_t family;        /* enum n2nmn_family */
+  int32_t H, W, D;       /* feature grid handed to Modules (D excludes the VQA coord channels) */
+  int32_t text_dim;      /* 300 */
+  int32_t map_dim;       /* 250 (CLEVR) / 500 (SHAPES) / 1024 (VQA) */
+  int32_t kernel_size;   /* 5 / 3; unused for VQA */
+  int32_t num_choices;
+  int32_t max_batch;     /* capacity: questions per bind */
+  int32_t max_T;         /* capacity: decoder steps */
+  int32_t device;        /* CUDA device ordinal */
+  int32_t flags;         /* enum n2nmn_flags */
+} n2nmn_config;
+
+/* Replaces `Modules.__init__` (models_clevr/nmn3_modules.py:12-47): allocates the context,
+ * weight storage and workspaces. Weights are NOT initialised here; see n2nmn_set_weight. */
+int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out);
+int n2nmn_destroy(n2nmn_ctx* ctx);
+const char* n2nmn_last_error(void);
+
+/* Number of variables the family owns and their TF names / shapes, in a fixed order
+ * (scope capture at models_clevr/nmn3_modules.py:17-18,91-92). Names are
+ * relative to `.../module_variables/`, e.g. "FindModule/conv_image/weights". */
+int n2nmn_num_variables(const n2nmn_ctx* ctx);
+int n2nmn_variable_info(const n2nmn_ctx* ctx, int index, const char** name, int64_t shape[4],
+                        int* ndim);
+
+/* Replaces tf.get_variable / Saver.restore for one variable: copies `src_dev` (fp32, TF layout)
+ * into the context, repacking it for the kernels (K-major padded conv_image matrices etc.).
+ * Call again after an optimiser step. */
+int n2nmn_set_weight(n2nmn_ctx* ctx, const char* name, const float* src_dev, const int64_t* shape,
+                     int ndim, void* stream);
+
+/* Replaces the placeholder feeds of `Modules(image_feat_grid, word_vecs, ...)`
+ * (models_clevr/nmn3_modules.py:12-26): image_feat_grid [N,H,W,D], word_vecs [T,N,text_dim].
+ * Both stay caller-owned and are read in place (VQA: an augmented copy with the two coordinate
+ * channels of models_vqa/nmn3_modules.py:11-31 is built on `stream`). */
+int n2nmn_bind_inputs(n2nmn_ctx* ctx, const float* feat_dev, const float* word_vecs_dev, int N,
+                      int T, void* stream);
+
+/* One batched module call = one `Modules.<X>Module(...)` invocation with leading dimension n
+ * (models_clevr/nmn3_modules.py:60-495): in0/in1 attention maps [n,H,W,1] (NULL when the module
+ * takes fewer), time_idx/batch_idx HOST int32 [n] (scheduling metadata), out = attention maps
+ * [n,H,W,1] or answer scores [n,num_choices] depending on the op. n == 0 is legal (TF Fold's
+ * zero-size batches, util/empty_safe_conv.py:9-11) and does nothing. */
+int n2nmn_module_fwd(n2nmn_ctx* ctx, int op, const float* in0_dev, const float* in1_dev,
+                     const int32_t* time_idx_host, const int32_t* batch_idx_host, int n,
+                     float* out_dev, void* stream);
+
+/* Replaces `Assembler.assemble` + `td.Compiler.build_feed_dict`
+ * (models_clevr/nmn3_assembler.py:153-222, models_clevr/nmn3_model.py:146-159): parses the
+ * Reverse-Polish layout tokens [T,N] (host int32, time-major) with the assembler's stack
+ * discipline, writes validity_out[N] (1 = valid), and compiles the valid trees into launch tables.
+ * `vocab_ops[v]` gives the n2nmn_op of token v, or -1 for <eos>. Host-only, no device sync; the
+ * tables are uploaded by the first n2nmn_run_schedule that uses them. */
+int n2nmn_compile_schedule(n2nmn_ctx* ctx, const int32_t* tokens_host, int T, int N,
+                           const int32_t* vocab_ops, int num_vocab, uint8_t* validity_out,
+                           n2nmn_sched** out);
+/* n2nmn_compile_schedule without a context or a GPU (pure host logic; used by the CPU tests and
+ * by callers that pre-compile layouts on loader threads). Only family/H/W/D/text_dim/map_dim/
+ * kernel_size/num_choices/max_T of `cfg` are read. */
+int n2nmn_compile_schedule_host(const n2nmn_config* cfg, const int32_t* tokens_host, int T, int N,
+                                const int32_t* vocab_ops, int num_vocab, uint8_t* validity_out,
+                                n2nmn_sched** out);
+/* Same output as n2nmn_compile_schedule, from already-assembled expression trees (what
+ * `compiler.build_feed_dict(expr_list)` receives, models_clevr/nmn3_model.py:158): nodes are listed
+ * question by question in post-order (operands before their consumer); q_ptr[NQ+1] delimits the
+ * questions (an empty range = INVALID_EXPR -> zero scores row); in0/in1 index into the node list
+ * (-1 = none). batch_idx may differ from the question index. */
+int n2nmn_compile_nodes(n2nmn_ctx* ctx, const int32_t* op, const int32_t* time_idx,
+                        const int32_t* batch_idx, const int32_t* in0, const int32_t* in1,
+                        int num_nodes, const int32_t* q_ptr, int num_questions,
+                        n2nmn_sched** out);
+int n2nmn_sched_destroy(n2nmn_sched* sched);
+
+typedef struct n2nmn_sched_info {
+  int32_t num_questions, num_valid, num_nodes, max_depth;
+  int32_t num_text_nodes, num_find_nodes, num_proj_tiles, num_launches;
+  int64_t algorithmic_bytes;   /* SURVEY.md §8(d)/App. D per-node figure summed over the batch */
+  int64_t algorithmic_flops;
+  /* §8(d) per-launch figures (distinct feature tiles counted once per launch, weights once):
+   * [0] text projection kernel, [1] conv_image contraction kernel, [2] node kernel(s) */
+  int64_t kernel_bytes[3];
+  int64_t kernel_flops[3];
+} n2nmn_sched_info;
+int n2nmn_sched_get_info(const n2nmn_sched* sched, n2nmn_sched_info* info);
+/* Node table in (question, token) order: op, time_idx, batch_idx, depth, in0, in1 (node ids or
+ * -1) as 6 int32 per node — lets callers map the attention arena back to expression nodes. */
+int n2nmn_sched_get_nodes(const n2nmn_sched* sched, int32_t* out6, int capacity_nodes);
+
+/* Replaces `sess.partial_run(h, scores, feed_dict=expr_feed)` (exp_clevr/eval_clevr.py:132):
+ * evaluates every node of the compiled batch against the bound inputs and writes
+ * scores_dev [N,num_choices] (rows of invalid layouts = 0, models_clevr/nmn3_model.py:144-155).
+ * att_arena_dev, if not NULL, receives every node's attention map, [num_nodes,H,W] indexed by
+ * node id (answer nodes' slots are left untouched). Asynchronous on `stream`. */
+int n2nmn_run_schedule(n2nmn_ctx* ctx, n2nmn_sched* sched, float* scores_dev,
+                       float* att_arena_dev, void* stream);
+
+/* End-to-end convenience with HOST buffers (what exp_clevr/eval_clevr.py:103-135 does per batch):
+ * H2D of features + word vectors, compile, run, D2H of scores; synchronises `stream` before
+ * returning. Host buffers should be pinned for full PCIe rate. */
+int n2nmn_forward_host(n2nmn_ctx* ctx, const float* feat_host, const float* word_vecs_host,
+                       const int32_t* tokens_host, int T, int N, const int32_t* vocab_ops,
+                       int num_vocab, float* scores_host, uint8_t* validity_out, void* stream);
+
+/* Per-launch device time of the last n2nmn_run_schedule in microseconds (CUDA events recorded
+ * around every launch when enabled). names/us arrays of length >= capacity. */
+int n2nmn_set_profiling(n2nmn_ctx* ctx, int enabled);
+int n2nmn_get_launch_times(n2nmn_ctx* ctx, const char** names, float* us, int capacity);
+/* Count of kernel launches issued by this ctx since creation. */
+int64_t n2nmn_launch_count(const n2nmn_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* N2NMN_B200_H_ */

@@ -1,0 +1,805 @@
+// C ABI of the N2NMN module-network hot path (include/n2nmn_b200.h): context, weight packing,
+// input binding, schedule upload and kernel launches. sm_100a only; no CPU fallback.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/n2nmn_b200.h"
+#include "common.cuh"
+#include "node_eval.cuh"
+#include "prep.cuh"
+#include "proj_simt.cuh"
+#include "proj_umma.cuh"
+#include "schedule.hpp"
+#include "text_proj.cuh"
+
+using namespace n2nmn;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      return fail(N2NMN_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));   \
+  } while (0)
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+enum VarKind { VK_PLAIN = 0, VK_PROJ_W, VK_PROJ_B };
+
+struct Variable {
+  std::string name;
+  std::vector<int64_t> shape;
+  VarKind kind;
+  int set;           // projection set for VK_PROJ_*
+  size_t offset;     // float offset of the plain copy inside wbuf
+  size_t count;
+  const float** slot;   // DevModel pointer to fill (plain copy)
+  bool loaded;
+};
+
+constexpr int kTableSlots = 4;
+
+struct TableSlot {
+  uint8_t* host = nullptr;   // pinned staging
+  uint8_t* dev = nullptr;
+  uint64_t uid = 0;          // schedule resident here (0 = none)
+  cudaEvent_t last_use = nullptr;
+};
+
+struct TableOffsets {
+  size_t nodes, q_ptr, text_t, text_b, groups, work, img_ptr, node_text, node_out, mslot,
+      wave_nodes, total;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct n2nmn_sched {
+  HostSchedule hs;
+  uint64_t uid;
+};
+
+struct n2nmn_ctx {
+  n2nmn_config cfg;
+  int device = 0, num_sms = 0;
+  int HW = 0, Dk = 0, Kp = 0, Mp = 0;
+  SchedShape shp;
+  DevModel md;
+  std::vector<Variable> vars;
+  float* wbuf = nullptr;
+  size_t wbuf_floats = 0;
+  float* proj_wt[NUM_PROJ_SETS] = {nullptr, nullptr};    // [Mp][Kp]
+  float* proj_bias[NUM_PROJ_SETS] = {nullptr, nullptr};  // [Mp]
+  // inputs
+  bool bound = false;
+  int N = 0, T = 0;
+  float* feat_aug = nullptr;   // ctx-owned re-pitched / coordinate-augmented copy
+  // workspaces
+  TextBufs tb = {nullptr, nullptr, nullptr};
+  int text_rows_cap = 0;
+  float* arena = nullptr;
+  int arena_slots = 0;
+  float* mbuf = nullptr;
+  float* scores_tmp = nullptr;
+  TableSlot slots[kTableSlots];
+  size_t table_cap = 0;
+  int next_slot = 0;
+  ProjTensorMaps tmaps;
+  bool tmap_b_ready[NUM_PROJ_SETS] = {false, false};
+  EncodeTiledFn encode = nullptr;
+  int node_smem_bytes = 0;
+  n2nmn_sched module_sched;    // scratch schedule of n2nmn_module_fwd
+  // e2e staging
+  float* e2e_feat = nullptr;
+  float* e2e_wv = nullptr;
+  float* e2e_scores = nullptr;
+  // profiling
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<const char*> ev_names;
+  int ev_used = 0;
+  int64_t launches = 0;
+};
+
+namespace {
+
+std::atomic<uint64_t> g_uid{1};
+
+void add_var(n2nmn_ctx* c, const std::string& name, std::vector<int64_t> shape, VarKind kind,
+             int set, const float** slot) {
+  Variable v;
+  v.name = name; v.shape = shape; v.kind = kind; v.set = set; v.slot = slot; v.loaded = false;
+  v.count = 1;
+  for (int64_t d : shape) v.count *= (size_t)d;
+  v.offset = c->wbuf_floats;
+  c->wbuf_floats += (v.count + 3) & ~(size_t)3;
+  c->vars.push_back(v);
+}
+
+void add_layer(n2nmn_ctx* c, const std::string& scope, std::vector<int64_t> wshape,
+               const float** wslot, const float** bslot, int proj_set = -1) {
+  add_var(c, scope + "/weights", wshape, proj_set >= 0 ? VK_PROJ_W : VK_PLAIN, proj_set, wslot);
+  add_var(c, scope + "/biases", {wshape.back()}, proj_set >= 0 ? VK_PROJ_B : VK_PLAIN, proj_set,
+          bslot);
+}
+
+// Variable table; order and names match n2nmn_b200/weights.py::variable_shapes.
+void build_variables(n2nmn_ctx* c) {
+  const n2nmn_config& g = c->cfg;
+  DevModel& md = c->md;
+  const int64_t D = c->Dk, M = g.map_dim, Dt = g.text_dim, C = g.num_choices, k = g.kernel_size;
+  const int64_t HW = c->HW;
+  add_layer(c, "FindModule/conv_image", {D, M}, &md.proj_w[PS_FIND], nullptr, PS_FIND);
+  add_layer(c, "FindModule/fc_text", {Dt, M}, &md.txt_w[TS_FIND], &md.txt_b[TS_FIND]);
+  add_layer(c, "FindModule/conv_eltwise", {M, 1}, &md.elt_w[ES_FIND], &md.elt_b[ES_FIND]);
+  if (g.family == N2NMN_VQA) {
+    add_layer(c, "TransformModule/conv_image", {D, M}, &md.proj_w[PS_FSP], nullptr, PS_FSP);
+    add_layer(c, "TransformModule/fc_text", {Dt, M}, &md.txt_w[TS_FSP], &md.txt_b[TS_FSP]);
+    add_layer(c, "TransformModule/fc_att", {D, M}, &md.att_w[AS_FSP], &md.att_b[AS_FSP]);
+    add_layer(c, "TransformModule/conv_eltwise", {M, 1}, &md.elt_w[ES_FSP], &md.elt_b[ES_FSP]);
+  } else {
+    add_layer(c, "TransformModule/conv_maps", {k, k, 1, M}, &md.conv_k, &md.conv_b);
+    add_layer(c, "TransformModule/text_fc", {Dt, M}, &md.txt_w[TS_TRANSFORM],
+              &md.txt_b[TS_TRANSFORM]);
+    add_layer(c, "TransformModule/conv_eltwise", {M, 1}, &md.elt_w[ES_TRANSFORM],
+              &md.elt_b[ES_TRANSFORM]);
+  }
+  if (g.family == N2NMN_SHAPES) {
+    add_layer(c, "AnswerModule/fc_scores", {3, C}, &md.sc_w[SS_EXIST], &md.sc_b[SS_EXIST]);
+    return;
+  }
+  if (g.family == N2NMN_CLEVR) {
+    add_layer(c, "FindSamePropertyModule/conv_image", {D, M}, &md.proj_w[PS_FSP], nullptr, PS_FSP);
+    add_layer(c, "FindSamePropertyModule/fc_text", {Dt, M}, &md.txt_w[TS_FSP], &md.txt_b[TS_FSP]);
+    add_layer(c, "FindSamePropertyModule/fc_att", {D, M}, &md.att_w[AS_FSP], &md.att_b[AS_FSP]);
+    add_layer(c, "FindSamePropertyModule/conv_eltwise", {M, 1}, &md.elt_w[ES_FSP],
+              &md.elt_b[ES_FSP]);
+    add_layer(c, "ExistModule/fc_scores", {3, C}, &md.sc_w[SS_EXIST], &md.sc_b[SS_EXIST]);
+    add_layer(c, "CountModule/fc_scores", {HW + 2, C}, &md.sc_w[SS_COUNT], &md.sc_b[SS_COUNT]);
+    add_layer(c, "EqualNumModule/fc_scores", {2 * (HW + 2), C}, &md.sc_w[SS_EQUAL],
+              &md.sc_b[SS_EQUAL]);
+    add_layer(c, "MoreNumModule/fc_scores", {2 * (HW + 2), C}, &md.sc_w[SS_MORE],
+              &md.sc_b[SS_MORE]);
+    add_layer(c, "LessNumModule/fc_scores", {2 * (HW + 2), C}, &md.sc_w[SS_LESS],
+              &md.sc_b[SS_LESS]);
+    add_layer(c, "SamePropertyModule/fc_text", {Dt, M}, &md.txt_w[TS_SAMEPROP],
+              &md.txt_b[TS_SAMEPROP]);
+    add_layer(c, "SamePropertyModule/fc_att_0", {D, M}, &md.att_w[AS_SAMEPROP0],
+              &md.att_b[AS_SAMEPROP0]);
+    add_layer(c, "SamePropertyModule/fc_att_1", {D, M}, &md.att_w[AS_SAMEPROP1],
+              &md.att_b[AS_SAMEPROP1]);
+    add_layer(c, "SamePropertyModule/fc_eltwise", {M, C}, &md.out_w[OS_SAMEPROP],
+              &md.out_b[OS_SAMEPROP]);
+  }
+  add_layer(c, "DescribeModule/fc_text", {Dt, M}, &md.txt_w[TS_DESCRIBE], &md.txt_b[TS_DESCRIBE]);
+  add_layer(c, "DescribeModule/fc_att", {D, M}, &md.att_w[AS_DESCRIBE], &md.att_b[AS_DESCRIBE]);
+  add_layer(c, "DescribeModule/fc_eltwise", {M, C}, &md.out_w[OS_DESCRIBE],
+            &md.out_b[OS_DESCRIBE]);
+}
+
+int encode_2d(n2nmn_ctx* c, CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer,
+              uint64_t pitch_elems, uint32_t box_inner, uint32_t box_outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * sizeof(float)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = c->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims,
+                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(N2NMN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
+  return 0;
+}
+
+TableOffsets table_offsets(const HostSchedule& S) {
+  TableOffsets o;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t at = off; off += (bytes + 15) & ~(size_t)15; return at; };
+  o.nodes = take(S.nodes.size() * sizeof(NodeRec));
+  o.q_ptr = take(S.q_ptr.size() * 4);
+  o.text_t = take(S.text_t.size() * 4);
+  o.text_b = take(S.text_b.size() * 4);
+  o.groups = take(S.groups.size() * sizeof(TextGroup));
+  o.work = take(S.work.size() * sizeof(ProjWork));
+  o.img_ptr = take(S.img_ptr.size() * 4);
+  o.node_text = take(S.node_text.size() * 4);
+  o.node_out = take(S.node_out.size() * 4);
+  o.mslot = take(S.mslot.size() * 4);
+  o.wave_nodes = take(S.wave_nodes.size() * 4);
+  o.total = off;
+  return o;
+}
+
+template <class V>
+void put(uint8_t* base, size_t off, const V& v) {
+  if (!v.empty()) std::memcpy(base + off, v.data(), v.size() * sizeof(v[0]));
+}
+
+void prof_mark(n2nmn_ctx* c, const char* name, cudaStream_t st) {
+  if (!c->profiling) return;
+  if (c->ev_used >= (int)c->ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    c->ev.push_back(e);
+    c->ev_names.push_back(name);
+  }
+  c->ev_names[c->ev_used] = name;
+  cudaEventRecord(c->ev[c->ev_used++], st);
+}
+
+// Uploads (if needed) and launches everything for one compiled batch.
+int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaStream_t st) {
+  const HostSchedule& S = sc->hs;
+  const TableOffsets o = table_offsets(S);
+  if (o.total > c->table_cap)
+    return fail(N2NMN_ERR_CAPACITY, "schedule tables exceed the context capacity");
+  if ((int)S.text_t.size() > c->text_rows_cap)
+    return fail(N2NMN_ERR_CAPACITY, "too many text nodes for this context");
+  // ---- table residency
+  TableSlot* slot = nullptr;
+  for (int i = 0; i < kTableSlots; ++i)
+    if (c->slots[i].uid == sc->uid) slot = &c->slots[i];
+  if (!slot) {
+    slot = &c->slots[c->next_slot];
+    c->next_slot = (c->next_slot + 1) % kTableSlots;
+    CUDA_TRY(cudaEventSynchronize(slot->last_use));   // previous tenant no longer in flight
+    put(slot->host, o.nodes, S.nodes);
+    put(slot->host, o.q_ptr, S.q_ptr);
+    put(slot->host, o.text_t, S.text_t);
+    put(slot->host, o.text_b, S.text_b);
+    put(slot->host, o.groups, S.groups);
+    put(slot->host, o.work, S.work);
+    put(slot->host, o.img_ptr, S.img_ptr);
+    put(slot->host, o.node_text, S.node_text);
+    put(slot->host, o.node_out, S.node_out);
+    put(slot->host, o.mslot, S.mslot);
+    put(slot->host, o.wave_nodes, S.wave_nodes);
+    CUDA_TRY(cudaMemcpyAsync(slot->dev, slot->host, o.total, cudaMemcpyHostToDevice, st));
+    slot->uid = sc->uid;
+  }
+  const uint8_t* d = slot->dev;
+  const NodeRec* d_nodes = reinterpret_cast<const NodeRec*>(d + o.nodes);
+  const int32_t* d_qptr = reinterpret_cast<const int32_t*>(d + o.q_ptr);
+
+  c->ev_used = 0;
+  prof_mark(c, "begin", st);
+  // ---- K1 text projections
+  if (!S.groups.empty()) {
+    dim3 grid(c->Mp / 256, (unsigned)S.groups.size());
+    text_proj_kernel<<<grid, 256, kTextRowsPerCta * c->cfg.text_dim * sizeof(float), st>>>(
+        c->md, c->tb, reinterpret_cast<const TextGroup*>(d + o.groups),
+        reinterpret_cast<const int32_t*>(d + o.text_t),
+        reinterpret_cast<const int32_t*>(d + o.text_b));
+    ++c->launches;
+    prof_mark(c, "text_proj_kernel", st);
+  }
+  // ---- K2 conv_image contraction with fused Find / stored FindSameProperty maps
+  if (!S.work.empty()) {
+    ProjParams p;
+    p.work = reinterpret_cast<const ProjWork*>(d + o.work);
+    p.num_work = (int)S.work.size();
+    p.total_rows = c->md.N * c->HW;
+    p.n_tiles = c->Mp / 256;
+    p.k_blocks = (c->Dk + kBK - 1) / kBK;
+    p.HW = c->HW; p.M = c->cfg.map_dim; p.Mp = c->Mp; p.Dk = c->Dk;
+    p.feat_pitch = c->md.feat_pitch;
+    p.feat = c->md.feat;
+    for (int s = 0; s < NUM_PROJ_SETS; ++s) {
+      p.bias[s] = c->proj_bias[s];
+      p.w_orig[s] = c->md.proj_w[s];
+    }
+    p.img_ptr = reinterpret_cast<const int32_t*>(d + o.img_ptr);
+    p.node_text = reinterpret_cast<const int32_t*>(d + o.node_text);
+    p.node_out = reinterpret_cast<const int32_t*>(d + o.node_out);
+    p.tauw = c->tb.tauw; p.tau2 = c->tb.tau2;
+    p.elt_b = c->md.elt_b[ES_FIND];
+    p.arena = arena;
+    p.mslot = reinterpret_cast<const int32_t*>(d + o.mslot);
+    p.mbuf = c->mbuf;
+    const int grid = std::min(p.num_work, c->num_sms);
+    if (c->cfg.flags & N2NMN_FLAG_PROJ_FP32_SIMT) {
+      const size_t smem = (size_t)(kSimtRows * kSimtKChunk + kSimtRows * c->Mp) * sizeof(float);
+      proj_simt_kernel<<<p.num_work, 256, smem, st>>>(p);
+      prof_mark(c, "proj_simt_kernel", st);
+    } else {
+      proj_umma_kernel<<<grid, kProjThreads, kProjSmemBytes, st>>>(c->tmaps, p);
+      prof_mark(c, "proj_umma_kernel", st);
+    }
+    ++c->launches;
+  }
+  // ---- K3 node evaluation
+  NodeCtx nc;
+  nc.md = c->md; nc.tb = c->tb; nc.arena = arena; nc.scores = scores; nc.mbuf = c->mbuf;
+  const int NQ = (int)S.q_ptr.size() - 1;
+  const bool ks3 = (c->cfg.kernel_size != 5);
+  if (c->cfg.flags & N2NMN_FLAG_WAVE_EXECUTOR) {
+    CUDA_TRY(cudaMemsetAsync(scores, 0, (size_t)NQ * c->cfg.num_choices * sizeof(float), st));
+    const int32_t* d_wave = reinterpret_cast<const int32_t*>(d + o.wave_nodes);
+    for (int dep = 1; dep <= S.max_depth; ++dep) {
+      const int first = S.wave_ptr[dep], cnt = S.wave_ptr[dep + 1] - first;
+      if (cnt == 0) continue;
+      if (ks3) wave_kernel<3><<<cnt, kNodeThreads, c->node_smem_bytes, st>>>(nc, d_nodes, d_wave, first);
+      else wave_kernel<5><<<cnt, kNodeThreads, c->node_smem_bytes, st>>>(nc, d_nodes, d_wave, first);
+      ++c->launches;
+      prof_mark(c, "wave_kernel", st);
+    }
+  } else if (NQ > 0) {
+    if (ks3) tree_kernel<3><<<NQ, kNodeThreads, c->node_smem_bytes, st>>>(nc, d_nodes, d_qptr);
+    else tree_kernel<5><<<NQ, kNodeThreads, c->node_smem_bytes, st>>>(nc, d_nodes, d_qptr);
+    ++c->launches;
+    prof_mark(c, "tree_kernel", st);
+  }
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(slot->last_use, st));
+  return 0;
+}
+
+int check_ready(n2nmn_ctx* c) {
+  if (!c->bound) return fail(N2NMN_ERR_STATE, "n2nmn_bind_inputs has not been called");
+  for (const Variable& v : c->vars)
+    if (!v.loaded) return fail(N2NMN_ERR_STATE, "variable not set: " + v.name);
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================== C ABI
+extern "C" {
+
+const char* n2nmn_last_error(void) { return g_err.c_str(); }
+
+int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
+  if (!cfg || !out) return fail(N2NMN_ERR_ARG, "null argument");
+  if (cfg->abi_version != N2NMN_ABI_VERSION) return fail(N2NMN_ERR_ARG, "ABI version mismatch");
+  if (cfg->family < 0 || cfg->family > 2 || cfg->H <= 0 || cfg->W <= 0 || cfg->D <= 0 ||
+      cfg->map_dim <= 0 || cfg->map_dim > 1024 || cfg->num_choices <= 0 || cfg->max_batch <= 0 ||
+      cfg->max_T <= 0 || cfg->text_dim <= 0)
+    return fail(N2NMN_ERR_ARG, "bad configuration");
+  if (cfg->family != N2NMN_VQA && cfg->kernel_size != 3 && cfg->kernel_size != 5)
+    return fail(N2NMN_ERR_ARG, "kernel_size must be 3 or 5");
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10)
+    return fail(N2NMN_ERR_DEVICE, std::string("n2nmn_b200 needs an sm_100 GPU, found sm_") +
+                                      std::to_string(prop.major) + std::to_string(prop.minor));
+  n2nmn_ctx* c = new n2nmn_ctx();
+  c->cfg = *cfg;
+  if (cfg->family == N2NMN_VQA) c->cfg.kernel_size = 1;
+  c->device = cfg->device;
+  c->num_sms = prop.multiProcessorCount;
+  c->HW = cfg->H * cfg->W;
+  c->Dk = cfg->D + (cfg->family == N2NMN_VQA ? 2 : 0);
+  c->Kp = round_up(c->Dk, kBK);
+  c->Mp = round_up(cfg->map_dim, 256);
+  std::memset(&c->md, 0, sizeof(c->md));
+  DevModel& md = c->md;
+  md.H = cfg->H; md.W = cfg->W; md.HW = c->HW; md.Dk = c->Dk; md.Dt = cfg->text_dim;
+  md.M = cfg->map_dim; md.Mp = c->Mp; md.C = cfg->num_choices; md.ksize = c->cfg.kernel_size;
+  md.family = cfg->family;
+  c->shp = SchedShape{cfg->family, cfg->H, cfg->W, c->Dk, cfg->text_dim, cfg->map_dim, c->Mp,
+                      cfg->num_choices, c->cfg.kernel_size, cfg->max_T};
+  build_variables(c);
+
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess)
+    return fail(N2NMN_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  c->encode = reinterpret_cast<EncodeTiledFn>(fn);
+
+  // weights: plain copies + repacked projection operands
+  CUDA_TRY(cudaMalloc(&c->wbuf, c->wbuf_floats * sizeof(float)));
+  CUDA_TRY(cudaMemset(c->wbuf, 0, c->wbuf_floats * sizeof(float)));
+  for (Variable& v : c->vars)
+    if (v.slot) *v.slot = c->wbuf + v.offset;
+  for (int s = 0; s < NUM_PROJ_SETS; ++s) {
+    CUDA_TRY(cudaMalloc(&c->proj_wt[s], (size_t)c->Mp * c->Kp * sizeof(float)));
+    CUDA_TRY(cudaMemset(c->proj_wt[s], 0, (size_t)c->Mp * c->Kp * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c->proj_bias[s], (size_t)c->Mp * sizeof(float)));
+    CUDA_TRY(cudaMemset(c->proj_bias[s], 0, (size_t)c->Mp * sizeof(float)));
+    md.proj_b[s] = c->proj_bias[s];
+    if (int rc = encode_2d(c, &c->tmaps.b[s], c->proj_wt[s], c->Kp, c->Mp, c->Kp, kBK, kBN))
+      return rc;
+  }
+  // workspaces
+  const int NB = cfg->max_batch, TT = cfg->max_T;
+  c->text_rows_cap = NB * TT;
+  const size_t tb_floats = (size_t)c->text_rows_cap * c->Mp;
+  CUDA_TRY(cudaMalloc(&c->tb.tau, 3 * tb_floats * sizeof(float)));
+  c->tb.tauw = c->tb.tau + tb_floats;
+  c->tb.tau2 = c->tb.tauw + tb_floats;
+  c->arena_slots = std::max(NB * TT, 3 * NB);
+  CUDA_TRY(cudaMalloc(&c->arena, (size_t)c->arena_slots * c->HW * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&c->mbuf, (size_t)NB * c->HW * c->Mp * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&c->scores_tmp, (size_t)NB * TT * cfg->num_choices * sizeof(float)));
+  if (cfg->family == N2NMN_VQA || (cfg->D % 4) != 0) {
+    CUDA_TRY(cudaMalloc(&c->feat_aug, (size_t)NB * c->HW * c->Kp * sizeof(float)));
+  }
+  // schedule tables: generous upper bound on every table for (max_batch, max_T)
+  {
+    const size_t nodes = (size_t)NB * TT;
+    const size_t tiles = ((size_t)NB * c->HW + 127) / 128 + 1;
+    c->table_cap = nodes * (sizeof(NodeRec) + 4 * 6) + (nodes / 8 + 8) * sizeof(TextGroup) +
+                   tiles * (TT / kMaxProjNodesPerPass + 2) * 2 * sizeof(ProjWork) +
+                   (size_t)NB * 16 + 4096;
+    for (int i = 0; i < kTableSlots; ++i) {
+      CUDA_TRY(cudaMallocHost(&c->slots[i].host, c->table_cap));
+      CUDA_TRY(cudaMalloc(&c->slots[i].dev, c->table_cap));
+      CUDA_TRY(cudaEventCreateWithFlags(&c->slots[i].last_use, cudaEventDisableTiming));
+    }
+  }
+  // kernel attributes
+  const NodeSmem L = node_smem_layout(cfg->H, cfg->W, c->Dk, c->Mp, c->cfg.kernel_size,
+                                      cfg->map_dim);
+  c->node_smem_bytes = L.total * (int)sizeof(float);
+  CUDA_TRY(cudaFuncSetAttribute(tree_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                c->node_smem_bytes));
+  CUDA_TRY(cudaFuncSetAttribute(tree_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                c->node_smem_bytes));
+  CUDA_TRY(cudaFuncSetAttribute(wave_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                c->node_smem_bytes));
+  CUDA_TRY(cudaFuncSetAttribute(wave_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                c->node_smem_bytes));
+  CUDA_TRY(cudaFuncSetAttribute(proj_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kProjSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(
+      proj_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      (int)((kSimtRows * kSimtKChunk + kSimtRows * c->Mp) * sizeof(float))));
+  c->module_sched.uid = g_uid++;
+  *out = c;
+  return 0;
+}
+
+int n2nmn_destroy(n2nmn_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  cudaFree(c->wbuf);
+  for (int s = 0; s < NUM_PROJ_SETS; ++s) { cudaFree(c->proj_wt[s]); cudaFree(c->proj_bias[s]); }
+  cudaFree(c->feat_aug); cudaFree(c->tb.tau); cudaFree(c->arena); cudaFree(c->mbuf);
+  cudaFree(c->scores_tmp); cudaFree(c->e2e_feat); cudaFree(c->e2e_wv); cudaFree(c->e2e_scores);
+  for (int i = 0; i < kTableSlots; ++i) {
+    cudaFreeHost(c->slots[i].host); cudaFree(c->slots[i].dev);
+    if (c->slots[i].last_use) cudaEventDestroy(c->slots[i].last_use);
+  }
+  for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+  delete c;
+  return 0;
+}
+
+int n2nmn_num_variables(const n2nmn_ctx* c) { return c ? (int)c->vars.size() : 0; }
+
+int n2nmn_variable_info(const n2nmn_ctx* c, int index, const char** name, int64_t shape[4],
+                        int* ndim) {
+  if (!c || index < 0 || index >= (int)c->vars.size()) return fail(N2NMN_ERR_ARG, "bad index");
+  const Variable& v = c->vars[index];
+  if (name) *name = v.name.c_str();
+  if (ndim) *ndim = (int)v.shape.size();
+  if (shape) for (size_t i = 0; i < v.shape.size() && i < 4; ++i) shape[i] = v.shape[i];
+  return 0;
+}
+
+int n2nmn_set_weight(n2nmn_ctx* c, const char* name, const float* src, const int64_t* shape,
+                     int ndim, void* stream) {
+  if (!c || !name || !src) return fail(N2NMN_ERR_ARG, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (Variable& v : c->vars) {
+    if (v.name != name) continue;
+    if (ndim != (int)v.shape.size()) return fail(N2NMN_ERR_ARG, std::string("rank mismatch for ") + name);
+    for (int i = 0; i < ndim; ++i)
+      if (shape[i] != v.shape[i]) return fail(N2NMN_ERR_ARG, std::string("shape mismatch for ") + name);
+    CUDA_TRY(cudaMemcpyAsync(c->wbuf + v.offset, src, v.count * sizeof(float),
+                             cudaMemcpyDeviceToDevice, st));
+    if (v.kind == VK_PROJ_W) {
+      dim3 grid((c->Kp + 31) / 32, (c->Mp + 31) / 32), block(32, 8);
+      transpose_pad_kernel<<<grid, block, 0, st>>>(c->wbuf + v.offset, c->Dk, c->cfg.map_dim,
+                                                   c->proj_wt[v.set], c->Kp, c->Mp);
+    } else if (v.kind == VK_PROJ_B) {
+      pad_copy_kernel<<<(c->Mp + 255) / 256, 256, 0, st>>>(c->wbuf + v.offset, c->cfg.map_dim,
+                                                           c->proj_bias[v.set], c->Mp);
+    }
+    CUDA_TRY(cudaGetLastError());
+    v.loaded = true;
+    return 0;
+  }
+  return fail(N2NMN_ERR_ARG, std::string("unknown variable: ") + name);
+}
+
+int n2nmn_bind_inputs(n2nmn_ctx* c, const float* feat, const float* wv, int N, int T,
+                      void* stream) {
+  if (!c || !feat || !wv) return fail(N2NMN_ERR_ARG, "null argument");
+  if (N <= 0 || T <= 0) return fail(N2NMN_ERR_ARG, "N and T must be positive");
+  if (N > c->cfg.max_batch || T > c->cfg.max_T)
+    return fail(N2NMN_ERR_CAPACITY, "N or T exceeds the context capacity");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int rows = N * c->HW;
+  const float* eff = feat;
+  int pitch = c->cfg.D;
+  if (c->feat_aug) {
+    augment_features_kernel<<<rows, 128, 0, st>>>(feat, rows, c->cfg.D, c->cfg.H, c->cfg.W,
+                                                 c->cfg.family == N2NMN_VQA ? 1 : 0, c->feat_aug,
+                                                 c->Kp);
+    CUDA_TRY(cudaGetLastError());
+    ++c->launches;
+    eff = c->feat_aug;
+    pitch = c->Kp;
+  }
+  if ((reinterpret_cast<uintptr_t>(eff) & 15) != 0)
+    return fail(N2NMN_ERR_ARG, "image_feat_grid must be 16-byte aligned");
+  c->md.feat = eff; c->md.feat_pitch = pitch; c->md.word_vecs = wv; c->md.N = N; c->md.T = T;
+  c->N = N; c->T = T;
+  if (int rc = encode_2d(c, &c->tmaps.a, eff, c->Dk, rows, pitch, kBK, kBM)) return rc;
+  c->bound = true;
+  return 0;
+}
+
+int n2nmn_compile_schedule(n2nmn_ctx* c, const int32_t* tokens, int T, int N,
+                           const int32_t* vocab_ops, int num_vocab, uint8_t* validity_out,
+                           n2nmn_sched** out) {
+  if (!c || !tokens || !vocab_ops || !out) return fail(N2NMN_ERR_ARG, "null argument");
+  if (N <= 0 || T <= 0) return fail(N2NMN_ERR_ARG, "N and T must be positive");
+  if (N > c->cfg.max_batch || T > c->cfg.max_T)
+    return fail(N2NMN_ERR_CAPACITY, "N or T exceeds the context capacity");
+  n2nmn_sched* sc = new n2nmn_sched();
+  sc->uid = g_uid++;
+  const char* err = nullptr;
+  const int rc = compile_schedule(c->shp, tokens, T, N, vocab_ops, num_vocab, &sc->hs, &err);
+  if (rc) { delete sc; return fail(rc, err ? err : "compile_schedule failed"); }
+  if (validity_out) std::memcpy(validity_out, sc->hs.validity.data(), N);
+  *out = sc;
+  return 0;
+}
+
+int n2nmn_compile_schedule_host(const n2nmn_config* cfg, const int32_t* tokens, int T, int N,
+                                const int32_t* vocab_ops, int num_vocab, uint8_t* validity_out,
+                                n2nmn_sched** out) {
+  if (!cfg || !tokens || !vocab_ops || !out) return fail(N2NMN_ERR_ARG, "null argument");
+  if (N <= 0 || T <= 0) return fail(N2NMN_ERR_ARG, "N and T must be positive");
+  const int Dk = cfg->D + (cfg->family == N2NMN_VQA ? 2 : 0);
+  const SchedShape shp{cfg->family, cfg->H, cfg->W, Dk, cfg->text_dim, cfg->map_dim,
+                       round_up(cfg->map_dim, 256), cfg->num_choices,
+                       cfg->family == N2NMN_VQA ? 1 : cfg->kernel_size, cfg->max_T};
+  n2nmn_sched* sc = new n2nmn_sched();
+  sc->uid = g_uid++;
+  const char* err = nullptr;
+  const int rc = compile_schedule(shp, tokens, T, N, vocab_ops, num_vocab, &sc->hs, &err);
+  if (rc) { delete sc; return fail(rc, err ? err : "compile_schedule failed"); }
+  if (validity_out) std::memcpy(validity_out, sc->hs.validity.data(), N);
+  *out = sc;
+  return 0;
+}
+
+int n2nmn_compile_nodes(n2nmn_ctx* c, const int32_t* op, const int32_t* t_idx,
+                        const int32_t* b_idx, const int32_t* in0, const int32_t* in1, int n,
+                        const int32_t* q_ptr, int nq, n2nmn_sched** out) {
+  if (!c || !q_ptr || !out || (n > 0 && (!op || !t_idx || !b_idx || !in0 || !in1)))
+    return fail(N2NMN_ERR_ARG, "null argument");
+  if (nq <= 0 || nq > c->cfg.max_batch) return fail(N2NMN_ERR_CAPACITY, "bad question count");
+  if (q_ptr[0] != 0 || q_ptr[nq] != n) return fail(N2NMN_ERR_ARG, "q_ptr does not span the nodes");
+  static const int arity[NUM_OPS] = {0, 0, 1, 1, 1, 2, 2, 1, 1, 2, 2, 2, 2, 1};
+  static const bool is_ans[NUM_OPS] = {0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1};
+  n2nmn_sched* sc = new n2nmn_sched();
+  sc->uid = g_uid++;
+  HostSchedule& S = sc->hs;
+  S.N = nq; S.T = c->cfg.max_T;
+  S.nodes.resize(n); S.depth.assign(n, 1);
+  S.q_ptr.assign(q_ptr, q_ptr + nq + 1);
+  S.validity.assign(nq, 0);
+  const int scene_bits = [] { float v = 3.0f; int b; std::memcpy(&b, &v, 4); return b; }();
+  for (int q = 0; q < nq; ++q) {
+    if (q_ptr[q + 1] < q_ptr[q]) { delete sc; return fail(N2NMN_ERR_ARG, "q_ptr not monotone"); }
+    if (q_ptr[q + 1] > q_ptr[q]) { S.validity[q] = 1; ++S.num_valid; }
+    for (int i = q_ptr[q]; i < q_ptr[q + 1]; ++i) {
+      NodeRec& r = S.nodes[i];
+      const int o = op[i];
+      bool ok = o >= 0 && o < NUM_OPS && t_idx[i] >= 0 && t_idx[i] < c->cfg.max_T &&
+                b_idx[i] >= 0 && b_idx[i] < c->cfg.max_batch;
+      const int kids[2] = {in0[i], in1[i]};
+      for (int k = 0; ok && k < 2; ++k) {
+        if (k < arity[o]) {
+          ok = kids[k] >= q_ptr[q] && kids[k] < i && !is_ans[op[kids[k]]];
+          if (ok) S.depth[i] = std::max(S.depth[i], S.depth[kids[k]] + 1);
+        } else {
+          ok = kids[k] < 0;
+        }
+      }
+      if (ok && is_ans[o] != (i == q_ptr[q + 1] - 1)) ok = false;   // exactly the root answers
+      if (!ok) { delete sc; return fail(N2NMN_ERR_ARG, "malformed expression node " + std::to_string(i)); }
+      r.op = o; r.t = t_idx[i]; r.b = b_idx[i];
+      r.in0 = in0[i]; r.in1 = in1[i];
+      r.out = is_ans[o] ? q : i;
+      r.text = -1;
+      r.aux = (o == OP_SCENE) ? scene_bits : -1;
+    }
+  }
+  if (int rc = finalize_schedule(c->shp, c->cfg.max_batch, &S)) {
+    delete sc;
+    return fail(rc, "finalize_schedule failed");
+  }
+  *out = sc;
+  return 0;
+}
+
+int n2nmn_sched_destroy(n2nmn_sched* s) { delete s; return 0; }
+
+int n2nmn_sched_get_info(const n2nmn_sched* s, n2nmn_sched_info* info) {
+  if (!s || !info) return fail(N2NMN_ERR_ARG, "null argument");
+  const HostSchedule& S = s->hs;
+  info->num_questions = (int)S.q_ptr.size() - 1;
+  info->num_valid = S.num_valid;
+  info->num_nodes = (int)S.nodes.size();
+  info->max_depth = S.max_depth;
+  info->num_text_nodes = (int)S.text_t.size();
+  info->num_find_nodes = S.num_find_nodes;
+  info->num_proj_tiles = (int)S.work.size();
+  info->num_launches = (S.groups.empty() ? 0 : 1) + (S.work.empty() ? 0 : 1) + 1;
+  info->algorithmic_bytes = S.per_node_bytes;
+  info->algorithmic_flops = S.per_node_flops;
+  for (int k = 0; k < 3; ++k) { info->kernel_bytes[k] = S.kbytes[k]; info->kernel_flops[k] = S.kflops[k]; }
+  return 0;
+}
+
+int n2nmn_sched_get_nodes(const n2nmn_sched* s, int32_t* out6, int cap) {
+  if (!s || !out6) return fail(N2NMN_ERR_ARG, "null argument");
+  const HostSchedule& S = s->hs;
+  if (cap < (int)S.nodes.size()) return fail(N2NMN_ERR_CAPACITY, "node buffer too small");
+  for (size_t i = 0; i < S.nodes.size(); ++i) {
+    const NodeRec& r = S.nodes[i];
+    int32_t* o = out6 + 6 * i;
+    o[0] = r.op; o[1] = r.t; o[2] = r.b; o[3] = S.depth[i]; o[4] = r.in0; o[5] = r.in1;
+  }
+  return (int)S.nodes.size();
+}
+
+int n2nmn_run_schedule(n2nmn_ctx* c, n2nmn_sched* s, float* scores, float* att_arena,
+                       void* stream) {
+  if (!c || !s || !scores) return fail(N2NMN_ERR_ARG, "null argument");
+  if (int rc = check_ready(c)) return rc;
+  for (const NodeRec& r : s->hs.nodes)
+    if (r.b >= c->N || r.t >= c->T)
+      return fail(N2NMN_ERR_ARG, "schedule refers to a batch/time index outside the bound inputs");
+  if ((int)s->hs.img_ptr.size() - 1 > c->N && s->hs.img_ptr.back() != s->hs.img_ptr[c->N])
+    return fail(N2NMN_ERR_ARG, "schedule image range exceeds the bound inputs");
+  float* arena = att_arena ? att_arena : c->arena;
+  if (!att_arena && (int)s->hs.nodes.size() > c->arena_slots)
+    return fail(N2NMN_ERR_CAPACITY, "too many nodes for the context arena");
+  return run_tables(c, s, scores, arena, static_cast<cudaStream_t>(stream));
+}
+
+int n2nmn_module_fwd(n2nmn_ctx* c, int op, const float* in0, const float* in1,
+                     const int32_t* t_idx, const int32_t* b_idx, int n, float* out,
+                     void* stream) {
+  if (!c) return fail(N2NMN_ERR_ARG, "null context");
+  if (op < 0 || op >= NUM_OPS) return fail(N2NMN_ERR_ARG, "bad opcode");
+  if (n == 0) return 0;   // TF Fold's zero-size batches: nothing to do
+  if (n < 0 || !out) return fail(N2NMN_ERR_ARG, "bad arguments");
+  if (int rc = check_ready(c)) return rc;
+  static const int arity[NUM_OPS] = {0, 0, 1, 1, 1, 2, 2, 1, 1, 2, 2, 2, 2, 1};
+  static const bool is_ans[NUM_OPS] = {0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1};
+  static const bool needs_idx[NUM_OPS] = {0, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 1, 1};
+  if ((arity[op] >= 1 && !in0) || (arity[op] >= 2 && !in1))
+    return fail(N2NMN_ERR_ARG, "missing attention input");
+  if (needs_idx[op] && (!t_idx || !b_idx))
+    return fail(N2NMN_ERR_ARG, "time_idx / batch_idx required for this module");
+  if (3 * n > c->arena_slots || n > c->text_rows_cap)
+    return fail(N2NMN_ERR_CAPACITY, "n exceeds the context capacity for a single module call");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  n2nmn_sched* sc = &c->module_sched;
+  sc->uid = g_uid++;   // tables change every call
+  HostSchedule& S = sc->hs;
+  S = HostSchedule();
+  S.N = c->N; S.T = c->T;
+  S.nodes.resize(n); S.depth.assign(n, 1); S.q_ptr.resize(n + 1);
+  const int scene_bits = [] { float v = 3.0f; int b; std::memcpy(&b, &v, 4); return b; }();
+  for (int i = 0; i < n; ++i) {
+    NodeRec& r = S.nodes[i];
+    r.op = op;
+    r.t = t_idx ? t_idx[i] : 0;
+    r.b = b_idx ? b_idx[i] : 0;
+    if (needs_idx[op] && (r.b < 0 || r.b >= c->N || r.t < 0 || r.t >= c->T))
+      return fail(N2NMN_ERR_ARG, "time_idx / batch_idx out of range");
+    if (!needs_idx[op]) { r.t = 0; r.b = 0; }
+    r.in0 = arity[op] >= 1 ? i : -1;
+    r.in1 = arity[op] >= 2 ? n + i : -1;
+    r.out = is_ans[op] ? i : 2 * n + i;
+    r.text = -1;
+    r.aux = (op == OP_SCENE) ? scene_bits : -1;
+    S.q_ptr[i] = i;
+  }
+  S.q_ptr[n] = n;
+  if (int rc = finalize_schedule(c->shp, c->N, &S)) return fail(rc, "finalize_schedule failed");
+  const size_t map_bytes = (size_t)n * c->HW * sizeof(float);
+  if (arity[op] >= 1)
+    CUDA_TRY(cudaMemcpyAsync(c->arena, in0, map_bytes, cudaMemcpyDeviceToDevice, st));
+  if (arity[op] >= 2)
+    CUDA_TRY(cudaMemcpyAsync(c->arena + (size_t)n * c->HW, in1, map_bytes,
+                             cudaMemcpyDeviceToDevice, st));
+  float* scores = is_ans[op] ? out : c->scores_tmp;
+  if (int rc = run_tables(c, sc, scores, c->arena, st)) return rc;
+  if (!is_ans[op])
+    CUDA_TRY(cudaMemcpyAsync(out, c->arena + (size_t)2 * n * c->HW, map_bytes,
+                             cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int n2nmn_forward_host(n2nmn_ctx* c, const float* feat_host, const float* wv_host,
+                       const int32_t* tokens, int T, int N, const int32_t* vocab_ops,
+                       int num_vocab, float* scores_host, uint8_t* validity_out, void* stream) {
+  if (!c || !feat_host || !wv_host || !tokens || !scores_host)
+    return fail(N2NMN_ERR_ARG, "null argument");
+  if (N <= 0 || N > c->cfg.max_batch || T <= 0 || T > c->cfg.max_T)
+    return fail(N2NMN_ERR_CAPACITY, "N or T exceeds the context capacity");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t fbytes = (size_t)N * c->HW * c->cfg.D * sizeof(float);
+  const size_t wbytes = (size_t)T * N * c->cfg.text_dim * sizeof(float);
+  const size_t sbytes = (size_t)N * c->cfg.num_choices * sizeof(float);
+  if (!c->e2e_feat) {
+    CUDA_TRY(cudaMalloc(&c->e2e_feat, (size_t)c->cfg.max_batch * c->HW * c->cfg.D * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c->e2e_wv, (size_t)c->cfg.max_T * c->cfg.max_batch * c->cfg.text_dim *
+                                        sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c->e2e_scores, (size_t)c->cfg.max_batch * c->cfg.num_choices *
+                                            sizeof(float)));
+  }
+  CUDA_TRY(cudaMemcpyAsync(c->e2e_feat, feat_host, fbytes, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(c->e2e_wv, wv_host, wbytes, cudaMemcpyHostToDevice, st));
+  if (int rc = n2nmn_bind_inputs(c, c->e2e_feat, c->e2e_wv, N, T, stream)) return rc;
+  n2nmn_sched* sc = nullptr;
+  if (int rc = n2nmn_compile_schedule(c, tokens, T, N, vocab_ops, num_vocab, validity_out, &sc))
+    return rc;
+  int rc = n2nmn_run_schedule(c, sc, c->e2e_scores, nullptr, stream);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(scores_host, c->e2e_scores, sbytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(N2NMN_ERR_CUDA, cudaGetErrorString(e));
+  } else {
+    cudaStreamSynchronize(st);
+  }
+  n2nmn_sched_destroy(sc);
+  return rc;
+}
+
+int n2nmn_set_profiling(n2nmn_ctx* c, int enabled) {
+  if (!c) return fail(N2NMN_ERR_ARG, "null context");
+  c->profiling = enabled != 0;
+  return 0;
+}
+
+int n2nmn_get_launch_times(n2nmn_ctx* c, const char** names, float* us, int cap) {
+  if (!c) return fail(N2NMN_ERR_ARG, "null context");
+  if (c->ev_used < 2) return 0;
+  if (cudaEventSynchronize(c->ev[c->ev_used - 1]) != cudaSuccess)
+    return fail(N2NMN_ERR_CUDA, "event sync failed");
+  int n = 0;
+  for (int i = 1; i < c->ev_used && n < cap; ++i, ++n) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev[i - 1], c->ev[i]);
+    if (names) names[n] = c->ev_names[i];
+    if (us) us[n] = ms * 1000.f;
+  }
+  return n;
+}
+
+int64_t n2nmn_launch_count(const n2nmn_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+// Shared device-side types and helpers for the N2NMN module-network kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace n2nmn {
+
+constexpr float kEps = 1e-12f;   // tf.nn.l2_normalize epsilon (models_clevr/nmn3_modules.py:107)
+constexpr int kNodeThreads = 256;
+constexpr int kMaxProjNodesPerPass = 8;
+
+// Opcodes mirror enum n2nmn_op in include/n2nmn_b200.h.
+enum Op : int {
+  OP_SCENE = 0, OP_FIND, OP_FILTER, OP_FIND_SAME_PROPERTY, OP_TRANSFORM, OP_AND, OP_OR,
+  OP_EXIST, OP_COUNT, OP_EQUAL_NUM, OP_MORE_NUM, OP_LESS_NUM, OP_SAME_PROPERTY, OP_DESCRIBE,
+  NUM_OPS
+};
+
+// Weight-set indices.
+enum ProjSetId { PS_FIND = 0, PS_FSP = 1, NUM_PROJ_SETS = 2 };
+enum TextSetId { TS_FIND = 0, TS_FSP, TS_TRANSFORM, TS_SAMEPROP, TS_DESCRIBE, NUM_TEXT_SETS };
+enum AttSetId { AS_FSP = 0, AS_SAMEPROP0, AS_SAMEPROP1, AS_DESCRIBE, NUM_ATT_SETS };
+enum OutSetId { OS_SAMEPROP = 0, OS_DESCRIBE, NUM_OUT_SETS };
+enum ScoreSetId { SS_EXIST = 0, SS_COUNT, SS_EQUAL, SS_MORE, SS_LESS, NUM_SCORE_SETS };
+enum EltSetId { ES_FIND = 0, ES_FSP, ES_TRANSFORM, NUM_ELT_SETS };
+
+// One expression-tree node as the kernels see it (32 bytes).
+struct NodeRec {
+  int32_t op;
+  int32_t t, b;      // time index (token position) and question / image index
+  int32_t in0, in1;  // arena slots of the attention inputs (-1 if none)
+  int32_t out;       // arena slot of the attention output, or score row for answer modules
+  int32_t text;      // row in the text-projection buffers (-1 if the module takes no text)
+  int32_t aux;       // FindSameProperty: slot of the image's projected map in mbuf
+};
+
+// Everything the kernels need to know about the model; pointers are device pointers into the
+// context-owned packed weight buffer.
+struct DevModel {
+  int H, W, HW, Dk, feat_pitch, Dt, M, Mp, C, ksize, family;
+  const float* feat;        // [N*HW, feat_pitch] (Dk valid channels)
+  const float* word_vecs;   // [T, N, Dt]
+  int N, T;
+  // conv_image contraction: original [Dk][M] (fp32 CUDA-core path), bias padded to Mp
+  const float* proj_w[NUM_PROJ_SETS];
+  const float* proj_b[NUM_PROJ_SETS];
+  const float* txt_w[NUM_TEXT_SETS];   // [Dt][M]
+  const float* txt_b[NUM_TEXT_SETS];   // [M]
+  const float* elt_w[NUM_ELT_SETS];    // conv_eltwise weights [M]
+  const float* elt_b[NUM_ELT_SETS];    // [1]
+  const float* conv_k;                 // conv_maps [k*k][M]
+  const float* conv_b;                 // [M]
+  const float* att_w[NUM_ATT_SETS];    // fc_att [Dk][M]
+  const float* att_b[NUM_ATT_SETS];
+  const float* out_w[NUM_OUT_SETS];    // fc_eltwise [M][C]
+  const float* out_b[NUM_OUT_SETS];
+  const float* sc_w[NUM_SCORE_SETS];   // fc_scores [L][C]
+  const float* sc_b[NUM_SCORE_SETS];
+};
+
+// Text-projection outputs, all [rows][Mp] with zero padding in columns >= M.
+struct TextBufs {
+  float* tau;    // t·W + b
+  float* tauw;   // tau ∘ conv_eltwise weights of the consuming module (or tau)
+  float* tau2;   // tau²
+};
+
+// Host-compiled launch tables (built by schedule.cpp, consumed by the kernels).
+struct TextGroup { int32_t set, start, count, pad; };   // <= kTextRowsPerCta rows of one text set
+constexpr int kTextRowsPerCta = 8;
+struct ProjWork { int32_t row0, pass, set, pad; };      // one 128-row tile of the contraction
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide reductions for kNodeThreads threads; `red` is >= 32 floats of shared scratch.
+// All threads get the result. Contains __syncthreads.
+template <int MODE>  // 0 sum, 1 max, 2 min
+__device__ __forceinline__ float block_reduce(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (MODE == 0) v = warp_sum(v);
+  else if (MODE == 1) v = warp_max(v);
+  else v = warp_min(v);
+  __syncthreads();   // protect `red` from the previous use
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  float r = (lane < nw) ? red[lane] : (MODE == 0 ? 0.f : (MODE == 1 ? -INFINITY : INFINITY));
+  if (MODE == 0) r = warp_sum(r);
+  else if (MODE == 1) r = warp_max(r);
+  else r = warp_min(r);
+  return r;
+}
+
+}  // namespace n2nmn

@@ -1,0 +1,53 @@
+// One-off data-layout kernels: weight repacking at n2nmn_set_weight time and the VQA
+// coordinate-channel augmentation at bind time.
+#pragma once
+#include "common.cuh"
+
+namespace n2nmn {
+
+// W [K][M] (TF layout, models_clevr/nmn3_modules.py:101 'conv_image/weights') ->
+// Wt [Mp][Kp] K-major with zero padding: the B operand layout of the tcgen05 contraction.
+__global__ void transpose_pad_kernel(const float* __restrict__ W, int K, int M,
+                                     float* __restrict__ Wt, int Kp, int Mp) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, m = m0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < K && m < M) ? W[(size_t)k * M + m] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int m = m0 + i, k = k0 + threadIdx.x;
+    if (m < Mp && k < Kp) Wt[(size_t)m * Kp + k] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void pad_copy_kernel(const float* __restrict__ src, int n, float* __restrict__ dst,
+                                int np) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < np) dst[i] = (i < n) ? src[i] : 0.f;
+}
+
+// add_spatial_coordinate_map (models_vqa/nmn3_modules.py:11-31): dst[r, :] =
+// [src[r, 0:D], x, y, 0...] with x = linspace(-1,1,W)[col], y = linspace(-1,1,H)[row]; also used
+// (with_coords = 0) to re-pitch feature grids whose channel count is not a multiple of 4.
+__global__ void augment_features_kernel(const float* __restrict__ src, int rows, int D, int H,
+                                        int W, int with_coords, float* __restrict__ dst,
+                                        int pitch) {
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  const int pix = r % (H * W);
+  const int y = pix / W, x = pix - y * W;
+  // tf.linspace(-1., 1., n)[i] = -1 + i * (2 / (n - 1)); n == 1 gives -1
+  const float xv = (W > 1) ? -1.f + (float)x * (2.f / (float)(W - 1)) : -1.f;
+  const float yv = (H > 1) ? -1.f + (float)y * (2.f / (float)(H - 1)) : -1.f;
+  for (int c = threadIdx.x; c < pitch; c += blockDim.x) {
+    float v = 0.f;
+    if (c < D) v = src[(size_t)r * D + c];
+    else if (with_coords && c == D) v = xv;
+    else if (with_coords && c == D + 1) v = yv;
+    dst[(size_t)r * pitch + c] = v;
+  }
+}
+
+}  // namespace n2nmn

@@ -1,0 +1,227 @@
+// K2: conv_image contraction on the 5th-gen tensor cores (tcgen05, kind::tf32) with the module
+// epilogue fused on the TMEM accumulator. See proj_common.cuh for the math and what is fused.
+//
+// Tiling: one work item = 128 consecutive rows of the flattened (image, pixel) axis x all Mp
+// output columns, walked as Mp/256 N-tiles of 256 columns (UMMA 128x256x8, fp32 operands read as
+// TF32 straight from the caller's fp32 feature grid — no conversion pass). K is streamed in
+// 32-float (128-byte, one swizzle atom) slices through a 4-stage TMA->smem ring:
+//     stage = A tile 128x32 fp32 (16 KB) + B tile 256x32 fp32 (32 KB), both SWIZZLE_128B K-major.
+// TMEM holds two 128x256 fp32 accumulators (all 512 columns), so the epilogue of N-tile i
+// overlaps the MMAs of N-tile i+1 / of the next work item.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
+// MMA issuer (one elected lane), warps 2..5 = epilogue; epilogue warp w reads TMEM lanes
+// [32*(w%4), 32*(w%4)+32) i.e. tile rows with that offset.
+//
+// Precision: TF32 operands (10-bit mantissa), fp32 accumulate. Error budget vs the fp32/fp64
+// oracle is in DESIGN.md; tests/test_gpu_parity.py holds every attention map to 1e-3 abs.
+#pragma once
+#include "proj_common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace n2nmn {
+
+constexpr int kBM = 128;           // rows per tile (UMMA M)
+constexpr int kBN = 256;           // columns per N-tile (UMMA N)
+constexpr int kBK = 32;            // fp32 elements per K slice = 128 bytes
+constexpr int kUmmaK = 8;          // K per tcgen05.mma for tf32 (32 bytes)
+constexpr int kStages = 4;
+constexpr int kABytes = kBM * kBK * 4;   // 16384
+constexpr int kBBytes = kBN * kBK * 4;   // 32768
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kProjThreads = 192;
+constexpr int kTmemCols = 512;
+// dynamic smem: stages + barriers, plus 1024 for manual alignment
+constexpr int kProjSmemBytes = kStages * kStageBytes + 256 + 1024;
+
+struct ProjTensorMaps {
+  CUtensorMap a;                     // features [total_rows, Dk] fp32, box 32 x 128
+  CUtensorMap b[NUM_PROJ_SETS];      // W^T [Mp, Kp] fp32 (K-major), box 32 x 256
+};
+
+__global__ void __launch_bounds__(kProjThreads, 1)
+proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tensormap(&tm.a);
+    ptx::prefetch_tensormap(&tm.b[0]);
+    ptx::prefetch_tensormap(&tm.b[1]);
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], 4);   // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<kTmemCols>(tmem_base_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int wi = blockIdx.x; wi < p.num_work; wi += gridDim.x) {
+        const ProjWork wk = p.work[wi];
+        for (int nt = 0; nt < p.n_tiles; ++nt) {
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+            ptx::tma_load_2d(smem_a + stage * kABytes, &tm.a, kb * kBK, wk.row0,
+                             &full_bar[stage]);
+            ptx::tma_load_2d(smem_b + stage * kBBytes, &tm.b[wk.set], kb * kBK, nt * kBN,
+                             &full_bar[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_tf32(kBM, kBN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;   // accumulator uses so far
+      for (int wi = blockIdx.x; wi < p.num_work; wi += gridDim.x) {
+        for (int nt = 0; nt < p.n_tiles; ++nt, ++it) {
+          const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+          ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // epilogue drained this buffer
+          ptx::tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * kBN;
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            ptx::mbar_wait(&full_bar[stage], phase);          // TMA bytes landed
+            ptx::tc_fence_after();
+            const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * kABytes));
+            const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * kBBytes));
+#pragma unroll
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              // advance 32 bytes (= 2 x 16-byte units) along K inside the swizzle atom
+              ptx::umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            }
+            ptx::umma_commit(&empty_bar[stage]);              // frees the smem slot when done
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          ptx::umma_commit(&tmem_full[acc]);                  // accumulator ready
+        }
+      }
+    }
+  } else {
+    // ===================================================================== epilogue warps
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may access
+    const int trow = quarter * 32 + lane;      // row inside the 128-row tile
+    uint32_t it = 0;
+    for (int wi = blockIdx.x; wi < p.num_work; wi += gridDim.x) {
+      const ProjWork wk = p.work[wi];
+      const int row = wk.row0 + trow;
+      const bool row_ok = row < p.total_rows;
+      const int b = row_ok ? row / p.HW : 0;
+      const int pix = row - b * p.HW;
+      // consumers of this row
+      int e_beg = 0, n_nodes = 0;
+      float* mdst = nullptr;
+      if (row_ok) {
+        if (wk.set == PS_FIND) {
+          e_beg = p.img_ptr[b] + wk.pass * kMaxProjNodesPerPass;
+          n_nodes = min(p.img_ptr[b + 1] - e_beg, kMaxProjNodesPerPass);
+          n_nodes = max(n_nodes, 0);
+        } else {
+          const int slot = p.mslot[b];
+          if (slot >= 0) mdst = p.mbuf + ((size_t)slot * p.HW + pix) * p.Mp;
+        }
+      }
+      float num[kMaxProjNodesPerPass], den[kMaxProjNodesPerPass];
+#pragma unroll
+      for (int j = 0; j < kMaxProjNodesPerPass; ++j) { num[j] = 0.f; den[j] = 0.f; }
+      const float* __restrict__ bias = p.bias[wk.set];
+
+      for (int nt = 0; nt < p.n_tiles; ++nt, ++it) {
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        ptx::mbar_wait(&tmem_full[acc], acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kBN;
+#pragma unroll 1
+        for (int ch = 0; ch < kBN / 32; ++ch) {
+          float v[32];
+          __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the per-lane branches
+          ptx::tmem_ld_32x32b_x32(taddr + ch * 32, v);
+          const int col0 = nt * kBN + ch * 32;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + col0) + q);
+            v[4 * q + 0] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
+          }
+          if (mdst != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              reinterpret_cast<float4*>(mdst + col0)[q] =
+                  make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+#pragma unroll
+          for (int j = 0; j < kMaxProjNodesPerPass; ++j) {
+            if (j < n_nodes) {
+              const int trow_txt = p.node_text[e_beg + j];
+              const float4* tw = reinterpret_cast<const float4*>(
+                  p.tauw + (size_t)trow_txt * p.Mp + col0);
+              const float4* t2 = reinterpret_cast<const float4*>(
+                  p.tau2 + (size_t)trow_txt * p.Mp + col0);
+              float n = num[j], d = den[j];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 a = __ldg(tw + q), s = __ldg(t2 + q);
+                n = fmaf(v[4 * q + 0], a.x, n); d = fmaf(v[4 * q + 0] * v[4 * q + 0], s.x, d);
+                n = fmaf(v[4 * q + 1], a.y, n); d = fmaf(v[4 * q + 1] * v[4 * q + 1], s.y, d);
+                n = fmaf(v[4 * q + 2], a.z, n); d = fmaf(v[4 * q + 2] * v[4 * q + 2], s.z, d);
+                n = fmaf(v[4 * q + 3], a.w, n); d = fmaf(v[4 * q + 3] * v[4 * q + 3], s.w, d);
+              }
+              num[j] = n; den[j] = d;
+            }
+          }
+        }
+        // release the accumulator buffer to the MMA warp
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      }
+      if (row_ok && wk.set == PS_FIND) {
+        const float b2 = __ldg(p.elt_b);
+#pragma unroll
+        for (int j = 0; j < kMaxProjNodesPerPass; ++j) {
+          if (j < n_nodes) {
+            const int slot = p.node_out[e_beg + j];
+            p.arena[(size_t)slot * p.HW + pix] = num[j] * rsqrtf(fmaxf(den[j], kEps)) + b2;
+          }
+        }
+      }
+    }
+  }
+
+  // teardown
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace n2nmn

@@ -1,0 +1,262 @@
+// Host-side layout compiler (see schedule.hpp). Plain C++; no CUDA calls.
+#include "schedule.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+namespace n2nmn {
+
+namespace {
+
+const int kArity[NUM_OPS] = {0, 0, 1, 1, 1, 2, 2, 1, 1, 2, 2, 2, 2, 1};
+const bool kIsAns[NUM_OPS] = {false, false, false, false, false, false, false,
+                              true, true, true, true, true, true, true};
+
+int text_set_of(int op) {
+  switch (op) {
+    case OP_FIND: case OP_FILTER: return TS_FIND;
+    case OP_FIND_SAME_PROPERTY: return TS_FSP;
+    case OP_TRANSFORM: return TS_TRANSFORM;
+    case OP_SAME_PROPERTY: return TS_SAMEPROP;
+    case OP_DESCRIBE: return TS_DESCRIBE;
+    default: return -1;
+  }
+}
+
+struct Pending {   // a parsed node before text rows are assigned
+  NodeRec rec;
+  int depth;
+  int tset;
+};
+
+uint64_t fnv1a(const void* data, size_t n, uint64_t h = 1469598103934665603ull) {
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+}  // namespace
+
+int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
+                     const int32_t* vocab_ops, int num_vocab, HostSchedule* out,
+                     const char** err) {
+  HostSchedule& S = *out;
+  S = HostSchedule();
+  S.N = N; S.T = T;
+  S.validity.assign(N, 0);
+  S.q_ptr.assign(N + 1, 0);
+  S.hash = fnv1a(tokens, sizeof(int32_t) * (size_t)T * N);
+  S.hash = fnv1a(vocab_ops, sizeof(int32_t) * num_vocab, S.hash);
+
+  std::vector<Pending> all;
+  all.reserve((size_t)N * 8);
+  std::vector<Pending> q;
+  std::vector<int> stack;   // indices into q
+  const int scene_bits = [] { float v = 3.0f; int b; std::memcpy(&b, &v, 4); return b; }();
+
+  for (int n = 0; n < N; ++n) {
+    q.clear(); stack.clear();
+    bool ok = false, has_eos = false;
+    for (int t = 0; t < T; ++t) {
+      const int tok = tokens[(size_t)t * N + n];
+      if (tok >= 0 && tok < num_vocab && vocab_ops[tok] < 0) { has_eos = true; break; }
+    }
+    if (has_eos) {
+      ok = true;
+      const int base = (int)all.size();
+      for (int t = 0; t < T && ok; ++t) {
+        const int tok = tokens[(size_t)t * N + n];
+        if (tok < 0 || tok >= num_vocab) { ok = false; break; }
+        const int op = vocab_ops[tok];
+        if (op < 0) break;                       // <eos>
+        if (op >= NUM_OPS) { ok = false; break; }
+        const int ar = kArity[op];
+        if ((int)stack.size() < ar) { ok = false; break; }   // not enough input
+        Pending nd;
+        nd.rec.op = op; nd.rec.t = t; nd.rec.b = n;
+        nd.rec.in0 = nd.rec.in1 = -1;
+        nd.rec.text = -1;
+        nd.rec.aux = (op == OP_SCENE) ? scene_bits : -1;
+        nd.depth = 1;
+        nd.tset = text_set_of(op);
+        // operands come off right-to-left: the last popped is input_0
+        for (int slot = ar - 1; slot >= 0; --slot) {
+          const int child = stack.back(); stack.pop_back();
+          if (kIsAns[q[child].rec.op]) { ok = false; break; }  // input must be attention
+          (slot == 0 ? nd.rec.in0 : nd.rec.in1) = base + child;
+          nd.depth = std::max(nd.depth, q[child].depth + 1);
+        }
+        if (!ok) break;
+        const int id = (int)q.size();
+        nd.rec.out = kIsAns[op] ? n : base + id;
+        q.push_back(nd);
+        stack.push_back(id);
+      }
+      if (ok && !(stack.size() == 1 && kIsAns[q[stack[0]].rec.op])) ok = false;
+    }
+    if (ok) {
+      S.validity[n] = 1;
+      ++S.num_valid;
+      all.insert(all.end(), q.begin(), q.end());
+    }
+    S.q_ptr[n + 1] = (int)all.size();
+  }
+
+  const int num_nodes = (int)all.size();
+  S.nodes.resize(num_nodes);
+  S.depth.resize(num_nodes);
+  for (int i = 0; i < num_nodes; ++i) { S.nodes[i] = all[i].rec; S.depth[i] = all[i].depth; }
+  (void)err;
+  return finalize_schedule(shp, N, out);
+}
+
+int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out) {
+  HostSchedule& S = *out;
+  const int N = num_images;                 // images (rows of the feature grid)
+  const int NQ = (int)S.q_ptr.size() - 1;   // questions (rows of the score matrix)
+  const int num_nodes = (int)S.nodes.size();
+  S.max_depth = 0;
+  // ---- text rows, grouped by weight set
+  int set_count[NUM_TEXT_SETS] = {0};
+  for (const NodeRec& r : S.nodes) if (text_set_of(r.op) >= 0) ++set_count[text_set_of(r.op)];
+  int set_start[NUM_TEXT_SETS + 1] = {0};
+  for (int s = 0; s < NUM_TEXT_SETS; ++s) set_start[s + 1] = set_start[s] + set_count[s];
+  const int num_text = set_start[NUM_TEXT_SETS];
+  S.text_t.assign(num_text, 0);
+  S.text_b.assign(num_text, 0);
+  int cursor[NUM_TEXT_SETS];
+  for (int s = 0; s < NUM_TEXT_SETS; ++s) cursor[s] = set_start[s];
+  for (int i = 0; i < num_nodes; ++i) {
+    NodeRec& r = S.nodes[i];
+    const int tset = text_set_of(r.op);
+    if (tset >= 0) {
+      const int row = cursor[tset]++;
+      r.text = row;
+      S.text_t[row] = r.t;
+      S.text_b[row] = r.b;
+    }
+    S.max_depth = std::max(S.max_depth, S.depth[i]);
+  }
+  for (int s = 0; s < NUM_TEXT_SETS; ++s)
+    for (int r = set_start[s]; r < set_start[s + 1]; r += kTextRowsPerCta) {
+      TextGroup g;
+      g.set = s; g.start = r; g.count = std::min(kTextRowsPerCta, set_start[s + 1] - r); g.pad = 0;
+      S.groups.push_back(g);
+    }
+
+  // ---- projection work: fused Find/Filter consumers per image, stored maps for FSP images
+  const int HW = shp.H * shp.W;
+  S.img_ptr.assign(N + 1, 0);
+  S.mslot.assign(N, -1);
+  for (const NodeRec& r : S.nodes) {
+    if (r.op == OP_FIND || r.op == OP_FILTER) ++S.img_ptr[r.b + 1];
+    if (r.op == OP_FIND_SAME_PROPERTY && S.mslot[r.b] < 0) S.mslot[r.b] = S.num_mslots++;
+  }
+  for (int n = 0; n < N; ++n) S.img_ptr[n + 1] += S.img_ptr[n];
+  S.num_find_nodes = S.img_ptr[N];
+  S.node_text.assign(S.num_find_nodes, 0);
+  S.node_out.assign(S.num_find_nodes, 0);
+  {
+    std::vector<int32_t> fill(S.img_ptr.begin(), S.img_ptr.end() - 1);
+    for (NodeRec& r : S.nodes) {
+      if (r.op == OP_FIND || r.op == OP_FILTER) {
+        const int e = fill[r.b]++;
+        S.node_text[e] = r.text;
+        S.node_out[e] = r.out;
+      }
+      if (r.op == OP_FIND_SAME_PROPERTY) r.aux = S.mslot[r.b];
+    }
+  }
+  const int total_rows = N * HW;
+  const int num_tiles = (total_rows + 127) / 128;
+  int u_find = 0, u_fsp = 0;
+  for (int n = 0; n < N; ++n) {
+    if (S.img_ptr[n + 1] > S.img_ptr[n]) ++u_find;
+    if (S.mslot[n] >= 0) ++u_fsp;
+  }
+  for (int set = 0; set < NUM_PROJ_SETS; ++set) {
+    for (int tile = 0; tile < num_tiles; ++tile) {
+      const int r0 = tile * 128, r1 = std::min(total_rows, r0 + 128) - 1;
+      int max_nodes = 0;
+      for (int b = r0 / HW; b <= r1 / HW; ++b) {
+        if (set == PS_FIND) max_nodes = std::max(max_nodes, S.img_ptr[b + 1] - S.img_ptr[b]);
+        else if (S.mslot[b] >= 0) max_nodes = 1;
+      }
+      const int passes = (max_nodes + kMaxProjNodesPerPass - 1) / kMaxProjNodesPerPass;
+      for (int pass = 0; pass < passes; ++pass) {
+        ProjWork w; w.row0 = r0; w.pass = pass; w.set = set; w.pad = 0;
+        S.work.push_back(w);
+      }
+    }
+  }
+
+  // ---- waves (Find is complete after the projection kernel, so it never enters a wave)
+  S.wave_ptr.assign(S.max_depth + 2, 0);
+  for (int i = 0; i < num_nodes; ++i)
+    if (S.nodes[i].op != OP_FIND) ++S.wave_ptr[S.depth[i] + 1];
+  for (int d = 0; d <= S.max_depth; ++d) S.wave_ptr[d + 1] += S.wave_ptr[d];
+  S.wave_nodes.assign(S.wave_ptr[S.max_depth + 1], 0);
+  {
+    std::vector<int32_t> fill(S.wave_ptr.begin(), S.wave_ptr.end() - 1);
+    for (int i = 0; i < num_nodes; ++i)
+      if (S.nodes[i].op != OP_FIND) S.wave_nodes[fill[S.depth[i]]++] = i;
+  }
+
+  // ---- algorithmic bytes / flops, fp32
+  const int64_t D = shp.Dk, M = shp.M, C = shp.C, Dt = shp.Dt, hw = HW;
+  const int64_t tile_b = hw * D * 4, att_b = hw * 4, txt_b = Dt * 4;
+  const int64_t contraction = 2 * hw * D * M, tail = 6 * hw * M, txt_f = 2 * Dt * M;
+  const int64_t pool_f = 2 * hw * D + 2 * D * M;
+  int64_t node_bytes = 0, node_flops = 0;      // what the node kernels move / compute
+  int questions_reading_feat = 0;
+  for (int n = 0; n < NQ; ++n) {
+    bool reads = false;
+    for (int i = S.q_ptr[n]; i < S.q_ptr[n + 1]; ++i) {
+      const int op = S.nodes[i].op;
+      int64_t rb = 0, wb = 0, fl = 0, kb = 0, kf = 0;   // per-node figure / node-kernel share
+      switch (op) {
+        case OP_SCENE: wb = att_b; kb = att_b; break;
+        case OP_FIND: rb = tile_b + txt_b; wb = att_b; fl = contraction + txt_f + tail; break;
+        case OP_FILTER: rb = tile_b + txt_b + att_b; wb = att_b; fl = contraction + txt_f + tail + hw;
+          kb = 3 * att_b; kf = hw; break;
+        case OP_FIND_SAME_PROPERTY: rb = tile_b + txt_b + att_b; wb = att_b;
+          fl = contraction + txt_f + tail + pool_f; kb = 2 * att_b + hw * M * 4; kf = tail + pool_f;
+          reads = true; break;
+        case OP_TRANSFORM: {
+          const int64_t stencil = 2 * hw * shp.ksize * shp.ksize * M;
+          rb = att_b + txt_b; wb = att_b; fl = stencil + txt_f + tail;
+          kb = 2 * att_b; kf = stencil + tail; break;
+        }
+        case OP_AND: case OP_OR: rb = 2 * att_b; wb = att_b; fl = hw; kb = 3 * att_b; kf = hw; break;
+        case OP_EXIST: rb = att_b; wb = C * 4; fl = 6 * C + 3 * hw; kb = rb + wb; kf = fl; break;
+        case OP_COUNT: rb = att_b; wb = C * 4; fl = 2 * (hw + 2) * C; kb = rb + wb; kf = fl; break;
+        case OP_EQUAL_NUM: case OP_MORE_NUM: case OP_LESS_NUM:
+          rb = 2 * att_b; wb = C * 4; fl = 4 * (hw + 2) * C; kb = rb + wb; kf = fl; break;
+        case OP_SAME_PROPERTY: rb = tile_b + txt_b + 2 * att_b; wb = C * 4;
+          fl = 2 * pool_f + txt_f + 2 * M * C; kb = 2 * att_b + wb; kf = 2 * pool_f + 2 * M * C;
+          reads = true; break;
+        case OP_DESCRIBE: rb = tile_b + txt_b + att_b; wb = C * 4;
+          fl = pool_f + txt_f + 2 * M * C; kb = att_b + wb; kf = pool_f + 2 * M * C;
+          reads = true; break;
+      }
+      S.per_node_bytes += rb + wb;
+      S.per_node_flops += fl;
+      node_bytes += kb;
+      node_flops += kf;
+    }
+    if (reads) ++questions_reading_feat;
+  }
+  int sets_used = 0;
+  for (int s = 0; s < NUM_TEXT_SETS; ++s) sets_used += set_count[s] > 0;
+  S.kbytes[0] = (int64_t)num_text * (txt_b + M * 4) + (int64_t)sets_used * Dt * M * 4;
+  S.kflops[0] = (int64_t)num_text * txt_f;
+  S.kbytes[1] = (int64_t)u_find * tile_b + (int64_t)S.num_find_nodes * (M * 4 + att_b) +
+                (u_find ? D * M * 4 : 0) +
+                (int64_t)u_fsp * (tile_b + hw * M * 4) + (u_fsp ? D * M * 4 : 0);
+  S.kflops[1] = (int64_t)(u_find + u_fsp) * contraction + (int64_t)S.num_find_nodes * tail;
+  S.kbytes[2] = node_bytes + (int64_t)questions_reading_feat * tile_b;
+  S.kflops[2] = node_flops;
+  return 0;
+}
+
+}  // namespace n2nmn

@@ -1,0 +1,52 @@
+// Host-side layout compiler: Reverse-Polish layout tokens [T,N] -> launch tables.
+//
+// Replaces, for the throughput path, the Python `Assembler.assemble`
+// (models_clevr/nmn3_assembler.py:153-222: RPN stack decode + validity rules) and TF Fold's
+// `compiler.build_feed_dict` (models_clevr/nmn3_model.py:146-159 + loom weaver): no Python dicts,
+// no per-node objects — flat int tables that go to the device in ONE copy.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "common.cuh"
+
+namespace n2nmn {
+
+struct SchedShape {
+  int family, H, W, Dk, Dt, M, Mp, C, ksize;
+  int max_T;
+};
+
+struct HostSchedule {
+  int N = 0, T = 0, num_valid = 0, max_depth = 0;
+  std::vector<uint8_t> validity;      // [N]
+  std::vector<NodeRec> nodes;         // (question, token) order; node id = index = arena slot
+  std::vector<int32_t> depth;         // per node
+  std::vector<int32_t> q_ptr;         // [N+1]
+  std::vector<int32_t> text_t, text_b;
+  std::vector<TextGroup> groups;
+  std::vector<ProjWork> work;
+  std::vector<int32_t> img_ptr, node_text, node_out, mslot;
+  int num_mslots = 0;
+  int num_find_nodes = 0;
+  std::vector<int32_t> wave_ptr;      // [max_depth+2], wave d = [wave_ptr[d], wave_ptr[d+1])
+  std::vector<int32_t> wave_nodes;
+  // §8(d) algorithmic traffic / work, per kernel: 0 text, 1 projection, 2 node kernels
+  int64_t kbytes[3] = {0, 0, 0};
+  int64_t kflops[3] = {0, 0, 0};
+  int64_t per_node_bytes = 0;         // Σ over nodes of the App. D per-node figure
+  int64_t per_node_flops = 0;
+  uint64_t hash = 0;
+};
+
+// Returns 0 or a negative n2nmn_status; `err` receives a message on failure.
+int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
+                     const int32_t* vocab_ops, int num_vocab, HostSchedule* out,
+                     const char** err);
+
+// Builds every derived table (text rows, projection work, waves, traffic accounting) from
+// S.nodes / S.depth / S.q_ptr. `num_images` bounds NodeRec::b. Used by compile_schedule and by the
+// per-module entry point, which fabricates one single-node "question" per call row.
+int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out);
+
+}  // namespace n2nmn

@@ -1,0 +1,204 @@
+"""Layout executor: Part 2 ("layout_execution") of the reference's NMN3Model
+(models_clevr/nmn3_model.py:49-159, models_shapes/nmn3_model.py:53-101,
+models_vqa/nmn3_model.py:60-104) without TF Fold.
+
+Reference call sequence (exp_clevr/eval_clevr.py:125-132)          here
+    expr_list, valid = assembler.assemble(tokens)                   same Assembler
+    feed = nmn3_model.compiler.build_feed_dict(expr_list)           model.compiler.build_feed_dict
+    scores = sess.partial_run(h, nmn3_model.scores, feed)           model.run(feed)  /  model.scores
+
+The fast path skips the Python dictionaries altogether: ``model.forward_tokens(tokens)`` hands
+the ``[T, N]`` token matrix to the C++ layout compiler (n2nmn_compile_schedule) and launches the
+compiled batch (n2nmn_run_schedule). Rows of invalid layouts are zeros
+(models_clevr/nmn3_model.py:144-155).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import config as cfgmod
+from .assembler import INVALID_EXPR, Assembler
+from .modules import MODULES_BY_FAMILY
+
+
+class CompiledBatch:
+    """A compiled layout batch (owns an n2nmn_sched). Plays the role of Fold's feed dict."""
+
+    def __init__(self, lib, handle, validity=None):
+        self._lib = lib
+        self._h = handle
+        self.validity = validity
+        info = _lib.SchedInfo()
+        _lib.check(lib.n2nmn_sched_get_info(handle, C.byref(info)))
+        self.info = {f[0]: getattr(info, f[0]) for f in info._fields_
+                     if not f[0].startswith('kernel_')}
+        self.info['kernel_bytes'] = list(info.kernel_bytes)
+        self.info['kernel_flops'] = list(info.kernel_flops)
+
+    def nodes(self):
+        """int32 [num_nodes, 6]: op, time_idx, batch_idx, depth, in0, in1 (arena slot = row)."""
+        n = self.info['num_nodes']
+        out = np.zeros((max(n, 1), 6), np.int32)
+        _lib.check(self._lib.n2nmn_sched_get_nodes(
+            self._h, out.ctypes.data_as(C.POINTER(C.c_int32)), max(n, 1)))
+        return out[:n]
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            self._lib.n2nmn_sched_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _Compiler:
+    """Stands in for ``td.Compiler`` (models_clevr/nmn3_model.py:158)."""
+
+    def __init__(self, model):
+        self._m = model
+
+    def build_feed_dict(self, expr_list):
+        return self._m.compile_exprs(expr_list)
+
+
+class LayoutExecutor:
+    """The module network + executor for one family."""
+
+    def __init__(self, family, image_feat_grid, word_vecs, num_choices, assembler, weights=None,
+                 **ctx_kwargs):
+        self.family = family
+        self.assembler = assembler
+        cls = MODULES_BY_FAMILY[family]
+        if family == 'vqa':
+            self.modules = cls(image_feat_grid, word_vecs, None, num_choices, weights=weights,
+                               **ctx_kwargs)
+        else:
+            self.modules = cls(image_feat_grid, word_vecs, num_choices, weights=weights,
+                               **ctx_kwargs)
+        self.num_choices = self.modules.num_choices
+        self._lib = self.modules._lib
+        fam = cfgmod.FAMILIES[family]
+        self.vocab_ops = np.array([fam.token_ops.get(n, -1) for n in assembler.module_names],
+                                  np.int32)
+        self.compiler = _Compiler(self)
+        self.scores = None   # last result, like fetching `nmn3_model.scores`
+        self._cache = {}
+
+    # -- compile ----------------------------------------------------------------------------
+    def compile_tokens(self, layout_tokens, cache=False):
+        """[T, N] int tokens -> CompiledBatch (C++ layout compiler; no Python dicts)."""
+        tok = np.ascontiguousarray(np.asarray(layout_tokens), dtype=np.int32)
+        key = tok.tobytes() if cache else None
+        if cache and key in self._cache:
+            return self._cache[key]
+        T, N = tok.shape
+        validity = np.zeros(N, np.uint8)
+        h = C.c_void_p()
+        _lib.check(self._lib.n2nmn_compile_schedule(
+            self.modules._h, tok.ctypes.data_as(C.POINTER(C.c_int32)), T, N,
+            self.vocab_ops.ctypes.data_as(C.POINTER(C.c_int32)), len(self.vocab_ops),
+            validity.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(h)))
+        cb = CompiledBatch(self._lib, h, validity.astype(bool))
+        if cache:
+            self._cache[key] = cb
+        return cb
+
+    def compile_exprs(self, expr_list):
+        """Assembler expression dicts -> CompiledBatch (compiler.build_feed_dict)."""
+        fam = cfgmod.FAMILIES[self.family]
+        op, t, b, in0, in1, q_ptr = [], [], [], [], [], [0]
+
+        def walk(e):
+            kids = [walk(e[k]) for k in ('input_0', 'input_1') if k in e]
+            op.append(fam.token_ops[e['module']])
+            t.append(int(e['time_idx']))
+            b.append(int(e['batch_idx']))
+            in0.append(kids[0] if len(kids) > 0 else -1)
+            in1.append(kids[1] if len(kids) > 1 else -1)
+            return len(op) - 1
+
+        for e in expr_list:
+            if e['module'] != INVALID_EXPR:
+                walk(e)
+            q_ptr.append(len(op))
+        arrs = [np.asarray(a, np.int32) for a in (op, t, b, in0, in1, q_ptr)]
+        ptr = [a.ctypes.data_as(C.POINTER(C.c_int32)) for a in arrs]
+        h = C.c_void_p()
+        _lib.check(self._lib.n2nmn_compile_nodes(self.modules._h, ptr[0], ptr[1], ptr[2], ptr[3],
+                                                 ptr[4], len(op), ptr[5], len(expr_list),
+                                                 C.byref(h)))
+        validity = np.array([e['module'] != INVALID_EXPR for e in expr_list], bool)
+        return CompiledBatch(self._lib, h, validity)
+
+    # -- run ----------------------------------------------------------------------------------
+    def run(self, compiled, return_att=False, out=None):
+        """Evaluate a compiled batch against the bound inputs -> scores [N, C] (CUDA tensor).
+        With return_att=True also returns the attention arena [num_nodes, H, W]."""
+        m = self.modules
+        nq = compiled.info['num_questions']
+        scores = out if out is not None else torch.empty((nq, self.num_choices),
+                                                         dtype=torch.float32, device=m.device)
+        arena = None
+        if return_att:
+            arena = torch.zeros((max(compiled.info['num_nodes'], 1), m.H, m.W),
+                                dtype=torch.float32, device=m.device)
+        _lib.check(self._lib.n2nmn_run_schedule(
+            m._h, compiled._h, C.c_void_p(scores.data_ptr()),
+            C.c_void_p(arena.data_ptr()) if arena is not None else None, m._stream()))
+        self.scores = scores
+        return (scores, arena) if return_att else scores
+
+    def forward_tokens(self, layout_tokens, cache=False):
+        """tokens [T,N] -> (scores [N,C] CUDA tensor, validity bool[N])."""
+        cb = self.compile_tokens(layout_tokens, cache=cache)
+        return self.run(cb), cb.validity
+
+    def forward(self, expr_list):
+        return self.run(self.compile_exprs(expr_list))
+
+    def bind(self, image_feat_grid, word_vecs):
+        self.modules.bind(image_feat_grid, word_vecs)
+
+    # -- e2e with host buffers ------------------------------------------------------------------
+    def forward_host(self, feat_host, word_vecs_host, layout_tokens, scores_host=None):
+        """Host numpy/pinned-tensor inputs -> host scores; H2D/D2H inside (n2nmn_forward_host)."""
+        m = self.modules
+        tok = np.ascontiguousarray(np.asarray(layout_tokens), dtype=np.int32)
+        T, N = tok.shape
+        f = feat_host if isinstance(feat_host, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(feat_host, np.float32))
+        w = word_vecs_host if isinstance(word_vecs_host, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(word_vecs_host, np.float32))
+        assert f.dtype == torch.float32 and w.dtype == torch.float32
+        assert f.is_contiguous() and w.is_contiguous() and not f.is_cuda and not w.is_cuda
+        if scores_host is None:
+            scores_host = torch.empty((N, self.num_choices), dtype=torch.float32).pin_memory()
+        validity = np.zeros(N, np.uint8)
+        _lib.check(self._lib.n2nmn_forward_host(
+            m._h, C.c_void_p(f.data_ptr()), C.c_void_p(w.data_ptr()),
+            tok.ctypes.data_as(C.POINTER(C.c_int32)), T, N,
+            self.vocab_ops.ctypes.data_as(C.POINTER(C.c_int32)), len(self.vocab_ops),
+            C.c_void_p(scores_host.data_ptr()), validity.ctypes.data_as(C.POINTER(C.c_uint8)),
+            m._stream()))
+        return scores_host, validity.astype(bool)
+
+    # -- profiling ------------------------------------------------------------------------------
+    def set_profiling(self, on):
+        _lib.check(self._lib.n2nmn_set_profiling(self.modules._h, int(bool(on))))
+
+    def launch_times(self):
+        names = (C.c_char_p * 64)()
+        us = (C.c_float * 64)()
+        n = _lib.check(self._lib.n2nmn_get_launch_times(self.modules._h, names, us, 64))
+        return [(names[i].decode(), float(us[i])) for i in range(n)]
+
+    def launch_count(self):
+        return int(self._lib.n2nmn_launch_count(self.modules._h))

@@ -1,0 +1,170 @@
+"""GPU parity: the CUDA path (through the C ABI) vs the goldens made from the reference's module
+code and vs the numpy oracle, for all three families, both executors and both projection
+kernels (tcgen05 TF32 default, fp32 CUDA-core verification path).
+
+Tolerance: 1e-3 absolute on attention maps and answer logits (north_star), tightened to 2e-4
+for the fp32 CUDA-core projection."""
+import numpy as np
+import pytest
+import torch
+
+from n2nmn_b200 import _lib, synth
+from n2nmn_b200.assembler import Assembler
+from tests.helpers import case_inputs, load_golden, node_inputs
+
+pytestmark = pytest.mark.gpu
+FAMILIES = ['clevr', 'shapes', 'vqa']
+TOL = {0: 1e-3, _lib.FLAG_PROJ_FP32_SIMT: 2e-4}
+
+
+def make_executor(family, feat, word_vecs, C, W, flags=0, **kw):
+    from n2nmn_b200.executor import LayoutExecutor
+    asm = Assembler(synth.vocab_file(family))
+    return LayoutExecutor(family, torch.from_numpy(feat).cuda(), torch.from_numpy(word_vecs).cuda(),
+                          C, asm, weights=W, flags=flags, **kw)
+
+
+@pytest.mark.parametrize('flags', [_lib.FLAG_PROJ_FP32_SIMT, 0])
+@pytest.mark.parametrize('family', FAMILIES)
+def test_modules_match_reference_goldens(family, flags):
+    z, meta = load_golden(family)
+    feat, word_vecs, W = case_inputs(meta)
+    ex = make_executor(family, feat, word_vecs, meta['C'], W, flags=flags, max_T=meta['T'])
+    m = ex.modules
+    worst = {}
+    for k, (name, arity) in enumerate(meta['module_calls']):
+        t, b, a0, a1 = node_inputs(meta, 5, meta['node_seed_base'] + k)
+        out = getattr(m, name)(*(a0, a1)[:arity], t, b)
+        torch.cuda.synchronize()
+        ref = z['mod_' + name]
+        assert tuple(out.shape) == ref.shape, name
+        worst[name] = float(np.max(np.abs(out.cpu().numpy() - ref)))
+    print(family, 'flags', flags, 'max abs err per module:', worst)
+    bad = {k: v for k, v in worst.items() if not v <= TOL[flags]}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize('flags', [_lib.FLAG_PROJ_FP32_SIMT, 0, _lib.FLAG_WAVE_EXECUTOR,
+                                   _lib.FLAG_WAVE_EXECUTOR | _lib.FLAG_PROJ_FP32_SIMT])
+@pytest.mark.parametrize('family', FAMILIES)
+def test_executor_matches_reference_goldens(family, flags):
+    z, meta = load_golden(family)
+    feat, word_vecs, W = case_inputs(meta)
+    ex = make_executor(family, feat, word_vecs, meta['C'], W, flags=flags, max_T=meta['T'])
+    tol = TOL[flags & _lib.FLAG_PROJ_FP32_SIMT]
+    cb = ex.compile_tokens(z['exec_tokens'])
+    assert cb.validity.tolist() == [bool(v) for v in z['exec_validity']]
+    scores, arena = ex.run(cb, return_att=True)
+    torch.cuda.synchronize()
+    scores, arena = scores.cpu().numpy(), arena.cpu().numpy()
+    err_s = float(np.max(np.abs(scores - z['exec_scores'])))
+    nodes = cb.nodes()
+    err_a = 0.0
+    n_att = 0
+    for i, (op, t, b, depth, in0, in1) in enumerate(nodes):
+        key = 'att_b%d_t%d' % (b, t)
+        if key in z.files:
+            err_a = max(err_a, float(np.max(np.abs(arena[i] - z[key]))))
+            n_att += 1
+    print(family, 'flags', flags, 'scores err', err_s, 'att err', err_a, 'att maps', n_att)
+    assert n_att == sum(1 for k in z.files if k.startswith('att_b'))
+    assert err_s <= tol and err_a <= tol
+    for i, v in enumerate(cb.validity):
+        if not v:
+            assert not scores[i].any()
+    # the dict route (compiler.build_feed_dict) gives the same numbers as the token route
+    exprs, _ = ex.assembler.assemble(z['exec_tokens'])
+    s2 = ex.run(ex.compiler.build_feed_dict(exprs)).cpu().numpy()
+    np.testing.assert_array_equal(s2, scores)
+
+
+def _oracle_scores(family, feat, word_vecs, C, W, tokens):
+    from oracle.nmn_oracle import OracleModules, run_depth_batched
+    asm = Assembler(synth.vocab_file(family))
+    exprs, valid = asm.assemble(tokens)
+    m = OracleModules(feat, word_vecs, C, W, family=family)
+    s, att = run_depth_batched(m, exprs, return_att=True)
+    return s, att, valid
+
+
+@pytest.mark.parametrize('flags', [0, _lib.FLAG_WAVE_EXECUTOR])
+def test_clevr_batch64_vs_oracle(flags):
+    """BASELINE config 2 shape: B=64, 10x15x512, T=20, expert mix + random valid layouts."""
+    from n2nmn_b200 import weights as wts
+    N, H, Wd, D, T, C = 64, 10, 15, 512, 20, 28
+    feat, word_vecs = synth.make_inputs(N, H, Wd, D, T, seed=1234)
+    W = wts.init_weights('clevr', H, Wd, D, C, seed=0, bias_std=0.1)
+    ex = make_executor('clevr', feat, word_vecs, C, W, flags=flags)
+    asm = ex.assembler
+    for name, tokens in [('expert', synth.expert_mix_tokens(asm, N, T)),
+                         ('random', synth.random_valid_tokens(asm, N, T, seed=7)),
+                         ('deep', synth.random_valid_tokens(asm, N, T, seed=9, ans_weight=0.15,
+                                                            min_depth=3, max_depth=12))]:
+        cb = ex.compile_tokens(tokens)
+        scores, arena = ex.run(cb, return_att=True)
+        torch.cuda.synchronize()
+        ref_s, ref_att, valid = _oracle_scores('clevr', feat, word_vecs, C, W, tokens)
+        assert cb.validity.tolist() == valid.tolist()
+        err_s = float(np.max(np.abs(scores.cpu().numpy() - ref_s)))
+        arena = arena.cpu().numpy()
+        err_a = 0.0
+        for i, (op, t, b, depth, in0, in1) in enumerate(cb.nodes()):
+            if (b, t) in ref_att:
+                err_a = max(err_a, float(np.max(np.abs(arena[i] - ref_att[(b, t)]))))
+        print(name, 'flags', flags, 'nodes', cb.info['num_nodes'], 'depth', cb.info['max_depth'],
+              'scores err', err_s, 'att err', err_a)
+        assert err_s <= 1e-3 and err_a <= 1e-3
+
+
+def test_many_find_nodes_per_image_and_ragged_inputs():
+    """> 8 Find/Filter nodes on one image (second projection pass), invalid rows interleaved,
+    a batch that is not a multiple of anything, T at the context maximum."""
+    from n2nmn_b200 import weights as wts
+    N, H, Wd, D, T, C = 5, 10, 15, 512, 24, 28
+    feat, word_vecs = synth.make_inputs(N, H, Wd, D, T, seed=77)
+    W = wts.init_weights('clevr', H, Wd, D, C, seed=3, bias_std=0.1)
+    ex = make_executor('clevr', feat, word_vecs, C, W)
+    asm = ex.assembler
+    long_chain = ['_Find'] + ['_Filter'] * 10 + ['_Count']            # 11 find-type nodes
+    many_and = ['_Find', '_Find', '_And'] + ['_Find', '_And'] * 8 + ['_Exist']   # 10 finds
+    layouts = [long_chain, ['_Find', '_Transform'], many_and, ['_Scene', '_Exist'],
+               ['_And', '_Count']]
+    tokens = synth.tokens_from_layouts(asm, layouts, T)
+    cb = ex.compile_tokens(tokens)
+    assert cb.validity.tolist() == [True, False, True, True, False]
+    scores = ex.run(cb).cpu().numpy()
+    ref_s, _, _ = _oracle_scores('clevr', feat, word_vecs, C, W, tokens)
+    assert not scores[1].any() and not scores[4].any()
+    assert float(np.max(np.abs(scores - ref_s))) <= 1e-3
+
+
+def test_zero_size_module_call_and_errors():
+    """n == 0 (TF Fold's empty batches) is a no-op; bad arguments fail loudly, never silently."""
+    from n2nmn_b200 import weights as wts
+    N, H, Wd, D, T, C = 2, 10, 15, 512, 4, 28
+    feat, word_vecs = synth.make_inputs(N, H, Wd, D, T, seed=5)
+    ex = make_executor('clevr', feat, word_vecs, C,
+                       wts.init_weights('clevr', H, Wd, D, C, seed=1))
+    m = ex.modules
+    out = m.FindModule(np.zeros(0, np.int32), np.zeros(0, np.int32))
+    assert tuple(out.shape) == (0, H, Wd, 1)
+    with pytest.raises(_lib.N2NMNError):
+        m.FindModule(np.array([0], np.int32), np.array([N], np.int32))     # batch_idx out of range
+    with pytest.raises(ValueError):
+        m.FindModule(np.array([0], np.int32), np.array([0], np.int32), map_dim=123)
+    with pytest.raises(_lib.N2NMNError):
+        ex.compile_tokens(np.zeros((T + 1, N), np.int32))                   # T above capacity
+
+
+def test_host_e2e_entry_matches_device_path():
+    from n2nmn_b200 import weights as wts
+    N, H, Wd, D, T, C = 16, 10, 15, 512, 10, 28
+    feat, word_vecs = synth.make_inputs(N, H, Wd, D, T, seed=21)
+    W = wts.init_weights('clevr', H, Wd, D, C, seed=2, bias_std=0.1)
+    ex = make_executor('clevr', feat, word_vecs, C, W)
+    tokens = synth.expert_mix_tokens(ex.assembler, N, T)
+    dev_scores, valid = ex.forward_tokens(tokens)
+    host_scores, valid2 = ex.forward_host(torch.from_numpy(feat).pin_memory(),
+                                          torch.from_numpy(word_vecs).pin_memory(), tokens)
+    assert valid.tolist() == valid2.tolist()
+    np.testing.assert_array_equal(host_scores.numpy(), dev_scores.cpu().numpy())
