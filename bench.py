@@ -218,11 +218,10 @@ def main():
     scores = torch.empty((B, C), dtype=torch.float32, device=dev)
 
     def step(i):
+        # public API, one call per batch: bind the batch's device-resident features, compile its
+        # layouts (C++), upload the tables, launch the kernels; asynchronous
         k = i % P
-        ex.bind(feats[k], wvs[k])
-        cb = ex.compile_tokens(toks[k])
-        ex.run(cb, out=scores)
-        return cb
+        ex.forward_device(feats[k], wvs[k], toks[k], out=scores)
 
     def barrier():
         if world > 1:
@@ -240,7 +239,7 @@ def main():
     barrier()
     e0.record()
     for i in range(args.steps):
-        cb = step(args.warmup + i)
+        step(args.warmup + i)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -284,11 +283,12 @@ def main():
         ex.set_profiling(True)
         acc, bytes_acc, flops_acc, n = {}, 0, 0, 0
         for i in range(min(args.steps, 50)):
-            cb = step(i)
+            step(i)
             for name, us in ex.launch_times():
                 acc.setdefault(name, []).append(us)
-            bytes_acc += cb.info['kernel_bytes'][1]
-            flops_acc += cb.info['kernel_flops'][1]
+            info = ex.last_step_info()
+            bytes_acc += info['kernel_bytes'][1]
+            flops_acc += info['kernel_flops'][1]
             n += 1
         ex.set_profiling(False)
         kernel_us = {k: float(np.mean(v)) for k, v in acc.items()}
@@ -322,7 +322,7 @@ def main():
                          'fp32 depth-batched restatement, Assembler.assemble included)' % (nb, B, el)}
 
     if rank == 0:
-        info = cb.info
+        info = ex.last_step_info()
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_max / args.steps, 'higher_is_better': True,

@@ -177,6 +177,17 @@ int n2nmn_sched_get_nodes(const n2nmn_sched* sched, int32_t* out6, int capacity_
 int n2nmn_run_schedule(n2nmn_ctx* ctx, n2nmn_sched* sched, float* scores_dev,
                        float* att_arena_dev, void* stream);
 
+/* bind + compile + run in one call, for the per-batch loop of exp_clevr/eval_clevr.py:103-135 with
+ * device-resident features (the reference keeps image_feat / word_vecs on the device between its
+ * two partial_run calls). The compiled tables live in the context and are overwritten by the next
+ * call. Asynchronous on `stream`; host cost is one layout compile + four enqueues. */
+int n2nmn_forward_tokens(n2nmn_ctx* ctx, const float* feat_dev, const float* word_vecs_dev,
+                         const int32_t* tokens_host, int T, int N, const int32_t* vocab_ops,
+                         int num_vocab, float* scores_dev, uint8_t* validity_out, void* stream);
+
+/* Statistics of the batch compiled by the last n2nmn_forward_tokens / n2nmn_forward_host. */
+int n2nmn_last_step_info(const n2nmn_ctx* ctx, n2nmn_sched_info* info);
+
 /* End-to-end convenience with HOST buffers (what exp_clevr/eval_clevr.py:103-135 does per batch):
  * H2D of features + word vectors, compile, run, D2H of scores; synchronises `stream` before
  * returning. Host buffers should be pinned for full PCIe rate. */

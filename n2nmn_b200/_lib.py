@@ -54,6 +54,8 @@ SIGNATURES = {
     'n2nmn_sched_get_info': (C.c_int, [_P, C.POINTER(SchedInfo)]),
     'n2nmn_sched_get_nodes': (C.c_int, [_P, _I32P, C.c_int]),
     'n2nmn_run_schedule': (C.c_int, [_P, _P, _P, _P, _P]),
+    'n2nmn_forward_tokens': (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P]),
+    'n2nmn_last_step_info': (C.c_int, [_P, C.POINTER(SchedInfo)]),
     'n2nmn_forward_host': (C.c_int, [_P, _P, _P, _I32P, C.c_int, C.c_int, _I32P, C.c_int, _P,
                                      C.POINTER(C.c_uint8), _P]),
     'n2nmn_set_profiling': (C.c_int, [_P, C.c_int]),

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -39,7 +40,7 @@ int fail(int code, const std::string& msg) {
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-enum VarKind { VK_PLAIN = 0, VK_PROJ_W, VK_PROJ_B };
+enum VarKind { VK_PLAIN = 0, VK_PROJ_W, VK_PROJ_B, VK_PITCHED };
 
 struct Variable {
   std::string name;
@@ -107,7 +108,9 @@ struct n2nmn_ctx {
   bool tmap_b_ready[NUM_PROJ_SETS] = {false, false};
   EncodeTiledFn encode = nullptr;
   int node_smem_bytes = 0;
+  int tree_cluster = 0;        // 0 = choose from the batch size; else forced (N2NMN_TREE_CLUSTER)
   n2nmn_sched module_sched;    // scratch schedule of n2nmn_module_fwd
+  n2nmn_sched step_sched;      // scratch schedule of n2nmn_forward_tokens
   // e2e staging
   float* e2e_feat = nullptr;
   float* e2e_wv = nullptr;
@@ -131,13 +134,17 @@ void add_var(n2nmn_ctx* c, const std::string& name, std::vector<int64_t> shape, 
   v.count = 1;
   for (int64_t d : shape) v.count *= (size_t)d;
   v.offset = c->wbuf_floats;
-  c->wbuf_floats += (v.count + 3) & ~(size_t)3;
+  const size_t stored = (kind == VK_PITCHED) ? (size_t)shape[0] * c->Mp : v.count;
+  c->wbuf_floats += (stored + 3) & ~(size_t)3;
   c->vars.push_back(v);
 }
 
+// proj_set >= 0: conv_image (repacked for the tensor cores); proj_set == -2: a [rows][M] matrix
+// stored with row pitch Mp (fc_text / fc_att) for aligned float4 loads.
 void add_layer(n2nmn_ctx* c, const std::string& scope, std::vector<int64_t> wshape,
                const float** wslot, const float** bslot, int proj_set = -1) {
-  add_var(c, scope + "/weights", wshape, proj_set >= 0 ? VK_PROJ_W : VK_PLAIN, proj_set, wslot);
+  add_var(c, scope + "/weights", wshape,
+          proj_set >= 0 ? VK_PROJ_W : (proj_set == -2 ? VK_PITCHED : VK_PLAIN), proj_set, wslot);
   add_var(c, scope + "/biases", {wshape.back()}, proj_set >= 0 ? VK_PROJ_B : VK_PLAIN, proj_set,
           bslot);
 }
@@ -149,17 +156,17 @@ void build_variables(n2nmn_ctx* c) {
   const int64_t D = c->Dk, M = g.map_dim, Dt = g.text_dim, C = g.num_choices, k = g.kernel_size;
   const int64_t HW = c->HW;
   add_layer(c, "FindModule/conv_image", {D, M}, &md.proj_w[PS_FIND], nullptr, PS_FIND);
-  add_layer(c, "FindModule/fc_text", {Dt, M}, &md.txt_w[TS_FIND], &md.txt_b[TS_FIND]);
+  add_layer(c, "FindModule/fc_text", {Dt, M}, &md.txt_w[TS_FIND], &md.txt_b[TS_FIND], -2);
   add_layer(c, "FindModule/conv_eltwise", {M, 1}, &md.elt_w[ES_FIND], &md.elt_b[ES_FIND]);
   if (g.family == N2NMN_VQA) {
     add_layer(c, "TransformModule/conv_image", {D, M}, &md.proj_w[PS_FSP], nullptr, PS_FSP);
-    add_layer(c, "TransformModule/fc_text", {Dt, M}, &md.txt_w[TS_FSP], &md.txt_b[TS_FSP]);
-    add_layer(c, "TransformModule/fc_att", {D, M}, &md.att_w[AS_FSP], &md.att_b[AS_FSP]);
+    add_layer(c, "TransformModule/fc_text", {Dt, M}, &md.txt_w[TS_FSP], &md.txt_b[TS_FSP], -2);
+    add_layer(c, "TransformModule/fc_att", {D, M}, &md.att_w[AS_FSP], &md.att_b[AS_FSP], -2);
     add_layer(c, "TransformModule/conv_eltwise", {M, 1}, &md.elt_w[ES_FSP], &md.elt_b[ES_FSP]);
   } else {
     add_layer(c, "TransformModule/conv_maps", {k, k, 1, M}, &md.conv_k, &md.conv_b);
     add_layer(c, "TransformModule/text_fc", {Dt, M}, &md.txt_w[TS_TRANSFORM],
-              &md.txt_b[TS_TRANSFORM]);
+              &md.txt_b[TS_TRANSFORM], -2);
     add_layer(c, "TransformModule/conv_eltwise", {M, 1}, &md.elt_w[ES_TRANSFORM],
               &md.elt_b[ES_TRANSFORM]);
   }
@@ -169,8 +176,8 @@ void build_variables(n2nmn_ctx* c) {
   }
   if (g.family == N2NMN_CLEVR) {
     add_layer(c, "FindSamePropertyModule/conv_image", {D, M}, &md.proj_w[PS_FSP], nullptr, PS_FSP);
-    add_layer(c, "FindSamePropertyModule/fc_text", {Dt, M}, &md.txt_w[TS_FSP], &md.txt_b[TS_FSP]);
-    add_layer(c, "FindSamePropertyModule/fc_att", {D, M}, &md.att_w[AS_FSP], &md.att_b[AS_FSP]);
+    add_layer(c, "FindSamePropertyModule/fc_text", {Dt, M}, &md.txt_w[TS_FSP], &md.txt_b[TS_FSP], -2);
+    add_layer(c, "FindSamePropertyModule/fc_att", {D, M}, &md.att_w[AS_FSP], &md.att_b[AS_FSP], -2);
     add_layer(c, "FindSamePropertyModule/conv_eltwise", {M, 1}, &md.elt_w[ES_FSP],
               &md.elt_b[ES_FSP]);
     add_layer(c, "ExistModule/fc_scores", {3, C}, &md.sc_w[SS_EXIST], &md.sc_b[SS_EXIST]);
@@ -182,16 +189,16 @@ void build_variables(n2nmn_ctx* c) {
     add_layer(c, "LessNumModule/fc_scores", {2 * (HW + 2), C}, &md.sc_w[SS_LESS],
               &md.sc_b[SS_LESS]);
     add_layer(c, "SamePropertyModule/fc_text", {Dt, M}, &md.txt_w[TS_SAMEPROP],
-              &md.txt_b[TS_SAMEPROP]);
+              &md.txt_b[TS_SAMEPROP], -2);
     add_layer(c, "SamePropertyModule/fc_att_0", {D, M}, &md.att_w[AS_SAMEPROP0],
-              &md.att_b[AS_SAMEPROP0]);
+              &md.att_b[AS_SAMEPROP0], -2);
     add_layer(c, "SamePropertyModule/fc_att_1", {D, M}, &md.att_w[AS_SAMEPROP1],
-              &md.att_b[AS_SAMEPROP1]);
+              &md.att_b[AS_SAMEPROP1], -2);
     add_layer(c, "SamePropertyModule/fc_eltwise", {M, C}, &md.out_w[OS_SAMEPROP],
               &md.out_b[OS_SAMEPROP]);
   }
-  add_layer(c, "DescribeModule/fc_text", {Dt, M}, &md.txt_w[TS_DESCRIBE], &md.txt_b[TS_DESCRIBE]);
-  add_layer(c, "DescribeModule/fc_att", {D, M}, &md.att_w[AS_DESCRIBE], &md.att_b[AS_DESCRIBE]);
+  add_layer(c, "DescribeModule/fc_text", {Dt, M}, &md.txt_w[TS_DESCRIBE], &md.txt_b[TS_DESCRIBE], -2);
+  add_layer(c, "DescribeModule/fc_att", {D, M}, &md.att_w[AS_DESCRIBE], &md.att_b[AS_DESCRIBE], -2);
   add_layer(c, "DescribeModule/fc_eltwise", {M, C}, &md.out_w[OS_DESCRIBE],
             &md.out_b[OS_DESCRIBE]);
 }
@@ -285,8 +292,10 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaS
   prof_mark(c, "begin", st);
   // ---- K1 text projections
   if (!S.groups.empty()) {
-    dim3 grid(c->Mp / 256, (unsigned)S.groups.size());
-    text_proj_kernel<<<grid, 256, kTextRowsPerCta * c->cfg.text_dim * sizeof(float), st>>>(
+    dim3 grid(c->Mp / kTextCols, (unsigned)S.groups.size());
+    const size_t smem = (size_t)(kTextRowsPerCta * c->cfg.text_dim +
+                                 8 * kTextRowsPerCta * kTextCols) * sizeof(float);
+    text_proj_kernel<<<grid, 256, smem, st>>>(
         c->md, c->tb, reinterpret_cast<const TextGroup*>(d + o.groups),
         reinterpret_cast<const int32_t*>(d + o.text_t),
         reinterpret_cast<const int32_t*>(d + o.text_b));
@@ -344,8 +353,24 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaS
       prof_mark(c, "wave_kernel", st);
     }
   } else if (NQ > 0) {
-    if (ks3) tree_kernel<3><<<NQ, kNodeThreads, c->node_smem_bytes, st>>>(nc, d_nodes, d_qptr);
-    else tree_kernel<5><<<NQ, kNodeThreads, c->node_smem_bytes, st>>>(nc, d_nodes, d_qptr);
+    // cluster size: spread one question over several SMs while the batch is small
+    int cs = c->tree_cluster;
+    if (cs <= 0) cs = (NQ * 4 <= 2 * c->num_sms) ? 4 : (NQ * 2 <= 2 * c->num_sms) ? 2 : 1;
+    cudaLaunchConfig_t lc;
+    std::memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3((unsigned)(NQ * cs));
+    lc.blockDim = dim3(kNodeThreads);
+    lc.dynamicSmemBytes = (size_t)c->node_smem_bytes;
+    lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr;
+    lc.numAttrs = cs > 1 ? 1 : 0;
+    if (ks3) CUDA_TRY(cudaLaunchKernelEx(&lc, tree_kernel<3>, nc, d_nodes, d_qptr, cs));
+    else CUDA_TRY(cudaLaunchKernelEx(&lc, tree_kernel<5>, nc, d_nodes, d_qptr, cs));
     ++c->launches;
     prof_mark(c, "tree_kernel", st);
   }
@@ -467,6 +492,10 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
       proj_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
       (int)((kSimtRows * kSimtKChunk + kSimtRows * c->Mp) * sizeof(float))));
   c->module_sched.uid = g_uid++;
+  if (const char* e = std::getenv("N2NMN_TREE_CLUSTER")) {
+    const int v = std::atoi(e);
+    if (v == 1 || v == 2 || v == 4 || v == 8) c->tree_cluster = v;
+  }
   *out = c;
   return 0;
 }
@@ -509,8 +538,14 @@ int n2nmn_set_weight(n2nmn_ctx* c, const char* name, const float* src, const int
     if (ndim != (int)v.shape.size()) return fail(N2NMN_ERR_ARG, std::string("rank mismatch for ") + name);
     for (int i = 0; i < ndim; ++i)
       if (shape[i] != v.shape[i]) return fail(N2NMN_ERR_ARG, std::string("shape mismatch for ") + name);
-    CUDA_TRY(cudaMemcpyAsync(c->wbuf + v.offset, src, v.count * sizeof(float),
-                             cudaMemcpyDeviceToDevice, st));
+    if (v.kind == VK_PITCHED) {
+      pitch_rows_kernel<<<(unsigned)v.shape[0], 256, 0, st>>>(src, (int)v.shape[0],
+                                                            (int)v.shape[1], c->wbuf + v.offset,
+                                                            c->Mp);
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(c->wbuf + v.offset, src, v.count * sizeof(float),
+                               cudaMemcpyDeviceToDevice, st));
+    }
     if (v.kind == VK_PROJ_W) {
       dim3 grid((c->Kp + 31) / 32, (c->Mp + 31) / 32), block(32, 8);
       transpose_pad_kernel<<<grid, block, 0, st>>>(c->wbuf + v.offset, c->Dk, c->cfg.map_dim,
@@ -660,6 +695,11 @@ int n2nmn_sched_get_info(const n2nmn_sched* s, n2nmn_sched_info* info) {
   return 0;
 }
 
+int n2nmn_last_step_info(const n2nmn_ctx* c, n2nmn_sched_info* info) {
+  if (!c) return fail(N2NMN_ERR_ARG, "null context");
+  return n2nmn_sched_get_info(&c->step_sched, info);
+}
+
 int n2nmn_sched_get_nodes(const n2nmn_sched* s, int32_t* out6, int cap) {
   if (!s || !out6) return fail(N2NMN_ERR_ARG, "null argument");
   const HostSchedule& S = s->hs;
@@ -708,7 +748,7 @@ int n2nmn_module_fwd(n2nmn_ctx* c, int op, const float* in0, const float* in1,
   n2nmn_sched* sc = &c->module_sched;
   sc->uid = g_uid++;   // tables change every call
   HostSchedule& S = sc->hs;
-  S = HostSchedule();
+  S.reset();
   S.N = c->N; S.T = c->T;
   S.nodes.resize(n); S.depth.assign(n, 1); S.q_ptr.resize(n + 1);
   const int scene_bits = [] { float v = 3.0f; int b; std::memcpy(&b, &v, 4); return b; }();
@@ -743,6 +783,23 @@ int n2nmn_module_fwd(n2nmn_ctx* c, int op, const float* in0, const float* in1,
   return 0;
 }
 
+int n2nmn_forward_tokens(n2nmn_ctx* c, const float* feat_dev, const float* wv_dev,
+                         const int32_t* tokens, int T, int N, const int32_t* vocab_ops,
+                         int num_vocab, float* scores_dev, uint8_t* validity_out, void* stream) {
+  if (!c || !tokens || !vocab_ops || !scores_dev) return fail(N2NMN_ERR_ARG, "null argument");
+  if (int rc = n2nmn_bind_inputs(c, feat_dev, wv_dev, N, T, stream)) return rc;
+  if (int rc = check_ready(c)) return rc;
+  n2nmn_sched* sc = &c->step_sched;
+  sc->uid = g_uid++;
+  const char* err = nullptr;
+  if (int rc = compile_schedule(c->shp, tokens, T, N, vocab_ops, num_vocab, &sc->hs, &err))
+    return fail(rc, err ? err : "compile_schedule failed");
+  if (validity_out) std::memcpy(validity_out, sc->hs.validity.data(), N);
+  if ((int)sc->hs.nodes.size() > c->arena_slots)
+    return fail(N2NMN_ERR_CAPACITY, "too many nodes for the context arena");
+  return run_tables(c, sc, scores_dev, c->arena, static_cast<cudaStream_t>(stream));
+}
+
 int n2nmn_forward_host(n2nmn_ctx* c, const float* feat_host, const float* wv_host,
                        const int32_t* tokens, int T, int N, const int32_t* vocab_ops,
                        int num_vocab, float* scores_host, uint8_t* validity_out, void* stream) {
@@ -763,11 +820,8 @@ int n2nmn_forward_host(n2nmn_ctx* c, const float* feat_host, const float* wv_hos
   }
   CUDA_TRY(cudaMemcpyAsync(c->e2e_feat, feat_host, fbytes, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(c->e2e_wv, wv_host, wbytes, cudaMemcpyHostToDevice, st));
-  if (int rc = n2nmn_bind_inputs(c, c->e2e_feat, c->e2e_wv, N, T, stream)) return rc;
-  n2nmn_sched* sc = nullptr;
-  if (int rc = n2nmn_compile_schedule(c, tokens, T, N, vocab_ops, num_vocab, validity_out, &sc))
-    return rc;
-  int rc = n2nmn_run_schedule(c, sc, c->e2e_scores, nullptr, stream);
+  int rc = n2nmn_forward_tokens(c, c->e2e_feat, c->e2e_wv, tokens, T, N, vocab_ops, num_vocab,
+                                c->e2e_scores, validity_out, stream);
   if (rc == 0) {
     cudaError_t e = cudaMemcpyAsync(scores_host, c->e2e_scores, sbytes, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -775,7 +829,6 @@ int n2nmn_forward_host(n2nmn_ctx* c, const float* feat_host, const float* wv_hos
   } else {
     cudaStreamSynchronize(st);
   }
-  n2nmn_sched_destroy(sc);
   return rc;
 }
 

@@ -1,17 +1,26 @@
-// K3: evaluation of one expression-tree node by one CTA, and the two executors built on it:
-//   * tree_kernel : one CTA per question walks that question's nodes in Reverse-Polish order
-//                   (every operand precedes its consumer), default;
+// K3: evaluation of expression-tree nodes, and the two executors built on it:
+//   * tree_kernel : one thread-block CLUSTER (1, 2 or 4 CTAs) per question walks that question's
+//                   nodes in Reverse-Polish order (every operand precedes its consumer); default;
 //   * wave_kernel : one CTA per node of one tree depth across the whole batch — the
 //                   depth-bucketed waves that replace TF Fold's dynamic batching
 //                   (models_clevr/nmn3_model.py:49-159).
 // Both call eval_node, so results are identical by construction.
 //
+// Inside a cluster the heavy modules are split across the CTAs: attention pooling by feature
+// channel, fc_att by weight rows (partial sums exchanged through distributed shared memory),
+// the stencil / per-pixel reductions by pixel. At batch 64 this spreads one question over 4 SMs
+// (L2->SM bandwidth, not arithmetic, bounds a node), at large batches the cluster size is 1.
+//
 // Find / Filter reach this kernel with their "find" map already in the arena (fused epilogue of
 // the projection kernel), FindSameProperty with its projected feature map in mbuf.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace n2nmn {
+
+namespace cg = cooperative_groups;
 
 struct NodeCtx {
   DevModel md;
@@ -21,9 +30,11 @@ struct NodeCtx {
   const float* mbuf;   // [mslots][HW][Mp]
 };
 
+constexpr int kNodeScratch = 2048;   // floats
+
 // Shared-memory carve-up (floats); the host computes the same layout to size the launch.
 struct NodeSmem {
-  int HWp, pad, f, scratch, v, z, k, total;
+  int HWp, pad, f, v, z, k, total;
 };
 __host__ __device__ inline NodeSmem node_smem_layout(int H, int W, int Dk, int Mp, int ksize,
                                                      int M) {
@@ -32,16 +43,15 @@ __host__ __device__ inline NodeSmem node_smem_layout(int H, int W, int Dk, int M
   s.HWp = (HW + 3) & ~3;
   s.pad = ((H + ksize - 1) * (W + ksize - 1) + 3) & ~3;
   s.f = 2 * ((Dk + 3) & ~3);
-  s.scratch = 1024;
-  s.v = 3 * Mp;
+  s.v = 5 * Mp;                      // v0 v1 v2 + two partial-sum buffers
   s.z = (2 * (HW + 2) + 3) & ~3;
   s.k = ksize * ksize * ((M + 127) / 128 * 128);
-  s.total = 2 * s.HWp + s.pad + s.f + s.scratch + s.v + 64 + s.z + s.k;
+  s.total = 2 * s.HWp + s.pad + s.f + kNodeScratch + s.v + 64 + s.z + s.k;
   return s;
 }
 
 struct SmemPtrs {
-  float *a0, *a1, *pad, *f, *scratch, *v0, *v1, *v2, *red, *z, *k;
+  float *a0, *a1, *pad, *f, *scratch, *v0, *v1, *v2, *part0, *part1, *red, *z, *k;
 };
 __device__ __forceinline__ SmemPtrs carve(float* base, const DevModel& md) {
   const NodeSmem L = node_smem_layout(md.H, md.W, md.Dk, md.Mp, md.ksize, md.M);
@@ -51,14 +61,28 @@ __device__ __forceinline__ SmemPtrs carve(float* base, const DevModel& md) {
   s.pad = s.a1 + L.HWp;
   s.f = s.pad + L.pad;
   s.scratch = s.f + L.f;
-  s.v0 = s.scratch + L.scratch;
+  s.v0 = s.scratch + kNodeScratch;
   s.v1 = s.v0 + md.Mp;
   s.v2 = s.v1 + md.Mp;
-  s.red = s.v2 + md.Mp;
+  s.part0 = s.v2 + md.Mp;
+  s.part1 = s.part0 + md.Mp;
+  s.red = s.part1 + md.Mp;
   s.z = s.red + 64;
   s.k = s.z + L.z;
   return s;
 }
+
+// Position of this CTA inside the cluster that evaluates the node.
+struct Coop {
+  int rank, size;
+  __device__ __forceinline__ void sync() const {
+    if (size > 1) cg::this_cluster().sync();   // also orders global + distributed-smem traffic
+    else __syncthreads();
+  }
+  __device__ __forceinline__ const float* peer(const float* p, int r) const {
+    return (size > 1) ? cg::this_cluster().map_shared_rank(const_cast<float*>(p), r) : p;
+  }
+};
 
 // ---- building blocks ---------------------------------------------------------------------------
 __device__ __forceinline__ void load_att(float* dst, const float* arena, int slot, int HW) {
@@ -82,20 +106,28 @@ __device__ __forceinline__ void softmax_inplace(float* a, int HW, float* red) {
   __syncthreads();
 }
 
-// att_feat = reduce_sum(image_feat_grid * att_softmax, [1,2]) (nmn3_modules.py:174): f[d] for the
-// node's image, read in place from the bound feature grid (the tf.gather copy of :49-51 is never
-// materialised). float4 over channels; pixel range split across thread slices when Dk is small.
+// This CTA's share [q0, q1) of `n` items split evenly over the cluster.
+__device__ __forceinline__ void coop_range(const Coop& co, int n, int& q0, int& q1) {
+  const int per = (n + co.size - 1) / co.size;
+  q0 = min(n, co.rank * per);
+  q1 = min(n, q0 + per);
+}
+
+// att_feat = reduce_sum(image_feat_grid * att_softmax, [1,2]) (nmn3_modules.py:174) for the
+// channel quads [g0, g1) of the node's image, read in place from the bound feature grid (the
+// tf.gather copy of :49-51 is never materialised). f[4*(g-g0) ..] receives the pooled values.
+// Threads form a (quad, pixel-slice) grid so that every thread has many independent loads.
 __device__ __forceinline__ void attention_pool(const DevModel& md, int b, const float* soft,
-                                               float* f, float* scratch) {
-  const int HW = md.HW, pitch = md.feat_pitch;
-  const int ng = (md.Dk + 3) >> 2;
-  const float4* X = reinterpret_cast<const float4*>(md.feat + (size_t)b * HW * pitch);
-  const int pitch4 = pitch >> 2;
+                                               int g0, int g1, float* f, float* scratch) {
+  const int HW = md.HW, pitch4 = md.feat_pitch >> 2;
+  const int ng = g1 - g0;
+  const float4* X = reinterpret_cast<const float4*>(md.feat + (size_t)b * HW * md.feat_pitch) + g0;
   const int nthreads = blockDim.x;
+  if (ng <= 0) { __syncthreads(); return; }
   if (ng >= nthreads) {
     for (int g = threadIdx.x; g < ng; g += nthreads) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
+#pragma unroll 8
       for (int p = 0; p < HW; ++p) {
         const float4 x = __ldg(X + (size_t)p * pitch4 + g);
         const float s = soft[p];
@@ -106,11 +138,11 @@ __device__ __forceinline__ void attention_pool(const DevModel& md, int b, const 
     }
   } else {
     int slices = nthreads / ng;
-    if (slices * ng * 4 > 1024) slices = 1024 / (ng * 4);
+    if (slices * ng * 4 > kNodeScratch) slices = kNodeScratch / (ng * 4);
     const int g = threadIdx.x % ng, sl = threadIdx.x / ng;
     if (sl < slices) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
+#pragma unroll 8
       for (int p = sl; p < HW; p += slices) {
         const float4 x = __ldg(X + (size_t)p * pitch4 + g);
         const float s = soft[p];
@@ -129,32 +161,86 @@ __device__ __forceinline__ void attention_pool(const DevModel& md, int b, const 
   __syncthreads();
 }
 
-// out[c] = bias[c] + Σ_k in[k]·W[k*M + c]  for c < M (zero for M <= c < Mp). fc_att etc.
-__device__ __forceinline__ void gemv_cols(const float* in, int L, const float* __restrict__ W,
-                                          const float* __restrict__ bias, float* out, int M,
-                                          int Mp) {
-  for (int c = threadIdx.x; c < Mp; c += blockDim.x) {
-    float acc = 0.f;
-    if (c < M) {
-      acc = bias[c];
-      const float* w = W + c;
-      int k = 0;
-      for (; k + 8 <= L; k += 8) {
-        float wv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + (size_t)(k + u) * M);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) acc = fmaf(in[k + u], wv[u], acc);
+// part[c] = Σ_{k in [k0,k1)} in[k-k0] · W[k*Mp + c] for all c < Mp (W has row pitch Mp, zero
+// padded). Threads form a (column quad, row slice) grid; row slices are reduced through scratch.
+__device__ __forceinline__ void gemv_partial(const float* in, int k0, int k1,
+                                             const float* __restrict__ W, int Mp, float* part,
+                                             float* scratch) {
+  const int quads = Mp >> 2, nthreads = blockDim.x;
+  if (quads >= nthreads) {
+    for (int q = threadIdx.x; q < quads; q += nthreads) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* w = reinterpret_cast<const float4*>(W) + q;
+#pragma unroll 8
+      for (int k = k0; k < k1; ++k) {
+        const float4 wv = __ldg(w + (size_t)k * quads);
+        const float x = in[k - k0];
+        acc.x = fmaf(x, wv.x, acc.x); acc.y = fmaf(x, wv.y, acc.y);
+        acc.z = fmaf(x, wv.z, acc.z); acc.w = fmaf(x, wv.w, acc.w);
       }
-      for (; k < L; ++k) acc = fmaf(in[k], __ldg(w + (size_t)k * M), acc);
+      reinterpret_cast<float4*>(part)[q] = acc;
     }
-    out[c] = acc;
+    __syncthreads();
+    return;
+  }
+  int slices = nthreads / quads;
+  if (slices * Mp > kNodeScratch) slices = kNodeScratch / Mp;
+  const int q = threadIdx.x % quads, sl = threadIdx.x / quads;
+  if (sl < slices) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* w = reinterpret_cast<const float4*>(W) + q;
+#pragma unroll 8
+    for (int k = k0 + sl; k < k1; k += slices) {
+      const float4 wv = __ldg(w + (size_t)k * quads);
+      const float x = in[k - k0];
+      acc.x = fmaf(x, wv.x, acc.x); acc.y = fmaf(x, wv.y, acc.y);
+      acc.z = fmaf(x, wv.z, acc.z); acc.w = fmaf(x, wv.w, acc.w);
+    }
+    reinterpret_cast<float4*>(scratch)[sl * quads + q] = acc;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Mp; c += nthreads) {
+    float s = 0.f;
+    for (int k = 0; k < slices; ++k) s += scratch[k * Mp + c];
+    part[c] = s;
+  }
+  __syncthreads();
+}
+
+// phi = fc_att(pooled(att)) for one attention input, cooperatively over the cluster:
+//   pooled channels are split over the CTAs, each CTA multiplies its channel slice with the
+//   matching rows of W_att, and `part` receives this CTA's partial sums (all Mp columns).
+// The caller exchanges the partials after a cluster sync (sum_partials).
+__device__ __forceinline__ void pooled_fc_partial(const DevModel& md, const Coop& co, int b,
+                                                  float* soft, const float* W, float* f,
+                                                  float* part, const SmemPtrs& s) {
+  softmax_inplace(soft, md.HW, s.red);
+  const int ng = (md.Dk + 3) >> 2;
+  int g0, g1;
+  coop_range(co, ng, g0, g1);
+  attention_pool(md, b, soft, g0, g1, f, s.scratch);
+  const int k0 = g0 * 4, k1 = min(md.Dk, g1 * 4);
+  gemv_partial(f, k0, max(k0, k1), W, md.Mp, part, s.scratch);
+}
+
+// out[c] = bias[c] + Σ_ranks part_r[c] (c < M; zero beyond), reading the peers' partial buffers
+// through distributed shared memory. Must be called after co.sync().
+__device__ __forceinline__ void sum_partials(const Coop& co, const float* part,
+                                             const float* __restrict__ bias, float* out, int M,
+                                             int Mp) {
+  for (int c = threadIdx.x; c < Mp; c += blockDim.x) {
+    float v = 0.f;
+    if (c < M) {
+      v = bias[c];
+      for (int r = 0; r < co.size; ++r) v += co.peer(part, r)[c];
+    }
+    out[c] = v;
   }
   __syncthreads();
 }
 
 // scores[c] = b[c] + Σ_k z[k]·W[k*C + c]: the fc('fc_scores') / fc('fc_eltwise') heads
-// (nmn3_modules.py:278,302,334,450,493). 8 thread groups split k, 32 lanes span c.
+// (nmn3_modules.py:278,302,334,450,493). Thread groups split k, 32 lanes span c.
 __device__ __forceinline__ void small_fc(const float* z, int L, const float* __restrict__ W,
                                          const float* __restrict__ bias, int C, float* out,
                                          float* scratch) {
@@ -162,8 +248,10 @@ __device__ __forceinline__ void small_fc(const float* z, int L, const float* __r
   for (int c0 = 0; c0 < C; c0 += 32) {
     const int c = c0 + lane;
     float acc = 0.f;
-    if (c < C)
+    if (c < C) {
+#pragma unroll 4
       for (int k = g; k < L; k += G) acc = fmaf(z[k], __ldg(W + (size_t)k * C + c), acc);
+    }
     scratch[g * 32 + lane] = acc;
     __syncthreads();
     if (g == 0 && c < C) {
@@ -175,7 +263,6 @@ __device__ __forceinline__ void small_fc(const float* z, int L, const float* __r
   }
 }
 
-// [a.flat, min, max] (Count / EqualNum...) or [min, mean, max] (Exist) into z.
 __device__ __forceinline__ void minmax(const float* a, int HW, float* red, float& mn, float& mx,
                                        float& sum) {
   float lmn = INFINITY, lmx = -INFINITY, ls = 0.f;
@@ -191,9 +278,10 @@ __device__ __forceinline__ void minmax(const float* a, int HW, float* red, float
 // ---- the modules -------------------------------------------------------------------------------
 template <int KS>
 __device__ __forceinline__ void eval_transform(const NodeCtx& c, const NodeRec& nd,
-                                               const SmemPtrs& s) {
+                                               const SmemPtrs& s, const Coop& co) {
   // TransformModule, conv variant (models_clevr/nmn3_modules.py:185-216, SHAPES :71-101):
   // SAME cross-correlation of the 1-channel map with [KS,KS,1,M], ∘ text, l2norm over M, ·w2 + b2
+  // Pixels are split over the cluster's warps; every CTA stages the (small) filter bank itself.
   const DevModel& md = c.md;
   const int H = md.H, W = md.W, HW = md.HW, M = md.M;
   const int PW = W + KS - 1, PH = H + KS - 1, R = (KS - 1) / 2;
@@ -207,7 +295,7 @@ __device__ __forceinline__ void eval_transform(const NodeCtx& c, const NodeRec& 
   }
   for (int i = threadIdx.x; i < KS * KS * Mq; i += blockDim.x) {
     const int tap = i / Mq, ch = i - tap * Mq;
-    s.k[i] = (ch < M) ? md.conv_k[tap * M + ch] : 0.f;
+    s.k[i] = (ch < M) ? __ldg(md.conv_k + tap * M + ch) : 0.f;
   }
   const float* tau = c.tb.tau + (size_t)nd.text * md.Mp;
   for (int ch = threadIdx.x; ch < Mq; ch += blockDim.x) {
@@ -217,10 +305,11 @@ __device__ __forceinline__ void eval_transform(const NodeCtx& c, const NodeRec& 
     s.v2[ch] = live ? md.conv_b[ch] : 0.f;
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int gwarp = co.rank * nwarps + (threadIdx.x >> 5), gwarps = co.size * nwarps;
   const float b2 = md.elt_b[ES_TRANSFORM][0];
   float* dst = c.arena + (size_t)nd.out * HW;
-  for (int p = warp; p < HW; p += nwarps) {
+  for (int p = gwarp; p < HW; p += gwarps) {
     const int y = p / W, x = p - y * W;
     float win[KS * KS];
 #pragma unroll
@@ -251,16 +340,16 @@ __device__ __forceinline__ void eval_transform(const NodeCtx& c, const NodeRec& 
 }
 
 __device__ __forceinline__ void eval_find_same_property(const NodeCtx& c, const NodeRec& nd,
-                                                        const SmemPtrs& s) {
+                                                        const SmemPtrs& s, const Coop& co) {
   // FindSamePropertyModule (models_clevr/nmn3_modules.py:134-183) and the VQA TransformModule
   // (models_vqa/nmn3_modules.py:123-171): l2norm_c(m ∘ τ ∘ φ)·w2 + b2 with φ = fc_att(pooled).
   const DevModel& md = c.md;
   const int HW = md.HW, Mp = md.Mp, M = md.M;
   load_att(s.a0, c.arena, nd.in0, HW);
   __syncthreads();
-  softmax_inplace(s.a0, HW, s.red);
-  attention_pool(md, nd.b, s.a0, s.f, s.scratch);
-  gemv_cols(s.f, md.Dk, md.att_w[AS_FSP], md.att_b[AS_FSP], s.v0, M, Mp);
+  pooled_fc_partial(md, co, nd.b, s.a0, md.att_w[AS_FSP], s.f, s.part0, s);
+  co.sync();
+  sum_partials(co, s.part0, md.att_b[AS_FSP], s.v0, M, Mp);
   const float* tauw = c.tb.tauw + (size_t)nd.text * Mp;   // τ∘w2
   const float* tau = c.tb.tau + (size_t)nd.text * Mp;
   for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
@@ -270,11 +359,12 @@ __device__ __forceinline__ void eval_find_same_property(const NodeCtx& c, const 
     s.v2[ch] = tp * tp;          // coefficient of m² in the squared norm
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int gwarp = co.rank * nwarps + (threadIdx.x >> 5), gwarps = co.size * nwarps;
   const float b2 = md.elt_b[ES_FSP][0];
   const float* mimg = c.mbuf + (size_t)nd.aux * HW * Mp;
   float* dst = c.arena + (size_t)nd.out * HW;
-  for (int p = warp; p < HW; p += nwarps) {
+  for (int p = gwarp; p < HW; p += gwarps) {
     const float4* mrow = reinterpret_cast<const float4*>(mimg + (size_t)p * Mp);
     float num = 0.f, den = 0.f;
     for (int q = lane; q < (Mp >> 2); q += 32) {
@@ -307,14 +397,15 @@ __device__ __forceinline__ void normalize_and_score(const NodeCtx& c, const Node
 }
 
 __device__ __forceinline__ void eval_describe(const NodeCtx& c, const NodeRec& nd,
-                                              const SmemPtrs& s) {
+                                              const SmemPtrs& s, const Coop& co) {
   // DescribeModule (models_clevr/nmn3_modules.py:454-495, VQA models_vqa/nmn3_modules.py:193-240)
   const DevModel& md = c.md;
   load_att(s.a0, c.arena, nd.in0, md.HW);
   __syncthreads();
-  softmax_inplace(s.a0, md.HW, s.red);
-  attention_pool(md, nd.b, s.a0, s.f, s.scratch);
-  gemv_cols(s.f, md.Dk, md.att_w[AS_DESCRIBE], md.att_b[AS_DESCRIBE], s.v0, md.M, md.Mp);
+  pooled_fc_partial(md, co, nd.b, s.a0, md.att_w[AS_DESCRIBE], s.f, s.part0, s);
+  co.sync();
+  if (co.rank != 0) return;   // the tail is tiny: one CTA finishes it
+  sum_partials(co, s.part0, md.att_b[AS_DESCRIBE], s.v0, md.M, md.Mp);
   const float* tau = c.tb.tau + (size_t)nd.text * md.Mp;
   for (int ch = threadIdx.x; ch < md.M; ch += blockDim.x) s.v1[ch] = tau[ch] * s.v0[ch];
   __syncthreads();
@@ -322,19 +413,19 @@ __device__ __forceinline__ void eval_describe(const NodeCtx& c, const NodeRec& n
 }
 
 __device__ __forceinline__ void eval_same_property(const NodeCtx& c, const NodeRec& nd,
-                                                   const SmemPtrs& s) {
+                                                   const SmemPtrs& s, const Coop& co) {
   // SamePropertyModule (models_clevr/nmn3_modules.py:402-452)
   const DevModel& md = c.md;
   load_att(s.a0, c.arena, nd.in0, md.HW);
   load_att(s.a1, c.arena, nd.in1, md.HW);
   __syncthreads();
-  softmax_inplace(s.a0, md.HW, s.red);
-  softmax_inplace(s.a1, md.HW, s.red);
   const int Dkp = (md.Dk + 3) & ~3;
-  attention_pool(md, nd.b, s.a0, s.f, s.scratch);
-  attention_pool(md, nd.b, s.a1, s.f + Dkp, s.scratch);
-  gemv_cols(s.f, md.Dk, md.att_w[AS_SAMEPROP0], md.att_b[AS_SAMEPROP0], s.v0, md.M, md.Mp);
-  gemv_cols(s.f + Dkp, md.Dk, md.att_w[AS_SAMEPROP1], md.att_b[AS_SAMEPROP1], s.v1, md.M, md.Mp);
+  pooled_fc_partial(md, co, nd.b, s.a0, md.att_w[AS_SAMEPROP0], s.f, s.part0, s);
+  pooled_fc_partial(md, co, nd.b, s.a1, md.att_w[AS_SAMEPROP1], s.f + Dkp, s.part1, s);
+  co.sync();
+  if (co.rank != 0) return;
+  sum_partials(co, s.part0, md.att_b[AS_SAMEPROP0], s.v0, md.M, md.Mp);
+  sum_partials(co, s.part1, md.att_b[AS_SAMEPROP1], s.v1, md.M, md.Mp);
   const float* tau = c.tb.tau + (size_t)nd.text * md.Mp;
   for (int ch = threadIdx.x; ch < md.M; ch += blockDim.x)
     s.v2[ch] = s.v0[ch] * tau[ch] * s.v1[ch];
@@ -375,14 +466,18 @@ __device__ __forceinline__ void eval_small_answer(const NodeCtx& c, const NodeRe
            s.scratch);
 }
 
+// Evaluates one node with the CTAs of `co`. Every CTA of the cluster must call it (the heavy
+// modules contain cluster barriers); the caller synchronises the cluster afterwards.
 template <int KS>
-__device__ __forceinline__ void eval_node(const NodeCtx& c, const NodeRec& nd, const SmemPtrs& s) {
+__device__ __forceinline__ void eval_node(const NodeCtx& c, const NodeRec& nd, const SmemPtrs& s,
+                                          const Coop& co) {
   const int HW = c.md.HW;
+  const int gtid = co.rank * blockDim.x + threadIdx.x, gthreads = co.size * blockDim.x;
   switch (nd.op) {
     case OP_SCENE: {   // models_clevr/nmn3_modules.py:60-72; aux carries pos_val's bits
       float* dst = c.arena + (size_t)nd.out * HW;
       const float v = __int_as_float(nd.aux);
-      for (int p = threadIdx.x; p < HW; p += blockDim.x) dst[p] = v;
+      for (int p = gtid; p < HW; p += gthreads) dst[p] = v;
       break;
     }
     case OP_FIND:      // already written by the projection kernel's epilogue
@@ -390,7 +485,7 @@ __device__ __forceinline__ void eval_node(const NodeCtx& c, const NodeRec& nd, c
     case OP_FILTER: {  // min(input_0, Find(t,b)) (nmn3_modules.py:129-130); find part is in `out`
       float* dst = c.arena + (size_t)nd.out * HW;
       const float* a = c.arena + (size_t)nd.in0 * HW;
-      for (int p = threadIdx.x; p < HW; p += blockDim.x) dst[p] = fminf(a[p], dst[p]);
+      for (int p = gtid; p < HW; p += gthreads) dst[p] = fminf(a[p], dst[p]);
       break;
     }
     case OP_AND:       // tf.minimum / tf.maximum (nmn3_modules.py:233,253)
@@ -398,34 +493,43 @@ __device__ __forceinline__ void eval_node(const NodeCtx& c, const NodeRec& nd, c
       float* dst = c.arena + (size_t)nd.out * HW;
       const float* a = c.arena + (size_t)nd.in0 * HW;
       const float* b = c.arena + (size_t)nd.in1 * HW;
-      for (int p = threadIdx.x; p < HW; p += blockDim.x)
+      for (int p = gtid; p < HW; p += gthreads)
         dst[p] = (nd.op == OP_AND) ? fminf(a[p], b[p]) : fmaxf(a[p], b[p]);
       break;
     }
-    case OP_TRANSFORM: eval_transform<KS>(c, nd, s); break;
-    case OP_FIND_SAME_PROPERTY: eval_find_same_property(c, nd, s); break;
-    case OP_DESCRIBE: eval_describe(c, nd, s); break;
-    case OP_SAME_PROPERTY: eval_same_property(c, nd, s); break;
-    default: eval_small_answer(c, nd, s); break;
+    case OP_TRANSFORM: eval_transform<KS>(c, nd, s, co); break;
+    case OP_FIND_SAME_PROPERTY: eval_find_same_property(c, nd, s, co); break;
+    case OP_DESCRIBE: eval_describe(c, nd, s, co); break;
+    case OP_SAME_PROPERTY: eval_same_property(c, nd, s, co); break;
+    default:
+      if (co.rank == 0) eval_small_answer(c, nd, s);
+      break;
   }
 }
 
-// One CTA per question; q_ptr delimits the question's nodes (Reverse-Polish order) in `nodes`.
+// One cluster of `csize` CTAs per question; q_ptr delimits the question's nodes (Reverse-Polish
+// order) in `nodes`. Launched with a cluster dimension of csize (plain launch when csize == 1).
 template <int KS>
 __global__ void __launch_bounds__(kNodeThreads)
-tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* __restrict__ q_ptr) {
-  extern __shared__ float node_smem[];
+tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* __restrict__ q_ptr,
+            int csize) {
+  extern __shared__ __align__(16) float node_smem[];
   const SmemPtrs s = carve(node_smem, c.md);
-  const int q = blockIdx.x;
+  Coop co;
+  co.size = csize;
+  co.rank = (csize > 1) ? (int)cg::this_cluster().block_rank() : 0;
+  const int q = blockIdx.x / csize;
   const int beg = q_ptr[q], end = q_ptr[q + 1];
   if (beg == end) {   // invalid layout: zeros(num_choices) (models_clevr/nmn3_model.py:144-155)
-    for (int i = threadIdx.x; i < c.md.C; i += blockDim.x) c.scores[(size_t)q * c.md.C + i] = 0.f;
+    if (co.rank == 0)
+      for (int i = threadIdx.x; i < c.md.C; i += blockDim.x)
+        c.scores[(size_t)q * c.md.C + i] = 0.f;
     return;
   }
   for (int i = beg; i < end; ++i) {
     const NodeRec nd = nodes[i];
-    eval_node<KS>(c, nd, s);
-    __syncthreads();   // arena writes of this node are visible to the block's next node
+    eval_node<KS>(c, nd, s, co);
+    co.sync();   // this node's arena writes (and DSMEM reads) are done before the next node
   }
 }
 
@@ -434,10 +538,12 @@ template <int KS>
 __global__ void __launch_bounds__(kNodeThreads)
 wave_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes,
             const int32_t* __restrict__ wave_nodes, int first) {
-  extern __shared__ float node_smem[];
+  extern __shared__ __align__(16) float node_smem[];
   const SmemPtrs s = carve(node_smem, c.md);
   const NodeRec nd = nodes[wave_nodes[first + blockIdx.x]];
-  eval_node<KS>(c, nd, s);
+  Coop co;
+  co.rank = 0; co.size = 1;
+  eval_node<KS>(c, nd, s, co);
 }
 
 }  // namespace n2nmn

@@ -28,6 +28,15 @@ __global__ void pad_copy_kernel(const float* __restrict__ src, int n, float* __r
   if (i < np) dst[i] = (i < n) ? src[i] : 0.f;
 }
 
+// [rows][M] -> [rows][Mp] with zero padding, so rows are 16-byte aligned for float4 loads.
+__global__ void pitch_rows_kernel(const float* __restrict__ src, int rows, int M,
+                                  float* __restrict__ dst, int Mp) {
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  for (int c = threadIdx.x; c < Mp; c += blockDim.x)
+    dst[(size_t)r * Mp + c] = (c < M) ? src[(size_t)r * M + c] : 0.f;
+}
+
 // add_spatial_coordinate_map (models_vqa/nmn3_modules.py:11-31): dst[r, :] =
 // [src[r, 0:D], x, y, 0...] with x = linspace(-1,1,W)[col], y = linspace(-1,1,H)[row]; also used
 // (with_coords = 0) to re-pitch feature grids whose channel count is not a multiple of 4.

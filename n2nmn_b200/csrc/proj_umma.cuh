@@ -31,8 +31,13 @@ constexpr int kBBytes = kBN * kBK * 4;   // 32768
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kProjThreads = 192;
 constexpr int kTmemCols = 512;
-// dynamic smem: stages + barriers, plus 1024 for manual alignment
-constexpr int kProjSmemBytes = kStages * kStageBytes + 256 + 1024;
+// Epilogue operand staging (only when a tile spans <= 2 images, i.e. HW >= 127): for each of the
+// two images up to 8 consumer nodes x {tau∘w2, tau²} x 256 columns, plus the 256 bias values.
+constexpr int kVecImages = 2;
+constexpr int kVecFloats = kVecImages * kMaxProjNodesPerPass * 2 * kBN;   // 8192 floats = 32 KB
+constexpr int kVecBytes = (kVecFloats + kBN) * 4;
+// dynamic smem: stages + staged vectors + barriers, plus 1024 for manual alignment
+constexpr int kProjSmemBytes = kStages * kStageBytes + kVecBytes + 256 + 1024;
 
 struct ProjTensorMaps {
   CUtensorMap a;                     // features [total_rows, Dk] fp32, box 32 x 128
@@ -47,7 +52,9 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  float* s_vec = reinterpret_cast<float*>(smem + kStages * kStageBytes);
+  float* s_bias = s_vec + kVecFloats;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kVecBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
@@ -129,13 +136,17 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
     // ===================================================================== epilogue warps
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int trow = quarter * 32 + lane;      // row inside the 128-row tile
+    const int etid = threadIdx.x - 64;         // 0..127 among the epilogue threads
+    const bool staged = p.HW >= kBM - 1;       // a tile then spans at most two images
     uint32_t it = 0;
     for (int wi = blockIdx.x; wi < p.num_work; wi += gridDim.x) {
       const ProjWork wk = p.work[wi];
       const int row = wk.row0 + trow;
       const bool row_ok = row < p.total_rows;
-      const int b = row_ok ? row / p.HW : 0;
+      const int b_first = wk.row0 / p.HW;
+      const int b = row_ok ? row / p.HW : b_first;
       const int pix = row - b * p.HW;
+      const int img_local = b - b_first;
       // consumers of this row
       int e_beg = 0, n_nodes = 0;
       float* mdst = nullptr;
@@ -153,8 +164,30 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
 #pragma unroll
       for (int j = 0; j < kMaxProjNodesPerPass; ++j) { num[j] = 0.f; den[j] = 0.f; }
       const float* __restrict__ bias = p.bias[wk.set];
+      const int n_img = min((p.total_rows - 1) / p.HW, (wk.row0 + kBM - 1) / p.HW) - b_first + 1;
 
       for (int nt = 0; nt < p.n_tiles; ++nt, ++it) {
+        // ---- stage this N-tile's epilogue operands while the MMAs are still running
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // previous readers of s_vec are done
+        for (int i = etid; i < kBN / 4; i += 128)
+          reinterpret_cast<float4*>(s_bias)[i] =
+              __ldg(reinterpret_cast<const float4*>(bias + nt * kBN) + i);
+        if (staged && wk.set == PS_FIND) {
+          // item = (image, node, vector kind, column quad): 2 x 8 x 2 x 64 float4
+          for (int i = etid; i < kVecFloats / 4; i += 128) {
+            const int q = i & 63, kind = (i >> 6) & 1, j = (i >> 7) & 7, im = i >> 10;
+            if (im < n_img) {
+              const int eb = p.img_ptr[b_first + im] + wk.pass * kMaxProjNodesPerPass;
+              if (eb + j < p.img_ptr[b_first + im + 1]) {
+                const float* src = (kind ? p.tau2 : p.tauw) +
+                                   (size_t)p.node_text[eb + j] * p.Mp + nt * kBN;
+                reinterpret_cast<float4*>(s_vec)[i] = __ldg(reinterpret_cast<const float4*>(src) + q);
+              }
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         ptx::mbar_wait(&tmem_full[acc], acc_phase);
         ptx::tc_fence_after();
@@ -167,7 +200,7 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
           const int col0 = nt * kBN + ch * 32;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + col0) + q);
+            const float4 bq = reinterpret_cast<const float4*>(s_bias + ch * 32)[q];
             v[4 * q + 0] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
           }
           if (mdst != nullptr) {
@@ -176,24 +209,35 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
               reinterpret_cast<float4*>(mdst + col0)[q] =
                   make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
+          if (n_nodes > 0) {
+            float v2[32];
 #pragma unroll
-          for (int j = 0; j < kMaxProjNodesPerPass; ++j) {
-            if (j < n_nodes) {
-              const int trow_txt = p.node_text[e_beg + j];
-              const float4* tw = reinterpret_cast<const float4*>(
-                  p.tauw + (size_t)trow_txt * p.Mp + col0);
-              const float4* t2 = reinterpret_cast<const float4*>(
-                  p.tau2 + (size_t)trow_txt * p.Mp + col0);
-              float n = num[j], d = den[j];
+            for (int i = 0; i < 32; ++i) v2[i] = v[i] * v[i];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 a = __ldg(tw + q), s = __ldg(t2 + q);
-                n = fmaf(v[4 * q + 0], a.x, n); d = fmaf(v[4 * q + 0] * v[4 * q + 0], s.x, d);
-                n = fmaf(v[4 * q + 1], a.y, n); d = fmaf(v[4 * q + 1] * v[4 * q + 1], s.y, d);
-                n = fmaf(v[4 * q + 2], a.z, n); d = fmaf(v[4 * q + 2] * v[4 * q + 2], s.z, d);
-                n = fmaf(v[4 * q + 3], a.w, n); d = fmaf(v[4 * q + 3] * v[4 * q + 3], s.w, d);
+            for (int j = 0; j < kMaxProjNodesPerPass; ++j) {
+              if (j < n_nodes) {
+                const float4 *tw, *t2;
+                if (staged) {
+                  const float* base = s_vec + ((img_local * kMaxProjNodesPerPass + j) * 2) * kBN +
+                                      ch * 32;
+                  tw = reinterpret_cast<const float4*>(base);
+                  t2 = reinterpret_cast<const float4*>(base + kBN);
+                } else {
+                  const int trow_txt = p.node_text[e_beg + j];
+                  tw = reinterpret_cast<const float4*>(p.tauw + (size_t)trow_txt * p.Mp + col0);
+                  t2 = reinterpret_cast<const float4*>(p.tau2 + (size_t)trow_txt * p.Mp + col0);
+                }
+                float n = num[j], d = den[j];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 a = tw[q], sq = t2[q];
+                  n = fmaf(v[4 * q + 0], a.x, n); d = fmaf(v2[4 * q + 0], sq.x, d);
+                  n = fmaf(v[4 * q + 1], a.y, n); d = fmaf(v2[4 * q + 1], sq.y, d);
+                  n = fmaf(v[4 * q + 2], a.z, n); d = fmaf(v2[4 * q + 2], sq.z, d);
+                  n = fmaf(v[4 * q + 3], a.w, n); d = fmaf(v2[4 * q + 3], sq.w, d);
+                }
+                num[j] = n; den[j] = d;
               }
-              num[j] = n; den[j] = d;
             }
           }
         }

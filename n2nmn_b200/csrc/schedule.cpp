@@ -41,17 +41,17 @@ int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
                      const int32_t* vocab_ops, int num_vocab, HostSchedule* out,
                      const char** err) {
   HostSchedule& S = *out;
-  S = HostSchedule();
+  S.reset();
   S.N = N; S.T = T;
   S.validity.assign(N, 0);
   S.q_ptr.assign(N + 1, 0);
   S.hash = fnv1a(tokens, sizeof(int32_t) * (size_t)T * N);
   S.hash = fnv1a(vocab_ops, sizeof(int32_t) * num_vocab, S.hash);
 
-  std::vector<Pending> all;
+  static thread_local std::vector<Pending> all, q;
+  static thread_local std::vector<int> stack;   // indices into q
+  all.clear();
   all.reserve((size_t)N * 8);
-  std::vector<Pending> q;
-  std::vector<int> stack;   // indices into q
   const int scene_bits = [] { float v = 3.0f; int b; std::memcpy(&b, &v, 4); return b; }();
 
   for (int n = 0; n < N; ++n) {
@@ -116,6 +116,10 @@ int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out) 
   const int NQ = (int)S.q_ptr.size() - 1;   // questions (rows of the score matrix)
   const int num_nodes = (int)S.nodes.size();
   S.max_depth = 0;
+  S.groups.clear(); S.work.clear();
+  S.num_mslots = 0; S.num_find_nodes = 0;
+  for (int k = 0; k < 3; ++k) S.kbytes[k] = S.kflops[k] = 0;
+  S.per_node_bytes = S.per_node_flops = 0;
   // ---- text rows, grouped by weight set
   int set_count[NUM_TEXT_SETS] = {0};
   for (const NodeRec& r : S.nodes) if (text_set_of(r.op) >= 0) ++set_count[text_set_of(r.op)];

@@ -37,6 +37,17 @@ struct HostSchedule {
   int64_t per_node_bytes = 0;         // Σ over nodes of the App. D per-node figure
   int64_t per_node_flops = 0;
   uint64_t hash = 0;
+
+  // Forget the contents but keep every vector's capacity (the per-step path reuses one object).
+  void reset() {
+    N = T = num_valid = max_depth = num_mslots = num_find_nodes = 0;
+    validity.clear(); nodes.clear(); depth.clear(); q_ptr.clear(); text_t.clear();
+    text_b.clear(); groups.clear(); work.clear(); img_ptr.clear(); node_text.clear();
+    node_out.clear(); mslot.clear(); wave_ptr.clear(); wave_nodes.clear();
+    for (int k = 0; k < 3; ++k) kbytes[k] = kflops[k] = 0;
+    per_node_bytes = per_node_flops = 0;
+    hash = 0;
+  }
 };
 
 // Returns 0 or a negative n2nmn_status; `err` receives a message on failure.

@@ -4,54 +4,83 @@
 //  util/cnn.py:116). The gather of _slice_word_vecs (nmn3_modules.py:53-57) is folded into the
 // load: row (t*N + b) of the time-major word_vecs.
 //
-// One CTA = up to 8 nodes of ONE weight set x 256 output columns; the weight matrix row is read
-// once per CTA (coalesced over columns) and reused for the 8 nodes from registers.
+// One CTA = up to 8 nodes of ONE weight set x 64 output columns. The 256 threads form a
+// 16 (column quads) x 16 (K slices) grid: every thread streams ~Dt/16 float4 weight rows with all
+// loads independent (the kernel is latency-bound, so memory-level parallelism is what matters),
+// keeps 8x4 accumulators, and the 16 K slices are reduced through shared memory.
 // Also emits tau∘w_eltwise and tau² so the consumers' epilogues are pure FMAs.
+// Weights are stored with row pitch Mp (zero padded), so padded columns come out as exact zeros.
 #pragma once
 #include "common.cuh"
 
 namespace n2nmn {
 
+constexpr int kTextCols = 64;   // output columns per CTA
+
 __global__ void __launch_bounds__(256)
 text_proj_kernel(DevModel md, TextBufs tb, const TextGroup* __restrict__ groups,
                  const int32_t* __restrict__ text_t, const int32_t* __restrict__ text_b) {
-  extern __shared__ float s_x[];  // [8][Dt]
-  const TextGroup g = groups[blockIdx.y];
+  extern __shared__ float s_dyn[];
   const int Dt = md.Dt, M = md.M, Mp = md.Mp;
-  for (int i = threadIdx.x; i < g.count * Dt; i += blockDim.x) {
+  float* s_x = s_dyn;                                 // [8][Dt]
+  float* s_red = s_dyn + kTextRowsPerCta * Dt;        // [8 warps][8 rows][64 cols]
+  const TextGroup g = groups[blockIdx.y];
+  for (int i = threadIdx.x; i < kTextRowsPerCta * Dt; i += blockDim.x) {
     const int r = i / Dt, k = i - r * Dt;
-    const int row = g.start + r;
-    s_x[r * Dt + k] = md.word_vecs[((size_t)text_t[row] * md.N + text_b[row]) * Dt + k];
+    float v = 0.f;
+    if (r < g.count) {
+      const int row = g.start + r;
+      v = md.word_vecs[((size_t)text_t[row] * md.N + text_b[row]) * Dt + k];
+    }
+    s_x[i] = v;
   }
   __syncthreads();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= Mp) return;
-  float acc[kTextRowsPerCta];
-  const bool live = c < M;
-  const float bias = live ? md.txt_b[g.set][c] : 0.f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tx = lane & 15;                    // column quad inside the CTA's 64 columns
+  const int ky = warp * 2 + (lane >> 4);       // K slice 0..15
+  const int c0 = blockIdx.x * kTextCols + tx * 4;
+  float4 acc[kTextRowsPerCta];
 #pragma unroll
-  for (int r = 0; r < kTextRowsPerCta; ++r) acc[r] = bias;
-  if (live) {
-    const float* __restrict__ w = md.txt_w[g.set] + c;
+  for (int r = 0; r < kTextRowsPerCta; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* __restrict__ wbase = md.txt_w[g.set] + c0;
 #pragma unroll 4
-    for (int k = 0; k < Dt; ++k) {
-      const float wk = __ldg(w + (size_t)k * M);
+  for (int k = ky; k < Dt; k += 16) {
+    const float4 w = __ldg(reinterpret_cast<const float4*>(wbase + (size_t)k * Mp));
 #pragma unroll
-      for (int r = 0; r < kTextRowsPerCta; ++r) acc[r] = fmaf(s_x[r * Dt + k], wk, acc[r]);
+    for (int r = 0; r < kTextRowsPerCta; ++r) {
+      const float x = s_x[r * Dt + k];
+      acc[r].x = fmaf(x, w.x, acc[r].x); acc[r].y = fmaf(x, w.y, acc[r].y);
+      acc[r].z = fmaf(x, w.z, acc[r].z); acc[r].w = fmaf(x, w.w, acc[r].w);
     }
   }
-  const int es = (g.set == TS_FIND) ? ES_FIND : (g.set == TS_FSP) ? ES_FSP
-               : (g.set == TS_TRANSFORM) ? ES_TRANSFORM : -1;
-  const float w2 = (live && es >= 0) ? md.elt_w[es][c] : 1.f;
+  // the two K slices inside a warp, then the 8 warps through shared memory
 #pragma unroll
   for (int r = 0; r < kTextRowsPerCta; ++r) {
-    if (r < g.count) {
-      const size_t o = (size_t)(g.start + r) * Mp + c;
-      const float v = live ? acc[r] : 0.f;
-      tb.tau[o] = v;
-      tb.tauw[o] = v * w2;
-      tb.tau2[o] = v * v;
-    }
+    acc[r].x += __shfl_xor_sync(0xffffffffu, acc[r].x, 16);
+    acc[r].y += __shfl_xor_sync(0xffffffffu, acc[r].y, 16);
+    acc[r].z += __shfl_xor_sync(0xffffffffu, acc[r].z, 16);
+    acc[r].w += __shfl_xor_sync(0xffffffffu, acc[r].w, 16);
+    if (lane < 16)
+      *reinterpret_cast<float4*>(s_red + ((warp * kTextRowsPerCta + r) * kTextCols + tx * 4)) =
+          acc[r];
+  }
+  __syncthreads();
+  const int es = (g.set == TS_FIND) ? ES_FIND : (g.set == TS_FSP) ? ES_FSP
+               : (g.set == TS_TRANSFORM) ? ES_TRANSFORM : -1;
+  for (int o = threadIdx.x; o < kTextRowsPerCta * kTextCols; o += blockDim.x) {
+    const int r = o / kTextCols, cc = o - r * kTextCols;
+    if (r >= g.count) continue;
+    const int c = blockIdx.x * kTextCols + cc;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += s_red[(w * kTextRowsPerCta + r) * kTextCols + cc];
+    const bool live = c < M;
+    v = live ? v + md.txt_b[g.set][c] : 0.f;
+    const float w2 = (live && es >= 0) ? md.elt_w[es][c] : 1.f;
+    const size_t idx = (size_t)(g.start + r) * Mp + c;
+    tb.tau[idx] = v;
+    tb.tauw[idx] = v * w2;
+    tb.tau2[idx] = v * v;
   }
 }
 

@@ -88,6 +88,7 @@ class LayoutExecutor:
         fam = cfgmod.FAMILIES[family]
         self.vocab_ops = np.array([fam.token_ops.get(n, -1) for n in assembler.module_names],
                                   np.int32)
+        self._vocab_ptr = self.vocab_ops.ctypes.data
         self.compiler = _Compiler(self)
         self.scores = None   # last result, like fetching `nmn3_model.scores`
         self._cache = {}
@@ -160,6 +161,38 @@ class LayoutExecutor:
         """tokens [T,N] -> (scores [N,C] CUDA tensor, validity bool[N])."""
         cb = self.compile_tokens(layout_tokens, cache=cache)
         return self.run(cb), cb.validity
+
+    def forward_device(self, image_feat_grid, word_vecs, layout_tokens, out=None):
+        """One eval step with device-resident inputs: bind + C++ layout compile + launches in a
+        single C call (n2nmn_forward_tokens). Inputs must be contiguous float32 CUDA tensors
+        ([N,H,W,D], [T,N,Dt]); tokens a C-contiguous int32 [T,N] numpy array. Returns
+        (scores [N,C] CUDA tensor, validity bool[N]). Asynchronous on the current stream."""
+        m = self.modules
+        tok = layout_tokens
+        if tok.dtype != np.int32 or not tok.flags['C_CONTIGUOUS']:
+            tok = np.ascontiguousarray(tok, dtype=np.int32)
+        T, N = tok.shape
+        if out is None:
+            out = torch.empty((N, self.num_choices), dtype=torch.float32, device=m.device)
+        validity = np.empty(N, np.uint8)
+        assert image_feat_grid.is_cuda and image_feat_grid.is_contiguous() and \
+            image_feat_grid.dtype == torch.float32 and word_vecs.is_cuda and \
+            word_vecs.is_contiguous() and word_vecs.dtype == torch.float32
+        m.image_feat_grid, m.word_vecs, m.N, m.T = image_feat_grid, word_vecs, N, T
+        _lib.check(self._lib.n2nmn_forward_tokens(
+            m._h, image_feat_grid.data_ptr(), word_vecs.data_ptr(), tok.ctypes.data, T, N,
+            self._vocab_ptr, len(self.vocab_ops), out.data_ptr(), validity.ctypes.data,
+            torch.cuda.current_stream(m.device).cuda_stream))
+        self.scores = out
+        return out, validity.view(bool)
+
+    def last_step_info(self):
+        info = _lib.SchedInfo()
+        _lib.check(self._lib.n2nmn_last_step_info(self.modules._h, C.byref(info)))
+        d = {f[0]: getattr(info, f[0]) for f in info._fields_ if not f[0].startswith('kernel_')}
+        d['kernel_bytes'] = list(info.kernel_bytes)
+        d['kernel_flops'] = list(info.kernel_flops)
+        return d
 
     def forward(self, expr_list):
         return self.run(self.compile_exprs(expr_list))

@@ -156,6 +156,41 @@ def test_zero_size_module_call_and_errors():
         ex.compile_tokens(np.zeros((T + 1, N), np.int32))                   # T above capacity
 
 
+def test_forward_device_single_call_matches_compiled_path():
+    from n2nmn_b200 import weights as wts
+    N, H, Wd, D, T, C = 64, 10, 15, 512, 20, 28
+    feat, word_vecs = synth.make_inputs(N, H, Wd, D, T, seed=31)
+    W = wts.init_weights('clevr', H, Wd, D, C, seed=2, bias_std=0.1)
+    ex = make_executor('clevr', feat, word_vecs, C, W)
+    tokens = synth.random_valid_tokens(ex.assembler, N, T, seed=11)
+    tokens[:, 5] = ex.assembler.module_list2tokens(['_Find', '_Find'], T)   # an invalid column
+    ref, valid = ex.forward_tokens(tokens)
+    f2, w2 = synth.make_inputs(N, H, Wd, D, T, seed=32)     # rebinding to other buffers works
+    other, _ = ex.forward_device(torch.from_numpy(f2).cuda(), torch.from_numpy(w2).cuda(), tokens)
+    got, valid2 = ex.forward_device(torch.from_numpy(feat).cuda(),
+                                    torch.from_numpy(word_vecs).cuda(), tokens)
+    torch.cuda.synchronize()
+    assert valid.tolist() == valid2.tolist() and not valid2[5]
+    np.testing.assert_array_equal(got.cpu().numpy(), ref.cpu().numpy())
+    assert not np.array_equal(other.cpu().numpy(), ref.cpu().numpy())
+    assert ex.last_step_info()['num_questions'] == N
+
+
+@pytest.mark.parametrize('cluster', ['1', '2', '4'])
+def test_tree_cluster_sizes_agree(cluster, monkeypatch):
+    """The tree kernel gives the same scores whether a question runs on 1, 2 or 4 CTAs."""
+    from n2nmn_b200 import weights as wts
+    monkeypatch.setenv('N2NMN_TREE_CLUSTER', cluster)
+    N, H, Wd, D, T, C = 24, 10, 15, 512, 20, 28
+    feat, word_vecs = synth.make_inputs(N, H, Wd, D, T, seed=41)
+    W = wts.init_weights('clevr', H, Wd, D, C, seed=4, bias_std=0.1)
+    ex = make_executor('clevr', feat, word_vecs, C, W)
+    tokens = synth.expert_mix_tokens(ex.assembler, N, T)
+    scores, _ = ex.forward_tokens(tokens)
+    ref_s, _, _ = _oracle_scores('clevr', feat, word_vecs, C, W, tokens)
+    assert float(np.max(np.abs(scores.cpu().numpy() - ref_s))) <= 1e-3
+
+
 def test_host_e2e_entry_matches_device_path():
     from n2nmn_b200 import weights as wts
     N, H, Wd, D, T, C = 16, 10, 15, 512, 10, 28
