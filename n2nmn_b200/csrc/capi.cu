@@ -88,8 +88,10 @@ struct n2nmn_ctx {
   std::vector<Variable> vars;
   float* wbuf = nullptr;
   size_t wbuf_floats = 0;
-  float* proj_wt[NUM_PROJ_SETS] = {nullptr, nullptr};    // [Mp][Kp]
-  float* proj_bias[NUM_PROJ_SETS] = {nullptr, nullptr};  // [Mp]
+  float* proj_wt[NUM_PROJ_SETS] = {};      // [Mp][Kp], allocated for the sets the family owns
+  float* proj_bias[NUM_PROJ_SETS] = {};    // [Mp]
+  bool proj_used[NUM_PROJ_SETS] = {};
+  int num_store_sets = 0;
   // inputs
   bool bound = false;
   int N = 0, T = 0;
@@ -100,15 +102,16 @@ struct n2nmn_ctx {
   float* arena = nullptr;
   int arena_slots = 0;
   float* mbuf = nullptr;
+  int mbuf_slots = 0;
   float* scores_tmp = nullptr;
   TableSlot slots[kTableSlots];
   size_t table_cap = 0;
   int next_slot = 0;
   ProjTensorMaps tmaps;
-  bool tmap_b_ready[NUM_PROJ_SETS] = {false, false};
   EncodeTiledFn encode = nullptr;
   int node_smem_bytes = 0;
   int tree_cluster = 0;        // 0 = choose from the batch size; else forced (N2NMN_TREE_CLUSTER)
+  bool use_pdl = true;         // programmatic dependent launch between the three kernels
   n2nmn_sched module_sched;    // scratch schedule of n2nmn_module_fwd
   n2nmn_sched step_sched;      // scratch schedule of n2nmn_forward_tokens
   // e2e staging
@@ -134,7 +137,7 @@ void add_var(n2nmn_ctx* c, const std::string& name, std::vector<int64_t> shape, 
   v.count = 1;
   for (int64_t d : shape) v.count *= (size_t)d;
   v.offset = c->wbuf_floats;
-  const size_t stored = (kind == VK_PITCHED) ? (size_t)shape[0] * c->Mp : v.count;
+  const size_t stored = (kind == VK_PITCHED) ? v.count / (size_t)shape.back() * c->Mp : v.count;
   c->wbuf_floats += (stored + 3) & ~(size_t)3;
   c->vars.push_back(v);
 }
@@ -159,12 +162,12 @@ void build_variables(n2nmn_ctx* c) {
   add_layer(c, "FindModule/fc_text", {Dt, M}, &md.txt_w[TS_FIND], &md.txt_b[TS_FIND], -2);
   add_layer(c, "FindModule/conv_eltwise", {M, 1}, &md.elt_w[ES_FIND], &md.elt_b[ES_FIND]);
   if (g.family == N2NMN_VQA) {
-    add_layer(c, "TransformModule/conv_image", {D, M}, &md.proj_w[PS_FSP], nullptr, PS_FSP);
+    add_layer(c, "TransformModule/conv_image", {D, M}, &md.proj_w[PS_FSP_IMG], nullptr, PS_FSP_IMG);
     add_layer(c, "TransformModule/fc_text", {Dt, M}, &md.txt_w[TS_FSP], &md.txt_b[TS_FSP], -2);
-    add_layer(c, "TransformModule/fc_att", {D, M}, &md.att_w[AS_FSP], &md.att_b[AS_FSP], -2);
+    add_layer(c, "TransformModule/fc_att", {D, M}, &md.proj_w[PS_FSP_ATT], nullptr, PS_FSP_ATT);
     add_layer(c, "TransformModule/conv_eltwise", {M, 1}, &md.elt_w[ES_FSP], &md.elt_b[ES_FSP]);
   } else {
-    add_layer(c, "TransformModule/conv_maps", {k, k, 1, M}, &md.conv_k, &md.conv_b);
+    add_layer(c, "TransformModule/conv_maps", {k, k, 1, M}, &md.conv_k, &md.conv_b, -2);
     add_layer(c, "TransformModule/text_fc", {Dt, M}, &md.txt_w[TS_TRANSFORM],
               &md.txt_b[TS_TRANSFORM], -2);
     add_layer(c, "TransformModule/conv_eltwise", {M, 1}, &md.elt_w[ES_TRANSFORM],
@@ -175,9 +178,11 @@ void build_variables(n2nmn_ctx* c) {
     return;
   }
   if (g.family == N2NMN_CLEVR) {
-    add_layer(c, "FindSamePropertyModule/conv_image", {D, M}, &md.proj_w[PS_FSP], nullptr, PS_FSP);
+    add_layer(c, "FindSamePropertyModule/conv_image", {D, M}, &md.proj_w[PS_FSP_IMG], nullptr,
+              PS_FSP_IMG);
     add_layer(c, "FindSamePropertyModule/fc_text", {Dt, M}, &md.txt_w[TS_FSP], &md.txt_b[TS_FSP], -2);
-    add_layer(c, "FindSamePropertyModule/fc_att", {D, M}, &md.att_w[AS_FSP], &md.att_b[AS_FSP], -2);
+    add_layer(c, "FindSamePropertyModule/fc_att", {D, M}, &md.proj_w[PS_FSP_ATT], nullptr,
+              PS_FSP_ATT);
     add_layer(c, "FindSamePropertyModule/conv_eltwise", {M, 1}, &md.elt_w[ES_FSP],
               &md.elt_b[ES_FSP]);
     add_layer(c, "ExistModule/fc_scores", {3, C}, &md.sc_w[SS_EXIST], &md.sc_b[SS_EXIST]);
@@ -190,15 +195,15 @@ void build_variables(n2nmn_ctx* c) {
               &md.sc_b[SS_LESS]);
     add_layer(c, "SamePropertyModule/fc_text", {Dt, M}, &md.txt_w[TS_SAMEPROP],
               &md.txt_b[TS_SAMEPROP], -2);
-    add_layer(c, "SamePropertyModule/fc_att_0", {D, M}, &md.att_w[AS_SAMEPROP0],
-              &md.att_b[AS_SAMEPROP0], -2);
-    add_layer(c, "SamePropertyModule/fc_att_1", {D, M}, &md.att_w[AS_SAMEPROP1],
-              &md.att_b[AS_SAMEPROP1], -2);
+    add_layer(c, "SamePropertyModule/fc_att_0", {D, M}, &md.proj_w[PS_SP_ATT0], nullptr,
+              PS_SP_ATT0);
+    add_layer(c, "SamePropertyModule/fc_att_1", {D, M}, &md.proj_w[PS_SP_ATT1], nullptr,
+              PS_SP_ATT1);
     add_layer(c, "SamePropertyModule/fc_eltwise", {M, C}, &md.out_w[OS_SAMEPROP],
               &md.out_b[OS_SAMEPROP]);
   }
   add_layer(c, "DescribeModule/fc_text", {Dt, M}, &md.txt_w[TS_DESCRIBE], &md.txt_b[TS_DESCRIBE], -2);
-  add_layer(c, "DescribeModule/fc_att", {D, M}, &md.att_w[AS_DESCRIBE], &md.att_b[AS_DESCRIBE], -2);
+  add_layer(c, "DescribeModule/fc_att", {D, M}, &md.proj_w[PS_DESC_ATT], nullptr, PS_DESC_ATT);
   add_layer(c, "DescribeModule/fc_eltwise", {M, C}, &md.out_w[OS_DESCRIBE],
             &md.out_b[OS_DESCRIBE]);
 }
@@ -262,6 +267,8 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaS
     return fail(N2NMN_ERR_CAPACITY, "schedule tables exceed the context capacity");
   if ((int)S.text_t.size() > c->text_rows_cap)
     return fail(N2NMN_ERR_CAPACITY, "too many text nodes for this context");
+  if (S.num_mslots > c->mbuf_slots)
+    return fail(N2NMN_ERR_CAPACITY, "too many stored feature maps for this context");
   // ---- table residency
   TableSlot* slot = nullptr;
   for (int i = 0; i < kTableSlots; ++i)
@@ -324,6 +331,7 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaS
     p.elt_b = c->md.elt_b[ES_FIND];
     p.arena = arena;
     p.mslot = reinterpret_cast<const int32_t*>(d + o.mslot);
+    p.num_images = (int)(S.mslot.size() / NUM_PROJ_SETS);
     p.mbuf = c->mbuf;
     const int grid = std::min(p.num_work, c->num_sms);
     if (c->cfg.flags & N2NMN_FLAG_PROJ_FP32_SIMT) {
@@ -331,7 +339,18 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaS
       proj_simt_kernel<<<p.num_work, 256, smem, st>>>(p);
       prof_mark(c, "proj_simt_kernel", st);
     } else {
-      proj_umma_kernel<<<grid, kProjThreads, kProjSmemBytes, st>>>(c->tmaps, p);
+      cudaLaunchConfig_t lc;
+      std::memset(&lc, 0, sizeof(lc));
+      lc.gridDim = dim3((unsigned)grid);
+      lc.blockDim = dim3(kProjThreads);
+      lc.dynamicSmemBytes = kProjSmemBytes;
+      lc.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      lc.attrs = attr;
+      lc.numAttrs = c->use_pdl ? 1 : 0;
+      CUDA_TRY(cudaLaunchKernelEx(&lc, proj_umma_kernel, c->tmaps, p));
       prof_mark(c, "proj_umma_kernel", st);
     }
     ++c->launches;
@@ -362,13 +381,22 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaS
     lc.blockDim = dim3(kNodeThreads);
     lc.dynamicSmemBytes = (size_t)c->node_smem_bytes;
     lc.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cs;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cs > 1) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = (unsigned)cs;
+      attr[na].val.clusterDim.y = 1;
+      attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    if (c->use_pdl) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
     lc.attrs = attr;
-    lc.numAttrs = cs > 1 ? 1 : 0;
+    lc.numAttrs = na;
     if (ks3) CUDA_TRY(cudaLaunchKernelEx(&lc, tree_kernel<3>, nc, d_nodes, d_qptr, cs));
     else CUDA_TRY(cudaLaunchKernelEx(&lc, tree_kernel<5>, nc, d_nodes, d_qptr, cs));
     ++c->launches;
@@ -438,7 +466,11 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
   CUDA_TRY(cudaMemset(c->wbuf, 0, c->wbuf_floats * sizeof(float)));
   for (Variable& v : c->vars)
     if (v.slot) *v.slot = c->wbuf + v.offset;
+  for (const Variable& v : c->vars)
+    if (v.kind == VK_PROJ_W) c->proj_used[v.set] = true;
   for (int s = 0; s < NUM_PROJ_SETS; ++s) {
+    if (!c->proj_used[s]) continue;
+    if (s != PS_FIND) ++c->num_store_sets;
     CUDA_TRY(cudaMalloc(&c->proj_wt[s], (size_t)c->Mp * c->Kp * sizeof(float)));
     CUDA_TRY(cudaMemset(c->proj_wt[s], 0, (size_t)c->Mp * c->Kp * sizeof(float)));
     CUDA_TRY(cudaMalloc(&c->proj_bias[s], (size_t)c->Mp * sizeof(float)));
@@ -447,6 +479,8 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
     if (int rc = encode_2d(c, &c->tmaps.b[s], c->proj_wt[s], c->Kp, c->Mp, c->Kp, kBK, kBN))
       return rc;
   }
+  for (int s = 0; s < NUM_PROJ_SETS; ++s)      // sets the family lacks alias set 0 (never used)
+    if (!c->proj_used[s]) c->tmaps.b[s] = c->tmaps.b[PS_FIND];
   // workspaces
   const int NB = cfg->max_batch, TT = cfg->max_T;
   c->text_rows_cap = NB * TT;
@@ -456,7 +490,8 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
   c->tb.tau2 = c->tb.tauw + tb_floats;
   c->arena_slots = std::max(NB * TT, 3 * NB);
   CUDA_TRY(cudaMalloc(&c->arena, (size_t)c->arena_slots * c->HW * sizeof(float)));
-  CUDA_TRY(cudaMalloc(&c->mbuf, (size_t)NB * c->HW * c->Mp * sizeof(float)));
+  c->mbuf_slots = std::max(1, c->num_store_sets) * NB;
+  CUDA_TRY(cudaMalloc(&c->mbuf, (size_t)c->mbuf_slots * c->HW * c->Mp * sizeof(float)));
   CUDA_TRY(cudaMalloc(&c->scores_tmp, (size_t)NB * TT * cfg->num_choices * sizeof(float)));
   if (cfg->family == N2NMN_VQA || (cfg->D % 4) != 0) {
     CUDA_TRY(cudaMalloc(&c->feat_aug, (size_t)NB * c->HW * c->Kp * sizeof(float)));
@@ -466,8 +501,8 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
     const size_t nodes = (size_t)NB * TT;
     const size_t tiles = ((size_t)NB * c->HW + 127) / 128 + 1;
     c->table_cap = nodes * (sizeof(NodeRec) + 4 * 6) + (nodes / 8 + 8) * sizeof(TextGroup) +
-                   tiles * (TT / kMaxProjNodesPerPass + 2) * 2 * sizeof(ProjWork) +
-                   (size_t)NB * 16 + 4096;
+                   tiles * (TT / kMaxProjNodesPerPass + 1 + NUM_PROJ_SETS) * sizeof(ProjWork) +
+                   (size_t)NB * (8 + 4 * NUM_PROJ_SETS) + 4096;
     for (int i = 0; i < kTableSlots; ++i) {
       CUDA_TRY(cudaMallocHost(&c->slots[i].host, c->table_cap));
       CUDA_TRY(cudaMalloc(&c->slots[i].dev, c->table_cap));
@@ -475,8 +510,8 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
     }
   }
   // kernel attributes
-  const NodeSmem L = node_smem_layout(cfg->H, cfg->W, c->Dk, c->Mp, c->cfg.kernel_size,
-                                      cfg->map_dim);
+  const NodeSmem L = node_smem_layout(cfg->H, cfg->W, c->Mp, c->cfg.kernel_size, cfg->map_dim,
+                                      cfg->num_choices);
   c->node_smem_bytes = L.total * (int)sizeof(float);
   CUDA_TRY(cudaFuncSetAttribute(tree_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 c->node_smem_bytes));
@@ -492,6 +527,7 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
       proj_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
       (int)((kSimtRows * kSimtKChunk + kSimtRows * c->Mp) * sizeof(float))));
   c->module_sched.uid = g_uid++;
+  if (const char* e = std::getenv("N2NMN_NO_PDL")) c->use_pdl = (std::atoi(e) == 0);
   if (const char* e = std::getenv("N2NMN_TREE_CLUSTER")) {
     const int v = std::atoi(e);
     if (v == 1 || v == 2 || v == 4 || v == 8) c->tree_cluster = v;
@@ -539,9 +575,9 @@ int n2nmn_set_weight(n2nmn_ctx* c, const char* name, const float* src, const int
     for (int i = 0; i < ndim; ++i)
       if (shape[i] != v.shape[i]) return fail(N2NMN_ERR_ARG, std::string("shape mismatch for ") + name);
     if (v.kind == VK_PITCHED) {
-      pitch_rows_kernel<<<(unsigned)v.shape[0], 256, 0, st>>>(src, (int)v.shape[0],
-                                                            (int)v.shape[1], c->wbuf + v.offset,
-                                                            c->Mp);
+      const int rows = (int)(v.count / (size_t)v.shape.back());
+      pitch_rows_kernel<<<(unsigned)rows, 256, 0, st>>>(src, rows, (int)v.shape.back(),
+                                                      c->wbuf + v.offset, c->Mp);
     } else {
       CUDA_TRY(cudaMemcpyAsync(c->wbuf + v.offset, src, v.count * sizeof(float),
                                cudaMemcpyDeviceToDevice, st));
@@ -666,6 +702,7 @@ int n2nmn_compile_nodes(n2nmn_ctx* c, const int32_t* op, const int32_t* t_idx,
       r.out = is_ans[o] ? q : i;
       r.text = -1;
       r.aux = (o == OP_SCENE) ? scene_bits : -1;
+      r.aux2 = -1; r.pad = 0;
     }
   }
   if (int rc = finalize_schedule(c->shp, c->cfg.max_batch, &S)) {
@@ -765,6 +802,7 @@ int n2nmn_module_fwd(n2nmn_ctx* c, int op, const float* in0, const float* in1,
     r.out = is_ans[op] ? i : 2 * n + i;
     r.text = -1;
     r.aux = (op == OP_SCENE) ? scene_bits : -1;
+    r.aux2 = -1; r.pad = 0;
     S.q_ptr[i] = i;
   }
   S.q_ptr[n] = n;

@@ -17,21 +17,30 @@ enum Op : int {
 };
 
 // Weight-set indices.
-enum ProjSetId { PS_FIND = 0, PS_FSP = 1, NUM_PROJ_SETS = 2 };
+// Feature-grid contractions done on the tensor cores, one weight matrix [Dk][M] each:
+//   PS_FIND     FindModule/conv_image      -> consumed in the fused epilogue (never stored)
+//   PS_FSP_IMG  FindSameProperty/conv_image -> stored map m[p,:]
+//   PS_*_ATT*   the fc_att layers. fc_att(Σ_p s_p·X[p,:]) = Σ_p s_p·(X[p,:]·W_att + b) because the
+//               softmax weights s sum to one, so the per-image map G = X·W_att + b is computed once
+//               on the tensor cores and the node kernel only does the 150-row weighted sum.
+enum ProjSetId { PS_FIND = 0, PS_FSP_IMG, PS_FSP_ATT, PS_DESC_ATT, PS_SP_ATT0, PS_SP_ATT1,
+                 NUM_PROJ_SETS };
 enum TextSetId { TS_FIND = 0, TS_FSP, TS_TRANSFORM, TS_SAMEPROP, TS_DESCRIBE, NUM_TEXT_SETS };
-enum AttSetId { AS_FSP = 0, AS_SAMEPROP0, AS_SAMEPROP1, AS_DESCRIBE, NUM_ATT_SETS };
 enum OutSetId { OS_SAMEPROP = 0, OS_DESCRIBE, NUM_OUT_SETS };
 enum ScoreSetId { SS_EXIST = 0, SS_COUNT, SS_EQUAL, SS_MORE, SS_LESS, NUM_SCORE_SETS };
 enum EltSetId { ES_FIND = 0, ES_FSP, ES_TRANSFORM, NUM_ELT_SETS };
 
-// One expression-tree node as the kernels see it (32 bytes).
+// One expression-tree node as the kernels see it (40 bytes).
 struct NodeRec {
   int32_t op;
   int32_t t, b;      // time index (token position) and question / image index
   int32_t in0, in1;  // arena slots of the attention inputs (-1 if none)
   int32_t out;       // arena slot of the attention output, or score row for answer modules
   int32_t text;      // row in the text-projection buffers (-1 if the module takes no text)
-  int32_t aux;       // FindSameProperty: slot of the image's projected map in mbuf
+  int32_t aux;       // mbuf slot: FSP conv_image map / Describe fc_att map / SameProperty fc_att_0
+                     // (Scene: the bits of pos_val)
+  int32_t aux2;      // mbuf slot: FSP fc_att map / SameProperty fc_att_1
+  int32_t pad;
 };
 
 // Everything the kernels need to know about the model; pointers are device pointers into the
@@ -44,14 +53,12 @@ struct DevModel {
   // conv_image contraction: original [Dk][M] (fp32 CUDA-core path), bias padded to Mp
   const float* proj_w[NUM_PROJ_SETS];
   const float* proj_b[NUM_PROJ_SETS];
-  const float* txt_w[NUM_TEXT_SETS];   // [Dt][M]
+  const float* txt_w[NUM_TEXT_SETS];   // [Dt][Mp] (row pitch Mp, zero padded)
   const float* txt_b[NUM_TEXT_SETS];   // [M]
   const float* elt_w[NUM_ELT_SETS];    // conv_eltwise weights [M]
   const float* elt_b[NUM_ELT_SETS];    // [1]
-  const float* conv_k;                 // conv_maps [k*k][M]
+  const float* conv_k;                 // conv_maps [k*k][Mp] (row pitch Mp, zero padded)
   const float* conv_b;                 // [M]
-  const float* att_w[NUM_ATT_SETS];    // fc_att [Dk][M]
-  const float* att_b[NUM_ATT_SETS];
   const float* out_w[NUM_OUT_SETS];    // fc_eltwise [M][C]
   const float* out_b[NUM_OUT_SETS];
   const float* sc_w[NUM_SCORE_SETS];   // fc_scores [L][C]
@@ -69,6 +76,17 @@ struct TextBufs {
 struct TextGroup { int32_t set, start, count, pad; };   // <= kTextRowsPerCta rows of one text set
 constexpr int kTextRowsPerCta = 8;
 struct ProjWork { int32_t row0, pass, set, pad; };      // one 128-row tile of the contraction
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization
+// attribute may start while its predecessor in the stream is still running; it must call
+// pdl_wait() before touching anything the predecessor writes. pdl_trigger() lets the successor's
+// CTAs be scheduled as early as possible.
+__device__ __forceinline__ void pdl_trigger() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -33,34 +33,38 @@ struct NodeCtx {
 constexpr int kNodeScratch = 2048;   // floats
 
 // Shared-memory carve-up (floats); the host computes the same layout to size the launch.
+constexpr int kHeadCapFloats = 12288;   // answer-head weights are staged in smem up to 48 KB
+
 struct NodeSmem {
-  int HWp, pad, f, v, z, k, total;
+  int HWp, pad, v, z, k, head, total;
 };
-__host__ __device__ inline NodeSmem node_smem_layout(int H, int W, int Dk, int Mp, int ksize,
-                                                     int M) {
+__host__ __device__ inline NodeSmem node_smem_layout(int H, int W, int Mp, int ksize, int M,
+                                                     int C) {
   NodeSmem s;
   const int HW = H * W;
   s.HWp = (HW + 3) & ~3;
   s.pad = ((H + ksize - 1) * (W + ksize - 1) + 3) & ~3;
-  s.f = 2 * ((Dk + 3) & ~3);
   s.v = 5 * Mp;                      // v0 v1 v2 + two partial-sum buffers
   s.z = (2 * (HW + 2) + 3) & ~3;
-  s.k = ksize * ksize * ((M + 127) / 128 * 128);
-  s.total = 2 * s.HWp + s.pad + s.f + kNodeScratch + s.v + 64 + s.z + s.k;
+  s.k = ksize * ksize * Mp;
+  const int rows = (2 * (HW + 2) > M) ? 2 * (HW + 2) : M;
+  s.head = (rows * C <= kHeadCapFloats) ? ((rows * C + 3) & ~3) : 0;
+  s.total = 2 * s.HWp + s.pad + kNodeScratch + s.v + 64 + s.z + s.k + s.head;
   return s;
 }
 
 struct SmemPtrs {
-  float *a0, *a1, *pad, *f, *scratch, *v0, *v1, *v2, *part0, *part1, *red, *z, *k;
+  float *a0, *a1, *pad, *scratch, *v0, *v1, *v2, *part0, *part1, *red, *z, *k, *head;
+  bool k_ready;        // conv filter bank already staged in k
+  const float* head_w; // staged answer-head weights (nullptr: read them from global memory)
 };
 __device__ __forceinline__ SmemPtrs carve(float* base, const DevModel& md) {
-  const NodeSmem L = node_smem_layout(md.H, md.W, md.Dk, md.Mp, md.ksize, md.M);
+  const NodeSmem L = node_smem_layout(md.H, md.W, md.Mp, md.ksize, md.M, md.C);
   SmemPtrs s;
   s.a0 = base;
   s.a1 = s.a0 + L.HWp;
   s.pad = s.a1 + L.HWp;
-  s.f = s.pad + L.pad;
-  s.scratch = s.f + L.f;
+  s.scratch = s.pad + L.pad;
   s.v0 = s.scratch + kNodeScratch;
   s.v1 = s.v0 + md.Mp;
   s.v2 = s.v1 + md.Mp;
@@ -69,7 +73,33 @@ __device__ __forceinline__ SmemPtrs carve(float* base, const DevModel& md) {
   s.red = s.part1 + md.Mp;
   s.z = s.red + 64;
   s.k = s.z + L.z;
+  s.head = L.head ? s.k + L.k : nullptr;
+  s.k_ready = false;
+  s.head_w = nullptr;
   return s;
+}
+
+// ---- asynchronous global -> shared staging (cp.async; completes behind other work) --------------
+__device__ __forceinline__ void cp_async_4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
+               ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+               ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+// n floats, issued by the whole CTA; 16-byte chunks when both sides allow it.
+__device__ __forceinline__ void stage_async(float* dst, const float* src, int n) {
+  const bool wide = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0
+                    && (n & 3) == 0;
+  if (wide) {
+    for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4) cp_async_16(dst + i, src + i);
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) cp_async_4(dst + i, src + i);
+  }
 }
 
 // Position of this CTA inside the cluster that evaluates the node.
@@ -111,54 +141,6 @@ __device__ __forceinline__ void coop_range(const Coop& co, int n, int& q0, int& 
   const int per = (n + co.size - 1) / co.size;
   q0 = min(n, co.rank * per);
   q1 = min(n, q0 + per);
-}
-
-// att_feat = reduce_sum(image_feat_grid * att_softmax, [1,2]) (nmn3_modules.py:174) for the
-// channel quads [g0, g1) of the node's image, read in place from the bound feature grid (the
-// tf.gather copy of :49-51 is never materialised). f[4*(g-g0) ..] receives the pooled values.
-// Threads form a (quad, pixel-slice) grid so that every thread has many independent loads.
-__device__ __forceinline__ void attention_pool(const DevModel& md, int b, const float* soft,
-                                               int g0, int g1, float* f, float* scratch) {
-  const int HW = md.HW, pitch4 = md.feat_pitch >> 2;
-  const int ng = g1 - g0;
-  const float4* X = reinterpret_cast<const float4*>(md.feat + (size_t)b * HW * md.feat_pitch) + g0;
-  const int nthreads = blockDim.x;
-  if (ng <= 0) { __syncthreads(); return; }
-  if (ng >= nthreads) {
-    for (int g = threadIdx.x; g < ng; g += nthreads) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-      for (int p = 0; p < HW; ++p) {
-        const float4 x = __ldg(X + (size_t)p * pitch4 + g);
-        const float s = soft[p];
-        acc.x = fmaf(s, x.x, acc.x); acc.y = fmaf(s, x.y, acc.y);
-        acc.z = fmaf(s, x.z, acc.z); acc.w = fmaf(s, x.w, acc.w);
-      }
-      reinterpret_cast<float4*>(f)[g] = acc;
-    }
-  } else {
-    int slices = nthreads / ng;
-    if (slices * ng * 4 > kNodeScratch) slices = kNodeScratch / (ng * 4);
-    const int g = threadIdx.x % ng, sl = threadIdx.x / ng;
-    if (sl < slices) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-      for (int p = sl; p < HW; p += slices) {
-        const float4 x = __ldg(X + (size_t)p * pitch4 + g);
-        const float s = soft[p];
-        acc.x = fmaf(s, x.x, acc.x); acc.y = fmaf(s, x.y, acc.y);
-        acc.z = fmaf(s, x.z, acc.z); acc.w = fmaf(s, x.w, acc.w);
-      }
-      reinterpret_cast<float4*>(scratch)[sl * ng + g] = acc;
-    }
-    __syncthreads();
-    for (int d = threadIdx.x; d < ng * 4; d += nthreads) {
-      float s = 0.f;
-      for (int k = 0; k < slices; ++k) s += scratch[k * ng * 4 + d];
-      f[d] = s;
-    }
-  }
-  __syncthreads();
 }
 
 // part[c] = Σ_{k in [k0,k1)} in[k-k0] · W[k*Mp + c] for all c < Mp (W has row pitch Mp, zero
@@ -207,20 +189,18 @@ __device__ __forceinline__ void gemv_partial(const float* in, int k0, int k1,
   __syncthreads();
 }
 
-// phi = fc_att(pooled(att)) for one attention input, cooperatively over the cluster:
-//   pooled channels are split over the CTAs, each CTA multiplies its channel slice with the
-//   matching rows of W_att, and `part` receives this CTA's partial sums (all Mp columns).
+// phi = fc_att(reduce_sum(image_feat_grid * softmax(att), [1,2])) (nmn3_modules.py:170-176) for one
+// attention input, cooperatively over the cluster. The projection kernel has already stored
+// G = X_b·W_att + b_att for the node's image, and Σ_p s_p = 1, so phi = Σ_p s_p·G[p,:]: the pixel
+// rows of G are split over the CTAs and `part` receives this CTA's partial sums (all Mp columns).
 // The caller exchanges the partials after a cluster sync (sum_partials).
-__device__ __forceinline__ void pooled_fc_partial(const DevModel& md, const Coop& co, int b,
-                                                  float* soft, const float* W, float* f,
-                                                  float* part, const SmemPtrs& s) {
+__device__ __forceinline__ void pooled_fc_partial(const DevModel& md, const Coop& co,
+                                                  const float* G, float* soft, float* part,
+                                                  const SmemPtrs& s) {
   softmax_inplace(soft, md.HW, s.red);
-  const int ng = (md.Dk + 3) >> 2;
-  int g0, g1;
-  coop_range(co, ng, g0, g1);
-  attention_pool(md, b, soft, g0, g1, f, s.scratch);
-  const int k0 = g0 * 4, k1 = min(md.Dk, g1 * 4);
-  gemv_partial(f, k0, max(k0, k1), W, md.Mp, part, s.scratch);
+  int p0, p1;
+  coop_range(co, md.HW, p0, p1);
+  gemv_partial(soft + p0, p0, p1, G, md.Mp, part, s.scratch);
 }
 
 // out[c] = bias[c] + Σ_ranks part_r[c] (c < M; zero beyond), reading the peers' partial buffers
@@ -231,7 +211,7 @@ __device__ __forceinline__ void sum_partials(const Coop& co, const float* part,
   for (int c = threadIdx.x; c < Mp; c += blockDim.x) {
     float v = 0.f;
     if (c < M) {
-      v = bias[c];
+      v = bias ? bias[c] : 0.f;
       for (int r = 0; r < co.size; ++r) v += co.peer(part, r)[c];
     }
     out[c] = v;
@@ -250,7 +230,7 @@ __device__ __forceinline__ void small_fc(const float* z, int L, const float* __r
     float acc = 0.f;
     if (c < C) {
 #pragma unroll 4
-      for (int k = g; k < L; k += G) acc = fmaf(z[k], __ldg(W + (size_t)k * C + c), acc);
+      for (int k = g; k < L; k += G) acc = fmaf(z[k], W[(size_t)k * C + c], acc);
     }
     scratch[g * 32 + lane] = acc;
     __syncthreads();
@@ -285,7 +265,7 @@ __device__ __forceinline__ void eval_transform(const NodeCtx& c, const NodeRec& 
   const DevModel& md = c.md;
   const int H = md.H, W = md.W, HW = md.HW, M = md.M;
   const int PW = W + KS - 1, PH = H + KS - 1, R = (KS - 1) / 2;
-  const int Mq = (M + 127) / 128 * 128;
+  const int Mq = md.Mp;   // filter bank and vectors are padded to the row pitch (zeros)
   for (int i = threadIdx.x; i < PH * PW; i += blockDim.x) s.pad[i] = 0.f;
   __syncthreads();
   const float* src = c.arena + (size_t)nd.in0 * HW;
@@ -293,10 +273,7 @@ __device__ __forceinline__ void eval_transform(const NodeCtx& c, const NodeRec& 
     const int y = p / W, x = p - y * W;
     s.pad[(y + R) * PW + x + R] = src[p];
   }
-  for (int i = threadIdx.x; i < KS * KS * Mq; i += blockDim.x) {
-    const int tap = i / Mq, ch = i - tap * Mq;
-    s.k[i] = (ch < M) ? __ldg(md.conv_k + tap * M + ch) : 0.f;
-  }
+  if (!s.k_ready) stage_async(s.k, md.conv_k, KS * KS * Mq);
   const float* tau = c.tb.tau + (size_t)nd.text * md.Mp;
   for (int ch = threadIdx.x; ch < Mq; ch += blockDim.x) {
     const bool live = ch < M;
@@ -304,6 +281,7 @@ __device__ __forceinline__ void eval_transform(const NodeCtx& c, const NodeRec& 
     s.v1[ch] = live ? md.elt_w[ES_TRANSFORM][ch] : 0.f;
     s.v2[ch] = live ? md.conv_b[ch] : 0.f;
   }
+  cp_async_commit_wait_all();
   __syncthreads();
   const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int gwarp = co.rank * nwarps + (threadIdx.x >> 5), gwarps = co.size * nwarps;
@@ -347,9 +325,9 @@ __device__ __forceinline__ void eval_find_same_property(const NodeCtx& c, const 
   const int HW = md.HW, Mp = md.Mp, M = md.M;
   load_att(s.a0, c.arena, nd.in0, HW);
   __syncthreads();
-  pooled_fc_partial(md, co, nd.b, s.a0, md.att_w[AS_FSP], s.f, s.part0, s);
+  pooled_fc_partial(md, co, c.mbuf + (size_t)nd.aux2 * HW * Mp, s.a0, s.part0, s);
   co.sync();
-  sum_partials(co, s.part0, md.att_b[AS_FSP], s.v0, M, Mp);
+  sum_partials(co, s.part0, nullptr, s.v0, M, Mp);
   const float* tauw = c.tb.tauw + (size_t)nd.text * Mp;   // τ∘w2
   const float* tau = c.tb.tau + (size_t)nd.text * Mp;
   for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
@@ -392,7 +370,7 @@ __device__ __forceinline__ void normalize_and_score(const NodeCtx& c, const Node
   const float inv = rsqrtf(fmaxf(ss, kEps));
   for (int ch = threadIdx.x; ch < md.M; ch += blockDim.x) e[ch] *= inv;
   __syncthreads();
-  small_fc(e, md.M, md.out_w[out_set], md.out_b[out_set], md.C,
+  small_fc(e, md.M, s.head_w ? s.head_w : md.out_w[out_set], md.out_b[out_set], md.C,
            c.scores + (size_t)nd.out * md.C, s.scratch);
 }
 
@@ -402,10 +380,10 @@ __device__ __forceinline__ void eval_describe(const NodeCtx& c, const NodeRec& n
   const DevModel& md = c.md;
   load_att(s.a0, c.arena, nd.in0, md.HW);
   __syncthreads();
-  pooled_fc_partial(md, co, nd.b, s.a0, md.att_w[AS_DESCRIBE], s.f, s.part0, s);
+  pooled_fc_partial(md, co, c.mbuf + (size_t)nd.aux * md.HW * md.Mp, s.a0, s.part0, s);
   co.sync();
   if (co.rank != 0) return;   // the tail is tiny: one CTA finishes it
-  sum_partials(co, s.part0, md.att_b[AS_DESCRIBE], s.v0, md.M, md.Mp);
+  sum_partials(co, s.part0, nullptr, s.v0, md.M, md.Mp);
   const float* tau = c.tb.tau + (size_t)nd.text * md.Mp;
   for (int ch = threadIdx.x; ch < md.M; ch += blockDim.x) s.v1[ch] = tau[ch] * s.v0[ch];
   __syncthreads();
@@ -419,13 +397,13 @@ __device__ __forceinline__ void eval_same_property(const NodeCtx& c, const NodeR
   load_att(s.a0, c.arena, nd.in0, md.HW);
   load_att(s.a1, c.arena, nd.in1, md.HW);
   __syncthreads();
-  const int Dkp = (md.Dk + 3) & ~3;
-  pooled_fc_partial(md, co, nd.b, s.a0, md.att_w[AS_SAMEPROP0], s.f, s.part0, s);
-  pooled_fc_partial(md, co, nd.b, s.a1, md.att_w[AS_SAMEPROP1], s.f + Dkp, s.part1, s);
+  const size_t map_floats = (size_t)md.HW * md.Mp;
+  pooled_fc_partial(md, co, c.mbuf + nd.aux * map_floats, s.a0, s.part0, s);
+  pooled_fc_partial(md, co, c.mbuf + nd.aux2 * map_floats, s.a1, s.part1, s);
   co.sync();
   if (co.rank != 0) return;
-  sum_partials(co, s.part0, md.att_b[AS_SAMEPROP0], s.v0, md.M, md.Mp);
-  sum_partials(co, s.part1, md.att_b[AS_SAMEPROP1], s.v1, md.M, md.Mp);
+  sum_partials(co, s.part0, nullptr, s.v0, md.M, md.Mp);
+  sum_partials(co, s.part1, nullptr, s.v1, md.M, md.Mp);
   const float* tau = c.tb.tau + (size_t)nd.text * md.Mp;
   for (int ch = threadIdx.x; ch < md.M; ch += blockDim.x)
     s.v2[ch] = s.v0[ch] * tau[ch] * s.v1[ch];
@@ -462,8 +440,8 @@ __device__ __forceinline__ void eval_small_answer(const NodeCtx& c, const NodeRe
         : (nd.op == OP_MORE_NUM) ? SS_MORE : SS_LESS;
   }
   __syncthreads();
-  small_fc(s.z, L, md.sc_w[set], md.sc_b[set], md.C, c.scores + (size_t)nd.out * md.C,
-           s.scratch);
+  small_fc(s.z, L, s.head_w ? s.head_w : md.sc_w[set], md.sc_b[set], md.C,
+           c.scores + (size_t)nd.out * md.C, s.scratch);
 }
 
 // Evaluates one node with the CTAs of `co`. Every CTA of the cluster must call it (the heavy
@@ -499,10 +477,10 @@ __device__ __forceinline__ void eval_node(const NodeCtx& c, const NodeRec& nd, c
     }
     case OP_TRANSFORM: eval_transform<KS>(c, nd, s, co); break;
     case OP_FIND_SAME_PROPERTY: eval_find_same_property(c, nd, s, co); break;
-    case OP_DESCRIBE: eval_describe(c, nd, s, co); break;
-    case OP_SAME_PROPERTY: eval_same_property(c, nd, s, co); break;
+    case OP_DESCRIBE: cp_async_commit_wait_all(); eval_describe(c, nd, s, co); break;
+    case OP_SAME_PROPERTY: cp_async_commit_wait_all(); eval_same_property(c, nd, s, co); break;
     default:
-      if (co.rank == 0) eval_small_answer(c, nd, s);
+      if (co.rank == 0) { cp_async_commit_wait_all(); eval_small_answer(c, nd, s); }
       break;
   }
 }
@@ -514,12 +492,46 @@ __global__ void __launch_bounds__(kNodeThreads)
 tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* __restrict__ q_ptr,
             int csize) {
   extern __shared__ __align__(16) float node_smem[];
-  const SmemPtrs s = carve(node_smem, c.md);
+  SmemPtrs s = carve(node_smem, c.md);
   Coop co;
   co.size = csize;
   co.rank = (csize > 1) ? (int)cg::this_cluster().block_rank() : 0;
   const int q = blockIdx.x / csize;
   const int beg = q_ptr[q], end = q_ptr[q + 1];
+  if (beg < end) {
+    // Prologue: start fetching the parameters this question will need (conv filter bank for
+    // Transform nodes, the root's answer-head weights on rank 0) while the first nodes run.
+    bool has_transform = false;
+    for (int i = beg; i < end; ++i) has_transform |= (nodes[i].op == OP_TRANSFORM);
+    if (has_transform) {
+      stage_async(s.k, c.md.conv_k, KS * KS * c.md.Mp);
+      s.k_ready = true;
+    }
+    if (co.rank == 0 && s.head != nullptr) {
+      const int rop = nodes[end - 1].op;
+      const DevModel& md = c.md;
+      const float* w = nullptr;
+      int rows = 0;
+      switch (rop) {
+        case OP_EXIST: w = md.sc_w[SS_EXIST]; rows = 3; break;
+        case OP_COUNT: w = md.sc_w[SS_COUNT]; rows = md.HW + 2; break;
+        case OP_EQUAL_NUM: w = md.sc_w[SS_EQUAL]; rows = 2 * (md.HW + 2); break;
+        case OP_MORE_NUM: w = md.sc_w[SS_MORE]; rows = 2 * (md.HW + 2); break;
+        case OP_LESS_NUM: w = md.sc_w[SS_LESS]; rows = 2 * (md.HW + 2); break;
+        case OP_SAME_PROPERTY: w = md.out_w[OS_SAMEPROP]; rows = md.M; break;
+        case OP_DESCRIBE: w = md.out_w[OS_DESCRIBE]; rows = md.M; break;
+        default: break;
+      }
+      if (w) {
+        stage_async(s.head, w, rows * md.C);
+        s.head_w = s.head;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  // Everything above reads only weights and the launch tables. The attention arena, the stored
+  // maps and the text projections come from the preceding kernels (PDL: they may still run).
+  pdl_wait();
   if (beg == end) {   // invalid layout: zeros(num_choices) (models_clevr/nmn3_model.py:144-155)
     if (co.rank == 0)
       for (int i = threadIdx.x; i < c.md.C; i += blockDim.x)
@@ -539,7 +551,8 @@ __global__ void __launch_bounds__(kNodeThreads)
 wave_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes,
             const int32_t* __restrict__ wave_nodes, int first) {
   extern __shared__ __align__(16) float node_smem[];
-  const SmemPtrs s = carve(node_smem, c.md);
+  const SmemPtrs s = carve(node_smem, c.md);   // nothing pre-staged: parameters come from L2
+  pdl_wait();
   const NodeRec nd = nodes[wave_nodes[first + blockIdx.x]];
   Coop co;
   co.rank = 0; co.size = 1;

@@ -8,8 +8,9 @@
 //   PS_FIND : every Find / Filter node of the image reduces the row on the fly
 //               att[p] = Σ_c m[p,c]·(τ∘w2)[c] · rsqrt(max(Σ_c m[p,c]²·τ²[c], 1e-12)) + b2
 //             (l2_normalize + conv_eltwise, nmn3_modules.py:107-108) — m never reaches HBM;
-//   PS_FSP  : FindSameProperty needs φ (a function of its input attention) before it can reduce,
-//             so rows of images that host such nodes are stored to `mbuf` for the node kernel.
+//   others  : rows of images that host a consumer (FindSameProperty's conv_image map, or one of
+//             the fc_att maps, see ProjSetId) are stored to `mbuf` (bias included) for the node
+//             kernel.
 #pragma once
 #include "common.cuh"
 
@@ -33,8 +34,9 @@ struct ProjParams {
   const float* tau2;
   const float* elt_b;         // conv_eltwise bias of FindModule, [1]
   float* arena;               // [slots][HW]
-  // PS_FSP store
-  const int32_t* mslot;       // [N] -> slot in mbuf or -1
+  // stored sets
+  const int32_t* mslot;       // [NUM_PROJ_SETS][num_images] -> slot in mbuf or -1
+  int num_images;
   float* mbuf;                // [slots][HW][Mp]
 };
 

@@ -13,6 +13,8 @@ constexpr int kSimtMaxColIters = 4;  // Mp <= 1024
 __global__ void __launch_bounds__(256)
 proj_simt_kernel(ProjParams p) {
   extern __shared__ float smem[];
+  pdl_trigger();
+  pdl_wait();
   float* xs = smem;                                  // [kSimtRows][kSimtKChunk]
   float* ms = smem + kSimtRows * kSimtKChunk;        // [kSimtRows][Mp]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -87,7 +89,7 @@ proj_simt_kernel(ProjParams p) {
                   num * rsqrtf(fmaxf(den, kEps)) + p.elt_b[0];
           }
         } else {
-          const int slot = p.mslot[b];
+          const int slot = p.mslot[wk.set * p.num_images + b];
           if (slot >= 0) {
             float* dst = p.mbuf + ((size_t)slot * p.HW + pix) * p.Mp;
             for (int c = lane; c < p.Mp; c += 32) dst[c] = mrow[c];

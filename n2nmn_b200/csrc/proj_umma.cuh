@@ -61,11 +61,11 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();   // let the node kernel's CTAs start prefetching their parameters
 
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tensormap(&tm.a);
-    ptx::prefetch_tensormap(&tm.b[0]);
-    ptx::prefetch_tensormap(&tm.b[1]);
+    for (int i = 0; i < NUM_PROJ_SETS; ++i) ptx::prefetch_tensormap(&tm.b[i]);
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -139,6 +139,9 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
     const int etid = threadIdx.x - 64;         // 0..127 among the epilogue threads
     const bool staged = p.HW >= kBM - 1;       // a tile then spans at most two images
     uint32_t it = 0;
+    // tauw / tau2 come from the text-projection kernel, which may still be running (PDL); the
+    // TMA / MMA warps above never touch its output and start immediately.
+    pdl_wait();
     for (int wi = blockIdx.x; wi < p.num_work; wi += gridDim.x) {
       const ProjWork wk = p.work[wi];
       const int row = wk.row0 + trow;
@@ -156,7 +159,7 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
           n_nodes = min(p.img_ptr[b + 1] - e_beg, kMaxProjNodesPerPass);
           n_nodes = max(n_nodes, 0);
         } else {
-          const int slot = p.mslot[b];
+          const int slot = p.mslot[wk.set * p.num_images + b];
           if (slot >= 0) mdst = p.mbuf + ((size_t)slot * p.HW + pix) * p.Mp;
         }
       }

@@ -77,6 +77,7 @@ int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
         nd.rec.in0 = nd.rec.in1 = -1;
         nd.rec.text = -1;
         nd.rec.aux = (op == OP_SCENE) ? scene_bits : -1;
+        nd.rec.aux2 = -1; nd.rec.pad = 0;
         nd.depth = 1;
         nd.tset = text_set_of(op);
         // operands come off right-to-left: the last popped is input_0
@@ -148,43 +149,60 @@ int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out) 
       S.groups.push_back(g);
     }
 
-  // ---- projection work: fused Find/Filter consumers per image, stored maps for FSP images
+  // ---- projection work: fused Find/Filter consumers per image; stored maps for the images that
+  //      host a FindSameProperty / Describe / SameProperty node (one mbuf slot per image and set)
   const int HW = shp.H * shp.W;
   S.img_ptr.assign(N + 1, 0);
-  S.mslot.assign(N, -1);
-  for (const NodeRec& r : S.nodes) {
-    if (r.op == OP_FIND || r.op == OP_FILTER) ++S.img_ptr[r.b + 1];
-    if (r.op == OP_FIND_SAME_PROPERTY && S.mslot[r.b] < 0) S.mslot[r.b] = S.num_mslots++;
+  S.mslot.assign((size_t)NUM_PROJ_SETS * N, -1);
+  auto want = [&](int set, int b) -> int {
+    int32_t& slot = S.mslot[(size_t)set * N + b];
+    if (slot < 0) slot = S.num_mslots++;
+    return slot;
+  };
+  for (NodeRec& r : S.nodes) {
+    switch (r.op) {
+      case OP_FIND: case OP_FILTER: ++S.img_ptr[r.b + 1]; break;
+      case OP_FIND_SAME_PROPERTY:
+        r.aux = want(PS_FSP_IMG, r.b); r.aux2 = want(PS_FSP_ATT, r.b); break;
+      case OP_DESCRIBE: r.aux = want(PS_DESC_ATT, r.b); break;
+      case OP_SAME_PROPERTY:
+        r.aux = want(PS_SP_ATT0, r.b); r.aux2 = want(PS_SP_ATT1, r.b); break;
+      default: break;
+    }
   }
   for (int n = 0; n < N; ++n) S.img_ptr[n + 1] += S.img_ptr[n];
   S.num_find_nodes = S.img_ptr[N];
   S.node_text.assign(S.num_find_nodes, 0);
   S.node_out.assign(S.num_find_nodes, 0);
   {
-    std::vector<int32_t> fill(S.img_ptr.begin(), S.img_ptr.end() - 1);
-    for (NodeRec& r : S.nodes) {
+    static thread_local std::vector<int32_t> fill;
+    fill.assign(S.img_ptr.begin(), S.img_ptr.end() - 1);
+    for (const NodeRec& r : S.nodes) {
       if (r.op == OP_FIND || r.op == OP_FILTER) {
         const int e = fill[r.b]++;
         S.node_text[e] = r.text;
         S.node_out[e] = r.out;
       }
-      if (r.op == OP_FIND_SAME_PROPERTY) r.aux = S.mslot[r.b];
     }
   }
   const int total_rows = N * HW;
   const int num_tiles = (total_rows + 127) / 128;
-  int u_find = 0, u_fsp = 0;
+  int u_set[NUM_PROJ_SETS] = {0}, u_any = 0;
   for (int n = 0; n < N; ++n) {
-    if (S.img_ptr[n + 1] > S.img_ptr[n]) ++u_find;
-    if (S.mslot[n] >= 0) ++u_fsp;
+    bool any = S.img_ptr[n + 1] > S.img_ptr[n];
+    if (any) ++u_set[PS_FIND];
+    for (int set = 1; set < NUM_PROJ_SETS; ++set)
+      if (S.mslot[(size_t)set * N + n] >= 0) { ++u_set[set]; any = true; }
+    if (any) ++u_any;
   }
   for (int set = 0; set < NUM_PROJ_SETS; ++set) {
+    if (u_set[set] == 0) continue;
     for (int tile = 0; tile < num_tiles; ++tile) {
       const int r0 = tile * 128, r1 = std::min(total_rows, r0 + 128) - 1;
       int max_nodes = 0;
       for (int b = r0 / HW; b <= r1 / HW; ++b) {
         if (set == PS_FIND) max_nodes = std::max(max_nodes, S.img_ptr[b + 1] - S.img_ptr[b]);
-        else if (S.mslot[b] >= 0) max_nodes = 1;
+        else if (S.mslot[(size_t)set * N + b] >= 0) max_nodes = 1;
       }
       const int passes = (max_nodes + kMaxProjNodesPerPass - 1) / kMaxProjNodesPerPass;
       for (int pass = 0; pass < passes; ++pass) {
@@ -212,9 +230,7 @@ int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out) 
   const int64_t contraction = 2 * hw * D * M, tail = 6 * hw * M, txt_f = 2 * Dt * M;
   const int64_t pool_f = 2 * hw * D + 2 * D * M;
   int64_t node_bytes = 0, node_flops = 0;      // what the node kernels move / compute
-  int questions_reading_feat = 0;
   for (int n = 0; n < NQ; ++n) {
-    bool reads = false;
     for (int i = S.q_ptr[n]; i < S.q_ptr[n + 1]; ++i) {
       const int op = S.nodes[i].op;
       int64_t rb = 0, wb = 0, fl = 0, kb = 0, kf = 0;   // per-node figure / node-kernel share
@@ -224,8 +240,7 @@ int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out) 
         case OP_FILTER: rb = tile_b + txt_b + att_b; wb = att_b; fl = contraction + txt_f + tail + hw;
           kb = 3 * att_b; kf = hw; break;
         case OP_FIND_SAME_PROPERTY: rb = tile_b + txt_b + att_b; wb = att_b;
-          fl = contraction + txt_f + tail + pool_f; kb = 2 * att_b + hw * M * 4; kf = tail + pool_f;
-          reads = true; break;
+          fl = contraction + txt_f + tail + pool_f; kb = 2 * att_b + 2 * hw * M * 4; kf = tail + 2 * hw * M; break;
         case OP_TRANSFORM: {
           const int64_t stencil = 2 * hw * shp.ksize * shp.ksize * M;
           rb = att_b + txt_b; wb = att_b; fl = stencil + txt_f + tail;
@@ -237,28 +252,32 @@ int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out) 
         case OP_EQUAL_NUM: case OP_MORE_NUM: case OP_LESS_NUM:
           rb = 2 * att_b; wb = C * 4; fl = 4 * (hw + 2) * C; kb = rb + wb; kf = fl; break;
         case OP_SAME_PROPERTY: rb = tile_b + txt_b + 2 * att_b; wb = C * 4;
-          fl = 2 * pool_f + txt_f + 2 * M * C; kb = 2 * att_b + wb; kf = 2 * pool_f + 2 * M * C;
-          reads = true; break;
+          fl = 2 * pool_f + txt_f + 2 * M * C; kb = 2 * att_b + wb + 2 * hw * M * 4;
+          kf = 4 * hw * M + 2 * M * C; break;
         case OP_DESCRIBE: rb = tile_b + txt_b + att_b; wb = C * 4;
-          fl = pool_f + txt_f + 2 * M * C; kb = att_b + wb; kf = pool_f + 2 * M * C;
-          reads = true; break;
+          fl = pool_f + txt_f + 2 * M * C; kb = att_b + wb + hw * M * 4;
+          kf = 2 * hw * M + 2 * M * C; break;
       }
       S.per_node_bytes += rb + wb;
       S.per_node_flops += fl;
       node_bytes += kb;
       node_flops += kf;
     }
-    if (reads) ++questions_reading_feat;
   }
   int sets_used = 0;
   for (int s = 0; s < NUM_TEXT_SETS; ++s) sets_used += set_count[s] > 0;
   S.kbytes[0] = (int64_t)num_text * (txt_b + M * 4) + (int64_t)sets_used * Dt * M * 4;
   S.kflops[0] = (int64_t)num_text * txt_f;
-  S.kbytes[1] = (int64_t)u_find * tile_b + (int64_t)S.num_find_nodes * (M * 4 + att_b) +
-                (u_find ? D * M * 4 : 0) +
-                (int64_t)u_fsp * (tile_b + hw * M * 4) + (u_fsp ? D * M * 4 : 0);
-  S.kflops[1] = (int64_t)(u_find + u_fsp) * contraction + (int64_t)S.num_find_nodes * tail;
-  S.kbytes[2] = node_bytes + (int64_t)questions_reading_feat * tile_b;
+  // projection launch: every distinct feature tile once, one weight matrix per set in use,
+  // Find outputs + text operands, stored maps of the other sets
+  S.kbytes[1] = (int64_t)u_any * tile_b + (int64_t)S.num_find_nodes * (M * 4 + att_b);
+  S.kflops[1] = (int64_t)S.num_find_nodes * tail;
+  for (int set = 0; set < NUM_PROJ_SETS; ++set) {
+    if (!u_set[set]) continue;
+    S.kbytes[1] += D * M * 4 + (set == PS_FIND ? 0 : (int64_t)u_set[set] * hw * M * 4);
+    S.kflops[1] += (int64_t)u_set[set] * contraction;
+  }
+  S.kbytes[2] = node_bytes;
   S.kflops[2] = node_flops;
   return 0;
 }

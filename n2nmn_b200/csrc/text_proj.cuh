@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(256)
 text_proj_kernel(DevModel md, TextBufs tb, const TextGroup* __restrict__ groups,
                  const int32_t* __restrict__ text_t, const int32_t* __restrict__ text_b) {
   extern __shared__ float s_dyn[];
+  pdl_trigger();   // the contraction kernel only needs our output in its epilogue
   const int Dt = md.Dt, M = md.M, Mp = md.Mp;
   float* s_x = s_dyn;                                 // [8][Dt]
   float* s_red = s_dyn + kTextRowsPerCta * Dt;        // [8 warps][8 rows][64 cols]
