@@ -19,6 +19,7 @@
 #include "proj_umma.cuh"
 #include "schedule.hpp"
 #include "text_proj.cuh"
+#include "tree_kernel.cuh"
 
 using namespace n2nmn;
 
@@ -110,6 +111,8 @@ struct n2nmn_ctx {
   ProjTensorMaps tmaps;
   EncodeTiledFn encode = nullptr;
   int node_smem_bytes = 0;
+  int tree_smem_bytes = 0;
+  int stack_cap = 0;           // attention-stack slots the tree kernel may use
   int tree_cluster = 0;        // 0 = choose from the batch size; else forced (N2NMN_TREE_CLUSTER)
   bool use_pdl = true;         // programmatic dependent launch between the three kernels
   n2nmn_sched module_sched;    // scratch schedule of n2nmn_module_fwd
@@ -260,7 +263,8 @@ void prof_mark(n2nmn_ctx* c, const char* name, cudaStream_t st) {
 }
 
 // Uploads (if needed) and launches everything for one compiled batch.
-int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaStream_t st) {
+int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaStream_t st,
+               bool force_wave = false, bool write_arena = false) {
   const HostSchedule& S = sc->hs;
   const TableOffsets o = table_offsets(S);
   if (o.total > c->table_cap)
@@ -360,7 +364,7 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaS
   nc.md = c->md; nc.tb = c->tb; nc.arena = arena; nc.scores = scores; nc.mbuf = c->mbuf;
   const int NQ = (int)S.q_ptr.size() - 1;
   const bool ks3 = (c->cfg.kernel_size != 5);
-  if (c->cfg.flags & N2NMN_FLAG_WAVE_EXECUTOR) {
+  if ((c->cfg.flags & N2NMN_FLAG_WAVE_EXECUTOR) || force_wave || S.max_stack > c->stack_cap) {
     CUDA_TRY(cudaMemsetAsync(scores, 0, (size_t)NQ * c->cfg.num_choices * sizeof(float), st));
     const int32_t* d_wave = reinterpret_cast<const int32_t*>(d + o.wave_nodes);
     for (int dep = 1; dep <= S.max_depth; ++dep) {
@@ -379,7 +383,10 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaS
     std::memset(&lc, 0, sizeof(lc));
     lc.gridDim = dim3((unsigned)(NQ * cs));
     lc.blockDim = dim3(kNodeThreads);
-    lc.dynamicSmemBytes = (size_t)c->node_smem_bytes;
+    const int slots = std::max(1, S.max_stack);
+    lc.dynamicSmemBytes = sizeof(float) * (size_t)tree_smem_layout(
+        c->cfg.H, c->cfg.W, c->Mp, c->cfg.kernel_size, c->cfg.map_dim, c->cfg.num_choices,
+        slots).total;
     lc.stream = st;
     cudaLaunchAttribute attr[2];
     int na = 0;
@@ -397,8 +404,9 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaS
     }
     lc.attrs = attr;
     lc.numAttrs = na;
-    if (ks3) CUDA_TRY(cudaLaunchKernelEx(&lc, tree_kernel<3>, nc, d_nodes, d_qptr, cs));
-    else CUDA_TRY(cudaLaunchKernelEx(&lc, tree_kernel<5>, nc, d_nodes, d_qptr, cs));
+    const int wa = write_arena ? 1 : 0;
+    if (ks3) CUDA_TRY(cudaLaunchKernelEx(&lc, tree_kernel<3>, nc, d_nodes, d_qptr, cs, slots, wa));
+    else CUDA_TRY(cudaLaunchKernelEx(&lc, tree_kernel<5>, nc, d_nodes, d_qptr, cs, slots, wa));
     ++c->launches;
     prof_mark(c, "tree_kernel", st);
   }
@@ -513,10 +521,18 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
   const NodeSmem L = node_smem_layout(cfg->H, cfg->W, c->Mp, c->cfg.kernel_size, cfg->map_dim,
                                       cfg->num_choices);
   c->node_smem_bytes = L.total * (int)sizeof(float);
+  c->stack_cap = cfg->max_T / 2 + 2;
+  for (;;) {   // largest attention stack that still fits in shared memory
+    c->tree_smem_bytes = (int)sizeof(float) * tree_smem_layout(
+        cfg->H, cfg->W, c->Mp, c->cfg.kernel_size, cfg->map_dim, cfg->num_choices,
+        c->stack_cap).total;
+    if (c->tree_smem_bytes <= 200 * 1024 || c->stack_cap <= 2) break;
+    --c->stack_cap;
+  }
   CUDA_TRY(cudaFuncSetAttribute(tree_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                c->node_smem_bytes));
+                                c->tree_smem_bytes));
   CUDA_TRY(cudaFuncSetAttribute(tree_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                c->node_smem_bytes));
+                                c->tree_smem_bytes));
   CUDA_TRY(cudaFuncSetAttribute(wave_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 c->node_smem_bytes));
   CUDA_TRY(cudaFuncSetAttribute(wave_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -702,7 +718,7 @@ int n2nmn_compile_nodes(n2nmn_ctx* c, const int32_t* op, const int32_t* t_idx,
       r.out = is_ans[o] ? q : i;
       r.text = -1;
       r.aux = (o == OP_SCENE) ? scene_bits : -1;
-      r.aux2 = -1; r.pad = 0;
+      r.aux2 = -1; r.s0 = r.s1 = r.so = -1;
     }
   }
   if (int rc = finalize_schedule(c->shp, c->cfg.max_batch, &S)) {
@@ -761,7 +777,8 @@ int n2nmn_run_schedule(n2nmn_ctx* c, n2nmn_sched* s, float* scores, float* att_a
   float* arena = att_arena ? att_arena : c->arena;
   if (!att_arena && (int)s->hs.nodes.size() > c->arena_slots)
     return fail(N2NMN_ERR_CAPACITY, "too many nodes for the context arena");
-  return run_tables(c, s, scores, arena, static_cast<cudaStream_t>(stream));
+  return run_tables(c, s, scores, arena, static_cast<cudaStream_t>(stream), false,
+                    att_arena != nullptr);
 }
 
 int n2nmn_module_fwd(n2nmn_ctx* c, int op, const float* in0, const float* in1,
@@ -802,7 +819,7 @@ int n2nmn_module_fwd(n2nmn_ctx* c, int op, const float* in0, const float* in1,
     r.out = is_ans[op] ? i : 2 * n + i;
     r.text = -1;
     r.aux = (op == OP_SCENE) ? scene_bits : -1;
-    r.aux2 = -1; r.pad = 0;
+    r.aux2 = -1; r.s0 = r.s1 = r.so = -1;
     S.q_ptr[i] = i;
   }
   S.q_ptr[n] = n;
@@ -814,7 +831,7 @@ int n2nmn_module_fwd(n2nmn_ctx* c, int op, const float* in0, const float* in1,
     CUDA_TRY(cudaMemcpyAsync(c->arena + (size_t)n * c->HW, in1, map_bytes,
                              cudaMemcpyDeviceToDevice, st));
   float* scores = is_ans[op] ? out : c->scores_tmp;
-  if (int rc = run_tables(c, sc, scores, c->arena, st)) return rc;
+  if (int rc = run_tables(c, sc, scores, c->arena, st, /*force_wave=*/true)) return rc;
   if (!is_ans[op])
     CUDA_TRY(cudaMemcpyAsync(out, c->arena + (size_t)2 * n * c->HW, map_bytes,
                              cudaMemcpyDeviceToDevice, st));

@@ -30,7 +30,7 @@ enum OutSetId { OS_SAMEPROP = 0, OS_DESCRIBE, NUM_OUT_SETS };
 enum ScoreSetId { SS_EXIST = 0, SS_COUNT, SS_EQUAL, SS_MORE, SS_LESS, NUM_SCORE_SETS };
 enum EltSetId { ES_FIND = 0, ES_FSP, ES_TRANSFORM, NUM_ELT_SETS };
 
-// One expression-tree node as the kernels see it (40 bytes).
+// One expression-tree node as the kernels see it (48 bytes).
 struct NodeRec {
   int32_t op;
   int32_t t, b;      // time index (token position) and question / image index
@@ -40,7 +40,9 @@ struct NodeRec {
   int32_t aux;       // mbuf slot: FSP conv_image map / Describe fc_att map / SameProperty fc_att_0
                      // (Scene: the bits of pos_val)
   int32_t aux2;      // mbuf slot: FSP fc_att map / SameProperty fc_att_1
-  int32_t pad;
+  // Slots of the per-question attention stack the tree kernel keeps in shared memory (live maps
+  // of one question; an output may reuse the slot of an input it consumes). -1 = none.
+  int32_t s0, s1, so;
 };
 
 // Everything the kernels need to know about the model; pointers are device pointers into the

@@ -1,18 +1,12 @@
-// K3: evaluation of expression-tree nodes, and the two executors built on it:
-//   * tree_kernel : one thread-block CLUSTER (1, 2 or 4 CTAs) per question walks that question's
-//                   nodes in Reverse-Polish order (every operand precedes its consumer); default;
-//   * wave_kernel : one CTA per node of one tree depth across the whole batch — the
-//                   depth-bucketed waves that replace TF Fold's dynamic batching
-//                   (models_clevr/nmn3_model.py:49-159).
-// Both call eval_node, so results are identical by construction.
+// K3, wave form: evaluation of ONE expression-tree node by one CTA through the global attention
+// arena, and wave_kernel = one CTA per node of one tree depth across the whole batch — the
+// depth-bucketed waves that replace TF Fold's dynamic batching (models_clevr/nmn3_model.py:49-159,
+// SURVEY.md §3.5). Also backs the per-module entry point (n2nmn_module_fwd). The default executor
+// (tree_kernel.cuh) shares the building blocks below.
 //
-// Inside a cluster the heavy modules are split across the CTAs: attention pooling by feature
-// channel, fc_att by weight rows (partial sums exchanged through distributed shared memory),
-// the stencil / per-pixel reductions by pixel. At batch 64 this spreads one question over 4 SMs
-// (L2->SM bandwidth, not arithmetic, bounds a node), at large batches the cluster size is 1.
-//
-// Find / Filter reach this kernel with their "find" map already in the arena (fused epilogue of
-// the projection kernel), FindSameProperty with its projected feature map in mbuf.
+// Find / Filter reach these kernels with their "find" map already in the arena (fused epilogue
+// of the projection kernel); FindSameProperty / Describe / SameProperty with their stored
+// tensor-core maps in mbuf.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -482,66 +476,6 @@ __device__ __forceinline__ void eval_node(const NodeCtx& c, const NodeRec& nd, c
     default:
       if (co.rank == 0) { cp_async_commit_wait_all(); eval_small_answer(c, nd, s); }
       break;
-  }
-}
-
-// One cluster of `csize` CTAs per question; q_ptr delimits the question's nodes (Reverse-Polish
-// order) in `nodes`. Launched with a cluster dimension of csize (plain launch when csize == 1).
-template <int KS>
-__global__ void __launch_bounds__(kNodeThreads)
-tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* __restrict__ q_ptr,
-            int csize) {
-  extern __shared__ __align__(16) float node_smem[];
-  SmemPtrs s = carve(node_smem, c.md);
-  Coop co;
-  co.size = csize;
-  co.rank = (csize > 1) ? (int)cg::this_cluster().block_rank() : 0;
-  const int q = blockIdx.x / csize;
-  const int beg = q_ptr[q], end = q_ptr[q + 1];
-  if (beg < end) {
-    // Prologue: start fetching the parameters this question will need (conv filter bank for
-    // Transform nodes, the root's answer-head weights on rank 0) while the first nodes run.
-    bool has_transform = false;
-    for (int i = beg; i < end; ++i) has_transform |= (nodes[i].op == OP_TRANSFORM);
-    if (has_transform) {
-      stage_async(s.k, c.md.conv_k, KS * KS * c.md.Mp);
-      s.k_ready = true;
-    }
-    if (co.rank == 0 && s.head != nullptr) {
-      const int rop = nodes[end - 1].op;
-      const DevModel& md = c.md;
-      const float* w = nullptr;
-      int rows = 0;
-      switch (rop) {
-        case OP_EXIST: w = md.sc_w[SS_EXIST]; rows = 3; break;
-        case OP_COUNT: w = md.sc_w[SS_COUNT]; rows = md.HW + 2; break;
-        case OP_EQUAL_NUM: w = md.sc_w[SS_EQUAL]; rows = 2 * (md.HW + 2); break;
-        case OP_MORE_NUM: w = md.sc_w[SS_MORE]; rows = 2 * (md.HW + 2); break;
-        case OP_LESS_NUM: w = md.sc_w[SS_LESS]; rows = 2 * (md.HW + 2); break;
-        case OP_SAME_PROPERTY: w = md.out_w[OS_SAMEPROP]; rows = md.M; break;
-        case OP_DESCRIBE: w = md.out_w[OS_DESCRIBE]; rows = md.M; break;
-        default: break;
-      }
-      if (w) {
-        stage_async(s.head, w, rows * md.C);
-        s.head_w = s.head;
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  // Everything above reads only weights and the launch tables. The attention arena, the stored
-  // maps and the text projections come from the preceding kernels (PDL: they may still run).
-  pdl_wait();
-  if (beg == end) {   // invalid layout: zeros(num_choices) (models_clevr/nmn3_model.py:144-155)
-    if (co.rank == 0)
-      for (int i = threadIdx.x; i < c.md.C; i += blockDim.x)
-        c.scores[(size_t)q * c.md.C + i] = 0.f;
-    return;
-  }
-  for (int i = beg; i < end; ++i) {
-    const NodeRec nd = nodes[i];
-    eval_node<KS>(c, nd, s, co);
-    co.sync();   // this node's arena writes (and DSMEM reads) are done before the next node
   }
 }
 

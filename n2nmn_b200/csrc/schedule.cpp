@@ -77,7 +77,7 @@ int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
         nd.rec.in0 = nd.rec.in1 = -1;
         nd.rec.text = -1;
         nd.rec.aux = (op == OP_SCENE) ? scene_bits : -1;
-        nd.rec.aux2 = -1; nd.rec.pad = 0;
+        nd.rec.aux2 = -1; nd.rec.s0 = nd.rec.s1 = nd.rec.so = -1;
         nd.depth = 1;
         nd.tset = text_set_of(op);
         // operands come off right-to-left: the last popped is input_0
@@ -209,6 +209,36 @@ int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out) 
         ProjWork w; w.row0 = r0; w.pass = pass; w.set = set; w.pad = 0;
         S.work.push_back(w);
       }
+    }
+  }
+
+  // ---- shared-memory stack slots for the tree kernel: a map lives from its producer to its
+  //      (single) consumer; inputs are released before the output is placed, so in-place reuse
+  //      is allowed (every module copies or finishes reading its inputs before it writes).
+  S.max_stack = 0;
+  {
+    static thread_local std::vector<int> free_slots;
+    for (int q = 0; q < NQ; ++q) {
+      free_slots.clear();
+      int next = 0;
+      for (int i = S.q_ptr[q]; i < S.q_ptr[q + 1]; ++i) {
+        NodeRec& r = S.nodes[i];
+        r.s0 = r.in0 >= 0 ? S.nodes[r.in0].so : -1;
+        r.s1 = r.in1 >= 0 ? S.nodes[r.in1].so : -1;
+        if (r.s0 >= 0) free_slots.push_back(r.s0);
+        if (r.s1 >= 0) free_slots.push_back(r.s1);
+        r.so = -1;
+        if (r.op <= OP_OR) {   // attention-typed output
+          if (!free_slots.empty()) {
+            auto it = std::min_element(free_slots.begin(), free_slots.end());
+            r.so = *it;
+            free_slots.erase(it);
+          } else {
+            r.so = next++;
+          }
+        }
+      }
+      S.max_stack = std::max(S.max_stack, next);
     }
   }
 

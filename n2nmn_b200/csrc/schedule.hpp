@@ -29,6 +29,7 @@ struct HostSchedule {
   std::vector<int32_t> img_ptr, node_text, node_out, mslot;
   int num_mslots = 0;
   int num_find_nodes = 0;
+  int max_stack = 0;                  // most attention maps of one question alive at once
   std::vector<int32_t> wave_ptr;      // [max_depth+2], wave d = [wave_ptr[d], wave_ptr[d+1])
   std::vector<int32_t> wave_nodes;
   // §8(d) algorithmic traffic / work, per kernel: 0 text, 1 projection, 2 node kernels
@@ -40,7 +41,7 @@ struct HostSchedule {
 
   // Forget the contents but keep every vector's capacity (the per-step path reuses one object).
   void reset() {
-    N = T = num_valid = max_depth = num_mslots = num_find_nodes = 0;
+    N = T = num_valid = max_depth = num_mslots = num_find_nodes = max_stack = 0;
     validity.clear(); nodes.clear(); depth.clear(); q_ptr.clear(); text_t.clear();
     text_b.clear(); groups.clear(); work.clear(); img_ptr.clear(); node_text.clear();
     node_out.clear(); mslot.clear(); wave_ptr.clear(); wave_nodes.clear();

@@ -17,41 +17,83 @@ namespace n2nmn {
 
 constexpr int kTextCols = 64;   // output columns per CTA
 
+constexpr int kTextKIter = 20;   // K rows per thread per chunk (16 slices x 20 = 320 >= Dt=300)
+
 __global__ void __launch_bounds__(256)
 text_proj_kernel(DevModel md, TextBufs tb, const TextGroup* __restrict__ groups,
                  const int32_t* __restrict__ text_t, const int32_t* __restrict__ text_b) {
   extern __shared__ float s_dyn[];
+  __shared__ int s_src[kTextRowsPerCta];
   pdl_trigger();   // the contraction kernel only needs our output in its epilogue
   const int Dt = md.Dt, M = md.M, Mp = md.Mp;
   float* s_x = s_dyn;                                 // [8][Dt]
   float* s_red = s_dyn + kTextRowsPerCta * Dt;        // [8 warps][8 rows][64 cols]
-  const TextGroup g = groups[blockIdx.y];
-  for (int i = threadIdx.x; i < kTextRowsPerCta * Dt; i += blockDim.x) {
-    const int r = i / Dt, k = i - r * Dt;
-    float v = 0.f;
-    if (r < g.count) {
-      const int row = g.start + r;
-      v = md.word_vecs[((size_t)text_t[row] * md.N + text_b[row]) * Dt + k];
-    }
-    s_x[i] = v;
-  }
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tx = lane & 15;                    // column quad inside the CTA's 64 columns
   const int ky = warp * 2 + (lane >> 4);       // K slice 0..15
   const int c0 = blockIdx.x * kTextCols + tx * 4;
+  const TextGroup g = groups[blockIdx.y];
+  const float* __restrict__ wbase = md.txt_w[g.set] + c0;
+
+  // (1) this thread's weight rows of the first chunk: independent of everything else, so the
+  //     loads fly while the word vectors are being gathered
+  float4 w[kTextKIter];
+#pragma unroll
+  for (int j = 0; j < kTextKIter; ++j) {
+    const int k = ky + 16 * j;
+    w[j] = (k < Dt) ? __ldg(reinterpret_cast<const float4*>(wbase + (size_t)k * Mp))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // (2) source rows of the group's nodes in the time-major word_vecs: t*N + b
+  if (threadIdx.x < kTextRowsPerCta) {
+    const int r = threadIdx.x;
+    s_src[r] = (r < g.count) ? text_t[g.start + r] * md.N + text_b[g.start + r] : -1;
+  }
+  __syncthreads();
+  // (3) gather the word vectors (all loads of a thread are independent)
+  for (int i0 = 0; i0 < kTextRowsPerCta * Dt; i0 += 8 * 256) {
+    float xv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * 256 + threadIdx.x;
+      xv[u] = 0.f;
+      if (i < kTextRowsPerCta * Dt) {
+        const int r = i / Dt, k = i - r * Dt;
+        const int src = s_src[r];
+        if (src >= 0) xv[u] = __ldg(md.word_vecs + (size_t)src * Dt + k);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * 256 + threadIdx.x;
+      if (i < kTextRowsPerCta * Dt) s_x[i] = xv[u];
+    }
+  }
+  __syncthreads();
+  // (4) 8 x 4 accumulators per thread
   float4 acc[kTextRowsPerCta];
 #pragma unroll
   for (int r = 0; r < kTextRowsPerCta; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float* __restrict__ wbase = md.txt_w[g.set] + c0;
-#pragma unroll 4
-  for (int k = ky; k < Dt; k += 16) {
-    const float4 w = __ldg(reinterpret_cast<const float4*>(wbase + (size_t)k * Mp));
+  for (int kb = 0; kb < Dt; kb += 16 * kTextKIter) {
+    if (kb > 0) {   // further chunks only when text_dim > 320
 #pragma unroll
-    for (int r = 0; r < kTextRowsPerCta; ++r) {
-      const float x = s_x[r * Dt + k];
-      acc[r].x = fmaf(x, w.x, acc[r].x); acc[r].y = fmaf(x, w.y, acc[r].y);
-      acc[r].z = fmaf(x, w.z, acc[r].z); acc[r].w = fmaf(x, w.w, acc[r].w);
+      for (int j = 0; j < kTextKIter; ++j) {
+        const int k = kb + ky + 16 * j;
+        w[j] = (k < Dt) ? __ldg(reinterpret_cast<const float4*>(wbase + (size_t)k * Mp))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kTextKIter; ++j) {
+      const int k = kb + ky + 16 * j;
+      if (k < Dt) {
+#pragma unroll
+        for (int r = 0; r < kTextRowsPerCta; ++r) {
+          const float x = s_x[r * Dt + k];
+          acc[r].x = fmaf(x, w[j].x, acc[r].x); acc[r].y = fmaf(x, w[j].y, acc[r].y);
+          acc[r].z = fmaf(x, w[j].z, acc[r].z); acc[r].w = fmaf(x, w[j].w, acc[r].w);
+        }
+      }
     }
   }
   // the two K slices inside a warp, then the 8 warps through shared memory
