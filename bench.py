@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--wave', action='store_true', help='depth-bucketed wave executor')
+    ap.add_argument('--streams', type=int, default=3,
+                    help='contexts/streams fed round-robin (independent batches overlap)')
     return ap.parse_args()
 
 
@@ -217,7 +219,7 @@ def main():
     import torch.distributed as dist
     from n2nmn_b200 import _lib, synth, weights as wts
     from n2nmn_b200.assembler import Assembler
-    from n2nmn_b200.executor import LayoutExecutor
+    from n2nmn_b200.executor import ExecutorPool, LayoutExecutor
 
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device. The product path has no CPU fallback.')
@@ -237,37 +239,45 @@ def main():
         wvs.append(torch.from_numpy(w).to(dev))
         toks.append(make_tokens(asm, args.layouts, B, seed=100 + 1000 * rank + i))
     flags = _lib.FLAG_WAVE_EXECUTOR if args.wave else 0
-    ex = LayoutExecutor('clevr', feats[0], wvs[0], C, asm, weights=weights, flags=flags,
-                        max_batch=B, max_T=T_DEC)
-    scores = torch.empty((B, C), dtype=torch.float32, device=dev)
+    K = max(1, args.streams)
+    pool = ExecutorPool('clevr', feats[0], wvs[0], C, asm, weights=weights, num_streams=K,
+                        flags=flags, max_batch=B, max_T=T_DEC)
+    ex = pool.executors[0]
+    scores_k = [torch.empty((B, C), dtype=torch.float32, device=dev) for _ in range(K)]
+    scores = scores_k[0]
 
     def step(i):
         # public API, one call per batch: bind the batch's device-resident features, compile its
-        # layouts (C++), upload the tables, launch the kernels; asynchronous
+        # layouts (C++), upload the tables, launch the kernels; asynchronous. Batches go
+        # round-robin over K contexts/streams so independent batches overlap on the GPU.
         k = i % P
-        ex.forward_device(feats[k], wvs[k], toks[k], out=scores)
+        pool.submit(feats[k], wvs[k], toks[k], out=scores_k[i % K])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    pool.begin()
     for i in range(args.warmup):
         step(i)
+    pool.end()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = ex.launch_count()
+    launches0 = pool.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    pool.begin()          # the K streams start after e0 ...
     for i in range(args.steps):
         step(args.warmup + i)
+    pool.end()            # ... and e1 is recorded after all of them have drained
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = ex.launch_count() - launches0
+    launches = pool.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -275,30 +285,40 @@ def main():
     ms_max = float(t.item())
     value = world * B * args.steps / (ms_max * 1e-3)
 
-    # ---- e2e: host (pinned) buffers in, host scores out, every step (n2nmn_forward_host)
+    # ---- e2e: host (pinned) buffers in, host scores out, every step, through the public API
     e2e = None
     if not args.no_e2e:
-        hp = min(P, 4)
+        hp = min(P, 6)
         hf = [feats[i].cpu().pin_memory() for i in range(hp)]
         hw = [wvs[i].cpu().pin_memory() for i in range(hp)]
-        hs = torch.empty((B, C), dtype=torch.float32).pin_memory()
-        for i in range(3):
-            ex.forward_host(hf[i % hp], hw[i % hp], toks[i % hp], hs)
+        hs = [torch.empty((B, C), dtype=torch.float32).pin_memory() for _ in range(hp)]
+        pool.begin()
+        for i in range(2 * K):
+            pool.submit_host(hf[i % hp], hw[i % hp], toks[i % hp], hs[i % hp])
+        pool.end()
         k_e2e = max(10, min(args.steps, 100))
         barrier()
         t0 = time.perf_counter()
+        pool.begin()
         for i in range(k_e2e):
-            ex.forward_host(hf[i % hp], hw[i % hp], toks[i % hp], hs)
+            pool.submit_host(hf[i % hp], hw[i % hp], toks[i % hp], hs[i % hp])
+        pool.end()
         torch.cuda.synchronize()
         el = time.perf_counter() - t0
+        # the copied-back scores are the device path's scores
+        chk, _ = ex.forward_device(feats[(k_e2e - 1) % hp], wvs[(k_e2e - 1) % hp],
+                                   toks[(k_e2e - 1) % hp])
+        torch.cuda.synchronize()
+        assert torch.equal(hs[(k_e2e - 1) % hp], chk.cpu()), 'e2e scores differ from device path'
         te = torch.tensor([el], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {'value': world * B * k_e2e / float(te.item()), 'unit': UNIT,
-               'h2d_bytes_per_step': int(hf[0].numel() * 4 + hw[0].numel() * 4 + 65536),
-               'd2h_bytes_per_step': int(hs.numel() * 4), 'steps': k_e2e,
-               'how': 'n2nmn_forward_host: pinned host features+word_vecs -> H2D -> compile -> '
-                      'kernels -> D2H scores, synchronous per step, wall clock'}
+               'h2d_bytes_per_step': int(hf[0].numel() * 4 + hw[0].numel() * 4),
+               'd2h_bytes_per_step': int(hs[0].numel() * 4), 'steps': k_e2e,
+               'how': 'ExecutorPool.submit_host: pinned host features+word_vecs -> async H2D -> '
+                      'C++ layout compile -> kernels -> async D2H scores, %d streams, every '
+                      'step, wall clock around the loop + final synchronize' % K}
 
     # ---- roofline of the dominant kernel: per-launch CUDA events, separate pass of the same steps
     roof, kernel_us = None, {}
@@ -307,7 +327,7 @@ def main():
         ex.set_profiling(True)
         acc, bytes_acc, flops_acc, n = {}, 0, 0, 0
         for i in range(min(args.steps, 50)):
-            step(i)
+            ex.forward_device(feats[i % P], wvs[i % P], toks[i % P], out=scores)
             for name, us in ex.launch_times():
                 acc.setdefault(name, []).append(us)
             info = ex.last_step_info()
@@ -360,6 +380,7 @@ def main():
                        'cache': 'inputs larger than L2: %d distinct resident batches (%.0f MB) '
                                 'walked round-robin' % (P, P * B * H * W * D * 4 / 1e6),
                        'executor': 'wave' if args.wave else 'tree',
+                       'streams': K,
                        'nodes_per_batch': info['num_nodes'], 'max_depth': info['max_depth']},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
             'roofline': roof, 'cpu_baseline': cpu, 'kernel_us': kernel_us,

@@ -18,7 +18,7 @@
 
 namespace n2nmn {
 
-constexpr int kTreeFindSlots = 8;    // Filter find-maps prefetched per question
+constexpr int kTreeFindSlots = 10;   // Find / Filter maps prefetched per question
 constexpr int kTransformPB = 5;      // pixels register-blocked per warp in the stencil
 
 struct TreeSmem {
@@ -159,9 +159,7 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
     int nf = 0;
     for (int i = beg; i < end; ++i) {
       const int op = nodes[i].op;
-      if (op == OP_FIND) {
-        stage_async(s.stack + nodes[i].so * L.HWp, c.arena + (size_t)nodes[i].out * HW, HW);
-      } else if (op == OP_FILTER) {
+      if (op == OP_FIND || op == OP_FILTER) {   // staged apart: stack slots are reused over time
         if (nf < kTreeFindSlots)
           stage_async(s.ftmp + nf * L.HWp, c.arena + (size_t)nodes[i].out * HW, HW);
         ++nf;
@@ -179,7 +177,13 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
     const float* in0 = (nd.s0 >= 0) ? s.stack + nd.s0 * L.HWp : nullptr;
     const float* in1 = (nd.s1 >= 0) ? s.stack + nd.s1 * L.HWp : nullptr;
     switch (nd.op) {
-      case OP_FIND: break;   // prefetched into its stack slot
+      case OP_FIND: {        // computed by the projection kernel's epilogue; prefetched above
+        const float* f = (nfilter < kTreeFindSlots) ? s.ftmp + nfilter * L.HWp
+                                                    : c.arena + (size_t)nd.out * HW;
+        ++nfilter;
+        for (int p = threadIdx.x; p < HW; p += blockDim.x) out[p] = f[p];
+        break;
+      }
       case OP_SCENE: {       // models_clevr/nmn3_modules.py:60-72
         const float v = __int_as_float(nd.aux);
         for (int p = threadIdx.x; p < HW; p += blockDim.x) out[p] = v;

@@ -235,3 +235,74 @@ class LayoutExecutor:
 
     def launch_count(self):
         return int(self._lib.n2nmn_launch_count(self.modules._h))
+
+
+class ExecutorPool:
+    """K LayoutExecutors (one context + one CUDA stream each) fed round-robin.
+
+    A batch of 64 questions is a short chain of small kernels that cannot fill 148 SMs on its
+    own; successive batches are independent (eval), so batch i+1's projection kernel can run
+    while batch i's tree kernel drains. Each executor owns its workspaces, so there is no
+    sharing hazard; weights are replicated (a few MB)."""
+
+    def __init__(self, family, image_feat_grid, word_vecs, num_choices, assembler, weights=None,
+                 num_streams=3, **ctx_kwargs):
+        first = LayoutExecutor(family, image_feat_grid, word_vecs, num_choices, assembler,
+                               weights=weights, **ctx_kwargs)
+        w = first.modules.get_weights()
+        self.executors = [first] + [
+            LayoutExecutor(family, image_feat_grid, word_vecs, num_choices, assembler, weights=w,
+                           **ctx_kwargs) for _ in range(num_streams - 1)]
+        dev = first.modules.device
+        self.streams = [torch.cuda.Stream(device=dev) for _ in self.executors]
+        self._i = 0
+        self.device = dev
+
+    def __len__(self):
+        return len(self.executors)
+
+    def begin(self):
+        """Make the pool's streams wait for work already queued on the current stream."""
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            st.wait_stream(cur)
+
+    def submit(self, image_feat_grid, word_vecs, layout_tokens, out=None):
+        """forward_device on the next executor/stream; returns (scores, validity, stream)."""
+        k = self._i % len(self.executors)
+        self._i += 1
+        with torch.cuda.stream(self.streams[k]):
+            scores, valid = self.executors[k].forward_device(image_feat_grid, word_vecs,
+                                                             layout_tokens, out=out)
+        return scores, valid, self.streams[k]
+
+    def submit_host(self, feat_host, word_vecs_host, layout_tokens, scores_host):
+        """End-to-end step from (pinned) HOST tensors: H2D of the batch's features and word
+        vectors, the forward pass, and D2H of the scores, all asynchronous on the slot's stream
+        (copy engines overlap the other slots' kernels). The result is valid in `scores_host`
+        after `end()` + a stream/device synchronise."""
+        k = self._i % len(self.executors)
+        self._i += 1
+        if not hasattr(self, '_dfeat'):
+            self._dfeat, self._dwv = {}, {}
+        if k not in self._dfeat or self._dfeat[k].shape != feat_host.shape or \
+                self._dwv[k].shape != word_vecs_host.shape:
+            self._dfeat[k] = torch.empty(feat_host.shape, dtype=torch.float32, device=self.device)
+            self._dwv[k] = torch.empty(word_vecs_host.shape, dtype=torch.float32,
+                                       device=self.device)
+        with torch.cuda.stream(self.streams[k]):
+            self._dfeat[k].copy_(feat_host, non_blocking=True)
+            self._dwv[k].copy_(word_vecs_host, non_blocking=True)
+            scores, valid = self.executors[k].forward_device(self._dfeat[k], self._dwv[k],
+                                                             layout_tokens)
+            scores_host.copy_(scores, non_blocking=True)
+        return valid
+
+    def end(self):
+        """Make the current stream wait for everything submitted so far."""
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            cur.wait_stream(st)
+
+    def launch_count(self):
+        return sum(e.launch_count() for e in self.executors)
