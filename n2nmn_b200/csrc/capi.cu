@@ -78,6 +78,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct n2nmn_sched {
   HostSchedule hs;
   uint64_t uid;
+  SchedShape shp;
 };
 
 struct n2nmn_ctx {
@@ -543,6 +544,8 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
       proj_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
       (int)((kSimtRows * kSimtKChunk + kSimtRows * c->Mp) * sizeof(float))));
   c->module_sched.uid = g_uid++;
+  c->module_sched.shp = c->shp;
+  c->step_sched.shp = c->shp;
   if (const char* e = std::getenv("N2NMN_NO_PDL")) c->use_pdl = (std::atoi(e) == 0);
   if (const char* e = std::getenv("N2NMN_TREE_CLUSTER")) {
     const int v = std::atoi(e);
@@ -650,6 +653,7 @@ int n2nmn_compile_schedule(n2nmn_ctx* c, const int32_t* tokens, int T, int N,
     return fail(N2NMN_ERR_CAPACITY, "N or T exceeds the context capacity");
   n2nmn_sched* sc = new n2nmn_sched();
   sc->uid = g_uid++;
+  sc->shp = c->shp;
   const char* err = nullptr;
   const int rc = compile_schedule(c->shp, tokens, T, N, vocab_ops, num_vocab, &sc->hs, &err);
   if (rc) { delete sc; return fail(rc, err ? err : "compile_schedule failed"); }
@@ -669,6 +673,7 @@ int n2nmn_compile_schedule_host(const n2nmn_config* cfg, const int32_t* tokens, 
                        cfg->family == N2NMN_VQA ? 1 : cfg->kernel_size, cfg->max_T};
   n2nmn_sched* sc = new n2nmn_sched();
   sc->uid = g_uid++;
+  sc->shp = shp;
   const char* err = nullptr;
   const int rc = compile_schedule(shp, tokens, T, N, vocab_ops, num_vocab, &sc->hs, &err);
   if (rc) { delete sc; return fail(rc, err ? err : "compile_schedule failed"); }
@@ -688,6 +693,7 @@ int n2nmn_compile_nodes(n2nmn_ctx* c, const int32_t* op, const int32_t* t_idx,
   static const bool is_ans[NUM_OPS] = {0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1};
   n2nmn_sched* sc = new n2nmn_sched();
   sc->uid = g_uid++;
+  sc->shp = c->shp;
   HostSchedule& S = sc->hs;
   S.N = nq; S.T = c->cfg.max_T;
   S.nodes.resize(n); S.depth.assign(n, 1);
@@ -733,6 +739,7 @@ int n2nmn_sched_destroy(n2nmn_sched* s) { delete s; return 0; }
 
 int n2nmn_sched_get_info(const n2nmn_sched* s, n2nmn_sched_info* info) {
   if (!s || !info) return fail(N2NMN_ERR_ARG, "null argument");
+  account_schedule(s->shp, const_cast<HostSchedule*>(&s->hs));
   const HostSchedule& S = s->hs;
   info->num_questions = (int)S.q_ptr.size() - 1;
   info->num_valid = S.num_valid;

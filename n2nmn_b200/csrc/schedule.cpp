@@ -29,12 +29,6 @@ struct Pending {   // a parsed node before text rows are assigned
   int tset;
 };
 
-uint64_t fnv1a(const void* data, size_t n, uint64_t h = 1469598103934665603ull) {
-  const unsigned char* p = static_cast<const unsigned char*>(data);
-  for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
-  return h;
-}
-
 }  // namespace
 
 int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
@@ -45,8 +39,6 @@ int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
   S.N = N; S.T = T;
   S.validity.assign(N, 0);
   S.q_ptr.assign(N + 1, 0);
-  S.hash = fnv1a(tokens, sizeof(int32_t) * (size_t)T * N);
-  S.hash = fnv1a(vocab_ops, sizeof(int32_t) * num_vocab, S.hash);
 
   static thread_local std::vector<Pending> all, q;
   static thread_local std::vector<int> stack;   // indices into q
@@ -254,6 +246,29 @@ int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out) 
       if (S.nodes[i].op != OP_FIND) S.wave_nodes[fill[S.depth[i]]++] = i;
   }
 
+  S.accounted = false;
+  S.u_any = u_any;
+  for (int set = 0; set < NUM_PROJ_SETS; ++set) S.u_set[set] = u_set[set];
+  S.set_count_text = 0;
+  for (int st = 0; st < NUM_TEXT_SETS; ++st) S.set_count_text += set_count[st] > 0;
+  return 0;
+}
+
+
+// §8(d) traffic / work accounting; only needed when statistics are requested, so it is kept off
+// the per-step path.
+void account_schedule(const SchedShape& shp, HostSchedule* out) {
+  HostSchedule& S = *out;
+  if (S.accounted) return;
+  S.accounted = true;
+  const int NQ = (int)S.q_ptr.size() - 1;
+  const int HW = shp.H * shp.W;
+  const int num_text = (int)S.text_t.size();
+  const int sets_used = S.set_count_text;
+  const int u_any = S.u_any;
+  const int* u_set = S.u_set;
+  for (int k = 0; k < 3; ++k) S.kbytes[k] = S.kflops[k] = 0;
+  S.per_node_bytes = S.per_node_flops = 0;
   // ---- algorithmic bytes / flops, fp32
   const int64_t D = shp.Dk, M = shp.M, C = shp.C, Dt = shp.Dt, hw = HW;
   const int64_t tile_b = hw * D * 4, att_b = hw * 4, txt_b = Dt * 4;
@@ -294,8 +309,6 @@ int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out) 
       node_flops += kf;
     }
   }
-  int sets_used = 0;
-  for (int s = 0; s < NUM_TEXT_SETS; ++s) sets_used += set_count[s] > 0;
   S.kbytes[0] = (int64_t)num_text * (txt_b + M * 4) + (int64_t)sets_used * Dt * M * 4;
   S.kflops[0] = (int64_t)num_text * txt_f;
   // projection launch: every distinct feature tile once, one weight matrix per set in use,
@@ -309,7 +322,6 @@ int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out) 
   }
   S.kbytes[2] = node_bytes;
   S.kflops[2] = node_flops;
-  return 0;
 }
 
 }  // namespace n2nmn

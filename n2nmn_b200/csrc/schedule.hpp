@@ -37,7 +37,9 @@ struct HostSchedule {
   int64_t kflops[3] = {0, 0, 0};
   int64_t per_node_bytes = 0;         // Σ over nodes of the App. D per-node figure
   int64_t per_node_flops = 0;
-  uint64_t hash = 0;
+  // inputs of the lazy accounting
+  bool accounted = false;
+  int u_any = 0, u_set[NUM_PROJ_SETS] = {0}, set_count_text = 0;
 
   // Forget the contents but keep every vector's capacity (the per-step path reuses one object).
   void reset() {
@@ -47,7 +49,7 @@ struct HostSchedule {
     node_out.clear(); mslot.clear(); wave_ptr.clear(); wave_nodes.clear();
     for (int k = 0; k < 3; ++k) kbytes[k] = kflops[k] = 0;
     per_node_bytes = per_node_flops = 0;
-    hash = 0;
+    accounted = false;
   }
 };
 
@@ -60,5 +62,8 @@ int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
 // S.nodes / S.depth / S.q_ptr. `num_images` bounds NodeRec::b. Used by compile_schedule and by the
 // per-module entry point, which fabricates one single-node "question" per call row.
 int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out);
+
+// Fills kbytes / kflops / per_node_* (SURVEY.md §8d). Idempotent.
+void account_schedule(const SchedShape& shp, HostSchedule* out);
 
 }  // namespace n2nmn

@@ -162,11 +162,12 @@ class LayoutExecutor:
         cb = self.compile_tokens(layout_tokens, cache=cache)
         return self.run(cb), cb.validity
 
-    def forward_device(self, image_feat_grid, word_vecs, layout_tokens, out=None):
+    def forward_device(self, image_feat_grid, word_vecs, layout_tokens, out=None, stream=None):
         """One eval step with device-resident inputs: bind + C++ layout compile + launches in a
         single C call (n2nmn_forward_tokens). Inputs must be contiguous float32 CUDA tensors
         ([N,H,W,D], [T,N,Dt]); tokens a C-contiguous int32 [T,N] numpy array. Returns
-        (scores [N,C] CUDA tensor, validity bool[N]). Asynchronous on the current stream."""
+        (scores [N,C] CUDA tensor, validity bool[N]). Asynchronous on `stream` (a
+        torch.cuda.Stream; default: the current stream)."""
         m = self.modules
         tok = layout_tokens
         if tok.dtype != np.int32 or not tok.flags['C_CONTIGUOUS']:
@@ -182,7 +183,7 @@ class LayoutExecutor:
         _lib.check(self._lib.n2nmn_forward_tokens(
             m._h, image_feat_grid.data_ptr(), word_vecs.data_ptr(), tok.ctypes.data, T, N,
             self._vocab_ptr, len(self.vocab_ops), out.data_ptr(), validity.ctypes.data,
-            torch.cuda.current_stream(m.device).cuda_stream))
+            (stream or torch.cuda.current_stream(m.device)).cuda_stream))
         self.scores = out
         return out, validity.view(bool)
 
@@ -271,9 +272,13 @@ class ExecutorPool:
         """forward_device on the next executor/stream; returns (scores, validity, stream)."""
         k = self._i % len(self.executors)
         self._i += 1
-        with torch.cuda.stream(self.streams[k]):
-            scores, valid = self.executors[k].forward_device(image_feat_grid, word_vecs,
-                                                             layout_tokens, out=out)
+        if out is None:   # allocate on the slot's stream so the caching allocator orders reuse
+            with torch.cuda.stream(self.streams[k]):
+                out = torch.empty((layout_tokens.shape[1], self.executors[k].num_choices),
+                                  dtype=torch.float32, device=self.device)
+        scores, valid = self.executors[k].forward_device(image_feat_grid, word_vecs,
+                                                         layout_tokens, out=out,
+                                                         stream=self.streams[k])
         return scores, valid, self.streams[k]
 
     def submit_host(self, feat_host, word_vecs_host, layout_tokens, scores_host):
