@@ -195,6 +195,32 @@ int n2nmn_forward_host(n2nmn_ctx* ctx, const float* feat_host, const float* word
                        const int32_t* tokens_host, int T, int N, const int32_t* vocab_ops,
                        int num_vocab, float* scores_host, uint8_t* validity_out, void* stream);
 
+/* ---- training step (exp_clevr/train_clevr_rl_gt_layout.py:108-139) -------------------------------
+ * Weights, gradients and the Adam moments live in caller-owned flat fp32 device buffers of
+ * n2nmn_flat_size() floats: the variables of n2nmn_variable_info() in order, each in its TF shape
+ * at n2nmn_flat_offset(). */
+int64_t n2nmn_flat_size(const n2nmn_ctx* ctx);
+int n2nmn_flat_offset(const n2nmn_ctx* ctx, int index, int64_t* offset, int64_t* count);
+/* n2nmn_set_weight for every variable from one flat buffer. */
+int n2nmn_load_flat_weights(n2nmn_ctx* ctx, const float* wflat_dev, void* stream);
+/* Forward + backward of one batch: scores_dev [N,C]; loss_dev[0] = Σ_i loss_i with
+ * loss_i = softmax cross-entropy for valid layouts and `invalid_expr_loss` otherwise
+ * (:108-114), loss_dev[1+i] = loss_i; gflat_dev = d(mean_i loss_i)/d(variables) (overwritten);
+ * dword_dev (optional) = d(mean loss)/d(word_vecs) [T,N,text_dim], the gradient handed on to the
+ * seq2seq. labels_host int32 [N]. Asynchronous on `stream`. */
+int n2nmn_train_backward(n2nmn_ctx* ctx, const float* feat_dev, const float* word_vecs_dev,
+                         const int32_t* tokens_host, int T, int N, const int32_t* vocab_ops,
+                         int num_vocab, const int32_t* labels_host, float invalid_expr_loss,
+                         float* scores_dev, float* gflat_dev, float* dword_dev, float* loss_dev,
+                         uint8_t* validity_out, void* stream);
+/* g += weight_decay * w on the ".../weights" variables (l2_reg, nmn3_model.py:163-166), per-tensor
+ * tf.clip_by_norm(g, max_norm) (:137-138), Adam step `step` (1-based, :132), then the updated
+ * weights are re-packed into the context. In data-parallel training the caller all-reduces
+ * gflat_dev (NCCL) between n2nmn_train_backward and this call. */
+int n2nmn_adam_step(n2nmn_ctx* ctx, float* wflat_dev, float* gflat_dev, float* m_dev, float* v_dev,
+                    int step, float lr, float beta1, float beta2, float eps, float max_norm,
+                    float weight_decay, void* stream);
+
 /* Per-launch device time of the last n2nmn_run_schedule in microseconds (CUDA events recorded
  * around every launch when enabled). names/us arrays of length >= capacity. */
 int n2nmn_set_profiling(n2nmn_ctx* ctx, int enabled);

@@ -58,6 +58,13 @@ SIGNATURES = {
     'n2nmn_last_step_info': (C.c_int, [_P, C.POINTER(SchedInfo)]),
     'n2nmn_forward_host': (C.c_int, [_P, _P, _P, _I32P, C.c_int, C.c_int, _I32P, C.c_int, _P,
                                      C.POINTER(C.c_uint8), _P]),
+    'n2nmn_flat_size': (C.c_int64, [_P]),
+    'n2nmn_flat_offset': (C.c_int, [_P, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    'n2nmn_load_flat_weights': (C.c_int, [_P, _P, _P]),
+    'n2nmn_train_backward': (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_int, _P,
+                                       C.c_float, _P, _P, _P, _P, _P, _P]),
+    'n2nmn_adam_step': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_float, C.c_float, C.c_float,
+                                  C.c_float, C.c_float, C.c_float, _P]),
     'n2nmn_set_profiling': (C.c_int, [_P, C.c_int]),
     'n2nmn_get_launch_times': (C.c_int, [_P, C.POINTER(C.c_char_p), C.POINTER(C.c_float),
                                          C.c_int]),

@@ -1,0 +1,671 @@
+// Backward pass of the module network: gradients of
+// avg_sample_loss (exp_clevr/train_clevr_rl_gt_layout.py:108-119) w.r.t. every module variable and
+// w.r.t. word_vecs, following TF 1.0's registered gradients (ties of tf.minimum/maximum go to
+// input_0; reduce_min/max split ties equally; l2_normalize takes the constant branch below eps).
+//
+// Structure (correctness-first; only the feature-side weight gradients are heavy):
+//   loss_kernel      : softmax cross-entropy, validity select, d(loss)/d(scores)
+//   tree_bwd_kernel  : one CTA per question walks its nodes in REVERSE Reverse-Polish order with
+//                      the gradient maps in shared memory; recomputes each module's forward
+//                      intermediates from the saved attention maps / stored tensor-core maps and
+//                      emits (a) small weight gradients by atomics, (b) d(tau) per text row,
+//                      (c) one [HW, Mp] "B map" per feature-side layer use (dm for conv_image,
+//                      s_p*dphi for the fc_att layers)
+//   text_bwd_kernel  : d(fc_text weights) = Σ t^T dtau, d(word_vecs) = dtau · W^T
+//   feat_grad_kernel : d(W_set) = Σ_entries X_b^T · B_entry, d(b_set) = Σ rows of B  (every
+//                      feature-side layer is "X·W + b" per image, so they all share this GEMM)
+//   adam kernels     : weight decay, per-tensor clip_by_norm, Adam (train_clevr_rl_gt_layout.py:
+//                      126-139)
+#pragma once
+#include "node_eval.cuh"
+
+namespace n2nmn {
+
+// Offsets (in floats) of every variable's gradient inside the flat gradient buffer, TF layout.
+struct GradOffsets {
+  int proj_w[NUM_PROJ_SETS], proj_b[NUM_PROJ_SETS];   // conv_image / fc_att layers
+  int txt_w[NUM_TEXT_SETS], txt_b[NUM_TEXT_SETS];
+  int elt_w[NUM_ELT_SETS], elt_b[NUM_ELT_SETS];
+  int conv_k, conv_b;
+  int out_w[NUM_OUT_SETS], out_b[NUM_OUT_SETS];
+  int sc_w[NUM_SCORE_SETS], sc_b[NUM_SCORE_SETS];
+};
+
+struct BwdEntry { int32_t set, b; };   // one B map: which layer, which image
+
+struct BwdCtx {
+  DevModel md;
+  TextBufs tb;
+  const float* arena;     // forward attention maps, [nodes][HW] (tree kernel ran with write_arena)
+  const float* scores;    // [NQ][C]
+  const float* dscores;   // [NQ][C]
+  const float* mbuf;      // stored maps; PS_FIND maps are stored too in training schedules
+  float* gflat;           // flat gradient buffer (zero-initialised)
+  float* dtau;            // [text rows][Mp]
+  float* dmap;            // [entries][HW][Mp]
+  GradOffsets go;
+  int max_nodes_q;        // capacity of the per-question gradient stack in shared memory
+};
+
+// ---- loss ------------------------------------------------------------------------------------
+// One warp per question. loss_acc[0] += per-sample loss, dscores = (softmax - onehot) / NQ for
+// valid questions, 0 otherwise (invalid rows cost the constant invalid_expr_loss).
+__global__ void loss_kernel(const float* __restrict__ scores, const int32_t* __restrict__ labels,
+                            const int32_t* __restrict__ q_ptr, int NQ, int C, float invalid_loss,
+                            float* __restrict__ dscores, float* __restrict__ per_sample,
+                            float* __restrict__ loss_acc) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= NQ) return;
+  const bool valid = q_ptr[q + 1] > q_ptr[q];
+  const float* s = scores + (size_t)q * C;
+  float* d = dscores + (size_t)q * C;
+  if (!valid) {
+    for (int c = lane; c < C; c += 32) d[c] = 0.f;
+    if (lane == 0) { per_sample[q] = invalid_loss; atomicAdd(loss_acc, invalid_loss); }
+    return;
+  }
+  float mx = -INFINITY;
+  for (int c = lane; c < C; c += 32) mx = fmaxf(mx, s[c]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int c = lane; c < C; c += 32) sum += expf(s[c] - mx);
+  sum = warp_sum(sum);
+  const int y = labels[q];
+  const float inv = 1.f / sum, invn = 1.f / (float)NQ;
+  for (int c = lane; c < C; c += 32) {
+    const float p = expf(s[c] - mx) * inv;
+    d[c] = (p - (c == y ? 1.f : 0.f)) * invn;
+  }
+  if (lane == 0) {
+    const float l = logf(sum) + mx - s[y];
+    per_sample[q] = l;
+    atomicAdd(loss_acc, l);
+  }
+}
+
+// ---- helpers for the reverse tree walk ---------------------------------------------------------
+// Backward of the answer heads' input vector z = [a.flat, min, max] (or [min, mean, max]).
+__device__ __forceinline__ void minmax_count(const float* a, int HW, float* red, float& mn,
+                                             float& mx, float& cmn, float& cmx) {
+  float lmn = INFINITY, lmx = -INFINITY;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) { lmn = fminf(lmn, a[p]); lmx = fmaxf(lmx, a[p]); }
+  mn = block_reduce<2>(lmn, red);
+  mx = block_reduce<1>(lmx, red);
+  float c0 = 0.f, c1 = 0.f;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) { c0 += (a[p] == mn); c1 += (a[p] == mx); }
+  cmn = block_reduce<0>(c0, red);
+  cmx = block_reduce<0>(c1, red);
+}
+
+// dz[k] = Σ_c W[k*C+c]·g[c]  and  dW[k*C+c] += z[k]·g[c], db[c] += g[c]
+__device__ __forceinline__ void head_backward(const float* z, int L, const float* __restrict__ W,
+                                              const float* g, int C, float* dz, float* gW,
+                                              float* gb) {
+  for (int k = threadIdx.x; k < L; k += blockDim.x) {
+    float acc = 0.f;
+    const float zk = z[k];
+    for (int c = 0; c < C; ++c) {
+      acc = fmaf(W[(size_t)k * C + c], g[c], acc);
+      atomicAdd(gW + (size_t)k * C + c, zk * g[c]);
+    }
+    dz[k] = acc;
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(gb + c, g[c]);
+  __syncthreads();
+}
+
+// Backward of  out = l2norm_c(e)·w2 + b2  for ONE pixel handled by one warp, e_c = base_c*coef_c.
+// Given lane-strided e values it returns de (in place of e) and accumulates dw2 / db2.
+//   ê = e*inv ; dê = g*w2 ; de = (dê - ê(ê·dê))*inv   (no projection term when ss <= eps)
+
+// Shared-memory layout of tree_bwd_kernel (floats).
+struct BwdSmem {
+  int HWp, g, pad, k, vec, z, total;
+};
+__host__ __device__ inline BwdSmem bwd_smem_layout(int H, int W, int Mp, int ksize, int C,
+                                                   int max_nodes_q) {
+  BwdSmem s;
+  const int HW = H * W;
+  s.HWp = (HW + 3) & ~3;
+  s.g = max_nodes_q * s.HWp;
+  s.pad = ((H + ksize - 1) * (W + ksize - 1) + 3) & ~3;
+  s.k = 2 * ksize * ksize * Mp;          // filter bank + its gradient
+  s.vec = 10 * Mp;
+  s.z = 2 * ((2 * (HW + 2) + 3) & ~3) + ((C + 3) & ~3);
+  s.total = s.g + 4 * s.HWp + 2 * s.pad + s.k + s.vec + s.z + 64;
+  return s;
+}
+
+// One CTA per question, nodes in reverse order.
+template <int KS>
+__global__ void __launch_bounds__(kNodeThreads)
+tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
+                const int32_t* __restrict__ q_ptr, const int32_t* __restrict__ node_entry) {
+  extern __shared__ __align__(16) float bsm[];
+  const DevModel& md = c.md;
+  const int HW = md.HW, Mp = md.Mp, M = md.M, C = md.C, Hh = md.H, Ww = md.W;
+  const BwdSmem L = bwd_smem_layout(Hh, Ww, Mp, md.ksize, C, c.max_nodes_q);
+  float* gst = bsm;                       // [nodes of the question][HWp] gradient maps
+  float* a0 = gst + L.g;                  // forward inputs / scratch maps
+  float* a1 = a0 + L.HWp;
+  float* da = a1 + L.HWp;
+  float* db_ = da + L.HWp;
+  float* pad = db_ + L.HWp;               // zero-padded forward input of Transform
+  float* dpad = pad + L.pad;              // gradient w.r.t. the padded input
+  float* ks = dpad + L.pad;               // conv filter bank [KS*KS][Mp]
+  float* dks = ks + KS * KS * Mp;         // its gradient
+  float* v = dks + KS * KS * Mp;          // 10 vectors of Mp
+  float* zb = v + 10 * Mp;                // z, dz, g(C)
+  float* red = zb + L.z;
+  const int q = blockIdx.x;
+  const int beg = q_ptr[q], end = q_ptr[q + 1];
+  if (beg == end) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int zlen = (2 * (HW + 2) + 3) & ~3;
+  float* z = zb;
+  float* dz = zb + zlen;
+  float* gsc = dz + zlen;
+  for (int i = threadIdx.x; i < (end - beg) * L.HWp; i += blockDim.x) gst[i] = 0.f;
+  __syncthreads();
+
+  for (int i = end - 1; i >= beg; --i) {
+    const NodeRec nd = nodes[i];
+    float* g = gst + (i - beg) * L.HWp;                       // d loss / d this node's map
+    float* gin0 = (nd.in0 >= 0) ? gst + (nd.in0 - beg) * L.HWp : nullptr;
+    float* gin1 = (nd.in1 >= 0) ? gst + (nd.in1 - beg) * L.HWp : nullptr;
+    const float* fin0 = (nd.in0 >= 0) ? c.arena + (size_t)nd.in0 * HW : nullptr;
+    const float* fin1 = (nd.in1 >= 0) ? c.arena + (size_t)nd.in1 * HW : nullptr;
+    const float* fout = c.arena + (size_t)i * HW;             // this node's forward map
+    switch (nd.op) {
+      case OP_SCENE: break;
+      case OP_AND: case OP_OR:   // ties -> input_0 (App. E)
+        for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+          const bool to0 = (nd.op == OP_AND) ? (fin0[p] <= fin1[p]) : (fin0[p] >= fin1[p]);
+          if (to0) gin0[p] += g[p]; else gin1[p] += g[p];
+        }
+        break;
+      case OP_EXIST: case OP_COUNT: case OP_EQUAL_NUM: case OP_MORE_NUM: case OP_LESS_NUM: {
+        for (int cc = threadIdx.x; cc < C; cc += blockDim.x) gsc[cc] = c.dscores[(size_t)nd.out * C + cc];
+        const bool two = (nd.op == OP_EQUAL_NUM || nd.op == OP_MORE_NUM || nd.op == OP_LESS_NUM);
+        const int set = (nd.op == OP_EXIST) ? SS_EXIST : (nd.op == OP_COUNT) ? SS_COUNT
+                      : (nd.op == OP_EQUAL_NUM) ? SS_EQUAL : (nd.op == OP_MORE_NUM) ? SS_MORE : SS_LESS;
+        float mn0, mx0, cmn0, cmx0, mn1 = 0, mx1 = 0, cmn1 = 1, cmx1 = 1, sum0 = 0.f;
+        for (int p = threadIdx.x; p < HW; p += blockDim.x) { a0[p] = fin0[p]; if (two) a1[p] = fin1[p]; }
+        __syncthreads();
+        minmax_count(a0, HW, red, mn0, mx0, cmn0, cmx0);
+        if (two) minmax_count(a1, HW, red, mn1, mx1, cmn1, cmx1);
+        int Lz;
+        if (nd.op == OP_EXIST) {
+          float ls = 0.f;
+          for (int p = threadIdx.x; p < HW; p += blockDim.x) ls += a0[p];
+          sum0 = block_reduce<0>(ls, red);
+          if (threadIdx.x == 0) { z[0] = mn0; z[1] = sum0 / (float)HW; z[2] = mx0; }
+          Lz = 3;
+        } else {
+          for (int p = threadIdx.x; p < HW; p += blockDim.x) { z[p] = a0[p]; if (two) z[HW + 2 + p] = a1[p]; }
+          if (threadIdx.x == 0) {
+            z[HW] = mn0; z[HW + 1] = mx0;
+            if (two) { z[2 * HW + 2] = mn1; z[2 * HW + 3] = mx1; }
+          }
+          Lz = two ? 2 * (HW + 2) : HW + 2;
+        }
+        __syncthreads();
+        head_backward(z, Lz, md.sc_w[set], gsc, C, dz, c.gflat + c.go.sc_w[set],
+                      c.gflat + c.go.sc_b[set]);
+        for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+          if (nd.op == OP_EXIST) {
+            gin0[p] += dz[0] * (a0[p] == mn0) / cmn0 + dz[1] / (float)HW + dz[2] * (a0[p] == mx0) / cmx0;
+          } else {
+            gin0[p] += dz[p] + dz[HW] * (a0[p] == mn0) / cmn0 + dz[HW + 1] * (a0[p] == mx0) / cmx0;
+            if (two)
+              gin1[p] += dz[HW + 2 + p] + dz[2 * HW + 2] * (a1[p] == mn1) / cmn1 +
+                         dz[2 * HW + 3] * (a1[p] == mx1) / cmx1;
+          }
+        }
+        break;
+      }
+      case OP_DESCRIBE: case OP_SAME_PROPERTY: {
+        // forward: s = softmax(a); phi = Σ_p s_p G[p]; e = tau∘phi (∘phi1); ê = e/n; scores = ê·Wout+b
+        const bool two = (nd.op == OP_SAME_PROPERTY);
+        const int os = two ? OS_SAMEPROP : OS_DESCRIBE;
+        float* phi0 = v; float* phi1 = v + Mp; float* e = v + 2 * Mp; float* de = v + 3 * Mp;
+        float* dphi0 = v + 4 * Mp; float* dphi1 = v + 5 * Mp;
+        for (int cc = threadIdx.x; cc < C; cc += blockDim.x) gsc[cc] = c.dscores[(size_t)nd.out * C + cc];
+        for (int p = threadIdx.x; p < HW; p += blockDim.x) { a0[p] = fin0[p]; if (two) a1[p] = fin1[p]; }
+        __syncthreads();
+        softmax_inplace(a0, HW, red);
+        if (two) softmax_inplace(a1, HW, red);
+        const float* G0 = c.mbuf + (size_t)nd.aux * HW * Mp;
+        const float* G1 = two ? c.mbuf + (size_t)nd.aux2 * HW * Mp : nullptr;
+        const float* tau = c.tb.tau + (size_t)nd.text * Mp;
+        for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
+          float p0 = 0.f, p1 = 0.f;
+          if (ch < M) {
+            for (int p = 0; p < HW; ++p) {
+              p0 = fmaf(a0[p], G0[(size_t)p * Mp + ch], p0);
+              if (two) p1 = fmaf(a1[p], G1[(size_t)p * Mp + ch], p1);
+            }
+          }
+          phi0[ch] = p0; phi1[ch] = p1;
+          e[ch] = (ch < M) ? (two ? p0 * tau[ch] * p1 : tau[ch] * p0) : 0.f;
+        }
+        __syncthreads();
+        float ss = 0.f;
+        for (int ch = threadIdx.x; ch < M; ch += blockDim.x) ss = fmaf(e[ch], e[ch], ss);
+        ss = block_reduce<0>(ss, red);
+        const float inv = rsqrtf(fmaxf(ss, kEps));
+        // dê = Wout·g ; head weight grads with ê
+        float dot = 0.f;
+        for (int ch = threadIdx.x; ch < M; ch += blockDim.x) {
+          const float eh = e[ch] * inv;
+          float acc = 0.f;
+          for (int cc = 0; cc < C; ++cc) {
+            acc = fmaf(md.out_w[os][(size_t)ch * C + cc], gsc[cc], acc);
+            atomicAdd(c.gflat + c.go.out_w[os] + (size_t)ch * C + cc, eh * gsc[cc]);
+          }
+          de[ch] = acc;            // holds dê for now
+          dot = fmaf(eh, acc, dot);
+        }
+        for (int cc = threadIdx.x; cc < C; cc += blockDim.x) atomicAdd(c.gflat + c.go.out_b[os] + cc, gsc[cc]);
+        dot = block_reduce<0>(dot, red);
+        if (!(ss > kEps)) dot = 0.f;
+        float* dtau = c.dtau + (size_t)nd.text * Mp;
+        for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
+          float d = 0.f, dt = 0.f, d0 = 0.f, d1 = 0.f;
+          if (ch < M) {
+            d = (de[ch] - e[ch] * inv * dot) * inv;            // de
+            if (two) { dt = d * phi0[ch] * phi1[ch]; d0 = d * tau[ch] * phi1[ch]; d1 = d * tau[ch] * phi0[ch]; }
+            else { dt = d * phi0[ch]; d0 = d * tau[ch]; }
+          }
+          dtau[ch] = dt; dphi0[ch] = d0; dphi1[ch] = d1;
+        }
+        __syncthreads();
+        // B maps: dG[p,:] = s_p * dphi ; input gradients through the softmax
+        const int ent = node_entry[i];
+        for (int which = 0; which < (two ? 2 : 1); ++which) {
+          const float* G = which ? G1 : G0;
+          const float* sft = which ? a1 : a0;
+          const float* dphi = which ? dphi1 : dphi0;
+          float* B = c.dmap + (size_t)(ent + which) * HW * Mp;
+          float* ds = which ? db_ : da;
+          for (int p = warp; p < HW; p += nwarps) {
+            float acc = 0.f;
+            const float sp = sft[p];
+            for (int ch = lane; ch < Mp; ch += 32) {
+              const float dp = dphi[ch];
+              acc = fmaf(G[(size_t)p * Mp + ch], dp, acc);
+              B[(size_t)p * Mp + ch] = sp * dp;
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) ds[p] = acc;
+          }
+          __syncthreads();
+          float sd = 0.f;
+          for (int p = threadIdx.x; p < HW; p += blockDim.x) sd = fmaf(sft[p], ds[p], sd);
+          sd = block_reduce<0>(sd, red);
+          float* gi = which ? gin1 : gin0;
+          for (int p = threadIdx.x; p < HW; p += blockDim.x) gi[p] += sft[p] * (ds[p] - sd);
+          __syncthreads();
+        }
+        break;
+      }
+      case OP_FIND: case OP_FILTER: case OP_FIND_SAME_PROPERTY: {
+        // out = l2norm_c(m∘coef)·w2 + b2 with coef = tau (Find/Filter) or tau∘phi (FSP)
+        const bool fsp = (nd.op == OP_FIND_SAME_PROPERTY);
+        const int es = fsp ? ES_FSP : ES_FIND;
+        float* coef = v; float* phi = v + Mp; float* dcoef = v + 2 * Mp; float* dw2 = v + 3 * Mp;
+        float* gm = a1;   // gradient that reaches the l2norm/conv_eltwise output
+        const float* tau = c.tb.tau + (size_t)nd.text * Mp;
+        const float* w2 = md.elt_w[es];
+        const float b2 = md.elt_b[es][0];
+        const float* mimg;
+        if (nd.op == OP_FILTER) {
+          // out = min(a, find): gradient to `a` where out == a (ties included), else to find
+          for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+            const bool to_a = (fout[p] == fin0[p]);
+            if (to_a) { gin0[p] += g[p]; gm[p] = 0.f; } else { gm[p] = g[p]; }
+          }
+        } else {
+          for (int p = threadIdx.x; p < HW; p += blockDim.x) gm[p] = g[p];
+        }
+        if (fsp) {
+          for (int p = threadIdx.x; p < HW; p += blockDim.x) a0[p] = fin0[p];
+          __syncthreads();
+          softmax_inplace(a0, HW, red);
+          const float* G = c.mbuf + (size_t)nd.aux2 * HW * Mp;
+          for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
+            float p0 = 0.f;
+            if (ch < M) for (int p = 0; p < HW; ++p) p0 = fmaf(a0[p], G[(size_t)p * Mp + ch], p0);
+            phi[ch] = p0;
+            coef[ch] = (ch < M) ? tau[ch] * p0 : 0.f;
+          }
+          mimg = c.mbuf + (size_t)nd.aux * HW * Mp;
+        } else {
+          for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) coef[ch] = (ch < M) ? tau[ch] : 0.f;
+          mimg = c.mbuf + (size_t)nd.aux * HW * Mp;   // training schedules store the Find maps too
+        }
+        for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) { dcoef[ch] = 0.f; dw2[ch] = 0.f; }
+        __syncthreads();
+        const int ent = node_entry[i];
+        float* B = c.dmap + (size_t)ent * HW * Mp;       // dm rows
+        float db2 = 0.f;
+        for (int p = warp; p < HW; p += nwarps) {
+          const float gp = gm[p];
+          const float* mrow = mimg + (size_t)p * Mp;
+          float ss = 0.f, num = 0.f;
+          for (int ch = lane; ch < M; ch += 32) {
+            const float ev = mrow[ch] * coef[ch];
+            ss = fmaf(ev, ev, ss);
+            num = fmaf(ev, w2[ch], num);
+          }
+          ss = warp_sum(ss); num = warp_sum(num);
+          const float inv = rsqrtf(fmaxf(ss, kEps));
+          const float proj = (ss > kEps) ? num * inv : 0.f;   // ê·w2
+          for (int ch = lane; ch < Mp; ch += 32) {
+            float dm = 0.f;
+            if (ch < M) {
+              const float mv = mrow[ch], eh = mv * coef[ch] * inv;
+              const float dev = gp * (w2[ch] - eh * proj) * inv;
+              dm = dev * coef[ch];
+              atomicAdd(&dcoef[ch], dev * mv);
+              atomicAdd(&dw2[ch], gp * eh);
+            }
+            B[(size_t)p * Mp + ch] = dm;
+          }
+          if (lane == 0) db2 += gp;
+        }
+        if (lane == 0) atomicAdd(c.gflat + c.go.elt_b[es], db2);
+        __syncthreads();
+        float* dtau = c.dtau + (size_t)nd.text * Mp;
+        for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
+          if (ch < M) atomicAdd(c.gflat + c.go.elt_w[es] + ch, dw2[ch]);
+          dtau[ch] = (ch < M) ? (fsp ? dcoef[ch] * phi[ch] : dcoef[ch]) : 0.f;
+        }
+        if (fsp) {
+          // dphi = dcoef∘tau -> second B map (s_p*dphi) and the softmax backward into input_0
+          float* dphi = v + 4 * Mp;
+          for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) dphi[ch] = (ch < M) ? dcoef[ch] * tau[ch] : 0.f;
+          __syncthreads();
+          const float* G = c.mbuf + (size_t)nd.aux2 * HW * Mp;
+          float* B2 = c.dmap + (size_t)(ent + 1) * HW * Mp;
+          for (int p = warp; p < HW; p += nwarps) {
+            float acc = 0.f;
+            const float sp = a0[p];
+            for (int ch = lane; ch < Mp; ch += 32) {
+              acc = fmaf(G[(size_t)p * Mp + ch], dphi[ch], acc);
+              B2[(size_t)p * Mp + ch] = sp * dphi[ch];
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) da[p] = acc;
+          }
+          __syncthreads();
+          float sd = 0.f;
+          for (int p = threadIdx.x; p < HW; p += blockDim.x) sd = fmaf(a0[p], da[p], sd);
+          sd = block_reduce<0>(sd, red);
+          for (int p = threadIdx.x; p < HW; p += blockDim.x) gin0[p] += a0[p] * (da[p] - sd);
+        }
+        break;
+      }
+      case OP_TRANSFORM: {
+        // A = conv(a)+bK ; e = A∘tau ; out = l2norm(e)·w2 + b2
+        const int PW = Ww + KS - 1, PH = Hh + KS - 1, R = (KS - 1) / 2;
+        float* tauv = v; float* w2v = v + Mp; float* bkv = v + 2 * Mp; float* dtauv = v + 3 * Mp;
+        float* dw2v = v + 4 * Mp; float* dbkv = v + 5 * Mp;
+        const float* tau = c.tb.tau + (size_t)nd.text * Mp;
+        for (int j = threadIdx.x; j < PH * PW; j += blockDim.x) { pad[j] = 0.f; dpad[j] = 0.f; }
+        for (int j = threadIdx.x; j < KS * KS * Mp; j += blockDim.x) { ks[j] = md.conv_k[j]; dks[j] = 0.f; }
+        for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
+          const bool live = ch < M;
+          tauv[ch] = live ? tau[ch] : 0.f;
+          w2v[ch] = live ? md.elt_w[ES_TRANSFORM][ch] : 0.f;
+          bkv[ch] = live ? md.conv_b[ch] : 0.f;
+          dtauv[ch] = 0.f; dw2v[ch] = 0.f; dbkv[ch] = 0.f;
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+          const int y = p / Ww, x = p - y * Ww;
+          pad[(y + R) * PW + x + R] = fin0[p];
+        }
+        __syncthreads();
+        float db2 = 0.f;
+        constexpr int kMaxCh = 16;   // conv Transform exists for Mp <= 512 (CLEVR 256, SHAPES 512)
+        const int nj = Mp >> 5;
+        for (int p = warp; p < HW; p += nwarps) {
+          const int y = p / Ww, x = p - y * Ww;
+          const float gp = g[p];
+          float A[kMaxCh];
+          float ss = 0.f, num = 0.f;
+#pragma unroll
+          for (int j = 0; j < kMaxCh; ++j) {
+            A[j] = 0.f;
+            if (j < nj) {
+              const int ch = j * 32 + lane;
+              float acc = bkv[ch];
+              for (int dy = 0; dy < KS; ++dy)
+                for (int dx = 0; dx < KS; ++dx)
+                  acc = fmaf(pad[(y + dy) * PW + x + dx], ks[(dy * KS + dx) * Mp + ch], acc);
+              A[j] = acc;
+              const float ev = acc * tauv[ch];
+              ss = fmaf(ev, ev, ss);
+              num = fmaf(ev, w2v[ch], num);
+            }
+          }
+          ss = warp_sum(ss); num = warp_sum(num);
+          const float inv = rsqrtf(fmaxf(ss, kEps));
+          const float proj = (ss > kEps) ? num * inv : 0.f;
+#pragma unroll
+          for (int j = 0; j < kMaxCh; ++j) {
+            if (j < nj) {
+              const int ch = j * 32 + lane;
+              const float eh = A[j] * tauv[ch] * inv;
+              const float dev = gp * (w2v[ch] - eh * proj) * inv;
+              const float dA = dev * tauv[ch];
+              atomicAdd(&dtauv[ch], dev * A[j]);
+              atomicAdd(&dw2v[ch], gp * eh);
+              atomicAdd(&dbkv[ch], dA);
+              A[j] = dA;   // keep dA for the filter / input gradients below
+            }
+          }
+          for (int dy = 0; dy < KS; ++dy)
+            for (int dx = 0; dx < KS; ++dx) {
+              const int off = (y + dy) * PW + x + dx, tap = dy * KS + dx;
+              const float av = pad[off];
+              float contrib = 0.f;
+#pragma unroll
+              for (int j = 0; j < kMaxCh; ++j) {
+                if (j < nj) {
+                  const int ch = j * 32 + lane;
+                  atomicAdd(&dks[tap * Mp + ch], av * A[j]);
+                  contrib = fmaf(ks[tap * Mp + ch], A[j], contrib);
+                }
+              }
+              contrib = warp_sum(contrib);
+              if (lane == 0) atomicAdd(&dpad[off], contrib);
+            }
+          if (lane == 0) db2 += gp;
+        }
+        if (lane == 0) atomicAdd(c.gflat + c.go.elt_b[ES_TRANSFORM], db2);
+        __syncthreads();
+        float* dtau = c.dtau + (size_t)nd.text * Mp;
+        for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
+          dtau[ch] = dtauv[ch];
+          if (ch < M) {
+            atomicAdd(c.gflat + c.go.elt_w[ES_TRANSFORM] + ch, dw2v[ch]);
+            atomicAdd(c.gflat + c.go.conv_b + ch, dbkv[ch]);
+          }
+        }
+        for (int j = threadIdx.x; j < KS * KS * M; j += blockDim.x) {
+          const int tap = j / M, ch = j - tap * M;
+          atomicAdd(c.gflat + c.go.conv_k + j, dks[tap * Mp + ch]);
+        }
+        for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+          const int y = p / Ww, x = p - y * Ww;
+          gin0[p] += dpad[(y + R) * PW + x + R];
+        }
+        break;
+      }
+      default: break;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- text layers ---------------------------------------------------------------------------------
+// grid = (ceil(Dt/8), NUM_TEXT_SETS): d(fc_text W)[k, :] for 8 rows k of one set, summed over the
+// set's text rows; block (0, set) also reduces the bias gradient.
+__global__ void __launch_bounds__(256)
+text_wgrad_kernel(DevModel md, const float* __restrict__ dtau, const int32_t* __restrict__ text_t,
+                  const int32_t* __restrict__ text_b, const int32_t* __restrict__ set_start,
+                  float* __restrict__ gflat, GradOffsets go) {
+  const int set = blockIdx.y, k0 = blockIdx.x * 8;
+  const int r0 = set_start[set], r1 = set_start[set + 1];
+  if (r0 == r1) return;
+  const int Dt = md.Dt, M = md.M, Mp = md.Mp;
+  for (int cbase = 0; cbase < M; cbase += blockDim.x) {
+    const int ch = cbase + threadIdx.x;
+    float acc[8], bsum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (ch < M) {
+      for (int r = r0; r < r1; ++r) {
+        const float d = dtau[(size_t)r * Mp + ch];
+        const float* t = md.word_vecs + ((size_t)text_t[r] * md.N + text_b[r]) * Dt;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (k0 + j < Dt) acc[j] = fmaf(t[k0 + j], d, acc[j]);
+        bsum += d;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (k0 + j < Dt) gflat[go.txt_w[set] + (size_t)(k0 + j) * M + ch] = acc[j];
+      if (blockIdx.x == 0) gflat[go.txt_b[set] + ch] = bsum;
+    }
+  }
+}
+
+// d(word_vecs)[t, b, k] = Σ_c W[k, c]·dtau[row, c]; one CTA per text row (each (t,b) belongs to
+// exactly one node, so plain stores; rows never touched stay zero from the memset).
+__global__ void __launch_bounds__(256)
+text_xgrad_kernel(DevModel md, const float* __restrict__ dtau, const int32_t* __restrict__ text_t,
+                  const int32_t* __restrict__ text_b, const int32_t* __restrict__ set_start,
+                  float* __restrict__ dword) {
+  extern __shared__ float sdt[];
+  const int r = blockIdx.x;
+  int set = 0;
+  while (set + 1 < NUM_TEXT_SETS && r >= set_start[set + 1]) ++set;
+  const int Dt = md.Dt, M = md.M, Mp = md.Mp;
+  for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) sdt[ch] = dtau[(size_t)r * Mp + ch];
+  __syncthreads();
+  float* dst = dword + ((size_t)text_t[r] * md.N + text_b[r]) * Dt;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int k = warp; k < Dt; k += nwarps) {
+    const float* w = md.txt_w[set] + (size_t)k * Mp;
+    float acc = 0.f;
+    for (int ch = lane; ch < M; ch += 32) acc = fmaf(w[ch], sdt[ch], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) dst[k] = acc;
+  }
+}
+
+// ---- feature-side weight gradients: dW_set[k, c] += Σ_entries Σ_p X_b[p, k]·B_entry[p, c] --------
+// grid = (Dk tiles of 64, M tiles of 64, entry chunks); 256 threads, 4x4 outputs each; the entry
+// chunks are combined with atomics into the zero-initialised gradient buffer.
+constexpr int kFgTile = 64, kFgRows = 32;
+__global__ void __launch_bounds__(256)
+feat_grad_kernel(DevModel md, const float* __restrict__ dmap, const BwdEntry* __restrict__ entries,
+                 int num_entries, int entries_per_cta, float* __restrict__ gflat, GradOffsets go) {
+  __shared__ float xs[kFgRows][kFgTile + 1];
+  __shared__ float bs[kFgRows][kFgTile + 1];
+  const int k0 = blockIdx.x * kFgTile, c0 = blockIdx.y * kFgTile;
+  const int e0 = blockIdx.z * entries_per_cta, e1 = min(num_entries, e0 + entries_per_cta);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, 4x4 outputs each
+  const int HW = md.HW, Mp = md.Mp, M = md.M, Dk = md.Dk;
+  int cur_set = -1;
+  float acc[4][4], bsum[4];
+  auto flush = [&](int set) {
+    if (set < 0) return;
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + ty * 4 + i, ch = c0 + tx * 4 + j;
+        if (k < Dk && ch < M && acc[i][j] != 0.f)
+          atomicAdd(gflat + go.proj_w[set] + (size_t)k * M + ch, acc[i][j]);
+      }
+    if (blockIdx.x == 0 && ty == 0)
+      for (int j = 0; j < 4; ++j) {
+        const int ch = c0 + tx * 4 + j;
+        if (ch < M && bsum[j] != 0.f) atomicAdd(gflat + go.proj_b[set] + ch, bsum[j]);
+      }
+  };
+  for (int e = e0; e < e1; ++e) {
+    const BwdEntry en = entries[e];
+    if (en.set != cur_set) {
+      flush(cur_set);
+      cur_set = en.set;
+      for (int i = 0; i < 4; ++i) { bsum[i] = 0.f; for (int j = 0; j < 4; ++j) acc[i][j] = 0.f; }
+    }
+    const float* X = md.feat + (size_t)en.b * HW * md.feat_pitch;
+    const float* B = dmap + (size_t)e * HW * Mp;
+    for (int p0 = 0; p0 < HW; p0 += kFgRows) {
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < kFgRows * kFgTile; idx += blockDim.x) {
+        const int r = idx / kFgTile, cc = idx - r * kFgTile;
+        const int p = p0 + r;
+        xs[r][cc] = (p < HW && k0 + cc < Dk) ? X[(size_t)p * md.feat_pitch + k0 + cc] : 0.f;
+        bs[r][cc] = (p < HW && c0 + cc < Mp) ? B[(size_t)p * Mp + c0 + cc] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int r = 0; r < kFgRows; ++r) {
+        float xv[4], bv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { xv[i] = xs[r][ty * 4 + i]; bv[i] = bs[r][tx * 4 + i]; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], bv[j], acc[i][j]);
+        if (ty == 0)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bsum[j] += bv[j];
+      }
+    }
+  }
+  flush(cur_set);
+}
+
+// ---- optimiser ---------------------------------------------------------------------------------
+struct VarSeg { int offset, count, decay; };   // decay = 1 for ".../weights" variables
+
+// g += wd*w for weights variables, then Σ g² per variable.
+__global__ void grad_norm_kernel(const float* __restrict__ w, float* __restrict__ g,
+                                 const VarSeg* __restrict__ segs, float weight_decay,
+                                 float* __restrict__ sumsq) {
+  const VarSeg s = segs[blockIdx.y];
+  float acc = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s.count; i += gridDim.x * blockDim.x) {
+    float gv = g[s.offset + i];
+    if (s.decay) { gv = fmaf(weight_decay, w[s.offset + i], gv); g[s.offset + i] = gv; }
+    acc = fmaf(gv, gv, acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0 && acc != 0.f) atomicAdd(sumsq + blockIdx.y, acc);
+}
+
+// tf.clip_by_norm per tensor, then Adam (TF: lr_t = lr*sqrt(1-b2^t)/(1-b1^t)).
+__global__ void adam_clip_kernel(float* __restrict__ w, const float* __restrict__ g,
+                                 float* __restrict__ m, float* __restrict__ v,
+                                 const VarSeg* __restrict__ segs, const float* __restrict__ sumsq,
+                                 float lr_t, float b1, float b2, float eps, float max_norm) {
+  const VarSeg s = segs[blockIdx.y];
+  const float nrm = sqrtf(sumsq[blockIdx.y]);
+  const float scale = (nrm > max_norm) ? max_norm / nrm : 1.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s.count; i += gridDim.x * blockDim.x) {
+    const int o = s.offset + i;
+    const float gv = g[o] * scale;
+    const float mv = b1 * m[o] + (1.f - b1) * gv;
+    const float vv = b2 * v[o] + (1.f - b2) * gv * gv;
+    m[o] = mv; v[o] = vv;
+    w[o] -= lr_t * mv / (sqrtf(vv) + eps);
+  }
+}
+
+}  // namespace n2nmn

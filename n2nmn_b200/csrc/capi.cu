@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -20,6 +21,7 @@
 #include "schedule.hpp"
 #include "text_proj.cuh"
 #include "tree_kernel.cuh"
+#include "backward.cuh"
 
 using namespace n2nmn;
 
@@ -65,7 +67,7 @@ struct TableSlot {
 
 struct TableOffsets {
   size_t nodes, q_ptr, text_t, text_b, groups, work, img_ptr, node_text, node_out, mslot,
-      wave_nodes, total;
+      wave_nodes, node_entry, entries, text_set_start, labels, total;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -118,6 +120,20 @@ struct n2nmn_ctx {
   bool use_pdl = true;         // programmatic dependent launch between the three kernels
   n2nmn_sched module_sched;    // scratch schedule of n2nmn_module_fwd
   n2nmn_sched step_sched;      // scratch schedule of n2nmn_forward_tokens
+  // training workspaces (allocated on first use)
+  const int32_t* train_labels = nullptr;   // host labels of the step being compiled
+  const uint8_t* last_tables = nullptr;    // device tables of the last run_tables
+  TableOffsets last_offsets;
+  float* dscores = nullptr;
+  float* per_sample = nullptr;
+  float* dtau = nullptr;
+  float* dmap = nullptr;
+  int dmap_entries = 0;
+  VarSeg* d_segs = nullptr;
+  float* d_sumsq = nullptr;
+  GradOffsets go;
+  std::vector<int64_t> flat_offset;
+  int64_t flat_size = 0;
   // e2e staging
   float* e2e_feat = nullptr;
   float* e2e_wv = nullptr;
@@ -242,6 +258,10 @@ TableOffsets table_offsets(const HostSchedule& S) {
   o.node_out = take(S.node_out.size() * 4);
   o.mslot = take(S.mslot.size() * 4);
   o.wave_nodes = take(S.wave_nodes.size() * 4);
+  o.node_entry = take(S.node_entry.size() * 4);
+  o.entries = take(S.entries.size() * sizeof(BwdEntryHost));
+  o.text_set_start = take(S.text_set_start.size() * 4);
+  o.labels = take(S.train ? (S.q_ptr.size() - 1) * 4 : 0);
   o.total = off;
   return o;
 }
@@ -293,10 +313,17 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaS
     put(slot->host, o.node_out, S.node_out);
     put(slot->host, o.mslot, S.mslot);
     put(slot->host, o.wave_nodes, S.wave_nodes);
+    put(slot->host, o.node_entry, S.node_entry);
+    put(slot->host, o.entries, S.entries);
+    put(slot->host, o.text_set_start, S.text_set_start);
+    if (S.train && c->train_labels)
+      std::memcpy(slot->host + o.labels, c->train_labels, (S.q_ptr.size() - 1) * 4);
     CUDA_TRY(cudaMemcpyAsync(slot->dev, slot->host, o.total, cudaMemcpyHostToDevice, st));
     slot->uid = sc->uid;
   }
   const uint8_t* d = slot->dev;
+  c->last_tables = d;
+  c->last_offsets = o;
   const NodeRec* d_nodes = reinterpret_cast<const NodeRec*>(d + o.nodes);
   const int32_t* d_qptr = reinterpret_cast<const int32_t*>(d + o.q_ptr);
 
@@ -462,6 +489,38 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
   c->shp = SchedShape{cfg->family, cfg->H, cfg->W, c->Dk, cfg->text_dim, cfg->map_dim, c->Mp,
                       cfg->num_choices, c->cfg.kernel_size, cfg->max_T};
   build_variables(c);
+  {   // flat TF-layout buffer (weights / gradients / Adam moments) and where each gradient goes
+    int64_t off = 0;
+    std::memset(&c->go, 0, sizeof(c->go));
+    for (const Variable& v : c->vars) {
+      c->flat_offset.push_back(off);
+      const int o = (int)off;
+      if (v.kind == VK_PROJ_W) c->go.proj_w[v.set] = o;
+      else if (v.kind == VK_PROJ_B) c->go.proj_b[v.set] = o;
+      else {
+        for (int i = 0; i < NUM_TEXT_SETS; ++i) {
+          if (v.slot == &md.txt_w[i]) c->go.txt_w[i] = o;
+          if (v.slot == &md.txt_b[i]) c->go.txt_b[i] = o;
+        }
+        for (int i = 0; i < NUM_ELT_SETS; ++i) {
+          if (v.slot == &md.elt_w[i]) c->go.elt_w[i] = o;
+          if (v.slot == &md.elt_b[i]) c->go.elt_b[i] = o;
+        }
+        for (int i = 0; i < NUM_OUT_SETS; ++i) {
+          if (v.slot == &md.out_w[i]) c->go.out_w[i] = o;
+          if (v.slot == &md.out_b[i]) c->go.out_b[i] = o;
+        }
+        for (int i = 0; i < NUM_SCORE_SETS; ++i) {
+          if (v.slot == &md.sc_w[i]) c->go.sc_w[i] = o;
+          if (v.slot == &md.sc_b[i]) c->go.sc_b[i] = o;
+        }
+        if (v.slot == &md.conv_k) c->go.conv_k = o;
+        if (v.slot == &md.conv_b) c->go.conv_b = o;
+      }
+      off += (int64_t)((v.count + 3) & ~(size_t)3);
+    }
+    c->flat_size = off;
+  }
 
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -499,7 +558,7 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
   c->tb.tau2 = c->tb.tauw + tb_floats;
   c->arena_slots = std::max(NB * TT, 3 * NB);
   CUDA_TRY(cudaMalloc(&c->arena, (size_t)c->arena_slots * c->HW * sizeof(float)));
-  c->mbuf_slots = std::max(1, c->num_store_sets) * NB;
+  c->mbuf_slots = (c->num_store_sets + 1) * NB;   // +1: conv_image maps of Find kept for backward
   CUDA_TRY(cudaMalloc(&c->mbuf, (size_t)c->mbuf_slots * c->HW * c->Mp * sizeof(float)));
   CUDA_TRY(cudaMalloc(&c->scores_tmp, (size_t)NB * TT * cfg->num_choices * sizeof(float)));
   if (cfg->family == N2NMN_VQA || (cfg->D % 4) != 0) {
@@ -511,7 +570,7 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
     const size_t tiles = ((size_t)NB * c->HW + 127) / 128 + 1;
     c->table_cap = nodes * (sizeof(NodeRec) + 4 * 6) + (nodes / 8 + 8) * sizeof(TextGroup) +
                    tiles * (TT / kMaxProjNodesPerPass + 1 + NUM_PROJ_SETS) * sizeof(ProjWork) +
-                   (size_t)NB * (8 + 4 * NUM_PROJ_SETS) + 4096;
+                   (size_t)NB * (12 + 4 * NUM_PROJ_SETS) + nodes * (4 + 2 * sizeof(BwdEntryHost)) + 4096;
     for (int i = 0; i < kTableSlots; ++i) {
       CUDA_TRY(cudaMallocHost(&c->slots[i].host, c->table_cap));
       CUDA_TRY(cudaMalloc(&c->slots[i].dev, c->table_cap));
@@ -562,6 +621,8 @@ int n2nmn_destroy(n2nmn_ctx* c) {
   cudaFree(c->wbuf);
   for (int s = 0; s < NUM_PROJ_SETS; ++s) { cudaFree(c->proj_wt[s]); cudaFree(c->proj_bias[s]); }
   cudaFree(c->feat_aug); cudaFree(c->tb.tau); cudaFree(c->arena); cudaFree(c->mbuf);
+  cudaFree(c->dscores); cudaFree(c->per_sample); cudaFree(c->dtau); cudaFree(c->dmap);
+  cudaFree(c->d_segs); cudaFree(c->d_sumsq);
   cudaFree(c->scores_tmp); cudaFree(c->e2e_feat); cudaFree(c->e2e_wv); cudaFree(c->e2e_scores);
   for (int i = 0; i < kTableSlots; ++i) {
     cudaFreeHost(c->slots[i].host); cudaFree(c->slots[i].dev);
@@ -892,6 +953,157 @@ int n2nmn_forward_host(n2nmn_ctx* c, const float* feat_host, const float* wv_hos
     cudaStreamSynchronize(st);
   }
   return rc;
+}
+
+
+int64_t n2nmn_flat_size(const n2nmn_ctx* c) { return c ? c->flat_size : 0; }
+
+int n2nmn_flat_offset(const n2nmn_ctx* c, int index, int64_t* offset, int64_t* count) {
+  if (!c || index < 0 || index >= (int)c->vars.size()) return fail(N2NMN_ERR_ARG, "bad index");
+  if (offset) *offset = c->flat_offset[index];
+  if (count) *count = (int64_t)c->vars[index].count;
+  return 0;
+}
+
+int n2nmn_load_flat_weights(n2nmn_ctx* c, const float* wflat_dev, void* stream) {
+  if (!c || !wflat_dev) return fail(N2NMN_ERR_ARG, "null argument");
+  for (size_t i = 0; i < c->vars.size(); ++i) {
+    const Variable& v = c->vars[i];
+    if (int rc = n2nmn_set_weight(c, v.name.c_str(), wflat_dev + c->flat_offset[i], v.shape.data(),
+                                  (int)v.shape.size(), stream))
+      return rc;
+  }
+  return 0;
+}
+
+int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_dev,
+                         const int32_t* tokens, int T, int N, const int32_t* vocab_ops,
+                         int num_vocab, const int32_t* labels_host, float invalid_expr_loss,
+                         float* scores_dev, float* gflat_dev, float* dword_dev, float* loss_dev,
+                         uint8_t* validity_out, void* stream) {
+  if (!c || !tokens || !vocab_ops || !labels_host || !scores_dev || !gflat_dev || !loss_dev)
+    return fail(N2NMN_ERR_ARG, "null argument");
+  if (c->cfg.flags & N2NMN_FLAG_WAVE_EXECUTOR)
+    return fail(N2NMN_ERR_ARG, "training uses the tree executor");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = n2nmn_bind_inputs(c, feat_dev, wv_dev, N, T, stream)) return rc;
+  if (int rc = check_ready(c)) return rc;
+  const int NB = c->cfg.max_batch, TT = c->cfg.max_T, C = c->cfg.num_choices;
+  if (!c->dscores) {
+    CUDA_TRY(cudaMalloc(&c->dscores, (size_t)NB * C * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c->per_sample, (size_t)NB * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c->dtau, (size_t)c->text_rows_cap * c->Mp * sizeof(float)));
+    c->dmap_entries = NB * TT;
+    CUDA_TRY(cudaMalloc(&c->dmap, (size_t)c->dmap_entries * c->HW * c->Mp * sizeof(float)));
+    const BwdSmem L = bwd_smem_layout(c->cfg.H, c->cfg.W, c->Mp, c->cfg.kernel_size, C, TT);
+    CUDA_TRY(cudaFuncSetAttribute(tree_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(L.total * sizeof(float))));
+    CUDA_TRY(cudaFuncSetAttribute(tree_bwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(L.total * sizeof(float))));
+  }
+  n2nmn_sched* sc = &c->step_sched;
+  sc->uid = g_uid++;
+  const char* err = nullptr;
+  if (int rc = compile_schedule(c->shp, tokens, T, N, vocab_ops, num_vocab, &sc->hs, &err, true))
+    return fail(rc, err ? err : "compile_schedule failed");
+  const HostSchedule& S = sc->hs;
+  if (validity_out) std::memcpy(validity_out, S.validity.data(), N);
+  if ((int)S.nodes.size() > c->arena_slots || (int)S.entries.size() > c->dmap_entries)
+    return fail(N2NMN_ERR_CAPACITY, "too many nodes for the context");
+  if (S.max_stack > c->stack_cap)
+    return fail(N2NMN_ERR_CAPACITY, "layout too deep for the training path");
+  for (int i = 0; i < N; ++i)
+    if (labels_host[i] < 0 || labels_host[i] >= C) return fail(N2NMN_ERR_ARG, "label out of range");
+  // ---- forward (keeps every attention map in the context arena + the stored maps)
+  c->train_labels = labels_host;
+  const int rc = run_tables(c, sc, scores_dev, c->arena, st, false, /*write_arena=*/true);
+  c->train_labels = nullptr;
+  if (rc) return rc;
+  const uint8_t* d = c->last_tables;
+  const TableOffsets& o = c->last_offsets;
+  const NodeRec* d_nodes = reinterpret_cast<const NodeRec*>(d + o.nodes);
+  const int32_t* d_qptr = reinterpret_cast<const int32_t*>(d + o.q_ptr);
+  // ---- loss and d(scores)
+  CUDA_TRY(cudaMemsetAsync(gflat_dev, 0, (size_t)c->flat_size * sizeof(float), st));
+  CUDA_TRY(cudaMemsetAsync(loss_dev, 0, sizeof(float), st));
+  if (dword_dev)
+    CUDA_TRY(cudaMemsetAsync(dword_dev, 0, (size_t)T * N * c->cfg.text_dim * sizeof(float), st));
+  loss_kernel<<<(N + 7) / 8, 256, 0, st>>>(scores_dev, reinterpret_cast<const int32_t*>(d + o.labels),
+                                           d_qptr, N, C, invalid_expr_loss, c->dscores,
+                                           loss_dev + 1, loss_dev);
+  ++c->launches;
+  // ---- reverse tree walk
+  BwdCtx bc;
+  bc.md = c->md; bc.tb = c->tb; bc.arena = c->arena; bc.scores = scores_dev;
+  bc.dscores = c->dscores; bc.mbuf = c->mbuf; bc.gflat = gflat_dev; bc.dtau = c->dtau;
+  bc.dmap = c->dmap; bc.go = c->go; bc.max_nodes_q = TT;
+  const BwdSmem L = bwd_smem_layout(c->cfg.H, c->cfg.W, c->Mp, c->cfg.kernel_size, C, TT);
+  const size_t bsm = L.total * sizeof(float);
+  const int32_t* d_entry = reinterpret_cast<const int32_t*>(d + o.node_entry);
+  if (c->cfg.kernel_size != 5)
+    tree_bwd_kernel<3><<<N, kNodeThreads, bsm, st>>>(bc, d_nodes, d_qptr, d_entry);
+  else
+    tree_bwd_kernel<5><<<N, kNodeThreads, bsm, st>>>(bc, d_nodes, d_qptr, d_entry);
+  ++c->launches;
+  // ---- text layers
+  const int rows = (int)S.text_t.size();
+  if (rows > 0) {
+    const int32_t* d_tt = reinterpret_cast<const int32_t*>(d + o.text_t);
+    const int32_t* d_tb = reinterpret_cast<const int32_t*>(d + o.text_b);
+    const int32_t* d_ss = reinterpret_cast<const int32_t*>(d + o.text_set_start);
+    dim3 g1((c->cfg.text_dim + 7) / 8, NUM_TEXT_SETS);
+    text_wgrad_kernel<<<g1, 256, 0, st>>>(c->md, c->dtau, d_tt, d_tb, d_ss, gflat_dev, c->go);
+    ++c->launches;
+    if (dword_dev) {
+      text_xgrad_kernel<<<rows, 256, c->Mp * sizeof(float), st>>>(c->md, c->dtau, d_tt, d_tb, d_ss,
+                                                                 dword_dev);
+      ++c->launches;
+    }
+  }
+  // ---- feature-side layers: dW_set = Σ X^T·B
+  const int ne = (int)S.entries.size();
+  if (ne > 0) {
+    const int chunks = std::min(ne, 8);
+    const int per = (ne + chunks - 1) / chunks;
+    dim3 g2((c->Dk + kFgTile - 1) / kFgTile, (c->cfg.map_dim + kFgTile - 1) / kFgTile,
+            (ne + per - 1) / per);
+    feat_grad_kernel<<<g2, 256, 0, st>>>(c->md, c->dmap,
+                                         reinterpret_cast<const BwdEntry*>(d + o.entries), ne, per,
+                                         gflat_dev, c->go);
+    ++c->launches;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int n2nmn_adam_step(n2nmn_ctx* c, float* wflat, float* gflat, float* m, float* v, int step,
+                    float lr, float beta1, float beta2, float eps, float max_norm,
+                    float weight_decay, void* stream) {
+  if (!c || !wflat || !gflat || !m || !v || step < 1) return fail(N2NMN_ERR_ARG, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nv = (int)c->vars.size();
+  if (!c->d_segs) {
+    std::vector<VarSeg> segs(nv);
+    for (int i = 0; i < nv; ++i) {
+      segs[i].offset = (int)c->flat_offset[i];
+      segs[i].count = (int)c->vars[i].count;
+      const std::string& n = c->vars[i].name;   // l2_reg covers ".../weights" only
+      segs[i].decay = n.size() >= 8 && n.compare(n.size() - 8, 8, "/weights") == 0;
+    }
+    CUDA_TRY(cudaMalloc(&c->d_segs, nv * sizeof(VarSeg)));
+    CUDA_TRY(cudaMemcpy(c->d_segs, segs.data(), nv * sizeof(VarSeg), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&c->d_sumsq, nv * sizeof(float)));
+  }
+  CUDA_TRY(cudaMemsetAsync(c->d_sumsq, 0, nv * sizeof(float), st));
+  dim3 grid(32, nv);
+  grad_norm_kernel<<<grid, 256, 0, st>>>(wflat, gflat, c->d_segs, weight_decay, c->d_sumsq);
+  const double lr_t = (double)lr * std::sqrt(1.0 - std::pow((double)beta2, step)) /
+                      (1.0 - std::pow((double)beta1, step));
+  adam_clip_kernel<<<grid, 256, 0, st>>>(wflat, gflat, m, v, c->d_segs, c->d_sumsq, (float)lr_t,
+                                         beta1, beta2, eps, max_norm);
+  c->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return n2nmn_load_flat_weights(c, wflat, stream);
 }
 
 int n2nmn_set_profiling(n2nmn_ctx* c, int enabled) {

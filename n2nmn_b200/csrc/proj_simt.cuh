@@ -88,9 +88,10 @@ proj_simt_kernel(ProjParams p) {
               p.arena[(size_t)p.node_out[e] * p.HW + pix] =
                   num * rsqrtf(fmaxf(den, kEps)) + p.elt_b[0];
           }
-        } else {
+        }
+        {
           const int slot = p.mslot[wk.set * p.num_images + b];
-          if (slot >= 0) {
+          if (slot >= 0 && wk.pass == 0) {
             float* dst = p.mbuf + ((size_t)slot * p.HW + pix) * p.Mp;
             for (int c = lane; c < p.Mp; c += 32) dst[c] = mrow[c];
           }

@@ -158,10 +158,10 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
           e_beg = p.img_ptr[b] + wk.pass * kMaxProjNodesPerPass;
           n_nodes = min(p.img_ptr[b + 1] - e_beg, kMaxProjNodesPerPass);
           n_nodes = max(n_nodes, 0);
-        } else {
-          const int slot = p.mslot[wk.set * p.num_images + b];
-          if (slot >= 0) mdst = p.mbuf + ((size_t)slot * p.HW + pix) * p.Mp;
         }
+        // stored map (always for the non-Find sets; for PS_FIND only in training schedules)
+        const int slot = p.mslot[wk.set * p.num_images + b];
+        if (slot >= 0 && wk.pass == 0) mdst = p.mbuf + ((size_t)slot * p.HW + pix) * p.Mp;
       }
       float num[kMaxProjNodesPerPass], den[kMaxProjNodesPerPass];
 #pragma unroll

@@ -33,7 +33,7 @@ struct Pending {   // a parsed node before text rows are assigned
 
 int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
                      const int32_t* vocab_ops, int num_vocab, HostSchedule* out,
-                     const char** err) {
+                     const char** err, bool train) {
   HostSchedule& S = *out;
   S.reset();
   S.N = N; S.T = T;
@@ -100,10 +100,10 @@ int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
   S.depth.resize(num_nodes);
   for (int i = 0; i < num_nodes; ++i) { S.nodes[i] = all[i].rec; S.depth[i] = all[i].depth; }
   (void)err;
-  return finalize_schedule(shp, N, out);
+  return finalize_schedule(shp, N, out, train);
 }
 
-int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out) {
+int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out, bool train) {
   HostSchedule& S = *out;
   const int N = num_images;                 // images (rows of the feature grid)
   const int NQ = (int)S.q_ptr.size() - 1;   // questions (rows of the score matrix)
@@ -134,6 +134,7 @@ int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out) 
     }
     S.max_depth = std::max(S.max_depth, S.depth[i]);
   }
+  S.text_set_start.assign(set_start, set_start + NUM_TEXT_SETS + 1);
   for (int s = 0; s < NUM_TEXT_SETS; ++s)
     for (int r = set_start[s]; r < set_start[s + 1]; r += kTextRowsPerCta) {
       TextGroup g;
@@ -151,14 +152,29 @@ int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out) 
     if (slot < 0) slot = S.num_mslots++;
     return slot;
   };
-  for (NodeRec& r : S.nodes) {
+  S.train = train;
+  S.entries.clear();
+  S.node_entry.assign(train ? num_nodes : 0, -1);
+  auto entry = [&](int node, int set, int b) {
+    if (!train) return;
+    if (S.node_entry[node] < 0) S.node_entry[node] = (int)S.entries.size();
+    S.entries.push_back(BwdEntryHost{set, b});
+  };
+  for (int i = 0; i < num_nodes; ++i) {
+    NodeRec& r = S.nodes[i];
     switch (r.op) {
-      case OP_FIND: case OP_FILTER: ++S.img_ptr[r.b + 1]; break;
+      case OP_FIND: case OP_FILTER:
+        ++S.img_ptr[r.b + 1];
+        // training keeps the conv_image map of the image: the backward pass needs m[p,:]
+        if (train) { r.aux = want(PS_FIND, r.b); entry(i, PS_FIND, r.b); }
+        break;
       case OP_FIND_SAME_PROPERTY:
-        r.aux = want(PS_FSP_IMG, r.b); r.aux2 = want(PS_FSP_ATT, r.b); break;
-      case OP_DESCRIBE: r.aux = want(PS_DESC_ATT, r.b); break;
+        r.aux = want(PS_FSP_IMG, r.b); r.aux2 = want(PS_FSP_ATT, r.b);
+        entry(i, PS_FSP_IMG, r.b); entry(i, PS_FSP_ATT, r.b); break;
+      case OP_DESCRIBE: r.aux = want(PS_DESC_ATT, r.b); entry(i, PS_DESC_ATT, r.b); break;
       case OP_SAME_PROPERTY:
-        r.aux = want(PS_SP_ATT0, r.b); r.aux2 = want(PS_SP_ATT1, r.b); break;
+        r.aux = want(PS_SP_ATT0, r.b); r.aux2 = want(PS_SP_ATT1, r.b);
+        entry(i, PS_SP_ATT0, r.b); entry(i, PS_SP_ATT1, r.b); break;
       default: break;
     }
   }
@@ -185,6 +201,7 @@ int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out) 
     if (any) ++u_set[PS_FIND];
     for (int set = 1; set < NUM_PROJ_SETS; ++set)
       if (S.mslot[(size_t)set * N + n] >= 0) { ++u_set[set]; any = true; }
+    // (PS_FIND maps stored for training ride along with the fused pass: no extra work items)
     if (any) ++u_any;
   }
   for (int set = 0; set < NUM_PROJ_SETS; ++set) {

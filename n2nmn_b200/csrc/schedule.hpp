@@ -17,6 +17,8 @@ struct SchedShape {
   int max_T;
 };
 
+struct BwdEntryHost { int32_t set, b; };   // mirrors BwdEntry (backward.cuh)
+
 struct HostSchedule {
   int N = 0, T = 0, num_valid = 0, max_depth = 0;
   std::vector<uint8_t> validity;      // [N]
@@ -32,6 +34,11 @@ struct HostSchedule {
   int max_stack = 0;                  // most attention maps of one question alive at once
   std::vector<int32_t> wave_ptr;      // [max_depth+2], wave d = [wave_ptr[d], wave_ptr[d+1])
   std::vector<int32_t> wave_nodes;
+  // training schedules only: one [HW,Mp] gradient map per feature-side layer use
+  bool train = false;
+  std::vector<BwdEntryHost> entries;
+  std::vector<int32_t> node_entry;     // per node: first entry (or -1)
+  std::vector<int32_t> text_set_start; // [NUM_TEXT_SETS+1] rows of each text weight set
   // §8(d) algorithmic traffic / work, per kernel: 0 text, 1 projection, 2 node kernels
   int64_t kbytes[3] = {0, 0, 0};
   int64_t kflops[3] = {0, 0, 0};
@@ -47,6 +54,7 @@ struct HostSchedule {
     validity.clear(); nodes.clear(); depth.clear(); q_ptr.clear(); text_t.clear();
     text_b.clear(); groups.clear(); work.clear(); img_ptr.clear(); node_text.clear();
     node_out.clear(); mslot.clear(); wave_ptr.clear(); wave_nodes.clear();
+    entries.clear(); node_entry.clear(); text_set_start.clear(); train = false;
     for (int k = 0; k < 3; ++k) kbytes[k] = kflops[k] = 0;
     per_node_bytes = per_node_flops = 0;
     accounted = false;
@@ -56,12 +64,13 @@ struct HostSchedule {
 // Returns 0 or a negative n2nmn_status; `err` receives a message on failure.
 int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
                      const int32_t* vocab_ops, int num_vocab, HostSchedule* out,
-                     const char** err);
+                     const char** err, bool train = false);
 
 // Builds every derived table (text rows, projection work, waves, traffic accounting) from
 // S.nodes / S.depth / S.q_ptr. `num_images` bounds NodeRec::b. Used by compile_schedule and by the
 // per-module entry point, which fabricates one single-node "question" per call row.
-int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out);
+int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out,
+                      bool train = false);
 
 // Fills kbytes / kflops / per_node_* (SURVEY.md §8d). Idempotent.
 void account_schedule(const SchedShape& shp, HostSchedule* out);
