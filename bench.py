@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--wave', action='store_true', help='depth-bucketed wave executor')
+    ap.add_argument('--no-train', action='store_true', help='skip the train-step measurement')
     ap.add_argument('--streams', type=int, default=3,
                     help='contexts/streams fed round-robin (independent batches overlap)')
     return ap.parse_args()
@@ -356,6 +357,40 @@ def main():
                     'peak_source': pk['source'] + '; TF32 peak taken as bf16 burst / 2',
                     'share_of_step': kernel_us[proj] / max(sum(kernel_us.values()), 1e-9)}
 
+    # ---- config 3: policy-search train step (fwd + bwd + ONE NCCL all-reduce + clip + Adam),
+    #      T=10 as in exp_clevr/train_clevr_rl_gt_layout.py; reported beside the eval headline
+    train = None
+    if not args.no_train:
+        from n2nmn_b200.trainer import ModuleNetTrainer
+        T_TRAIN = 10
+        tr_ex = LayoutExecutor('clevr', feats[0], wvs[0][:T_TRAIN].contiguous(), C, asm,
+                               weights=weights, max_batch=B, max_T=T_TRAIN)
+        tr = ModuleNetTrainer(tr_ex)
+        ttok = [np.ascontiguousarray(synth.expert_mix_tokens(asm, B, T_TRAIN)[
+            :, np.random.RandomState(7 + i).permutation(B)]) for i in range(P)]
+        twv = [w[:T_TRAIN].contiguous() for w in wvs]
+        tlab = [np.random.RandomState(11 + i).randint(0, C, size=B) for i in range(P)]
+        lsp = torch.full((B,), -2.0, device=dev)
+        for i in range(5):
+            tr.train_step(feats[i % P], twv[i % P], ttok[i % P], tlab[i % P], log_seq_prob=lsp)
+        k_tr = max(10, min(args.steps, 50))
+        barrier()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for i in range(k_tr):
+            out = tr.train_step(feats[i % P], twv[i % P], ttok[i % P], tlab[i % P],
+                                log_seq_prob=lsp)
+        t1e.record()
+        barrier()
+        tms = torch.tensor([t0e.elapsed_time(t1e)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        train = {'questions_per_sec': world * B * k_tr / (float(tms.item()) * 1e-3),
+                 'ms_per_step': float(tms.item()) / k_tr, 'steps': k_tr, 'global_batch': B * world,
+                 'T_decoder': T_TRAIN, 'last_avg_sample_loss': out['avg_sample_loss'],
+                 'what': 'fwd + bwd + all-reduce(flat grads, %d floats) + per-tensor clip + Adam '
+                         '+ weight re-pack' % (tr.flat_size + 1)}
+
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -383,7 +418,7 @@ def main():
                        'streams': K,
                        'nodes_per_batch': info['num_nodes'], 'max_depth': info['max_depth']},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
-            'roofline': roof, 'cpu_baseline': cpu, 'kernel_us': kernel_us,
+            'roofline': roof, 'cpu_baseline': cpu, 'kernel_us': kernel_us, 'train_step': train,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

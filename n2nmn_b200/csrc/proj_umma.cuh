@@ -92,11 +92,21 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
         for (int nt = 0; nt < p.n_tiles; ++nt) {
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+#if defined(N2NMN_EXP_SKIP_A)      // timing experiments only (results are garbage)
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], kBBytes);
+            ptx::tma_load_2d(smem_b + stage * kBBytes, &tm.b[wk.set], kb * kBK, nt * kBN,
+                             &full_bar[stage]);
+#elif defined(N2NMN_EXP_SKIP_B)
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], kABytes);
+            ptx::tma_load_2d(smem_a + stage * kABytes, &tm.a, kb * kBK, wk.row0,
+                             &full_bar[stage]);
+#else
             ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
             ptx::tma_load_2d(smem_a + stage * kABytes, &tm.a, kb * kBK, wk.row0,
                              &full_bar[stage]);
             ptx::tma_load_2d(smem_b + stage * kBBytes, &tm.b[wk.set], kb * kBK, nt * kBN,
                              &full_bar[stage]);
+#endif
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -120,11 +130,13 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
             ptx::tc_fence_after();
             const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * kABytes));
             const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * kBBytes));
+#if !defined(N2NMN_EXP_SKIP_MMA)
 #pragma unroll
             for (int k = 0; k < kBK / kUmmaK; ++k) {
               // advance 32 bytes (= 2 x 16-byte units) along K inside the swizzle atom
               ptx::umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
             }
+#endif
             ptx::umma_commit(&empty_bar[stage]);              // frees the smem slot when done
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
