@@ -1106,6 +1106,12 @@ int n2nmn_adam_step(n2nmn_ctx* c, float* wflat, float* gflat, float* m, float* v
   return n2nmn_load_flat_weights(c, wflat, stream);
 }
 
+#if defined(N2NMN_EXP_TIMELINE)
+extern "C" int n2nmn_exp_set_timeline(long long* dev_buf) {
+  return cudaMemcpyToSymbol(n2nmn::g_timeline, &dev_buf, sizeof(dev_buf)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 int n2nmn_set_profiling(n2nmn_ctx* c, int enabled) {
   if (!c) return fail(N2NMN_ERR_ARG, "null context");
   c->profiling = enabled != 0;

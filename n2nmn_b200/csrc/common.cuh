@@ -90,6 +90,22 @@ __device__ __forceinline__ void pdl_wait() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// Timeline instrumentation (experiment builds only, -DN2NMN_EXP_TIMELINE): clock64 stamps per CTA.
+#if defined(N2NMN_EXP_TIMELINE)
+__device__ long long* g_timeline = nullptr;   // [kernel 0..2][cta < 512][64]: clock64 | globaltimer
+#define N2NMN_STAMP(kernel, slot)                                                          \
+  do {                                                                                     \
+    if (g_timeline && blockIdx.x < 512 && (slot) < 32 && (threadIdx.x & 31) == 0) {        \
+      unsigned long long gt_;                                                              \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                              \
+      g_timeline[((kernel) * 512 + blockIdx.x) * 64 + (slot)] = clock64();                 \
+      g_timeline[((kernel) * 512 + blockIdx.x) * 64 + 32 + (slot)] = (long long)gt_;       \
+    }                                                                                      \
+  } while (0)
+#else
+#define N2NMN_STAMP(kernel, slot) do {} while (0)
+#endif
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

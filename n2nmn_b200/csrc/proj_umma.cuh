@@ -62,6 +62,7 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_trigger();   // let the node kernel's CTAs start prefetching their parameters
+  if (threadIdx.x == 0) N2NMN_STAMP(1, 0);
 
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tensormap(&tm.a);
@@ -81,6 +82,7 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  if (threadIdx.x == 0) N2NMN_STAMP(1, 1);
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -127,6 +129,7 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
           const uint32_t tmem_d = tmem_base + acc * kBN;
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             ptx::mbar_wait(&full_bar[stage], phase);          // TMA bytes landed
+            if (kb < 16) N2NMN_STAMP(1, 8 + kb);
             ptx::tc_fence_after();
             const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * kABytes));
             const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * kBBytes));
@@ -153,7 +156,9 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
     uint32_t it = 0;
     // tauw / tau2 come from the text-projection kernel, which may still be running (PDL); the
     // TMA / MMA warps above never touch its output and start immediately.
+    if (warp == 2) N2NMN_STAMP(1, 2);
     pdl_wait();
+    if (warp == 2) N2NMN_STAMP(1, 3);
     for (int wi = blockIdx.x; wi < p.num_work; wi += gridDim.x) {
       const ProjWork wk = p.work[wi];
       const int row = wk.row0 + trow;
@@ -202,9 +207,11 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
           }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 2) N2NMN_STAMP(1, 4);
 
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         ptx::mbar_wait(&tmem_full[acc], acc_phase);
+        if (warp == 2) N2NMN_STAMP(1, 5);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kBN;
 #pragma unroll 1
@@ -274,6 +281,7 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
     }
   }
 
+  if (warp == 2) N2NMN_STAMP(1, 6);
   // teardown
   ptx::tc_fence_before();
   __syncthreads();

@@ -25,6 +25,7 @@ text_proj_kernel(DevModel md, TextBufs tb, const TextGroup* __restrict__ groups,
   extern __shared__ float s_dyn[];
   __shared__ int s_src[kTextRowsPerCta];
   pdl_trigger();   // the contraction kernel only needs our output in its epilogue
+  if (threadIdx.x == 0) N2NMN_STAMP(0, 0);
   const int Dt = md.Dt, M = md.M, Mp = md.Mp;
   float* s_x = s_dyn;                                 // [8][Dt]
   float* s_red = s_dyn + kTextRowsPerCta * Dt;        // [8 warps][8 rows][64 cols]
@@ -44,12 +45,14 @@ text_proj_kernel(DevModel md, TextBufs tb, const TextGroup* __restrict__ groups,
     w[j] = (k < Dt) ? __ldg(reinterpret_cast<const float4*>(wbase + (size_t)k * Mp))
                     : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  if (threadIdx.x == 0) N2NMN_STAMP(0, 1);
   // (2) source rows of the group's nodes in the time-major word_vecs: t*N + b
   if (threadIdx.x < kTextRowsPerCta) {
     const int r = threadIdx.x;
     s_src[r] = (r < g.count) ? text_t[g.start + r] * md.N + text_b[g.start + r] : -1;
   }
   __syncthreads();
+  if (threadIdx.x == 0) N2NMN_STAMP(0, 2);
   // (3) gather the word vectors (all loads of a thread are independent)
   for (int i0 = 0; i0 < kTextRowsPerCta * Dt; i0 += 8 * 256) {
     float xv[8];
@@ -70,6 +73,7 @@ text_proj_kernel(DevModel md, TextBufs tb, const TextGroup* __restrict__ groups,
     }
   }
   __syncthreads();
+  if (threadIdx.x == 0) N2NMN_STAMP(0, 3);
   // (4) 8 x 4 accumulators per thread
   float4 acc[kTextRowsPerCta];
 #pragma unroll
@@ -96,6 +100,7 @@ text_proj_kernel(DevModel md, TextBufs tb, const TextGroup* __restrict__ groups,
       }
     }
   }
+  if (threadIdx.x == 0) N2NMN_STAMP(0, 4);
   // the two K slices inside a warp, then the 8 warps through shared memory
 #pragma unroll
   for (int r = 0; r < kTextRowsPerCta; ++r) {
@@ -125,6 +130,7 @@ text_proj_kernel(DevModel md, TextBufs tb, const TextGroup* __restrict__ groups,
     tb.tauw[idx] = v * w2;
     tb.tau2[idx] = v * v;
   }
+  if (threadIdx.x == 0) N2NMN_STAMP(0, 5);
 }
 
 }  // namespace n2nmn

@@ -124,6 +124,7 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int gwarp = co.rank * nwarps + warp, gwarps = co.size * nwarps;
 
+  if (threadIdx.x == 0) N2NMN_STAMP(2, 0);
   // ---- prologue part 1: parameters (weights + launch tables only; overlaps the predecessors)
   const float* head_w = nullptr;
   if (beg < end) {
@@ -148,7 +149,9 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
     }
   }
   // ---- the attention arena, stored maps and text projections come from the preceding kernels
+  if (threadIdx.x == 0) N2NMN_STAMP(2, 1);
   pdl_wait();
+  if (threadIdx.x == 0) N2NMN_STAMP(2, 2);
   if (beg == end) {   // invalid layout: zeros(num_choices) (models_clevr/nmn3_model.py:144-155)
     if (co.rank == 0)
       for (int i = threadIdx.x; i < md.C; i += blockDim.x) c.scores[(size_t)q * md.C + i] = 0.f;
@@ -169,6 +172,7 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
     __syncthreads();
   }
 
+  if (threadIdx.x == 0) N2NMN_STAMP(2, 3);
   int exch = 0;        // cluster exchanges so far: selects the double-buffered outbuf / part half
   int nfilter = 0;
   for (int i = beg; i < end; ++i) {
@@ -405,6 +409,7 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
       }
     }
     __syncthreads();   // this node's stack writes are visible to the CTA's next node
+    if (threadIdx.x == 0) N2NMN_STAMP(2, 4 + (i - beg));
     if (write_arena && co.rank == 0 && out != nullptr && nd.op != OP_FIND) {
       float* g = c.arena + (size_t)nd.out * HW;
       for (int p = threadIdx.x; p < HW; p += blockDim.x) g[p] = out[p];

@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Per-CTA phase timeline of the three kernels from the -DN2NMN_EXP_TIMELINE build
+(N2NMN_LIB=.../libn2nmn_b200_timeline.so python tools/timeline.py)."""
+import ctypes as C, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from n2nmn_b200 import _lib, synth, weights as wts
+from n2nmn_b200.assembler import Assembler
+from n2nmn_b200.executor import LayoutExecutor
+
+B, H, W, D, T, Cc = 64, 10, 15, 512, 20, 28
+asm = Assembler(synth.vocab_file('clevr'))
+toks = synth.expert_mix_tokens(asm, B, T)
+weights = wts.init_weights('clevr', H, W, D, Cc, seed=0, bias_std=0.1)
+P = 10
+feats, wvs = [], []
+for i in range(P):
+    f, w = synth.make_inputs(B, H, W, D, T, seed=1234 + i)
+    feats.append(torch.from_numpy(f).cuda()); wvs.append(torch.from_numpy(w).cuda())
+ex = LayoutExecutor('clevr', feats[0], wvs[0], Cc, asm, weights=weights, max_batch=B, max_T=T)
+lib = _lib.lib()
+buf = torch.zeros(3 * 512 * 64, dtype=torch.int64, device='cuda')
+lib.n2nmn_exp_set_timeline.argtypes = [C.c_void_p]
+assert lib.n2nmn_exp_set_timeline(C.c_void_p(buf.data_ptr())) == 0
+for i in range(12):
+    ex.forward_device(feats[i % P], wvs[i % P], toks)
+torch.cuda.synchronize()
+buf.zero_()
+ex.forward_device(feats[3], wvs[3], toks)
+torch.cuda.synchronize()
+t = buf.cpu().numpy().reshape(3, 512, 64)
+clk, gt = t[:, :, :32], t[:, :, 32:]
+g0 = gt[gt > 0].min()
+names = ['text', 'proj', 'tree']
+for k in range(3):
+    used = np.where(clk[k, :, 0] > 0)[0]
+    if len(used) == 0:
+        continue
+    print('== %s: %d CTAs; kernel span (globaltimer) start %.2f us .. last stamp %.2f us'
+          % (names[k], len(used), (gt[k][gt[k] > 0].min() - g0) / 1e3, (gt[k].max() - g0) / 1e3))
+    # per-slot cycles relative to the CTA's slot 0, median and max over CTAs
+    for slot in range(1, 32):
+        col = clk[k, used, slot]
+        ok = col > 0
+        if ok.sum() == 0:
+            continue
+        rel = col[ok] - clk[k, used, 0][ok]
+        gts = (gt[k, used, slot][ok] - g0) / 1e3
+        print('  slot %2d: n=%3d  cycles since CTA start  median %7.0f  max %7.0f | abs time us median %.2f max %.2f'
+              % (slot, ok.sum(), np.median(rel), rel.max(), np.median(gts), gts.max()))
