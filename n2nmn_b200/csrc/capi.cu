@@ -334,8 +334,10 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaS
     dim3 grid(c->Mp / kTextCols, (unsigned)S.groups.size());
     const size_t smem = (size_t)(kTextRowsPerCta * c->cfg.text_dim +
                                  8 * kTextRowsPerCta * kTextCols) * sizeof(float);
+    TextSetRows tsr;
+    for (int i = 0; i <= NUM_TEXT_SETS; ++i) tsr.start[i] = S.text_set_start[i];
     text_proj_kernel<<<grid, 256, smem, st>>>(
-        c->md, c->tb, reinterpret_cast<const TextGroup*>(d + o.groups),
+        c->md, c->tb, tsr,
         reinterpret_cast<const int32_t*>(d + o.text_t),
         reinterpret_cast<const int32_t*>(d + o.text_b));
     ++c->launches;

@@ -95,11 +95,12 @@ __device__ __forceinline__ void pdl_wait() {
 __device__ long long* g_timeline = nullptr;   // [kernel 0..2][cta < 512][64]: clock64 | globaltimer
 #define N2NMN_STAMP(kernel, slot)                                                          \
   do {                                                                                     \
-    if (g_timeline && blockIdx.x < 512 && (slot) < 32 && (threadIdx.x & 31) == 0) {        \
+    const int cta_ = blockIdx.y * gridDim.x + blockIdx.x;                                  \
+    if (g_timeline && cta_ < 512 && (slot) < 32 && (threadIdx.x & 31) == 0) {              \
       unsigned long long gt_;                                                              \
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                              \
-      g_timeline[((kernel) * 512 + blockIdx.x) * 64 + (slot)] = clock64();                 \
-      g_timeline[((kernel) * 512 + blockIdx.x) * 64 + 32 + (slot)] = (long long)gt_;       \
+      g_timeline[((kernel) * 512 + cta_) * 64 + (slot)] = clock64();                       \
+      g_timeline[((kernel) * 512 + cta_) * 64 + 32 + (slot)] = (long long)gt_;             \
     }                                                                                      \
   } while (0)
 #else

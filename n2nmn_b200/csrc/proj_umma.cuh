@@ -214,11 +214,22 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
         if (warp == 2) N2NMN_STAMP(1, 5);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kBN;
-#pragma unroll 1
+        // warp-uniform upper bound of the per-lane node counts: unused node slots are skipped by
+        // a uniform branch instead of being executed predicated-off
+        int n_max = n_nodes;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, o));
+        float vbuf[2][32];
+        __syncwarp();
+        ptx::tmem_ld_32x32b_x32_nowait(taddr, vbuf[0]);
+#pragma unroll 2
         for (int ch = 0; ch < kBN / 32; ++ch) {
-          float v[32];
-          __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the per-lane branches
-          ptx::tmem_ld_32x32b_x32(taddr + ch * 32, v);
+          float (&v)[32] = vbuf[ch & 1];
+          ptx::tmem_ld_wait();
+          if (ch + 1 < kBN / 32) {   // next chunk's TMEM load flies under this chunk's math
+            __syncwarp();
+            ptx::tmem_ld_32x32b_x32_nowait(taddr + (ch + 1) * 32, vbuf[(ch + 1) & 1]);
+          }
           const int col0 = nt * kBN + ch * 32;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -231,13 +242,13 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
               reinterpret_cast<float4*>(mdst + col0)[q] =
                   make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
-          if (n_nodes > 0) {
+          if (n_max > 0) {
             float v2[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) v2[i] = v[i] * v[i];
 #pragma unroll
             for (int j = 0; j < kMaxProjNodesPerPass; ++j) {
-              if (j < n_nodes) {
+              if (j < n_max) {            // warp-uniform
                 const float4 *tw, *t2;
                 if (staged) {
                   const float* base = s_vec + ((img_local * kMaxProjNodesPerPass + j) * 2) * kBN +
@@ -245,7 +256,7 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
                   tw = reinterpret_cast<const float4*>(base);
                   t2 = reinterpret_cast<const float4*>(base + kBN);
                 } else {
-                  const int trow_txt = p.node_text[e_beg + j];
+                  const int trow_txt = p.node_text[e_beg + min(j, max(n_nodes - 1, 0))];
                   tw = reinterpret_cast<const float4*>(p.tauw + (size_t)trow_txt * p.Mp + col0);
                   t2 = reinterpret_cast<const float4*>(p.tau2 + (size_t)trow_txt * p.Mp + col0);
                 }
@@ -258,7 +269,7 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
                   n = fmaf(v[4 * q + 2], a.z, n); d = fmaf(v2[4 * q + 2], sq.z, d);
                   n = fmaf(v[4 * q + 3], a.w, n); d = fmaf(v2[4 * q + 3], sq.w, d);
                 }
-                num[j] = n; den[j] = d;
+                if (j < n_nodes) { num[j] = n; den[j] = d; }   // lanes with fewer nodes discard
               }
             }
           }

@@ -19,8 +19,12 @@ constexpr int kTextCols = 64;   // output columns per CTA
 
 constexpr int kTextKIter = 20;   // K rows per thread per chunk (16 slices x 20 = 320 >= Dt=300)
 
+// Rows of each text weight set, by value: a CTA finds its group without touching global memory,
+// so its weight loads can start immediately.
+struct TextSetRows { int32_t start[NUM_TEXT_SETS + 1]; };
+
 __global__ void __launch_bounds__(256)
-text_proj_kernel(DevModel md, TextBufs tb, const TextGroup* __restrict__ groups,
+text_proj_kernel(DevModel md, TextBufs tb, TextSetRows rows,
                  const int32_t* __restrict__ text_t, const int32_t* __restrict__ text_b) {
   extern __shared__ float s_dyn[];
   __shared__ int s_src[kTextRowsPerCta];
@@ -33,7 +37,18 @@ text_proj_kernel(DevModel md, TextBufs tb, const TextGroup* __restrict__ groups,
   const int tx = lane & 15;                    // column quad inside the CTA's 64 columns
   const int ky = warp * 2 + (lane >> 4);       // K slice 0..15
   const int c0 = blockIdx.x * kTextCols + tx * 4;
-  const TextGroup g = groups[blockIdx.y];
+  TextGroup g;   // blockIdx.y-th group of <= 8 rows, groups never straddle weight sets
+  {
+    int gi = blockIdx.y, set = 0;
+    for (; set < NUM_TEXT_SETS; ++set) {
+      const int ng = (rows.start[set + 1] - rows.start[set] + kTextRowsPerCta - 1) / kTextRowsPerCta;
+      if (gi < ng) break;
+      gi -= ng;
+    }
+    g.set = set;
+    g.start = rows.start[set] + gi * kTextRowsPerCta;
+    g.count = min(kTextRowsPerCta, rows.start[set + 1] - g.start);
+  }
   const float* __restrict__ wbase = md.txt_w[g.set] + c0;
 
   // (1) this thread's weight rows of the first chunk: independent of everything else, so the
@@ -54,10 +69,11 @@ text_proj_kernel(DevModel md, TextBufs tb, const TextGroup* __restrict__ groups,
   __syncthreads();
   if (threadIdx.x == 0) N2NMN_STAMP(0, 2);
   // (3) gather the word vectors (all loads of a thread are independent)
-  for (int i0 = 0; i0 < kTextRowsPerCta * Dt; i0 += 8 * 256) {
-    float xv[8];
+  constexpr int kGather = 10;   // 8 rows x 300 words / 256 threads = 9.4 loads per thread
+  for (int i0 = 0; i0 < kTextRowsPerCta * Dt; i0 += kGather * 256) {
+    float xv[kGather];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < kGather; ++u) {
       const int i = i0 + u * 256 + threadIdx.x;
       xv[u] = 0.f;
       if (i < kTextRowsPerCta * Dt) {
@@ -67,7 +83,7 @@ text_proj_kernel(DevModel md, TextBufs tb, const TextGroup* __restrict__ groups,
       }
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < kGather; ++u) {
       const int i = i0 + u * 256 + threadIdx.x;
       if (i < kTextRowsPerCta * Dt) s_x[i] = xv[u];
     }

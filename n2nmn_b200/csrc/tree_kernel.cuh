@@ -20,9 +20,11 @@ namespace n2nmn {
 
 constexpr int kTreeFindSlots = 10;   // Find / Filter maps prefetched per question
 constexpr int kTransformPB = 5;      // pixels register-blocked per warp in the stencil
+constexpr int kTreeNodeCap = 48;     // node records of one question kept in smem
+constexpr int kTreeTextCap = 6;      // text vectors (tau, tau∘w2) of one question prefetched
 
 struct TreeSmem {
-  int HWp, stack, ftmp, outbuf, pad, v, part, z, k, head, total;
+  int HWp, stack, ftmp, outbuf, pad, v, part, z, k, head, nodes, tvec, total;
 };
 __host__ __device__ inline TreeSmem tree_smem_layout(int H, int W, int Mp, int ksize, int M, int C,
                                                      int stack_slots) {
@@ -39,8 +41,10 @@ __host__ __device__ inline TreeSmem tree_smem_layout(int H, int W, int Mp, int k
   s.k = ksize * ksize * Mp;
   const int rows = (2 * (HW + 2) > M) ? 2 * (HW + 2) : M;
   s.head = (rows * C <= kHeadCapFloats) ? ((rows * C + 3) & ~3) : 0;
+  s.nodes = kTreeNodeCap * (int)(sizeof(NodeRec) / sizeof(float));
+  s.tvec = (Mp <= 512) ? kTreeTextCap * 2 * Mp : 0;
   s.total = s.stack + s.ftmp + s.outbuf + 2 * s.HWp + s.pad + kNodeScratch + s.v + s.part + 64 +
-            s.z + s.k + s.head;
+            s.z + s.k + s.head + s.nodes + s.tvec + 2 * Mp;
   return s;
 }
 
@@ -115,6 +119,10 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
   s.z = s.red + 64;
   s.k = s.z + L.z;
   s.head = L.head ? s.k + L.k : nullptr;
+  NodeRec* s_nodes = reinterpret_cast<NodeRec*>(s.k + L.k + L.head);
+  float* s_tvec = reinterpret_cast<float*>(s_nodes) + L.nodes;    // [kTreeTextCap][2][Mp]
+  float* s_tw2 = s_tvec + L.tvec;                                   // Transform conv_eltwise w
+  float* s_tcb = s_tw2 + Mp;                                        // Transform conv bias
 
   Coop co;
   co.size = csize;
@@ -127,10 +135,23 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
   if (threadIdx.x == 0) N2NMN_STAMP(2, 0);
   // ---- prologue part 1: parameters (weights + launch tables only; overlaps the predecessors)
   const float* head_w = nullptr;
+  const bool nodes_in_smem = (end - beg) <= kTreeNodeCap;
   if (beg < end) {
+    if (nodes_in_smem) {   // node records: the loop below must not wait on L2 after pdl_wait
+      const int nwords = (end - beg) * (int)(sizeof(NodeRec) / 4);
+      const int32_t* src = reinterpret_cast<const int32_t*>(nodes + beg);
+      int32_t* dst = reinterpret_cast<int32_t*>(s_nodes);
+      for (int j = threadIdx.x; j < nwords; j += blockDim.x) dst[j] = src[j];
+    }
     bool has_transform = false;
     for (int i = beg; i < end; ++i) has_transform |= (nodes[i].op == OP_TRANSFORM);
-    if (has_transform) stage_async(s.k, md.conv_k, KS * KS * Mp);
+    if (has_transform) {
+      stage_async(s.k, md.conv_k, KS * KS * Mp);
+      for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
+        s_tw2[ch] = (ch < M) ? md.elt_w[ES_TRANSFORM][ch] : 0.f;
+        s_tcb[ch] = (ch < M) ? md.conv_b[ch] : 0.f;
+      }
+    }
     if (co.rank == 0 && s.head != nullptr) {
       const int rop = nodes[end - 1].op;
       const float* w = nullptr;
@@ -158,10 +179,20 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
     return;
   }
   // ---- prologue part 2: the question's Find maps (written by the projection kernel's epilogue)
+  //      and the text vectors of its Transform / pooled nodes (written by the text kernel)
+  const NodeRec* qnodes = nodes_in_smem ? s_nodes : nodes + beg;
   {
-    int nf = 0;
+    int nf = 0, nt = 0;
     for (int i = beg; i < end; ++i) {
-      const int op = nodes[i].op;
+      const int op = qnodes[i - beg].op;
+      if (L.tvec && nt < kTreeTextCap &&
+          (op == OP_TRANSFORM || op == OP_FIND_SAME_PROPERTY || op == OP_DESCRIBE ||
+           op == OP_SAME_PROPERTY)) {
+        const size_t row = (size_t)qnodes[i - beg].text * Mp;
+        stage_async(s_tvec + (nt * 2) * Mp, c.tb.tau + row, Mp);
+        stage_async(s_tvec + (nt * 2 + 1) * Mp, c.tb.tauw + row, Mp);
+        ++nt;
+      }
       if (op == OP_FIND || op == OP_FILTER) {   // staged apart: stack slots are reused over time
         if (nf < kTreeFindSlots)
           stage_async(s.ftmp + nf * L.HWp, c.arena + (size_t)nodes[i].out * HW, HW);
@@ -174,9 +205,23 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
 
   if (threadIdx.x == 0) N2NMN_STAMP(2, 3);
   int exch = 0;        // cluster exchanges so far: selects the double-buffered outbuf / part half
-  int nfilter = 0;
+  int nfilter = 0, ntext = 0;
   for (int i = beg; i < end; ++i) {
-    const NodeRec nd = nodes[i];
+    const NodeRec nd = qnodes[i - beg];
+    // text vectors of this node: prefetched copy if it got a slot, else straight from L2
+    const float* tau = nullptr;
+    const float* tauw = nullptr;
+    if (nd.op == OP_TRANSFORM || nd.op == OP_FIND_SAME_PROPERTY || nd.op == OP_DESCRIBE ||
+        nd.op == OP_SAME_PROPERTY) {
+      if (L.tvec && ntext < kTreeTextCap) {
+        tau = s_tvec + (ntext * 2) * Mp;
+        tauw = tau + Mp;
+      } else {
+        tau = c.tb.tau + (size_t)nd.text * Mp;
+        tauw = c.tb.tauw + (size_t)nd.text * Mp;
+      }
+      ++ntext;
+    }
     float* out = (nd.so >= 0) ? s.stack + nd.so * L.HWp : nullptr;
     const float* in0 = (nd.s0 >= 0) ? s.stack + nd.s0 * L.HWp : nullptr;
     const float* in1 = (nd.s1 >= 0) ? s.stack + nd.s1 * L.HWp : nullptr;
@@ -210,12 +255,10 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
         const int Hh = md.H, Ww = md.W;
         const int PW = Ww + KS - 1, PH = Hh + KS - 1, R = (KS - 1) / 2;
         for (int j = threadIdx.x; j < PH * PW; j += blockDim.x) s.pad[j] = 0.f;
-        const float* tau = c.tb.tau + (size_t)nd.text * Mp;
         for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
-          const bool live = ch < M;
-          s.v0[ch] = live ? tau[ch] : 0.f;
-          s.v1[ch] = live ? md.elt_w[ES_TRANSFORM][ch] : 0.f;
-          s.v2[ch] = live ? md.conv_b[ch] : 0.f;
+          s.v0[ch] = (ch < M) ? tau[ch] : 0.f;
+          s.v1[ch] = s_tw2[ch];
+          s.v2[ch] = s_tcb[ch];
         }
         __syncthreads();
         for (int p = threadIdx.x; p < HW; p += blockDim.x) {
@@ -295,8 +338,6 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
         co.sync();
         ++exch;
         sum_partials(co, part, nullptr, s.v0, M, Mp);
-        const float* tauw = c.tb.tauw + (size_t)nd.text * Mp;
-        const float* tau = c.tb.tau + (size_t)nd.text * Mp;
         for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
           const float phi = s.v0[ch];
           const float tp = tau[ch] * phi;
@@ -352,7 +393,6 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
         if (co.rank == 0) {   // the tail is tiny: one CTA finishes it
           sum_partials(co, part, nullptr, s.v0, M, Mp);
           if (two) sum_partials(co, part + Mp, nullptr, s.v1, M, Mp);
-          const float* tau = c.tb.tau + (size_t)nd.text * Mp;
           float ss = 0.f;
           for (int ch = threadIdx.x; ch < M; ch += blockDim.x) {
             const float e = two ? s.v0[ch] * tau[ch] * s.v1[ch] : tau[ch] * s.v0[ch];

@@ -32,6 +32,29 @@ t = buf.cpu().numpy().reshape(3, 512, 64)
 clk, gt = t[:, :, :32], t[:, :, 32:]
 g0 = gt[gt > 0].min()
 names = ['text', 'proj', 'tree']
+from n2nmn_b200 import config as cfgmod
+cb = ex.compile_tokens(toks)
+nodes = cb.nodes()
+qptr = np.zeros(B + 1, np.int64)
+for op, t_, b_, dep, i0, i1 in nodes:
+    qptr[b_ + 1] += 1
+qptr = np.cumsum(qptr)
+# tree kernel: per-op node durations on rank 0 of each cluster (cluster size 4 -> CTA 4*q)
+per_op = {}
+for q in range(B):
+    cta = 4 * q
+    if clk[2, cta, 0] == 0:
+        continue
+    prev = clk[2, cta, 3]
+    for j, i in enumerate(range(qptr[q], qptr[q + 1])):
+        cur = clk[2, cta, 4 + j]
+        if cur == 0:
+            break
+        per_op.setdefault(cfgmod.OP_NAMES[nodes[i][0]], []).append(cur - prev)
+        prev = cur
+print('== tree kernel, rank-0 CTA, cycles per node by module:')
+for k_, v_ in sorted(per_op.items(), key=lambda kv: -np.median(kv[1])):
+    print('   %-18s n=%3d median %6.0f max %6.0f' % (k_, len(v_), np.median(v_), max(v_)))
 for k in range(3):
     used = np.where(clk[k, :, 0] > 0)[0]
     if len(used) == 0:
