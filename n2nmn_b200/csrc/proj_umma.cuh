@@ -32,10 +32,12 @@ constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kProjThreads = 192;
 constexpr int kTmemCols = 512;
 // Epilogue operand staging (only when a tile spans <= 2 images, i.e. HW >= 127): for each of the
-// two images up to 8 consumer nodes x {tau∘w2, tau²} x 256 columns, plus the 256 bias values.
+// two images up to 8 consumer nodes x tau x 256 columns, plus conv_eltwise w2 and the bias.
+// The epilogue is shared-memory-bandwidth bound (every lane = row reads every vector element), so
+// only tau is staged; tau∘w2 and tau² are formed in registers.
 constexpr int kVecImages = 2;
-constexpr int kVecFloats = kVecImages * kMaxProjNodesPerPass * 2 * kBN;   // 8192 floats = 32 KB
-constexpr int kVecBytes = (kVecFloats + kBN) * 4;
+constexpr int kVecFloats = kVecImages * kMaxProjNodesPerPass * kBN;   // 4096 floats = 16 KB
+constexpr int kVecBytes = (kVecFloats + 2 * kBN) * 4;
 // dynamic smem: stages + staged vectors + barriers, plus 1024 for manual alignment
 constexpr int kProjSmemBytes = kStages * kStageBytes + kVecBytes + 256 + 1024;
 
@@ -54,6 +56,7 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
   uint8_t* smem_b = smem + kStages * kABytes;
   float* s_vec = reinterpret_cast<float*>(smem + kStages * kStageBytes);
   float* s_bias = s_vec + kVecFloats;
+  float* s_w2 = s_bias + kBN;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kVecBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;   // [2]
@@ -193,14 +196,21 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
           reinterpret_cast<float4*>(s_bias)[i] =
               __ldg(reinterpret_cast<const float4*>(bias + nt * kBN) + i);
         if (staged && wk.set == PS_FIND) {
-          // item = (image, node, vector kind, column quad): 2 x 8 x 2 x 64 float4
+          for (int i = etid; i < kBN / 4; i += 128)
+            reinterpret_cast<float4*>(s_w2)[i] =
+                (nt * kBN + i * 4 < p.M)   // conv_eltwise weights are [M], not padded
+                    ? make_float4(p.elt_w[min(nt * kBN + i * 4 + 0, p.M - 1)],
+                                  nt * kBN + i * 4 + 1 < p.M ? p.elt_w[nt * kBN + i * 4 + 1] : 0.f,
+                                  nt * kBN + i * 4 + 2 < p.M ? p.elt_w[nt * kBN + i * 4 + 2] : 0.f,
+                                  nt * kBN + i * 4 + 3 < p.M ? p.elt_w[nt * kBN + i * 4 + 3] : 0.f)
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+          // item = (image, node, column quad): 2 x 8 x 64 float4 of tau
           for (int i = etid; i < kVecFloats / 4; i += 128) {
-            const int q = i & 63, kind = (i >> 6) & 1, j = (i >> 7) & 7, im = i >> 10;
+            const int q = i & 63, j = (i >> 6) & 7, im = i >> 9;
             if (im < n_img) {
               const int eb = p.img_ptr[b_first + im] + wk.pass * kMaxProjNodesPerPass;
               if (eb + j < p.img_ptr[b_first + im + 1]) {
-                const float* src = (kind ? p.tau2 : p.tauw) +
-                                   (size_t)p.node_text[eb + j] * p.Mp + nt * kBN;
+                const float* src = p.tau + (size_t)p.node_text[eb + j] * p.Mp + nt * kBN;
                 reinterpret_cast<float4*>(s_vec)[i] = __ldg(reinterpret_cast<const float4*>(src) + q);
               }
             }
@@ -243,36 +253,60 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
                   make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
           if (n_max > 0) {
-            float v2[32];
+            if (staged) {
+              // num += Σ (m·w2)·tau ; den += Σ (m·tau)²  — one vector (tau) read per node
+              float vw[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v2[i] = v[i] * v[i];
+              for (int q = 0; q < 8; ++q) {
+                const float4 w4 = reinterpret_cast<const float4*>(s_w2 + ch * 32)[q];
+                vw[4 * q + 0] = v[4 * q + 0] * w4.x; vw[4 * q + 1] = v[4 * q + 1] * w4.y;
+                vw[4 * q + 2] = v[4 * q + 2] * w4.z; vw[4 * q + 3] = v[4 * q + 3] * w4.w;
+              }
 #pragma unroll
-            for (int j = 0; j < kMaxProjNodesPerPass; ++j) {
-              if (j < n_max) {            // warp-uniform
-                const float4 *tw, *t2;
-                if (staged) {
-                  const float* base = s_vec + ((img_local * kMaxProjNodesPerPass + j) * 2) * kBN +
-                                      ch * 32;
-                  tw = reinterpret_cast<const float4*>(base);
-                  t2 = reinterpret_cast<const float4*>(base + kBN);
-                } else {
+              for (int j = 0; j < kMaxProjNodesPerPass; ++j) {
+                if (j < n_max) {            // warp-uniform
+                  const float4* tv = reinterpret_cast<const float4*>(
+                      s_vec + (img_local * kMaxProjNodesPerPass + j) * kBN + ch * 32);
+                  float n = num[j], d = den[j];
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    const float4 t4 = tv[q];
+                    float e;
+                    n = fmaf(vw[4 * q + 0], t4.x, n); e = v[4 * q + 0] * t4.x; d = fmaf(e, e, d);
+                    n = fmaf(vw[4 * q + 1], t4.y, n); e = v[4 * q + 1] * t4.y; d = fmaf(e, e, d);
+                    n = fmaf(vw[4 * q + 2], t4.z, n); e = v[4 * q + 2] * t4.z; d = fmaf(e, e, d);
+                    n = fmaf(vw[4 * q + 3], t4.w, n); e = v[4 * q + 3] * t4.w; d = fmaf(e, e, d);
+                  }
+                  if (j < n_nodes) { num[j] = n; den[j] = d; }   // lanes with fewer nodes discard
+                }
+              }
+            } else {
+              float v2[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v2[i] = v[i] * v[i];
+#pragma unroll
+              for (int j = 0; j < kMaxProjNodesPerPass; ++j) {
+                if (j < n_max) {            // warp-uniform
                   const int trow_txt = p.node_text[e_beg + min(j, max(n_nodes - 1, 0))];
-                  tw = reinterpret_cast<const float4*>(p.tauw + (size_t)trow_txt * p.Mp + col0);
-                  t2 = reinterpret_cast<const float4*>(p.tau2 + (size_t)trow_txt * p.Mp + col0);
-                }
-                float n = num[j], d = den[j];
+                  const float4* tw =
+                      reinterpret_cast<const float4*>(p.tauw + (size_t)trow_txt * p.Mp + col0);
+                  const float4* t2 =
+                      reinterpret_cast<const float4*>(p.tau2 + (size_t)trow_txt * p.Mp + col0);
+                  float n = num[j], d = den[j];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  const float4 a = tw[q], sq = t2[q];
-                  n = fmaf(v[4 * q + 0], a.x, n); d = fmaf(v2[4 * q + 0], sq.x, d);
-                  n = fmaf(v[4 * q + 1], a.y, n); d = fmaf(v2[4 * q + 1], sq.y, d);
-                  n = fmaf(v[4 * q + 2], a.z, n); d = fmaf(v2[4 * q + 2], sq.z, d);
-                  n = fmaf(v[4 * q + 3], a.w, n); d = fmaf(v2[4 * q + 3], sq.w, d);
+                  for (int q = 0; q < 8; ++q) {
+                    const float4 a = tw[q], sq = t2[q];
+                    n = fmaf(v[4 * q + 0], a.x, n); d = fmaf(v2[4 * q + 0], sq.x, d);
+                    n = fmaf(v[4 * q + 1], a.y, n); d = fmaf(v2[4 * q + 1], sq.y, d);
+                    n = fmaf(v[4 * q + 2], a.z, n); d = fmaf(v2[4 * q + 2], sq.z, d);
+                    n = fmaf(v[4 * q + 3], a.w, n); d = fmaf(v2[4 * q + 3], sq.w, d);
+                  }
+                  if (j < n_nodes) { num[j] = n; den[j] = d; }
                 }
-                if (j < n_nodes) { num[j] = n; den[j] = d; }   // lanes with fewer nodes discard
               }
             }
           }
+          if (warp == 2) N2NMN_STAMP(1, 24 + ch);
         }
         // release the accumulator buffer to the MMA warp
         ptx::tc_fence_before();

@@ -81,17 +81,17 @@ __device__ __forceinline__ void warp_minmax(const float* a, int HW, float& mn, f
   mn = warp_min(lmn); mx = warp_max(lmx); sum = warp_sum(ls);
 }
 
-// Which CTA of the cluster produced pixel p in the pixel-split phases (p = gwarp + j*gwarps).
-__device__ __forceinline__ int pixel_owner(int p, int nwarps, int gwarps) {
-  return (p % gwarps) / nwarps;
-}
-
 // After a pixel-split phase and its cluster barrier: assemble the full map in the local stack.
+// Work unit u (a pixel, or a horizontal run of `run` pixels) was done by global warp u % gwarps.
 __device__ __forceinline__ void gather_pixels(const Coop& co, const float* outbuf, float* dst,
-                                              int HW) {
+                                              int HW, int W, int run) {
   const int nwarps = blockDim.x >> 5, gwarps = co.size * nwarps;
-  for (int p = threadIdx.x; p < HW; p += blockDim.x)
-    dst[p] = co.peer(outbuf, pixel_owner(p, nwarps, gwarps))[p];
+  const int runs_x = (W + run - 1) / run;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    const int y = p / W, x = p - y * W;
+    const int unit = (run == 1) ? p : y * runs_x + x / run;
+    dst[p] = co.peer(outbuf, (unit % gwarps) / nwarps)[p];
+  }
 }
 
 template <int KS>
@@ -251,6 +251,7 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
           out[p] = (nd.op == OP_AND) ? fminf(in0[p], in1[p]) : fmaxf(in0[p], in1[p]);
         break;
       case OP_TRANSFORM: {
+        if (threadIdx.x == 0) N2NMN_STAMP(2, 20);
         // TransformModule, conv variant (models_clevr/nmn3_modules.py:185-216, SHAPES :71-101)
         const int Hh = md.H, Ww = md.W;
         const int PW = Ww + KS - 1, PH = Hh + KS - 1, R = (KS - 1) / 2;
@@ -267,26 +268,31 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
         }
         cp_async_commit_wait_all();   // the filter bank (prologue)
         __syncthreads();
+        if (threadIdx.x == 0) N2NMN_STAMP(2, 21);
         const float b2 = md.elt_b[ES_TRANSFORM][0];
         float* ob = s.outbuf + (exch & 1) * L.HWp;
-        // each warp owns pixels gwarp, gwarp+gwarps, ...; kTransformPB of them share every
-        // filter-bank read (the stencil is shared-memory-bandwidth bound otherwise)
-        for (int base = gwarp; base < HW; base += gwarps * kTransformPB) {
-          int off[kTransformPB];
+        // Each warp owns horizontal runs of kTransformPB pixels: their stencil windows overlap, so
+        // one (KS x (PB+KS-1)) window is read into registers once and every filter-bank read is
+        // shared by the PB pixels (the stencil is shared-memory-bandwidth bound otherwise).
+        constexpr int WW = kTransformPB + KS - 1;
+        const int runs_x = (Ww + kTransformPB - 1) / kTransformPB;
+        for (int run = gwarp; run < Hh * runs_x; run += gwarps) {
+          const int y = run / runs_x, x0 = (run - y * runs_x) * kTransformPB;
+          float win[KS][WW];
+#pragma unroll
+          for (int dy = 0; dy < KS; ++dy)
+#pragma unroll
+            for (int i = 0; i < WW; ++i)
+              win[dy][i] = s.pad[(y + dy) * PW + min(x0 + i, PW - 1)];
           float num[kTransformPB], den[kTransformPB];
 #pragma unroll
-          for (int j = 0; j < kTransformPB; ++j) {
-            const int p = min(base + j * gwarps, HW - 1);
-            const int y = p / Ww, x = p - y * Ww;
-            off[j] = y * PW + x;
-            num[j] = 0.f; den[j] = 0.f;
-          }
+          for (int j = 0; j < kTransformPB; ++j) { num[j] = 0.f; den[j] = 0.f; }
           for (int c0 = lane * 4; c0 < Mp; c0 += 128) {
             float4 A[kTransformPB];
             const float4 bias4 = *reinterpret_cast<const float4*>(s.v2 + c0);
 #pragma unroll
             for (int j = 0; j < kTransformPB; ++j) A[j] = bias4;
-#pragma unroll 1
+#pragma unroll
             for (int dy = 0; dy < KS; ++dy) {
 #pragma unroll
               for (int dx = 0; dx < KS; ++dx) {
@@ -294,7 +300,7 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
                     *reinterpret_cast<const float4*>(s.k + (dy * KS + dx) * Mp + c0);
 #pragma unroll
                 for (int j = 0; j < kTransformPB; ++j) {
-                  const float wv = s.pad[off[j] + dy * PW + dx];
+                  const float wv = win[dy][dx + j];
                   A[j].x = fmaf(wv, k4.x, A[j].x); A[j].y = fmaf(wv, k4.y, A[j].y);
                   A[j].z = fmaf(wv, k4.z, A[j].z); A[j].w = fmaf(wv, k4.w, A[j].w);
                 }
@@ -315,12 +321,14 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
 #pragma unroll
           for (int j = 0; j < kTransformPB; ++j) {
             const float n = warp_sum(num[j]), d = warp_sum(den[j]);
-            const int p = base + j * gwarps;
-            if (lane == 0 && p < HW) ob[p] = n * rsqrtf(fmaxf(d, kEps)) + b2;
+            if (lane == 0 && x0 + j < Ww) ob[y * Ww + x0 + j] = n * rsqrtf(fmaxf(d, kEps)) + b2;
           }
         }
+        if (threadIdx.x == 0) N2NMN_STAMP(2, 22);
         co.sync();
-        gather_pixels(co, ob, out, HW);
+        if (threadIdx.x == 0) N2NMN_STAMP(2, 23);
+        gather_pixels(co, ob, out, HW, Ww, kTransformPB);
+        if (threadIdx.x == 0) N2NMN_STAMP(2, 24);
         ++exch;
         break;
       }
@@ -365,7 +373,7 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
           if (lane == 0) ob[p] = num * rsqrtf(fmaxf(den, kEps)) + b2;
         }
         co.sync();
-        gather_pixels(co, ob, out, HW);
+        gather_pixels(co, ob, out, HW, md.W, 1);
         ++exch;
         break;
       }
@@ -373,6 +381,7 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
       case OP_SAME_PROPERTY: {
         // DescribeModule (nmn3_modules.py:454-495) / SamePropertyModule (:402-452)
         const bool two = (nd.op == OP_SAME_PROPERTY);
+        if (threadIdx.x == 0) N2NMN_STAMP(2, 26);
         for (int p = threadIdx.x; p < HW; p += blockDim.x) {
           s.a0[p] = in0[p];
           if (two) s.a1[p] = in1[p];
@@ -381,6 +390,7 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
         if (warp == 0) warp_softmax(s.a0, HW);
         if (two && warp == 1) warp_softmax(s.a1, HW);
         __syncthreads();
+        if (threadIdx.x == 0) N2NMN_STAMP(2, 27);
         float* part = s.part + (exch & 1) * 2 * Mp;
         int p0, p1;
         coop_range(co, HW, p0, p1);
@@ -388,7 +398,9 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
         gemv_partial(s.a0 + p0, p0, p1, c.mbuf + nd.aux * map_floats, Mp, part, s.scratch);
         if (two)
           gemv_partial(s.a1 + p0, p0, p1, c.mbuf + nd.aux2 * map_floats, Mp, part + Mp, s.scratch);
+        if (threadIdx.x == 0) N2NMN_STAMP(2, 28);
         co.sync();
+        if (threadIdx.x == 0) N2NMN_STAMP(2, 29);
         ++exch;
         if (co.rank == 0) {   // the tail is tiny: one CTA finishes it
           sum_partials(co, part, nullptr, s.v0, M, Mp);
@@ -404,6 +416,7 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
           for (int ch = threadIdx.x; ch < M; ch += blockDim.x) s.v2[ch] *= inv;
           cp_async_commit_wait_all();
           __syncthreads();
+          if (threadIdx.x == 0) N2NMN_STAMP(2, 30);
           const int os = two ? OS_SAMEPROP : OS_DESCRIBE;
           small_fc(s.v2, M, head_w ? head_w : md.out_w[os], md.out_b[os], md.C,
                    c.scores + (size_t)nd.out * md.C, s.scratch);

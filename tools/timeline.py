@@ -71,3 +71,24 @@ for k in range(3):
         gts = (gt[k, used, slot][ok] - g0) / 1e3
         print('  slot %2d: n=%3d  cycles since CTA start  median %7.0f  max %7.0f | abs time us median %.2f max %.2f'
               % (slot, ok.sum(), np.median(rel), rel.max(), np.median(gts), gts.max()))
+
+# phase stamps inside Transform (20..24) and Describe/SameProperty (26..30), rank-0 CTAs
+def phases(name, slots):
+    rows_ = []
+    for q in range(B):
+        cta = 4 * q
+        v_ = [clk[2, cta, s_] for s_ in slots]
+        if all(x > 0 for x in v_):
+            rows_.append(np.diff(v_))
+    if rows_:
+        print(name, 'n=%d' % len(rows_), 'median cycles per phase', np.median(np.array(rows_), axis=0))
+phases('transform [stage->ready, compute, cluster sync, gather]', [20, 21, 22, 23, 24])
+phases('pooled    [copy+softmax, rowsum, cluster sync, partial-sum+normalize(rank0)]', [26, 27, 28, 29, 30])
+# proj epilogue chunks (slots 24..31) relative to tmem_full (slot 5)
+rows_ = []
+for cta in range(148):
+    v_ = [clk[1, cta, 5]] + [clk[1, cta, 24 + j] for j in range(8)] + [clk[1, cta, 6]]
+    if all(x > 0 for x in v_):
+        rows_.append(np.diff(v_))
+if rows_:
+    print('proj epilogue: cycles per 32-column chunk then tail', np.median(np.array(rows_), axis=0))
