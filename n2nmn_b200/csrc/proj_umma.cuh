@@ -254,30 +254,38 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
           }
           if (n_max > 0) {
             if (staged) {
-              // num += Σ (m·w2)·tau ; den += Σ (m·tau)²  — one vector (tau) read per node
-              float vw[32];
+              // num += Σ (m·w2)·tau ; den += Σ (m·tau)²  — one vector (tau) read per node.
+              // Two-wide fp32 FMAs (FFMA2) and two independent partial sums per quantity: with one
+              // epilogue warp per scheduler the loop is otherwise bound by the FMA dependency chain.
+              float2 vw[16], vv[16];
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
                 const float4 w4 = reinterpret_cast<const float4*>(s_w2 + ch * 32)[q];
-                vw[4 * q + 0] = v[4 * q + 0] * w4.x; vw[4 * q + 1] = v[4 * q + 1] * w4.y;
-                vw[4 * q + 2] = v[4 * q + 2] * w4.z; vw[4 * q + 3] = v[4 * q + 3] * w4.w;
+                vv[2 * q] = make_float2(v[4 * q], v[4 * q + 1]);
+                vv[2 * q + 1] = make_float2(v[4 * q + 2], v[4 * q + 3]);
+                vw[2 * q] = __fmul2_rn(vv[2 * q], make_float2(w4.x, w4.y));
+                vw[2 * q + 1] = __fmul2_rn(vv[2 * q + 1], make_float2(w4.z, w4.w));
               }
 #pragma unroll
               for (int j = 0; j < kMaxProjNodesPerPass; ++j) {
                 if (j < n_max) {            // warp-uniform
                   const float4* tv = reinterpret_cast<const float4*>(
                       s_vec + (img_local * kMaxProjNodesPerPass + j) * kBN + ch * 32);
-                  float n = num[j], d = den[j];
+                  float2 na = make_float2(0.f, 0.f), nb = na, da = na, db = na;
 #pragma unroll
                   for (int q = 0; q < 8; ++q) {
                     const float4 t4 = tv[q];
-                    float e;
-                    n = fmaf(vw[4 * q + 0], t4.x, n); e = v[4 * q + 0] * t4.x; d = fmaf(e, e, d);
-                    n = fmaf(vw[4 * q + 1], t4.y, n); e = v[4 * q + 1] * t4.y; d = fmaf(e, e, d);
-                    n = fmaf(vw[4 * q + 2], t4.z, n); e = v[4 * q + 2] * t4.z; d = fmaf(e, e, d);
-                    n = fmaf(vw[4 * q + 3], t4.w, n); e = v[4 * q + 3] * t4.w; d = fmaf(e, e, d);
+                    const float2 ta = make_float2(t4.x, t4.y), tb2 = make_float2(t4.z, t4.w);
+                    na = __ffma2_rn(vw[2 * q], ta, na);
+                    nb = __ffma2_rn(vw[2 * q + 1], tb2, nb);
+                    const float2 ea = __fmul2_rn(vv[2 * q], ta), eb = __fmul2_rn(vv[2 * q + 1], tb2);
+                    da = __ffma2_rn(ea, ea, da);
+                    db = __ffma2_rn(eb, eb, db);
                   }
-                  if (j < n_nodes) { num[j] = n; den[j] = d; }   // lanes with fewer nodes discard
+                  if (j < n_nodes) {        // lanes with fewer nodes discard
+                    num[j] += (na.x + na.y) + (nb.x + nb.y);
+                    den[j] += (da.x + da.y) + (db.x + db.y);
+                  }
                 }
               }
             } else {

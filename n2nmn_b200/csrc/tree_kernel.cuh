@@ -288,21 +288,28 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
 #pragma unroll
           for (int j = 0; j < kTransformPB; ++j) { num[j] = 0.f; den[j] = 0.f; }
           for (int c0 = lane * 4; c0 < Mp; c0 += 128) {
-            float4 A[kTransformPB];
+            // 4 channels x PB pixels of accumulators, updated with two-wide fp32 FMAs (FFMA2):
+            // the stencil is FMA-issue bound (0.94 MFMA per node)
+            float2 Alo[kTransformPB], Ahi[kTransformPB];
             const float4 bias4 = *reinterpret_cast<const float4*>(s.v2 + c0);
 #pragma unroll
-            for (int j = 0; j < kTransformPB; ++j) A[j] = bias4;
+            for (int j = 0; j < kTransformPB; ++j) {
+              Alo[j] = make_float2(bias4.x, bias4.y);
+              Ahi[j] = make_float2(bias4.z, bias4.w);
+            }
 #pragma unroll
             for (int dy = 0; dy < KS; ++dy) {
 #pragma unroll
               for (int dx = 0; dx < KS; ++dx) {
                 const float4 k4 =
                     *reinterpret_cast<const float4*>(s.k + (dy * KS + dx) * Mp + c0);
+                const float2 klo = make_float2(k4.x, k4.y), khi = make_float2(k4.z, k4.w);
 #pragma unroll
                 for (int j = 0; j < kTransformPB; ++j) {
                   const float wv = win[dy][dx + j];
-                  A[j].x = fmaf(wv, k4.x, A[j].x); A[j].y = fmaf(wv, k4.y, A[j].y);
-                  A[j].z = fmaf(wv, k4.z, A[j].z); A[j].w = fmaf(wv, k4.w, A[j].w);
+                  const float2 w2v = make_float2(wv, wv);
+                  Alo[j] = __ffma2_rn(w2v, klo, Alo[j]);
+                  Ahi[j] = __ffma2_rn(w2v, khi, Ahi[j]);
                 }
               }
             }
@@ -310,8 +317,8 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
             const float4 w4 = *reinterpret_cast<const float4*>(s.v1 + c0);
 #pragma unroll
             for (int j = 0; j < kTransformPB; ++j) {
-              const float ex = A[j].x * t4.x, ey = A[j].y * t4.y, ez = A[j].z * t4.z,
-                          ew = A[j].w * t4.w;
+              const float ex = Alo[j].x * t4.x, ey = Alo[j].y * t4.y, ez = Ahi[j].x * t4.z,
+                          ew = Ahi[j].y * t4.w;
               num[j] = fmaf(ex, w4.x, num[j]); num[j] = fmaf(ey, w4.y, num[j]);
               num[j] = fmaf(ez, w4.z, num[j]); num[j] = fmaf(ew, w4.w, num[j]);
               den[j] = fmaf(ex, ex, den[j]); den[j] = fmaf(ey, ey, den[j]);
