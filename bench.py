@@ -38,8 +38,8 @@ UNIT = 'questions/s'
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
-    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=4000)
+    ap.add_argument('--warmup', type=int, default=50)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=64, help='questions per GPU per step')
     ap.add_argument('--layouts', default='expert', choices=['expert', 'random', 'deep'])
@@ -66,6 +66,17 @@ def peaks():
                 source='fallback (B200_PROFILING.md)')
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
+    `ncu --set full` capture of this same command (profiles/ncu_traffic.json), or None."""
+    p = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f).get(kernel)
+    return None if not d else d['dram_read_bytes'] + d['dram_write_bytes']
+
+
 def make_tokens(asm, kind, n, seed):
     from n2nmn_b200 import synth
     if kind == 'expert':
@@ -79,47 +90,46 @@ def make_tokens(asm, kind, n, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md): one
+    `nvidia-smi -lms` process started right before the region and stopped right after it."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.rows = []
-        self._stop = threading.Event()
-        self._th = None
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(',')])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        self.proc = None
 
     def start(self):
-        self._th = threading.Thread(target=self._run, daemon=True)
-        self._th.start()
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '20'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.15)      # let the first samples start flowing
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self._stop.set()
-        if self._th:
-            self._th.join(timeout=6)
-        sm = [float(r[1]) for r in self.rows if r[1].replace('.', '').isdigit()]
-        mx = [float(r[2]) for r in self.rows if r[2].replace('.', '').isdigit()]
+        rows = []
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                out = ''
+            rows = [[c.strip() for c in ln.split(',')] for ln in out.splitlines() if ln.strip()]
+        sm = [float(r[1]) for r in rows if len(r) > 2 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace('.', '').isdigit()]
         reasons = []
         for name, col in (('hw_slowdown', 4), ('hw_thermal_slowdown', 5),
                           ('sw_thermal_slowdown', 6), ('sw_power_cap', 7)):
-            if any(len(r) > col and r[col].lower().startswith('active') for r in self.rows):
+            if any(len(r) > col and r[col].lower().startswith('active') for r in rows):
                 reasons.append(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None,
                 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
-                'samples': len(self.rows)}
+                'samples': len(rows)}
 
 
 def best_blas_threads(run_once):
@@ -185,7 +195,7 @@ def run_reference_arm(args, rank, world):
     limiter, threads = best_blas_threads(lambda: run_depth_batched(m, exprs0))
     for i in range(max(args.warmup, 1)):
         run_depth_batched(m, asm.assemble(toks[i % 4])[0])
-    steps = min(args.steps, 400)
+    steps = min(args.steps, 200)
     t0 = time.perf_counter()
     for i in range(steps):
         run_depth_batched(m, asm.assemble(toks[i % 4])[0])
@@ -349,7 +359,7 @@ def main():
                     'achieved': gbs if bound == 'hbm' else tfs,
                     'peak': pk['hbm_gbs'] if bound == 'hbm' else tf32_peak,
                     'unit': 'GB/s' if bound == 'hbm' else 'TFLOP/s',
-                    'frac': max(hbm_frac, tc_frac), 'traffic': None,
+                    'frac': max(hbm_frac, tc_frac), 'traffic': ncu_traffic(proj),
                     'hbm_frac': hbm_frac, 'tensor_frac_of_tf32_peak': tc_frac,
                     'avg_launch_us': kernel_us[proj],
                     'algorithmic_bytes_per_launch': bytes_acc / n,

@@ -204,10 +204,13 @@ int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out, 
     // (PS_FIND maps stored for training ride along with the fused pass: no extra work items)
     if (any) ++u_any;
   }
-  for (int set = 0; set < NUM_PROJ_SETS; ++set) {
-    if (u_set[set] == 0) continue;
-    for (int tile = 0; tile < num_tiles; ++tile) {
-      const int r0 = tile * 128, r1 = std::min(total_rows, r0 + 128) - 1;
+  // Tile-major order: the layers that need the same 128 rows of features are handed to
+  // neighbouring CTAs at about the same time, so the A tile is fetched from HBM once and the
+  // other layers hit it in L2 (matters once the batch no longer fits in L2).
+  for (int tile = 0; tile < num_tiles; ++tile) {
+    const int r0 = tile * 128, r1 = std::min(total_rows, r0 + 128) - 1;
+    for (int set = 0; set < NUM_PROJ_SETS; ++set) {
+      if (u_set[set] == 0) continue;
       int max_nodes = 0;
       for (int b = r0 / HW; b <= r1 / HW; ++b) {
         if (set == PS_FIND) max_nodes = std::max(max_nodes, S.img_ptr[b + 1] - S.img_ptr[b]);

@@ -42,5 +42,17 @@ for r in rows[2:]:
     for w in want:
         if w in h:
             out.write('  - %s = %s %s\n' % (w, r[h.index(w)], rows[1][h.index(w)]))
+traffic = {}
+for r in rows[2:]:
+    k = r[h.index('Kernel Name')].split('(')[0].replace('void ', '').split('<')[0]
+    def val(name):
+        v, u = float(r[h.index(name)].replace(',', '')), rows[1][h.index(name)]
+        return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1)
+    traffic.setdefault(k, []).append((val('dram__bytes_read.sum'), val('dram__bytes_write.sum')))
+import json
+json.dump({k: {'dram_read_bytes': sum(x[0] for x in v) / len(v),
+               'dram_write_bytes': sum(x[1] for x in v) / len(v), 'launches': len(v),
+               'capture': 'profiles/%s.md' % tag} for k, v in traffic.items()},
+          open('profiles/ncu_traffic.json', 'w'), indent=1)
 out.close()
 print(open('profiles/%s.md' % tag).read())
