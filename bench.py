@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--wave', action='store_true', help='depth-bucketed wave executor')
+    ap.add_argument('--host-threads', type=int, default=1,
+                    help='1: one host thread per context (ExecutorPool.forward_many); 0: one '
+                         'host thread feeds all contexts')
     ap.add_argument('--no-train', action='store_true', help='skip the train-step measurement')
     ap.add_argument('--streams', type=int, default=3,
                     help='contexts/streams fed round-robin (independent batches overlap)')
@@ -282,8 +285,13 @@ def main():
     barrier()
     e0.record()
     pool.begin()          # the K streams start after e0 ...
-    for i in range(args.steps):
-        step(args.warmup + i)
+    if args.host_threads:
+        idx = [(args.warmup + i) % P for i in range(args.steps)]
+        pool.forward_many([feats[k] for k in idx], [wvs[k] for k in idx], [toks[k] for k in idx],
+                          [scores_k[i % K] for i in range(args.steps)])
+    else:
+        for i in range(args.steps):
+            step(args.warmup + i)
     pool.end()            # ... and e1 is recorded after all of them have drained
     e1.record()
     barrier()
@@ -425,7 +433,7 @@ def main():
                        'cache': 'inputs larger than L2: %d distinct resident batches (%.0f MB) '
                                 'walked round-robin' % (P, P * B * H * W * D * 4 / 1e6),
                        'executor': 'wave' if args.wave else 'tree',
-                       'streams': K,
+                       'streams': K, 'host_threads': K if args.host_threads else 1,
                        'nodes_per_batch': info['num_nodes'], 'max_depth': info['max_depth']},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
             'roofline': roof, 'cpu_baseline': cpu, 'kernel_us': kernel_us, 'train_step': train,

@@ -143,6 +143,9 @@ int n2nmn_compile_schedule(n2nmn_ctx* ctx, const int32_t* tokens_host, int T, in
 int n2nmn_compile_schedule_host(const n2nmn_config* cfg, const int32_t* tokens_host, int T, int N,
                                 const int32_t* vocab_ops, int num_vocab, uint8_t* validity_out,
                                 n2nmn_sched** out);
+/* Diagnostic: average nanoseconds of one host layout compile (no GPU). */
+double n2nmn_time_compile(const n2nmn_config* cfg, const int32_t* tokens_host, int T, int N,
+                          const int32_t* vocab_ops, int num_vocab, int iters);
 /* Same output as n2nmn_compile_schedule, from already-assembled expression trees (what
  * `compiler.build_feed_dict(expr_list)` receives, models_clevr/nmn3_model.py:158): nodes are listed
  * question by question in post-order (operands before their consumer); q_ptr[NQ+1] delimits the

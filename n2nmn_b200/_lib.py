@@ -48,6 +48,8 @@ SIGNATURES = {
                                          C.POINTER(C.c_uint8), C.POINTER(_P)]),
     'n2nmn_compile_schedule_host': (C.c_int, [C.POINTER(Config), _I32P, C.c_int, C.c_int, _I32P,
                                               C.c_int, C.POINTER(C.c_uint8), C.POINTER(_P)]),
+    'n2nmn_time_compile': (C.c_double, [C.POINTER(Config), _I32P, C.c_int, C.c_int, _I32P, C.c_int,
+                                        C.c_int]),
     'n2nmn_compile_nodes': (C.c_int, [_P, _I32P, _I32P, _I32P, _I32P, _I32P, C.c_int, _I32P,
                                       C.c_int, C.POINTER(_P)]),
     'n2nmn_sched_destroy': (C.c_int, [_P]),

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -286,6 +287,9 @@ void prof_mark(n2nmn_ctx* c, const char* name, cudaStream_t st) {
 // Uploads (if needed) and launches everything for one compiled batch.
 int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaStream_t st,
                bool force_wave = false, bool write_arena = false) {
+  const bool use_wave = (c->cfg.flags & N2NMN_FLAG_WAVE_EXECUTOR) || force_wave ||
+                        sc->hs.max_stack > c->stack_cap;
+  if (use_wave) build_waves(&sc->hs);
   const HostSchedule& S = sc->hs;
   const TableOffsets o = table_offsets(S);
   if (o.total > c->table_cap)
@@ -395,7 +399,7 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaS
   nc.md = c->md; nc.tb = c->tb; nc.arena = arena; nc.scores = scores; nc.mbuf = c->mbuf;
   const int NQ = (int)S.q_ptr.size() - 1;
   const bool ks3 = (c->cfg.kernel_size != 5);
-  if ((c->cfg.flags & N2NMN_FLAG_WAVE_EXECUTOR) || force_wave || S.max_stack > c->stack_cap) {
+  if (use_wave) {
     CUDA_TRY(cudaMemsetAsync(scores, 0, (size_t)NQ * c->cfg.num_choices * sizeof(float), st));
     const int32_t* d_wave = reinterpret_cast<const int32_t*>(d + o.wave_nodes);
     for (int dep = 1; dep <= S.max_depth; ++dep) {
@@ -746,6 +750,25 @@ int n2nmn_compile_schedule_host(const n2nmn_config* cfg, const int32_t* tokens, 
   return 0;
 }
 
+// Diagnostic: nanoseconds per layout compile (host only), reusing one schedule object the way
+// n2nmn_forward_tokens does.
+double n2nmn_time_compile(const n2nmn_config* cfg, const int32_t* tokens, int T, int N,
+                          const int32_t* vocab_ops, int num_vocab, int iters) {
+  if (!cfg || !tokens || !vocab_ops || iters <= 0) return -1.0;
+  const int Dk = cfg->D + (cfg->family == N2NMN_VQA ? 2 : 0);
+  const SchedShape shp{cfg->family, cfg->H, cfg->W, Dk, cfg->text_dim, cfg->map_dim,
+                       round_up(cfg->map_dim, 256), cfg->num_choices,
+                       cfg->family == N2NMN_VQA ? 1 : cfg->kernel_size, cfg->max_T};
+  HostSchedule hs;
+  const char* err = nullptr;
+  compile_schedule(shp, tokens, T, N, vocab_ops, num_vocab, &hs, &err);
+  timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int i = 0; i < iters; ++i) compile_schedule(shp, tokens, T, N, vocab_ops, num_vocab, &hs, &err);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  return ((t1.tv_sec - t0.tv_sec) * 1e9 + (t1.tv_nsec - t0.tv_nsec)) / iters;
+}
+
 int n2nmn_compile_nodes(n2nmn_ctx* c, const int32_t* op, const int32_t* t_idx,
                         const int32_t* b_idx, const int32_t* in0, const int32_t* in1, int n,
                         const int32_t* q_ptr, int nq, n2nmn_sched** out) {
@@ -913,6 +936,7 @@ int n2nmn_forward_tokens(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
                          const int32_t* tokens, int T, int N, const int32_t* vocab_ops,
                          int num_vocab, float* scores_dev, uint8_t* validity_out, void* stream) {
   if (!c || !tokens || !vocab_ops || !scores_dev) return fail(N2NMN_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(c->device));   // callers may drive one context per host thread
   if (int rc = n2nmn_bind_inputs(c, feat_dev, wv_dev, N, T, stream)) return rc;
   if (int rc = check_ready(c)) return rc;
   n2nmn_sched* sc = &c->step_sched;

@@ -23,12 +23,6 @@ int text_set_of(int op) {
   }
 }
 
-struct Pending {   // a parsed node before text rows are assigned
-  NodeRec rec;
-  int depth;
-  int tset;
-};
-
 }  // namespace
 
 int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
@@ -40,65 +34,67 @@ int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
   S.validity.assign(N, 0);
   S.q_ptr.assign(N + 1, 0);
 
-  static thread_local std::vector<Pending> all, q;
-  static thread_local std::vector<int> stack;   // indices into q
-  all.clear();
-  all.reserve((size_t)N * 8);
+  // tokens are time-major [T,N]: transpose once so that every question is a contiguous row
+  static thread_local std::vector<int32_t> tq;
+  tq.resize((size_t)N * T);
+  for (int t = 0; t < T; ++t)
+    for (int n = 0; n < N; ++n) tq[(size_t)n * T + t] = tokens[(size_t)t * N + n];
   const int scene_bits = [] { float v = 3.0f; int b; std::memcpy(&b, &v, 4); return b; }();
+  S.nodes.clear();
+  S.depth.clear();
+  S.nodes.reserve((size_t)N * 8);
+  S.depth.reserve((size_t)N * 8);
+  int stack[64];   // node ids of the question's open attention / answer values
 
   for (int n = 0; n < N; ++n) {
-    q.clear(); stack.clear();
-    bool ok = false, has_eos = false;
+    const int32_t* col = tq.data() + (size_t)n * T;
+    bool has_eos = false;
     for (int t = 0; t < T; ++t) {
-      const int tok = tokens[(size_t)t * N + n];
+      const int tok = col[t];
       if (tok >= 0 && tok < num_vocab && vocab_ops[tok] < 0) { has_eos = true; break; }
     }
-    if (has_eos) {
-      ok = true;
-      const int base = (int)all.size();
-      for (int t = 0; t < T && ok; ++t) {
-        const int tok = tokens[(size_t)t * N + n];
-        if (tok < 0 || tok >= num_vocab) { ok = false; break; }
-        const int op = vocab_ops[tok];
-        if (op < 0) break;                       // <eos>
-        if (op >= NUM_OPS) { ok = false; break; }
-        const int ar = kArity[op];
-        if ((int)stack.size() < ar) { ok = false; break; }   // not enough input
-        Pending nd;
-        nd.rec.op = op; nd.rec.t = t; nd.rec.b = n;
-        nd.rec.in0 = nd.rec.in1 = -1;
-        nd.rec.text = -1;
-        nd.rec.aux = (op == OP_SCENE) ? scene_bits : -1;
-        nd.rec.aux2 = -1; nd.rec.s0 = nd.rec.s1 = nd.rec.so = -1;
-        nd.depth = 1;
-        nd.tset = text_set_of(op);
-        // operands come off right-to-left: the last popped is input_0
-        for (int slot = ar - 1; slot >= 0; --slot) {
-          const int child = stack.back(); stack.pop_back();
-          if (kIsAns[q[child].rec.op]) { ok = false; break; }  // input must be attention
-          (slot == 0 ? nd.rec.in0 : nd.rec.in1) = base + child;
-          nd.depth = std::max(nd.depth, q[child].depth + 1);
-        }
-        if (!ok) break;
-        const int id = (int)q.size();
-        nd.rec.out = kIsAns[op] ? n : base + id;
-        q.push_back(nd);
-        stack.push_back(id);
+    const int base = (int)S.nodes.size();
+    bool ok = has_eos;
+    int sp = 0;
+    for (int t = 0; t < T && ok; ++t) {
+      const int tok = col[t];
+      if (tok < 0 || tok >= num_vocab) { ok = false; break; }
+      const int op = vocab_ops[tok];
+      if (op < 0) break;                       // <eos>
+      if (op >= NUM_OPS) { ok = false; break; }
+      const int ar = kArity[op];
+      if (sp < ar || sp - ar >= 63) { ok = false; break; }   // not enough input
+      NodeRec nd;
+      nd.op = op; nd.t = t; nd.b = n;
+      nd.in0 = nd.in1 = -1;
+      nd.text = -1;
+      nd.aux = (op == OP_SCENE) ? scene_bits : -1;
+      nd.aux2 = -1; nd.s0 = nd.s1 = nd.so = -1;
+      int depth = 1;
+      // operands come off right-to-left: the last popped is input_0
+      for (int slot = ar - 1; slot >= 0; --slot) {
+        const int child = stack[--sp];
+        if (kIsAns[S.nodes[child].op]) { ok = false; break; }  // input must be attention
+        (slot == 0 ? nd.in0 : nd.in1) = child;
+        depth = std::max(depth, S.depth[child] + 1);
       }
-      if (ok && !(stack.size() == 1 && kIsAns[q[stack[0]].rec.op])) ok = false;
+      if (!ok) break;
+      const int id = (int)S.nodes.size();
+      nd.out = kIsAns[op] ? n : id;
+      S.nodes.push_back(nd);
+      S.depth.push_back(depth);
+      stack[sp++] = id;
     }
+    if (ok && !(sp == 1 && kIsAns[S.nodes[stack[0]].op])) ok = false;
     if (ok) {
       S.validity[n] = 1;
       ++S.num_valid;
-      all.insert(all.end(), q.begin(), q.end());
+    } else {
+      S.nodes.resize(base);   // an invalid layout contributes no nodes
+      S.depth.resize(base);
     }
-    S.q_ptr[n + 1] = (int)all.size();
+    S.q_ptr[n + 1] = (int)S.nodes.size();
   }
-
-  const int num_nodes = (int)all.size();
-  S.nodes.resize(num_nodes);
-  S.depth.resize(num_nodes);
-  for (int i = 0; i < num_nodes; ++i) { S.nodes[i] = all[i].rec; S.depth[i] = all[i].depth; }
   (void)err;
   return finalize_schedule(shp, N, out, train);
 }
@@ -207,16 +203,18 @@ int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out, 
   // Tile-major order: the layers that need the same 128 rows of features are handed to
   // neighbouring CTAs at about the same time, so the A tile is fetched from HBM once and the
   // other layers hit it in L2 (matters once the batch no longer fits in L2).
+  S.work.reserve((size_t)num_tiles * 2);
   for (int tile = 0; tile < num_tiles; ++tile) {
     const int r0 = tile * 128, r1 = std::min(total_rows, r0 + 128) - 1;
+    const int b0 = r0 / HW, b1 = r1 / HW;
+    int need[NUM_PROJ_SETS] = {0};     // consumers per layer among the tile's images
+    for (int b = b0; b <= b1; ++b) {
+      need[PS_FIND] = std::max(need[PS_FIND], S.img_ptr[b + 1] - S.img_ptr[b]);
+      for (int set = 1; set < NUM_PROJ_SETS; ++set)
+        if (u_set[set] && S.mslot[(size_t)set * N + b] >= 0) need[set] = 1;
+    }
     for (int set = 0; set < NUM_PROJ_SETS; ++set) {
-      if (u_set[set] == 0) continue;
-      int max_nodes = 0;
-      for (int b = r0 / HW; b <= r1 / HW; ++b) {
-        if (set == PS_FIND) max_nodes = std::max(max_nodes, S.img_ptr[b + 1] - S.img_ptr[b]);
-        else if (S.mslot[(size_t)set * N + b] >= 0) max_nodes = 1;
-      }
-      const int passes = (max_nodes + kMaxProjNodesPerPass - 1) / kMaxProjNodesPerPass;
+      const int passes = (need[set] + kMaxProjNodesPerPass - 1) / kMaxProjNodesPerPass;
       for (int pass = 0; pass < passes; ++pass) {
         ProjWork w; w.row0 = r0; w.pass = pass; w.set = set; w.pad = 0;
         S.work.push_back(w);
@@ -254,6 +252,21 @@ int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out, 
     }
   }
 
+  S.wave_ptr.clear(); S.wave_nodes.clear();   // built on demand (build_waves)
+  S.accounted = false;
+  S.u_any = u_any;
+  for (int set = 0; set < NUM_PROJ_SETS; ++set) S.u_set[set] = u_set[set];
+  S.set_count_text = 0;
+  for (int st = 0; st < NUM_TEXT_SETS; ++st) S.set_count_text += set_count[st] > 0;
+  return 0;
+}
+
+
+// Depth-bucketed waves for the wave executor; the tree executor never needs them.
+void build_waves(HostSchedule* out) {
+  HostSchedule& S = *out;
+  if (!S.wave_ptr.empty()) return;
+  const int num_nodes = (int)S.nodes.size();
   // ---- waves (Find is complete after the projection kernel, so it never enters a wave)
   S.wave_ptr.assign(S.max_depth + 2, 0);
   for (int i = 0; i < num_nodes; ++i)
@@ -266,14 +279,7 @@ int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out, 
       if (S.nodes[i].op != OP_FIND) S.wave_nodes[fill[S.depth[i]]++] = i;
   }
 
-  S.accounted = false;
-  S.u_any = u_any;
-  for (int set = 0; set < NUM_PROJ_SETS; ++set) S.u_set[set] = u_set[set];
-  S.set_count_text = 0;
-  for (int st = 0; st < NUM_TEXT_SETS; ++st) S.set_count_text += set_count[st] > 0;
-  return 0;
 }
-
 
 // §8(d) traffic / work accounting; only needed when statistics are requested, so it is kept off
 // the per-step path.

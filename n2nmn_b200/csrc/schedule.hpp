@@ -72,6 +72,9 @@ int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
 int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out,
                       bool train = false);
 
+// Fills wave_ptr / wave_nodes (depth-bucketed waves). Idempotent.
+void build_waves(HostSchedule* out);
+
 // Fills kbytes / kflops / per_node_* (SURVEY.md §8d). Idempotent.
 void account_schedule(const SchedShape& shp, HostSchedule* out);
 

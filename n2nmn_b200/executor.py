@@ -303,6 +303,36 @@ class ExecutorPool:
             scores_host.copy_(scores, non_blocking=True)
         return valid
 
+    def forward_many(self, feats, word_vecs, tokens, outs):
+        """Evaluate a list of independent batches: item i goes to context/stream i % K, and the K
+        contexts are driven by K host threads (the C call releases the GIL, so layout compilation
+        and kernel launches of different batches proceed in parallel on the host as well as on
+        the GPU). outs[i] is the [N,C] CUDA tensor that receives item i's scores. Returns the
+        validity arrays. Call begin() before and end() after, like submit()."""
+        import threading
+        K, n = len(self.executors), len(feats)
+        valid = [None] * n
+        errors = []
+
+        def work(k):
+            try:
+                ex, st = self.executors[k], self.streams[k]
+                for i in range(k, n, K):
+                    _, valid[i] = ex.forward_device(feats[i], word_vecs[i], tokens[i],
+                                                    out=outs[i], stream=st)
+            except Exception as e:   # surface worker failures in the caller
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(1, K)]
+        for t in threads:
+            t.start()
+        work(0)
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return valid
+
     def end(self):
         """Make the current stream wait for everything submitted so far."""
         cur = torch.cuda.current_stream(self.device)

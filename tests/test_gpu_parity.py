@@ -191,6 +191,30 @@ def test_tree_cluster_sizes_agree(cluster, monkeypatch):
     assert float(np.max(np.abs(scores.cpu().numpy() - ref_s))) <= 1e-3
 
 
+def test_executor_pool_threads_match_single_context():
+    from n2nmn_b200 import weights as wts
+    from n2nmn_b200.executor import ExecutorPool
+    N, H, Wd, D, T, C = 32, 10, 15, 512, 20, 28
+    W = wts.init_weights('clevr', H, Wd, D, C, seed=6, bias_std=0.1)
+    asm = Assembler(synth.vocab_file('clevr'))
+    items = []
+    for i in range(7):
+        f, w = synth.make_inputs(N, H, Wd, D, T, seed=200 + i)
+        items.append((torch.from_numpy(f).cuda(), torch.from_numpy(w).cuda(),
+                      synth.random_valid_tokens(asm, N, T, seed=300 + i)))
+    pool = ExecutorPool('clevr', items[0][0], items[0][1], C, asm, weights=W, num_streams=3)
+    outs = [torch.empty((N, C), device='cuda') for _ in items]
+    pool.begin()
+    pool.forward_many([x[0] for x in items], [x[1] for x in items], [x[2] for x in items], outs)
+    pool.end()
+    torch.cuda.synchronize()
+    ex = pool.executors[0]
+    for (f, w, tok), got in zip(items, outs):
+        want, _ = ex.forward_device(f, w, tok)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(got.cpu().numpy(), want.cpu().numpy())
+
+
 def test_host_e2e_entry_matches_device_path():
     from n2nmn_b200 import weights as wts
     N, H, Wd, D, T, C = 16, 10, 15, 512, 10, 28
