@@ -48,11 +48,11 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--wave', action='store_true', help='depth-bucketed wave executor')
-    ap.add_argument('--host-threads', type=int, default=1,
+    ap.add_argument('--host-threads', type=int, default=0,
                     help='1: one host thread per context (ExecutorPool.forward_many); 0: one '
                          'host thread feeds all contexts')
     ap.add_argument('--no-train', action='store_true', help='skip the train-step measurement')
-    ap.add_argument('--streams', type=int, default=3,
+    ap.add_argument('--streams', type=int, default=4,
                     help='contexts/streams fed round-robin (independent batches overlap)')
     return ap.parse_args()
 

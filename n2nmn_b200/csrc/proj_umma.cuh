@@ -9,9 +9,11 @@
 // TMEM holds two 128x256 fp32 accumulators (all 512 columns), so the epilogue of N-tile i
 // overlaps the MMAs of N-tile i+1 / of the next work item.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
-// MMA issuer (one elected lane), warps 2..5 = epilogue; epilogue warp w reads TMEM lanes
-// [32*(w%4), 32*(w%4)+32) i.e. tile rows with that offset.
+// Warp roles (320 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
+// MMA issuer (one elected lane), warps 2..9 = epilogue; epilogue warp w reads TMEM lanes
+// [32*(w%4), 32*(w%4)+32) i.e. tile rows with that offset, and the two warps that share a lane
+// quarter split the 256 columns of an N-tile in halves (the epilogue of a lone tile is a latency
+// chain; two warpgroups halve it). Their partial sums meet in shared memory.
 //
 // Precision: TF32 operands (10-bit mantissa), fp32 accumulate. Error budget vs the fp32/fp64
 // oracle is in DESIGN.md; tests/test_gpu_parity.py holds every attention map to 1e-3 abs.
@@ -29,7 +31,8 @@ constexpr int kStages = 4;
 constexpr int kABytes = kBM * kBK * 4;   // 16384
 constexpr int kBBytes = kBN * kBK * 4;   // 32768
 constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kProjThreads = 192;
+constexpr int kProjThreads = 320;       // TMA warp, MMA warp, 2 x 4 epilogue warps
+constexpr int kEpiThreads = 256;
 constexpr int kTmemCols = 512;
 // Epilogue operand staging (only when a tile spans <= 2 images, i.e. HW >= 127): for each of the
 // two images up to 8 consumer nodes x tau x 256 columns, plus conv_eltwise w2 and the bias.
@@ -37,7 +40,9 @@ constexpr int kTmemCols = 512;
 // only tau is staged; tau∘w2 and tau² are formed in registers.
 constexpr int kVecImages = 2;
 constexpr int kVecFloats = kVecImages * kMaxProjNodesPerPass * kBN;   // 4096 floats = 16 KB
-constexpr int kVecBytes = (kVecFloats + 2 * kBN) * 4;
+// + partial (num, den) of the second epilogue warpgroup: 128 rows x 8 nodes x 2
+constexpr int kPartFloats = kBM * kMaxProjNodesPerPass * 2;
+constexpr int kVecBytes = (kVecFloats + 2 * kBN + kPartFloats) * 4;
 // dynamic smem: stages + staged vectors + barriers, plus 1024 for manual alignment
 constexpr int kProjSmemBytes = kStages * kStageBytes + kVecBytes + 256 + 1024;
 
@@ -57,6 +62,7 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
   float* s_vec = reinterpret_cast<float*>(smem + kStages * kStageBytes);
   float* s_bias = s_vec + kVecFloats;
   float* s_w2 = s_bias + kBN;
+  float* s_part = s_w2 + kBN;   // [128 rows][8 nodes][2]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kVecBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;   // [2]
@@ -76,7 +82,7 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
-      ptx::mbar_init(&tmem_empty[i], 4);   // one arrive per epilogue warp
+      ptx::mbar_init(&tmem_empty[i], 8);   // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -154,7 +160,8 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
     // ===================================================================== epilogue warps
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int trow = quarter * 32 + lane;      // row inside the 128-row tile
-    const int etid = threadIdx.x - 64;         // 0..127 among the epilogue threads
+    const int etid = threadIdx.x - 64;         // 0..255 among the epilogue threads
+    const int half = (warp - 2) >> 2;          // which 128 columns of each N-tile this warp takes
     const bool staged = p.HW >= kBM - 1;       // a tile then spans at most two images
     uint32_t it = 0;
     // tauw / tau2 come from the text-projection kernel, which may still be running (PDL); the
@@ -191,12 +198,12 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
 
       for (int nt = 0; nt < p.n_tiles; ++nt, ++it) {
         // ---- stage this N-tile's epilogue operands while the MMAs are still running
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // previous readers of s_vec are done
-        for (int i = etid; i < kBN / 4; i += 128)
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // previous readers of s_vec are done
+        for (int i = etid; i < kBN / 4; i += kEpiThreads)
           reinterpret_cast<float4*>(s_bias)[i] =
               __ldg(reinterpret_cast<const float4*>(bias + nt * kBN) + i);
         if (staged && wk.set == PS_FIND) {
-          for (int i = etid; i < kBN / 4; i += 128)
+          for (int i = etid; i < kBN / 4; i += kEpiThreads)
             reinterpret_cast<float4*>(s_w2)[i] =
                 (nt * kBN + i * 4 < p.M)   // conv_eltwise weights are [M], not padded
                     ? make_float4(p.elt_w[min(nt * kBN + i * 4 + 0, p.M - 1)],
@@ -205,7 +212,7 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
                                   nt * kBN + i * 4 + 3 < p.M ? p.elt_w[nt * kBN + i * 4 + 3] : 0.f)
                     : make_float4(0.f, 0.f, 0.f, 0.f);
           // item = (image, node, column quad): 2 x 8 x 64 float4 of tau
-          for (int i = etid; i < kVecFloats / 4; i += 128) {
+          for (int i = etid; i < kVecFloats / 4; i += kEpiThreads) {
             const int q = i & 63, j = (i >> 6) & 7, im = i >> 9;
             if (im < n_img) {
               const int eb = p.img_ptr[b_first + im] + wk.pass * kMaxProjNodesPerPass;
@@ -216,7 +223,7 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
             }
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (warp == 2) N2NMN_STAMP(1, 4);
 
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -230,15 +237,16 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, o));
         float vbuf[2][32];
+        const int ch0 = half * (kBN / 64), ch1 = ch0 + kBN / 64;   // this warp's 4 chunks
         __syncwarp();
-        ptx::tmem_ld_32x32b_x32_nowait(taddr, vbuf[0]);
+        ptx::tmem_ld_32x32b_x32_nowait(taddr + ch0 * 32, vbuf[0]);
 #pragma unroll 2
-        for (int ch = 0; ch < kBN / 32; ++ch) {
-          float (&v)[32] = vbuf[ch & 1];
+        for (int ch = ch0; ch < ch1; ++ch) {
+          float (&v)[32] = vbuf[(ch - ch0) & 1];
           ptx::tmem_ld_wait();
-          if (ch + 1 < kBN / 32) {   // next chunk's TMEM load flies under this chunk's math
+          if (ch + 1 < ch1) {   // next chunk's TMEM load flies under this chunk's math
             __syncwarp();
-            ptx::tmem_ld_32x32b_x32_nowait(taddr + (ch + 1) * 32, vbuf[(ch + 1) & 1]);
+            ptx::tmem_ld_32x32b_x32_nowait(taddr + (ch + 1) * 32, vbuf[(ch + 1 - ch0) & 1]);
           }
           const int col0 = nt * kBN + ch * 32;
 #pragma unroll
@@ -321,15 +329,29 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
       }
-      if (row_ok && wk.set == PS_FIND) {
-        const float b2 = __ldg(p.elt_b);
+      // the two column halves of a row meet here: warpgroup 1 hands its partial sums over
+      if (wk.set == PS_FIND) {
+        if (half == 1) {
 #pragma unroll
-        for (int j = 0; j < kMaxProjNodesPerPass; ++j) {
-          if (j < n_nodes) {
-            const int slot = p.node_out[e_beg + j];
-            p.arena[(size_t)slot * p.HW + pix] = num[j] * rsqrtf(fmaxf(den[j], kEps)) + b2;
+          for (int j = 0; j < kMaxProjNodesPerPass; ++j) {
+            s_part[(trow * kMaxProjNodesPerPass + j) * 2] = num[j];
+            s_part[(trow * kMaxProjNodesPerPass + j) * 2 + 1] = den[j];
           }
         }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (half == 0 && row_ok) {
+          const float b2 = __ldg(p.elt_b);
+#pragma unroll
+          for (int j = 0; j < kMaxProjNodesPerPass; ++j) {
+            if (j < n_nodes) {
+              const float nn = num[j] + s_part[(trow * kMaxProjNodesPerPass + j) * 2];
+              const float dd = den[j] + s_part[(trow * kMaxProjNodesPerPass + j) * 2 + 1];
+              const int slot = p.node_out[e_beg + j];
+              p.arena[(size_t)slot * p.HW + pix] = nn * rsqrtf(fmaxf(dd, kEps)) + b2;
+            }
+          }
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");   // s_part may be rewritten by the next tile
       }
     }
   }
