@@ -227,24 +227,35 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
         if (warp == 2) N2NMN_STAMP(1, 4);
 
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-        ptx::mbar_wait(&tmem_full[acc], acc_phase);
-        if (warp == 2) N2NMN_STAMP(1, 5);
-        ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kBN;
         // warp-uniform upper bound of the per-lane node counts: unused node slots are skipped by
         // a uniform branch instead of being executed predicated-off
         int n_max = n_nodes;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, o));
-        float vbuf[2][32];
         const int ch0 = half * (kBN / 64), ch1 = ch0 + kBN / 64;   // this warp's 4 chunks
+        // rep 0 (first tile of the CTA only) is a dry run on zeros while the MMAs are still in
+        // flight: the epilogue is a few hundred straight-line instructions executed once per
+        // tile, and at batch 64 their cold instruction fetch costs more than their execution.
+        // The dry run pulls the code in during time the epilogue warps would spend waiting.
+#pragma unroll 1
+        for (int rep = (it == 0) ? 0 : 1; rep < 2; ++rep) {
+        const bool live = (rep == 1);
+        if (live) {
+          ptx::mbar_wait(&tmem_full[acc], acc_phase);
+          if (warp == 2) N2NMN_STAMP(1, 5);
+          ptx::tc_fence_after();
+        }
+        float vbuf[2][32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { vbuf[0][i] = 0.f; vbuf[1][i] = 0.f; }
         __syncwarp();
-        ptx::tmem_ld_32x32b_x32_nowait(taddr + ch0 * 32, vbuf[0]);
+        if (live) ptx::tmem_ld_32x32b_x32_nowait(taddr + ch0 * 32, vbuf[0]);
 #pragma unroll 2
         for (int ch = ch0; ch < ch1; ++ch) {
           float (&v)[32] = vbuf[(ch - ch0) & 1];
-          ptx::tmem_ld_wait();
-          if (ch + 1 < ch1) {   // next chunk's TMEM load flies under this chunk's math
+          if (live) ptx::tmem_ld_wait();
+          if (live && ch + 1 < ch1) {   // next chunk's TMEM load flies under this chunk's math
             __syncwarp();
             ptx::tmem_ld_32x32b_x32_nowait(taddr + (ch + 1) * 32, vbuf[(ch + 1 - ch0) & 1]);
           }
@@ -254,7 +265,7 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
             const float4 bq = reinterpret_cast<const float4*>(s_bias + ch * 32)[q];
             v[4 * q + 0] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
           }
-          if (mdst != nullptr) {
+          if (live && mdst != nullptr) {
 #pragma unroll
             for (int q = 0; q < 8; ++q)
               reinterpret_cast<float4*>(mdst + col0)[q] =
@@ -324,6 +335,11 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
           }
           if (warp == 2) N2NMN_STAMP(1, 24 + ch);
         }
+        if (!live) {   // discard the dry run
+#pragma unroll
+          for (int j = 0; j < kMaxProjNodesPerPass; ++j) { num[j] = 0.f; den[j] = 0.f; }
+        }
+        }   // rep
         // release the accumulator buffer to the MMA warp
         ptx::tc_fence_before();
         __syncwarp();
