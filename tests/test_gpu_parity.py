@@ -227,3 +227,54 @@ def test_host_e2e_entry_matches_device_path():
                                           torch.from_numpy(word_vecs).pin_memory(), tokens)
     assert valid.tolist() == valid2.tolist()
     np.testing.assert_array_equal(host_scores.numpy(), dev_scores.cpu().numpy())
+
+
+# ---- the other BASELINE.json configurations at their real grid / channel / head sizes -----------
+def _check_family_batch(family, N, H, Wd, D, T, C, tokens, flags=0, tol=1e-3, **kw):
+    from n2nmn_b200 import weights as wts
+    feat, word_vecs = synth.make_inputs(N, H, Wd, D, T, seed=900 + N)
+    W = wts.init_weights(family, H, Wd, D, C, seed=9, bias_std=0.1)
+    ex = make_executor(family, feat, word_vecs, C, W, flags=flags, **kw)
+    cb = ex.compile_tokens(tokens)
+    scores, arena = ex.run(cb, return_att=True)
+    torch.cuda.synchronize()
+    ref_s, ref_att, valid = _oracle_scores(family, feat, word_vecs, C, W, tokens)
+    assert cb.validity.tolist() == valid.tolist()
+    err_s = float(np.max(np.abs(scores.cpu().numpy() - ref_s)))
+    arena = arena.cpu().numpy()
+    err_a = 0.0
+    for i, (op, t, b, depth, in0, in1) in enumerate(cb.nodes()):
+        if (b, t) in ref_att:
+            err_a = max(err_a, float(np.max(np.abs(arena[i] - ref_att[(b, t)]))))
+    print(family, 'N', N, 'nodes', cb.info['num_nodes'], 'depth', cb.info['max_depth'],
+          'scores err', err_s, 'att err', err_a)
+    assert err_s <= tol and err_a <= tol
+    return ex
+
+
+def test_config1_shapes_batch32_real_layout_mix():
+    """SHAPES gt-layout eval, batch 32, 3x3x64 grid, map_dim 500, kernel 3, the three real layouts."""
+    asm = Assembler(synth.vocab_file('shapes'))
+    tokens = synth.histogram_tokens(asm, synth.SHAPES_LAYOUTS, 32, 11, seed=3)
+    for flags in (0, _lib.FLAG_WAVE_EXECUTOR):
+        _check_family_batch('shapes', 32, 3, 3, 64, 11, 2, tokens, flags=flags)
+
+
+def test_config4_vqa_14x14x512_map1024_3001_choices():
+    """VQA gt-layout eval shapes: 14x14 grid, 512(+2 coord) channels, map_dim 1024 (4 N-tiles),
+    3001 answer choices (head weights too large for smem), real layout histogram, T=13."""
+    asm = Assembler(synth.vocab_file('vqa'))
+    tokens = synth.histogram_tokens(asm, synth.VQA_LAYOUTS, 12, 13, seed=4)
+    tokens[:, 0] = asm.module_list2tokens(['_Find', '_Transform', '_Find', '_And', '_Describe'], 13)
+    _check_family_batch('vqa', 12, 14, 14, 512, 13, 3001, tokens)
+
+
+def test_config5_stress_20x20x1024_depth16():
+    """Synthetic stress shapes: 20x20x1024 grid, CLEVR module set, T=40, layouts of depth up to 16
+    (the deepest ones exceed the shared-memory attention stack and take the wave executor)."""
+    asm = Assembler(synth.vocab_file('clevr'))
+    tokens = synth.random_valid_tokens(asm, 12, 40, seed=21, ans_weight=0.08, min_depth=8,
+                                       max_depth=16)
+    depths = [synth.layout_depth(asm, tokens[:, i]) for i in range(12)]
+    assert max(depths) >= 12
+    _check_family_batch('clevr', 12, 20, 20, 1024, 40, 28, tokens)
