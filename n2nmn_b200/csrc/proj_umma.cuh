@@ -43,8 +43,8 @@ constexpr int kVecFloats = kVecImages * kMaxProjNodesPerPass * kBN;   // 4096 fl
 // + partial (num, den) of the second epilogue warpgroup: 128 rows x 8 nodes x 2
 constexpr int kPartFloats = kBM * kMaxProjNodesPerPass * 2;
 constexpr int kVecBytes = (kVecFloats + 2 * kBN + kPartFloats) * 4;
-// dynamic smem: stages + staged vectors + barriers, plus 1024 for manual alignment
-constexpr int kProjSmemBytes = kStages * kStageBytes + kVecBytes + 256 + 1024;
+// dynamic smem: stages + staged vectors + barriers
+constexpr int kProjSmemBytes = kStages * kStageBytes + kVecBytes + 256;
 
 struct ProjTensorMaps {
   CUtensorMap a;                     // features [total_rows, Dk] fp32, box 32 x 128
@@ -53,10 +53,13 @@ struct ProjTensorMaps {
 
 __global__ void __launch_bounds__(kProjThreads, 1)
 proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B tiles need 1024-byte alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // SWIZZLE_128B tiles need 1024-byte alignment. The alignment comes from the declaration, NOT
+  // from integer arithmetic on the pointer: that would demote every shared-memory access below
+  // to generic LD/ST (measured: the epilogue's staged-vector reads became LD.E.128 and the
+  // epilogue 2x slower).
+  extern __shared__ __align__(1024) uint8_t proj_smem[];
+  uint8_t* smem = proj_smem;
+  if ((ptx::smem_u32(proj_smem) & 1023u) != 0) __trap();
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kABytes;
   float* s_vec = reinterpret_cast<float*>(smem + kStages * kStageBytes);
