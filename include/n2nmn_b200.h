@@ -224,6 +224,13 @@ int n2nmn_adam_step(n2nmn_ctx* ctx, float* wflat_dev, float* gflat_dev, float* m
                     int step, float lr, float beta1, float beta2, float eps, float max_norm,
                     float weight_decay, void* stream);
 
+/* CTAs per question in the layout-executor kernel: 1, 2, 4 or 8 thread-block clusters; 0 (the
+ * default) picks from the batch size so that one batch alone spreads over the SMs (lowest latency
+ * of a single batch). Callers that keep several batches in flight on different streams get more
+ * throughput from smaller clusters. Tuning only: results are identical. No reference counterpart
+ * (the reference executor is TensorFlow Fold's scheduler, models_clevr/nmn3_model.py:118-133). */
+int n2nmn_set_tree_cluster(n2nmn_ctx* ctx, int ctas_per_question);
+
 /* Per-launch device time of the last n2nmn_run_schedule in microseconds (CUDA events recorded
  * around every launch when enabled). names/us arrays of length >= capacity. */
 int n2nmn_set_profiling(n2nmn_ctx* ctx, int enabled);

@@ -67,6 +67,7 @@ SIGNATURES = {
                                        C.c_float, _P, _P, _P, _P, _P, _P]),
     'n2nmn_adam_step': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_float, C.c_float, C.c_float,
                                   C.c_float, C.c_float, C.c_float, _P]),
+    'n2nmn_set_tree_cluster': (C.c_int, [_P, C.c_int]),
     'n2nmn_set_profiling': (C.c_int, [_P, C.c_int]),
     'n2nmn_get_launch_times': (C.c_int, [_P, C.POINTER(C.c_char_p), C.POINTER(C.c_float),
                                          C.c_int]),

@@ -1139,6 +1139,15 @@ extern "C" int n2nmn_exp_set_timeline(long long* dev_buf) {
 }
 #endif
 
+int n2nmn_set_tree_cluster(n2nmn_ctx* c, int ctas_per_question) {
+  if (!c) return fail(N2NMN_ERR_ARG, "n2nmn_set_tree_cluster: null context");
+  const int v = ctas_per_question;
+  if (!(v == 0 || v == 1 || v == 2 || v == 4 || v == 8))
+    return fail(N2NMN_ERR_ARG, "n2nmn_set_tree_cluster: ctas_per_question must be 0, 1, 2, 4 or 8");
+  c->tree_cluster = v;
+  return 0;
+}
+
 int n2nmn_set_profiling(n2nmn_ctx* c, int enabled) {
   if (!c) return fail(N2NMN_ERR_ARG, "null context");
   c->profiling = enabled != 0;

@@ -27,7 +27,11 @@ constexpr int kBM = 128;           // rows per tile (UMMA M)
 constexpr int kBN = 256;           // columns per N-tile (UMMA N)
 constexpr int kBK = 32;            // fp32 elements per K slice = 128 bytes
 constexpr int kUmmaK = 8;          // K per tcgen05.mma for tf32 (32 bytes)
+#if defined(N2NMN_EXP_STAGES)
+constexpr int kStages = N2NMN_EXP_STAGES;
+#else
 constexpr int kStages = 4;
+#endif
 constexpr int kABytes = kBM * kBK * 4;   // 16384
 constexpr int kBBytes = kBN * kBK * 4;   // 32768
 constexpr int kStageBytes = kABytes + kBBytes;
@@ -237,44 +241,50 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, o));
         const int ch0 = half * (kBN / 64), ch1 = ch0 + kBN / 64;   // this warp's 4 chunks
-        // rep 0 (first tile of the CTA only) is a dry run on zeros while the MMAs are still in
-        // flight: the epilogue is a few hundred straight-line instructions executed once per
-        // tile, and at batch 64 their cold instruction fetch costs more than their execution.
-        // The dry run pulls the code in during time the epilogue warps would spend waiting.
-#pragma unroll 1
-        for (int rep = (it == 0) ? 0 : 1; rep < 2; ++rep) {
-        const bool live = (rep == 1);
-        if (live) {
-          ptx::mbar_wait(&tmem_full[acc], acc_phase);
-          if (warp == 2) N2NMN_STAMP(1, 5);
-          ptx::tc_fence_after();
-        }
+        ptx::mbar_wait(&tmem_full[acc], acc_phase);
+        if (warp == 2) N2NMN_STAMP(1, 5);
+        ptx::tc_fence_after();
         float vbuf[2][32];
+#if defined(N2NMN_EXP_EPI_NOLD)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { vbuf[0][i] = 0.f; vbuf[1][i] = 0.f; }
-        __syncwarp();
-        if (live) ptx::tmem_ld_32x32b_x32_nowait(taddr + ch0 * 32, vbuf[0]);
+        for (int i = 0; i < 32; ++i) { vbuf[0][i] = 1.f; vbuf[1][i] = 1.f; }
+#define N2NMN_TMEM_LD(addr, dst)
+#define N2NMN_TMEM_WAIT()
+#else
+#define N2NMN_TMEM_LD(addr, dst) ptx::tmem_ld_32x32b_x32_nowait(addr, dst)
+#define N2NMN_TMEM_WAIT() ptx::tmem_ld_wait()
+#endif
+        N2NMN_TMEM_LD(taddr + ch0 * 32, vbuf[0]);
 #pragma unroll 2
         for (int ch = ch0; ch < ch1; ++ch) {
           float (&v)[32] = vbuf[(ch - ch0) & 1];
-          if (live) ptx::tmem_ld_wait();
-          if (live && ch + 1 < ch1) {   // next chunk's TMEM load flies under this chunk's math
+          N2NMN_TMEM_WAIT();
+          if (ch + 1 < ch1) {   // next chunk's TMEM load flies under this chunk's math
             __syncwarp();
-            ptx::tmem_ld_32x32b_x32_nowait(taddr + (ch + 1) * 32, vbuf[(ch + 1 - ch0) & 1]);
+            N2NMN_TMEM_LD(taddr + (ch + 1) * 32, vbuf[(ch + 1 - ch0) & 1]);
           }
+#if defined(N2NMN_EXP_EPI_NONE)
+          continue;
+#endif
           const int col0 = nt * kBN + ch * 32;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 bq = reinterpret_cast<const float4*>(s_bias + ch * 32)[q];
             v[4 * q + 0] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
           }
-          if (live && mdst != nullptr) {
+#if !defined(N2NMN_EXP_EPI_NOSTORE)
+          if (mdst != nullptr) {
 #pragma unroll
             for (int q = 0; q < 8; ++q)
               reinterpret_cast<float4*>(mdst + col0)[q] =
                   make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
+#endif
+#if defined(N2NMN_EXP_EPI_NOMATH)
+          if (false) {
+#else
           if (n_max > 0) {
+#endif
             if (staged) {
               // num += Σ (m·w2)·tau ; den += Σ (m·tau)²  — one vector (tau) read per node.
               // Two-wide fp32 FMAs (FFMA2) and two independent partial sums per quantity: with one
@@ -338,16 +348,12 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
           }
           if (warp == 2) N2NMN_STAMP(1, 24 + ch);
         }
-        if (!live) {   // discard the dry run
-#pragma unroll
-          for (int j = 0; j < kMaxProjNodesPerPass; ++j) { num[j] = 0.f; den[j] = 0.f; }
-        }
-        }   // rep
         // release the accumulator buffer to the MMA warp
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
       }
+      if (warp == 2) N2NMN_STAMP(1, 7);
       // the two column halves of a row meet here: warpgroup 1 hands its partial sums over
       if (wk.set == PS_FIND) {
         if (half == 1) {
@@ -358,6 +364,7 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
           }
         }
         asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (warp == 2) N2NMN_STAMP(1, 28);
         if (half == 0 && row_ok) {
           const float b2 = __ldg(p.elt_b);
 #pragma unroll
@@ -370,7 +377,9 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
             }
           }
         }
+        if (warp == 2) N2NMN_STAMP(1, 29);
         asm volatile("bar.sync 2, 256;" ::: "memory");   // s_part may be rewritten by the next tile
+        if (warp == 2) N2NMN_STAMP(1, 30);
       }
     }
   }

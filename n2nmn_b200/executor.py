@@ -14,6 +14,8 @@ compiled batch (n2nmn_run_schedule). Rows of invalid layouts are zeros
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 
 import numpy as np
@@ -224,6 +226,10 @@ class LayoutExecutor:
             m._stream()))
         return scores_host, validity.astype(bool)
 
+    def set_tree_cluster(self, ctas_per_question):
+        """CTAs per question in the executor kernel (0 = automatic). Tuning only."""
+        _lib.check(self._lib.n2nmn_set_tree_cluster(self.modules._h, int(ctas_per_question)))
+
     # -- profiling ------------------------------------------------------------------------------
     def set_profiling(self, on):
         _lib.check(self._lib.n2nmn_set_profiling(self.modules._h, int(bool(on))))
@@ -247,7 +253,7 @@ class ExecutorPool:
     sharing hazard; weights are replicated (a few MB)."""
 
     def __init__(self, family, image_feat_grid, word_vecs, num_choices, assembler, weights=None,
-                 num_streams=3, **ctx_kwargs):
+                 num_streams=3, tree_cluster=None, **ctx_kwargs):
         first = LayoutExecutor(family, image_feat_grid, word_vecs, num_choices, assembler,
                                weights=weights, **ctx_kwargs)
         w = first.modules.get_weights()
@@ -255,6 +261,13 @@ class ExecutorPool:
             LayoutExecutor(family, image_feat_grid, word_vecs, num_choices, assembler, weights=w,
                            **ctx_kwargs) for _ in range(num_streams - 1)]
         dev = first.modules.device
+        # several batches in flight: throughput, not the latency of one batch, is what counts, and
+        # two CTAs per question leave more SMs to the other streams' kernels (measured: DESIGN §9)
+        if tree_cluster is None:
+            tree_cluster = 2 if num_streams > 1 else 0
+        if 'N2NMN_TREE_CLUSTER' not in os.environ:
+            for ex in self.executors:
+                ex.set_tree_cluster(tree_cluster)
         self.streams = [torch.cuda.Stream(device=dev) for _ in self.executors]
         self._i = 0
         self.device = dev

@@ -84,6 +84,19 @@ def phases(name, slots):
         print(name, 'n=%d' % len(rows_), 'median cycles per phase', np.median(np.array(rows_), axis=0))
 phases('transform [stage->ready, compute, cluster sync, gather]', [20, 21, 22, 23, 24])
 phases('pooled    [copy+softmax, rowsum, cluster sync, partial-sum+normalize(rank0)]', [26, 27, 28, 29, 30])
+rows_ = []
+for cta in range(148):
+    v_ = [clk[1, cta, j] for j in (5, 7, 28, 29, 30, 6)]
+    if all(x > 0 for x in v_):
+        rows_.append(np.diff(v_))
+if rows_:
+    print('proj FIND tiles: [chunks, bar, outputs, bar, to-exit] n=%d' % len(rows_), np.median(np.array(rows_), axis=0))
+rows_ = []
+for cta in range(148):
+    if clk[1, cta, 28] == 0 and clk[1, cta, 5] > 0 and clk[1, cta, 7] > 0:
+        rows_.append([clk[1, cta, 7] - clk[1, cta, 5], clk[1, cta, 6] - clk[1, cta, 7]])
+if rows_:
+    print('proj STORED tiles: [chunks, to-exit] n=%d' % len(rows_), np.median(np.array(rows_), axis=0))
 # proj epilogue chunks (slots 24..31) relative to tmem_full (slot 5)
 rows_ = []
 for cta in range(148):
