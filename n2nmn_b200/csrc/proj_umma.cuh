@@ -27,26 +27,43 @@ constexpr int kBM = 128;           // rows per tile (UMMA M)
 constexpr int kBN = 256;           // columns per N-tile (UMMA N)
 constexpr int kBK = 32;            // fp32 elements per K slice = 128 bytes
 constexpr int kUmmaK = 8;          // K per tcgen05.mma for tf32 (32 bytes)
+// 3 x 48 KB of operand stages: a K slice is consumed in ~700 cycles at the TF32 rate, so three
+// slices in flight cover the L2/DRAM latency (measured: 4 stages are no faster at batch 256 and
+// 1024), and the 48 KB this frees pay for the epilogue staging below.
 #if defined(N2NMN_EXP_STAGES)
 constexpr int kStages = N2NMN_EXP_STAGES;
 #else
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 #endif
 constexpr int kABytes = kBM * kBK * 4;   // 16384
 constexpr int kBBytes = kBN * kBK * 4;   // 32768
 constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kProjThreads = 320;       // TMA warp, MMA warp, 2 x 4 epilogue warps
+// Warpgroup 0 = {TMA warp, MMA warp, two idle warps}, warpgroups 1-2 = epilogue. Roles are split on
+// warpgroup boundaries so that setmaxnreg can move registers from the producers (which need ~30)
+// to the epilogue warps (which want > 200: a 32-column accumulator chunk in flight, the one being
+// reduced, its squares, and a consumer node's two staged vectors loaded as ONE batch — with two
+// epilogue warps per scheduler, load -> use -> load chains expose the shared-memory latency).
+constexpr int kProjThreads = 384;
+constexpr int kProducerRegs = 40, kEpilogueRegs = 232;   // 4*40 + 8*232 <= 2048 per 32 lanes
 constexpr int kEpiThreads = 256;
 constexpr int kTmemCols = 512;
 // Epilogue operand staging (only when a tile spans <= 2 images, i.e. HW >= 127): for each of the
-// two images up to 8 consumer nodes x tau x 256 columns, plus conv_eltwise w2 and the bias.
-// The epilogue is shared-memory-bandwidth bound (every lane = row reads every vector element), so
-// only tau is staged; tau∘w2 and tau² are formed in registers.
+// two images up to 8 consumer nodes x (tau∘w2, tau²) x 256 columns, plus the bias. With both
+// vectors staged a node costs two FMAs per column (num += m·(τw2), den += m²·τ²); the epilogue of
+// a fused tile is bound by the SM's 128 fp32 lanes, so the FMA count is what matters.
 constexpr int kVecImages = 2;
 constexpr int kVecFloats = kVecImages * kMaxProjNodesPerPass * kBN;   // 4096 floats = 16 KB
-// + partial (num, den) of the second epilogue warpgroup: 128 rows x 8 nodes x 2
-constexpr int kPartFloats = kBM * kMaxProjNodesPerPass * 2;
-constexpr int kVecBytes = (kVecFloats + 2 * kBN + kPartFloats) * 4;
+// running (num, den) of every (row, consumer node), one copy per epilogue warpgroup (column half):
+// [2 halves][8 nodes][2][128 rows]. Kept in shared memory so that the node loop is a ROLLED loop:
+// unrolled over 8 nodes the epilogue was ~70 KB of straight-line code executed once per tile, and
+// skipping the unused node blocks cost a chain of taken branches into cold instruction-cache lines.
+constexpr int kPartFloats = 2 * kMaxProjNodesPerPass * 2 * kBM;
+// stored maps leave through a per-warp 32 x 32 transpose buffer so that 8 lanes write one full
+// 128-byte line (a lane owns a ROW of the accumulator: direct stores touch 32 lines per
+// instruction and the L1 takes one line per cycle — measured 8.2 K cycles per stored tile)
+constexpr int kStoreFloats = (kEpiThreads / 32) * 32 * 32;            // 8 warps x 4 KB
+constexpr int kVecBytes =
+    (2 * kVecFloats + kBN + kPartFloats + kStoreFloats) * 4 + kBM * (int)sizeof(float*);
 // dynamic smem: stages + staged vectors + barriers
 constexpr int kProjSmemBytes = kStages * kStageBytes + kVecBytes + 256;
 
@@ -66,10 +83,12 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
   if ((ptx::smem_u32(proj_smem) & 1023u) != 0) __trap();
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kABytes;
-  float* s_vec = reinterpret_cast<float*>(smem + kStages * kStageBytes);
-  float* s_bias = s_vec + kVecFloats;
-  float* s_w2 = s_bias + kBN;
-  float* s_part = s_w2 + kBN;   // [128 rows][8 nodes][2]
+  float* s_tw = reinterpret_cast<float*>(smem + kStages * kStageBytes);   // [2][8][256] τ∘w2
+  float* s_t2 = s_tw + kVecFloats;                                         // [2][8][256] τ²
+  float* s_bias = s_t2 + kVecFloats;
+  float* s_part = s_bias + kBN;          // [2 halves][8 nodes][num|den][128 rows]
+  float* s_store = s_part + kPartFloats; // [8 warps][32 rows][32 cols], 16-byte chunks swizzled
+  float** s_rowdst = reinterpret_cast<float**>(s_store + kStoreFloats);   // [128] or nullptr
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kVecBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;   // [2]
@@ -100,6 +119,8 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
   const uint32_t tmem_base = *tmem_base_slot;
   if (threadIdx.x == 0) N2NMN_STAMP(1, 1);
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (ptx::elect_one()) {
@@ -163,19 +184,21 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
         }
       }
     }
+  }
   } else {
     // ===================================================================== epilogue warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpilogueRegs));
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int trow = quarter * 32 + lane;      // row inside the 128-row tile
-    const int etid = threadIdx.x - 64;         // 0..255 among the epilogue threads
-    const int half = (warp - 2) >> 2;          // which 128 columns of each N-tile this warp takes
+    const int etid = threadIdx.x - 128;        // 0..255 among the epilogue threads
+    const int half = (warp - 4) >> 2;          // which 128 columns of each N-tile this warp takes
     const bool staged = p.HW >= kBM - 1;       // a tile then spans at most two images
     uint32_t it = 0;
     // tauw / tau2 come from the text-projection kernel, which may still be running (PDL); the
     // TMA / MMA warps above never touch its output and start immediately.
-    if (warp == 2) N2NMN_STAMP(1, 2);
+    if (warp == 4) N2NMN_STAMP(1, 2);
     pdl_wait();
-    if (warp == 2) N2NMN_STAMP(1, 3);
+    if (warp == 4) N2NMN_STAMP(1, 3);
     for (int wi = blockIdx.x; wi < p.num_work; wi += gridDim.x) {
       const ProjWork wk = p.work[wi];
       const int row = wk.row0 + trow;
@@ -197,41 +220,37 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
         const int slot = p.mslot[wk.set * p.num_images + b];
         if (slot >= 0 && wk.pass == 0) mdst = p.mbuf + ((size_t)slot * p.HW + pix) * p.Mp;
       }
-      float num[kMaxProjNodesPerPass], den[kMaxProjNodesPerPass];
-#pragma unroll
-      for (int j = 0; j < kMaxProjNodesPerPass; ++j) { num[j] = 0.f; den[j] = 0.f; }
+      float* acc_row = s_part + half * (kMaxProjNodesPerPass * 2 * kBM) + trow;   // + j*2*kBM (+kBM)
       const float* __restrict__ bias = p.bias[wk.set];
       const int n_img = min((p.total_rows - 1) / p.HW, (wk.row0 + kBM - 1) / p.HW) - b_first + 1;
+      // does any row of this warp's quarter leave through the stored-map path? (warp-uniform)
+      const bool any_store = __any_sync(0xffffffffu, mdst != nullptr);
 
       for (int nt = 0; nt < p.n_tiles; ++nt, ++it) {
         // ---- stage this N-tile's epilogue operands while the MMAs are still running
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // previous readers of s_vec are done
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // previous readers of the staging are done
+        if (half == 0) s_rowdst[trow] = mdst;
         for (int i = etid; i < kBN / 4; i += kEpiThreads)
           reinterpret_cast<float4*>(s_bias)[i] =
               __ldg(reinterpret_cast<const float4*>(bias + nt * kBN) + i);
         if (staged && wk.set == PS_FIND) {
-          for (int i = etid; i < kBN / 4; i += kEpiThreads)
-            reinterpret_cast<float4*>(s_w2)[i] =
-                (nt * kBN + i * 4 < p.M)   // conv_eltwise weights are [M], not padded
-                    ? make_float4(p.elt_w[min(nt * kBN + i * 4 + 0, p.M - 1)],
-                                  nt * kBN + i * 4 + 1 < p.M ? p.elt_w[nt * kBN + i * 4 + 1] : 0.f,
-                                  nt * kBN + i * 4 + 2 < p.M ? p.elt_w[nt * kBN + i * 4 + 2] : 0.f,
-                                  nt * kBN + i * 4 + 3 < p.M ? p.elt_w[nt * kBN + i * 4 + 3] : 0.f)
-                    : make_float4(0.f, 0.f, 0.f, 0.f);
-          // item = (image, node, column quad): 2 x 8 x 64 float4 of tau
+          // item = (image, node, column quad): 2 x 8 x 64 float4 of tau∘w2 and of tau²
           for (int i = etid; i < kVecFloats / 4; i += kEpiThreads) {
             const int q = i & 63, j = (i >> 6) & 7, im = i >> 9;
             if (im < n_img) {
               const int eb = p.img_ptr[b_first + im] + wk.pass * kMaxProjNodesPerPass;
               if (eb + j < p.img_ptr[b_first + im + 1]) {
-                const float* src = p.tau + (size_t)p.node_text[eb + j] * p.Mp + nt * kBN;
-                reinterpret_cast<float4*>(s_vec)[i] = __ldg(reinterpret_cast<const float4*>(src) + q);
+                const size_t off = (size_t)p.node_text[eb + j] * p.Mp + nt * kBN;
+                reinterpret_cast<float4*>(s_tw)[i] =
+                    __ldg(reinterpret_cast<const float4*>(p.tauw + off) + q);
+                reinterpret_cast<float4*>(s_t2)[i] =
+                    __ldg(reinterpret_cast<const float4*>(p.tau2 + off) + q);
               }
             }
           }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (warp == 2) N2NMN_STAMP(1, 4);
+        if (warp == 4) N2NMN_STAMP(1, 4);
 
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kBN;
@@ -241,8 +260,14 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, o));
         const int ch0 = half * (kBN / 64), ch1 = ch0 + kBN / 64;   // this warp's 4 chunks
+        float4* st4 = reinterpret_cast<float4*>(s_store) + (warp - 4) * (32 * 8);
+        const int cq = lane & 7;
+        float* dstp[8];   // destination rows of the 8 store instructions of a chunk (per tile)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          dstp[i] = any_store ? s_rowdst[quarter * 32 + i * 4 + (lane >> 3)] : nullptr;
         ptx::mbar_wait(&tmem_full[acc], acc_phase);
-        if (warp == 2) N2NMN_STAMP(1, 5);
+        if (warp == 4) N2NMN_STAMP(1, 5);
         ptx::tc_fence_after();
         float vbuf[2][32];
 #if defined(N2NMN_EXP_EPI_NOLD)
@@ -273,11 +298,26 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
             v[4 * q + 0] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
           }
 #if !defined(N2NMN_EXP_EPI_NOSTORE)
-          if (mdst != nullptr) {
+          if (any_store) {
+            // lane = row holds 32 consecutive columns; transpose through shared memory (chunk
+            // index XOR row keeps both the row-wise writes and the line-wise reads conflict-free)
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-              reinterpret_cast<float4*>(mdst + col0)[q] =
+              st4[lane * 8 + (q ^ (lane & 7))] =
                   make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            __syncwarp();
+            // all eight reads first, then the stores: with two epilogue warps per scheduler a
+            // load -> use -> load chain would expose the shared-memory latency eight times
+            float4 tq[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {       // 4 rows x 128 bytes per instruction
+              const int r = i * 4 + (lane >> 3);
+              tq[i] = st4[r * 8 + (cq ^ (r & 7))];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (dstp[i] != nullptr) reinterpret_cast<float4*>(dstp[i] + col0)[cq] = tq[i];
+            __syncwarp();
           }
 #endif
 #if defined(N2NMN_EXP_EPI_NOMATH)
@@ -285,106 +325,99 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
 #else
           if (n_max > 0) {
 #endif
+            const bool first = (nt == 0 && ch == ch0);   // first chunk of the tile: overwrite
             if (staged) {
-              // num += Σ (m·w2)·tau ; den += Σ (m·tau)²  — one vector (tau) read per node.
-              // Two-wide fp32 FMAs (FFMA2) and two independent partial sums per quantity: with one
-              // epilogue warp per scheduler the loop is otherwise bound by the FMA dependency chain.
-              float2 vw[16], vv[16];
+              // num += m·(τ∘w2) ; den += m²·τ²  — two-wide fp32 FMAs and two independent partial
+              // sums per quantity; lanes whose image has fewer nodes compute into slots nobody reads
+              float2 vv[16], v2[16];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 w4 = reinterpret_cast<const float4*>(s_w2 + ch * 32)[q];
-                vv[2 * q] = make_float2(v[4 * q], v[4 * q + 1]);
-                vv[2 * q + 1] = make_float2(v[4 * q + 2], v[4 * q + 3]);
-                vw[2 * q] = __fmul2_rn(vv[2 * q], make_float2(w4.x, w4.y));
-                vw[2 * q + 1] = __fmul2_rn(vv[2 * q + 1], make_float2(w4.z, w4.w));
+              for (int q = 0; q < 16; ++q) {
+                vv[q] = make_float2(v[2 * q], v[2 * q + 1]);
+                v2[q] = __fmul2_rn(vv[q], vv[q]);
               }
+#pragma unroll 1
+              for (int j = 0; j < n_max; ++j) {
+                const int vo = (img_local * kMaxProjNodesPerPass + j) * kBN + ch * 32;
+                const float4* tw = reinterpret_cast<const float4*>(s_tw + vo);
+                const float4* t2 = reinterpret_cast<const float4*>(s_t2 + vo);
+                // both vectors are read up front (see the note at the stored-map path)
+                float4 a4[8], s4[8];
 #pragma unroll
-              for (int j = 0; j < kMaxProjNodesPerPass; ++j) {
-                if (j < n_max) {            // warp-uniform
-                  const float4* tv = reinterpret_cast<const float4*>(
-                      s_vec + (img_local * kMaxProjNodesPerPass + j) * kBN + ch * 32);
-                  float2 na = make_float2(0.f, 0.f), nb = na, da = na, db = na;
+                for (int q = 0; q < 8; ++q) a4[q] = tw[q];
 #pragma unroll
-                  for (int q = 0; q < 8; ++q) {
-                    const float4 t4 = tv[q];
-                    const float2 ta = make_float2(t4.x, t4.y), tb2 = make_float2(t4.z, t4.w);
-                    na = __ffma2_rn(vw[2 * q], ta, na);
-                    nb = __ffma2_rn(vw[2 * q + 1], tb2, nb);
-                    const float2 ea = __fmul2_rn(vv[2 * q], ta), eb = __fmul2_rn(vv[2 * q + 1], tb2);
-                    da = __ffma2_rn(ea, ea, da);
-                    db = __ffma2_rn(eb, eb, db);
-                  }
-                  if (j < n_nodes) {        // lanes with fewer nodes discard
-                    num[j] += (na.x + na.y) + (nb.x + nb.y);
-                    den[j] += (da.x + da.y) + (db.x + db.y);
-                  }
+                for (int q = 0; q < 8; ++q) s4[q] = t2[q];
+                float* pa = acc_row + j * (2 * kBM);
+                float2 na = make_float2(first ? 0.f : pa[0], 0.f), nb = make_float2(0.f, 0.f);
+                float2 da = make_float2(first ? 0.f : pa[kBM], 0.f), db = nb;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  na = __ffma2_rn(vv[2 * q], make_float2(a4[q].x, a4[q].y), na);
+                  nb = __ffma2_rn(vv[2 * q + 1], make_float2(a4[q].z, a4[q].w), nb);
                 }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  da = __ffma2_rn(v2[2 * q], make_float2(s4[q].x, s4[q].y), da);
+                  db = __ffma2_rn(v2[2 * q + 1], make_float2(s4[q].z, s4[q].w), db);
+                }
+                pa[0] = (na.x + na.y) + (nb.x + nb.y);
+                pa[kBM] = (da.x + da.y) + (db.x + db.y);
               }
             } else {
               float v2[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) v2[i] = v[i] * v[i];
+#pragma unroll 1
+              for (int j = 0; j < n_max; ++j) {
+                const int trow_txt = p.node_text[e_beg + min(j, max(n_nodes - 1, 0))];
+                const float4* tw =
+                    reinterpret_cast<const float4*>(p.tauw + (size_t)trow_txt * p.Mp + col0);
+                const float4* t2 =
+                    reinterpret_cast<const float4*>(p.tau2 + (size_t)trow_txt * p.Mp + col0);
+                float* pa = acc_row + j * (2 * kBM);
+                float n = first ? 0.f : pa[0], d = first ? 0.f : pa[kBM];
 #pragma unroll
-              for (int j = 0; j < kMaxProjNodesPerPass; ++j) {
-                if (j < n_max) {            // warp-uniform
-                  const int trow_txt = p.node_text[e_beg + min(j, max(n_nodes - 1, 0))];
-                  const float4* tw =
-                      reinterpret_cast<const float4*>(p.tauw + (size_t)trow_txt * p.Mp + col0);
-                  const float4* t2 =
-                      reinterpret_cast<const float4*>(p.tau2 + (size_t)trow_txt * p.Mp + col0);
-                  float n = num[j], d = den[j];
-#pragma unroll
-                  for (int q = 0; q < 8; ++q) {
-                    const float4 a = tw[q], sq = t2[q];
-                    n = fmaf(v[4 * q + 0], a.x, n); d = fmaf(v2[4 * q + 0], sq.x, d);
-                    n = fmaf(v[4 * q + 1], a.y, n); d = fmaf(v2[4 * q + 1], sq.y, d);
-                    n = fmaf(v[4 * q + 2], a.z, n); d = fmaf(v2[4 * q + 2], sq.z, d);
-                    n = fmaf(v[4 * q + 3], a.w, n); d = fmaf(v2[4 * q + 3], sq.w, d);
-                  }
-                  if (j < n_nodes) { num[j] = n; den[j] = d; }
+                for (int q = 0; q < 8; ++q) {
+                  const float4 a = __ldg(tw + q), sq = __ldg(t2 + q);
+                  n = fmaf(v[4 * q + 0], a.x, n); d = fmaf(v2[4 * q + 0], sq.x, d);
+                  n = fmaf(v[4 * q + 1], a.y, n); d = fmaf(v2[4 * q + 1], sq.y, d);
+                  n = fmaf(v[4 * q + 2], a.z, n); d = fmaf(v2[4 * q + 2], sq.z, d);
+                  n = fmaf(v[4 * q + 3], a.w, n); d = fmaf(v2[4 * q + 3], sq.w, d);
                 }
+                pa[0] = n;
+                pa[kBM] = d;
               }
             }
           }
-          if (warp == 2) N2NMN_STAMP(1, 24 + ch);
+          if (warp == 4) N2NMN_STAMP(1, 24 + ch);
         }
         // release the accumulator buffer to the MMA warp
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
       }
-      if (warp == 2) N2NMN_STAMP(1, 7);
-      // the two column halves of a row meet here: warpgroup 1 hands its partial sums over
+      if (warp == 4) N2NMN_STAMP(1, 7);
+      // the two column halves of a row meet here
       if (wk.set == PS_FIND) {
-        if (half == 1) {
-#pragma unroll
-          for (int j = 0; j < kMaxProjNodesPerPass; ++j) {
-            s_part[(trow * kMaxProjNodesPerPass + j) * 2] = num[j];
-            s_part[(trow * kMaxProjNodesPerPass + j) * 2 + 1] = den[j];
-          }
-        }
         asm volatile("bar.sync 2, 256;" ::: "memory");
-        if (warp == 2) N2NMN_STAMP(1, 28);
+        if (warp == 4) N2NMN_STAMP(1, 28);
         if (half == 0 && row_ok) {
           const float b2 = __ldg(p.elt_b);
-#pragma unroll
-          for (int j = 0; j < kMaxProjNodesPerPass; ++j) {
-            if (j < n_nodes) {
-              const float nn = num[j] + s_part[(trow * kMaxProjNodesPerPass + j) * 2];
-              const float dd = den[j] + s_part[(trow * kMaxProjNodesPerPass + j) * 2 + 1];
-              const int slot = p.node_out[e_beg + j];
-              p.arena[(size_t)slot * p.HW + pix] = nn * rsqrtf(fmaxf(dd, kEps)) + b2;
-            }
+          const float* other = acc_row + kMaxProjNodesPerPass * 2 * kBM;
+          for (int j = 0; j < n_nodes; ++j) {
+            const float nn = acc_row[j * 2 * kBM] + other[j * 2 * kBM];
+            const float dd = acc_row[j * 2 * kBM + kBM] + other[j * 2 * kBM + kBM];
+            const int slot = p.node_out[e_beg + j];
+            p.arena[(size_t)slot * p.HW + pix] = nn * rsqrtf(fmaxf(dd, kEps)) + b2;
           }
         }
-        if (warp == 2) N2NMN_STAMP(1, 29);
-        asm volatile("bar.sync 2, 256;" ::: "memory");   // s_part may be rewritten by the next tile
-        if (warp == 2) N2NMN_STAMP(1, 30);
+        if (warp == 4) N2NMN_STAMP(1, 29);
+        asm volatile("bar.sync 2, 256;" ::: "memory");   // s_part is rewritten by the next tile
+        if (warp == 4) N2NMN_STAMP(1, 30);
       }
     }
   }
 
-  if (warp == 2) N2NMN_STAMP(1, 6);
+  if (warp == 4) N2NMN_STAMP(1, 6);
   // teardown
   ptx::tc_fence_before();
   __syncthreads();

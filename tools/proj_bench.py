@@ -34,4 +34,4 @@ for i in range(60):
     for name, us in ex.launch_times():
         acc.setdefault(name, []).append(us)
 print(os.environ.get('N2NMN_LIB', 'default'), layout, 'B=%d' % B,
-      {k: round(float(np.median(v)), 2) for k, v in acc.items()})
+      {k: (round(float(np.median(v)), 2), round(float(np.mean(v)), 2)) for k, v in acc.items()}, '(median, mean us)')

@@ -97,11 +97,17 @@ for cta in range(148):
         rows_.append([clk[1, cta, 7] - clk[1, cta, 5], clk[1, cta, 6] - clk[1, cta, 7]])
 if rows_:
     print('proj STORED tiles: [chunks, to-exit] n=%d' % len(rows_), np.median(np.array(rows_), axis=0))
-# proj epilogue chunks (slots 24..31) relative to tmem_full (slot 5)
-rows_ = []
-for cta in range(148):
-    v_ = [clk[1, cta, 5]] + [clk[1, cta, 24 + j] for j in range(8)] + [clk[1, cta, 6]]
-    if all(x > 0 for x in v_):
-        rows_.append(np.diff(v_))
-if rows_:
-    print('proj epilogue: cycles per 32-column chunk then tail', np.median(np.array(rows_), axis=0))
+# proj epilogue: the four 32-column chunks of warp 4 (slots 24..27) after tmem_full (slot 5)
+for kind in ('FIND', 'STORED'):
+    rows_ = []
+    for cta in range(148):
+        is_find = clk[1, cta, 28] > 0
+        if is_find != (kind == 'FIND'):
+            continue
+        v_ = [clk[1, cta, 5]] + [clk[1, cta, 24 + j] for j in range(4)] + [clk[1, cta, 7]]
+        if all(x > 0 for x in v_):
+            rows_.append(np.diff(v_))
+    if rows_:
+        a_ = np.array(rows_)
+        print('proj %s tiles: cycles per chunk [c0, c1, c2, c3, release] median' % kind,
+              np.median(a_, axis=0), ' p90', np.percentile(a_, 90, axis=0))
