@@ -27,18 +27,26 @@ constexpr int kBM = 128;           // rows per tile (UMMA M)
 constexpr int kBN = 256;           // columns per N-tile (UMMA N)
 constexpr int kBK = 32;            // fp32 elements per K slice = 128 bytes
 constexpr int kUmmaK = 8;          // K per tcgen05.mma for tf32 (32 bytes)
-// 3 x 48 KB of operand stages: a K slice is consumed in ~700 cycles at the TF32 rate, so three
-// slices in flight cover the L2/DRAM latency (measured: 4 stages are no faster at batch 256 and
-// 1024), and the 48 KB this frees pay for the epilogue staging below.
-#if defined(N2NMN_EXP_STAGES)
-constexpr int kStages = N2NMN_EXP_STAGES;
+// Operand rings: separate rings (and producer warps) for the A slices (features, 16 KB, streamed
+// from DRAM exactly once) and the B slices (weights, 32 KB, L2-resident after the first touch), so
+// that their depths can be chosen independently. Measured at batch 64 / 256 / 1024 (kernel alone):
+// A3/B3 24.5 / 50.7 / 140 us, A5/B2 26.8 / 52.8 / 153 us: the weight ring needs the depth as much as
+// the feature ring does, and 3 + 3 (144 KB) is what fits next to the epilogue staging. (Four
+// 48 KB stages were ~2 us faster at batch 64 but leave no room for that staging.)
+#if defined(N2NMN_EXP_STAGES_A)
+constexpr int kStagesA = N2NMN_EXP_STAGES_A;
 #else
-constexpr int kStages = 3;
+constexpr int kStagesA = 3;
+#endif
+#if defined(N2NMN_EXP_STAGES_B)
+constexpr int kStagesB = N2NMN_EXP_STAGES_B;
+#else
+constexpr int kStagesB = 3;
 #endif
 constexpr int kABytes = kBM * kBK * 4;   // 16384
 constexpr int kBBytes = kBN * kBK * 4;   // 32768
-constexpr int kStageBytes = kABytes + kBBytes;
-// Warpgroup 0 = {TMA warp, MMA warp, two idle warps}, warpgroups 1-2 = epilogue. Roles are split on
+constexpr int kRingBytes = kStagesA * kABytes + kStagesB * kBBytes;
+// Warpgroup 0 = {A-TMA warp, MMA warp, B-TMA warp, one idle warp}, warpgroups 1-2 = epilogue. Roles are split on
 // warpgroup boundaries so that setmaxnreg can move registers from the producers (which need ~30)
 // to the epilogue warps (which want > 200: a 32-column accumulator chunk in flight, the one being
 // reduced, its squares, and a consumer node's two staged vectors loaded as ONE batch — with two
@@ -65,7 +73,7 @@ constexpr int kStoreFloats = (kEpiThreads / 32) * 32 * 32;            // 8 warps
 constexpr int kVecBytes =
     (2 * kVecFloats + kBN + kPartFloats + kStoreFloats) * 4 + kBM * (int)sizeof(float*);
 // dynamic smem: stages + staged vectors + barriers
-constexpr int kProjSmemBytes = kStages * kStageBytes + kVecBytes + 256;
+constexpr int kProjSmemBytes = kRingBytes + kVecBytes + 256;
 
 struct ProjTensorMaps {
   CUtensorMap a;                     // features [total_rows, Dk] fp32, box 32 x 128
@@ -82,16 +90,18 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
   uint8_t* smem = proj_smem;
   if ((ptx::smem_u32(proj_smem) & 1023u) != 0) __trap();
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kStages * kABytes;
-  float* s_tw = reinterpret_cast<float*>(smem + kStages * kStageBytes);   // [2][8][256] τ∘w2
+  uint8_t* smem_b = smem + kStagesA * kABytes;
+  float* s_tw = reinterpret_cast<float*>(smem + kRingBytes);              // [2][8][256] τ∘w2
   float* s_t2 = s_tw + kVecFloats;                                         // [2][8][256] τ²
   float* s_bias = s_t2 + kVecFloats;
   float* s_part = s_bias + kBN;          // [2 halves][8 nodes][num|den][128 rows]
   float* s_store = s_part + kPartFloats; // [8 warps][32 rows][32 cols], 16-byte chunks swizzled
   float** s_rowdst = reinterpret_cast<float**>(s_store + kStoreFloats);   // [128] or nullptr
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kVecBytes);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full = empty_bar + kStages;   // [2]
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(smem + kRingBytes + kVecBytes);
+  uint64_t* empty_a = full_a + kStagesA;
+  uint64_t* full_b = empty_a + kStagesA;
+  uint64_t* empty_b = full_b + kStagesB;
+  uint64_t* tmem_full = empty_b + kStagesB;    // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -102,9 +112,13 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tensormap(&tm.a);
     for (int i = 0; i < NUM_PROJ_SETS; ++i) ptx::prefetch_tensormap(&tm.b[i]);
-    for (int s = 0; s < kStages; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < kStagesA; ++s) {
+      ptx::mbar_init(&full_a[s], 1);
+      ptx::mbar_init(&empty_a[s], 1);
+    }
+    for (int s = 0; s < kStagesB; ++s) {
+      ptx::mbar_init(&full_b[s], 1);
+      ptx::mbar_init(&empty_b[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
@@ -122,7 +136,7 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
   if (warp == 0) {
-    // ===================================================================== TMA producer
+    // ===================================================================== TMA producer, A ring
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
@@ -130,23 +144,36 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
         const ProjWork wk = p.work[wi];
         for (int nt = 0; nt < p.n_tiles; ++nt) {
           for (int kb = 0; kb < p.k_blocks; ++kb) {
-            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-#if defined(N2NMN_EXP_SKIP_A)      // timing experiments only (results are garbage)
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], kBBytes);
-            ptx::tma_load_2d(smem_b + stage * kBBytes, &tm.b[wk.set], kb * kBK, nt * kBN,
-                             &full_bar[stage]);
-#elif defined(N2NMN_EXP_SKIP_B)
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], kABytes);
-            ptx::tma_load_2d(smem_a + stage * kABytes, &tm.a, kb * kBK, wk.row0,
-                             &full_bar[stage]);
+            ptx::mbar_wait(&empty_a[stage], phase ^ 1);
+            ptx::mbar_arrive_expect_tx(&full_a[stage], kABytes);
+#if !defined(N2NMN_EXP_SKIP_A)      // timing experiments only (results are garbage)
+            ptx::tma_load_2d(smem_a + stage * kABytes, &tm.a, kb * kBK, wk.row0, &full_a[stage]);
 #else
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-            ptx::tma_load_2d(smem_a + stage * kABytes, &tm.a, kb * kBK, wk.row0,
-                             &full_bar[stage]);
-            ptx::tma_load_2d(smem_b + stage * kBBytes, &tm.b[wk.set], kb * kBK, nt * kBN,
-                             &full_bar[stage]);
+            ptx::tma_load_2d(smem_a + stage * kABytes, &tm.a, 0, 0, &full_a[stage]);
 #endif
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            if (++stage == kStagesA) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================================================================== TMA producer, B ring
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int wi = blockIdx.x; wi < p.num_work; wi += gridDim.x) {
+        const ProjWork wk = p.work[wi];
+        for (int nt = 0; nt < p.n_tiles; ++nt) {
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            ptx::mbar_wait(&empty_b[stage], phase ^ 1);
+            ptx::mbar_arrive_expect_tx(&full_b[stage], kBBytes);
+#if !defined(N2NMN_EXP_SKIP_B)
+            ptx::tma_load_2d(smem_b + stage * kBBytes, &tm.b[wk.set], kb * kBK, nt * kBN,
+                             &full_b[stage]);
+#else
+            ptx::tma_load_2d(smem_b + stage * kBBytes, &tm.b[wk.set], 0, 0, &full_b[stage]);
+#endif
+            if (++stage == kStagesB) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -155,8 +182,8 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
     // ===================================================================== MMA issuer
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_tf32(kBM, kBN);
-      int stage = 0;
-      uint32_t phase = 0;
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
       uint32_t it = 0;   // accumulator uses so far
       for (int wi = blockIdx.x; wi < p.num_work; wi += gridDim.x) {
         for (int nt = 0; nt < p.n_tiles; ++nt, ++it) {
@@ -165,11 +192,12 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
           ptx::tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc * kBN;
           for (int kb = 0; kb < p.k_blocks; ++kb) {
-            ptx::mbar_wait(&full_bar[stage], phase);          // TMA bytes landed
+            ptx::mbar_wait(&full_b[sb], phb);                 // TMA bytes landed
+            ptx::mbar_wait(&full_a[sa], pha);
             if (kb < 16) N2NMN_STAMP(1, 8 + kb);
             ptx::tc_fence_after();
-            const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * kABytes));
-            const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * kBBytes));
+            const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a + sa * kABytes));
+            const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b + sb * kBBytes));
 #if !defined(N2NMN_EXP_SKIP_MMA)
 #pragma unroll
             for (int k = 0; k < kBK / kUmmaK; ++k) {
@@ -177,8 +205,10 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
               ptx::umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
             }
 #endif
-            ptx::umma_commit(&empty_bar[stage]);              // frees the smem slot when done
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            ptx::umma_commit(&empty_a[sa]);                   // frees the smem slots when done
+            ptx::umma_commit(&empty_b[sb]);
+            if (++sa == kStagesA) { sa = 0; pha ^= 1; }
+            if (++sb == kStagesB) { sb = 0; phb ^= 1; }
           }
           ptx::umma_commit(&tmem_full[acc]);                  // accumulator ready
         }
