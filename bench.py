@@ -49,10 +49,14 @@ def parse_args():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--wave', action='store_true', help='depth-bucketed wave executor')
     ap.add_argument('--host-threads', type=int, default=0,
-                    help='1: one host thread per context (ExecutorPool.forward_many); 0: one '
-                         'host thread feeds all contexts')
+                    help='ignored (kept for old command lines): every context of the pool has its '
+                         'own native worker thread')
     ap.add_argument('--no-train', action='store_true', help='skip the train-step measurement')
-    ap.add_argument('--streams', type=int, default=4,
+    ap.add_argument('--tree-cluster', type=int, default=None,
+                    help='CTAs per question in the executor kernel (default: chosen by the pool)')
+    ap.add_argument('--proj-ctas', type=int, default=None,
+                    help='cap of the contraction kernel grid (default: chosen by the pool; 0 = all SMs)')
+    ap.add_argument('--streams', type=int, default=12,
                     help='contexts/streams fed round-robin (independent batches overlap)')
     return ap.parse_args()
 
@@ -220,6 +224,31 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(torch, index):
+    """Run this process (and so its pinned-buffer allocations and the pool's worker threads) on
+    the CPUs that are local to the GPU's PCIe root: host<->device copies from the other socket
+    run at about half the rate on a two-socket box. Best effort; returns what was done."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = '%04x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open('/sys/bus/pci/devices/%s/local_cpulist' % bdf) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(','):
+            if '-' in part:
+                a, b = part.split('-')
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return 'no local cpus in the affinity mask'
+        os.sched_setaffinity(0, cpus)
+        return 'bound to %d cpus local to %s (%s)' % (len(cpus), bdf, spec)
+    except Exception as e:   # no sysfs in this container, or not a PCI device
+        return 'not bound: %s' % e
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -239,6 +268,7 @@ def main():
         raise SystemExit('bench.py: no CUDA device. The product path has no CPU fallback.')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa = bind_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
@@ -255,8 +285,10 @@ def main():
     flags = _lib.FLAG_WAVE_EXECUTOR if args.wave else 0
     K = max(1, args.streams)
     pool = ExecutorPool('clevr', feats[0], wvs[0], C, asm, weights=weights, num_streams=K,
-                        flags=flags, max_batch=B, max_T=T_DEC)
+                        flags=flags, max_batch=B, max_T=T_DEC, tree_cluster=args.tree_cluster,
+                        proj_ctas=args.proj_ctas)
     ex = pool.executors[0]
+    PROJ_CTAS, TREE_CLUSTER = pool.proj_ctas, pool.tree_cluster
     scores_k = [torch.empty((B, C), dtype=torch.float32, device=dev) for _ in range(K)]
     scores = scores_k[0]
 
@@ -284,16 +316,13 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    t_host0 = time.perf_counter()
     pool.begin()          # the K streams start after e0 ...
-    if args.host_threads:
-        idx = [(args.warmup + i) % P for i in range(args.steps)]
-        pool.forward_many([feats[k] for k in idx], [wvs[k] for k in idx], [toks[k] for k in idx],
-                          [scores_k[i % K] for i in range(args.steps)])
-    else:
-        for i in range(args.steps):
-            step(args.warmup + i)
+    for i in range(args.steps):
+        step(args.warmup + i)
     pool.end()            # ... and e1 is recorded after all of them have drained
     e1.record()
+    host_ms = (time.perf_counter() - t_host0) * 1e3   # time the host needed to enqueue the steps
     barrier()
     ms = e0.elapsed_time(e1)
     launches = pool.launch_count() - launches0
@@ -315,7 +344,7 @@ def main():
         for i in range(2 * K):
             pool.submit_host(hf[i % hp], hw[i % hp], toks[i % hp], hs[i % hp])
         pool.end()
-        k_e2e = max(10, min(args.steps, 100))
+        k_e2e = max(10, min(args.steps, 400))
         barrier()
         t0 = time.perf_counter()
         pool.begin()
@@ -343,26 +372,34 @@ def main():
     roof, kernel_us = None, {}
     if rank == 0:
         pk = peaks()
-        ex.set_profiling(True)
-        acc, bytes_acc, flops_acc, n = {}, 0, 0, 0
-        for i in range(min(args.steps, 50)):
-            ex.forward_device(feats[i % P], wvs[i % P], toks[i % P], out=scores)
-            for name, us in ex.launch_times():
-                acc.setdefault(name, []).append(us)
-            info = ex.last_step_info()
-            bytes_acc += info['kernel_bytes'][1]
-            flops_acc += info['kernel_flops'][1]
-            n += 1
-        ex.set_profiling(False)
-        kernel_us = {k: float(np.mean(v)) for k, v in acc.items()}
+        def timed_pass():
+            ex.set_profiling(True)
+            acc, bytes_acc, flops_acc, n = {}, 0, 0, 0
+            for i in range(min(args.steps, 50)):
+                ex.forward_device(feats[i % P], wvs[i % P], toks[i % P], out=scores)
+                for name, us in ex.launch_times():
+                    acc.setdefault(name, []).append(us)
+                info = ex.last_step_info()
+                bytes_acc += info['kernel_bytes'][1]
+                flops_acc += info['kernel_flops'][1]
+                n += 1
+            ex.set_profiling(False)
+            return {k: float(np.mean(v)) for k, v in acc.items()}, bytes_acc / max(n, 1), \
+                flops_acc / max(n, 1)
+
+        def fractions(us, nbytes, nflops):
+            dur = us * 1e-6
+            gbs, tfs = nbytes / dur / 1e9, nflops / dur / 1e12
+            return gbs, tfs, gbs / pk['hbm_gbs'], tfs / (pk['bf16_tflops'] / 2)
+
+        # as run in the timed region (the pool's narrow grid when several batches are in flight)
+        kernel_us, nbytes, nflops = timed_pass()
         proj = 'proj_umma_kernel'
-        if proj in kernel_us and n:
-            dur = kernel_us[proj] * 1e-6
-            gbs = bytes_acc / n / dur / 1e9
-            tfs = flops_acc / n / dur / 1e12
+        if proj in kernel_us:
             tf32_peak = pk['bf16_tflops'] / 2
-            hbm_frac, tc_frac = gbs / pk['hbm_gbs'], tfs / tf32_peak
+            gbs, tfs, hbm_frac, tc_frac = fractions(kernel_us[proj], nbytes, nflops)
             bound = 'hbm' if hbm_frac >= tc_frac else 'tensor'
+            grid = min(PROJ_CTAS, 148) if PROJ_CTAS > 0 else 148
             roof = {'kernel': proj, 'bound': bound,
                     'achieved': gbs if bound == 'hbm' else tfs,
                     'peak': pk['hbm_gbs'] if bound == 'hbm' else tf32_peak,
@@ -370,10 +407,23 @@ def main():
                     'frac': max(hbm_frac, tc_frac), 'traffic': ncu_traffic(proj),
                     'hbm_frac': hbm_frac, 'tensor_frac_of_tf32_peak': tc_frac,
                     'avg_launch_us': kernel_us[proj],
-                    'algorithmic_bytes_per_launch': bytes_acc / n,
-                    'flops_per_launch': flops_acc / n,
+                    'algorithmic_bytes_per_launch': nbytes,
+                    'flops_per_launch': nflops,
                     'peak_source': pk['source'] + '; TF32 peak taken as bf16 burst / 2',
-                    'share_of_step': kernel_us[proj] / max(sum(kernel_us.values()), 1e-9)}
+                    'share_of_step': kernel_us[proj] / max(sum(kernel_us.values()), 1e-9),
+                    'grid_ctas': grid,
+                    'frac_of_occupied_sms': max(hbm_frac, tc_frac) / (grid / 148.0),
+                    'note': 'as launched in the timed region: a persistent grid of %d CTAs (one '
+                            'per SM) so that the other SMs run the other in-flight batches; '
+                            'frac is against the WHOLE chip' % grid}
+            if PROJ_CTAS > 0:   # the same launch spread over every SM (lowest single-batch latency)
+                ex.set_proj_ctas(0)
+                kus2, nb2, nf2 = timed_pass()
+                ex.set_proj_ctas(PROJ_CTAS)
+                g2, t2, hf2, tf2 = fractions(kus2[proj], nb2, nf2)
+                roof['full_grid'] = {'grid_ctas': 148, 'avg_launch_us': kus2[proj],
+                                     'hbm_frac': hf2, 'tensor_frac_of_tf32_peak': tf2,
+                                     'frac': max(hf2, tf2)}
 
     # ---- config 3: policy-search train step (fwd + bwd + ONE NCCL all-reduce + clip + Adam),
     #      T=10 as in exp_clevr/train_clevr_rl_gt_layout.py; reported beside the eval headline
@@ -433,9 +483,11 @@ def main():
                        'cache': 'inputs larger than L2: %d distinct resident batches (%.0f MB) '
                                 'walked round-robin' % (P, P * B * H * W * D * 4 / 1e6),
                        'executor': 'wave' if args.wave else 'tree',
-                       'streams': K, 'host_threads': K if args.host_threads else 1,
+                       'streams': K, 'host_threads': K, 'tree_cluster_ctas': TREE_CLUSTER,
+                       'proj_grid_ctas': PROJ_CTAS if PROJ_CTAS > 0 else 148,
                        'nodes_per_batch': info['num_nodes'], 'max_depth': info['max_depth']},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
+            'host_enqueue_ms_per_step': host_ms / args.steps, 'host_numa': numa,
             'roofline': roof, 'cpu_baseline': cpu, 'kernel_us': kernel_us, 'train_step': train,
         }
         print(json.dumps(line), flush=True)

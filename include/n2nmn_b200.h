@@ -198,6 +198,34 @@ int n2nmn_forward_host(n2nmn_ctx* ctx, const float* feat_host, const float* word
                        const int32_t* tokens_host, int T, int N, const int32_t* vocab_ops,
                        int num_vocab, float* scores_host, uint8_t* validity_out, void* stream);
 
+/* Same, but returns without synchronising: the H2D copies, the kernels and the D2H copy of the
+ * scores are only enqueued on `stream`; `scores_host` is valid once the stream has drained. Host
+ * buffers must be pinned and must stay untouched until then. */
+int n2nmn_forward_host_async(n2nmn_ctx* ctx, const float* feat_host, const float* word_vecs_host,
+                             const int32_t* tokens_host, int T, int N, const int32_t* vocab_ops,
+                             int num_vocab, float* scores_host, uint8_t* validity_out,
+                             void* stream);
+
+/* ---- several batches in flight -------------------------------------------------------------------
+ * One worker thread per (context, stream) pair; n2nmn_pool_submit copies the token matrix into a
+ * job for worker `slot` and returns, the worker runs n2nmn_forward_tokens (host_io == 0: device
+ * pointers) or n2nmn_forward_host_async (host_io != 0: pinned host pointers) on its stream.
+ * n2nmn_pool_wait blocks until every submitted batch has been ENQUEUED (not finished) and returns
+ * the first error; `validity_out` arrays are valid after it. The contexts must outlive the pool
+ * and must not be used directly while jobs are pending. No reference counterpart (the reference
+ * evaluates one batch per session.run, exp_clevr/eval_clevr.py:96-133). */
+typedef struct n2nmn_pool n2nmn_pool;
+int n2nmn_pool_create(n2nmn_ctx** ctxs, void** streams, int num, const int32_t* vocab_ops,
+                      int num_vocab, n2nmn_pool** out);
+int n2nmn_pool_destroy(n2nmn_pool* pool);
+int n2nmn_pool_size(const n2nmn_pool* pool);
+int n2nmn_pool_submit(n2nmn_pool* pool, int slot, const float* feat, const float* word_vecs,
+                      const int32_t* tokens_host, int T, int N, float* scores,
+                      uint8_t* validity_out, int host_io);
+int n2nmn_pool_wait(n2nmn_pool* pool);
+const char* n2nmn_pool_last_error(void);
+
+
 /* ---- training step (exp_clevr/train_clevr_rl_gt_layout.py:108-139) -------------------------------
  * Weights, gradients and the Adam moments live in caller-owned flat fp32 device buffers of
  * n2nmn_flat_size() floats: the variables of n2nmn_variable_info() in order, each in its TF shape
@@ -230,6 +258,13 @@ int n2nmn_adam_step(n2nmn_ctx* ctx, float* wflat_dev, float* gflat_dev, float* m
  * throughput from smaller clusters. Tuning only: results are identical. No reference counterpart
  * (the reference executor is TensorFlow Fold's scheduler, models_clevr/nmn3_model.py:118-133). */
 int n2nmn_set_tree_cluster(n2nmn_ctx* ctx, int ctas_per_question);
+
+/* Cap of the persistent grid of the conv_image contraction kernel; 0 (the default) = one CTA per
+ * SM, which gives the shortest kernel for a single batch. With many batches in flight a narrower
+ * grid (each CTA then walks several tiles, its epilogue overlapping the next tile's MMAs) leaves
+ * the other SMs to the other batches' kernels and raises the throughput. Tuning only: results are
+ * identical. */
+int n2nmn_set_proj_ctas(n2nmn_ctx* ctx, int max_ctas);
 
 /* Per-launch device time of the last n2nmn_run_schedule in microseconds (CUDA events recorded
  * around every launch when enabled). names/us arrays of length >= capacity. */

@@ -60,6 +60,15 @@ SIGNATURES = {
     'n2nmn_last_step_info': (C.c_int, [_P, C.POINTER(SchedInfo)]),
     'n2nmn_forward_host': (C.c_int, [_P, _P, _P, _I32P, C.c_int, C.c_int, _I32P, C.c_int, _P,
                                      C.POINTER(C.c_uint8), _P]),
+    'n2nmn_forward_host_async': (C.c_int, [_P, _P, _P, _I32P, C.c_int, C.c_int, _I32P, C.c_int, _P,
+                                           C.POINTER(C.c_uint8), _P]),
+    'n2nmn_pool_create': (C.c_int, [C.POINTER(_P), C.POINTER(_P), C.c_int, _P, C.c_int,
+                                    C.POINTER(_P)]),
+    'n2nmn_pool_destroy': (C.c_int, [_P]),
+    'n2nmn_pool_size': (C.c_int, [_P]),
+    'n2nmn_pool_submit': (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_int]),
+    'n2nmn_pool_wait': (C.c_int, [_P]),
+    'n2nmn_pool_last_error': (C.c_char_p, []),
     'n2nmn_flat_size': (C.c_int64, [_P]),
     'n2nmn_flat_offset': (C.c_int, [_P, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     'n2nmn_load_flat_weights': (C.c_int, [_P, _P, _P]),
@@ -68,6 +77,7 @@ SIGNATURES = {
     'n2nmn_adam_step': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_float, C.c_float, C.c_float,
                                   C.c_float, C.c_float, C.c_float, _P]),
     'n2nmn_set_tree_cluster': (C.c_int, [_P, C.c_int]),
+    'n2nmn_set_proj_ctas': (C.c_int, [_P, C.c_int]),
     'n2nmn_set_profiling': (C.c_int, [_P, C.c_int]),
     'n2nmn_get_launch_times': (C.c_int, [_P, C.POINTER(C.c_char_p), C.POINTER(C.c_float),
                                          C.c_int]),

@@ -118,6 +118,8 @@ struct n2nmn_ctx {
   int tree_smem_bytes = 0;
   int stack_cap = 0;           // attention-stack slots the tree kernel may use
   int tree_cluster = 0;        // 0 = choose from the batch size; else forced (N2NMN_TREE_CLUSTER)
+  bool fp32_stencil = false;   // N2NMN_FP32_STENCIL=1: CUDA-core Transform stencil (A/B timing)
+  int proj_max_ctas = 0;       // 0 = one CTA per SM; else cap of the persistent projection grid
   bool use_pdl = true;         // programmatic dependent launch between the three kernels
   n2nmn_sched module_sched;    // scratch schedule of n2nmn_module_fwd
   n2nmn_sched step_sched;      // scratch schedule of n2nmn_forward_tokens
@@ -372,7 +374,8 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaS
     p.mslot = reinterpret_cast<const int32_t*>(d + o.mslot);
     p.num_images = (int)(S.mslot.size() / NUM_PROJ_SETS);
     p.mbuf = c->mbuf;
-    const int grid = std::min(p.num_work, c->num_sms);
+    const int grid = std::min(p.num_work, c->proj_max_ctas > 0 ? std::min(c->proj_max_ctas, c->num_sms)
+                                                              : c->num_sms);
     if (c->cfg.flags & N2NMN_FLAG_PROJ_FP32_SIMT) {
       const size_t smem = (size_t)(kSimtRows * kSimtKChunk + kSimtRows * c->Mp) * sizeof(float);
       proj_simt_kernel<<<p.num_work, 256, smem, st>>>(p);
@@ -439,7 +442,8 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaS
     }
     lc.attrs = attr;
     lc.numAttrs = na;
-    const int wa = write_arena ? 1 : 0;
+    const int wa = (write_arena ? kTreeWriteArena : 0) |
+                   (((c->cfg.flags & N2NMN_FLAG_PROJ_FP32_SIMT) || c->fp32_stencil) ? kTreeFp32Stencil : 0);
     if (ks3) CUDA_TRY(cudaLaunchKernelEx(&lc, tree_kernel<3>, nc, d_nodes, d_qptr, cs, slots, wa));
     else CUDA_TRY(cudaLaunchKernelEx(&lc, tree_kernel<5>, nc, d_nodes, d_qptr, cs, slots, wa));
     ++c->launches;
@@ -613,6 +617,8 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
   c->module_sched.shp = c->shp;
   c->step_sched.shp = c->shp;
   if (const char* e = std::getenv("N2NMN_NO_PDL")) c->use_pdl = (std::atoi(e) == 0);
+  if (const char* e = std::getenv("N2NMN_FP32_STENCIL")) c->fp32_stencil = (std::atoi(e) != 0);
+  if (const char* e = std::getenv("N2NMN_PROJ_CTAS")) c->proj_max_ctas = std::max(0, std::atoi(e));
   if (const char* e = std::getenv("N2NMN_TREE_CLUSTER")) {
     const int v = std::atoi(e);
     if (v == 1 || v == 2 || v == 4 || v == 8) c->tree_cluster = v;
@@ -950,13 +956,16 @@ int n2nmn_forward_tokens(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
   return run_tables(c, sc, scores_dev, c->arena, static_cast<cudaStream_t>(stream));
 }
 
-int n2nmn_forward_host(n2nmn_ctx* c, const float* feat_host, const float* wv_host,
-                       const int32_t* tokens, int T, int N, const int32_t* vocab_ops,
-                       int num_vocab, float* scores_host, uint8_t* validity_out, void* stream) {
+namespace {
+int forward_host_impl(n2nmn_ctx* c, const float* feat_host, const float* wv_host,
+                      const int32_t* tokens, int T, int N, const int32_t* vocab_ops,
+                      int num_vocab, float* scores_host, uint8_t* validity_out, void* stream,
+                      bool sync) {
   if (!c || !feat_host || !wv_host || !tokens || !scores_host)
     return fail(N2NMN_ERR_ARG, "null argument");
   if (N <= 0 || N > c->cfg.max_batch || T <= 0 || T > c->cfg.max_T)
     return fail(N2NMN_ERR_CAPACITY, "N or T exceeds the context capacity");
+  CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t fbytes = (size_t)N * c->HW * c->cfg.D * sizeof(float);
   const size_t wbytes = (size_t)T * N * c->cfg.text_dim * sizeof(float);
@@ -974,12 +983,28 @@ int n2nmn_forward_host(n2nmn_ctx* c, const float* feat_host, const float* wv_hos
                                 c->e2e_scores, validity_out, stream);
   if (rc == 0) {
     cudaError_t e = cudaMemcpyAsync(scores_host, c->e2e_scores, sbytes, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && sync) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) rc = fail(N2NMN_ERR_CUDA, cudaGetErrorString(e));
-  } else {
+  } else if (sync) {
     cudaStreamSynchronize(st);
   }
   return rc;
+}
+}  // namespace
+
+int n2nmn_forward_host(n2nmn_ctx* c, const float* feat_host, const float* wv_host,
+                       const int32_t* tokens, int T, int N, const int32_t* vocab_ops,
+                       int num_vocab, float* scores_host, uint8_t* validity_out, void* stream) {
+  return forward_host_impl(c, feat_host, wv_host, tokens, T, N, vocab_ops, num_vocab, scores_host,
+                           validity_out, stream, true);
+}
+
+int n2nmn_forward_host_async(n2nmn_ctx* c, const float* feat_host, const float* wv_host,
+                             const int32_t* tokens, int T, int N, const int32_t* vocab_ops,
+                             int num_vocab, float* scores_host, uint8_t* validity_out,
+                             void* stream) {
+  return forward_host_impl(c, feat_host, wv_host, tokens, T, N, vocab_ops, num_vocab, scores_host,
+                           validity_out, stream, false);
 }
 
 
@@ -1145,6 +1170,13 @@ int n2nmn_set_tree_cluster(n2nmn_ctx* c, int ctas_per_question) {
   if (!(v == 0 || v == 1 || v == 2 || v == 4 || v == 8))
     return fail(N2NMN_ERR_ARG, "n2nmn_set_tree_cluster: ctas_per_question must be 0, 1, 2, 4 or 8");
   c->tree_cluster = v;
+  return 0;
+}
+
+int n2nmn_set_proj_ctas(n2nmn_ctx* c, int max_ctas) {
+  if (!c) return fail(N2NMN_ERR_ARG, "n2nmn_set_proj_ctas: null context");
+  if (max_ctas < 0) return fail(N2NMN_ERR_ARG, "n2nmn_set_proj_ctas: max_ctas must be >= 0");
+  c->proj_max_ctas = max_ctas;
   return 0;
 }
 

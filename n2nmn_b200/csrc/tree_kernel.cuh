@@ -18,6 +18,8 @@
 
 namespace n2nmn {
 
+constexpr int kTreeWriteArena = 1;     // launch flags
+constexpr int kTreeFp32Stencil = 2;    // exact-fp32 Transform stencil on the CUDA cores (verification)
 constexpr int kTreeFindSlots = 10;   // Find / Filter maps prefetched per question
 constexpr int kTransformPB = 5;      // pixels register-blocked per warp in the stencil
 constexpr int kTreeNodeCap = 48;     // node records of one question kept in smem
@@ -34,7 +36,7 @@ __host__ __device__ inline TreeSmem tree_smem_layout(int H, int W, int Mp, int k
   s.stack = stack_slots * s.HWp;
   s.ftmp = kTreeFindSlots * s.HWp;
   s.outbuf = 2 * s.HWp;
-  s.pad = ((H + ksize - 1) * (W + ksize - 1) + 3) & ~3;
+  s.pad = (2 * (H + ksize - 1) * (W + ksize - 1) + 3) & ~3;   // padded map + zero guard copy
   s.v = 3 * Mp;
   s.part = 4 * Mp;
   s.z = (2 * (HW + 2) + 3) & ~3;
@@ -94,10 +96,166 @@ __device__ __forceinline__ void gather_pixels(const Coop& co, const float* outbu
   }
 }
 
+// ---- Transform stencil on the tensor cores ---------------------------------------------------------
+// conv_maps of TransformModule (models_clevr/nmn3_modules.py:197-201, SHAPES :83-87) is the GEMM
+//   maps[p, c] = Σ_tap window(p)[tap] · K[tap, c]        (H·W x KS² x M, 0.94 MFMA per node)
+// and its consumer (∘τ, l2-normalise over c, ·w2) is a per-row reduction over c. The CUDA cores
+// need ~5.6-11 K cycles per node for it; as m16n8k8 TF32 MMAs with the window gathered straight out
+// of the zero-padded attention map it is ~1.5 K. Register-fragment `mma.sync` rather than tcgen05:
+// the product is 160 x 256 x 32 per node, issued from inside a latency-bound walk, and its result
+// is consumed by the issuing lanes' own row reductions — no TMEM round trip, no descriptors.
+// Operands are rounded to TF32 once, where they are written to shared memory (the padded map when
+// it is filled, the filter bank after it has been staged): cvt.rna.tf32 is a three-instruction
+// sequence on sm_100 and the fragment loads are the inner loop. Accumulation is fp32.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void mma_tf32_m16n8k8(float (&d)[4], const uint32_t (&a)[4],
+                                                 const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+constexpr int kStencilRowsPerPass = 128;   // rows reduced through `scratch` at a time (8 m-tiles)
+
+// Owner rank of pixel p when the 16-row tiles of the map are dealt to the cluster in contiguous
+// blocks (the tensor-core stencil's split).
+__device__ __forceinline__ int stencil_owner(int p, int HW, int csize) {
+  const int n_mt = (HW + 15) >> 4, per = (n_mt + csize - 1) / csize;
+  return (p >> 4) / per;
+}
+
+// One Transform node on this CTA's share of the pixels. pad: zero-padded input map
+// [(H+KS-1)][(W+KS-1)], TF32-rounded, followed by an all-zero copy of the same size; kbank: [KS*KS][Mp], TF32-rounded;
+// tau / w2 / cbias: [Mp] (zero beyond M);
+// scratch: >= 8 warps x 128 rows x 2 floats; ob: this CTA's output pixels (indexed by p).
+template <int KS>
+__device__ __forceinline__ void transform_stencil_mma(const Coop& co, const float* pad,
+                                                      const float* kbank, const float* tau,
+                                                      const float* w2, const float* cbias,
+                                                      float b2, float* scratch, float* ob,
+                                                      int Hh, int Ww, int Mp) {
+  constexpr int KK = KS * KS, KSTEPS = (KK + 7) / 8;
+  const int HW = Hh * Ww, PW = Ww + KS - 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int n_mt = (HW + 15) >> 4, per = (n_mt + co.size - 1) / co.size;
+  const int mt_beg = co.rank * per, mt_end = min(n_mt, mt_beg + per);
+  // taps beyond KS² read the all-zero guard copy that follows the padded map (any row base lands in
+  // it); rows beyond the map use base 0 and are never written out. No clamps in the inner loop.
+  const int zero_off = (Hh + KS - 1) * PW;
+  const uint32_t inv_w = (1u << 20) / (uint32_t)Ww + 1u;   // p / Ww for p < 4096
+  // window offsets of the taps this lane feeds: 8*ks + t and 8*ks + t + 4
+  int toff[KSTEPS][2];
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int tap = 8 * ks + t + 4 * h;
+      toff[ks][h] = (tap < KK) ? (tap / KS) * PW + (tap % KS) : zero_off;   // -> the zero guard
+    }
+  for (int pass = mt_beg; pass < mt_end; pass += kStencilRowsPerPass / 16) {
+    const int pass_end = min(mt_end, pass + kStencilRowsPerPass / 16);
+    bool first_cb = true;
+    for (int cb = warp * 32; cb < Mp; cb += nwarps * 32) {   // this warp's 32-channel blocks
+      uint32_t bf[KSTEPS][4][2];
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS; ++ks)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int tap = 8 * ks + t + 4 * h;
+            const uint32_t v = __float_as_uint(kbank[min(tap, KK - 1) * Mp + cb + 8 * j + g]);
+            bf[ks][j][h] = (tap < KK) ? v : 0u;
+          }
+      // per-channel constants of this lane's 8 output columns (c = cb + 8j + 2t, +1)
+      float2 cb2[4], tw2[4], tt2[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = cb + 8 * j + 2 * t;
+        const float2 tv = *reinterpret_cast<const float2*>(tau + c);
+        const float2 wv = *reinterpret_cast<const float2*>(w2 + c);
+        cb2[j] = *reinterpret_cast<const float2*>(cbias + c);
+        tw2[j] = make_float2(tv.x * wv.x, tv.y * wv.y);
+        tt2[j] = make_float2(tv.x * tv.x, tv.y * tv.y);
+      }
+      if (threadIdx.x == 0) N2NMN_STAMP(2, 25);
+      for (int mt = pass; mt < pass_end; ++mt) {
+        if (threadIdx.x == 0 && mt - pass < 3) N2NMN_STAMP(2, 17 + (mt - pass));
+        const int p0 = mt * 16 + g, p1 = p0 + 8;
+        const int y0 = (int)(((uint32_t)p0 * inv_w) >> 20), y1 = (int)(((uint32_t)p1 * inv_w) >> 20);
+        const int base0 = (p0 < HW) ? y0 * PW + (p0 - y0 * Ww) : 0;
+        const int base1 = (p1 < HW) ? y1 * PW + (p1 - y1 * Ww) : 0;
+        float acc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          uint32_t af[4];
+          af[0] = __float_as_uint(pad[base0 + toff[ks][0]]);
+          af[1] = __float_as_uint(pad[base1 + toff[ks][0]]);
+          af[2] = __float_as_uint(pad[base0 + toff[ks][1]]);
+          af[3] = __float_as_uint(pad[base1 + toff[ks][1]]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mma_tf32_m16n8k8(acc[j], af, bf[ks][j]);
+        }
+        // rows g and g+8: num = Σ_c (m+b)·τ·w2, den = Σ_c ((m+b)·τ)²
+        float n0 = 0.f, d0 = 0.f, n1 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = acc[j][0] + cb2[j].x, b = acc[j][1] + cb2[j].y;
+          const float c2 = acc[j][2] + cb2[j].x, d = acc[j][3] + cb2[j].y;
+          n0 = fmaf(a, tw2[j].x, n0); n0 = fmaf(b, tw2[j].y, n0);
+          d0 = fmaf(a * a, tt2[j].x, d0); d0 = fmaf(b * b, tt2[j].y, d0);
+          n1 = fmaf(c2, tw2[j].x, n1); n1 = fmaf(d, tw2[j].y, n1);
+          d1 = fmaf(c2 * c2, tt2[j].x, d1); d1 = fmaf(d * d, tt2[j].y, d1);
+        }
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+          n0 += __shfl_xor_sync(0xffffffffu, n0, o); d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+          n1 += __shfl_xor_sync(0xffffffffu, n1, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+        }
+        if (t == 0) {
+          float* r0 = scratch + ((warp * kStencilRowsPerPass) + (mt - pass) * 16 + g) * 2;
+          float* r1 = r0 + 16;
+          if (first_cb) { r0[0] = n0; r0[1] = d0; r1[0] = n1; r1[1] = d1; }
+          else { r0[0] += n0; r0[1] += d0; r1[0] += n1; r1[1] += d1; }
+        }
+      }
+      first_cb = false;
+    }
+    if (threadIdx.x == 0) N2NMN_STAMP(2, 31);
+    __syncthreads();
+    for (int r = threadIdx.x; r < (pass_end - pass) * 16; r += blockDim.x) {
+      const int p = pass * 16 + r;
+      if (p < HW) {
+        float n = 0.f, d = 0.f;
+        for (int w = 0; w < nwarps; ++w) {
+          if (w * 32 < Mp) {   // warps beyond the channel range wrote nothing
+            n += scratch[(w * kStencilRowsPerPass + r) * 2];
+            d += scratch[(w * kStencilRowsPerPass + r) * 2 + 1];
+          }
+        }
+        ob[p] = n * rsqrtf(fmaxf(d, kEps)) + b2;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 template <int KS>
 __global__ void __launch_bounds__(kNodeThreads, 2)
 tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* __restrict__ q_ptr,
-            int csize, int stack_slots, int write_arena) {
+            int csize, int stack_slots, int flags) {
+  const bool write_arena = (flags & kTreeWriteArena) != 0;
+  const bool fp32_stencil = (flags & kTreeFp32Stencil) != 0;
   extern __shared__ __align__(16) float tree_smem[];
   const DevModel& md = c.md;
   const int HW = md.HW, Mp = md.Mp, M = md.M;
@@ -146,7 +304,18 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
     bool has_transform = false;
     for (int i = beg; i < end; ++i) has_transform |= (nodes[i].op == OP_TRANSFORM);
     if (has_transform) {
-      stage_async(s.k, md.conv_k, KS * KS * Mp);
+      // the filter bank: as is for the fp32 stencil, rounded to TF32 on the way in for the tensor
+      // path (this runs under the predecessors' tail, before griddepcontrol.wait)
+      if (fp32_stencil) {
+        stage_async(s.k, md.conv_k, KS * KS * Mp);
+      } else {
+        const float4* src = reinterpret_cast<const float4*>(md.conv_k);
+        float4* dst = reinterpret_cast<float4*>(s.k);
+        for (int j = threadIdx.x; j < KS * KS * Mp / 4; j += blockDim.x) {
+          const float4 v = __ldg(src + j);
+          dst[j] = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+        }
+      }
       for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
         s_tw2[ch] = (ch < M) ? md.elt_w[ES_TRANSFORM][ch] : 0.f;
         s_tcb[ch] = (ch < M) ? md.conv_b[ch] : 0.f;
@@ -255,7 +424,7 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
         // TransformModule, conv variant (models_clevr/nmn3_modules.py:185-216, SHAPES :71-101)
         const int Hh = md.H, Ww = md.W;
         const int PW = Ww + KS - 1, PH = Hh + KS - 1, R = (KS - 1) / 2;
-        for (int j = threadIdx.x; j < PH * PW; j += blockDim.x) s.pad[j] = 0.f;
+        for (int j = threadIdx.x; j < 2 * PH * PW; j += blockDim.x) s.pad[j] = 0.f;
         for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
           s.v0[ch] = (ch < M) ? tau[ch] : 0.f;
           s.v1[ch] = s_tw2[ch];
@@ -264,13 +433,17 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
         __syncthreads();
         for (int p = threadIdx.x; p < HW; p += blockDim.x) {
           const int y = p / Ww, x = p - y * Ww;
-          s.pad[(y + R) * PW + x + R] = in0[p];
+          s.pad[(y + R) * PW + x + R] = fp32_stencil ? in0[p] : round_tf32(in0[p]);
         }
         cp_async_commit_wait_all();   // the filter bank (prologue)
         __syncthreads();
+
         if (threadIdx.x == 0) N2NMN_STAMP(2, 21);
         const float b2 = md.elt_b[ES_TRANSFORM][0];
         float* ob = s.outbuf + (exch & 1) * L.HWp;
+        if (!fp32_stencil) {
+          transform_stencil_mma<KS>(co, s.pad, s.k, s.v0, s.v1, s.v2, b2, s.scratch, ob, Hh, Ww, Mp);
+        } else {
         // Each warp owns horizontal runs of kTransformPB pixels: their stencil windows overlap, so
         // one (KS x (PB+KS-1)) window is read into registers once and every filter-bank read is
         // shared by the PB pixels (the stencil is shared-memory-bandwidth bound otherwise).
@@ -331,10 +504,16 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
             if (lane == 0 && x0 + j < Ww) ob[y * Ww + x0 + j] = n * rsqrtf(fmaxf(d, kEps)) + b2;
           }
         }
+        }
         if (threadIdx.x == 0) N2NMN_STAMP(2, 22);
         co.sync();
         if (threadIdx.x == 0) N2NMN_STAMP(2, 23);
-        gather_pixels(co, ob, out, HW, Ww, kTransformPB);
+        if (!fp32_stencil) {
+          for (int p = threadIdx.x; p < HW; p += blockDim.x)
+            out[p] = co.peer(ob, stencil_owner(p, HW, co.size))[p];
+        } else {
+          gather_pixels(co, ob, out, HW, Ww, kTransformPB);
+        }
         if (threadIdx.x == 0) N2NMN_STAMP(2, 24);
         ++exch;
         break;

@@ -230,6 +230,10 @@ class LayoutExecutor:
         """CTAs per question in the executor kernel (0 = automatic). Tuning only."""
         _lib.check(self._lib.n2nmn_set_tree_cluster(self.modules._h, int(ctas_per_question)))
 
+    def set_proj_ctas(self, max_ctas):
+        """Cap of the contraction kernel's persistent grid (0 = one CTA per SM). Tuning only."""
+        _lib.check(self._lib.n2nmn_set_proj_ctas(self.modules._h, int(max_ctas)))
+
     # -- profiling ------------------------------------------------------------------------------
     def set_profiling(self, on):
         _lib.check(self._lib.n2nmn_set_profiling(self.modules._h, int(bool(on))))
@@ -245,15 +249,21 @@ class LayoutExecutor:
 
 
 class ExecutorPool:
-    """K LayoutExecutors (one context + one CUDA stream each) fed round-robin.
+    """K LayoutExecutors (one context + one CUDA stream + one native worker thread each) fed
+    round-robin.
 
     A batch of 64 questions is a short chain of small kernels that cannot fill 148 SMs on its
     own; successive batches are independent (eval), so batch i+1's projection kernel can run
-    while batch i's tree kernel drains. Each executor owns its workspaces, so there is no
-    sharing hazard; weights are replicated (a few MB)."""
+    while batch i's tree kernel drains. The host side of a step (layout compile, table upload,
+    launches) costs about as much as its GPU side, so each context is driven by its own C++ worker
+    thread (csrc/pool.cpp): submit() only queues the batch. Each executor owns its workspaces, so
+    there is no sharing hazard; weights are replicated (a few MB).
+
+        pool.begin(); pool.submit(...) x n; pool.end()   # scores / validity valid after end()
+    """
 
     def __init__(self, family, image_feat_grid, word_vecs, num_choices, assembler, weights=None,
-                 num_streams=3, tree_cluster=None, **ctx_kwargs):
+                 num_streams=12, tree_cluster=None, proj_ctas=None, **ctx_kwargs):
         first = LayoutExecutor(family, image_feat_grid, word_vecs, num_choices, assembler,
                                weights=weights, **ctx_kwargs)
         w = first.modules.get_weights()
@@ -261,19 +271,46 @@ class ExecutorPool:
             LayoutExecutor(family, image_feat_grid, word_vecs, num_choices, assembler, weights=w,
                            **ctx_kwargs) for _ in range(num_streams - 1)]
         dev = first.modules.device
-        # several batches in flight: throughput, not the latency of one batch, is what counts, and
-        # two CTAs per question leave more SMs to the other streams' kernels (measured: DESIGN §9)
+        # Several batches in flight: throughput, not the latency of one batch, is what counts. The
+        # kernels of a batch are latency chains, so the GPU does more work per second when every
+        # batch is NARROW (one CTA per question, a contraction grid of a few dozen CTAs) and many
+        # of them overlap, than when each batch is spread over all SMs (measured: DESIGN §9).
         if tree_cluster is None:
-            tree_cluster = 2 if num_streams > 1 else 0
-        if 'N2NMN_TREE_CLUSTER' not in os.environ:
-            for ex in self.executors:
-                ex.set_tree_cluster(tree_cluster)
+            tree_cluster = 0 if num_streams == 1 else (2 if num_streams < 8 else 1)
+        if proj_ctas is None:
+            proj_ctas = 0 if num_streams < 8 else 32
+        if 'N2NMN_TREE_CLUSTER' in os.environ:
+            tree_cluster = int(os.environ['N2NMN_TREE_CLUSTER'])
+        if 'N2NMN_PROJ_CTAS' in os.environ:
+            proj_ctas = int(os.environ['N2NMN_PROJ_CTAS'])
+        self.tree_cluster, self.proj_ctas = tree_cluster, proj_ctas
+        for ex in self.executors:
+            ex.set_tree_cluster(tree_cluster)
+            ex.set_proj_ctas(proj_ctas)
         self.streams = [torch.cuda.Stream(device=dev) for _ in self.executors]
         self._i = 0
         self.device = dev
+        self._lib = first._lib
+        K = len(self.executors)
+        ctxs = (C.c_void_p * K)(*[ex.modules._h for ex in self.executors])
+        sts = (C.c_void_p * K)(*[st.cuda_stream for st in self.streams])
+        h = C.c_void_p()
+        rc = self._lib.n2nmn_pool_create(ctxs, sts, K, first._vocab_ptr, len(first.vocab_ops),
+                                         C.byref(h))
+        if rc < 0:
+            raise _lib.N2NMNError('n2nmn_pool_create failed: %s' %
+                                  (self._lib.n2nmn_pool_last_error() or b'').decode())
+        self._h = h
+        self._keep = []          # arrays the workers still write to (validity) or read from
 
     def __len__(self):
         return len(self.executors)
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h:
+            self._lib.n2nmn_pool_destroy(h)
+            self._h = None
 
     def begin(self):
         """Make the pool's streams wait for work already queued on the current stream."""
@@ -281,73 +318,69 @@ class ExecutorPool:
         for st in self.streams:
             st.wait_stream(cur)
 
+    def _submit(self, k, feat_ptr, wv_ptr, tok, scores_ptr, host_io):
+        T, N = tok.shape
+        validity = np.empty(N, np.uint8)
+        rc = self._lib.n2nmn_pool_submit(self._h, k, feat_ptr, wv_ptr, tok.ctypes.data, T, N,
+                                         scores_ptr, validity.ctypes.data, host_io)
+        if rc < 0:
+            raise _lib.N2NMNError('n2nmn_pool_submit failed: %s' %
+                                  (self._lib.n2nmn_pool_last_error() or b'').decode())
+        self._keep.append(validity)
+        return validity.view(bool)
+
+    @staticmethod
+    def _tokens(layout_tokens):
+        tok = layout_tokens
+        if tok.dtype != np.int32 or not tok.flags['C_CONTIGUOUS']:
+            tok = np.ascontiguousarray(tok, dtype=np.int32)
+        return tok
+
     def submit(self, image_feat_grid, word_vecs, layout_tokens, out=None):
-        """forward_device on the next executor/stream; returns (scores, validity, stream)."""
+        """Queue one batch (device-resident inputs) on the next executor/stream; returns
+        (scores, validity, stream). `scores` is ordered on `stream`; `validity` is filled by the
+        worker thread and valid after end()."""
         k = self._i % len(self.executors)
         self._i += 1
+        tok = self._tokens(layout_tokens)
         if out is None:   # allocate on the slot's stream so the caching allocator orders reuse
             with torch.cuda.stream(self.streams[k]):
-                out = torch.empty((layout_tokens.shape[1], self.executors[k].num_choices),
+                out = torch.empty((tok.shape[1], self.executors[k].num_choices),
                                   dtype=torch.float32, device=self.device)
-        scores, valid = self.executors[k].forward_device(image_feat_grid, word_vecs,
-                                                         layout_tokens, out=out,
-                                                         stream=self.streams[k])
-        return scores, valid, self.streams[k]
+        assert image_feat_grid.is_cuda and image_feat_grid.is_contiguous() and \
+            image_feat_grid.dtype == torch.float32 and word_vecs.is_cuda and \
+            word_vecs.is_contiguous() and word_vecs.dtype == torch.float32
+        valid = self._submit(k, image_feat_grid.data_ptr(), word_vecs.data_ptr(), tok,
+                             out.data_ptr(), 0)
+        return out, valid, self.streams[k]
 
     def submit_host(self, feat_host, word_vecs_host, layout_tokens, scores_host):
-        """End-to-end step from (pinned) HOST tensors: H2D of the batch's features and word
-        vectors, the forward pass, and D2H of the scores, all asynchronous on the slot's stream
-        (copy engines overlap the other slots' kernels). The result is valid in `scores_host`
-        after `end()` + a stream/device synchronise."""
+        """End-to-end step from pinned HOST tensors: H2D of the batch's features and word
+        vectors, the forward pass, and D2H of the scores, all enqueued by the slot's worker on
+        the slot's stream (copy engines overlap the other slots' kernels). `scores_host` and the
+        returned validity are valid after end() + a stream/device synchronise."""
         k = self._i % len(self.executors)
         self._i += 1
-        if not hasattr(self, '_dfeat'):
-            self._dfeat, self._dwv = {}, {}
-        if k not in self._dfeat or self._dfeat[k].shape != feat_host.shape or \
-                self._dwv[k].shape != word_vecs_host.shape:
-            self._dfeat[k] = torch.empty(feat_host.shape, dtype=torch.float32, device=self.device)
-            self._dwv[k] = torch.empty(word_vecs_host.shape, dtype=torch.float32,
-                                       device=self.device)
-        with torch.cuda.stream(self.streams[k]):
-            self._dfeat[k].copy_(feat_host, non_blocking=True)
-            self._dwv[k].copy_(word_vecs_host, non_blocking=True)
-            scores, valid = self.executors[k].forward_device(self._dfeat[k], self._dwv[k],
-                                                             layout_tokens)
-            scores_host.copy_(scores, non_blocking=True)
-        return valid
+        tok = self._tokens(layout_tokens)
+        for t in (feat_host, word_vecs_host, scores_host):
+            assert (not t.is_cuda) and t.is_contiguous() and t.dtype == torch.float32
+        valid = self._submit(k, feat_host.data_ptr(), word_vecs_host.data_ptr(), tok,
+                             scores_host.data_ptr(), 1)
+        return scores_host, valid, self.streams[k]
 
     def forward_many(self, feats, word_vecs, tokens, outs):
-        """Evaluate a list of independent batches: item i goes to context/stream i % K, and the K
-        contexts are driven by K host threads (the C call releases the GIL, so layout compilation
-        and kernel launches of different batches proceed in parallel on the host as well as on
-        the GPU). outs[i] is the [N,C] CUDA tensor that receives item i's scores. Returns the
-        validity arrays. Call begin() before and end() after, like submit()."""
-        import threading
-        K, n = len(self.executors), len(feats)
-        valid = [None] * n
-        errors = []
-
-        def work(k):
-            try:
-                ex, st = self.executors[k], self.streams[k]
-                for i in range(k, n, K):
-                    _, valid[i] = ex.forward_device(feats[i], word_vecs[i], tokens[i],
-                                                    out=outs[i], stream=st)
-            except Exception as e:   # surface worker failures in the caller
-                errors.append(e)
-
-        threads = [threading.Thread(target=work, args=(k,)) for k in range(1, K)]
-        for t in threads:
-            t.start()
-        work(0)
-        for t in threads:
-            t.join()
-        if errors:
-            raise errors[0]
-        return valid
+        """Queue a list of independent batches (item i -> context i % K); returns the validity
+        arrays. Call begin() before and end() after, like submit()."""
+        return [self.submit(f, w, t, out=o)[1] for f, w, t, o in zip(feats, word_vecs, tokens, outs)]
 
     def end(self):
-        """Make the current stream wait for everything submitted so far."""
+        """Wait until the workers have enqueued everything submitted so far, then make the current
+        stream wait for the pool's streams."""
+        rc = self._lib.n2nmn_pool_wait(self._h)
+        self._keep.clear()
+        if rc < 0:
+            raise _lib.N2NMNError('n2nmn_b200 error %d: %s' % (
+                rc, (self._lib.n2nmn_pool_last_error() or b'').decode()))
         cur = torch.cuda.current_stream(self.device)
         for st in self.streams:
             cur.wait_stream(st)

@@ -213,6 +213,29 @@ def test_executor_pool_threads_match_single_context():
         want, _ = ex.forward_device(f, w, tok)
         torch.cuda.synchronize()
         np.testing.assert_array_equal(got.cpu().numpy(), want.cpu().numpy())
+    # the same batches from pinned host buffers (H2D, kernels, D2H all enqueued by the workers),
+    # one of them with an invalid layout: validity comes back through the worker as well
+    toks = [x[2].copy() for x in items]
+    toks[3][:, 5] = asm.name2idx_dict['_Find']          # Find Find Find ... never terminates
+    hf = [x[0].cpu().pin_memory() for x in items]
+    hw = [x[1].cpu().pin_memory() for x in items]
+    hs = [torch.empty((N, C)).pin_memory() for _ in items]
+    pool.begin()
+    valids = [pool.submit_host(f, w, t, o)[1] for f, w, t, o in zip(hf, hw, toks, hs)]
+    pool.end()
+    torch.cuda.synchronize()
+    for (f, w, _), tok, got, valid in zip(items, toks, hs, valids):
+        want, v = ex.forward_device(f, w, tok)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(got.numpy(), want.cpu().numpy())
+        assert valid.tolist() == v.tolist()
+    assert not valids[3][5] and valids[3][4]
+    # errors raised inside a worker surface at end()
+    import pytest as _pt
+    pool.begin()
+    pool.submit(items[0][0], items[0][1], np.zeros((T + 50, N), np.int32))   # T beyond capacity
+    with _pt.raises(Exception):
+        pool.end()
 
 
 def test_host_e2e_entry_matches_device_path():

@@ -83,6 +83,7 @@ def phases(name, slots):
     if rows_:
         print(name, 'n=%d' % len(rows_), 'median cycles per phase', np.median(np.array(rows_), axis=0))
 phases('transform [stage->ready, compute, cluster sync, gather]', [20, 21, 22, 23, 24])
+phases('stencil   [bank frags, (stamp), m-tile 0, m-tile 1, m-tile 2, sync+reduce]', [21, 25, 17, 18, 19, 31, 22])
 phases('pooled    [copy+softmax, rowsum, cluster sync, partial-sum+normalize(rank0)]', [26, 27, 28, 29, 30])
 rows_ = []
 for cta in range(148):
