@@ -38,7 +38,7 @@ UNIT = 'questions/s'
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=4000)
+    ap.add_argument('--steps', type=int, default=20000)
     ap.add_argument('--warmup', type=int, default=50)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=64, help='questions per GPU per step')
