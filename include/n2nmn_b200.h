@@ -266,6 +266,11 @@ int n2nmn_set_tree_cluster(n2nmn_ctx* ctx, int ctas_per_question);
  * identical. */
 int n2nmn_set_proj_ctas(n2nmn_ctx* ctx, int max_ctas);
 
+/* CTAs per group of 8 text nodes in the text-projection kernel: each CTA then walks
+ * ceil((Mp/64) / n) blocks of 64 output columns. 0 (the default) = one CTA per column block
+ * (shortest kernel); 1 = one CTA per group (least SM-time). Tuning only: results are identical. */
+int n2nmn_set_text_ctas_per_group(n2nmn_ctx* ctx, int n);
+
 /* Per-launch device time of the last n2nmn_run_schedule in microseconds (CUDA events recorded
  * around every launch when enabled). names/us arrays of length >= capacity. */
 int n2nmn_set_profiling(n2nmn_ctx* ctx, int enabled);

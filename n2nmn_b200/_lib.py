@@ -78,6 +78,7 @@ SIGNATURES = {
                                   C.c_float, C.c_float, C.c_float, _P]),
     'n2nmn_set_tree_cluster': (C.c_int, [_P, C.c_int]),
     'n2nmn_set_proj_ctas': (C.c_int, [_P, C.c_int]),
+    'n2nmn_set_text_ctas_per_group': (C.c_int, [_P, C.c_int]),
     'n2nmn_set_profiling': (C.c_int, [_P, C.c_int]),
     'n2nmn_get_launch_times': (C.c_int, [_P, C.POINTER(C.c_char_p), C.POINTER(C.c_float),
                                          C.c_int]),

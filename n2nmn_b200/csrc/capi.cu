@@ -119,6 +119,7 @@ struct n2nmn_ctx {
   int stack_cap = 0;           // attention-stack slots the tree kernel may use
   int tree_cluster = 0;        // 0 = choose from the batch size; else forced (N2NMN_TREE_CLUSTER)
   bool fp32_stencil = false;   // N2NMN_FP32_STENCIL=1: CUDA-core Transform stencil (A/B timing)
+  int text_ctas_per_group = 0; // 0 = one CTA per 64-column block
   int proj_max_ctas = 0;       // 0 = one CTA per SM; else cap of the persistent projection grid
   bool use_pdl = true;         // programmatic dependent launch between the three kernels
   n2nmn_sched module_sched;    // scratch schedule of n2nmn_module_fwd
@@ -337,7 +338,9 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaS
   prof_mark(c, "begin", st);
   // ---- K1 text projections
   if (!S.groups.empty()) {
-    dim3 grid(c->Mp / kTextCols, (unsigned)S.groups.size());
+    const int n_cblk = c->Mp / kTextCols;
+    dim3 grid(c->text_ctas_per_group > 0 ? std::min(c->text_ctas_per_group, n_cblk) : n_cblk,
+              (unsigned)S.groups.size());
     const size_t smem = (size_t)(kTextRowsPerCta * c->cfg.text_dim +
                                  8 * kTextRowsPerCta * kTextCols) * sizeof(float);
     TextSetRows tsr;
@@ -618,6 +621,7 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
   c->step_sched.shp = c->shp;
   if (const char* e = std::getenv("N2NMN_NO_PDL")) c->use_pdl = (std::atoi(e) == 0);
   if (const char* e = std::getenv("N2NMN_FP32_STENCIL")) c->fp32_stencil = (std::atoi(e) != 0);
+  if (const char* e = std::getenv("N2NMN_TEXT_CTAS")) c->text_ctas_per_group = std::max(0, std::atoi(e));
   if (const char* e = std::getenv("N2NMN_PROJ_CTAS")) c->proj_max_ctas = std::max(0, std::atoi(e));
   if (const char* e = std::getenv("N2NMN_TREE_CLUSTER")) {
     const int v = std::atoi(e);
@@ -1177,6 +1181,13 @@ int n2nmn_set_proj_ctas(n2nmn_ctx* c, int max_ctas) {
   if (!c) return fail(N2NMN_ERR_ARG, "n2nmn_set_proj_ctas: null context");
   if (max_ctas < 0) return fail(N2NMN_ERR_ARG, "n2nmn_set_proj_ctas: max_ctas must be >= 0");
   c->proj_max_ctas = max_ctas;
+  return 0;
+}
+
+int n2nmn_set_text_ctas_per_group(n2nmn_ctx* c, int n) {
+  if (!c) return fail(N2NMN_ERR_ARG, "n2nmn_set_text_ctas_per_group: null context");
+  if (n < 0) return fail(N2NMN_ERR_ARG, "n2nmn_set_text_ctas_per_group: n must be >= 0");
+  c->text_ctas_per_group = n;
   return 0;
 }
 

@@ -165,7 +165,7 @@ __device__ __forceinline__ void gemv_partial(const float* in, int k0, int k1,
   if (sl < slices) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4* w = reinterpret_cast<const float4*>(W) + q;
-#pragma unroll 5
+#pragma unroll 8
     for (int k = k0 + sl; k < k1; k += slices) {
       const float4 wv = __ldg(w + (size_t)k * quads);
       const float x = in[k - k0];

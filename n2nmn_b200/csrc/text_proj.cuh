@@ -4,7 +4,10 @@
 //  util/cnn.py:116). The gather of _slice_word_vecs (nmn3_modules.py:53-57) is folded into the
 // load: row (t*N + b) of the time-major word_vecs.
 //
-// One CTA = up to 8 nodes of ONE weight set x 64 output columns. The 256 threads form a
+// One CTA = up to 8 nodes of ONE weight set x the 64-column blocks blockIdx.x, blockIdx.x +
+// gridDim.x, ... (gridDim.x = Mp/64: one block per CTA, shortest kernel; gridDim.x = 1: one CTA
+// per node group walks all column blocks and gathers its word vectors once — fewer, longer CTAs,
+// less SM-time, used when many batches are in flight). The 256 threads form a
 // 16 (column quads) x 16 (K slices) grid: every thread streams ~Dt/16 float4 weight rows with all
 // loads independent (the kernel is latency-bound, so memory-level parallelism is what matters),
 // keeps 8x4 accumulators, and the 16 K slices are reduced through shared memory.
@@ -36,7 +39,9 @@ text_proj_kernel(DevModel md, TextBufs tb, TextSetRows rows,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tx = lane & 15;                    // column quad inside the CTA's 64 columns
   const int ky = warp * 2 + (lane >> 4);       // K slice 0..15
-  const int c0 = blockIdx.x * kTextCols + tx * 4;
+  const int n_cblk = Mp / kTextCols;
+  int cblk = blockIdx.x;
+  int c0 = cblk * kTextCols + tx * 4;
   TextGroup g;   // blockIdx.y-th group of <= 8 rows, groups never straddle weight sets
   {
     int gi = blockIdx.y, set = 0;
@@ -50,6 +55,8 @@ text_proj_kernel(DevModel md, TextBufs tb, TextSetRows rows,
     g.count = min(kTextRowsPerCta, rows.start[set + 1] - g.start);
   }
   const float* __restrict__ wbase = md.txt_w[g.set] + c0;
+  const int es = (g.set == TS_FIND) ? ES_FIND : (g.set == TS_FSP) ? ES_FSP
+               : (g.set == TS_TRANSFORM) ? ES_TRANSFORM : -1;
 
   // (1) this thread's weight rows of the first chunk: independent of everything else, so the
   //     loads fly while the word vectors are being gathered
@@ -90,16 +97,19 @@ text_proj_kernel(DevModel md, TextBufs tb, TextSetRows rows,
   }
   __syncthreads();
   if (threadIdx.x == 0) N2NMN_STAMP(0, 3);
+  for (; cblk < n_cblk; cblk += gridDim.x) {
+  c0 = cblk * kTextCols + tx * 4;
+  const float* __restrict__ wb = md.txt_w[g.set] + c0;
   // (4) 8 x 4 accumulators per thread
   float4 acc[kTextRowsPerCta];
 #pragma unroll
   for (int r = 0; r < kTextRowsPerCta; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int kb = 0; kb < Dt; kb += 16 * kTextKIter) {
-    if (kb > 0) {   // further chunks only when text_dim > 320
+    if (kb > 0 || cblk != (int)blockIdx.x) {   // chunk / column block not prefetched above
 #pragma unroll
       for (int j = 0; j < kTextKIter; ++j) {
         const int k = kb + ky + 16 * j;
-        w[j] = (k < Dt) ? __ldg(reinterpret_cast<const float4*>(wbase + (size_t)k * Mp))
+        w[j] = (k < Dt) ? __ldg(reinterpret_cast<const float4*>(wb + (size_t)k * Mp))
                         : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
@@ -129,12 +139,10 @@ text_proj_kernel(DevModel md, TextBufs tb, TextSetRows rows,
           acc[r];
   }
   __syncthreads();
-  const int es = (g.set == TS_FIND) ? ES_FIND : (g.set == TS_FSP) ? ES_FSP
-               : (g.set == TS_TRANSFORM) ? ES_TRANSFORM : -1;
   for (int o = threadIdx.x; o < kTextRowsPerCta * kTextCols; o += blockDim.x) {
     const int r = o / kTextCols, cc = o - r * kTextCols;
     if (r >= g.count) continue;
-    const int c = blockIdx.x * kTextCols + cc;
+    const int c = cblk * kTextCols + cc;
     float v = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) v += s_red[(w * kTextRowsPerCta + r) * kTextCols + cc];
@@ -145,6 +153,8 @@ text_proj_kernel(DevModel md, TextBufs tb, TextSetRows rows,
     tb.tau[idx] = v;
     tb.tauw[idx] = v * w2;
     tb.tau2[idx] = v * v;
+  }
+  __syncthreads();   // s_red is reused by the next column block
   }
   if (threadIdx.x == 0) N2NMN_STAMP(0, 5);
 }

@@ -542,21 +542,36 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
         const float b2 = md.elt_b[ES_FSP][0];
         const float* mimg = c.mbuf + (size_t)nd.aux * HW * Mp;
         float* ob = s.outbuf + (exch & 1) * L.HWp;
-        for (int p = gwarp; p < HW; p += gwarps) {
-          const float4* mrow = reinterpret_cast<const float4*>(mimg + (size_t)p * Mp);
-          float num = 0.f, den = 0.f;
+        // four pixels per step: their map rows are independent L2 reads, issued together (one pixel
+        // at a time the warp pays an L2 round trip per pixel: ~19 of them with one CTA per question)
+        constexpr int PX = 4;
+        for (int pb = gwarp; pb < HW; pb += gwarps * PX) {
+          float num[PX], den[PX];
+#pragma unroll
+          for (int u = 0; u < PX; ++u) { num[u] = 0.f; den[u] = 0.f; }
           for (int qd = lane; qd < (Mp >> 2); qd += 32) {
-            const float4 m = __ldg(mrow + qd);
+            float4 m[PX];
+#pragma unroll
+            for (int u = 0; u < PX; ++u) {
+              const int p = min(pb + u * gwarps, HW - 1);
+              m[u] = __ldg(reinterpret_cast<const float4*>(mimg + (size_t)p * Mp) + qd);
+            }
             const float4 a = reinterpret_cast<const float4*>(s.v1)[qd];
             const float4 d = reinterpret_cast<const float4*>(s.v2)[qd];
-            num = fmaf(m.x, a.x, num); num = fmaf(m.y, a.y, num);
-            num = fmaf(m.z, a.z, num); num = fmaf(m.w, a.w, num);
-            den = fmaf(m.x * m.x, d.x, den); den = fmaf(m.y * m.y, d.y, den);
-            den = fmaf(m.z * m.z, d.z, den); den = fmaf(m.w * m.w, d.w, den);
+#pragma unroll
+            for (int u = 0; u < PX; ++u) {
+              num[u] = fmaf(m[u].x, a.x, num[u]); num[u] = fmaf(m[u].y, a.y, num[u]);
+              num[u] = fmaf(m[u].z, a.z, num[u]); num[u] = fmaf(m[u].w, a.w, num[u]);
+              den[u] = fmaf(m[u].x * m[u].x, d.x, den[u]); den[u] = fmaf(m[u].y * m[u].y, d.y, den[u]);
+              den[u] = fmaf(m[u].z * m[u].z, d.z, den[u]); den[u] = fmaf(m[u].w * m[u].w, d.w, den[u]);
+            }
           }
-          num = warp_sum(num);
-          den = warp_sum(den);
-          if (lane == 0) ob[p] = num * rsqrtf(fmaxf(den, kEps)) + b2;
+#pragma unroll
+          for (int u = 0; u < PX; ++u) {
+            const float n = warp_sum(num[u]), dd = warp_sum(den[u]);
+            const int p = pb + u * gwarps;
+            if (lane == 0 && p < HW) ob[p] = n * rsqrtf(fmaxf(dd, kEps)) + b2;
+          }
         }
         co.sync();
         gather_pixels(co, ob, out, HW, md.W, 1);

@@ -234,6 +234,10 @@ class LayoutExecutor:
         """Cap of the contraction kernel's persistent grid (0 = one CTA per SM). Tuning only."""
         _lib.check(self._lib.n2nmn_set_proj_ctas(self.modules._h, int(max_ctas)))
 
+    def set_text_ctas_per_group(self, n):
+        """CTAs per group of 8 text nodes in the text kernel (0 = one per column block)."""
+        _lib.check(self._lib.n2nmn_set_text_ctas_per_group(self.modules._h, int(n)))
+
     # -- profiling ------------------------------------------------------------------------------
     def set_profiling(self, on):
         _lib.check(self._lib.n2nmn_set_profiling(self.modules._h, int(bool(on))))
@@ -279,14 +283,19 @@ class ExecutorPool:
             tree_cluster = 0 if num_streams == 1 else (2 if num_streams < 8 else 1)
         if proj_ctas is None:
             proj_ctas = 0 if num_streams < 8 else 32
+        text_ctas = 0 if num_streams < 8 else 1
         if 'N2NMN_TREE_CLUSTER' in os.environ:
             tree_cluster = int(os.environ['N2NMN_TREE_CLUSTER'])
         if 'N2NMN_PROJ_CTAS' in os.environ:
             proj_ctas = int(os.environ['N2NMN_PROJ_CTAS'])
         self.tree_cluster, self.proj_ctas = tree_cluster, proj_ctas
+        if 'N2NMN_TEXT_CTAS' in os.environ:
+            text_ctas = int(os.environ['N2NMN_TEXT_CTAS'])
+        self.text_ctas_per_group = text_ctas
         for ex in self.executors:
             ex.set_tree_cluster(tree_cluster)
             ex.set_proj_ctas(proj_ctas)
+            ex.set_text_ctas_per_group(text_ctas)
         self.streams = [torch.cuda.Stream(device=dev) for _ in self.executors]
         self._i = 0
         self.device = dev

@@ -8,6 +8,7 @@ from n2nmn_b200 import _lib, synth, weights as wts
 from n2nmn_b200.assembler import Assembler
 from n2nmn_b200.executor import LayoutExecutor
 
+CS = int(os.environ.get("N2NMN_TREE_CLUSTER", 4))   # CTAs per question (rank 0 = CTA CS*q)
 B, H, W, D, T, Cc = 64, 10, 15, 512, 20, 28
 asm = Assembler(synth.vocab_file('clevr'))
 toks = synth.expert_mix_tokens(asm, B, T)
@@ -42,7 +43,7 @@ qptr = np.cumsum(qptr)
 # tree kernel: per-op node durations on rank 0 of each cluster (cluster size 4 -> CTA 4*q)
 per_op = {}
 for q in range(B):
-    cta = 4 * q
+    cta = CS * q
     if clk[2, cta, 0] == 0:
         continue
     prev = clk[2, cta, 3]
@@ -76,7 +77,7 @@ for k in range(3):
 def phases(name, slots):
     rows_ = []
     for q in range(B):
-        cta = 4 * q
+        cta = CS * q
         v_ = [clk[2, cta, s_] for s_ in slots]
         if all(x > 0 for x in v_):
             rows_.append(np.diff(v_))
