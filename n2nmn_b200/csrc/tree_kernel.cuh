@@ -185,6 +185,7 @@ __device__ __forceinline__ void transform_stencil_mma(const Coop& co, const floa
         tt2[j] = make_float2(tv.x * tv.x, tv.y * tv.y);
       }
       if (threadIdx.x == 0) N2NMN_STAMP(2, 25);
+#pragma unroll 1   // (two row tiles in flight were measured slower: registers)
       for (int mt = pass; mt < pass_end; ++mt) {
         if (threadIdx.x == 0 && mt - pass < 3) N2NMN_STAMP(2, 17 + (mt - pass));
         const int p0 = mt * 16 + g, p1 = p0 + 8;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Kernel-only timing of the projection kernel (per-launch CUDA events) on a Find-only batch.
-Used with N2NMN_LIB=<experiment build> to attribute its time (tools/gpu_exp.sh)."""
+Used with N2NMN_LIB=<experiment build> to attribute its time (tools/build_variants.py + tools/gpu_epilogue_attrib.sh)."""
 import os, sys
 import numpy as np
 import torch
