@@ -3,7 +3,8 @@
 // w.r.t. word_vecs, following TF 1.0's registered gradients (ties of tf.minimum/maximum go to
 // input_0; reduce_min/max split ties equally; l2_normalize takes the constant branch below eps).
 //
-// Structure (correctness-first; only the feature-side weight gradients are heavy):
+// Structure (the forward got the tuning; here only the measured hot spots were restructured — see
+// the notes at the Find pixel loop, the stencil's butterfly and feat_grad_kernel):
 //   loss_kernel      : softmax cross-entropy, validity select, d(loss)/d(scores)
 //   tree_bwd_kernel  : one CTA per question walks its nodes in REVERSE Reverse-Polish order with
 //                      the gradient maps in shared memory; recomputes each module's forward
@@ -43,6 +44,7 @@ struct BwdCtx {
   float* gflat;           // flat gradient buffer (zero-initialised)
   float* dtau;            // [text rows][Mp]
   float* dmap;            // [entries][HW][Mp]
+  float* dstencil;        // [NQ][HW][Mp] scratch: d(conv_maps output) of the Transform being walked
   GradOffsets go;
   int max_nodes_q;        // capacity of the per-question gradient stack in shared memory
 };
@@ -242,6 +244,7 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
         for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
           float p0 = 0.f, p1 = 0.f;
           if (ch < M) {
+#pragma unroll 8
             for (int p = 0; p < HW; ++p) {
               p0 = fmaf(a0[p], G0[(size_t)p * Mp + ch], p0);
               if (two) p1 = fmaf(a1[p], G1[(size_t)p * Mp + ch], p1);
@@ -336,7 +339,10 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
           const float* G = c.mbuf + (size_t)nd.aux2 * HW * Mp;
           for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
             float p0 = 0.f;
-            if (ch < M) for (int p = 0; p < HW; ++p) p0 = fmaf(a0[p], G[(size_t)p * Mp + ch], p0);
+            if (ch < M) {
+#pragma unroll 8
+              for (int p = 0; p < HW; ++p) p0 = fmaf(a0[p], G[(size_t)p * Mp + ch], p0);
+            }
             phi[ch] = p0;
             coef[ch] = (ch < M) ? tau[ch] * p0 : 0.f;
           }
@@ -345,35 +351,67 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
           for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) coef[ch] = (ch < M) ? tau[ch] : 0.f;
           mimg = c.mbuf + (size_t)nd.aux * HW * Mp;   // training schedules store the Find maps too
         }
-        for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) { dcoef[ch] = 0.f; dw2[ch] = 0.f; }
+        float* w2s = v + 5 * Mp;   // conv_eltwise weights of this layer, zero beyond M
+        for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
+          dcoef[ch] = 0.f; dw2[ch] = 0.f;
+          w2s[ch] = (ch < M) ? w2[ch] : 0.f;
+        }
         __syncthreads();
         const int ent = node_entry[i];
         float* B = c.dmap + (size_t)ent * HW * Mp;       // dm rows
         float db2 = 0.f;
+        // lane owns channels lane + 32k: the map row is read once into registers, and the
+        // per-channel sums over this warp's pixels stay in registers until the end (they used to
+        // be one shared-memory atomic per (pixel, channel) with all 8 warps on the same addresses)
+        constexpr int kCh = 16;                 // Mp <= 512 on the training path
+        const int nk = Mp >> 5;
+        float dcoef_r[kCh], dw2_r[kCh];
+#pragma unroll
+        for (int k = 0; k < kCh; ++k) { dcoef_r[k] = 0.f; dw2_r[k] = 0.f; }
         for (int p = warp; p < HW; p += nwarps) {
           const float gp = gm[p];
           const float* mrow = mimg + (size_t)p * Mp;
+          float mv[kCh];
+          // all loads of the row first (columns beyond M are exact zeros in the stored map), then
+          // the math: interleaved, every chunk waited for its own L2 round trip
+#pragma unroll
+          for (int k = 0; k < kCh; ++k) mv[k] = (k < nk) ? __ldg(mrow + k * 32 + lane) : 0.f;
           float ss = 0.f, num = 0.f;
-          for (int ch = lane; ch < M; ch += 32) {
-            const float ev = mrow[ch] * coef[ch];
-            ss = fmaf(ev, ev, ss);
-            num = fmaf(ev, w2[ch], num);
+#pragma unroll
+          for (int k = 0; k < kCh; ++k) {
+            if (k < nk) {
+              const int ch = k * 32 + lane;
+              const float ev = mv[k] * coef[ch];
+              ss = fmaf(ev, ev, ss);
+              num = fmaf(ev, w2s[ch], num);
+            }
           }
           ss = warp_sum(ss); num = warp_sum(num);
           const float inv = rsqrtf(fmaxf(ss, kEps));
           const float proj = (ss > kEps) ? num * inv : 0.f;   // ê·w2
-          for (int ch = lane; ch < Mp; ch += 32) {
-            float dm = 0.f;
-            if (ch < M) {
-              const float mv = mrow[ch], eh = mv * coef[ch] * inv;
-              const float dev = gp * (w2[ch] - eh * proj) * inv;
-              dm = dev * coef[ch];
-              atomicAdd(&dcoef[ch], dev * mv);
-              atomicAdd(&dw2[ch], gp * eh);
+#pragma unroll
+          for (int k = 0; k < kCh; ++k) {
+            if (k < nk) {
+              const int ch = k * 32 + lane;
+              float dm = 0.f;
+              if (ch < M) {
+                const float eh = mv[k] * coef[ch] * inv;
+                const float dev = gp * (w2s[ch] - eh * proj) * inv;
+                dm = dev * coef[ch];
+                dcoef_r[k] = fmaf(dev, mv[k], dcoef_r[k]);
+                dw2_r[k] = fmaf(gp, eh, dw2_r[k]);
+              }
+              B[(size_t)p * Mp + ch] = dm;
             }
-            B[(size_t)p * Mp + ch] = dm;
           }
           if (lane == 0) db2 += gp;
+        }
+#pragma unroll
+        for (int k = 0; k < kCh; ++k) {
+          if (k < nk) {
+            atomicAdd(&dcoef[k * 32 + lane], dcoef_r[k]);
+            atomicAdd(&dw2[k * 32 + lane], dw2_r[k]);
+          }
         }
         if (lane == 0) atomicAdd(c.gflat + c.go.elt_b[es], db2);
         __syncthreads();
@@ -414,7 +452,7 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
         float* dw2v = v + 4 * Mp; float* dbkv = v + 5 * Mp;
         const float* tau = c.tb.tau + (size_t)nd.text * Mp;
         for (int j = threadIdx.x; j < PH * PW; j += blockDim.x) { pad[j] = 0.f; dpad[j] = 0.f; }
-        for (int j = threadIdx.x; j < KS * KS * Mp; j += blockDim.x) { ks[j] = md.conv_k[j]; dks[j] = 0.f; }
+        for (int j = threadIdx.x; j < KS * KS * Mp; j += blockDim.x) ks[j] = md.conv_k[j];
         for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
           const bool live = ch < M;
           tauv[ch] = live ? tau[ch] : 0.f;
@@ -431,6 +469,10 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
         float db2 = 0.f;
         constexpr int kMaxCh = 16;   // conv Transform exists for Mp <= 512 (CLEVR 256, SHAPES 512)
         const int nj = Mp >> 5;
+        float* dA_all = c.dstencil + (size_t)q * HW * Mp;
+        float dtau_r[kMaxCh], dw2_r[kMaxCh], dbk_r[kMaxCh];
+#pragma unroll
+        for (int j = 0; j < kMaxCh; ++j) { dtau_r[j] = 0.f; dw2_r[j] = 0.f; dbk_r[j] = 0.f; }
         for (int p = warp; p < HW; p += nwarps) {
           const int y = p / Ww, x = p - y * Ww;
           const float gp = g[p];
@@ -461,29 +503,68 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
               const float eh = A[j] * tauv[ch] * inv;
               const float dev = gp * (w2v[ch] - eh * proj) * inv;
               const float dA = dev * tauv[ch];
-              atomicAdd(&dtauv[ch], dev * A[j]);
-              atomicAdd(&dw2v[ch], gp * eh);
-              atomicAdd(&dbkv[ch], dA);
-              A[j] = dA;   // keep dA for the filter / input gradients below
+              dtau_r[j] = fmaf(dev, A[j], dtau_r[j]);
+              dw2_r[j] = fmaf(gp, eh, dw2_r[j]);
+              dbk_r[j] += dA;
+              A[j] = dA;   // keep dA for the input gradient below
+              dA_all[(size_t)p * Mp + ch] = dA;   // and for the filter gradient (second pass)
             }
           }
-          for (int dy = 0; dy < KS; ++dy)
-            for (int dx = 0; dx < KS; ++dx) {
-              const int off = (y + dy) * PW + x + dx, tap = dy * KS + dx;
-              const float av = pad[off];
-              float contrib = 0.f;
+          // d(input)[p + tap] += Σ_ch K[tap, ch]·dA[ch]: per-lane partial sums of all KS² taps, then
+          // ONE butterfly that leaves the total of tap L on lane L (31 shuffles with full ILP; a
+          // warp_sum per tap was 5 dependent shuffle+add pairs x KS² and dominated the kernel)
+          float cv[32];
 #pragma unroll
-              for (int j = 0; j < kMaxCh; ++j) {
-                if (j < nj) {
-                  const int ch = j * 32 + lane;
-                  atomicAdd(&dks[tap * Mp + ch], av * A[j]);
-                  contrib = fmaf(ks[tap * Mp + ch], A[j], contrib);
-                }
-              }
-              contrib = warp_sum(contrib);
-              if (lane == 0) atomicAdd(&dpad[off], contrib);
+          for (int t = 0; t < 32; ++t) {
+            cv[t] = 0.f;
+            if (t < KS * KS) {
+#pragma unroll
+              for (int j = 0; j < kMaxCh; ++j)
+                if (j < nj) cv[t] = fmaf(ks[t * Mp + j * 32 + lane], A[j], cv[t]);
             }
+          }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i2 = 0; i2 < off; ++i2) {
+              const float send = up ? cv[i2] : cv[i2 + off];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+              cv[i2] = (up ? cv[i2 + off] : cv[i2]) + recv;
+            }
+          }
+          if (lane < KS * KS)
+            atomicAdd(&dpad[(y + lane / KS) * PW + x + lane % KS], cv[0]);
           if (lane == 0) db2 += gp;
+        }
+#pragma unroll
+        for (int j = 0; j < kMaxCh; ++j) {
+          if (j < nj) {
+            atomicAdd(&dtauv[j * 32 + lane], dtau_r[j]);
+            atomicAdd(&dw2v[j * 32 + lane], dw2_r[j]);
+            atomicAdd(&dbkv[j * 32 + lane], dbk_r[j]);
+          }
+        }
+        __syncthreads();   // dA_all (global, written by this CTA) is complete
+        // d(conv_maps weights)[tap, ch] = Σ_p window(p)[tap]·dA[p, ch]: one thread per channel with
+        // the KS² taps in registers (this was one shared-memory atomic per (pixel, tap, channel))
+        for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
+          float acc[KS * KS];
+#pragma unroll
+          for (int t = 0; t < KS * KS; ++t) acc[t] = 0.f;
+          int y = 0, x = 0;
+#pragma unroll 2
+          for (int p = 0; p < HW; ++p, ++x) {
+            if (x == Ww) { x = 0; ++y; }
+            const float d = dA_all[(size_t)p * Mp + ch];
+#pragma unroll
+            for (int dy = 0; dy < KS; ++dy)
+#pragma unroll
+              for (int dx = 0; dx < KS; ++dx)
+                acc[dy * KS + dx] = fmaf(pad[(y + dy) * PW + x + dx], d, acc[dy * KS + dx]);
+          }
+#pragma unroll
+          for (int t = 0; t < KS * KS; ++t) dks[t * Mp + ch] = acc[t];
         }
         if (lane == 0) atomicAdd(c.gflat + c.go.elt_b[ES_TRANSFORM], db2);
         __syncthreads();
@@ -574,8 +655,8 @@ constexpr int kFgTile = 64, kFgRows = 32;
 __global__ void __launch_bounds__(256)
 feat_grad_kernel(DevModel md, const float* __restrict__ dmap, const BwdEntry* __restrict__ entries,
                  int num_entries, int entries_per_cta, float* __restrict__ gflat, GradOffsets go) {
-  __shared__ float xs[kFgRows][kFgTile + 1];
-  __shared__ float bs[kFgRows][kFgTile + 1];
+  __shared__ __align__(16) float xs[kFgRows][kFgTile];
+  __shared__ __align__(16) float bs[kFgRows][kFgTile];
   const int k0 = blockIdx.x * kFgTile, c0 = blockIdx.y * kFgTile;
   const int e0 = blockIdx.z * entries_per_cta, e1 = min(num_entries, e0 + entries_per_cta);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, 4x4 outputs each
@@ -596,37 +677,57 @@ feat_grad_kernel(DevModel md, const float* __restrict__ dmap, const BwdEntry* __
         if (ch < M && bsum[j] != 0.f) atomicAdd(gflat + go.proj_b[set] + ch, bsum[j]);
       }
   };
-  for (int e = e0; e < e1; ++e) {
-    const BwdEntry en = entries[e];
-    if (en.set != cur_set) {
-      flush(cur_set);
-      cur_set = en.set;
-      for (int i = 0; i < 4; ++i) { bsum[i] = 0.f; for (int j = 0; j < 4; ++j) acc[i][j] = 0.f; }
-    }
-    const float* X = md.feat + (size_t)en.b * HW * md.feat_pitch;
+  // The (entry, 32-row chunk) pairs form one sequence of steps; the global loads of step s+1 are
+  // issued into registers before the FMAs of step s (the kernel was a load -> barrier -> compute ->
+  // barrier chain that exposed the DRAM latency of every chunk).
+  constexpr int kPer = kFgRows * kFgTile / 256;   // 8 elements of each operand per thread
+  const int chunks_per_entry = (HW + kFgRows - 1) / kFgRows;
+  const int n_steps = (e1 - e0) * chunks_per_entry;
+  float xr[kPer], br[kPer];
+  auto fetch = [&](int step) {
+    const int e = e0 + step / chunks_per_entry, p0 = (step % chunks_per_entry) * kFgRows;
+    const float* X = md.feat + (size_t)entries[e].b * HW * md.feat_pitch;
     const float* B = dmap + (size_t)e * HW * Mp;
-    for (int p0 = 0; p0 < HW; p0 += kFgRows) {
-      __syncthreads();
-      for (int idx = threadIdx.x; idx < kFgRows * kFgTile; idx += blockDim.x) {
-        const int r = idx / kFgTile, cc = idx - r * kFgTile;
-        const int p = p0 + r;
-        xs[r][cc] = (p < HW && k0 + cc < Dk) ? X[(size_t)p * md.feat_pitch + k0 + cc] : 0.f;
-        bs[r][cc] = (p < HW && c0 + cc < Mp) ? B[(size_t)p * Mp + c0 + cc] : 0.f;
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const int idx = threadIdx.x + u * 256;
+      const int r = idx / kFgTile, cc = idx - r * kFgTile, p = p0 + r;
+      xr[u] = (p < HW && k0 + cc < Dk) ? X[(size_t)p * md.feat_pitch + k0 + cc] : 0.f;
+      br[u] = (p < HW && c0 + cc < Mp) ? B[(size_t)p * Mp + c0 + cc] : 0.f;
+    }
+  };
+  if (n_steps > 0) fetch(0);
+  for (int step = 0; step < n_steps; ++step) {
+    const int e = e0 + step / chunks_per_entry;
+    if (step % chunks_per_entry == 0) {
+      const int set = entries[e].set;
+      if (set != cur_set) {
+        flush(cur_set);
+        cur_set = set;
+        for (int i = 0; i < 4; ++i) { bsum[i] = 0.f; for (int j = 0; j < 4; ++j) acc[i][j] = 0.f; }
       }
-      __syncthreads();
-#pragma unroll 4
-      for (int r = 0; r < kFgRows; ++r) {
-        float xv[4], bv[4];
+    }
+    __syncthreads();   // the previous step's readers are done with xs / bs
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { xv[i] = xs[r][ty * 4 + i]; bv[i] = bs[r][tx * 4 + i]; }
+    for (int u = 0; u < kPer; ++u) {
+      const int idx = threadIdx.x + u * 256;
+      (&xs[0][0])[idx] = xr[u];
+      (&bs[0][0])[idx] = br[u];
+    }
+    __syncthreads();
+    if (step + 1 < n_steps) fetch(step + 1);
+#pragma unroll 8
+    for (int r = 0; r < kFgRows; ++r) {
+      const float4 x4 = *reinterpret_cast<const float4*>(&xs[r][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&bs[r][tx * 4]);
+      const float xv[4] = {x4.x, x4.y, x4.z, x4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], bv[j], acc[i][j]);
-        if (ty == 0)
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], bv[j], acc[i][j]);
+      if (ty == 0)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) bsum[j] += bv[j];
-      }
+        for (int j = 0; j < 4; ++j) bsum[j] += bv[j];
     }
   }
   flush(cur_set);

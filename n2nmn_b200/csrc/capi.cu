@@ -132,6 +132,7 @@ struct n2nmn_ctx {
   float* per_sample = nullptr;
   float* dtau = nullptr;
   float* dmap = nullptr;
+  float* dstencil = nullptr;   // [max_batch][HW][Mp] scratch of the Transform backward
   int dmap_entries = 0;
   VarSeg* d_segs = nullptr;
   float* d_sumsq = nullptr;
@@ -638,7 +639,7 @@ int n2nmn_destroy(n2nmn_ctx* c) {
   cudaFree(c->wbuf);
   for (int s = 0; s < NUM_PROJ_SETS; ++s) { cudaFree(c->proj_wt[s]); cudaFree(c->proj_bias[s]); }
   cudaFree(c->feat_aug); cudaFree(c->tb.tau); cudaFree(c->arena); cudaFree(c->mbuf);
-  cudaFree(c->dscores); cudaFree(c->per_sample); cudaFree(c->dtau); cudaFree(c->dmap);
+  cudaFree(c->dscores); cudaFree(c->per_sample); cudaFree(c->dtau); cudaFree(c->dmap); cudaFree(c->dstencil);
   cudaFree(c->d_segs); cudaFree(c->d_sumsq);
   cudaFree(c->scores_tmp); cudaFree(c->e2e_feat); cudaFree(c->e2e_wv); cudaFree(c->e2e_scores);
   for (int i = 0; i < kTableSlots; ++i) {
@@ -1051,6 +1052,7 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
     CUDA_TRY(cudaMalloc(&c->dtau, (size_t)c->text_rows_cap * c->Mp * sizeof(float)));
     c->dmap_entries = NB * TT;
     CUDA_TRY(cudaMalloc(&c->dmap, (size_t)c->dmap_entries * c->HW * c->Mp * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c->dstencil, (size_t)c->cfg.max_batch * c->HW * c->Mp * sizeof(float)));
     const BwdSmem L = bwd_smem_layout(c->cfg.H, c->cfg.W, c->Mp, c->cfg.kernel_size, C, TT);
     CUDA_TRY(cudaFuncSetAttribute(tree_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(L.total * sizeof(float))));
@@ -1092,7 +1094,7 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
   BwdCtx bc;
   bc.md = c->md; bc.tb = c->tb; bc.arena = c->arena; bc.scores = scores_dev;
   bc.dscores = c->dscores; bc.mbuf = c->mbuf; bc.gflat = gflat_dev; bc.dtau = c->dtau;
-  bc.dmap = c->dmap; bc.go = c->go; bc.max_nodes_q = TT;
+  bc.dmap = c->dmap; bc.dstencil = c->dstencil; bc.go = c->go; bc.max_nodes_q = TT;
   const BwdSmem L = bwd_smem_layout(c->cfg.H, c->cfg.W, c->Mp, c->cfg.kernel_size, C, TT);
   const size_t bsm = L.total * sizeof(float);
   const int32_t* d_entry = reinterpret_cast<const int32_t*>(d + o.node_entry);
@@ -1119,7 +1121,7 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
   // ---- feature-side layers: dW_set = Σ X^T·B
   const int ne = (int)S.entries.size();
   if (ne > 0) {
-    const int chunks = std::min(ne, 8);
+    const int chunks = std::min(ne, 16);
     const int per = (ne + chunks - 1) / chunks;
     dim3 g2((c->Dk + kFgTile - 1) / kFgTile, (c->cfg.map_dim + kFgTile - 1) / kFgTile,
             (ne + per - 1) / per);

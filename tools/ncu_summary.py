@@ -50,7 +50,8 @@ for r in rows[2:]:
         return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1)
     traffic.setdefault(k, []).append((val('dram__bytes_read.sum'), val('dram__bytes_write.sum')))
 import json
-json.dump({k: {'dram_read_bytes': sum(x[0] for x in v) / len(v),
+if traffic:   # a launch-list-only run keeps the previous --set full figures
+  json.dump({k: {'dram_read_bytes': sum(x[0] for x in v) / len(v),
                'dram_write_bytes': sum(x[1] for x in v) / len(v), 'launches': len(v),
                'capture': 'profiles/%s.md' % tag} for k, v in traffic.items()},
           open('profiles/ncu_traffic.json', 'w'), indent=1)
