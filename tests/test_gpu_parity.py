@@ -191,6 +191,35 @@ def test_tree_cluster_sizes_agree(cluster, monkeypatch):
     assert float(np.max(np.abs(scores.cpu().numpy() - ref_s))) <= 1e-3
 
 
+def test_tuning_knobs_do_not_change_results():
+    """n2nmn_set_tree_cluster / _proj_ctas / _text_ctas_per_group are tuning only: the contraction
+    grid cap and the text kernel's column walk give bit-identical scores; cluster sizes agree to
+    rounding (the split of a reduction changes its order). Bad values are rejected."""
+    from n2nmn_b200 import weights as wts
+    N, H, Wd, D, T, C = 40, 10, 15, 512, 20, 28
+    feat, word_vecs = synth.make_inputs(N, H, Wd, D, T, seed=51)
+    W = wts.init_weights('clevr', H, Wd, D, C, seed=5, bias_std=0.1)
+    ex = make_executor('clevr', feat, word_vecs, C, W)
+    tokens = synth.random_valid_tokens(ex.assembler, N, T, seed=52)
+    f, w = torch.from_numpy(feat).cuda(), torch.from_numpy(word_vecs).cuda()
+    base = ex.forward_device(f, w, tokens)[0].cpu().numpy().copy()
+    for proj_ctas, text_ctas in [(7, 0), (32, 1), (1, 2), (0, 3)]:
+        ex.set_proj_ctas(proj_ctas)
+        ex.set_text_ctas_per_group(text_ctas)
+        got = ex.forward_device(f, w, tokens)[0].cpu().numpy()
+        np.testing.assert_array_equal(got, base)
+    ex.set_proj_ctas(0)
+    ex.set_text_ctas_per_group(0)
+    for cs in (1, 2, 4, 0):
+        ex.set_tree_cluster(cs)
+        got = ex.forward_device(f, w, tokens)[0].cpu().numpy()
+        assert float(np.max(np.abs(got - base))) <= 2e-5
+    for bad in (lambda: ex.set_tree_cluster(3), lambda: ex.set_proj_ctas(-1),
+                lambda: ex.set_text_ctas_per_group(-2)):
+        with pytest.raises(_lib.N2NMNError):
+            bad()
+
+
 def test_executor_pool_threads_match_single_context():
     from n2nmn_b200 import weights as wts
     from n2nmn_b200.executor import ExecutorPool
