@@ -321,7 +321,6 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
         float* gm = a1;   // gradient that reaches the l2norm/conv_eltwise output
         const float* tau = c.tb.tau + (size_t)nd.text * Mp;
         const float* w2 = md.elt_w[es];
-        const float b2 = md.elt_b[es][0];
         const float* mimg;
         if (nd.op == OP_FILTER) {
           // out = min(a, find): gradient to `a` where out == a (ties included), else to find

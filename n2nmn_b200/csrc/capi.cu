@@ -371,8 +371,7 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaS
     p.img_ptr = reinterpret_cast<const int32_t*>(d + o.img_ptr);
     p.node_text = reinterpret_cast<const int32_t*>(d + o.node_text);
     p.node_out = reinterpret_cast<const int32_t*>(d + o.node_out);
-    p.tau = c->tb.tau; p.tauw = c->tb.tauw; p.tau2 = c->tb.tau2;
-    p.elt_w = c->md.elt_w[ES_FIND];
+    p.tauw = c->tb.tauw; p.tau2 = c->tb.tau2;
     p.elt_b = c->md.elt_b[ES_FIND];
     p.arena = arena;
     p.mslot = reinterpret_cast<const int32_t*>(d + o.mslot);

@@ -30,10 +30,8 @@ struct ProjParams {
   const int32_t* img_ptr;     // [N+1]
   const int32_t* node_text;   // text row of each CSR entry
   const int32_t* node_out;    // arena slot of each CSR entry
-  const float* tau;           // [rows][Mp]
-  const float* tauw;
+  const float* tauw;          // [text rows][Mp]: τ∘w2 and τ² from the text kernel
   const float* tau2;
-  const float* elt_w;         // conv_eltwise weights of FindModule, [M]
   const float* elt_b;         // conv_eltwise bias of FindModule, [1]
   float* arena;               // [slots][HW]
   // stored sets

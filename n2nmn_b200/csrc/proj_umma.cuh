@@ -4,16 +4,20 @@
 // Tiling: one work item = 128 consecutive rows of the flattened (image, pixel) axis x all Mp
 // output columns, walked as Mp/256 N-tiles of 256 columns (UMMA 128x256x8, fp32 operands read as
 // TF32 straight from the caller's fp32 feature grid — no conversion pass). K is streamed in
-// 32-float (128-byte, one swizzle atom) slices through a 4-stage TMA->smem ring:
-//     stage = A tile 128x32 fp32 (16 KB) + B tile 256x32 fp32 (32 KB), both SWIZZLE_128B K-major.
+// 32-float (128-byte, one swizzle atom) slices through two TMA->smem rings, one per operand:
+//     A slice 128x32 fp32 (16 KB, 3 slots) and B slice 256x32 fp32 (32 KB, 3 slots), both
+//     SWIZZLE_128B K-major.
 // TMEM holds two 128x256 fp32 accumulators (all 512 columns), so the epilogue of N-tile i
-// overlaps the MMAs of N-tile i+1 / of the next work item.
+// overlaps the MMAs of N-tile i+1 / of the next work item. The grid is persistent: CTA i walks
+// work items i, i+gridDim, ... (gridDim = min(items, SMs), or fewer on request: n2nmn_set_proj_ctas).
 //
-// Warp roles (320 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
-// MMA issuer (one elected lane), warps 2..9 = epilogue; epilogue warp w reads TMEM lanes
-// [32*(w%4), 32*(w%4)+32) i.e. tile rows with that offset, and the two warps that share a lane
-// quarter split the 256 columns of an N-tile in halves (the epilogue of a lone tile is a latency
-// chain; two warpgroups halve it). Their partial sums meet in shared memory.
+// Warp roles (384 threads): warpgroup 0 = {A-ring TMA producer, TMEM allocator + MMA issuer,
+// B-ring TMA producer, idle} (one elected lane each, registers handed to the epilogue with
+// setmaxnreg), warps 4..11 = epilogue; epilogue warp w reads TMEM lanes [32*(w%4), 32*(w%4)+32)
+// i.e. tile rows with that offset, and the two warps that share a lane quarter split the 256
+// columns of an N-tile in halves (the epilogue of a lone tile is a latency chain; two warpgroups
+// halve it). Their partial sums meet in shared memory. DESIGN.md §4 has the anatomy and what was
+// measured on the way.
 //
 // Precision: TF32 operands (10-bit mantissa), fp32 accumulate. Error budget vs the fp32/fp64
 // oracle is in DESIGN.md; tests/test_gpu_parity.py holds every attention map to 1e-3 abs.

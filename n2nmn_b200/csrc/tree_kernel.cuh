@@ -11,8 +11,13 @@
 //   * only the heavy modules are split over the cluster: Transform / FindSameProperty by pixel,
 //     the attention-pooled fc_att (Describe / SameProperty / FindSameProperty) by rows of the
 //     stored map; pieces are exchanged through double-buffered distributed shared memory with ONE
-//     cluster barrier per exchange.
-// Results are identical to wave_kernel / eval_node (node_eval.cuh) up to fp32 summation order.
+//     cluster barrier per exchange;
+//   * the Transform stencil (the one arithmetic-heavy step) runs on TF32 mma.sync fragments; the
+//     exact-fp32 CUDA-core stencil is kept for the verification mode (kTreeFp32Stencil).
+// With many batches in flight the pool launches ONE CTA per question instead (no cluster
+// barriers at all): less latency hiding per question, more questions per second.
+// Results agree with wave_kernel / eval_node (node_eval.cuh) up to fp32 summation order and the
+// TF32 rounding of the stencil operands.
 #pragma once
 #include "node_eval.cuh"
 
