@@ -1124,7 +1124,12 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
     const int per = (ne + chunks - 1) / chunks;
     dim3 g2((c->Dk + kFgTile - 1) / kFgTile, (c->cfg.map_dim + kFgTile - 1) / kFgTile,
             (ne + per - 1) / per);
-    feat_grad_kernel<<<g2, 256, 0, st>>>(c->md, c->dmap,
+    if (c->cfg.flags & N2NMN_FLAG_PROJ_FP32_SIMT)
+      feat_grad_kernel<<<g2, 256, 0, st>>>(c->md, c->dmap,
+                                         reinterpret_cast<const BwdEntry*>(d + o.entries), ne, per,
+                                         gflat_dev, c->go);
+    else
+      feat_grad_mma_kernel<<<g2, 256, 0, st>>>(c->md, c->dmap,
                                          reinterpret_cast<const BwdEntry*>(d + o.entries), ne, per,
                                          gflat_dev, c->go);
     ++c->launches;
