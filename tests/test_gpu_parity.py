@@ -321,6 +321,36 @@ def test_config4_vqa_14x14x512_map1024_3001_choices():
     _check_family_batch('vqa', 12, 14, 14, 512, 13, 3001, tokens)
 
 
+@pytest.mark.parametrize('family,H,Wd,D,T,C,layouts', [
+    ('shapes', 3, 3, 64, 11, 2, 'SHAPES_LAYOUTS'), ('vqa', 14, 14, 512, 13, 3001, 'VQA_LAYOUTS')])
+def test_pool_narrow_mode_other_families(family, H, Wd, D, T, C, layouts):
+    """The pool's narrow configuration (one CTA per question, capped contraction grid, one text
+    CTA per node group, 12 worker threads) on the SHAPES and VQA shapes (Mp = 512 / 1024: several
+    column blocks and N-tiles per CTA) gives the scores of a single default context."""
+    from n2nmn_b200 import weights as wts
+    from n2nmn_b200.executor import ExecutorPool, LayoutExecutor
+    N = 10
+    asm = Assembler(synth.vocab_file(family))
+    W = wts.init_weights(family, H, Wd, D, C, seed=8, bias_std=0.1)
+    items = []
+    for i in range(5):
+        f, w = synth.make_inputs(N, H, Wd, D, T, seed=700 + i)
+        items.append((torch.from_numpy(f).cuda(), torch.from_numpy(w).cuda(),
+                      synth.histogram_tokens(asm, getattr(synth, layouts), N, T, seed=70 + i)))
+    pool = ExecutorPool(family, items[0][0], items[0][1], C, asm, weights=W, num_streams=12,
+                        max_batch=N, max_T=T)
+    assert (pool.tree_cluster, pool.proj_ctas, pool.text_ctas_per_group) == (1, 32, 1)
+    pool.begin()
+    outs = [pool.submit(f, w, tok)[0] for f, w, tok in items]
+    pool.end()
+    torch.cuda.synchronize()
+    ref_ex = LayoutExecutor(family, items[0][0], items[0][1], C, asm, weights=W, max_batch=N, max_T=T)
+    for (f, w, tok), got in zip(items, outs):
+        want, _ = ref_ex.forward_device(f, w, tok)
+        torch.cuda.synchronize()
+        assert float(np.max(np.abs(got.cpu().numpy() - want.cpu().numpy()))) <= 2e-5
+
+
 def test_config5_stress_20x20x1024_depth16():
     """Synthetic stress shapes: 20x20x1024 grid, CLEVR module set, T=40, layouts of depth up to 16
     (the deepest ones exceed the shared-memory attention stack and take the wave executor)."""
