@@ -52,6 +52,8 @@ def parse_args():
                     help='ignored (kept for old command lines): every context of the pool has its '
                          'own native worker thread')
     ap.add_argument('--no-train', action='store_true', help='skip the train-step measurement')
+    ap.add_argument('--no-other-sets', action='store_true',
+                    help='skip the random / deep layout sets reported beside the expert mix')
     ap.add_argument('--tree-cluster', type=int, default=None,
                     help='CTAs per question in the executor kernel (default: chosen by the pool)')
     ap.add_argument('--proj-ctas', type=int, default=None,
@@ -333,6 +335,34 @@ def main():
     ms_max = float(t.item())
     value = world * B * args.steps / (ms_max * 1e-3)
 
+    # ---- the other two layout sets of SURVEY.md §8(d) (random valid layouts; deep layouts), same
+    #      pool, same inputs, shorter runs: reported beside the headline, not as the headline
+    other_sets = None
+    if args.layouts == 'expert' and not args.no_other_sets:
+        other_sets = {}
+        for kind in ('random', 'deep'):
+            otoks = [make_tokens(asm, kind, B, seed=100 + 1000 * rank + i) for i in range(P)]
+            n_o = max(200, min(args.steps // 4, 4000))
+            pool.begin()
+            for i in range(3 * K):
+                pool.submit(feats[i % P], wvs[i % P], otoks[i % P], out=scores_k[i % K])
+            pool.end()
+            barrier()
+            oe0, oe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            oe0.record()
+            pool.begin()
+            for i in range(n_o):
+                pool.submit(feats[i % P], wvs[i % P], otoks[i % P], out=scores_k[i % K])
+            pool.end()
+            oe1.record()
+            barrier()
+            to = torch.tensor([oe0.elapsed_time(oe1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(to, op=dist.ReduceOp.MAX)
+            nodes = int(np.mean([int((t != asm.EOS_idx).sum()) for t in otoks]))
+            other_sets[kind] = {'value': world * B * n_o / (float(to.item()) * 1e-3), 'unit': UNIT,
+                                'steps': n_o, 'nodes_per_batch': nodes}
+
     # ---- e2e: host (pinned) buffers in, host scores out, every step, through the public API
     e2e = None
     if not args.no_e2e:
@@ -489,6 +519,7 @@ def main():
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
             'host_enqueue_ms_per_step': host_ms / args.steps, 'host_numa': numa,
             'roofline': roof, 'cpu_baseline': cpu, 'kernel_us': kernel_us, 'train_step': train,
+            'other_layout_sets': other_sets,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
