@@ -1,27 +1,32 @@
 #!/usr/bin/env python
-"""bench.py — CLEVR questions/sec of the module-network hot path on B200 (BASELINE.json metric).
+"""bench.py — questions/sec of the N2NMN module-network hot path on B200 (BASELINE.json metric).
 
-One step = one pass of the hot path over one CLEVR-shaped batch (default 64 questions,
-10x15x512 pool5 grid, T=20 layout tokens, expert-layout mix): host layout compile (C++) ->
-table upload -> text projection -> tcgen05 conv_image contraction with fused Find epilogue ->
-tree kernel -> scores [64,28] on device. Inputs come from a pool of distinct batches resident in
-HBM that is larger than L2, walked round-robin, so no step re-reads a cached batch.
+One step = one pass of the hot path over one batch of synthetic input (default workload: CLEVR
+gt-layout eval, 64 questions, 10x15x512 pool5 grid, T=20 layout tokens, expert-layout mix): host
+layout compile (C++) -> table upload -> text projection -> tcgen05 conv_image contraction with the
+fused Find epilogue -> tree kernel -> scores [64,28] on device. Inputs come from a pool of distinct
+batches resident in HBM that is larger than L2, walked round-robin, so no step re-reads a cached
+batch.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
-    python bench.py --impl reference ...                           # CPU arm (the oracle restatement)
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config clevr|shapes|vqa514|vqa2050|stress]
+    python bench.py --impl reference ...        # CPU arm (the oracle restatement of the reference)
 
-Under torchrun every rank owns one GPU and its own shard of the questions (weak scaling, no
-data-path collective: questions are independent); timing is CUDA events between
-barriers, max over ranks; rank 0 prints ONE JSON line.
+How the number is taken (a 20-step region is ~1 ms of host wake-up noise): the block of
+K steps is repeated R times back to back, R chosen from a calibration run so that one timed region
+lasts >= --min-seconds (0.5 s), each region bracketed by barrier + synchronize and timed with CUDA
+events; `--trials` (3) regions are taken and the MEDIAN is reported (`repeats`, `timed_region_s`,
+`trial_values` are in the line). Under torchrun every rank owns one GPU and its own shard of the
+questions (weak scaling, no data-path collective: questions are independent);
+region time = max over ranks; rank 0 prints ONE JSON line.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -30,36 +35,60 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-H, W, D, T_DEC, C, TEXT_DIM = 10, 15, 512, 20, 28, 300
-METRIC = 'clevr_questions_per_sec'
+TEXT_DIM = 300
 UNIT = 'questions/s'
+
+# BASELINE.json configs made concrete. `clevr` is the configuration the
+# metric is quoted on; the others are reported beside it (`other_configs`) or with --config.
+WORKLOADS = {
+    'clevr': dict(family='clevr', B=64, H=10, W=15, D=512, T=20, C=28, layouts='expert',
+                  metric='clevr_questions_per_sec',
+                  title='CLEVR gt-layout eval, batch=64/GPU, 10x15x512 pool5, %s layouts depth<=12, T=20'),
+    'shapes': dict(family='shapes', B=32, H=3, W=3, D=64, T=11, C=2, layouts='shapes_hist',
+                   metric='shapes_questions_per_sec',
+                   title='SHAPES gt-layout eval, batch=32/GPU, 3x3x64 conv features, %s layouts, T=11'),
+    'vqa514': dict(family='vqa', B=128, H=14, W=14, D=512, T=13, C=3001, layouts='vqa_hist',
+                   metric='vqa_questions_per_sec',
+                   title='VQA gt-layout eval, batch=128/GPU, 14x14x512(+2 coord) features, %s layouts, T=13'),
+    'vqa2050': dict(family='vqa', B=128, H=14, W=14, D=2048, T=13, C=3001, layouts='vqa_hist',
+                    metric='vqa_questions_per_sec',
+                    title='VQA gt-layout eval, batch=128/GPU, 14x14x2048(+2 coord) res5c features, %s layouts, T=13'),
+    'stress': dict(family='clevr', B=128, H=20, W=20, D=1024, T=40, C=28, layouts='deep16',
+                   metric='stress_questions_per_sec',
+                   title='synthetic stress, batch=128/GPU, 20x20x1024 features, %s layouts depth<=16, T=40'),
+}
+L2_BYTES = 126e6
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20000)
-    ap.add_argument('--warmup', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=64, help='questions per GPU per step')
-    ap.add_argument('--layouts', default='expert', choices=['expert', 'random', 'deep'])
-    ap.add_argument('--pool', type=int, default=10, help='distinct resident batches (x19.7 MB)')
-    ap.add_argument('--cpu-seconds', type=float, default=12.0, help='cpu_baseline sample budget')
+    ap.add_argument('--config', default='clevr', choices=sorted(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=0, help='questions per GPU per step (0 = the config\'s)')
+    ap.add_argument('--layouts', default=None, choices=['expert', 'random', 'deep'],
+                    help='CLEVR layout set (default expert)')
+    ap.add_argument('--min-seconds', type=float, default=0.5, help='length of one timed region')
+    ap.add_argument('--trials', type=int, default=3, help='timed regions; the median is reported')
+    ap.add_argument('--cpu-seconds', type=float, default=10.0, help='cpu_baseline sample budget')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--wave', action='store_true', help='depth-bucketed wave executor')
-    ap.add_argument('--host-threads', type=int, default=0,
-                    help='ignored (kept for old command lines): every context of the pool has its '
-                         'own native worker thread')
     ap.add_argument('--no-train', action='store_true', help='skip the train-step measurement')
     ap.add_argument('--no-other-sets', action='store_true',
                     help='skip the random / deep layout sets reported beside the expert mix')
+    ap.add_argument('--no-other-configs', action='store_true',
+                    help='skip the other BASELINE.json workloads reported beside the headline')
     ap.add_argument('--tree-cluster', type=int, default=None,
                     help='CTAs per question in the executor kernel (default: chosen by the pool)')
     ap.add_argument('--proj-ctas', type=int, default=None,
                     help='cap of the contraction kernel grid (default: chosen by the pool; 0 = all SMs)')
-    ap.add_argument('--streams', type=int, default=12,
-                    help='contexts/streams fed round-robin (independent batches overlap)')
+    ap.add_argument('--streams', type=int, default=0,
+                    help='contexts/streams/worker threads (0 = the library default)')
+    ap.add_argument('--host-threads', type=int, default=0, help='ignored (old command lines)')
+    ap.add_argument('--pool', type=int, default=0, help='ignored (old command lines)')
     return ap.parse_args()
 
 
@@ -86,16 +115,32 @@ def ncu_traffic(kernel):
     return None if not d else d['dram_read_bytes'] + d['dram_write_bytes']
 
 
-def make_tokens(asm, kind, n, seed):
+def workload_title(wl, layouts):
+    names = {'expert': 'expert', 'random': 'random valid', 'deep': 'deep', 'shapes_hist':
+             'the 3 real SHAPES', 'vqa_hist': 'VQA gt-layout histogram', 'deep16': 'random deep'}
+    return wl['title'] % names[layouts]
+
+
+def make_tokens(asm, kind, n, T, seed):
     from n2nmn_b200 import synth
+    rng = np.random.RandomState(seed)
     if kind == 'expert':
-        toks = synth.expert_mix_tokens(asm, n, T_DEC)
-        rng = np.random.RandomState(seed)          # same mix, different question order per batch
+        toks = synth.expert_mix_tokens(asm, n, T)       # same mix, different question order
         return np.ascontiguousarray(toks[:, rng.permutation(n)])
     if kind == 'random':
-        return synth.random_valid_tokens(asm, n, T_DEC, seed=seed)
-    return synth.random_valid_tokens(asm, n, T_DEC, seed=seed, ans_weight=0.15, min_depth=3,
-                                     max_depth=12)
+        return synth.random_valid_tokens(asm, n, T, seed=seed)
+    if kind == 'deep':
+        return synth.random_valid_tokens(asm, n, T, seed=seed, ans_weight=0.15, min_depth=3,
+                                         max_depth=12)
+    if kind == 'shapes_hist':
+        return synth.histogram_tokens(asm, synth.SHAPES_LAYOUTS, n, T, seed=seed)
+    if kind == 'vqa_hist':
+        return synth.histogram_tokens(asm, synth.VQA_LAYOUTS, n, T, seed=seed)
+    if kind == 'deep16':   # sampling by rejection is slow: 16 distinct deep layouts, tiled
+        base = synth.random_valid_tokens(asm, 16, T, seed=21, ans_weight=0.08, min_depth=8,
+                                         max_depth=16)
+        return np.ascontiguousarray(base[:, rng.randint(0, 16, size=n)])
+    raise ValueError(kind)
 
 
 class ClockSampler:
@@ -131,6 +176,7 @@ class ClockSampler:
             rows = [[c.strip() for c in ln.split(',')] for ln in out.splitlines() if ln.strip()]
         sm = [float(r[1]) for r in rows if len(r) > 2 and r[1].replace('.', '').isdigit()]
         mx = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace('.', '').isdigit()]
+        pw = [float(r[3]) for r in rows if len(r) > 3 and r[3].replace('.', '').isdigit()]
         reasons = []
         for name, col in (('hw_slowdown', 4), ('hw_thermal_slowdown', 5),
                           ('sw_thermal_slowdown', 6), ('sw_power_cap', 7)):
@@ -138,94 +184,156 @@ class ClockSampler:
                 reasons.append(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None,
                 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
-                'samples': len(rows)}
+                'power_w_max': max(pw) if pw else None, 'samples': len(rows)}
 
 
-def best_blas_threads(run_once):
-    """OpenBLAS with one thread per core is slow on many-core hosts for these small GEMMs.
-    Give the CPU arm its best shot: try a few thread counts, keep the fastest."""
-    try:
-        from threadpoolctl import threadpool_limits
-    except Exception:
-        return None, os.cpu_count()
+# =========================================================================== CPU arms (oracle)
+def _thread_candidates():
     ncpu = os.cpu_count() or 1
-    best = (None, None)
-    for nt in sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)}):
-        with threadpool_limits(limits=nt):
-            run_once()
+    return sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)})
+
+
+class CpuPort:
+    """One CPU restatement of the reference path (TF 1.0 + Fold cannot be installed here,
+    DESIGN.md): Assembler.assemble + depth-batched module calls. kind 'numpy' = oracle/nmn_oracle.py
+    (numpy + OpenBLAS), kind 'torch' = oracle/nmn_oracle_torch.py::run_depth_batched (MKL/oneDNN)."""
+
+    def __init__(self, kind, wl, feat, word_vecs, weights):
+        from n2nmn_b200 import synth
+        from n2nmn_b200.assembler import Assembler
+        self.kind = kind
+        self.asm = Assembler(synth.vocab_file(wl['family']))
+        if kind == 'numpy':
+            from oracle.nmn_oracle import OracleModules, run_depth_batched
+            self.m = OracleModules(feat, word_vecs, wl['C'], weights, family=wl['family'])
+            self.run = run_depth_batched
+        else:
+            from oracle import nmn_oracle_torch as ot
+            self.m = ot.TorchOracleModules(feat, word_vecs, wl['C'], weights, family=wl['family'])
+            self.run = ot.run_depth_batched
+        self.threads = None
+
+    def step(self, tokens):
+        exprs, _ = self.asm.assemble(tokens)
+        return self.run(self.m, exprs)
+
+    def set_threads(self, nt):
+        if self.kind == 'torch':
+            import torch
+            torch.set_num_threads(int(nt))
+        else:
+            from threadpoolctl import threadpool_limits
+            if getattr(self, '_lim', None) is not None:
+                self._lim.restore_original_limits()
+            self._lim = threadpool_limits(limits=int(nt))
+        self.threads = int(nt)
+
+    def pick_threads(self, tokens, trials=3, max_seconds=6.0):
+        """One thread per core is slow on many-core hosts for these small GEMMs, and one noisy
+        trial picked a 2x slower count in round 1: median of `trials` per candidate."""
+        best, t_start = (None, None), time.perf_counter()
+        log = {}
+        for nt in _thread_candidates():
+            self.set_threads(nt)
+            self.step(tokens)
+            ts = []
+            for _ in range(trials):
+                t0 = time.perf_counter()
+                self.step(tokens)
+                ts.append(time.perf_counter() - t0)
+            med = float(np.median(ts))
+            log[nt] = round(med * 1e3, 2)
+            if best[0] is None or med < best[0]:
+                best = (med, nt)
+            if time.perf_counter() - t_start > max_seconds and best[0] is not None:
+                break
+        self.set_threads(best[1])
+        self.pick_log = log
+        return best[1]
+
+    def measure(self, tokens_list, budget_s, min_batches=2):
+        n_q, t0, k = 0, time.perf_counter(), 0
+        while True:
+            tok = tokens_list[k % len(tokens_list)]
+            self.step(tok)
+            n_q += tok.shape[1]
+            k += 1
+            el = time.perf_counter() - t0
+            if k >= min_batches and el >= budget_s:
+                break
+        return n_q / el, k, el
+
+
+def best_cpu_port(wl, feat, word_vecs, weights, toks, pick_seconds=6.0):
+    """Both ports with their best thread count; returns (faster port, {kind: ms per batch})."""
+    ports, ms = [], {}
+    for kind in ('numpy', 'torch'):
+        try:
+            p = CpuPort(kind, wl, feat, word_vecs, weights)
+            p.pick_threads(toks[0], max_seconds=pick_seconds)
             t0 = time.perf_counter()
-            run_once()
-            dt = time.perf_counter() - t0
-        if best[0] is None or dt < best[0]:
-            best = (dt, nt)
-    return threadpool_limits(limits=best[1]), best[1]
+            for i in range(2):
+                p.step(toks[i % len(toks)])
+            ms[kind] = {'ms_per_batch': round((time.perf_counter() - t0) * 500, 2),
+                        'threads': p.threads, 'ms_by_threads': p.pick_log}
+            ports.append(p)
+        except Exception as e:   # threadpoolctl / torch missing: keep the other port
+            ms[kind] = {'error': repr(e)}
+    best = min(ports, key=lambda p: ms[p.kind]['ms_per_batch'])
+    best.set_threads(best.threads)
+    return best, ms
 
 
-def cpu_reference_qps(feat, word_vecs, weights, tokens_list, budget_s, min_batches=2):
-    """Times the oracle restatement of the reference path (Assembler.assemble + TF-Fold-style
-    depth-batched module calls, numpy/OpenBLAS fp32) on a bounded sample of the workload.
-    Returns (questions/s, batches, seconds, BLAS threads used)."""
-    from n2nmn_b200 import synth
-    from n2nmn_b200.assembler import Assembler
-    from oracle.nmn_oracle import OracleModules, run_depth_batched
-    asm = Assembler(synth.vocab_file('clevr'))
-    m = OracleModules(feat, word_vecs, C, weights, family='clevr')
-    exprs, _ = asm.assemble(tokens_list[0])
-    limiter, threads = best_blas_threads(lambda: run_depth_batched(m, exprs))
-    n_q, t0, k = 0, time.perf_counter(), 0
-    while True:
-        tok = tokens_list[k % len(tokens_list)]
-        exprs, _ = asm.assemble(tok)
-        run_depth_batched(m, exprs)
-        n_q += tok.shape[1]
-        k += 1
-        el = time.perf_counter() - t0
-        if k >= min_batches and el >= budget_s:
-            break
-    if limiter is not None:
-        limiter.restore_original_limits()
-    return n_q / el, k, el, threads
+def port_desc(p):
+    return ('oracle/nmn_oracle.py: numpy+OpenBLAS' if p.kind == 'numpy' else
+            'oracle/nmn_oracle_torch.py: torch-CPU MKL/oneDNN') + \
+        ' fp32 depth-batched restatement, Assembler.assemble included'
 
 
 def run_reference_arm(args, rank, world):
-    """--impl reference: the CPU restatement (oracle) of the reference's TF1 path on host cores;
-    TF 1.0 + TF Fold cannot be installed here. Rank 0 only."""
+    """--impl reference: the faster CPU restatement (oracle) of the reference's TF1 path on the
+    box's host cores, same workload/config strings as the b200 arm. Rank 0 only."""
     if rank != 0:
         return
     from n2nmn_b200 import synth, weights as wts
     from n2nmn_b200.assembler import Assembler
-    asm = Assembler(synth.vocab_file('clevr'))
-    feat, word_vecs = synth.make_inputs(args.batch, H, W, D, T_DEC, seed=1234)
-    weights = wts.init_weights('clevr', H, W, D, C, seed=0, bias_std=0.1)
-    toks = [make_tokens(asm, args.layouts, args.batch, seed=100 + i) for i in range(4)]
-    from oracle.nmn_oracle import OracleModules, run_depth_batched
-    m = OracleModules(feat, word_vecs, C, weights, family='clevr')
-    exprs0 = asm.assemble(toks[0])[0]
-    limiter, threads = best_blas_threads(lambda: run_depth_batched(m, exprs0))
+    wl = dict(WORKLOADS[args.config])
+    B = args.batch or wl['B']
+    layouts = args.layouts or wl['layouts']
+    asm = Assembler(synth.vocab_file(wl['family']))
+    feat, word_vecs = synth.make_inputs(B, wl['H'], wl['W'], wl['D'], wl['T'], seed=1234)
+    weights = wts.init_weights(wl['family'], wl['H'], wl['W'], wl['D'], wl['C'], seed=0,
+                               bias_std=0.1)
+    toks = [make_tokens(asm, layouts, B, wl['T'], seed=100 + i) for i in range(4)]
+    port, ports_ms = best_cpu_port(wl, feat, word_vecs, weights, toks)
     for i in range(max(args.warmup, 1)):
-        run_depth_batched(m, asm.assemble(toks[i % 4])[0])
+        port.step(toks[i % 4])
     steps = min(args.steps, 200)
+    per = []
     t0 = time.perf_counter()
     for i in range(steps):
-        run_depth_batched(m, asm.assemble(toks[i % 4])[0])
+        t1 = time.perf_counter()
+        port.step(toks[i % 4])
+        per.append(time.perf_counter() - t1)
     el = time.perf_counter() - t0
-    qps = steps * args.batch / el
+    qps = steps * B / el
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': qps, 'unit': UNIT, 'n_gpus': args.gpus,
-        'steps': steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * el / steps,
+        'impl': 'reference', 'metric': wl['metric'], 'value': qps, 'unit': UNIT,
+        'n_gpus': args.gpus, 'steps': steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * el / steps, 'median_ms_per_step': 1e3 * float(np.median(per)),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': {'workload': 'CLEVR gt-layout eval, batch=%d, 10x15x512 pool5, %s layouts, T=%d'
-                   % (args.batch, args.layouts, T_DEC), 'global_batch': args.batch},
-        'cpu_baseline': {'value': qps, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                         'sample': '%d batches of %d questions (oracle/nmn_oracle.py: numpy + '
-                                   'OpenBLAS, Assembler.assemble included)' % (steps, args.batch)},
+        'config': {'workload': workload_title(wl, layouts), 'global_batch': B},
+        'cpu_baseline': {'value': qps, 'unit': UNIT, 'cores': port.threads, 'kind': 'port',
+                         'host_cpus': os.cpu_count(), 'ports': ports_ms,
+                         'sample': '%d batches of %d questions (%s)' % (steps, B, port_desc(port))},
         'e2e': {'value': qps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
 
 
+# =========================================================================== GPU arm
 def bind_to_gpu_numa_node(torch, index):
     """Run this process (and so its pinned-buffer allocations and the pool's worker threads) on
     the CPUs that are local to the GPU's PCIe root: host<->device copies from the other socket
@@ -251,6 +359,237 @@ def bind_to_gpu_numa_node(torch, index):
         return 'not bound: %s' % e
 
 
+class Bench:
+    """One workload on this rank's GPU: resident batches, the executor pool, timed regions."""
+
+    def __init__(self, torch, dist, args, wl, layouts, B, rank, world, dev, streams=None,
+                 device_synth=False):
+        from n2nmn_b200 import _lib, synth, weights as wts
+        from n2nmn_b200.assembler import Assembler
+        from n2nmn_b200.executor import ExecutorPool
+        self.torch, self.dist, self.args, self.wl = torch, dist, args, wl
+        self.rank, self.world, self.dev, self.B, self.layouts = rank, world, dev, B, layouts
+        H, W, D, T, C = wl['H'], wl['W'], wl['D'], wl['T'], wl['C']
+        self.asm = Assembler(synth.vocab_file(wl['family']))
+        self.weights = wts.init_weights(wl['family'], H, W, D, C, seed=0, bias_std=0.1)
+        batch_bytes = B * H * W * D * 4
+        self.P = P = int(min(2048, max(2, math.ceil(1.5 * L2_BYTES / batch_bytes))))
+        self.batch_bytes = batch_bytes
+        self.feats, self.wvs = [], []
+        for i in range(P):   # per-rank seeds = per-rank shard of the global question stream
+            seed = 1234 + 1000 * rank + i
+            if device_synth:   # big grids: generate on the device (same distributions)
+                g = torch.Generator(device=dev)
+                g.manual_seed(seed)
+                f = torch.randn((B, H, W, D), generator=g, device=dev).clamp_(min=0)
+                w = torch.randn((T, B, TEXT_DIM), generator=g, device=dev).mul_(0.3)
+            else:
+                fn, wn = synth.make_inputs(B, H, W, D, T, seed=seed)
+                f, w = torch.from_numpy(fn).to(dev), torch.from_numpy(wn).to(dev)
+            self.feats.append(f)
+            self.wvs.append(w)
+        n_tok = min(P, 16)
+        self.toks = [make_tokens(self.asm, layouts, B, T, seed=100 + 1000 * rank + i)
+                     for i in range(n_tok)]
+        kw = {}
+        if streams:
+            kw['num_streams'] = streams
+        flags = _lib.FLAG_WAVE_EXECUTOR if args.wave else 0
+        self.pool = ExecutorPool(wl['family'], self.feats[0], self.wvs[0], C, self.asm,
+                                 weights=self.weights, flags=flags, max_batch=B, max_T=T,
+                                 tree_cluster=args.tree_cluster, proj_ctas=args.proj_ctas, **kw)
+        self.K = len(self.pool)
+        self.ex = self.pool.executors[0]
+        self.nout = max(2 * self.K, 8)
+        self.outs = [torch.empty((B, C), dtype=torch.float32, device=dev) for _ in range(self.nout)]
+
+    def tok(self, i):
+        return self.toks[i % len(self.toks)]
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def allmax(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def blocks(self, steps, toks=None):
+        """Pre-marshalled blocks of `steps` steps that together walk all P resident batches."""
+        P = self.P
+        nb = min(64, P // math.gcd(steps, P))
+        out = []
+        for b in range(nb):
+            idx = [(b * steps + j) % P for j in range(steps)]
+            tk = [(toks or self.toks)[i % len(toks or self.toks)] for i in idx]
+            out.append(self.pool.make_block([self.feats[i] for i in idx],
+                                            [self.wvs[i] for i in idx], tk,
+                                            [self.outs[(b * steps + j) % self.nout]
+                                             for j in range(steps)]))
+        return out
+
+    def region(self, blocks, repeats):
+        """`repeats` back-to-back repetitions of the step block, CUDA events on the current stream
+        (pool.begin()/end() order the pool's streams after e0 / before e1). Returns ms, max over
+        ranks, and the host time needed to enqueue."""
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        t0 = time.perf_counter()
+        self.pool.begin()
+        for r in range(repeats):
+            self.pool.submit_block(blocks[r % len(blocks)])
+        self.pool.end()
+        e1.record()
+        host_ms = (time.perf_counter() - t0) * 1e3
+        self.barrier()
+        return self.allmax(e0.elapsed_time(e1)), host_ms
+
+    def timed(self, steps, warmup, min_seconds, trials, toks=None):
+        """warm-up, calibration, then `trials` regions of >= min_seconds; median region reported."""
+        if warmup > 0:
+            wb = self.blocks(warmup, toks)
+            self.region(wb[:1], 1)
+        blocks = self.blocks(steps, toks)
+        cal_ms, _ = self.region(blocks, max(1, len(blocks)))      # touches every resident batch
+        per_block = cal_ms / max(1, len(blocks))
+        R = int(max(1, math.ceil(min_seconds * 1e3 / max(per_block, 1e-6))))
+        res = []
+        for _ in range(trials):
+            l0 = self.pool.launch_count()
+            ms, host_ms = self.region(blocks, R)
+            res.append((ms, host_ms, self.pool.launch_count() - l0))
+        res.sort()
+        ms, host_ms, launches = res[len(res) // 2]
+        n_steps = R * steps
+        return {'ms_per_step': ms / n_steps, 'repeats': R, 'timed_steps': n_steps,
+                'gpu_launches': int(launches),
+                'timed_region_s': ms * 1e-3, 'host_enqueue_ms_per_step': host_ms / n_steps,
+                'value': self.world * self.B * n_steps / (ms * 1e-3),
+                'trial_values': [self.world * self.B * n_steps / (r[0] * 1e-3) for r in res]}
+
+    def kernel_pass(self, n=40):
+        """Per-launch CUDA events (library profiling mode) of single-context forwards walking the
+        resident batches: {kernel: mean us}, mean algorithmic bytes / flops per launch of each of
+        the three kernels."""
+        ex, acc, nb, nf = self.ex, {}, np.zeros(3), np.zeros(3)
+        ex.set_profiling(True)
+        for i in range(n):
+            ex.forward_device(self.feats[i % self.P], self.wvs[i % self.P], self.tok(i),
+                              out=self.outs[0])
+            for name, us in ex.launch_times():
+                acc.setdefault(name, []).append(us)
+            info = ex.last_step_info()
+            nb += np.array(info['kernel_bytes'], float)
+            nf += np.array(info['kernel_flops'], float)
+        ex.set_profiling(False)
+        return {k: float(np.mean(v)) for k, v in acc.items()}, nb / n, nf / n
+
+    def roofline(self, pk):
+        """roofline of the dominant kernel (the contraction) + HBM fractions of the other two."""
+        kus, nb, nf = self.kernel_pass()
+        tf32_peak = pk['bf16_tflops'] / 2
+        total = max(sum(kus.values()), 1e-9)
+
+        def frac(us, b, f):
+            d = us * 1e-6
+            return b / d / 1e9, f / d / 1e12, b / d / 1e9 / pk['hbm_gbs'], f / d / 1e12 / tf32_peak
+
+        out = {'kernel_us': kus}
+        proj = 'proj_umma_kernel'
+        if proj in kus:
+            gbs, tfs, hf, tf = frac(kus[proj], nb[1], nf[1])
+            bound = 'hbm' if hf >= tf else 'tensor'
+            out['roofline'] = {
+                'kernel': proj, 'bound': bound, 'achieved': gbs if bound == 'hbm' else tfs,
+                'peak': pk['hbm_gbs'] if bound == 'hbm' else tf32_peak,
+                'unit': 'GB/s' if bound == 'hbm' else 'TFLOP/s', 'frac': max(hf, tf),
+                'traffic': ncu_traffic(proj) if self.wl is WORKLOADS['clevr'] else None,
+                'hbm_frac': hf, 'tensor_frac_of_tf32_peak': tf, 'avg_launch_us': kus[proj],
+                'algorithmic_bytes_per_launch': nb[1], 'flops_per_launch': nf[1],
+                'peak_source': pk['source'] + '; TF32 peak taken as bf16 burst / 2',
+                'share_of_step': kus[proj] / total,
+                'how': 'CUDA events around every launch (library profiling mode), one context, '
+                       'mean of 40 steps over the resident batches'}
+        for key, name, k in (('roofline_text', 'text_proj_kernel', 0),
+                             ('roofline_tree', 'tree_kernel', 2)):
+            if name in kus:
+                gbs, tfs, hf, tf = frac(kus[name], nb[k], nf[k])
+                out[key] = {'kernel': name, 'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'],
+                            'unit': 'GB/s', 'frac': hf, 'avg_launch_us': kus[name],
+                            'algorithmic_bytes_per_launch': nb[k], 'flops_per_launch': nf[k],
+                            'share_of_step': kus[name] / total}
+        return out
+
+    def e2e(self, steps, min_seconds):
+        """Pinned host features + word vectors -> H2D -> kernels -> D2H scores, every step, through
+        ExecutorPool (n2nmn_forward_host_async per step); wall clock + final synchronize."""
+        torch = self.torch
+        hp = int(min(self.P, max(2, math.ceil(1.2 * L2_BYTES / self.batch_bytes)), 8))
+        hf = [self.feats[i].cpu().pin_memory() for i in range(hp)]
+        hw = [self.wvs[i].cpu().pin_memory() for i in range(hp)]
+        # one score buffer per host batch: steps that share a buffer have identical inputs
+        hs = [torch.empty((self.B, self.wl['C']), dtype=torch.float32).pin_memory()
+              for _ in range(hp)]
+        k = max(hp, min(steps, 50))
+        idx = [j % hp for j in range(k)]
+        blk = self.pool.make_block([hf[i] for i in idx], [hw[i] for i in idx],
+                                   [self.tok(i) for i in idx], [hs[i] for i in idx],
+                                   host_io=True)
+
+        def run(reps):
+            self.barrier()
+            t0 = time.perf_counter()
+            self.pool.begin()
+            for _ in range(reps):
+                self.pool.submit_block(blk)
+            self.pool.end()
+            torch.cuda.synchronize()
+            return self.allmax(time.perf_counter() - t0)
+
+        run(1)
+        cal = run(1)
+        reps = int(max(1, math.ceil(min_seconds / max(cal, 1e-6))))
+        els = sorted(run(reps) for _ in range(3))
+        el = els[1]
+        # the copied-back scores are the device path's scores
+        last = k - 1
+        chk, _ = self.ex.forward_device(self.feats[idx[last]], self.wvs[idx[last]],
+                                        self.tok(idx[last]))
+        torch.cuda.synchronize()
+        assert torch.equal(hs[idx[last]], chk.cpu()), 'e2e scores differ from the device path'
+        h2d = int(hf[0].numel() * 4 + hw[0].numel() * 4)
+        d2h = int(hs[0].numel() * 4)
+        n = reps * k
+        return {'value': self.world * self.B * n / el, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': d2h, 'steps': n, 'timed_region_s': el,
+                'bound': 'pcie', 'achieved_h2d_gbs_per_gpu': h2d * n / el / 1e9,
+                'how': 'ExecutorPool.submit_block(host_io): pinned host features+word_vecs -> '
+                       'async H2D -> C++ layout compile -> kernels -> async D2H scores, %d '
+                       'streams, every step; wall clock around the loop + final synchronize, '
+                       'median of 3 regions' % self.K}
+
+    def cpu_baseline(self, budget_s):
+        f0, w0 = self.feats[0].cpu().numpy(), self.wvs[0].cpu().numpy()
+        port, ports_ms = best_cpu_port(self.wl, f0, w0, self.weights, self.toks[:4],
+                                       pick_seconds=min(6.0, budget_s))
+        qps, nb, el = port.measure(self.toks[:4], budget_s)
+        return {'value': qps, 'unit': UNIT, 'cores': port.threads, 'kind': 'port',
+                'host_cpus': os.cpu_count(), 'ports': ports_ms,
+                'sample': '%d batches of %d questions in %.1f s (%s)' % (nb, self.B, el,
+                                                                         port_desc(port))}
+
+    def close(self):
+        self.pool = None
+        self.ex = None
+        self.feats = self.wvs = self.outs = None
+        self.torch.cuda.empty_cache()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -262,9 +601,8 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from n2nmn_b200 import _lib, synth, weights as wts
-    from n2nmn_b200.assembler import Assembler
-    from n2nmn_b200.executor import ExecutorPool, LayoutExecutor
+    from n2nmn_b200 import synth
+    from n2nmn_b200.executor import LayoutExecutor
 
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device. The product path has no CPU fallback.')
@@ -274,256 +612,155 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
-    B, P = args.batch, args.pool
-    asm = Assembler(synth.vocab_file('clevr'))
-    weights = wts.init_weights('clevr', H, W, D, C, seed=0, bias_std=0.1)
-    # pool of distinct batches (per-rank seeds = per-rank shard of the global question stream)
-    feats, wvs, toks = [], [], []
-    for i in range(P):
-        f, w = synth.make_inputs(B, H, W, D, T_DEC, seed=1234 + 1000 * rank + i)
-        feats.append(torch.from_numpy(f).to(dev))
-        wvs.append(torch.from_numpy(w).to(dev))
-        toks.append(make_tokens(asm, args.layouts, B, seed=100 + 1000 * rank + i))
-    flags = _lib.FLAG_WAVE_EXECUTOR if args.wave else 0
-    K = max(1, args.streams)
-    pool = ExecutorPool('clevr', feats[0], wvs[0], C, asm, weights=weights, num_streams=K,
-                        flags=flags, max_batch=B, max_T=T_DEC, tree_cluster=args.tree_cluster,
-                        proj_ctas=args.proj_ctas)
-    ex = pool.executors[0]
-    PROJ_CTAS, TREE_CLUSTER = pool.proj_ctas, pool.tree_cluster
-    scores_k = [torch.empty((B, C), dtype=torch.float32, device=dev) for _ in range(K)]
-    scores = scores_k[0]
+    wl = WORKLOADS[args.config]
+    B = args.batch or wl['B']
+    layouts = args.layouts or wl['layouts']
+    bn = Bench(torch, dist, args, wl, layouts, B, rank, world, dev, streams=args.streams or None,
+               device_synth=(args.config not in ('clevr', 'shapes')))
+    pool, ex, K = bn.pool, bn.ex, bn.K
+    pk = peaks()
 
-    def step(i):
-        # public API, one call per batch: bind the batch's device-resident features, compile its
-        # layouts (C++), upload the tables, launch the kernels; asynchronous. Batches go
-        # round-robin over K contexts/streams so independent batches overlap on the GPU.
-        k = i % P
-        pool.submit(feats[k], wvs[k], toks[k], out=scores_k[i % K])
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    pool.begin()
-    for i in range(args.warmup):
-        step(i)
-    pool.end()
-    barrier()
+    # ---- headline: device-resident inputs, median of `trials` regions of >= min_seconds
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = pool.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    t_host0 = time.perf_counter()
-    pool.begin()          # the K streams start after e0 ...
-    for i in range(args.steps):
-        step(args.warmup + i)
-    pool.end()            # ... and e1 is recorded after all of them have drained
-    e1.record()
-    host_ms = (time.perf_counter() - t_host0) * 1e3   # time the host needed to enqueue the steps
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = pool.launch_count() - launches0
+    head = bn.timed(args.steps, args.warmup, args.min_seconds, args.trials)
+    launches = head['gpu_launches']
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * B * args.steps / (ms_max * 1e-3)
 
-    # ---- the other two layout sets of SURVEY.md §8(d) (random valid layouts; deep layouts), same
-    #      pool, same inputs, shorter runs: reported beside the headline, not as the headline
+    # ---- the other two layout sets of SURVEY.md §8(d) (CLEVR: random valid; deep), same pool
     other_sets = None
-    if args.layouts == 'expert' and not args.no_other_sets:
+    if args.config == 'clevr' and layouts == 'expert' and not args.no_other_sets:
         other_sets = {}
         for kind in ('random', 'deep'):
-            otoks = [make_tokens(asm, kind, B, seed=100 + 1000 * rank + i) for i in range(P)]
-            n_o = max(200, min(args.steps // 4, 4000))
-            pool.begin()
-            for i in range(3 * K):
-                pool.submit(feats[i % P], wvs[i % P], otoks[i % P], out=scores_k[i % K])
-            pool.end()
-            barrier()
-            oe0, oe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            oe0.record()
-            pool.begin()
-            for i in range(n_o):
-                pool.submit(feats[i % P], wvs[i % P], otoks[i % P], out=scores_k[i % K])
-            pool.end()
-            oe1.record()
-            barrier()
-            to = torch.tensor([oe0.elapsed_time(oe1)], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(to, op=dist.ReduceOp.MAX)
-            nodes = int(np.mean([int((t != asm.EOS_idx).sum()) for t in otoks]))
-            other_sets[kind] = {'value': world * B * n_o / (float(to.item()) * 1e-3), 'unit': UNIT,
-                                'steps': n_o, 'nodes_per_batch': nodes}
+            otoks = [make_tokens(bn.asm, kind, B, wl['T'], seed=100 + 1000 * rank + i)
+                     for i in range(8)]
+            r = bn.timed(min(args.steps, 100), 12, 0.25, 1, toks=otoks)
+            other_sets[kind] = {'value': r['value'], 'unit': UNIT, 'steps': r['timed_steps'],
+                                'timed_region_s': r['timed_region_s'], 'nodes_per_batch': int(
+                                    np.mean([int((t != bn.asm.EOS_idx).sum()) for t in otoks]))}
 
     # ---- e2e: host (pinned) buffers in, host scores out, every step, through the public API
-    e2e = None
-    if not args.no_e2e:
-        hp = min(P, 6)
-        hf = [feats[i].cpu().pin_memory() for i in range(hp)]
-        hw = [wvs[i].cpu().pin_memory() for i in range(hp)]
-        hs = [torch.empty((B, C), dtype=torch.float32).pin_memory() for _ in range(hp)]
-        pool.begin()
-        for i in range(2 * K):
-            pool.submit_host(hf[i % hp], hw[i % hp], toks[i % hp], hs[i % hp])
-        pool.end()
-        k_e2e = max(10, min(args.steps, 400))
-        barrier()
-        t0 = time.perf_counter()
-        pool.begin()
-        for i in range(k_e2e):
-            pool.submit_host(hf[i % hp], hw[i % hp], toks[i % hp], hs[i % hp])
-        pool.end()
-        torch.cuda.synchronize()
-        el = time.perf_counter() - t0
-        # the copied-back scores are the device path's scores
-        chk, _ = ex.forward_device(feats[(k_e2e - 1) % hp], wvs[(k_e2e - 1) % hp],
-                                   toks[(k_e2e - 1) % hp])
-        torch.cuda.synchronize()
-        assert torch.equal(hs[(k_e2e - 1) % hp], chk.cpu()), 'e2e scores differ from device path'
-        te = torch.tensor([el], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {'value': world * B * k_e2e / float(te.item()), 'unit': UNIT,
-               'h2d_bytes_per_step': int(hf[0].numel() * 4 + hw[0].numel() * 4),
-               'd2h_bytes_per_step': int(hs[0].numel() * 4), 'steps': k_e2e,
-               'how': 'ExecutorPool.submit_host: pinned host features+word_vecs -> async H2D -> '
-                      'C++ layout compile -> kernels -> async D2H scores, %d streams, every '
-                      'step, wall clock around the loop + final synchronize' % K}
+    e2e = None if args.no_e2e else bn.e2e(args.steps, 0.4)
 
-    # ---- roofline of the dominant kernel: per-launch CUDA events, separate pass of the same steps
-    roof, kernel_us = None, {}
-    if rank == 0:
-        pk = peaks()
-        def timed_pass():
-            ex.set_profiling(True)
-            acc, bytes_acc, flops_acc, n = {}, 0, 0, 0
-            for i in range(min(args.steps, 50)):
-                ex.forward_device(feats[i % P], wvs[i % P], toks[i % P], out=scores)
-                for name, us in ex.launch_times():
-                    acc.setdefault(name, []).append(us)
-                info = ex.last_step_info()
-                bytes_acc += info['kernel_bytes'][1]
-                flops_acc += info['kernel_flops'][1]
-                n += 1
-            ex.set_profiling(False)
-            return {k: float(np.mean(v)) for k, v in acc.items()}, bytes_acc / max(n, 1), \
-                flops_acc / max(n, 1)
+    # ---- strong scaling point: the SAME global batch split over the ranks
+    strong = None
+    if world > 1 and B % world == 0 and args.config == 'clevr':
+        Bs = B // world
+        sb = Bench(torch, dist, args, wl, layouts, Bs, rank, world, dev,
+                   streams=args.streams or None)
+        r = sb.timed(args.steps, args.warmup, 0.3, 1)
+        strong = {'value': r['value'], 'unit': UNIT, 'global_batch': B, 'batch_per_gpu': Bs,
+                  'ms_per_step': r['ms_per_step'], 'timed_region_s': r['timed_region_s'],
+                  'scaling': 'strong'}
+        sb.close()
 
-        def fractions(us, nbytes, nflops):
-            dur = us * 1e-6
-            gbs, tfs = nbytes / dur / 1e9, nflops / dur / 1e12
-            return gbs, tfs, gbs / pk['hbm_gbs'], tfs / (pk['bf16_tflops'] / 2)
-
-        # as run in the timed region (the pool's narrow grid when several batches are in flight)
-        kernel_us, nbytes, nflops = timed_pass()
-        proj = 'proj_umma_kernel'
-        if proj in kernel_us:
-            tf32_peak = pk['bf16_tflops'] / 2
-            gbs, tfs, hbm_frac, tc_frac = fractions(kernel_us[proj], nbytes, nflops)
-            bound = 'hbm' if hbm_frac >= tc_frac else 'tensor'
-            grid = min(PROJ_CTAS, 148) if PROJ_CTAS > 0 else 148
-            roof = {'kernel': proj, 'bound': bound,
-                    'achieved': gbs if bound == 'hbm' else tfs,
-                    'peak': pk['hbm_gbs'] if bound == 'hbm' else tf32_peak,
-                    'unit': 'GB/s' if bound == 'hbm' else 'TFLOP/s',
-                    'frac': max(hbm_frac, tc_frac), 'traffic': ncu_traffic(proj),
-                    'hbm_frac': hbm_frac, 'tensor_frac_of_tf32_peak': tc_frac,
-                    'avg_launch_us': kernel_us[proj],
-                    'algorithmic_bytes_per_launch': nbytes,
-                    'flops_per_launch': nflops,
-                    'peak_source': pk['source'] + '; TF32 peak taken as bf16 burst / 2',
-                    'share_of_step': kernel_us[proj] / max(sum(kernel_us.values()), 1e-9),
-                    'grid_ctas': grid,
-                    'frac_of_occupied_sms': max(hbm_frac, tc_frac) / (grid / 148.0),
-                    'note': 'as launched in the timed region: a persistent grid of %d CTAs (one '
-                            'per SM) so that the other SMs run the other in-flight batches; '
-                            'frac is against the WHOLE chip' % grid}
-            if PROJ_CTAS > 0:   # the same launch spread over every SM (lowest single-batch latency)
-                ex.set_proj_ctas(0)
-                kus2, nb2, nf2 = timed_pass()
-                ex.set_proj_ctas(PROJ_CTAS)
-                g2, t2, hf2, tf2 = fractions(kus2[proj], nb2, nf2)
-                roof['full_grid'] = {'grid_ctas': 148, 'avg_launch_us': kus2[proj],
-                                     'hbm_frac': hf2, 'tensor_frac_of_tf32_peak': tf2,
-                                     'frac': max(hf2, tf2)}
+    # ---- roofline of the dominant kernel + HBM fractions of the two latency kernels (rank 0)
+    roof = bn.roofline(pk) if rank == 0 else {}
+    if rank == 0 and 'roofline' in roof:
+        roof['roofline']['grid_ctas'] = pool.proj_ctas if pool.proj_ctas > 0 else 148
 
     # ---- config 3: policy-search train step (fwd + bwd + ONE NCCL all-reduce + clip + Adam),
     #      T=10 as in exp_clevr/train_clevr_rl_gt_layout.py; reported beside the eval headline
     train = None
-    if not args.no_train:
+    if args.config == 'clevr' and not args.no_train:
         from n2nmn_b200.trainer import ModuleNetTrainer
-        T_TRAIN = 10
-        tr_ex = LayoutExecutor('clevr', feats[0], wvs[0][:T_TRAIN].contiguous(), C, asm,
-                               weights=weights, max_batch=B, max_T=T_TRAIN)
+        T_TRAIN, C, P = 10, wl['C'], bn.P
+        tr_ex = LayoutExecutor('clevr', bn.feats[0], bn.wvs[0][:T_TRAIN].contiguous(), C, bn.asm,
+                               weights=bn.weights, max_batch=B, max_T=T_TRAIN)
         tr = ModuleNetTrainer(tr_ex)
-        ttok = [np.ascontiguousarray(synth.expert_mix_tokens(asm, B, T_TRAIN)[
+        ttok = [np.ascontiguousarray(synth.expert_mix_tokens(bn.asm, B, T_TRAIN)[
             :, np.random.RandomState(7 + i).permutation(B)]) for i in range(P)]
-        twv = [w[:T_TRAIN].contiguous() for w in wvs]
+        twv = [w[:T_TRAIN].contiguous() for w in bn.wvs]
         tlab = [np.random.RandomState(11 + i).randint(0, C, size=B) for i in range(P)]
         lsp = torch.full((B,), -2.0, device=dev)
         for i in range(5):
-            tr.train_step(feats[i % P], twv[i % P], ttok[i % P], tlab[i % P], log_seq_prob=lsp)
-        k_tr = max(10, min(args.steps, 50))
-        barrier()
+            tr.train_step(bn.feats[i % P], twv[i % P], ttok[i % P], tlab[i % P], log_seq_prob=lsp)
+        k_tr = max(50, min(args.steps, 200))
+        bn.barrier()
         t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0e.record()
         for i in range(k_tr):
-            out = tr.train_step(feats[i % P], twv[i % P], ttok[i % P], tlab[i % P],
+            out = tr.train_step(bn.feats[i % P], twv[i % P], ttok[i % P], tlab[i % P],
                                 log_seq_prob=lsp)
         t1e.record()
-        barrier()
-        tms = torch.tensor([t0e.elapsed_time(t1e)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        train = {'questions_per_sec': world * B * k_tr / (float(tms.item()) * 1e-3),
-                 'ms_per_step': float(tms.item()) / k_tr, 'steps': k_tr, 'global_batch': B * world,
-                 'T_decoder': T_TRAIN, 'last_avg_sample_loss': out['avg_sample_loss'],
+        bn.barrier()
+        tms = bn.allmax(t0e.elapsed_time(t1e))
+        train = {'questions_per_sec': world * B * k_tr / (tms * 1e-3),
+                 'ms_per_step': tms / k_tr, 'steps': k_tr, 'global_batch': B * world,
+                 'T_decoder': T_TRAIN, 'last_avg_sample_loss': float(out['avg_sample_loss']),
                  'what': 'fwd + bwd + all-reduce(flat grads, %d floats) + per-tensor clip + Adam '
                          '+ weight re-pack' % (tr.flat_size + 1)}
+        del tr, tr_ex
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        f0, w0 = feats[0].cpu().numpy(), wvs[0].cpu().numpy()
-        qps, nb, el, threads = cpu_reference_qps(f0, w0, weights, toks[:4], args.cpu_seconds)
-        cpu = {'value': qps, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-               'host_cpus': os.cpu_count(),
-               'sample': '%d batches of %d questions in %.1f s (oracle/nmn_oracle.py: numpy+OpenBLAS '
-                         'fp32 depth-batched restatement, Assembler.assemble included)' % (nb, B, el)}
+        cpu = bn.cpu_baseline(args.cpu_seconds)
+
+    info = ex.last_step_info()
+    pool_cfg = {'streams': K, 'host_threads': K, 'tree_cluster_ctas': pool.tree_cluster,
+                'proj_grid_ctas': pool.proj_ctas if pool.proj_ctas > 0 else 148}
+
+    # ---- the other BASELINE.json workloads at their real sizes (N=1 only): q/s, roofline, CPU port
+    others = None
+    if world == 1 and args.config == 'clevr' and layouts == 'expert' and not args.no_other_configs:
+        others = {}
+        bn.close()
+        for name in ('shapes', 'vqa514', 'vqa2050', 'stress'):
+            w2 = WORKLOADS[name]
+            try:
+                ob = Bench(torch, dist, args, w2, w2['layouts'], w2['B'], rank, world, dev,
+                           streams=4, device_synth=(name != 'shapes'))
+                r = ob.timed(min(args.steps, 40), 8, 0.3, 1)
+                entry = {'workload': workload_title(w2, w2['layouts']), 'value': r['value'],
+                         'unit': UNIT, 'ms_per_step': r['ms_per_step'],
+                         'timed_region_s': r['timed_region_s'], 'repeats': r['repeats'],
+                         'streams': ob.K, 'resident_batches': ob.P,
+                         'cache': cache_note(ob)}
+                entry.update(ob.roofline(pk))
+                oi = ob.ex.last_step_info()
+                entry['nodes_per_batch'] = oi['num_nodes']
+                entry['max_depth'] = oi['max_depth']
+                if not args.no_cpu_baseline:
+                    entry['cpu_baseline'] = ob.cpu_baseline(3.0)
+                others[name] = entry
+                ob.close()
+                del ob
+            except Exception as e:   # one workload failing must not lose the headline line
+                others[name] = {'error': repr(e)}
 
     if rank == 0:
-        info = ex.last_step_info()
         line = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': ms_max / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32 (fp32 in/out, fp32 accumulate)',
-            'data': 'synthetic',
-            'config': {'workload': 'CLEVR gt-layout eval, batch=%d/GPU, 10x15x512 pool5, %s '
-                                   'layouts depth<=12, T=%d' % (B, args.layouts, T_DEC),
-                       'global_batch': B * world, 'parallelism': 'dp%d (question shards, no '
-                       'collective)' % world,
-                       'cache': 'inputs larger than L2: %d distinct resident batches (%.0f MB) '
-                                'walked round-robin' % (P, P * B * H * W * D * 4 / 1e6),
-                       'executor': 'wave' if args.wave else 'tree',
-                       'streams': K, 'host_threads': K, 'tree_cluster_ctas': TREE_CLUSTER,
-                       'proj_grid_ctas': PROJ_CTAS if PROJ_CTAS > 0 else 148,
-                       'nodes_per_batch': info['num_nodes'], 'max_depth': info['max_depth']},
+            'metric': wl['metric'], 'value': head['value'], 'unit': UNIT, 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': head['ms_per_step'],
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'tf32 (fp32 in/out, fp32 accumulate)', 'data': 'synthetic',
+            'repeats': head['repeats'], 'timed_steps': head['timed_steps'],
+            'timed_region_s': head['timed_region_s'], 'trials': args.trials,
+            'trial_values': head['trial_values'],
+            'config': dict({'workload': workload_title(wl, layouts), 'global_batch': B * world,
+                            'parallelism': 'dp%d (question shards, no collective)' % world,
+                            'cache': cache_note(bn),
+                            'executor': 'wave' if args.wave else 'tree',
+                            'nodes_per_batch': info['num_nodes'], 'max_depth': info['max_depth']},
+                           **pool_cfg),
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
-            'host_enqueue_ms_per_step': host_ms / args.steps, 'host_numa': numa,
-            'roofline': roof, 'cpu_baseline': cpu, 'kernel_us': kernel_us, 'train_step': train,
-            'other_layout_sets': other_sets,
+            'host_enqueue_ms_per_step': head['host_enqueue_ms_per_step'], 'host_numa': numa,
+            'roofline': roof.get('roofline'), 'roofline_text': roof.get('roofline_text'),
+            'roofline_tree': roof.get('roofline_tree'), 'kernel_us': roof.get('kernel_us'),
+            'cpu_baseline': cpu, 'train_step': train, 'other_layout_sets': other_sets,
+            'strong_scaling': strong, 'other_configs': others,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cache_note(b):
+    tot = b.P * b.batch_bytes / 1e6
+    return 'inputs larger than L2: %d distinct resident batches (%.0f MB) walked round-robin' % (
+        b.P, tot)
 
 
 if __name__ == '__main__':

@@ -128,6 +128,10 @@ int n2nmn_module_fwd(n2nmn_ctx* ctx, int op, const float* in0_dev, const float* 
                      const int32_t* time_idx_host, const int32_t* batch_idx_host, int n,
                      float* out_dev, void* stream);
 
+/* `Modules.SceneModule(time_idx, batch_idx, pos_val)` with an arbitrary constant
+ * (models_clevr/nmn3_modules.py:60-72; n2nmn_module_fwd(N2NMN_OP_SCENE) uses the default 3). */
+int n2nmn_scene_fwd(n2nmn_ctx* ctx, int n, float pos_val, float* out_dev, void* stream);
+
 /* Replaces `Assembler.assemble` + `td.Compiler.build_feed_dict`
  * (models_clevr/nmn3_assembler.py:153-222, models_clevr/nmn3_model.py:146-159): parses the
  * Reverse-Polish layout tokens [T,N] (host int32, time-major) with the assembler's stack
@@ -222,6 +226,11 @@ int n2nmn_pool_size(const n2nmn_pool* pool);
 int n2nmn_pool_submit(n2nmn_pool* pool, int slot, const float* feat, const float* word_vecs,
                       const int32_t* tokens_host, int T, int N, float* scores,
                       uint8_t* validity_out, int host_io);
+/* n batches of identical shape in one call (arrays of n pointers; validity_out may be NULL),
+ * dealt to the workers round-robin. Saves the per-batch cost of crossing the FFI. */
+int n2nmn_pool_submit_many(n2nmn_pool* pool, int n, const float* const* feat,
+                           const float* const* word_vecs, const int32_t* const* tokens_host, int T,
+                           int N, float* const* scores, uint8_t* const* validity_out, int host_io);
 int n2nmn_pool_wait(n2nmn_pool* pool);
 const char* n2nmn_pool_last_error(void);
 

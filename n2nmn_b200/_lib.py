@@ -44,6 +44,7 @@ SIGNATURES = {
     'n2nmn_set_weight': (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int, _P]),
     'n2nmn_bind_inputs': (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),
     'n2nmn_module_fwd': (C.c_int, [_P, C.c_int, _P, _P, _I32P, _I32P, C.c_int, _P, _P]),
+    'n2nmn_scene_fwd': (C.c_int, [_P, C.c_int, C.c_float, _P, _P]),
     'n2nmn_compile_schedule': (C.c_int, [_P, _I32P, C.c_int, C.c_int, _I32P, C.c_int,
                                          C.POINTER(C.c_uint8), C.POINTER(_P)]),
     'n2nmn_compile_schedule_host': (C.c_int, [C.POINTER(Config), _I32P, C.c_int, C.c_int, _I32P,
@@ -67,6 +68,8 @@ SIGNATURES = {
     'n2nmn_pool_destroy': (C.c_int, [_P]),
     'n2nmn_pool_size': (C.c_int, [_P]),
     'n2nmn_pool_submit': (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_int]),
+    'n2nmn_pool_submit_many': (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P,
+                                         C.c_int]),
     'n2nmn_pool_wait': (C.c_int, [_P]),
     'n2nmn_pool_last_error': (C.c_char_p, []),
     'n2nmn_flat_size': (C.c_int64, [_P]),

@@ -885,9 +885,26 @@ int n2nmn_run_schedule(n2nmn_ctx* c, n2nmn_sched* s, float* scores, float* att_a
                     att_arena != nullptr);
 }
 
+namespace {
+int module_fwd_impl(n2nmn_ctx* c, int op, const float* in0, const float* in1,
+                    const int32_t* t_idx, const int32_t* b_idx, int n, float* out, void* stream,
+                    float scene_val);
+}
+
 int n2nmn_module_fwd(n2nmn_ctx* c, int op, const float* in0, const float* in1,
                      const int32_t* t_idx, const int32_t* b_idx, int n, float* out,
                      void* stream) {
+  return module_fwd_impl(c, op, in0, in1, t_idx, b_idx, n, out, stream, 3.0f);
+}
+
+int n2nmn_scene_fwd(n2nmn_ctx* c, int n, float pos_val, float* out, void* stream) {
+  return module_fwd_impl(c, OP_SCENE, nullptr, nullptr, nullptr, nullptr, n, out, stream, pos_val);
+}
+
+namespace {
+int module_fwd_impl(n2nmn_ctx* c, int op, const float* in0, const float* in1,
+                    const int32_t* t_idx, const int32_t* b_idx, int n, float* out, void* stream,
+                    float scene_val) {
   if (!c) return fail(N2NMN_ERR_ARG, "null context");
   if (op < 0 || op >= NUM_OPS) return fail(N2NMN_ERR_ARG, "bad opcode");
   if (n == 0) return 0;   // TF Fold's zero-size batches: nothing to do
@@ -909,7 +926,8 @@ int n2nmn_module_fwd(n2nmn_ctx* c, int op, const float* in0, const float* in1,
   S.reset();
   S.N = c->N; S.T = c->T;
   S.nodes.resize(n); S.depth.assign(n, 1); S.q_ptr.resize(n + 1);
-  const int scene_bits = [] { float v = 3.0f; int b; std::memcpy(&b, &v, 4); return b; }();
+  int scene_bits;
+  std::memcpy(&scene_bits, &scene_val, 4);
   for (int i = 0; i < n; ++i) {
     NodeRec& r = S.nodes[i];
     r.op = op;
@@ -941,6 +959,7 @@ int n2nmn_module_fwd(n2nmn_ctx* c, int op, const float* in0, const float* in1,
                              cudaMemcpyDeviceToDevice, st));
   return 0;
 }
+}  // namespace
 
 int n2nmn_forward_tokens(n2nmn_ctx* c, const float* feat_dev, const float* wv_dev,
                          const int32_t* tokens, int T, int N, const int32_t* vocab_ops,
@@ -1041,6 +1060,11 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
     return fail(N2NMN_ERR_ARG, "null argument");
   if (c->cfg.flags & N2NMN_FLAG_WAVE_EXECUTOR)
     return fail(N2NMN_ERR_ARG, "training uses the tree executor");
+  // The backward walk is instantiated for the 3x3 / 5x5 Transform families and sizes its channel
+  // loops for Mp <= 512 (backward.cuh); the VQA family (no conv Transform, Mp = 1024) has no
+  // backward path yet.
+  if (c->cfg.family == N2NMN_VQA || c->Mp > 512)
+    return fail(N2NMN_ERR_ARG, "n2nmn_train_backward: the VQA family / map_dim > 512 is not supported");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (int rc = n2nmn_bind_inputs(c, feat_dev, wv_dev, N, T, stream)) return rc;
   if (int rc = check_ready(c)) return rc;

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <deque>
@@ -40,17 +41,32 @@ struct Worker {
   std::mutex mu;
   std::condition_variable cv;
   std::deque<Job> q;
+  std::atomic<int> qsize{0};   // mirrors q.size() so that an idle worker can poll without the lock
   bool stop = false;
 };
+
+// An idle worker polls its queue for this long before it sleeps on the condition variable: a
+// step is ~10 us of host work, a futex wake-up is 50-100 us, so a sleeping worker turns a short
+// burst of submissions (the driver's --steps 20) into a measurement of wake-up latency.
+constexpr int kSpinMicros = 300;
+
+inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#elif defined(__aarch64__)
+  asm volatile("yield" ::: "memory");
+#endif
+}
 
 }  // namespace
 
 struct n2nmn_pool {
   std::vector<Worker*> workers;
   std::vector<int32_t> vocab;
+  uint64_t next = 0;          // round-robin cursor of n2nmn_pool_submit_many
   std::mutex done_mu;
   std::condition_variable done_cv;
-  int64_t pending = 0;        // jobs queued or running
+  std::atomic<int64_t> pending{0};   // jobs queued or running
   int err_code = 0;           // first failure since the last wait
   std::string err_msg;
 };
@@ -74,18 +90,25 @@ void run_job(n2nmn_pool* p, Worker* w, Job& j) {
     p->err_code = rc;
     p->err_msg = n2nmn_last_error();
   }
-  if (--p->pending == 0) p->done_cv.notify_all();
+  if (p->pending.fetch_sub(1) == 1) p->done_cv.notify_all();
 }
 
 void worker_main(n2nmn_pool* p, Worker* w) {
   for (;;) {
     Job j;
+    if (w->qsize.load(std::memory_order_acquire) == 0) {   // stay hot for a while
+      const auto t_end = std::chrono::steady_clock::now() + std::chrono::microseconds(kSpinMicros);
+      while (w->qsize.load(std::memory_order_acquire) == 0 &&
+             std::chrono::steady_clock::now() < t_end)
+        for (int i = 0; i < 64; ++i) cpu_relax();
+    }
     {
       std::unique_lock<std::mutex> lk(w->mu);
       w->cv.wait(lk, [&] { return w->stop || !w->q.empty(); });
       if (w->q.empty()) return;   // stop requested and nothing left
       j = std::move(w->q.front());
       w->q.pop_front();
+      w->qsize.store((int)w->q.size(), std::memory_order_release);
     }
     run_job(p, w, j);
   }
@@ -147,23 +170,43 @@ int n2nmn_pool_submit(n2nmn_pool* p, int slot, const float* feat, const float* w
   j.feat = feat; j.wv = wv; j.T = T; j.N = N; j.scores = scores; j.validity = validity_out;
   j.host_io = host_io;
   j.tokens.assign(tokens, tokens + (size_t)T * N);
-  {
-    std::lock_guard<std::mutex> lk(p->done_mu);
-    ++p->pending;
-  }
+  p->pending.fetch_add(1);
   Worker* w = p->workers[slot];
   {
     std::lock_guard<std::mutex> lk(w->mu);
     w->q.push_back(std::move(j));
+    w->qsize.store((int)w->q.size(), std::memory_order_release);
   }
   w->cv.notify_one();
   return 0;
 }
 
+int n2nmn_pool_submit_many(n2nmn_pool* p, int n, const float* const* feat,
+                           const float* const* wv, const int32_t* const* tokens, int T, int N,
+                           float* const* scores, uint8_t* const* validity_out, int host_io) {
+  if (!p || n < 0 || (n > 0 && (!feat || !wv || !tokens || !scores))) {
+    g_pool_err = "n2nmn_pool_submit_many: bad argument";
+    return N2NMN_ERR_ARG;
+  }
+  const int K = (int)p->workers.size();
+  for (int i = 0; i < n; ++i) {
+    const int slot = (int)(p->next++ % (uint64_t)K);
+    if (int rc = n2nmn_pool_submit(p, slot, feat[i], wv[i], tokens[i], T, N, scores[i],
+                                   validity_out ? validity_out[i] : nullptr, host_io))
+      return rc;
+  }
+  return 0;
+}
+
 int n2nmn_pool_wait(n2nmn_pool* p) {
   if (!p) return 0;
+  {   // the workers are usually a few microseconds from done: poll before sleeping
+    const auto t_end = std::chrono::steady_clock::now() + std::chrono::microseconds(kSpinMicros);
+    while (p->pending.load() != 0 && std::chrono::steady_clock::now() < t_end)
+      for (int i = 0; i < 64; ++i) cpu_relax();
+  }
   std::unique_lock<std::mutex> lk(p->done_mu);
-  p->done_cv.wait(lk, [&] { return p->pending == 0; });
+  p->done_cv.wait(lk, [&] { return p->pending.load() == 0; });
   const int rc = p->err_code;
   if (rc != 0) g_pool_err = p->err_msg;
   p->err_code = 0;

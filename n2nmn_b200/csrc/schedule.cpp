@@ -44,7 +44,10 @@ int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
   S.depth.clear();
   S.nodes.reserve((size_t)N * 8);
   S.depth.reserve((size_t)N * 8);
-  int stack[64];   // node ids of the question's open attention / answer values
+  // node ids of the question's open attention / answer values (at most one push per token)
+  static thread_local std::vector<int> stack_buf;
+  stack_buf.resize((size_t)T + 1);
+  int* stack = stack_buf.data();
 
   for (int n = 0; n < N; ++n) {
     const int32_t* col = tq.data() + (size_t)n * T;
@@ -63,7 +66,7 @@ int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
       if (op < 0) break;                       // <eos>
       if (op >= NUM_OPS) { ok = false; break; }
       const int ar = kArity[op];
-      if (sp < ar || sp - ar >= 63) { ok = false; break; }   // not enough input
+      if (sp < ar) { ok = false; break; }   // not enough input
       NodeRec nd;
       nd.op = op; nd.t = t; nd.b = n;
       nd.in0 = nd.in1 = -1;

@@ -88,6 +88,10 @@ class LayoutExecutor:
         self.num_choices = self.modules.num_choices
         self._lib = self.modules._lib
         fam = cfgmod.FAMILIES[family]
+        unknown = [n for n in assembler.module_names if n != '<eos>' and n not in fam.token_ops]
+        if unknown:   # the reference would raise KeyError when such a token is executed
+            raise ValueError('layout vocabulary names %r are not modules of the %r family'
+                             % (unknown, family))
         self.vocab_ops = np.array([fam.token_ops.get(n, -1) for n in assembler.module_names],
                                   np.int32)
         self._vocab_ptr = self.vocab_ops.ctypes.data
@@ -361,6 +365,10 @@ class ExecutorPool:
             word_vecs.is_contiguous() and word_vecs.dtype == torch.float32
         valid = self._submit(k, image_feat_grid.data_ptr(), word_vecs.data_ptr(), tok,
                              out.data_ptr(), 0)
+        # the worker enqueues later, on the slot's stream: keep the buffers alive until end(),
+        # which orders the caller's stream after the pool's streams (so a free after end() is
+        # stream-ordered after the last use)
+        self._keep.append((image_feat_grid, word_vecs, out))
         return out, valid, self.streams[k]
 
     def submit_host(self, feat_host, word_vecs_host, layout_tokens, scores_host):
@@ -375,12 +383,45 @@ class ExecutorPool:
             assert (not t.is_cuda) and t.is_contiguous() and t.dtype == torch.float32
         valid = self._submit(k, feat_host.data_ptr(), word_vecs_host.data_ptr(), tok,
                              scores_host.data_ptr(), 1)
+        self._keep.append((feat_host, word_vecs_host, scores_host))
         return scores_host, valid, self.streams[k]
 
     def forward_many(self, feats, word_vecs, tokens, outs):
         """Queue a list of independent batches (item i -> context i % K); returns the validity
         arrays. Call begin() before and end() after, like submit()."""
         return [self.submit(f, w, t, out=o)[1] for f, w, t, o in zip(feats, word_vecs, tokens, outs)]
+
+    def make_block(self, feats, word_vecs, tokens, outs, host_io=False):
+        """Pre-marshal a list of same-shape batches for submit_block(): pointer arrays for ONE
+        FFI call (n2nmn_pool_submit_many). The tensors/arrays must stay alive and unchanged for as
+        long as the block is used; the block keeps references. `outs` device tensors (host_io:
+        pinned host tensors; then feats / word_vecs are pinned host tensors too)."""
+        toks = [self._tokens(t) for t in tokens]
+        n = len(toks)
+        T, N = toks[0].shape
+        assert all(t.shape == (T, N) for t in toks)
+        for f, w, o in zip(feats, word_vecs, outs):
+            for t in (f, w, o):
+                assert t.is_contiguous() and t.dtype == torch.float32 and t.is_cuda != bool(host_io)
+        valid = np.empty((n, N), np.uint8)
+        arr = lambda ptrs: (C.c_void_p * n)(*ptrs)
+        return {'n': n, 'T': T, 'N': N, 'host_io': int(bool(host_io)), 'valid': valid,
+                'feat': arr([f.data_ptr() for f in feats]),
+                'wv': arr([w.data_ptr() for w in word_vecs]),
+                'tok': arr([t.ctypes.data for t in toks]),
+                'out': arr([o.data_ptr() for o in outs]),
+                'val': arr([valid[i].ctypes.data for i in range(n)]),
+                'keep': (list(feats), list(word_vecs), toks, list(outs))}
+
+    def submit_block(self, block):
+        """Queue every batch of a make_block() result (one step each). Between begin() / end()."""
+        rc = self._lib.n2nmn_pool_submit_many(self._h, block['n'], block['feat'], block['wv'],
+                                              block['tok'], block['T'], block['N'], block['out'],
+                                              block['val'], block['host_io'])
+        if rc < 0:
+            raise _lib.N2NMNError('n2nmn_pool_submit_many failed: %s' %
+                                  (self._lib.n2nmn_pool_last_error() or b'').decode())
+        return block['valid']
 
     def end(self):
         """Wait until the workers have enqueued everything submitted so far, then make the current

@@ -112,7 +112,10 @@ class ModulesBase:
             self._weights[name] = t   # keep the source alive until the async copy has run
 
     def get_weights(self):
-        return dict(self._weights)
+        """Current weights by TF name. After optimiser steps (ModuleNetTrainer) these are views of
+        the trainer's flat buffer, i.e. the values the context was last re-packed from."""
+        src = getattr(self, '_weights_source', None)
+        return dict(src()) if src is not None else dict(self._weights)
 
     def bind(self, image_feat_grid, word_vecs):
         """Re-point the context at a new batch (the reference re-feeds its placeholders)."""
@@ -164,9 +167,12 @@ class ModulesCLEVR(ModulesBase):
     family = 'clevr'
 
     def SceneModule(self, time_idx, batch_idx, pos_val=3, scope='SceneModule', reuse=True):
-        if pos_val != 3:
-            raise NotImplementedError('the reference only ever uses pos_val=3')
-        return self._run(cfgmod.OP_SCENE, [], time_idx, batch_idx)
+        n = len(_as_host_i32(time_idx))
+        out = torch.empty((n, self.H, self.W, 1), dtype=torch.float32, device=self.device)
+        if n:
+            _lib.check(self._lib.n2nmn_scene_fwd(self._h, n, C.c_float(float(pos_val)),
+                                                 C.c_void_p(out.data_ptr()), self._stream()))
+        return out
 
     def FilterModule(self, input_0, time_idx, batch_idx, map_dim=250, scope='FilterModule',
                      reuse=True):

@@ -60,6 +60,9 @@ class ModuleNetTrainer:
         for name, t in self.m.get_weights().items():
             off, cnt, shp = self.layout[name]
             self.w[off:off + cnt] = t.reshape(-1)
+        # the context is re-packed from self.w after every step: hand out those values, not the
+        # tensors cached by set_weights() at construction time (replicas, checkpoints)
+        self.m._weights_source = self.weights
         self._loss = torch.zeros(1 + self.m.max_batch, dtype=torch.float32, device=dev)
         self._decay_mask = torch.zeros(self.flat_size, dtype=torch.float32, device=dev)
         for name, (off, cnt, _) in self.layout.items():

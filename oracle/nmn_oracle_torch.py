@@ -236,3 +236,41 @@ def adam_clip_step(weights, grads, state, lr=1e-4, beta1=0.9, beta2=0.999, eps=1
         state['m'][n], state['v'][n] = m, v
         out[n] = (np.asarray(w, np.float64) - lr_t * m / (np.sqrt(v) + eps)).astype(np.float32)
     return out
+
+
+def run_depth_batched(m, expr_list):
+    """TF-Fold-like dynamic batching with torch-CPU kernels (MKL / oneDNN, all cores), no autograd:
+    the same schedule as oracle/nmn_oracle.py::run_depth_batched (one module call per (depth,
+    module type) with leading dim n, gathers materialised). Timed by bench.py as the second CPU
+    port of the reference path; its forward is checked against the numpy oracle in
+    tests/test_oracle_torch.py."""
+    nodes = []   # (depth, module, t, b, child ids, question or -1)
+
+    def walk(e, q_root):
+        kids = [walk(e[k], -1) for k in ('input_0', 'input_1') if k in e]
+        depth = 1 + max([nodes[k][0] for k in kids], default=0)
+        nodes.append((depth, e['module'], e['time_idx'], e['batch_idx'], kids, q_root))
+        return len(nodes) - 1
+
+    for q, e in enumerate(expr_list):
+        if e['module'] != INVALID_EXPR:
+            walk(e, q)
+    with torch.no_grad():
+        scores = torch.zeros((len(expr_list), m.C), dtype=m.feat.dtype)
+        values = [None] * len(nodes)
+        max_depth = max([n[0] for n in nodes], default=0)
+        for d in range(1, max_depth + 1):
+            by_type = {}
+            for i, nd in enumerate(nodes):
+                if nd[0] == d:
+                    by_type.setdefault(nd[1], []).append(i)
+            for mod, ids in by_type.items():
+                arity = len(nodes[ids[0]][4])
+                ins = [torch.stack([values[nodes[i][4][k]] for i in ids]) for k in range(arity)]
+                out = getattr(m, _TOKEN_METHOD[mod])(*ins, [nodes[i][2] for i in ids],
+                                                     [nodes[i][3] for i in ids])
+                for j, i in enumerate(ids):
+                    values[i] = out[j]
+                    if nodes[i][5] >= 0:
+                        scores[nodes[i][5]] = out[j]
+    return scores.numpy()

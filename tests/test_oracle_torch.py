@@ -19,6 +19,8 @@ def test_torch_oracle_forward_matches_goldens(family):
     exprs, valid = asm.assemble(z['exec_tokens'])
     scores = ot.forward_scores(m, exprs).detach().numpy()
     np.testing.assert_allclose(scores, z['exec_scores'], rtol=0, atol=5e-5)
+    # the depth-batched torch executor (bench.py's second CPU port) gives the same rows
+    np.testing.assert_allclose(ot.run_depth_batched(m, exprs), z['exec_scores'], rtol=0, atol=5e-5)
 
 
 def test_tf_tie_rules_and_loss():
