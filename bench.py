@@ -73,6 +73,8 @@ def parse_args():
     ap.add_argument('--min-seconds', type=float, default=0.5, help='length of one timed region')
     ap.add_argument('--trials', type=int, default=3, help='timed regions; the median is reported')
     ap.add_argument('--cpu-seconds', type=float, default=10.0, help='cpu_baseline sample budget')
+    ap.add_argument('--ref-seconds', type=float, default=0.0,
+                    help='--impl reference: stop after this many seconds (0 = run all --steps)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--wave', action='store_true', help='depth-bucketed wave executor')
@@ -189,8 +191,10 @@ class ClockSampler:
 
 # =========================================================================== CPU arms (oracle)
 def _thread_candidates():
-    ncpu = os.cpu_count() or 1
-    return sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)})
+    # (one thread per hardware thread was measured pathological on the 128-cpu box: 5.8 s per
+    # batch with torch, 0.2-0.3 s with OpenBLAS, against 8-40 ms at 16-32 threads)
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    return sorted({min(ncpu, c) for c in (8, 16, 32, 64)})
 
 
 class CpuPort:
@@ -236,6 +240,7 @@ class CpuPort:
         for nt in _thread_candidates():
             self.set_threads(nt)
             self.step(tokens)
+            self.step(tokens)
             ts = []
             for _ in range(trials):
                 t0 = time.perf_counter()
@@ -271,10 +276,12 @@ def best_cpu_port(wl, feat, word_vecs, weights, toks, pick_seconds=6.0):
         try:
             p = CpuPort(kind, wl, feat, word_vecs, weights)
             p.pick_threads(toks[0], max_seconds=pick_seconds)
-            t0 = time.perf_counter()
-            for i in range(2):
+            for i in range(3):   # settle on the chosen thread count before timing
                 p.step(toks[i % len(toks)])
-            ms[kind] = {'ms_per_batch': round((time.perf_counter() - t0) * 500, 2),
+            t0 = time.perf_counter()
+            for i in range(4):
+                p.step(toks[i % len(toks)])
+            ms[kind] = {'ms_per_batch': round((time.perf_counter() - t0) * 250, 2),
                         'threads': p.threads, 'ms_by_threads': p.pick_log}
             ports.append(p)
         except Exception as e:   # threadpoolctl / torch missing: keep the other port
@@ -295,6 +302,10 @@ def run_reference_arm(args, rank, world):
     box's host cores, same workload/config strings as the b200 arm. Rank 0 only."""
     if rank != 0:
         return
+    try:   # all host cores, whatever the launcher (or a parent GPU arm bound to a NUMA node) set
+        os.sched_setaffinity(0, range(os.cpu_count()))
+    except Exception:
+        pass
     from n2nmn_b200 import synth, weights as wts
     from n2nmn_b200.assembler import Assembler
     wl = dict(WORKLOADS[args.config])
@@ -315,6 +326,9 @@ def run_reference_arm(args, rank, world):
         t1 = time.perf_counter()
         port.step(toks[i % 4])
         per.append(time.perf_counter() - t1)
+        if args.ref_seconds > 0 and time.perf_counter() - t0 > args.ref_seconds and i >= 1:
+            steps = i + 1      # bounded sample (big workloads: seconds per batch)
+            break
     el = time.perf_counter() - t0
     qps = steps * B / el
     line = {
@@ -457,6 +471,11 @@ class Bench:
         blocks = self.blocks(steps, toks)
         cal_ms, _ = self.region(blocks, max(1, len(blocks)))      # touches every resident batch
         per_block = cal_ms / max(1, len(blocks))
+        # the first estimate includes the pipeline fill of a short region: refine it on ~15 % of
+        # the target length before fixing the number of repetitions
+        R1 = int(max(1, math.ceil(0.15 * min_seconds * 1e3 / max(per_block, 1e-6))))
+        cal_ms, _ = self.region(blocks, R1)
+        per_block = cal_ms / R1
         R = int(max(1, math.ceil(min_seconds * 1e3 / max(per_block, 1e-6))))
         res = []
         for _ in range(trials):
@@ -573,15 +592,24 @@ class Bench:
                        'streams, every step; wall clock around the loop + final synchronize, '
                        'median of 3 regions' % self.K}
 
-    def cpu_baseline(self, budget_s):
-        f0, w0 = self.feats[0].cpu().numpy(), self.wvs[0].cpu().numpy()
-        port, ports_ms = best_cpu_port(self.wl, f0, w0, self.weights, self.toks[:4],
-                                       pick_seconds=min(6.0, budget_s))
-        qps, nb, el = port.measure(self.toks[:4], budget_s)
-        return {'value': qps, 'unit': UNIT, 'cores': port.threads, 'kind': 'port',
-                'host_cpus': os.cpu_count(), 'ports': ports_ms,
-                'sample': '%d batches of %d questions in %.1f s (%s)' % (nb, self.B, el,
-                                                                         port_desc(port))}
+    def cpu_baseline(self, budget_s, config):
+        """The reference arm (`bench.py --impl reference`) in a subprocess on a bounded sample:
+        the same code path and process conditions (all host cores, no CUDA context, no NUMA
+        binding) as the driver's own reference run, so the two numbers agree."""
+        cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--config',
+               config, '--steps', '200', '--warmup', '3', '--ref-seconds', str(budget_s),
+               '--batch', str(self.B)]
+        if config == 'clevr':
+            cmd += ['--layouts', self.layouts]
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+            line = json.loads(r.stdout.strip().splitlines()[-1])
+            cb = line['cpu_baseline']
+            cb['value'] = line['value']
+            cb['median_ms_per_step'] = line.get('median_ms_per_step')
+            return cb
+        except Exception as e:
+            return {'error': repr(e)}
 
     def close(self):
         self.pool = None
@@ -696,7 +724,7 @@ def main():
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = bn.cpu_baseline(args.cpu_seconds)
+        cpu = bn.cpu_baseline(args.cpu_seconds, args.config)
 
     info = ex.last_step_info()
     pool_cfg = {'streams': K, 'host_threads': K, 'tree_cluster_ctas': pool.tree_cluster,
@@ -723,7 +751,7 @@ def main():
                 entry['nodes_per_batch'] = oi['num_nodes']
                 entry['max_depth'] = oi['max_depth']
                 if not args.no_cpu_baseline:
-                    entry['cpu_baseline'] = ob.cpu_baseline(3.0)
+                    entry['cpu_baseline'] = ob.cpu_baseline(3.0, name)
                 others[name] = entry
                 ob.close()
                 del ob

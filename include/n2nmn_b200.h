@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define N2NMN_ABI_VERSION 1
+#define N2NMN_ABI_VERSION 2
 
 typedef struct n2nmn_ctx n2nmn_ctx;
 typedef struct n2nmn_sched n2nmn_sched;
@@ -91,6 +91,9 @@ typedef struct n2nmn_config {
   int32_t max_T;         /* capacity: decoder steps */
   int32_t device;        /* CUDA device ordinal */
   int32_t flags;         /* enum n2nmn_flags */
+  int32_t max_group;     /* capacity: independent batches (each <= max_batch questions) that one
+                          * n2nmn_forward_group call may evaluate with one set of launches;
+                          * 0 or 1 = none, at most 8. Workspaces scale with it. */
 } n2nmn_config;
 
 /* Replaces `Modules.__init__` (models_clevr/nmn3_modules.py:12-47): allocates the context,
@@ -192,6 +195,29 @@ int n2nmn_forward_tokens(n2nmn_ctx* ctx, const float* feat_dev, const float* wor
                          const int32_t* tokens_host, int T, int N, const int32_t* vocab_ops,
                          int num_vocab, float* scores_dev, uint8_t* validity_out, void* stream);
 
+/* n2nmn_forward_tokens for `num_batches` (<= cfg.max_group) INDEPENDENT batches of identical shape
+ * in one set of launches: batch i has its own feature grid feat_dev[i] [N,H,W,D], word vectors
+ * word_vecs_dev[i] [T,N,text_dim], layout tokens tokens_host[i] [T,N] and writes scores_dev[i]
+ * [N,num_choices] (validity_out may be NULL, or hold NULL entries). Results are those of
+ * num_batches separate n2nmn_forward_tokens calls; the point is that a batch of 64 CLEVR
+ * questions is ~4 us of tensor work, far too little to fill 148 SMs per launch, while the reference's
+ * eval loop (exp_clevr/eval_clevr.py:103-135) offers an endless stream of independent batches. */
+int n2nmn_forward_group(n2nmn_ctx* ctx, int num_batches, const float* const* feat_dev,
+                        const float* const* word_vecs_dev, const int32_t* const* tokens_host,
+                        int T, int N, const int32_t* vocab_ops, int num_vocab,
+                        float* const* scores_dev, uint8_t* const* validity_out, void* stream);
+/* The same with pinned HOST buffers (cf. n2nmn_forward_host_async): H2D copies, kernels and D2H
+ * copies are only enqueued on `stream`. */
+int n2nmn_forward_group_host_async(n2nmn_ctx* ctx, int num_batches,
+                                   const float* const* feat_host,
+                                   const float* const* word_vecs_host,
+                                   const int32_t* const* tokens_host, int T, int N,
+                                   const int32_t* vocab_ops, int num_vocab,
+                                   float* const* scores_host, uint8_t* const* validity_out,
+                                   void* stream);
+/* cfg.max_group as clamped by n2nmn_create. */
+int n2nmn_max_group(const n2nmn_ctx* ctx);
+
 /* Statistics of the batch compiled by the last n2nmn_forward_tokens / n2nmn_forward_host. */
 int n2nmn_last_step_info(const n2nmn_ctx* ctx, n2nmn_sched_info* info);
 
@@ -212,8 +238,10 @@ int n2nmn_forward_host_async(n2nmn_ctx* ctx, const float* feat_host, const float
 
 /* ---- several batches in flight -------------------------------------------------------------------
  * One worker thread per (context, stream) pair; n2nmn_pool_submit copies the token matrix into a
- * job for worker `slot` and returns, the worker runs n2nmn_forward_tokens (host_io == 0: device
- * pointers) or n2nmn_forward_host_async (host_io != 0: pinned host pointers) on its stream.
+ * job for worker `slot` and returns. A worker takes up to n2nmn_max_group(ctx) queued jobs of
+ * identical shape at a time and runs them as ONE n2nmn_forward_group (host_io == 0: device
+ * pointers) or n2nmn_forward_group_host_async (host_io != 0: pinned host pointers) on its stream:
+ * dynamic batching of whatever the caller has queued, never waiting for more.
  * n2nmn_pool_wait blocks until every submitted batch has been ENQUEUED (not finished) and returns
  * the first error; `validity_out` arrays are valid after it. The contexts must outlive the pool
  * and must not be used directly while jobs are pending. No reference counterpart (the reference
@@ -232,6 +260,8 @@ int n2nmn_pool_submit_many(n2nmn_pool* pool, int n, const float* const* feat,
                            const float* const* word_vecs, const int32_t* const* tokens_host, int T,
                            int N, float* const* scores, uint8_t* const* validity_out, int host_io);
 int n2nmn_pool_wait(n2nmn_pool* pool);
+/* How the workers batched the jobs so far: number of n2nmn_forward_group calls and of jobs. */
+int n2nmn_pool_group_stats(const n2nmn_pool* pool, int64_t* groups, int64_t* jobs);
 const char* n2nmn_pool_last_error(void);
 
 

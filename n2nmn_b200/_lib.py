@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libn2nmn_b200.so')
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 FLAG_PROJ_FP32_SIMT = 1
 FLAG_WAVE_EXECUTOR = 2
 FAMILY_ID = {'clevr': 0, 'shapes': 1, 'vqa': 2}
@@ -20,7 +20,7 @@ FAMILY_ID = {'clevr': 0, 'shapes': 1, 'vqa': 2}
 class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         'abi_version', 'family', 'H', 'W', 'D', 'text_dim', 'map_dim', 'kernel_size',
-        'num_choices', 'max_batch', 'max_T', 'device', 'flags')]
+        'num_choices', 'max_batch', 'max_T', 'device', 'flags', 'max_group')]
 
 
 class SchedInfo(C.Structure):
@@ -58,6 +58,11 @@ SIGNATURES = {
     'n2nmn_sched_get_nodes': (C.c_int, [_P, _I32P, C.c_int]),
     'n2nmn_run_schedule': (C.c_int, [_P, _P, _P, _P, _P]),
     'n2nmn_forward_tokens': (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P]),
+    'n2nmn_forward_group': (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, C.c_int, _P,
+                                      _P, _P]),
+    'n2nmn_forward_group_host_async': (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P,
+                                                 C.c_int, _P, _P, _P]),
+    'n2nmn_max_group': (C.c_int, [_P]),
     'n2nmn_last_step_info': (C.c_int, [_P, C.POINTER(SchedInfo)]),
     'n2nmn_forward_host': (C.c_int, [_P, _P, _P, _I32P, C.c_int, C.c_int, _I32P, C.c_int, _P,
                                      C.POINTER(C.c_uint8), _P]),
@@ -71,6 +76,7 @@ SIGNATURES = {
     'n2nmn_pool_submit_many': (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P,
                                          C.c_int]),
     'n2nmn_pool_wait': (C.c_int, [_P]),
+    'n2nmn_pool_group_stats': (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     'n2nmn_pool_last_error': (C.c_char_p, []),
     'n2nmn_flat_size': (C.c_int64, [_P]),
     'n2nmn_flat_offset': (C.c_int, [_P, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

@@ -88,6 +88,8 @@ struct n2nmn_ctx {
   n2nmn_config cfg;
   int device = 0, num_sms = 0;
   int HW = 0, Dk = 0, Kp = 0, Mp = 0;
+  int G = 1;                   // segments (batches) one set of launches may cover
+  int QB = 0;                  // question capacity of one launch: G * max_batch
   SchedShape shp;
   DevModel md;
   std::vector<Variable> vars;
@@ -289,8 +291,8 @@ void prof_mark(n2nmn_ctx* c, const char* name, cudaStream_t st) {
 }
 
 // Uploads (if needed) and launches everything for one compiled batch.
-int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaStream_t st,
-               bool force_wave = false, bool write_arena = false) {
+int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* arena,
+               cudaStream_t st, bool force_wave = false, bool write_arena = false) {
   const bool use_wave = (c->cfg.flags & N2NMN_FLAG_WAVE_EXECUTOR) || force_wave ||
                         sc->hs.max_stack > c->stack_cap;
   if (use_wave) build_waves(&sc->hs);
@@ -359,11 +361,13 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaS
     p.work = reinterpret_cast<const ProjWork*>(d + o.work);
     p.num_work = (int)S.work.size();
     p.total_rows = c->md.N * c->HW;
+    p.num_seg = c->md.num_seg;
+    p.seg_images = c->md.N;
     p.n_tiles = c->Mp / 256;
     p.k_blocks = (c->Dk + kBK - 1) / kBK;
     p.HW = c->HW; p.M = c->cfg.map_dim; p.Mp = c->Mp; p.Dk = c->Dk;
     p.feat_pitch = c->md.feat_pitch;
-    p.feat = c->md.feat;
+    for (int s = 0; s < kMaxSeg; ++s) p.feat_seg[s] = c->md.feat_seg[s];
     for (int s = 0; s < NUM_PROJ_SETS; ++s) {
       p.bias[s] = c->proj_bias[s];
       p.w_orig[s] = c->md.proj_w[s];
@@ -377,16 +381,17 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaS
     p.mslot = reinterpret_cast<const int32_t*>(d + o.mslot);
     p.num_images = (int)(S.mslot.size() / NUM_PROJ_SETS);
     p.mbuf = c->mbuf;
-    const int grid = std::min(p.num_work, c->proj_max_ctas > 0 ? std::min(c->proj_max_ctas, c->num_sms)
-                                                              : c->num_sms);
+    // persistent grid of CTA pairs (clusters of 2): pair i walks work items i, i + pairs, ...
+    const int max_ctas = c->proj_max_ctas > 0 ? std::min(c->proj_max_ctas, c->num_sms) : c->num_sms;
+    const int pairs = std::max(1, std::min(p.num_work, max_ctas / 2));
     if (c->cfg.flags & N2NMN_FLAG_PROJ_FP32_SIMT) {
       const size_t smem = (size_t)(kSimtRows * kSimtKChunk + kSimtRows * c->Mp) * sizeof(float);
-      proj_simt_kernel<<<p.num_work, 256, smem, st>>>(p);
+      proj_simt_kernel<<<2 * p.num_work, 256, smem, st>>>(p);
       prof_mark(c, "proj_simt_kernel", st);
     } else {
       cudaLaunchConfig_t lc;
       std::memset(&lc, 0, sizeof(lc));
-      lc.gridDim = dim3((unsigned)grid);
+      lc.gridDim = dim3((unsigned)(2 * pairs));
       lc.blockDim = dim3(kProjThreads);
       lc.dynamicSmemBytes = kProjSmemBytes;
       lc.stream = st;
@@ -402,11 +407,19 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* scores, float* arena, cudaS
   }
   // ---- K3 node evaluation
   NodeCtx nc;
-  nc.md = c->md; nc.tb = c->tb; nc.arena = arena; nc.scores = scores; nc.mbuf = c->mbuf;
+  nc.md = c->md; nc.tb = c->tb; nc.arena = arena; nc.scores = scores_seg[0]; nc.mbuf = c->mbuf;
   const int NQ = (int)S.q_ptr.size() - 1;
+  // several segments: question q writes row q % N of segment q / N; one segment: row q (the
+  // per-module entry point numbers its call rows beyond the bound batch size)
+  const int nseg = std::max(1, S.num_seg);
+  nc.score_rows = nseg > 1 ? S.N : (1 << 30);
+  for (int s = 0; s < kMaxSeg; ++s) nc.scores_seg[s] = scores_seg[s < nseg ? s : 0];
   const bool ks3 = (c->cfg.kernel_size != 5);
   if (use_wave) {
-    CUDA_TRY(cudaMemsetAsync(scores, 0, (size_t)NQ * c->cfg.num_choices * sizeof(float), st));
+    for (int s = 0; s < nseg; ++s)
+      CUDA_TRY(cudaMemsetAsync(scores_seg[s], 0,
+                               (size_t)(nseg > 1 ? S.N : NQ) * c->cfg.num_choices * sizeof(float),
+                               st));
     const int32_t* d_wave = reinterpret_cast<const int32_t*>(d + o.wave_nodes);
     for (int dep = 1; dep <= S.max_depth; ++dep) {
       const int first = S.wave_ptr[dep], cnt = S.wave_ptr[dep + 1] - first;
@@ -476,7 +489,7 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
   if (cfg->abi_version != N2NMN_ABI_VERSION) return fail(N2NMN_ERR_ARG, "ABI version mismatch");
   if (cfg->family < 0 || cfg->family > 2 || cfg->H <= 0 || cfg->W <= 0 || cfg->D <= 0 ||
       cfg->map_dim <= 0 || cfg->map_dim > 1024 || cfg->num_choices <= 0 || cfg->max_batch <= 0 ||
-      cfg->max_T <= 0 || cfg->text_dim <= 0)
+      cfg->max_T <= 0 || cfg->text_dim <= 0 || cfg->max_group < 0 || cfg->max_group > kMaxSeg)
     return fail(N2NMN_ERR_ARG, "bad configuration");
   if (cfg->family != N2NMN_VQA && cfg->kernel_size != 3 && cfg->kernel_size != 5)
     return fail(N2NMN_ERR_ARG, "kernel_size must be 3 or 5");
@@ -495,6 +508,8 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
   c->Dk = cfg->D + (cfg->family == N2NMN_VQA ? 2 : 0);
   c->Kp = round_up(c->Dk, kBK);
   c->Mp = round_up(cfg->map_dim, 256);
+  c->G = std::max(1, std::min(cfg->max_group, kMaxSeg));
+  c->QB = c->G * cfg->max_batch;
   std::memset(&c->md, 0, sizeof(c->md));
   DevModel& md = c->md;
   md.H = cfg->H; md.W = cfg->W; md.HW = c->HW; md.Dk = c->Dk; md.Dt = cfg->text_dim;
@@ -558,13 +573,13 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
     CUDA_TRY(cudaMalloc(&c->proj_bias[s], (size_t)c->Mp * sizeof(float)));
     CUDA_TRY(cudaMemset(c->proj_bias[s], 0, (size_t)c->Mp * sizeof(float)));
     md.proj_b[s] = c->proj_bias[s];
-    if (int rc = encode_2d(c, &c->tmaps.b[s], c->proj_wt[s], c->Kp, c->Mp, c->Kp, kBK, kBN))
+    if (int rc = encode_2d(c, &c->tmaps.b[s], c->proj_wt[s], c->Kp, c->Mp, c->Kp, kBK, kBNHalf))
       return rc;
   }
   for (int s = 0; s < NUM_PROJ_SETS; ++s)      // sets the family lacks alias set 0 (never used)
     if (!c->proj_used[s]) c->tmaps.b[s] = c->tmaps.b[PS_FIND];
-  // workspaces
-  const int NB = cfg->max_batch, TT = cfg->max_T;
+  // workspaces (sized for a full group of segments)
+  const int NB = c->QB, TT = cfg->max_T;
   c->text_rows_cap = NB * TT;
   const size_t tb_floats = (size_t)c->text_rows_cap * c->Mp;
   CUDA_TRY(cudaMalloc(&c->tb.tau, 3 * tb_floats * sizeof(float)));
@@ -574,14 +589,15 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
   CUDA_TRY(cudaMalloc(&c->arena, (size_t)c->arena_slots * c->HW * sizeof(float)));
   c->mbuf_slots = (c->num_store_sets + 1) * NB;   // +1: conv_image maps of Find kept for backward
   CUDA_TRY(cudaMalloc(&c->mbuf, (size_t)c->mbuf_slots * c->HW * c->Mp * sizeof(float)));
-  CUDA_TRY(cudaMalloc(&c->scores_tmp, (size_t)NB * TT * cfg->num_choices * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&c->scores_tmp,
+                      (size_t)cfg->max_batch * TT * cfg->num_choices * sizeof(float)));
   if (cfg->family == N2NMN_VQA || (cfg->D % 4) != 0) {
     CUDA_TRY(cudaMalloc(&c->feat_aug, (size_t)NB * c->HW * c->Kp * sizeof(float)));
   }
   // schedule tables: generous upper bound on every table for (max_batch, max_T)
   {
     const size_t nodes = (size_t)NB * TT;
-    const size_t tiles = ((size_t)NB * c->HW + 127) / 128 + 1;
+    const size_t tiles = (size_t)c->G * (((size_t)cfg->max_batch * c->HW + 127) / 128 + 1);
     c->table_cap = nodes * (sizeof(NodeRec) + 4 * 6) + (nodes / 8 + 8) * sizeof(TextGroup) +
                    tiles * (TT / kMaxProjNodesPerPass + 1 + NUM_PROJ_SETS) * sizeof(ProjWork) +
                    (size_t)NB * (12 + 4 * NUM_PROJ_SETS) + nodes * (4 + 2 * sizeof(BwdEntryHost)) + 4096;
@@ -694,32 +710,51 @@ int n2nmn_set_weight(n2nmn_ctx* c, const char* name, const float* src, const int
   return fail(N2NMN_ERR_ARG, std::string("unknown variable: ") + name);
 }
 
-int n2nmn_bind_inputs(n2nmn_ctx* c, const float* feat, const float* wv, int N, int T,
-                      void* stream) {
-  if (!c || !feat || !wv) return fail(N2NMN_ERR_ARG, "null argument");
+namespace {
+// Points the context at `nseg` batches of identical shape (segments): feature grids [N,H,W,D],
+// word vectors [T,N,Dt]. One TMA tensor map per segment; VQA / odd channel counts get their
+// augmented / re-pitched copy per segment.
+int bind_segments(n2nmn_ctx* c, int nseg, const float* const* feat, const float* const* wv, int N,
+                  int T, cudaStream_t st) {
+  if (nseg <= 0 || nseg > c->G) return fail(N2NMN_ERR_CAPACITY, "too many batches for one group");
   if (N <= 0 || T <= 0) return fail(N2NMN_ERR_ARG, "N and T must be positive");
   if (N > c->cfg.max_batch || T > c->cfg.max_T)
     return fail(N2NMN_ERR_CAPACITY, "N or T exceeds the context capacity");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int rows = N * c->HW;
-  const float* eff = feat;
-  int pitch = c->cfg.D;
-  if (c->feat_aug) {
-    augment_features_kernel<<<rows, 128, 0, st>>>(feat, rows, c->cfg.D, c->cfg.H, c->cfg.W,
-                                                 c->cfg.family == N2NMN_VQA ? 1 : 0, c->feat_aug,
-                                                 c->Kp);
-    CUDA_TRY(cudaGetLastError());
-    ++c->launches;
-    eff = c->feat_aug;
-    pitch = c->Kp;
+  const int pitch = c->feat_aug ? c->Kp : c->cfg.D;
+  for (int sgi = 0; sgi < nseg; ++sgi) {
+    if (!feat[sgi] || !wv[sgi]) return fail(N2NMN_ERR_ARG, "null argument");
+    const float* eff = feat[sgi];
+    if (c->feat_aug) {
+      float* dst = c->feat_aug + (size_t)sgi * c->cfg.max_batch * c->HW * c->Kp;
+      augment_features_kernel<<<rows, 128, 0, st>>>(feat[sgi], rows, c->cfg.D, c->cfg.H, c->cfg.W,
+                                                   c->cfg.family == N2NMN_VQA ? 1 : 0, dst, c->Kp);
+      CUDA_TRY(cudaGetLastError());
+      ++c->launches;
+      eff = dst;
+    }
+    if ((reinterpret_cast<uintptr_t>(eff) & 15) != 0)
+      return fail(N2NMN_ERR_ARG, "image_feat_grid must be 16-byte aligned");
+    c->md.feat_seg[sgi] = eff;
+    c->md.wv_seg[sgi] = wv[sgi];
+    if (int rc = encode_2d(c, &c->tmaps.a[sgi], eff, c->Dk, rows, pitch, kBK, kBM)) return rc;
   }
-  if ((reinterpret_cast<uintptr_t>(eff) & 15) != 0)
-    return fail(N2NMN_ERR_ARG, "image_feat_grid must be 16-byte aligned");
-  c->md.feat = eff; c->md.feat_pitch = pitch; c->md.word_vecs = wv; c->md.N = N; c->md.T = T;
+  for (int sgi = nseg; sgi < kMaxSeg; ++sgi) {
+    c->md.feat_seg[sgi] = c->md.feat_seg[0];
+    c->md.wv_seg[sgi] = c->md.wv_seg[0];
+  }
+  c->md.feat = c->md.feat_seg[0]; c->md.feat_pitch = pitch; c->md.word_vecs = c->md.wv_seg[0];
+  c->md.N = N; c->md.T = T; c->md.num_seg = nseg;
   c->N = N; c->T = T;
-  if (int rc = encode_2d(c, &c->tmaps.a, eff, c->Dk, rows, pitch, kBK, kBM)) return rc;
   c->bound = true;
   return 0;
+}
+}  // namespace
+
+int n2nmn_bind_inputs(n2nmn_ctx* c, const float* feat, const float* wv, int N, int T,
+                      void* stream) {
+  if (!c || !feat || !wv) return fail(N2NMN_ERR_ARG, "null argument");
+  return bind_segments(c, 1, &feat, &wv, N, T, static_cast<cudaStream_t>(stream));
 }
 
 int n2nmn_compile_schedule(n2nmn_ctx* c, const int32_t* tokens, int T, int N,
@@ -881,7 +916,9 @@ int n2nmn_run_schedule(n2nmn_ctx* c, n2nmn_sched* s, float* scores, float* att_a
   float* arena = att_arena ? att_arena : c->arena;
   if (!att_arena && (int)s->hs.nodes.size() > c->arena_slots)
     return fail(N2NMN_ERR_CAPACITY, "too many nodes for the context arena");
-  return run_tables(c, s, scores, arena, static_cast<cudaStream_t>(stream), false,
+  if (s->hs.num_seg != 1 || c->md.num_seg != 1)
+    return fail(N2NMN_ERR_STATE, "n2nmn_run_schedule works on a single bound batch");
+  return run_tables(c, s, &scores, arena, static_cast<cudaStream_t>(stream), false,
                     att_arena != nullptr);
 }
 
@@ -917,8 +954,9 @@ int module_fwd_impl(n2nmn_ctx* c, int op, const float* in0, const float* in1,
     return fail(N2NMN_ERR_ARG, "missing attention input");
   if (needs_idx[op] && (!t_idx || !b_idx))
     return fail(N2NMN_ERR_ARG, "time_idx / batch_idx required for this module");
-  if (3 * n > c->arena_slots || n > c->text_rows_cap)
+  if (3 * n > c->arena_slots || n > c->cfg.max_batch * c->cfg.max_T)
     return fail(N2NMN_ERR_CAPACITY, "n exceeds the context capacity for a single module call");
+  if (c->md.num_seg != 1) return fail(N2NMN_ERR_STATE, "module calls need a single bound batch");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   n2nmn_sched* sc = &c->module_sched;
   sc->uid = g_uid++;   // tables change every call
@@ -953,7 +991,7 @@ int module_fwd_impl(n2nmn_ctx* c, int op, const float* in0, const float* in1,
     CUDA_TRY(cudaMemcpyAsync(c->arena + (size_t)n * c->HW, in1, map_bytes,
                              cudaMemcpyDeviceToDevice, st));
   float* scores = is_ans[op] ? out : c->scores_tmp;
-  if (int rc = run_tables(c, sc, scores, c->arena, st, /*force_wave=*/true)) return rc;
+  if (int rc = run_tables(c, sc, &scores, c->arena, st, /*force_wave=*/true)) return rc;
   if (!is_ans[op])
     CUDA_TRY(cudaMemcpyAsync(out, c->arena + (size_t)2 * n * c->HW, map_bytes,
                              cudaMemcpyDeviceToDevice, st));
@@ -961,51 +999,80 @@ int module_fwd_impl(n2nmn_ctx* c, int op, const float* in0, const float* in1,
 }
 }  // namespace
 
-int n2nmn_forward_tokens(n2nmn_ctx* c, const float* feat_dev, const float* wv_dev,
-                         const int32_t* tokens, int T, int N, const int32_t* vocab_ops,
-                         int num_vocab, float* scores_dev, uint8_t* validity_out, void* stream) {
-  if (!c || !tokens || !vocab_ops || !scores_dev) return fail(N2NMN_ERR_ARG, "null argument");
+int n2nmn_forward_group(n2nmn_ctx* c, int num_batches, const float* const* feat_dev,
+                        const float* const* wv_dev, const int32_t* const* tokens, int T, int N,
+                        const int32_t* vocab_ops, int num_vocab, float* const* scores_dev,
+                        uint8_t* const* validity_out, void* stream) {
+  if (!c || !feat_dev || !wv_dev || !tokens || !vocab_ops || !scores_dev || num_batches <= 0)
+    return fail(N2NMN_ERR_ARG, "null argument");
+  for (int i = 0; i < num_batches; ++i)
+    if (!tokens[i] || !scores_dev[i]) return fail(N2NMN_ERR_ARG, "null argument");
   CUDA_TRY(cudaSetDevice(c->device));   // callers may drive one context per host thread
-  if (int rc = n2nmn_bind_inputs(c, feat_dev, wv_dev, N, T, stream)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = bind_segments(c, num_batches, feat_dev, wv_dev, N, T, st)) return rc;
   if (int rc = check_ready(c)) return rc;
   n2nmn_sched* sc = &c->step_sched;
   sc->uid = g_uid++;
   const char* err = nullptr;
-  if (int rc = compile_schedule(c->shp, tokens, T, N, vocab_ops, num_vocab, &sc->hs, &err))
+  if (int rc = compile_schedule_group(c->shp, tokens, num_batches, T, N, vocab_ops, num_vocab,
+                                      &sc->hs, &err))
     return fail(rc, err ? err : "compile_schedule failed");
-  if (validity_out) std::memcpy(validity_out, sc->hs.validity.data(), N);
+  if (validity_out)
+    for (int i = 0; i < num_batches; ++i)
+      if (validity_out[i]) std::memcpy(validity_out[i], sc->hs.validity.data() + (size_t)i * N, N);
   if ((int)sc->hs.nodes.size() > c->arena_slots)
     return fail(N2NMN_ERR_CAPACITY, "too many nodes for the context arena");
-  return run_tables(c, sc, scores_dev, c->arena, static_cast<cudaStream_t>(stream));
+  return run_tables(c, sc, scores_dev, c->arena, st);
+}
+
+int n2nmn_forward_tokens(n2nmn_ctx* c, const float* feat_dev, const float* wv_dev,
+                         const int32_t* tokens, int T, int N, const int32_t* vocab_ops,
+                         int num_vocab, float* scores_dev, uint8_t* validity_out, void* stream) {
+  if (!c || !tokens || !vocab_ops || !scores_dev) return fail(N2NMN_ERR_ARG, "null argument");
+  return n2nmn_forward_group(c, 1, &feat_dev, &wv_dev, &tokens, T, N, vocab_ops, num_vocab,
+                             &scores_dev, validity_out ? &validity_out : nullptr, stream);
 }
 
 namespace {
-int forward_host_impl(n2nmn_ctx* c, const float* feat_host, const float* wv_host,
-                      const int32_t* tokens, int T, int N, const int32_t* vocab_ops,
-                      int num_vocab, float* scores_host, uint8_t* validity_out, void* stream,
-                      bool sync) {
-  if (!c || !feat_host || !wv_host || !tokens || !scores_host)
+// Host-buffer variant of n2nmn_forward_group: H2D of every batch's features and word vectors into
+// context-owned staging, the kernels, D2H of every batch's scores — all enqueued on `stream`.
+int forward_host_impl(n2nmn_ctx* c, int nb, const float* const* feat_host,
+                      const float* const* wv_host, const int32_t* const* tokens, int T, int N,
+                      const int32_t* vocab_ops, int num_vocab, float* const* scores_host,
+                      uint8_t* const* validity_out, void* stream, bool sync) {
+  if (!c || !feat_host || !wv_host || !tokens || !scores_host || nb <= 0)
     return fail(N2NMN_ERR_ARG, "null argument");
+  if (nb > c->G) return fail(N2NMN_ERR_CAPACITY, "too many batches for one group");
   if (N <= 0 || N > c->cfg.max_batch || T <= 0 || T > c->cfg.max_T)
     return fail(N2NMN_ERR_CAPACITY, "N or T exceeds the context capacity");
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t fcap = (size_t)c->cfg.max_batch * c->HW * c->cfg.D;
+  const size_t wcap = (size_t)c->cfg.max_T * c->cfg.max_batch * c->cfg.text_dim;
+  const size_t scap = (size_t)c->cfg.max_batch * c->cfg.num_choices;
   const size_t fbytes = (size_t)N * c->HW * c->cfg.D * sizeof(float);
   const size_t wbytes = (size_t)T * N * c->cfg.text_dim * sizeof(float);
   const size_t sbytes = (size_t)N * c->cfg.num_choices * sizeof(float);
   if (!c->e2e_feat) {
-    CUDA_TRY(cudaMalloc(&c->e2e_feat, (size_t)c->cfg.max_batch * c->HW * c->cfg.D * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&c->e2e_wv, (size_t)c->cfg.max_T * c->cfg.max_batch * c->cfg.text_dim *
-                                        sizeof(float)));
-    CUDA_TRY(cudaMalloc(&c->e2e_scores, (size_t)c->cfg.max_batch * c->cfg.num_choices *
-                                            sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c->e2e_feat, c->G * fcap * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c->e2e_wv, c->G * wcap * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c->e2e_scores, c->G * scap * sizeof(float)));
   }
-  CUDA_TRY(cudaMemcpyAsync(c->e2e_feat, feat_host, fbytes, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(c->e2e_wv, wv_host, wbytes, cudaMemcpyHostToDevice, st));
-  int rc = n2nmn_forward_tokens(c, c->e2e_feat, c->e2e_wv, tokens, T, N, vocab_ops, num_vocab,
-                                c->e2e_scores, validity_out, stream);
+  const float* fd[kMaxSeg];
+  const float* wd[kMaxSeg];
+  float* sd[kMaxSeg];
+  for (int i = 0; i < nb; ++i) {
+    if (!feat_host[i] || !wv_host[i] || !scores_host[i]) return fail(N2NMN_ERR_ARG, "null argument");
+    fd[i] = c->e2e_feat + i * fcap; wd[i] = c->e2e_wv + i * wcap; sd[i] = c->e2e_scores + i * scap;
+    CUDA_TRY(cudaMemcpyAsync(c->e2e_feat + i * fcap, feat_host[i], fbytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c->e2e_wv + i * wcap, wv_host[i], wbytes, cudaMemcpyHostToDevice, st));
+  }
+  int rc = n2nmn_forward_group(c, nb, fd, wd, tokens, T, N, vocab_ops, num_vocab, sd, validity_out,
+                               stream);
   if (rc == 0) {
-    cudaError_t e = cudaMemcpyAsync(scores_host, c->e2e_scores, sbytes, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < nb && e == cudaSuccess; ++i)
+      e = cudaMemcpyAsync(scores_host[i], sd[i], sbytes, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && sync) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) rc = fail(N2NMN_ERR_CUDA, cudaGetErrorString(e));
   } else if (sync) {
@@ -1018,17 +1085,28 @@ int forward_host_impl(n2nmn_ctx* c, const float* feat_host, const float* wv_host
 int n2nmn_forward_host(n2nmn_ctx* c, const float* feat_host, const float* wv_host,
                        const int32_t* tokens, int T, int N, const int32_t* vocab_ops,
                        int num_vocab, float* scores_host, uint8_t* validity_out, void* stream) {
-  return forward_host_impl(c, feat_host, wv_host, tokens, T, N, vocab_ops, num_vocab, scores_host,
-                           validity_out, stream, true);
+  return forward_host_impl(c, 1, &feat_host, &wv_host, &tokens, T, N, vocab_ops, num_vocab,
+                           &scores_host, validity_out ? &validity_out : nullptr, stream, true);
 }
 
 int n2nmn_forward_host_async(n2nmn_ctx* c, const float* feat_host, const float* wv_host,
                              const int32_t* tokens, int T, int N, const int32_t* vocab_ops,
                              int num_vocab, float* scores_host, uint8_t* validity_out,
                              void* stream) {
-  return forward_host_impl(c, feat_host, wv_host, tokens, T, N, vocab_ops, num_vocab, scores_host,
-                           validity_out, stream, false);
+  return forward_host_impl(c, 1, &feat_host, &wv_host, &tokens, T, N, vocab_ops, num_vocab,
+                           &scores_host, validity_out ? &validity_out : nullptr, stream, false);
 }
+
+int n2nmn_forward_group_host_async(n2nmn_ctx* c, int num_batches, const float* const* feat_host,
+                                   const float* const* wv_host, const int32_t* const* tokens,
+                                   int T, int N, const int32_t* vocab_ops, int num_vocab,
+                                   float* const* scores_host, uint8_t* const* validity_out,
+                                   void* stream) {
+  return forward_host_impl(c, num_batches, feat_host, wv_host, tokens, T, N, vocab_ops, num_vocab,
+                           scores_host, validity_out, stream, false);
+}
+
+int n2nmn_max_group(const n2nmn_ctx* c) { return c ? c->G : 0; }
 
 
 int64_t n2nmn_flat_size(const n2nmn_ctx* c) { return c ? c->flat_size : 0; }
@@ -1097,7 +1175,7 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
     if (labels_host[i] < 0 || labels_host[i] >= C) return fail(N2NMN_ERR_ARG, "label out of range");
   // ---- forward (keeps every attention map in the context arena + the stored maps)
   c->train_labels = labels_host;
-  const int rc = run_tables(c, sc, scores_dev, c->arena, st, false, /*write_arena=*/true);
+  const int rc = run_tables(c, sc, &scores_dev, c->arena, st, false, /*write_arena=*/true);
   c->train_labels = nullptr;
   if (rc) return rc;
   const uint8_t* d = c->last_tables;

@@ -8,6 +8,10 @@ namespace n2nmn {
 constexpr float kEps = 1e-12f;   // tf.nn.l2_normalize epsilon (models_clevr/nmn3_modules.py:107)
 constexpr int kNodeThreads = 256;
 constexpr int kMaxProjNodesPerPass = 8;
+// One launch may cover several independent batches ("segments": separate feature / word-vector /
+// score buffers of identical shape) so that the kernels see enough work per launch. Images and
+// questions are numbered across the segments: g = seg * N + b.
+constexpr int kMaxSeg = 8;
 
 // Opcodes mirror enum n2nmn_op in include/n2nmn_b200.h.
 enum Op : int {
@@ -49,9 +53,12 @@ struct NodeRec {
 // context-owned packed weight buffer.
 struct DevModel {
   int H, W, HW, Dk, feat_pitch, Dt, M, Mp, C, ksize, family;
-  const float* feat;        // [N*HW, feat_pitch] (Dk valid channels)
-  const float* word_vecs;   // [T, N, Dt]
-  int N, T;
+  const float* feat;        // segment 0: [N*HW, feat_pitch] (Dk valid channels)
+  const float* word_vecs;   // segment 0: [T, N, Dt]
+  int N, T;                 // images (= questions) per segment, decoder steps
+  int num_seg;
+  const float* feat_seg[kMaxSeg];
+  const float* wv_seg[kMaxSeg];
   // conv_image contraction: original [Dk][M] (fp32 CUDA-core path), bias padded to Mp
   const float* proj_w[NUM_PROJ_SETS];
   const float* proj_b[NUM_PROJ_SETS];
@@ -77,7 +84,12 @@ struct TextBufs {
 // Host-compiled launch tables (built by schedule.cpp, consumed by the kernels).
 struct TextGroup { int32_t set, start, count, pad; };   // <= kTextRowsPerCta rows of one text set
 constexpr int kTextRowsPerCta = 8;
-struct ProjWork { int32_t row0, pass, set, pad; };      // one 128-row tile of the contraction
+// One work item of the contraction kernel = a PAIR of 128-row tiles of the same weight set, one per
+// CTA of a cta_group::2 pair (the tiles share nothing but the weight matrix, so they may come from
+// different images, passes or segments). row0 = first row inside the segment's [N*HW] row axis;
+// pass = which block of <= 8 Find consumers the fused epilogue serves, or -1 for a filler tile
+// (odd tile count: the MMA runs, nothing is written).
+struct ProjWork { int32_t row0[2], seg[2], pass[2], set, pad; };
 
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization
 // attribute may start while its predecessor in the stream is still running; it must call
@@ -106,6 +118,12 @@ __device__ long long* g_timeline = nullptr;   // [kernel 0..2][cta < 512][64]: c
 #else
 #define N2NMN_STAMP(kernel, slot) do {} while (0)
 #endif
+
+// word_vecs row of (time t, global image g): segment g / N, row t*N + (g % N)
+__device__ __forceinline__ const float* word_vec_row(const DevModel& md, int t, int g) {
+  const int seg = g / md.N;
+  return md.wv_seg[seg] + ((size_t)t * md.N + (g - seg * md.N)) * md.Dt;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

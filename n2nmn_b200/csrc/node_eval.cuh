@@ -20,9 +20,17 @@ struct NodeCtx {
   DevModel md;
   TextBufs tb;
   float* arena;        // [slots][HW]
-  float* scores;       // [N][C]
+  float* scores;       // segment 0: [rows][C]
+  float* scores_seg[kMaxSeg];
+  int score_rows;      // score rows per segment (a huge value when there is one segment)
   const float* mbuf;   // [mslots][HW][Mp]
 };
+
+// score row of question / call row q (numbered across the segments)
+__device__ __forceinline__ float* score_row(const NodeCtx& c, int q) {
+  const int seg = q / c.score_rows;
+  return c.scores_seg[seg] + (size_t)(q - seg * c.score_rows) * c.md.C;
+}
 
 constexpr int kNodeScratch = 2048;   // floats
 
@@ -365,7 +373,7 @@ __device__ __forceinline__ void normalize_and_score(const NodeCtx& c, const Node
   for (int ch = threadIdx.x; ch < md.M; ch += blockDim.x) e[ch] *= inv;
   __syncthreads();
   small_fc(e, md.M, s.head_w ? s.head_w : md.out_w[out_set], md.out_b[out_set], md.C,
-           c.scores + (size_t)nd.out * md.C, s.scratch);
+           score_row(c, nd.out), s.scratch);
 }
 
 __device__ __forceinline__ void eval_describe(const NodeCtx& c, const NodeRec& nd,
@@ -435,7 +443,7 @@ __device__ __forceinline__ void eval_small_answer(const NodeCtx& c, const NodeRe
   }
   __syncthreads();
   small_fc(s.z, L, s.head_w ? s.head_w : md.sc_w[set], md.sc_b[set], md.C,
-           c.scores + (size_t)nd.out * md.C, s.scratch);
+           score_row(c, nd.out), s.scratch);
 }
 
 // Evaluates one node with the CTAs of `co`. Every CTA of the cluster must call it (the heavy

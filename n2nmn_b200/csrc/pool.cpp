@@ -1,15 +1,20 @@
-// Native host runtime for keeping several batches in flight: one worker thread per context.
+// Native host runtime for keeping several batches in flight: one worker thread per context, and
+// dynamic batching of whatever is queued.
 //
 // A step's host work (layout compile ~10 us, table upload, three launches) is about as long as its
-// GPU work at batch 64 once several streams overlap, so a single host thread feeding K streams
-// caps the throughput. Here every context (= stream) has its own worker thread with a job queue;
-// n2nmn_pool_submit only copies the token matrix into a job and returns. There is no reference
-// counterpart: the reference's executor is a Python loop around session.run
-// (exp_clevr/eval_clevr.py:96-133), one batch at a time.
+// GPU work at batch 64, and ONE batch of 64 questions is ~4 us of tensor work — far too little to
+// fill 148 SMs per launch. So every context (= stream) has its own worker thread with a job queue;
+// n2nmn_pool_submit only copies the token matrix into a job and returns, and a worker takes up to
+// n2nmn_max_group(ctx) queued jobs of identical shape at a time and evaluates them with ONE set of
+// launches (n2nmn_forward_group): the contraction kernel then walks several tiles per CTA pair and
+// its epilogues overlap the next tile's MMAs. A worker never waits for more jobs: with one job
+// queued it runs one. There is no reference counterpart: the reference's executor is a Python loop
+// around session.run (exp_clevr/eval_clevr.py:96-133), one batch at a time.
 //
 // Uses nothing but the public C ABI of include/n2nmn_b200.h.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -37,6 +42,7 @@ struct Job {
 struct Worker {
   n2nmn_ctx* ctx = nullptr;
   void* stream = nullptr;
+  int max_group = 1;
   std::thread th;
   std::mutex mu;
   std::condition_variable cv;
@@ -49,6 +55,7 @@ struct Worker {
 // step is ~10 us of host work, a futex wake-up is 50-100 us, so a sleeping worker turns a short
 // burst of submissions (the driver's --steps 20) into a measurement of wake-up latency.
 constexpr int kSpinMicros = 300;
+constexpr int kMaxGroup = 8;
 
 inline void cpu_relax() {
 #if defined(__x86_64__) || defined(__i386__)
@@ -63,10 +70,12 @@ inline void cpu_relax() {
 struct n2nmn_pool {
   std::vector<Worker*> workers;
   std::vector<int32_t> vocab;
-  uint64_t next = 0;          // round-robin cursor of n2nmn_pool_submit_many
+  uint64_t next = 0;          // cursor of n2nmn_pool_submit_many
+  int deal = 1;               // consecutive jobs dealt to one worker before moving to the next
   std::mutex done_mu;
   std::condition_variable done_cv;
   std::atomic<int64_t> pending{0};   // jobs queued or running
+  std::atomic<int64_t> groups{0}, grouped_jobs{0};
   int err_code = 0;           // first failure since the last wait
   std::string err_msg;
 };
@@ -75,42 +84,61 @@ namespace {
 
 thread_local std::string g_pool_err;
 
-void run_job(n2nmn_pool* p, Worker* w, Job& j) {
-  int rc;
-  if (j.host_io) {
-    rc = n2nmn_forward_host_async(w->ctx, j.feat, j.wv, j.tokens.data(), j.T, j.N,
-                                  p->vocab.data(), (int)p->vocab.size(), j.scores, j.validity,
-                                  w->stream);
-  } else {
-    rc = n2nmn_forward_tokens(w->ctx, j.feat, j.wv, j.tokens.data(), j.T, j.N, p->vocab.data(),
-                              (int)p->vocab.size(), j.scores, j.validity, w->stream);
+void run_group(n2nmn_pool* p, Worker* w, std::vector<Job>& js) {
+  const int n = (int)js.size();
+  const float* feat[kMaxGroup];
+  const float* wv[kMaxGroup];
+  const int32_t* tok[kMaxGroup];
+  float* scores[kMaxGroup];
+  uint8_t* valid[kMaxGroup];
+  for (int i = 0; i < n; ++i) {
+    feat[i] = js[i].feat; wv[i] = js[i].wv; tok[i] = js[i].tokens.data();
+    scores[i] = js[i].scores; valid[i] = js[i].validity;
   }
+  const Job& j0 = js[0];
+  int rc;
+  if (j0.host_io)
+    rc = n2nmn_forward_group_host_async(w->ctx, n, feat, wv, tok, j0.T, j0.N, p->vocab.data(),
+                                        (int)p->vocab.size(), scores, valid, w->stream);
+  else
+    rc = n2nmn_forward_group(w->ctx, n, feat, wv, tok, j0.T, j0.N, p->vocab.data(),
+                             (int)p->vocab.size(), scores, valid, w->stream);
+  p->groups.fetch_add(1, std::memory_order_relaxed);
+  p->grouped_jobs.fetch_add(n, std::memory_order_relaxed);
   std::lock_guard<std::mutex> lk(p->done_mu);
   if (rc != 0 && p->err_code == 0) {
     p->err_code = rc;
     p->err_msg = n2nmn_last_error();
   }
-  if (p->pending.fetch_sub(1) == 1) p->done_cv.notify_all();
+  if (p->pending.fetch_sub(n) == n) p->done_cv.notify_all();
 }
 
 void worker_main(n2nmn_pool* p, Worker* w) {
+  std::vector<Job> js;
   for (;;) {
-    Job j;
     if (w->qsize.load(std::memory_order_acquire) == 0) {   // stay hot for a while
       const auto t_end = std::chrono::steady_clock::now() + std::chrono::microseconds(kSpinMicros);
       while (w->qsize.load(std::memory_order_acquire) == 0 &&
              std::chrono::steady_clock::now() < t_end)
         for (int i = 0; i < 64; ++i) cpu_relax();
     }
+    js.clear();
     {
       std::unique_lock<std::mutex> lk(w->mu);
       w->cv.wait(lk, [&] { return w->stop || !w->q.empty(); });
       if (w->q.empty()) return;   // stop requested and nothing left
-      j = std::move(w->q.front());
+      // whatever is queued right now, up to the context's group capacity, same shape only
+      js.push_back(std::move(w->q.front()));
       w->q.pop_front();
+      while ((int)js.size() < w->max_group && !w->q.empty()) {
+        const Job& nx = w->q.front();
+        if (nx.T != js[0].T || nx.N != js[0].N || nx.host_io != js[0].host_io) break;
+        js.push_back(std::move(w->q.front()));
+        w->q.pop_front();
+      }
       w->qsize.store((int)w->q.size(), std::memory_order_release);
     }
-    run_job(p, w, j);
+    run_group(p, w, js);
   }
 }
 
@@ -128,12 +156,16 @@ int n2nmn_pool_create(n2nmn_ctx** ctxs, void** streams, int num, const int32_t* 
   }
   n2nmn_pool* p = new n2nmn_pool();
   p->vocab.assign(vocab_ops, vocab_ops + num_vocab);
+  int g = kMaxGroup;
   for (int i = 0; i < num; ++i) {
     Worker* w = new Worker();
     w->ctx = ctxs[i];
     w->stream = streams[i];
+    w->max_group = std::max(1, std::min(n2nmn_max_group(ctxs[i]), kMaxGroup));
+    g = std::min(g, w->max_group);
     p->workers.push_back(w);
   }
+  p->deal = g;   // a run of `deal` consecutive jobs lands in one queue -> one full group
   for (Worker* w : p->workers) w->th = std::thread(worker_main, p, w);
   *out = p;
   return 0;
@@ -188,9 +220,9 @@ int n2nmn_pool_submit_many(n2nmn_pool* p, int n, const float* const* feat,
     g_pool_err = "n2nmn_pool_submit_many: bad argument";
     return N2NMN_ERR_ARG;
   }
-  const int K = (int)p->workers.size();
+  const uint64_t K = p->workers.size();
   for (int i = 0; i < n; ++i) {
-    const int slot = (int)(p->next++ % (uint64_t)K);
+    const int slot = (int)((p->next++ / (uint64_t)p->deal) % K);
     if (int rc = n2nmn_pool_submit(p, slot, feat[i], wv[i], tokens[i], T, N, scores[i],
                                    validity_out ? validity_out[i] : nullptr, host_io))
       return rc;
@@ -212,6 +244,13 @@ int n2nmn_pool_wait(n2nmn_pool* p) {
   p->err_code = 0;
   p->err_msg.clear();
   return rc;
+}
+
+int n2nmn_pool_group_stats(const n2nmn_pool* p, int64_t* groups, int64_t* jobs) {
+  if (!p) return N2NMN_ERR_ARG;
+  if (groups) *groups = p->groups.load();
+  if (jobs) *jobs = p->grouped_jobs.load();
+  return 0;
 }
 
 }  // extern "C"

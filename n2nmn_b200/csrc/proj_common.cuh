@@ -17,16 +17,18 @@
 namespace n2nmn {
 
 struct ProjParams {
-  const ProjWork* work;
+  const ProjWork* work;   // pair items (two 128-row tiles each, common.cuh)
   int num_work;
-  int total_rows;   // N*HW
+  int total_rows;   // rows of ONE segment: N*HW
+  int num_seg;      // segments covered by this launch
+  int seg_images;   // N: images per segment (global image g = seg*N + b)
   int n_tiles;      // Mp / 256
   int k_blocks;     // ceil(Dk / 32)
   int HW, M, Mp, Dk, feat_pitch;
-  const float* feat;
+  const float* feat_seg[kMaxSeg];   // [N*HW, feat_pitch] per segment (CUDA-core path only)
   const float* bias[NUM_PROJ_SETS];      // [Mp], zero padded
   const float* w_orig[NUM_PROJ_SETS];    // [Dk][M] (CUDA-core path only)
-  // fused consumers of PS_FIND: CSR over images
+  // fused consumers of PS_FIND: CSR over the images of all segments
   const int32_t* img_ptr;     // [N+1]
   const int32_t* node_text;   // text row of each CSR entry
   const int32_t* node_out;    // arena slot of each CSR entry
@@ -36,7 +38,7 @@ struct ProjParams {
   float* arena;               // [slots][HW]
   // stored sets
   const int32_t* mslot;       // [NUM_PROJ_SETS][num_images] -> slot in mbuf or -1
-  int num_images;
+  int num_images;             // num_seg * N
   float* mbuf;                // [slots][HW][Mp]
 };
 

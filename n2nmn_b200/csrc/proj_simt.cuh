@@ -20,11 +20,17 @@ proj_simt_kernel(ProjParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int col_iters = p.Mp / 256;
 
-  for (int wi = blockIdx.x; wi < p.num_work; wi += gridDim.x) {
-    const ProjWork wk = p.work[wi];
+  // one CTA per TILE: CTA 2i / 2i+1 take the two halves of pair item i
+  for (int ti = blockIdx.x; ti < 2 * p.num_work; ti += gridDim.x) {
+    const ProjWork wk = p.work[ti >> 1];
+    const int hf = ti & 1;
+    const int wk_pass = wk.pass[hf], wk_row0 = wk.row0[hf];
+    if (wk_pass < 0) continue;   // filler half of an odd pair
+    const int g0 = wk.seg[hf] * p.seg_images;
+    const float* __restrict__ feat = p.feat_seg[wk.seg[hf]];
     const float* __restrict__ W = p.w_orig[wk.set];
     for (int r0 = 0; r0 < 128; r0 += kSimtRows) {
-      const int row_base = wk.row0 + r0;
+      const int row_base = wk_row0 + r0;
       if (row_base >= p.total_rows) break;
       float acc[kSimtMaxColIters][kSimtRows];
 #pragma unroll
@@ -37,7 +43,7 @@ proj_simt_kernel(ProjParams p) {
           const int r = i / kSimtKChunk, k = i - r * kSimtKChunk;
           const int row = row_base + r;
           xs[i] = (row < p.total_rows && k0 + k < p.Dk)
-                      ? p.feat[(size_t)row * p.feat_pitch + k0 + k] : 0.f;
+                      ? feat[(size_t)row * p.feat_pitch + k0 + k] : 0.f;
         }
         __syncthreads();
         const int kmax = min(kSimtKChunk, p.Dk - k0);
@@ -68,10 +74,11 @@ proj_simt_kernel(ProjParams p) {
       // epilogue: warp `warp` owns row row_base + warp
       const int row = row_base + warp;
       if (row < p.total_rows) {
-        const int b = row / p.HW, pix = row - b * p.HW;
+        const int bl = row / p.HW, pix = row - bl * p.HW;
+        const int b = g0 + bl;   // image index across the segments
         const float* mrow = ms + warp * p.Mp;
         if (wk.set == PS_FIND) {
-          const int beg = p.img_ptr[b] + wk.pass * kMaxProjNodesPerPass;
+          const int beg = p.img_ptr[b] + wk_pass * kMaxProjNodesPerPass;
           const int end = min(p.img_ptr[b + 1], beg + kMaxProjNodesPerPass);
           for (int e = beg; e < end; ++e) {
             const float* tw = p.tauw + (size_t)p.node_text[e] * p.Mp;
@@ -91,7 +98,7 @@ proj_simt_kernel(ProjParams p) {
         }
         {
           const int slot = p.mslot[wk.set * p.num_images + b];
-          if (slot >= 0 && wk.pass == 0) {
+          if (slot >= 0 && wk_pass == 0) {
             float* dst = p.mbuf + ((size_t)slot * p.HW + pix) * p.Mp;
             for (int c = lane; c < p.Mp; c += 32) dst[c] = mrow[c];
           }

@@ -1,22 +1,30 @@
-// K2: conv_image contraction on the 5th-gen tensor cores (tcgen05, kind::tf32) with the module
-// epilogue fused on the TMEM accumulator. See proj_common.cuh for the math and what is fused.
+// K2: conv_image contraction on the 5th-gen tensor cores (tcgen05, kind::tf32, cta_group::2) with
+// the module epilogue fused on the TMEM accumulator. See proj_common.cuh for the math and what is
+// fused.
 //
-// Tiling: one work item = 128 consecutive rows of the flattened (image, pixel) axis x all Mp
-// output columns, walked as Mp/256 N-tiles of 256 columns (UMMA 128x256x8, fp32 operands read as
-// TF32 straight from the caller's fp32 feature grid — no conversion pass). K is streamed in
-// 32-float (128-byte, one swizzle atom) slices through two TMA->smem rings, one per operand:
-//     A slice 128x32 fp32 (16 KB, 3 slots) and B slice 256x32 fp32 (32 KB, 3 slots), both
-//     SWIZZLE_128B K-major.
-// TMEM holds two 128x256 fp32 accumulators (all 512 columns), so the epilogue of N-tile i
-// overlaps the MMAs of N-tile i+1 / of the next work item. The grid is persistent: CTA i walks
-// work items i, i+gridDim, ... (gridDim = min(items, SMs), or fewer on request: n2nmn_set_proj_ctas).
+// Tiling. The kernel runs as CTA PAIRS (clusters of 2 = one TPC). One work item = two 128-row
+// tiles of the flattened (image, pixel) axis that use the same weight set, one per CTA, x all Mp
+// output columns, walked as Mp/256 N-tiles: ONE tcgen05.mma.cta_group::2 of shape 256x256x8 (fp32
+// operands read as TF32 straight from the caller's fp32 feature grid — no conversion pass) covers
+// both tiles. Each CTA stages its own A slice (128 rows x 32 floats, 16 KB) and only HALF of the
+// B slice (128 of the 256 weight columns x 32 floats, 16 KB): the tensor cores of both SMs read
+// both halves, so the L2->SM operand traffic per MMA is 32 KB instead of the 48 KB of the
+// single-CTA form (the mainloop was bound by exactly that traffic, 4.2x the
+// algorithmic bytes). K is streamed in 32-float (128-byte, one swizzle atom) slices through a
+// 4-stage TMA ring (SWIZZLE_128B, K-major); the bytes of both CTAs are counted on the LEADER's
+// `full` barrier, the MMA completion is multicast to both CTAs' `empty` barriers.
+// TMEM of each CTA holds two 128x256 fp32 accumulators (all 512 columns), so the epilogue of
+// N-tile i overlaps the MMAs of N-tile i+1 / of the next work item. The grid is persistent: pair i
+// walks work items i, i+pairs, ... One launch may span several batches (segments, common.cuh): a
+// work item names the segment of each of its tiles and the feature tensor map is picked by it.
 //
-// Warp roles (384 threads): warpgroup 0 = {A-ring TMA producer, TMEM allocator + MMA issuer,
-// B-ring TMA producer, idle} (one elected lane each, registers handed to the epilogue with
+// Warp roles (384 threads per CTA): warp 0 = TMA producer (one elected lane), warp 1 = TMEM
+// allocator + (leader CTA only) MMA issuer, warps 2-3 idle (registers handed to the epilogue with
 // setmaxnreg), warps 4..11 = epilogue; epilogue warp w reads TMEM lanes [32*(w%4), 32*(w%4)+32)
 // i.e. tile rows with that offset, and the two warps that share a lane quarter split the 256
-// columns of an N-tile in halves (the epilogue of a lone tile is a latency chain; two warpgroups
-// halve it). Their partial sums meet in shared memory. DESIGN.md §4 has the anatomy and what was
+// columns of an N-tile in halves. Their partial sums meet in shared memory. Each CTA's epilogue
+// works on its own tile exactly as in the single-CTA form; it releases the accumulator to the
+// leader's MMA warp with a remote mbarrier arrive. DESIGN.md §4 has the anatomy and what was
 // measured on the way.
 //
 // Precision: TF32 operands (10-bit mantissa), fp32 accumulate. Error budget vs the fp32/fp64
@@ -27,34 +35,25 @@
 
 namespace n2nmn {
 
-constexpr int kBM = 128;           // rows per tile (UMMA M)
+constexpr int kBM = 128;           // rows per tile = rows per CTA (UMMA M = 256 over the pair)
 constexpr int kBN = 256;           // columns per N-tile (UMMA N)
+constexpr int kBNHalf = kBN / 2;   // weight columns staged by each CTA
 constexpr int kBK = 32;            // fp32 elements per K slice = 128 bytes
 constexpr int kUmmaK = 8;          // K per tcgen05.mma for tf32 (32 bytes)
-// Operand rings: separate rings (and producer warps) for the A slices (features, 16 KB, streamed
-// from DRAM exactly once) and the B slices (weights, 32 KB, L2-resident after the first touch), so
-// that their depths can be chosen independently. Measured at batch 64 / 256 / 1024 (kernel alone):
-// A3/B3 24.5 / 50.7 / 140 us, A5/B2 26.8 / 52.8 / 153 us: the weight ring needs the depth as much as
-// the feature ring does, and 3 + 3 (144 KB) is what fits next to the epilogue staging. (Four
-// 48 KB stages were ~2 us faster at batch 64 but leave no room for that staging.)
-#if defined(N2NMN_EXP_STAGES_A)
-constexpr int kStagesA = N2NMN_EXP_STAGES_A;
+#if defined(N2NMN_EXP_STAGES)
+constexpr int kStages = N2NMN_EXP_STAGES;
 #else
-constexpr int kStagesA = 3;
+constexpr int kStages = 4;
 #endif
-#if defined(N2NMN_EXP_STAGES_B)
-constexpr int kStagesB = N2NMN_EXP_STAGES_B;
-#else
-constexpr int kStagesB = 3;
-#endif
-constexpr int kABytes = kBM * kBK * 4;   // 16384
-constexpr int kBBytes = kBN * kBK * 4;   // 32768
-constexpr int kRingBytes = kStagesA * kABytes + kStagesB * kBBytes;
-// Warpgroup 0 = {A-TMA warp, MMA warp, B-TMA warp, one idle warp}, warpgroups 1-2 = epilogue. Roles are split on
-// warpgroup boundaries so that setmaxnreg can move registers from the producers (which need ~30)
-// to the epilogue warps (which want > 200: a 32-column accumulator chunk in flight, the one being
-// reduced, its squares, and a consumer node's two staged vectors loaded as ONE batch — with two
-// epilogue warps per scheduler, load -> use -> load chains expose the shared-memory latency).
+constexpr int kABytes = kBM * kBK * 4;        // 16384
+constexpr int kBHalfBytes = kBNHalf * kBK * 4;   // 16384
+constexpr int kStageBytes = kABytes + kBHalfBytes;
+constexpr int kRingBytes = kStages * kStageBytes;
+// Roles are split on warpgroup boundaries so that setmaxnreg can move registers from the producers
+// (which need ~30) to the epilogue warps (which want > 200: a 32-column accumulator chunk in
+// flight, the one being reduced, its squares, and a consumer node's two staged vectors loaded as
+// ONE batch — with two epilogue warps per scheduler, load -> use -> load chains expose the
+// shared-memory latency).
 constexpr int kProjThreads = 384;
 constexpr int kProducerRegs = 40, kEpilogueRegs = 232;   // 4*40 + 8*232 <= 2048 per 32 lanes
 constexpr int kEpiThreads = 256;
@@ -80,11 +79,11 @@ constexpr int kVecBytes =
 constexpr int kProjSmemBytes = kRingBytes + kVecBytes + 256;
 
 struct ProjTensorMaps {
-  CUtensorMap a;                     // features [total_rows, Dk] fp32, box 32 x 128
-  CUtensorMap b[NUM_PROJ_SETS];      // W^T [Mp, Kp] fp32 (K-major), box 32 x 256
+  CUtensorMap a[kMaxSeg];            // features of each segment [rows, Dk] fp32, box 32 x 128
+  CUtensorMap b[NUM_PROJ_SETS];      // W^T [Mp, Kp] fp32 (K-major), box 32 x 128 (half an N-tile)
 };
 
-__global__ void __launch_bounds__(kProjThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kProjThreads, 1)
 proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) {
   // SWIZZLE_128B tiles need 1024-byte alignment. The alignment comes from the declaration, NOT
   // from integer arithmetic on the pointer: that would demote every shared-memory access below
@@ -93,46 +92,41 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
   extern __shared__ __align__(1024) uint8_t proj_smem[];
   uint8_t* smem = proj_smem;
   if ((ptx::smem_u32(proj_smem) & 1023u) != 0) __trap();
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kStagesA * kABytes;
   float* s_tw = reinterpret_cast<float*>(smem + kRingBytes);              // [2][8][256] τ∘w2
   float* s_t2 = s_tw + kVecFloats;                                         // [2][8][256] τ²
   float* s_bias = s_t2 + kVecFloats;
   float* s_part = s_bias + kBN;          // [2 halves][8 nodes][num|den][128 rows]
   float* s_store = s_part + kPartFloats; // [8 warps][32 rows][32 cols], 16-byte chunks swizzled
   float** s_rowdst = reinterpret_cast<float**>(s_store + kStoreFloats);   // [128] or nullptr
-  uint64_t* full_a = reinterpret_cast<uint64_t*>(smem + kRingBytes + kVecBytes);
-  uint64_t* empty_a = full_a + kStagesA;
-  uint64_t* full_b = empty_a + kStagesA;
-  uint64_t* empty_b = full_b + kStagesB;
-  uint64_t* tmem_full = empty_b + kStagesB;    // [2]
-  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kRingBytes + kVecBytes);   // leader's is used
+  uint64_t* empty = full + kStages;
+  uint64_t* tmem_full = empty + kStages;       // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2], leader's is used
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();        // 0 = leader of the pair
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   pdl_trigger();   // let the node kernel's CTAs start prefetching their parameters
   if (threadIdx.x == 0) N2NMN_STAMP(1, 0);
 
   if (warp == 0 && ptx::elect_one()) {
-    ptx::prefetch_tensormap(&tm.a);
+    for (int i = 0; i < kMaxSeg; ++i)
+      if (i < p.num_seg) ptx::prefetch_tensormap(&tm.a[i]);
     for (int i = 0; i < NUM_PROJ_SETS; ++i) ptx::prefetch_tensormap(&tm.b[i]);
-    for (int s = 0; s < kStagesA; ++s) {
-      ptx::mbar_init(&full_a[s], 1);
-      ptx::mbar_init(&empty_a[s], 1);
-    }
-    for (int s = 0; s < kStagesB; ++s) {
-      ptx::mbar_init(&full_b[s], 1);
-      ptx::mbar_init(&empty_b[s], 1);
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full[s], 1);        // the leader producer's arrive.expect_tx
+      ptx::mbar_init(&empty[s], 1);       // one multicast tcgen05.commit
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
-      ptx::mbar_init(&tmem_empty[i], 8);   // one arrive per epilogue warp
+      ptx::mbar_init(&tmem_empty[i], 16);   // one arrive per epilogue warp of BOTH CTAs
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc<kTmemCols>(tmem_base_slot);
+  if (warp == 1) ptx::tmem_alloc_pair<kTmemCols>(tmem_base_slot);
   ptx::tc_fence_before();
-  __syncthreads();
+  ptx::cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / TMA
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
   if (threadIdx.x == 0) N2NMN_STAMP(1, 1);
@@ -140,81 +134,57 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
   if (warp == 0) {
-    // ===================================================================== TMA producer, A ring
+    // ===================================================================== TMA producer
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int wi = blockIdx.x; wi < p.num_work; wi += gridDim.x) {
-        const ProjWork wk = p.work[wi];
+      for (int wi = pair; wi < p.num_work; wi += npairs) {
+        const ProjWork* wk = p.work + wi;
+        const int row0 = wk->row0[rank], seg = wk->seg[rank], set = wk->set;
         for (int nt = 0; nt < p.n_tiles; ++nt) {
           for (int kb = 0; kb < p.k_blocks; ++kb) {
-            ptx::mbar_wait(&empty_a[stage], phase ^ 1);
-            ptx::mbar_arrive_expect_tx(&full_a[stage], kABytes);
-#if !defined(N2NMN_EXP_SKIP_A)      // timing experiments only (results are garbage)
-            ptx::tma_load_2d(smem_a + stage * kABytes, &tm.a, kb * kBK, wk.row0, &full_a[stage]);
-#else
-            ptx::tma_load_2d(smem_a + stage * kABytes, &tm.a, 0, 0, &full_a[stage]);
-#endif
-            if (++stage == kStagesA) { stage = 0; phase ^= 1; }
+            ptx::mbar_wait(&empty[stage], phase ^ 1);
+            // both CTAs' bytes land on the leader's barrier (the MMA issuer waits there)
+            const uint32_t bar = ptx::map_to_cta(&full[stage], 0);
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], 2 * kStageBytes);
+            uint8_t* dst = smem + stage * kStageBytes;
+            ptx::tma_load_2d_pair(dst, &tm.a[seg], kb * kBK, row0, bar);
+            ptx::tma_load_2d_pair(dst + kABytes, &tm.b[set], kb * kBK,
+                                  nt * kBN + (int)rank * kBNHalf, bar);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
-  } else if (warp == 2) {
-    // ===================================================================== TMA producer, B ring
+  } else if (warp == 1 && rank == 0) {
+    // ===================================================================== MMA issuer (leader)
     if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_tf32(2 * kBM, kBN);
       int stage = 0;
       uint32_t phase = 0;
-      for (int wi = blockIdx.x; wi < p.num_work; wi += gridDim.x) {
-        const ProjWork wk = p.work[wi];
-        for (int nt = 0; nt < p.n_tiles; ++nt) {
-          for (int kb = 0; kb < p.k_blocks; ++kb) {
-            ptx::mbar_wait(&empty_b[stage], phase ^ 1);
-            ptx::mbar_arrive_expect_tx(&full_b[stage], kBBytes);
-#if !defined(N2NMN_EXP_SKIP_B)
-            ptx::tma_load_2d(smem_b + stage * kBBytes, &tm.b[wk.set], kb * kBK, nt * kBN,
-                             &full_b[stage]);
-#else
-            ptx::tma_load_2d(smem_b + stage * kBBytes, &tm.b[wk.set], 0, 0, &full_b[stage]);
-#endif
-            if (++stage == kStagesB) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::make_idesc_tf32(kBM, kBN);
-      int sa = 0, sb = 0;
-      uint32_t pha = 0, phb = 0;
       uint32_t it = 0;   // accumulator uses so far
-      for (int wi = blockIdx.x; wi < p.num_work; wi += gridDim.x) {
+      for (int wi = pair; wi < p.num_work; wi += npairs) {
         for (int nt = 0; nt < p.n_tiles; ++nt, ++it) {
           const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-          ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // epilogue drained this buffer
+          ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // both epilogues drained this buffer
           ptx::tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc * kBN;
           for (int kb = 0; kb < p.k_blocks; ++kb) {
-            ptx::mbar_wait(&full_b[sb], phb);                 // TMA bytes landed
-            ptx::mbar_wait(&full_a[sa], pha);
+            ptx::mbar_wait(&full[stage], phase);              // TMA bytes of both CTAs landed
             if (kb < 16) N2NMN_STAMP(1, 8 + kb);
             ptx::tc_fence_after();
-            const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a + sa * kABytes));
-            const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b + sb * kBBytes));
-#if !defined(N2NMN_EXP_SKIP_MMA)
+            const uint32_t sa = ptx::smem_u32(smem + stage * kStageBytes);
+            const uint64_t da = ptx::make_smem_desc_sw128(sa);
+            const uint64_t db = ptx::make_smem_desc_sw128(sa + kABytes);
 #pragma unroll
             for (int k = 0; k < kBK / kUmmaK; ++k) {
               // advance 32 bytes (= 2 x 16-byte units) along K inside the swizzle atom
-              ptx::umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              ptx::umma_tf32_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
             }
-#endif
-            ptx::umma_commit(&empty_a[sa]);                   // frees the smem slots when done
-            ptx::umma_commit(&empty_b[sb]);
-            if (++sa == kStagesA) { sa = 0; pha ^= 1; }
-            if (++sb == kStagesB) { sb = 0; phb ^= 1; }
+            ptx::umma_commit_pair(&empty[stage], 3);          // frees the slot in both CTAs
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          ptx::umma_commit(&tmem_full[acc]);                  // accumulator ready
+          ptx::umma_commit_pair(&tmem_full[acc], 3);          // accumulator ready in both CTAs
         }
       }
     }
@@ -227,17 +197,34 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
     const int etid = threadIdx.x - 128;        // 0..255 among the epilogue threads
     const int half = (warp - 4) >> 2;          // which 128 columns of each N-tile this warp takes
     const bool staged = p.HW >= kBM - 1;       // a tile then spans at most two images
+    const uint32_t tmem_empty_leader[2] = {ptx::map_to_cta(&tmem_empty[0], 0),
+                                           ptx::map_to_cta(&tmem_empty[1], 0)};
     uint32_t it = 0;
     // tauw / tau2 come from the text-projection kernel, which may still be running (PDL); the
     // TMA / MMA warps above never touch its output and start immediately.
     if (warp == 4) N2NMN_STAMP(1, 2);
     pdl_wait();
     if (warp == 4) N2NMN_STAMP(1, 3);
-    for (int wi = blockIdx.x; wi < p.num_work; wi += gridDim.x) {
-      const ProjWork wk = p.work[wi];
-      const int row = wk.row0 + trow;
+    for (int wi = pair; wi < p.num_work; wi += npairs) {
+      const ProjWork* wkp = p.work + wi;
+      const int row0 = wkp->row0[rank], pass = wkp->pass[rank];
+      const int g0 = wkp->seg[rank] * p.seg_images;   // first image of this tile's segment
+      struct { int set; } wk = {wkp->set};
+      if (pass < 0) {
+        // filler tile of an odd pair: the MMA ran on it, nothing to write — just hand the
+        // accumulator back
+        for (int nt = 0; nt < p.n_tiles; ++nt, ++it) {
+          const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+          ptx::mbar_wait(&tmem_full[acc], acc_phase);
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(tmem_empty_leader[acc]);
+        }
+        continue;
+      }
+      const int row = row0 + trow;
       const bool row_ok = row < p.total_rows;
-      const int b_first = wk.row0 / p.HW;
+      const int b_first = row0 / p.HW;                 // image index inside the segment
       const int b = row_ok ? row / p.HW : b_first;
       const int pix = row - b * p.HW;
       const int img_local = b - b_first;
@@ -246,17 +233,17 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
       float* mdst = nullptr;
       if (row_ok) {
         if (wk.set == PS_FIND) {
-          e_beg = p.img_ptr[b] + wk.pass * kMaxProjNodesPerPass;
-          n_nodes = min(p.img_ptr[b + 1] - e_beg, kMaxProjNodesPerPass);
+          e_beg = p.img_ptr[g0 + b] + pass * kMaxProjNodesPerPass;
+          n_nodes = min(p.img_ptr[g0 + b + 1] - e_beg, kMaxProjNodesPerPass);
           n_nodes = max(n_nodes, 0);
         }
         // stored map (always for the non-Find sets; for PS_FIND only in training schedules)
-        const int slot = p.mslot[wk.set * p.num_images + b];
-        if (slot >= 0 && wk.pass == 0) mdst = p.mbuf + ((size_t)slot * p.HW + pix) * p.Mp;
+        const int slot = p.mslot[wk.set * p.num_images + g0 + b];
+        if (slot >= 0 && pass == 0) mdst = p.mbuf + ((size_t)slot * p.HW + pix) * p.Mp;
       }
       float* acc_row = s_part + half * (kMaxProjNodesPerPass * 2 * kBM) + trow;   // + j*2*kBM (+kBM)
       const float* __restrict__ bias = p.bias[wk.set];
-      const int n_img = min((p.total_rows - 1) / p.HW, (wk.row0 + kBM - 1) / p.HW) - b_first + 1;
+      const int n_img = min((p.total_rows - 1) / p.HW, (row0 + kBM - 1) / p.HW) - b_first + 1;
       // does any row of this warp's quarter leave through the stored-map path? (warp-uniform)
       const bool any_store = __any_sync(0xffffffffu, mdst != nullptr);
 
@@ -272,8 +259,8 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
           for (int i = etid; i < kVecFloats / 4; i += kEpiThreads) {
             const int q = i & 63, j = (i >> 6) & 7, im = i >> 9;
             if (im < n_img) {
-              const int eb = p.img_ptr[b_first + im] + wk.pass * kMaxProjNodesPerPass;
-              if (eb + j < p.img_ptr[b_first + im + 1]) {
+              const int eb = p.img_ptr[g0 + b_first + im] + pass * kMaxProjNodesPerPass;
+              if (eb + j < p.img_ptr[g0 + b_first + im + 1]) {
                 const size_t off = (size_t)p.node_text[eb + j] * p.Mp + nt * kBN;
                 reinterpret_cast<float4*>(s_tw)[i] =
                     __ldg(reinterpret_cast<const float4*>(p.tauw + off) + q);
@@ -304,34 +291,21 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
         if (warp == 4) N2NMN_STAMP(1, 5);
         ptx::tc_fence_after();
         float vbuf[2][32];
-#if defined(N2NMN_EXP_EPI_NOLD)
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { vbuf[0][i] = 1.f; vbuf[1][i] = 1.f; }
-#define N2NMN_TMEM_LD(addr, dst)
-#define N2NMN_TMEM_WAIT()
-#else
-#define N2NMN_TMEM_LD(addr, dst) ptx::tmem_ld_32x32b_x32_nowait(addr, dst)
-#define N2NMN_TMEM_WAIT() ptx::tmem_ld_wait()
-#endif
-        N2NMN_TMEM_LD(taddr + ch0 * 32, vbuf[0]);
+        ptx::tmem_ld_32x32b_x32_nowait(taddr + ch0 * 32, vbuf[0]);
 #pragma unroll 2
         for (int ch = ch0; ch < ch1; ++ch) {
           float (&v)[32] = vbuf[(ch - ch0) & 1];
-          N2NMN_TMEM_WAIT();
+          ptx::tmem_ld_wait();
           if (ch + 1 < ch1) {   // next chunk's TMEM load flies under this chunk's math
             __syncwarp();
-            N2NMN_TMEM_LD(taddr + (ch + 1) * 32, vbuf[(ch + 1 - ch0) & 1]);
+            ptx::tmem_ld_32x32b_x32_nowait(taddr + (ch + 1) * 32, vbuf[(ch + 1 - ch0) & 1]);
           }
-#if defined(N2NMN_EXP_EPI_NONE)
-          continue;
-#endif
           const int col0 = nt * kBN + ch * 32;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 bq = reinterpret_cast<const float4*>(s_bias + ch * 32)[q];
             v[4 * q + 0] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
           }
-#if !defined(N2NMN_EXP_EPI_NOSTORE)
           if (any_store) {
             // lane = row holds 32 consecutive columns; transpose through shared memory (chunk
             // index XOR row keeps both the row-wise writes and the line-wise reads conflict-free)
@@ -353,12 +327,7 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
               if (dstp[i] != nullptr) reinterpret_cast<float4*>(dstp[i] + col0)[cq] = tq[i];
             __syncwarp();
           }
-#endif
-#if defined(N2NMN_EXP_EPI_NOMATH)
-          if (false) {
-#else
           if (n_max > 0) {
-#endif
             const bool first = (nt == 0 && ch == ch0);   // first chunk of the tile: overwrite
             if (staged) {
               // num += m·(τ∘w2) ; den += m²·τ²  — two-wide fp32 FMAs and two independent partial
@@ -424,16 +393,15 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
           }
           if (warp == 4) N2NMN_STAMP(1, 24 + ch);
         }
-        // release the accumulator buffer to the MMA warp
+        // release the accumulator buffer to the leader's MMA warp
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) ptx::mbar_arrive_cluster(tmem_empty_leader[acc]);
       }
       if (warp == 4) N2NMN_STAMP(1, 7);
       // the two column halves of a row meet here
       if (wk.set == PS_FIND) {
         asm volatile("bar.sync 2, 256;" ::: "memory");
-        if (warp == 4) N2NMN_STAMP(1, 28);
         if (half == 0 && row_ok) {
           const float b2 = __ldg(p.elt_b);
           const float* other = acc_row + kMaxProjNodesPerPass * 2 * kBM;
@@ -444,20 +412,19 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
             p.arena[(size_t)slot * p.HW + pix] = nn * rsqrtf(fmaxf(dd, kEps)) + b2;
           }
         }
-        if (warp == 4) N2NMN_STAMP(1, 29);
         asm volatile("bar.sync 2, 256;" ::: "memory");   // s_part is rewritten by the next tile
-        if (warp == 4) N2NMN_STAMP(1, 30);
       }
     }
   }
 
   if (warp == 4) N2NMN_STAMP(1, 6);
-  // teardown
+  // teardown: the peer may still read its TMEM / the leader's MMAs may still read our operands
+  __syncwarp();   // the single-lane role loops above rejoin their warps before the aligned barrier
   ptx::tc_fence_before();
-  __syncthreads();
+  ptx::cluster_sync_all();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<kTmemCols>(tmem_base);
+    ptx::tmem_dealloc_pair<kTmemCols>(tmem_base);
   }
 }
 

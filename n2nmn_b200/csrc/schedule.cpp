@@ -28,28 +28,38 @@ int text_set_of(int op) {
 int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
                      const int32_t* vocab_ops, int num_vocab, HostSchedule* out,
                      const char** err, bool train) {
+  return compile_schedule_group(shp, &tokens, 1, T, N, vocab_ops, num_vocab, out, err, train);
+}
+
+int compile_schedule_group(const SchedShape& shp, const int32_t* const* tokens_seg, int num_seg,
+                           int T, int N, const int32_t* vocab_ops, int num_vocab,
+                           HostSchedule* out, const char** err, bool train) {
   HostSchedule& S = *out;
   S.reset();
-  S.N = N; S.T = T;
-  S.validity.assign(N, 0);
-  S.q_ptr.assign(N + 1, 0);
+  S.N = N; S.T = T; S.num_seg = num_seg;
+  const int NQ = num_seg * N;
+  S.validity.assign(NQ, 0);
+  S.q_ptr.assign(NQ + 1, 0);
 
-  // tokens are time-major [T,N]: transpose once so that every question is a contiguous row
   static thread_local std::vector<int32_t> tq;
   tq.resize((size_t)N * T);
-  for (int t = 0; t < T; ++t)
-    for (int n = 0; n < N; ++n) tq[(size_t)n * T + t] = tokens[(size_t)t * N + n];
   const int scene_bits = [] { float v = 3.0f; int b; std::memcpy(&b, &v, 4); return b; }();
   S.nodes.clear();
   S.depth.clear();
-  S.nodes.reserve((size_t)N * 8);
-  S.depth.reserve((size_t)N * 8);
+  S.nodes.reserve((size_t)NQ * 8);
+  S.depth.reserve((size_t)NQ * 8);
   // node ids of the question's open attention / answer values (at most one push per token)
   static thread_local std::vector<int> stack_buf;
   stack_buf.resize((size_t)T + 1);
   int* stack = stack_buf.data();
 
+  for (int seg = 0; seg < num_seg; ++seg) {
+  const int32_t* tokens = tokens_seg[seg];
+  // tokens are time-major [T,N]: transpose once so that every question is a contiguous row
+  for (int t = 0; t < T; ++t)
+    for (int n = 0; n < N; ++n) tq[(size_t)n * T + t] = tokens[(size_t)t * N + n];
   for (int n = 0; n < N; ++n) {
+    const int q = seg * N + n;   // question = image index across the segments
     const int32_t* col = tq.data() + (size_t)n * T;
     bool has_eos = false;
     for (int t = 0; t < T; ++t) {
@@ -68,7 +78,7 @@ int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
       const int ar = kArity[op];
       if (sp < ar) { ok = false; break; }   // not enough input
       NodeRec nd;
-      nd.op = op; nd.t = t; nd.b = n;
+      nd.op = op; nd.t = t; nd.b = q;
       nd.in0 = nd.in1 = -1;
       nd.text = -1;
       nd.aux = (op == OP_SCENE) ? scene_bits : -1;
@@ -83,28 +93,29 @@ int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
       }
       if (!ok) break;
       const int id = (int)S.nodes.size();
-      nd.out = kIsAns[op] ? n : id;
+      nd.out = kIsAns[op] ? q : id;
       S.nodes.push_back(nd);
       S.depth.push_back(depth);
       stack[sp++] = id;
     }
     if (ok && !(sp == 1 && kIsAns[S.nodes[stack[0]].op])) ok = false;
     if (ok) {
-      S.validity[n] = 1;
+      S.validity[q] = 1;
       ++S.num_valid;
     } else {
       S.nodes.resize(base);   // an invalid layout contributes no nodes
       S.depth.resize(base);
     }
-    S.q_ptr[n + 1] = (int)S.nodes.size();
+    S.q_ptr[q + 1] = (int)S.nodes.size();
+  }
   }
   (void)err;
   return finalize_schedule(shp, N, out, train);
 }
 
-int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out, bool train) {
+int finalize_schedule(const SchedShape& shp, int images_per_seg, HostSchedule* out, bool train) {
   HostSchedule& S = *out;
-  const int N = num_images;                 // images (rows of the feature grid)
+  const int N = images_per_seg * std::max(1, S.num_seg);   // images over all segments
   const int NQ = (int)S.q_ptr.size() - 1;   // questions (rows of the score matrix)
   const int num_nodes = (int)S.nodes.size();
   S.max_depth = 0;
@@ -192,8 +203,6 @@ int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out, 
       }
     }
   }
-  const int total_rows = N * HW;
-  const int num_tiles = (total_rows + 127) / 128;
   int u_set[NUM_PROJ_SETS] = {0}, u_any = 0;
   for (int n = 0; n < N; ++n) {
     bool any = S.img_ptr[n + 1] > S.img_ptr[n];
@@ -203,27 +212,53 @@ int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out, 
     // (PS_FIND maps stored for training ride along with the fused pass: no extra work items)
     if (any) ++u_any;
   }
-  // Tile-major order: the layers that need the same 128 rows of features are handed to
-  // neighbouring CTAs at about the same time, so the A tile is fetched from HBM once and the
-  // other layers hit it in L2 (matters once the batch no longer fits in L2).
-  S.work.reserve((size_t)num_tiles * 2);
-  for (int tile = 0; tile < num_tiles; ++tile) {
-    const int r0 = tile * 128, r1 = std::min(total_rows, r0 + 128) - 1;
-    const int b0 = r0 / HW, b1 = r1 / HW;
-    int need[NUM_PROJ_SETS] = {0};     // consumers per layer among the tile's images
-    for (int b = b0; b <= b1; ++b) {
-      need[PS_FIND] = std::max(need[PS_FIND], S.img_ptr[b + 1] - S.img_ptr[b]);
-      for (int set = 1; set < NUM_PROJ_SETS; ++set)
-        if (u_set[set] && S.mslot[(size_t)set * N + b] >= 0) need[set] = 1;
-    }
-    for (int set = 0; set < NUM_PROJ_SETS; ++set) {
-      const int passes = (need[set] + kMaxProjNodesPerPass - 1) / kMaxProjNodesPerPass;
-      for (int pass = 0; pass < passes; ++pass) {
-        ProjWork w; w.row0 = r0; w.pass = pass; w.set = set; w.pad = 0;
-        S.work.push_back(w);
+  // Tiles (128 rows of one segment x one layer x one pass of <= 8 Find consumers) in tile-major
+  // order: the layers that need the same 128 rows of features are handed out at about the same
+  // time, so the A tile is fetched from HBM once and the other layers hit it in L2 (matters once
+  // the batch no longer fits in L2). The kernel runs CTA pairs (cta_group::2): two tiles of the
+  // SAME layer form one work item — they share only the weight matrix, so a tile is paired with the
+  // next tile of its layer wherever that one comes from. A layer with an odd tile count gets a
+  // filler half (pass = -1: the MMA runs on a repeated tile, nothing is written).
+  const int seg_rows = images_per_seg * HW;
+  const int tiles_per_seg = (seg_rows + 127) / 128;
+  S.work.reserve((size_t)tiles_per_seg * std::max(1, S.num_seg));
+  struct Half { int row0, seg, pass; bool open; };
+  Half pending[NUM_PROJ_SETS];
+  for (int set = 0; set < NUM_PROJ_SETS; ++set) pending[set].open = false;
+  auto emit = [&](int set, const Half& a, const Half& b) {
+    ProjWork w;
+    w.row0[0] = a.row0; w.seg[0] = a.seg; w.pass[0] = a.pass;
+    w.row0[1] = b.row0; w.seg[1] = b.seg; w.pass[1] = b.pass;
+    w.set = set; w.pad = 0;
+    S.work.push_back(w);
+  };
+  for (int seg = 0; seg < std::max(1, S.num_seg); ++seg) {
+    const int g0 = seg * images_per_seg;
+    for (int tile = 0; tile < tiles_per_seg; ++tile) {
+      const int r0 = tile * 128, r1 = std::min(seg_rows, r0 + 128) - 1;
+      const int b0 = g0 + r0 / HW, b1 = g0 + r1 / HW;
+      int need[NUM_PROJ_SETS] = {0};     // consumers per layer among the tile's images
+      for (int b = b0; b <= b1; ++b) {
+        need[PS_FIND] = std::max(need[PS_FIND], S.img_ptr[b + 1] - S.img_ptr[b]);
+        for (int set = 1; set < NUM_PROJ_SETS; ++set)
+          if (u_set[set] && S.mslot[(size_t)set * N + b] >= 0) need[set] = 1;
+      }
+      for (int set = 0; set < NUM_PROJ_SETS; ++set) {
+        const int passes = (need[set] + kMaxProjNodesPerPass - 1) / kMaxProjNodesPerPass;
+        for (int pass = 0; pass < passes; ++pass) {
+          const Half h{r0, seg, pass, true};
+          if (pending[set].open) { emit(set, pending[set], h); pending[set].open = false; }
+          else pending[set] = h;
+        }
       }
     }
   }
+  for (int set = 0; set < NUM_PROJ_SETS; ++set)
+    if (pending[set].open) {
+      Half filler = pending[set];
+      filler.pass = -1;
+      emit(set, pending[set], filler);
+    }
 
   // ---- shared-memory stack slots for the tree kernel: a map lives from its producer to its
   //      (single) consumer; inputs are released before the output is placed, so in-place reuse

@@ -20,8 +20,9 @@ struct SchedShape {
 struct BwdEntryHost { int32_t set, b; };   // mirrors BwdEntry (backward.cuh)
 
 struct HostSchedule {
-  int N = 0, T = 0, num_valid = 0, max_depth = 0;
-  std::vector<uint8_t> validity;      // [N]
+  int N = 0, T = 0, num_valid = 0, max_depth = 0;   // N = images (questions) per segment
+  int num_seg = 1;                    // batches covered by this schedule (common.cuh: segments)
+  std::vector<uint8_t> validity;      // [num_seg*N]
   std::vector<NodeRec> nodes;         // (question, token) order; node id = index = arena slot
   std::vector<int32_t> depth;         // per node
   std::vector<int32_t> q_ptr;         // [N+1]
@@ -51,6 +52,7 @@ struct HostSchedule {
   // Forget the contents but keep every vector's capacity (the per-step path reuses one object).
   void reset() {
     N = T = num_valid = max_depth = num_mslots = num_find_nodes = max_stack = 0;
+    num_seg = 1;
     validity.clear(); nodes.clear(); depth.clear(); q_ptr.clear(); text_t.clear();
     text_b.clear(); groups.clear(); work.clear(); img_ptr.clear(); node_text.clear();
     node_out.clear(); mslot.clear(); wave_ptr.clear(); wave_nodes.clear();
@@ -65,11 +67,17 @@ struct HostSchedule {
 int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
                      const int32_t* vocab_ops, int num_vocab, HostSchedule* out,
                      const char** err, bool train = false);
+// Same for `num_seg` token matrices [T,N] (independent batches of identical shape evaluated by
+// one set of launches): questions and images are numbered seg*N + n.
+int compile_schedule_group(const SchedShape& shp, const int32_t* const* tokens, int num_seg, int T,
+                           int N, const int32_t* vocab_ops, int num_vocab, HostSchedule* out,
+                           const char** err, bool train = false);
 
 // Builds every derived table (text rows, projection work, waves, traffic accounting) from
-// S.nodes / S.depth / S.q_ptr. `num_images` bounds NodeRec::b. Used by compile_schedule and by the
-// per-module entry point, which fabricates one single-node "question" per call row.
-int finalize_schedule(const SchedShape& shp, int num_images, HostSchedule* out,
+// S.nodes / S.depth / S.q_ptr. `images_per_seg` x S.num_seg bounds NodeRec::b. Used by
+// compile_schedule and by the per-module entry point, which fabricates one single-node
+// "question" per call row.
+int finalize_schedule(const SchedShape& shp, int images_per_seg, HostSchedule* out,
                       bool train = false);
 
 // Fills wave_ptr / wave_nodes (depth-bucketed waves). Idempotent.

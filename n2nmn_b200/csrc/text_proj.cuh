@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256)
 text_proj_kernel(DevModel md, TextBufs tb, TextSetRows rows,
                  const int32_t* __restrict__ text_t, const int32_t* __restrict__ text_b) {
   extern __shared__ float s_dyn[];
-  __shared__ int s_src[kTextRowsPerCta];
+  __shared__ const float* s_src[kTextRowsPerCta];
   pdl_trigger();   // the contraction kernel only needs our output in its epilogue
   if (threadIdx.x == 0) N2NMN_STAMP(0, 0);
   const int Dt = md.Dt, M = md.M, Mp = md.Mp;
@@ -68,10 +68,10 @@ text_proj_kernel(DevModel md, TextBufs tb, TextSetRows rows,
                     : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (threadIdx.x == 0) N2NMN_STAMP(0, 1);
-  // (2) source rows of the group's nodes in the time-major word_vecs: t*N + b
+  // (2) source rows of the group's nodes in the time-major word_vecs: row t*N + b of the segment
   if (threadIdx.x < kTextRowsPerCta) {
     const int r = threadIdx.x;
-    s_src[r] = (r < g.count) ? text_t[g.start + r] * md.N + text_b[g.start + r] : -1;
+    s_src[r] = (r < g.count) ? word_vec_row(md, text_t[g.start + r], text_b[g.start + r]) : nullptr;
   }
   __syncthreads();
   if (threadIdx.x == 0) N2NMN_STAMP(0, 2);
@@ -85,8 +85,8 @@ text_proj_kernel(DevModel md, TextBufs tb, TextSetRows rows,
       xv[u] = 0.f;
       if (i < kTextRowsPerCta * Dt) {
         const int r = i / Dt, k = i - r * Dt;
-        const int src = s_src[r];
-        if (src >= 0) xv[u] = __ldg(md.word_vecs + (size_t)src * Dt + k);
+        const float* src = s_src[r];
+        if (src != nullptr) xv[u] = __ldg(src + k);
       }
     }
 #pragma unroll

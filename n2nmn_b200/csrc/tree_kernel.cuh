@@ -350,7 +350,7 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
   if (threadIdx.x == 0) N2NMN_STAMP(2, 2);
   if (beg == end) {   // invalid layout: zeros(num_choices) (models_clevr/nmn3_model.py:144-155)
     if (co.rank == 0)
-      for (int i = threadIdx.x; i < md.C; i += blockDim.x) c.scores[(size_t)q * md.C + i] = 0.f;
+      for (int i = threadIdx.x; i < md.C; i += blockDim.x) score_row(c, q)[i] = 0.f;
     return;
   }
   // ---- prologue part 2: the question's Find maps (written by the projection kernel's epilogue)
@@ -626,7 +626,7 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
           if (threadIdx.x == 0) N2NMN_STAMP(2, 30);
           const int os = two ? OS_SAMEPROP : OS_DESCRIBE;
           small_fc(s.v2, M, head_w ? head_w : md.out_w[os], md.out_b[os], md.C,
-                   c.scores + (size_t)nd.out * md.C, s.scratch);
+                   score_row(c, nd.out), s.scratch);
         }
         break;
       }
@@ -664,7 +664,7 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
         cp_async_commit_wait_all();
         __syncthreads();
         small_fc(s.z, Lz, head_w ? head_w : md.sc_w[set], md.sc_b[set], md.C,
-                 c.scores + (size_t)nd.out * md.C, s.scratch);
+                 score_row(c, nd.out), s.scratch);
         break;
       }
     }

@@ -193,6 +193,36 @@ class LayoutExecutor:
         self.scores = out
         return out, validity.view(bool)
 
+    def forward_group(self, feats, word_vecs, tokens, outs=None, stream=None):
+        """Several INDEPENDENT batches of identical shape in one set of launches
+        (n2nmn_forward_group; at most the context's max_group). feats / word_vecs: lists of
+        contiguous float32 CUDA tensors [N,H,W,D] / [T,N,Dt]; tokens: list of int32 [T,N] arrays.
+        Returns (list of scores [N,C], list of validity bool[N]); results equal those of separate
+        forward_device calls."""
+        m = self.modules
+        n = len(feats)
+        toks = [t if (t.dtype == np.int32 and t.flags['C_CONTIGUOUS'])
+                else np.ascontiguousarray(t, dtype=np.int32) for t in tokens]
+        T, N = toks[0].shape
+        assert all(t.shape == (T, N) for t in toks) and len(word_vecs) == n and len(toks) == n
+        if outs is None:
+            outs = [torch.empty((N, self.num_choices), dtype=torch.float32, device=m.device)
+                    for _ in range(n)]
+        for f, w in zip(feats, word_vecs):
+            assert f.is_cuda and f.is_contiguous() and f.dtype == torch.float32 and \
+                w.is_cuda and w.is_contiguous() and w.dtype == torch.float32
+        valid = np.empty((n, N), np.uint8)
+        arr = lambda ptrs: (C.c_void_p * n)(*ptrs)
+        _lib.check(self._lib.n2nmn_forward_group(
+            m._h, n, arr([f.data_ptr() for f in feats]), arr([w.data_ptr() for w in word_vecs]),
+            arr([t.ctypes.data for t in toks]), T, N, self._vocab_ptr, len(self.vocab_ops),
+            arr([o.data_ptr() for o in outs]), arr([valid[i].ctypes.data for i in range(n)]),
+            (stream or torch.cuda.current_stream(m.device)).cuda_stream))
+        m.image_feat_grid, m.word_vecs, m.N, m.T = feats[0], word_vecs[0], N, T
+        self._group_keep = (list(feats), list(word_vecs), toks, outs)
+        self.scores = outs[0]
+        return outs, [valid[i].view(bool) for i in range(n)]
+
     def last_step_info(self):
         info = _lib.SchedInfo()
         _lib.check(self._lib.n2nmn_last_step_info(self.modules._h, C.byref(info)))
@@ -257,37 +287,45 @@ class LayoutExecutor:
 
 
 class ExecutorPool:
-    """K LayoutExecutors (one context + one CUDA stream + one native worker thread each) fed
-    round-robin.
+    """K LayoutExecutors (one context + one CUDA stream + one native worker thread each) with
+    dynamic batching of the queued work.
 
-    A batch of 64 questions is a short chain of small kernels that cannot fill 148 SMs on its
-    own; successive batches are independent (eval), so batch i+1's projection kernel can run
-    while batch i's tree kernel drains. The host side of a step (layout compile, table upload,
-    launches) costs about as much as its GPU side, so each context is driven by its own C++ worker
-    thread (csrc/pool.cpp): submit() only queues the batch. Each executor owns its workspaces, so
-    there is no sharing hazard; weights are replicated (a few MB).
+    A batch of 64 questions is a short chain of small kernels (~4 us of tensor work) that cannot
+    fill 148 SMs on its own; successive batches are independent (eval). submit() only queues the
+    batch; each context's C++ worker thread (csrc/pool.cpp) takes up to `max_group` queued batches
+    at a time and runs them with ONE set of launches (n2nmn_forward_group), so the contraction
+    kernel's CTA pairs walk several tiles each and the kernels of different contexts overlap on
+    the GPU. Each executor owns its workspaces, so there is no sharing hazard; weights are
+    replicated (a few MB).
 
         pool.begin(); pool.submit(...) x n; pool.end()   # scores / validity valid after end()
     """
 
     def __init__(self, family, image_feat_grid, word_vecs, num_choices, assembler, weights=None,
-                 num_streams=12, tree_cluster=None, proj_ctas=None, **ctx_kwargs):
+                 num_streams=4, tree_cluster=None, proj_ctas=None, max_group=None, **ctx_kwargs):
+        nb = int(ctx_kwargs.get('max_batch') or image_feat_grid.shape[0])
+        if max_group is None:   # ~512 questions per launch set is enough to fill the chip
+            max_group = 1 if num_streams == 1 else max(1, min(8, 512 // max(nb, 1)))
+        if 'N2NMN_MAX_GROUP' in os.environ:
+            max_group = int(os.environ['N2NMN_MAX_GROUP'])
+        self.max_group = int(max_group)
         first = LayoutExecutor(family, image_feat_grid, word_vecs, num_choices, assembler,
-                               weights=weights, **ctx_kwargs)
+                               weights=weights, max_group=self.max_group, **ctx_kwargs)
         w = first.modules.get_weights()
         self.executors = [first] + [
             LayoutExecutor(family, image_feat_grid, word_vecs, num_choices, assembler, weights=w,
-                           **ctx_kwargs) for _ in range(num_streams - 1)]
+                           max_group=self.max_group, **ctx_kwargs) for _ in range(num_streams - 1)]
         dev = first.modules.device
         # Several batches in flight: throughput, not the latency of one batch, is what counts. The
-        # kernels of a batch are latency chains, so the GPU does more work per second when every
-        # batch is NARROW (one CTA per question, a contraction grid of a few dozen CTAs) and many
-        # of them overlap, than when each batch is spread over all SMs (measured: DESIGN §9).
+        # node kernels of a batch are latency chains, so the GPU does more work per second with
+        # one CTA per question and many questions per launch than with a question spread over a
+        # cluster (measured: DESIGN §9). The contraction kernel keeps the whole grid of CTA pairs:
+        # a group gives every pair several tiles.
         if tree_cluster is None:
-            tree_cluster = 0 if num_streams == 1 else (2 if num_streams < 8 else 1)
+            tree_cluster = 0 if num_streams == 1 else 1
         if proj_ctas is None:
-            proj_ctas = 0 if num_streams < 8 else 32
-        text_ctas = 0 if num_streams < 8 else 1
+            proj_ctas = 0
+        text_ctas = 0 if num_streams == 1 else 1
         if 'N2NMN_TREE_CLUSTER' in os.environ:
             tree_cluster = int(os.environ['N2NMN_TREE_CLUSTER'])
         if 'N2NMN_PROJ_CTAS' in os.environ:
@@ -315,6 +353,12 @@ class ExecutorPool:
                                   (self._lib.n2nmn_pool_last_error() or b'').decode())
         self._h = h
         self._keep = []          # arrays the workers still write to (validity) or read from
+
+    def group_stats(self):
+        """(n2nmn_forward_group calls, batches) the workers have run so far."""
+        g, j = C.c_int64(), C.c_int64()
+        self._lib.n2nmn_pool_group_stats(self._h, C.byref(g), C.byref(j))
+        return int(g.value), int(j.value)
 
     def __len__(self):
         return len(self.executors)
@@ -353,7 +397,7 @@ class ExecutorPool:
         """Queue one batch (device-resident inputs) on the next executor/stream; returns
         (scores, validity, stream). `scores` is ordered on `stream`; `validity` is filled by the
         worker thread and valid after end()."""
-        k = self._i % len(self.executors)
+        k = (self._i // self.max_group) % len(self.executors)   # runs of max_group per context
         self._i += 1
         tok = self._tokens(layout_tokens)
         if out is None:   # allocate on the slot's stream so the caching allocator orders reuse
@@ -376,7 +420,7 @@ class ExecutorPool:
         vectors, the forward pass, and D2H of the scores, all enqueued by the slot's worker on
         the slot's stream (copy engines overlap the other slots' kernels). `scores_host` and the
         returned validity are valid after end() + a stream/device synchronise."""
-        k = self._i % len(self.executors)
+        k = (self._i // self.max_group) % len(self.executors)
         self._i += 1
         tok = self._tokens(layout_tokens)
         for t in (feat_host, word_vecs_host, scores_host):

@@ -44,7 +44,7 @@ class ModulesBase:
     family = None
 
     def __init__(self, image_feat_grid, word_vecs, num_choices, weights=None, device=None,
-                 max_batch=None, max_T=None, flags=0, seed=0):
+                 max_batch=None, max_T=None, flags=0, seed=0, max_group=1):
         self._lib = _lib.lib()
         fam = cfgmod.FAMILIES[self.family]
         if not torch.cuda.is_available():
@@ -66,7 +66,8 @@ class ModulesBase:
                           W=W, D=D, text_dim=Dt, map_dim=fam.map_dim,
                           kernel_size=fam.kernel_size, num_choices=self.num_choices,
                           max_batch=int(max_batch or N), max_T=int(max_T or T),
-                          device=self.device.index or 0, flags=int(flags))
+                          device=self.device.index or 0, flags=int(flags),
+                          max_group=int(max_group))
         self.max_batch, self.max_T = cfg.max_batch, cfg.max_T
         h = C.c_void_p()
         _lib.check(self._lib.n2nmn_create(C.byref(cfg), C.byref(h)))

@@ -267,6 +267,44 @@ def test_executor_pool_threads_match_single_context():
         pool.end()
 
 
+@pytest.mark.parametrize('N', [1, 2, 5, 64])
+def test_forward_group_equals_separate_batches(N):
+    """n2nmn_forward_group: G independent batches in one set of launches give bit-identical scores
+    to G separate calls — every group size up to the capacity, batch sizes whose tile counts are
+    odd (filler half of a CTA pair) or not multiples of a tile, an invalid layout in the middle,
+    and the fp32 CUDA-core contraction as a second opinion."""
+    from n2nmn_b200 import weights as wts
+    H, Wd, D, T, C = 10, 15, 512, 12, 28
+    W = wts.init_weights('clevr', H, Wd, D, C, seed=16, bias_std=0.1)
+    asm = Assembler(synth.vocab_file('clevr'))
+    items = []
+    for i in range(8):
+        f, w = synth.make_inputs(N, H, Wd, D, T, seed=400 + i)
+        tok = synth.random_valid_tokens(asm, N, T, seed=500 + i)
+        items.append((torch.from_numpy(f).cuda(), torch.from_numpy(w).cuda(), tok))
+    items[3][2][:, 0] = asm.name2idx_dict['_Find']      # never terminates: invalid -> zero row
+    for flags in (0, _lib.FLAG_PROJ_FP32_SIMT):
+        ex = make_executor('clevr', items[0][0].cpu().numpy(), items[0][1].cpu().numpy(), C, W,
+                           flags=flags, max_batch=N, max_T=T, max_group=8)
+        single = []
+        for f, w, tok in items:
+            sc, v = ex.forward_device(f, w, tok)
+            single.append((sc.cpu().numpy().copy(), v.copy()))
+        assert not single[3][1][0] and not single[3][0][0].any()
+        for G in (1, 2, 3, 8):
+            outs, valids = ex.forward_group([x[0] for x in items[:G]], [x[1] for x in items[:G]],
+                                            [x[2] for x in items[:G]])
+            torch.cuda.synchronize()
+            for g in range(G):
+                np.testing.assert_array_equal(outs[g].cpu().numpy(), single[g][0])
+                assert valids[g].tolist() == single[g][1].tolist()
+        with pytest.raises(_lib.N2NMNError):   # more batches than the context was created for
+            ex2 = make_executor('clevr', items[0][0].cpu().numpy(), items[0][1].cpu().numpy(), C,
+                                W, max_batch=N, max_T=T, max_group=2)
+            ex2.forward_group([x[0] for x in items[:3]], [x[1] for x in items[:3]],
+                              [x[2] for x in items[:3]])
+
+
 def test_host_e2e_entry_matches_device_path():
     from n2nmn_b200 import weights as wts
     N, H, Wd, D, T, C = 16, 10, 15, 512, 10, 28
@@ -339,11 +377,14 @@ def test_pool_narrow_mode_other_families(family, H, Wd, D, T, C, layouts):
                       synth.histogram_tokens(asm, getattr(synth, layouts), N, T, seed=70 + i)))
     pool = ExecutorPool(family, items[0][0], items[0][1], C, asm, weights=W, num_streams=12,
                         max_batch=N, max_T=T)
-    assert (pool.tree_cluster, pool.proj_ctas, pool.text_ctas_per_group) == (1, 32, 1)
+    assert (pool.tree_cluster, pool.proj_ctas, pool.text_ctas_per_group) == (1, 0, 1)
+    assert pool.max_group == 8
     pool.begin()
     outs = [pool.submit(f, w, tok)[0] for f, w, tok in items]
     pool.end()
     torch.cuda.synchronize()
+    groups, jobs = pool.group_stats()
+    assert jobs == len(items) and 1 <= groups <= jobs
     ref_ex = LayoutExecutor(family, items[0][0], items[0][1], C, asm, weights=W, max_batch=N, max_T=T)
     for (f, w, tok), got in zip(items, outs):
         want, _ = ref_ex.forward_device(f, w, tok)
