@@ -491,15 +491,24 @@ class Bench:
                 'value': self.world * self.B * n_steps / (ms * 1e-3),
                 'trial_values': [self.world * self.B * n_steps / (r[0] * 1e-3) for r in res]}
 
-    def kernel_pass(self, n=40):
-        """Per-launch CUDA events (library profiling mode) of single-context forwards walking the
-        resident batches: {kernel: mean us}, mean algorithmic bytes / flops per launch of each of
-        the three kernels."""
+    def kernel_pass(self, n=30):
+        """Per-launch CUDA events (library profiling mode) of the kernels AS LAUNCHED IN THE TIMED
+        REGION: one context evaluating groups of `max_group` batches per set of launches
+        (n2nmn_forward_group), walking the resident batches: {kernel: mean us per launch}, mean
+        algorithmic bytes / flops per launch of each of the three kernels."""
         ex, acc, nb, nf = self.ex, {}, np.zeros(3), np.zeros(3)
+        G = self.pool.max_group
+        outs = self.outs[:G]
+
+        def run(i):
+            idx = [(i * G + g) % self.P for g in range(G)]
+            ex.forward_group([self.feats[j] for j in idx], [self.wvs[j] for j in idx],
+                             [self.tok(j) for j in idx], outs=outs)
+        for i in range(3):
+            run(i)
         ex.set_profiling(True)
         for i in range(n):
-            ex.forward_device(self.feats[i % self.P], self.wvs[i % self.P], self.tok(i),
-                              out=self.outs[0])
+            run(i)
             for name, us in ex.launch_times():
                 acc.setdefault(name, []).append(us)
             info = ex.last_step_info()
@@ -532,8 +541,11 @@ class Bench:
                 'algorithmic_bytes_per_launch': nb[1], 'flops_per_launch': nf[1],
                 'peak_source': pk['source'] + '; TF32 peak taken as bf16 burst / 2',
                 'share_of_step': kus[proj] / total,
-                'how': 'CUDA events around every launch (library profiling mode), one context, '
-                       'mean of 40 steps over the resident batches'}
+                'batches_per_launch': self.pool.max_group,
+                'how': 'CUDA events around every launch (library profiling mode), one context '
+                       'running groups of %d batches per launch as the pool does in the timed '
+                       'region, mean of 30 groups over the resident batches'
+                       % self.pool.max_group}
         for key, name, k in (('roofline_text', 'text_proj_kernel', 0),
                              ('roofline_tree', 'tree_kernel', 2)):
             if name in kus:
@@ -541,6 +553,7 @@ class Bench:
                 out[key] = {'kernel': name, 'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'],
                             'unit': 'GB/s', 'frac': hf, 'avg_launch_us': kus[name],
                             'algorithmic_bytes_per_launch': nb[k], 'flops_per_launch': nf[k],
+                            'batches_per_launch': self.pool.max_group,
                             'share_of_step': kus[name] / total}
         return out
 

@@ -22,6 +22,7 @@
 #include "schedule.hpp"
 #include "text_proj.cuh"
 #include "tree_kernel.cuh"
+#include "head_kernel.cuh"
 #include "backward.cuh"
 
 using namespace n2nmn;
@@ -68,7 +69,7 @@ struct TableSlot {
 
 struct TableOffsets {
   size_t nodes, q_ptr, text_t, text_b, groups, work, img_ptr, node_text, node_out, mslot,
-      wave_nodes, node_entry, entries, text_set_start, labels, total;
+      wave_nodes, node_entry, entries, text_set_start, labels, head_work, head_list, total;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -110,6 +111,9 @@ struct n2nmn_ctx {
   int arena_slots = 0;
   float* mbuf = nullptr;
   int mbuf_slots = 0;
+  float* pooled = nullptr;     // [2*QB][Kp] pooled feature vectors of Describe / SameProperty roots
+  int head_nn = 16;            // root nodes per head-kernel CTA
+  int head_smem_bytes = 0;
   float* scores_tmp = nullptr;
   TableSlot slots[kTableSlots];
   size_t table_cap = 0;
@@ -269,6 +273,8 @@ TableOffsets table_offsets(const HostSchedule& S) {
   o.entries = take(S.entries.size() * sizeof(BwdEntryHost));
   o.text_set_start = take(S.text_set_start.size() * 4);
   o.labels = take(S.train ? (S.q_ptr.size() - 1) * 4 : 0);
+  o.head_work = take(S.head_work.size() * sizeof(HeadWork));
+  o.head_list = take(S.head_list.size() * 4);
   o.total = off;
   return o;
 }
@@ -295,6 +301,14 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
                cudaStream_t st, bool force_wave = false, bool write_arena = false) {
   const bool use_wave = (c->cfg.flags & N2NMN_FLAG_WAVE_EXECUTOR) || force_wave ||
                         sc->hs.max_stack > c->stack_cap;
+  if (use_wave && sc->hs.pooled_direct) {
+    // the wave executor evaluates Describe / SameProperty from stored fc_att maps: rebuild the
+    // derived tables in that form (layouts deeper than the shared-memory stack end up here)
+    sc->hs.pooled_direct = false;
+    if (int rc = finalize_schedule(sc->shp, sc->hs.N, &sc->hs, false))
+      return fail(rc, "finalize_schedule failed");
+    sc->uid = g_uid++;
+  }
   if (use_wave) build_waves(&sc->hs);
   const HostSchedule& S = sc->hs;
   const TableOffsets o = table_offsets(S);
@@ -326,6 +340,8 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
     put(slot->host, o.node_entry, S.node_entry);
     put(slot->host, o.entries, S.entries);
     put(slot->host, o.text_set_start, S.text_set_start);
+    put(slot->host, o.head_work, S.head_work);
+    put(slot->host, o.head_list, S.head_list);
     if (S.train && c->train_labels)
       std::memcpy(slot->host + o.labels, c->train_labels, (S.q_ptr.size() - 1) * 4);
     CUDA_TRY(cudaMemcpyAsync(slot->dev, slot->host, o.total, cudaMemcpyHostToDevice, st));
@@ -393,14 +409,15 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
       std::memset(&lc, 0, sizeof(lc));
       lc.gridDim = dim3((unsigned)(2 * pairs));
       lc.blockDim = dim3(kProjThreads);
-      lc.dynamicSmemBytes = kProjSmemBytes;
+      lc.dynamicSmemBytes = proj_smem_bytes(S.train);
       lc.stream = st;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[0].val.programmaticStreamSerializationAllowed = 1;
       lc.attrs = attr;
       lc.numAttrs = c->use_pdl ? 1 : 0;
-      CUDA_TRY(cudaLaunchKernelEx(&lc, proj_umma_kernel, c->tmaps, p));
+      if (S.train) CUDA_TRY(cudaLaunchKernelEx(&lc, proj_umma_kernel<true>, c->tmaps, p));
+      else CUDA_TRY(cudaLaunchKernelEx(&lc, proj_umma_kernel<false>, c->tmaps, p));
       prof_mark(c, "proj_umma_kernel", st);
     }
     ++c->launches;
@@ -408,6 +425,7 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
   // ---- K3 node evaluation
   NodeCtx nc;
   nc.md = c->md; nc.tb = c->tb; nc.arena = arena; nc.scores = scores_seg[0]; nc.mbuf = c->mbuf;
+  nc.pooled = c->pooled; nc.pool_pitch = c->Kp;
   const int NQ = (int)S.q_ptr.size() - 1;
   // several segments: question q writes row q % N of segment q / N; one segment: row q (the
   // per-module entry point numbers its call rows beyond the bound batch size)
@@ -460,10 +478,38 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
     lc.numAttrs = na;
     const int wa = (write_arena ? kTreeWriteArena : 0) |
                    (((c->cfg.flags & N2NMN_FLAG_PROJ_FP32_SIMT) || c->fp32_stencil) ? kTreeFp32Stencil : 0);
-    if (ks3) CUDA_TRY(cudaLaunchKernelEx(&lc, tree_kernel<3>, nc, d_nodes, d_qptr, cs, slots, wa));
-    else CUDA_TRY(cudaLaunchKernelEx(&lc, tree_kernel<5>, nc, d_nodes, d_qptr, cs, slots, wa));
+    if (S.pooled_direct) {
+      if (ks3) CUDA_TRY(cudaLaunchKernelEx(&lc, tree_kernel<3, true>, nc, d_nodes, d_qptr, cs, slots, wa));
+      else CUDA_TRY(cudaLaunchKernelEx(&lc, tree_kernel<5, true>, nc, d_nodes, d_qptr, cs, slots, wa));
+    } else {
+      if (ks3) CUDA_TRY(cudaLaunchKernelEx(&lc, tree_kernel<3, false>, nc, d_nodes, d_qptr, cs, slots, wa));
+      else CUDA_TRY(cudaLaunchKernelEx(&lc, tree_kernel<5, false>, nc, d_nodes, d_qptr, cs, slots, wa));
+    }
     ++c->launches;
     prof_mark(c, "tree_kernel", st);
+    // ---- K4 batched answer heads of the attention-pooled roots
+    if (S.pooled_direct && !S.head_work.empty()) {
+      if ((int)S.num_pool_rows > 2 * c->QB)
+        return fail(N2NMN_ERR_CAPACITY, "too many pooled root nodes for this context");
+      cudaLaunchConfig_t hc;
+      std::memset(&hc, 0, sizeof(hc));
+      hc.gridDim = dim3((unsigned)S.head_work.size());
+      hc.blockDim = dim3(kHeadThreads);
+      hc.dynamicSmemBytes = (size_t)c->head_smem_bytes;
+      hc.stream = st;
+      cudaLaunchAttribute hattr[1];
+      hattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      hattr[0].val.programmaticStreamSerializationAllowed = 1;
+      hc.attrs = hattr;
+      hc.numAttrs = c->use_pdl ? 1 : 0;
+      const HeadWork* d_hw = reinterpret_cast<const HeadWork*>(d + o.head_work);
+      const int32_t* d_hl = reinterpret_cast<const int32_t*>(d + o.head_list);
+      if (c->head_nn == 16) CUDA_TRY(cudaLaunchKernelEx(&hc, head_kernel<16>, nc, d_nodes, d_hw, d_hl));
+      else if (c->head_nn == 8) CUDA_TRY(cudaLaunchKernelEx(&hc, head_kernel<8>, nc, d_nodes, d_hw, d_hl));
+      else CUDA_TRY(cudaLaunchKernelEx(&hc, head_kernel<4>, nc, d_nodes, d_hw, d_hl));
+      ++c->launches;
+      prof_mark(c, "head_kernel", st);
+    }
   }
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(slot->last_use, st));
@@ -591,6 +637,9 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
   CUDA_TRY(cudaMalloc(&c->mbuf, (size_t)c->mbuf_slots * c->HW * c->Mp * sizeof(float)));
   CUDA_TRY(cudaMalloc(&c->scores_tmp,
                       (size_t)cfg->max_batch * TT * cfg->num_choices * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&c->pooled, (size_t)2 * NB * c->Kp * sizeof(float)));
+  c->head_nn = head_nodes_per_cta(c->Dk);
+  c->head_smem_bytes = head_smem_layout(c->head_nn, c->Kp, c->Mp).total * (int)sizeof(float);
   if (cfg->family == N2NMN_VQA || (cfg->D % 4) != 0) {
     CUDA_TRY(cudaMalloc(&c->feat_aug, (size_t)NB * c->HW * c->Kp * sizeof(float)));
   }
@@ -600,7 +649,8 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
     const size_t tiles = (size_t)c->G * (((size_t)cfg->max_batch * c->HW + 127) / 128 + 1);
     c->table_cap = nodes * (sizeof(NodeRec) + 4 * 6) + (nodes / 8 + 8) * sizeof(TextGroup) +
                    tiles * (TT / kMaxProjNodesPerPass + 1 + NUM_PROJ_SETS) * sizeof(ProjWork) +
-                   (size_t)NB * (12 + 4 * NUM_PROJ_SETS) + nodes * (4 + 2 * sizeof(BwdEntryHost)) + 4096;
+                   (size_t)NB * (12 + 4 * NUM_PROJ_SETS) + nodes * (4 + 2 * sizeof(BwdEntryHost)) +
+                   (size_t)NB * (4 + sizeof(HeadWork)) + 4096;
     for (int i = 0; i < kTableSlots; ++i) {
       CUDA_TRY(cudaMallocHost(&c->slots[i].host, c->table_cap));
       CUDA_TRY(cudaMalloc(&c->slots[i].dev, c->table_cap));
@@ -619,16 +669,40 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
     if (c->tree_smem_bytes <= 200 * 1024 || c->stack_cap <= 2) break;
     --c->stack_cap;
   }
-  CUDA_TRY(cudaFuncSetAttribute(tree_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_TRY(cudaFuncSetAttribute(tree_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 c->tree_smem_bytes));
-  CUDA_TRY(cudaFuncSetAttribute(tree_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_TRY(cudaFuncSetAttribute(tree_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 c->tree_smem_bytes));
+  CUDA_TRY(cudaFuncSetAttribute(tree_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                c->tree_smem_bytes));
+  CUDA_TRY(cudaFuncSetAttribute(tree_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                c->tree_smem_bytes));
+  CUDA_TRY(cudaFuncSetAttribute(head_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                head_smem_layout(16, c->Kp, c->Mp).total * (int)sizeof(float) <=
+                                        200 * 1024
+                                    ? head_smem_layout(16, c->Kp, c->Mp).total * (int)sizeof(float)
+                                    : 48 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(head_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                head_smem_layout(8, c->Kp, c->Mp).total * (int)sizeof(float) <=
+                                        200 * 1024
+                                    ? head_smem_layout(8, c->Kp, c->Mp).total * (int)sizeof(float)
+                                    : 48 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(head_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                head_smem_layout(4, c->Kp, c->Mp).total * (int)sizeof(float) <=
+                                        200 * 1024
+                                    ? head_smem_layout(4, c->Kp, c->Mp).total * (int)sizeof(float)
+                                    : 48 * 1024));
+  if (c->head_smem_bytes > 200 * 1024)
+    return fail(N2NMN_ERR_ARG, "feature depth too large for the answer-head kernel");
   CUDA_TRY(cudaFuncSetAttribute(wave_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 c->node_smem_bytes));
   CUDA_TRY(cudaFuncSetAttribute(wave_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 c->node_smem_bytes));
-  CUDA_TRY(cudaFuncSetAttribute(proj_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                kProjSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(proj_umma_kernel<true>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, proj_smem_bytes(true)));
+  CUDA_TRY(cudaFuncSetAttribute(proj_umma_kernel<false>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                proj_smem_bytes(false)));
   CUDA_TRY(cudaFuncSetAttribute(
       proj_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
       (int)((kSimtRows * kSimtKChunk + kSimtRows * c->Mp) * sizeof(float))));
@@ -654,6 +728,7 @@ int n2nmn_destroy(n2nmn_ctx* c) {
   cudaFree(c->wbuf);
   for (int s = 0; s < NUM_PROJ_SETS; ++s) { cudaFree(c->proj_wt[s]); cudaFree(c->proj_bias[s]); }
   cudaFree(c->feat_aug); cudaFree(c->tb.tau); cudaFree(c->arena); cudaFree(c->mbuf);
+  cudaFree(c->pooled);
   cudaFree(c->dscores); cudaFree(c->per_sample); cudaFree(c->dtau); cudaFree(c->dmap); cudaFree(c->dstencil);
   cudaFree(c->d_segs); cudaFree(c->d_sumsq);
   cudaFree(c->scores_tmp); cudaFree(c->e2e_feat); cudaFree(c->e2e_wv); cudaFree(c->e2e_scores);
@@ -768,7 +843,9 @@ int n2nmn_compile_schedule(n2nmn_ctx* c, const int32_t* tokens, int T, int N,
   sc->uid = g_uid++;
   sc->shp = c->shp;
   const char* err = nullptr;
-  const int rc = compile_schedule(c->shp, tokens, T, N, vocab_ops, num_vocab, &sc->hs, &err);
+  const bool direct = !(c->cfg.flags & N2NMN_FLAG_WAVE_EXECUTOR);
+  const int rc = compile_schedule_group(c->shp, &tokens, 1, T, N, vocab_ops, num_vocab, &sc->hs,
+                                        &err, false, direct);
   if (rc) { delete sc; return fail(rc, err ? err : "compile_schedule failed"); }
   if (validity_out) std::memcpy(validity_out, sc->hs.validity.data(), N);
   *out = sc;
@@ -827,7 +904,8 @@ int n2nmn_compile_nodes(n2nmn_ctx* c, const int32_t* op, const int32_t* t_idx,
   sc->uid = g_uid++;
   sc->shp = c->shp;
   HostSchedule& S = sc->hs;
-  S.N = nq; S.T = c->cfg.max_T;
+  S.N = c->cfg.max_batch; S.T = c->cfg.max_T;   // batch_idx may name any bound image
+  S.pooled_direct = !(c->cfg.flags & N2NMN_FLAG_WAVE_EXECUTOR);
   S.nodes.resize(n); S.depth.assign(n, 1);
   S.q_ptr.assign(q_ptr, q_ptr + nq + 1);
   S.validity.assign(nq, 0);
@@ -880,7 +958,8 @@ int n2nmn_sched_get_info(const n2nmn_sched* s, n2nmn_sched_info* info) {
   info->num_text_nodes = (int)S.text_t.size();
   info->num_find_nodes = S.num_find_nodes;
   info->num_proj_tiles = (int)S.work.size();
-  info->num_launches = (S.groups.empty() ? 0 : 1) + (S.work.empty() ? 0 : 1) + 1;
+  info->num_launches = (S.groups.empty() ? 0 : 1) + (S.work.empty() ? 0 : 1) + 1 +
+                       (S.head_work.empty() ? 0 : 1);
   info->algorithmic_bytes = S.per_node_bytes;
   info->algorithmic_flops = S.per_node_flops;
   for (int k = 0; k < 3; ++k) { info->kernel_bytes[k] = S.kbytes[k]; info->kernel_flops[k] = S.kflops[k]; }
@@ -1014,8 +1093,9 @@ int n2nmn_forward_group(n2nmn_ctx* c, int num_batches, const float* const* feat_
   n2nmn_sched* sc = &c->step_sched;
   sc->uid = g_uid++;
   const char* err = nullptr;
+  const bool direct = !(c->cfg.flags & N2NMN_FLAG_WAVE_EXECUTOR);
   if (int rc = compile_schedule_group(c->shp, tokens, num_batches, T, N, vocab_ops, num_vocab,
-                                      &sc->hs, &err))
+                                      &sc->hs, &err, false, direct))
     return fail(rc, err ? err : "compile_schedule failed");
   if (validity_out)
     for (int i = 0; i < num_batches; ++i)

@@ -42,8 +42,9 @@ struct NodeRec {
   int32_t out;       // arena slot of the attention output, or score row for answer modules
   int32_t text;      // row in the text-projection buffers (-1 if the module takes no text)
   int32_t aux;       // mbuf slot: FSP conv_image map / Describe fc_att map / SameProperty fc_att_0
-                     // (Scene: the bits of pos_val)
-  int32_t aux2;      // mbuf slot: FSP fc_att map / SameProperty fc_att_1
+                     // (Scene: the bits of pos_val). Schedules with pooled_direct: for Describe /
+                     // SameProperty the row of the pooled-feature buffer instead (head_kernel.cuh)
+  int32_t aux2;      // mbuf slot: FSP fc_att map / SameProperty fc_att_1 (pooled_direct: 2nd row)
   // Slots of the per-question attention stack the tree kernel keeps in shared memory (live maps
   // of one question; an output may reuse the slot of an input it consumes). -1 = none.
   int32_t s0, s1, so;
@@ -90,6 +91,16 @@ constexpr int kTextRowsPerCta = 8;
 // pass = which block of <= 8 Find consumers the fused epilogue serves, or -1 for a filler tile
 // (odd tile count: the MMA runs, nothing is written).
 struct ProjWork { int32_t row0[2], seg[2], pass[2], set, pad; };
+// One CTA of the answer-head kernel (head_kernel.cuh): `count` <= kHeadNodesMax root nodes of
+// the same type (Describe or SameProperty), listed in head_list[first .. first+count).
+struct HeadWork { int32_t first, count, op, pad; };
+constexpr int kHeadNodesMax = 16;
+// Root nodes per head-kernel CTA: their pooled feature rows (Kp floats each) are staged in shared
+// memory, <= 72 KB of it. 16 for D <= 1024, 8 for the VQA grid (D = 2050), else 4.
+__host__ __device__ inline int head_nodes_per_cta(int Dk) {
+  const int kp = (Dk + 31) / 32 * 32;
+  return (16 * kp * 4 <= 72 * 1024) ? 16 : (8 * kp * 4 <= 72 * 1024) ? 8 : 4;
+}
 
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization
 // attribute may start while its predecessor in the stream is still running; it must call

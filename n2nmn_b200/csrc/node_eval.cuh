@@ -24,6 +24,8 @@ struct NodeCtx {
   float* scores_seg[kMaxSeg];
   int score_rows;      // score rows per segment (a huge value when there is one segment)
   const float* mbuf;   // [mslots][HW][Mp]
+  float* pooled;       // [rows][pool_pitch]: pooled feature vectors of Describe / SameProperty
+  int pool_pitch;      //   roots (schedules with pooled_direct: tree kernel -> head kernel)
 };
 
 // score row of question / call row q (numbered across the segments)

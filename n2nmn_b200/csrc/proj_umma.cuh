@@ -40,15 +40,17 @@ constexpr int kBN = 256;           // columns per N-tile (UMMA N)
 constexpr int kBNHalf = kBN / 2;   // weight columns staged by each CTA
 constexpr int kBK = 32;            // fp32 elements per K slice = 128 bytes
 constexpr int kUmmaK = 8;          // K per tcgen05.mma for tf32 (32 bytes)
-#if defined(N2NMN_EXP_STAGES)
-constexpr int kStages = N2NMN_EXP_STAGES;
-#else
-constexpr int kStages = 4;
-#endif
 constexpr int kABytes = kBM * kBK * 4;        // 16384
 constexpr int kBHalfBytes = kBNHalf * kBK * 4;   // 16384
 constexpr int kStageBytes = kABytes + kBHalfBytes;
-constexpr int kRingBytes = kStages * kStageBytes;
+// Ring depth. The MMAs of a slice take ~512 cycles per SM, a TMA box under load needs 1.5-2 K
+// cycles from issue to landing, so the ring has to hold > 4 slices (ncu r2b: with 4 stages the
+// tensor pipe was busy 64 % of the active cycles at 37 % L2 / 31 % DRAM utilisation — waiting on
+// data in flight, not on bandwidth). Evaluation launches get 5 stages by letting the stored-map
+// transpose buffer share the bytes of the staged Find vectors (a tile is either fused-Find or
+// stored, never both); training launches also store the Find maps for the backward pass, need
+// both buffers at once, and run 4 stages.
+__host__ __device__ constexpr int proj_stages(bool store_and_fuse) { return store_and_fuse ? 4 : 5; }
 // Roles are split on warpgroup boundaries so that setmaxnreg can move registers from the producers
 // (which need ~30) to the epilogue warps (which want > 200: a 32-column accumulator chunk in
 // flight, the one being reduced, its squares, and a consumer node's two staged vectors loaded as
@@ -73,18 +75,27 @@ constexpr int kPartFloats = 2 * kMaxProjNodesPerPass * 2 * kBM;
 // 128-byte line (a lane owns a ROW of the accumulator: direct stores touch 32 lines per
 // instruction and the L1 takes one line per cycle — measured 8.2 K cycles per stored tile)
 constexpr int kStoreFloats = (kEpiThreads / 32) * 32 * 32;            // 8 warps x 4 KB
-constexpr int kVecBytes =
-    (2 * kVecFloats + kBN + kPartFloats + kStoreFloats) * 4 + kBM * (int)sizeof(float*);
+static_assert(kStoreFloats <= 2 * kVecFloats, "the store buffer aliases the staged Find vectors");
+__host__ __device__ constexpr int proj_vec_bytes(bool store_and_fuse) {
+  return (2 * kVecFloats + kBN + kPartFloats + (store_and_fuse ? kStoreFloats : 0)) * 4 +
+         kBM * (int)sizeof(float*);
+}
 // dynamic smem: stages + staged vectors + barriers
-constexpr int kProjSmemBytes = kRingBytes + kVecBytes + 256;
+__host__ __device__ constexpr int proj_smem_bytes(bool store_and_fuse) {
+  return proj_stages(store_and_fuse) * kStageBytes + proj_vec_bytes(store_and_fuse) + 256;
+}
 
 struct ProjTensorMaps {
   CUtensorMap a[kMaxSeg];            // features of each segment [rows, Dk] fp32, box 32 x 128
   CUtensorMap b[NUM_PROJ_SETS];      // W^T [Mp, Kp] fp32 (K-major), box 32 x 128 (half an N-tile)
 };
 
+template <bool kStoreAndFuse>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kProjThreads, 1)
 proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) {
+  constexpr int kStages = proj_stages(kStoreAndFuse);
+  constexpr int kRingBytes = kStages * kStageBytes;
+  constexpr int kVecBytes = proj_vec_bytes(kStoreAndFuse);
   // SWIZZLE_128B tiles need 1024-byte alignment. The alignment comes from the declaration, NOT
   // from integer arithmetic on the pointer: that would demote every shared-memory access below
   // to generic LD/ST (measured: the epilogue's staged-vector reads became LD.E.128 and the
@@ -96,8 +107,10 @@ proj_umma_kernel(const __grid_constant__ ProjTensorMaps tm, const ProjParams p) 
   float* s_t2 = s_tw + kVecFloats;                                         // [2][8][256] τ²
   float* s_bias = s_t2 + kVecFloats;
   float* s_part = s_bias + kBN;          // [2 halves][8 nodes][num|den][128 rows]
-  float* s_store = s_part + kPartFloats; // [8 warps][32 rows][32 cols], 16-byte chunks swizzled
-  float** s_rowdst = reinterpret_cast<float**>(s_store + kStoreFloats);   // [128] or nullptr
+  // [8 warps][32 rows][32 cols], 16-byte chunks swizzled
+  float* s_store = kStoreAndFuse ? s_part + kPartFloats : s_tw;
+  float** s_rowdst = reinterpret_cast<float**>(s_part + kPartFloats +
+                                               (kStoreAndFuse ? kStoreFloats : 0));   // [128]
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kRingBytes + kVecBytes);   // leader's is used
   uint64_t* empty = full + kStages;
   uint64_t* tmem_full = empty + kStages;       // [2]

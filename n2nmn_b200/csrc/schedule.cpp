@@ -33,10 +33,11 @@ int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
 
 int compile_schedule_group(const SchedShape& shp, const int32_t* const* tokens_seg, int num_seg,
                            int T, int N, const int32_t* vocab_ops, int num_vocab,
-                           HostSchedule* out, const char** err, bool train) {
+                           HostSchedule* out, const char** err, bool train, bool pooled_direct) {
   HostSchedule& S = *out;
   S.reset();
   S.N = N; S.T = T; S.num_seg = num_seg;
+  S.pooled_direct = pooled_direct && !train;
   const int NQ = num_seg * N;
   S.validity.assign(NQ, 0);
   S.q_ptr.assign(NQ + 1, 0);
@@ -163,6 +164,9 @@ int finalize_schedule(const SchedShape& shp, int images_per_seg, HostSchedule* o
     return slot;
   };
   S.train = train;
+  if (train) S.pooled_direct = false;
+  S.num_pool_rows = 0;
+  S.head_work.clear(); S.head_list.clear();
   S.entries.clear();
   S.node_entry.assign(train ? num_nodes : 0, -1);
   auto entry = [&](int node, int set, int b) {
@@ -181,11 +185,29 @@ int finalize_schedule(const SchedShape& shp, int images_per_seg, HostSchedule* o
       case OP_FIND_SAME_PROPERTY:
         r.aux = want(PS_FSP_IMG, r.b); r.aux2 = want(PS_FSP_ATT, r.b);
         entry(i, PS_FSP_IMG, r.b); entry(i, PS_FSP_ATT, r.b); break;
-      case OP_DESCRIBE: r.aux = want(PS_DESC_ATT, r.b); entry(i, PS_DESC_ATT, r.b); break;
+      case OP_DESCRIBE:
+        if (S.pooled_direct) { r.aux = S.num_pool_rows++; break; }
+        r.aux = want(PS_DESC_ATT, r.b); entry(i, PS_DESC_ATT, r.b); break;
       case OP_SAME_PROPERTY:
+        if (S.pooled_direct) { r.aux = S.num_pool_rows++; r.aux2 = S.num_pool_rows++; break; }
         r.aux = want(PS_SP_ATT0, r.b); r.aux2 = want(PS_SP_ATT1, r.b);
         entry(i, PS_SP_ATT0, r.b); entry(i, PS_SP_ATT1, r.b); break;
       default: break;
+    }
+  }
+  if (S.pooled_direct) {   // head-kernel work: chunks of root nodes of one type
+    const int per = head_nodes_per_cta(shp.Dk);
+    for (int op : {(int)OP_DESCRIBE, (int)OP_SAME_PROPERTY}) {
+      int open = -1;
+      for (int i = 0; i < num_nodes; ++i) {
+        if (S.nodes[i].op != op) continue;
+        if (open < 0 || S.head_work[open].count == per) {
+          open = (int)S.head_work.size();
+          S.head_work.push_back(HeadWork{(int32_t)S.head_list.size(), 0, op, 0});
+        }
+        S.head_list.push_back(i);
+        ++S.head_work[open].count;
+      }
     }
   }
   for (int n = 0; n < N; ++n) S.img_ptr[n + 1] += S.img_ptr[n];
@@ -360,12 +382,18 @@ void account_schedule(const SchedShape& shp, HostSchedule* out) {
         case OP_COUNT: rb = att_b; wb = C * 4; fl = 2 * (hw + 2) * C; kb = rb + wb; kf = fl; break;
         case OP_EQUAL_NUM: case OP_MORE_NUM: case OP_LESS_NUM:
           rb = 2 * att_b; wb = C * 4; fl = 4 * (hw + 2) * C; kb = rb + wb; kf = fl; break;
+        // pooled_direct: the node kernels (tree + head) read the feature tile itself and do the
+        // fc_att product on the pooled vector; else they read the stored [HW,M] map(s)
         case OP_SAME_PROPERTY: rb = tile_b + txt_b + 2 * att_b; wb = C * 4;
-          fl = 2 * pool_f + txt_f + 2 * M * C; kb = 2 * att_b + wb + 2 * hw * M * 4;
-          kf = 4 * hw * M + 2 * M * C; break;
+          fl = 2 * pool_f + txt_f + 2 * M * C;
+          if (S.pooled_direct) { kb = 2 * att_b + wb + tile_b + txt_b; kf = 2 * pool_f + 2 * M * C; }
+          else { kb = 2 * att_b + wb + 2 * hw * M * 4; kf = 4 * hw * M + 2 * M * C; }
+          break;
         case OP_DESCRIBE: rb = tile_b + txt_b + att_b; wb = C * 4;
-          fl = pool_f + txt_f + 2 * M * C; kb = att_b + wb + hw * M * 4;
-          kf = 2 * hw * M + 2 * M * C; break;
+          fl = pool_f + txt_f + 2 * M * C;
+          if (S.pooled_direct) { kb = att_b + wb + tile_b + txt_b; kf = pool_f + 2 * M * C; }
+          else { kb = att_b + wb + hw * M * 4; kf = 2 * hw * M + 2 * M * C; }
+          break;
       }
       S.per_node_bytes += rb + wb;
       S.per_node_flops += fl;

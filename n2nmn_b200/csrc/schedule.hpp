@@ -32,6 +32,14 @@ struct HostSchedule {
   std::vector<int32_t> img_ptr, node_text, node_out, mslot;
   int num_mslots = 0;
   int num_find_nodes = 0;
+  // Evaluation schedules of the tree executor: the attention-pooled answer roots (Describe,
+  // SameProperty) do not get stored fc_att maps from the contraction kernel; the tree kernel writes
+  // their pooled feature vectors Σ_p s_p·X[p,:] and a batched head kernel finishes them
+  // (head_kernel.cuh). Requested by the caller before finalize_schedule; never with `train`.
+  bool pooled_direct = false;
+  int num_pool_rows = 0;               // rows of the pooled-feature buffer in use
+  std::vector<HeadWork> head_work;     // one entry per CTA of the head kernel
+  std::vector<int32_t> head_list;      // node ids, grouped by head_work
   int max_stack = 0;                  // most attention maps of one question alive at once
   std::vector<int32_t> wave_ptr;      // [max_depth+2], wave d = [wave_ptr[d], wave_ptr[d+1])
   std::vector<int32_t> wave_nodes;
@@ -57,6 +65,7 @@ struct HostSchedule {
     text_b.clear(); groups.clear(); work.clear(); img_ptr.clear(); node_text.clear();
     node_out.clear(); mslot.clear(); wave_ptr.clear(); wave_nodes.clear();
     entries.clear(); node_entry.clear(); text_set_start.clear(); train = false;
+    pooled_direct = false; num_pool_rows = 0; head_work.clear(); head_list.clear();
     for (int k = 0; k < 3; ++k) kbytes[k] = kflops[k] = 0;
     per_node_bytes = per_node_flops = 0;
     accounted = false;
@@ -71,7 +80,7 @@ int compile_schedule(const SchedShape& shp, const int32_t* tokens, int T, int N,
 // one set of launches): questions and images are numbered seg*N + n.
 int compile_schedule_group(const SchedShape& shp, const int32_t* const* tokens, int num_seg, int T,
                            int N, const int32_t* vocab_ops, int num_vocab, HostSchedule* out,
-                           const char** err, bool train = false);
+                           const char** err, bool train = false, bool pooled_direct = false);
 
 // Builds every derived table (text rows, projection work, waves, traffic accounting) from
 // S.nodes / S.depth / S.q_ptr. `images_per_seg` x S.num_seg bounds NodeRec::b. Used by
