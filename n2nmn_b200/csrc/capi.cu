@@ -69,7 +69,8 @@ struct TableSlot {
 
 struct TableOffsets {
   size_t nodes, q_ptr, text_t, text_b, groups, work, img_ptr, node_text, node_out, mslot,
-      wave_nodes, node_entry, entries, text_set_start, labels, head_work, head_list, total;
+      wave_nodes, node_entry, entries, text_set_start, labels, head_work, head_list, pool_img,
+      total;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -112,6 +113,7 @@ struct n2nmn_ctx {
   float* mbuf = nullptr;
   int mbuf_slots = 0;
   float* pooled = nullptr;     // [2*QB][Kp] pooled feature vectors of Describe / SameProperty roots
+  float* pool_att = nullptr;   // [2*QB][HWp] their softmaxed attention weights
   int head_nn = 16;            // root nodes per head-kernel CTA
   int head_smem_bytes = 0;
   float* scores_tmp = nullptr;
@@ -275,6 +277,7 @@ TableOffsets table_offsets(const HostSchedule& S) {
   o.labels = take(S.train ? (S.q_ptr.size() - 1) * 4 : 0);
   o.head_work = take(S.head_work.size() * sizeof(HeadWork));
   o.head_list = take(S.head_list.size() * 4);
+  o.pool_img = take(S.pool_img.size() * 4);
   o.total = off;
   return o;
 }
@@ -342,6 +345,7 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
     put(slot->host, o.text_set_start, S.text_set_start);
     put(slot->host, o.head_work, S.head_work);
     put(slot->host, o.head_list, S.head_list);
+    put(slot->host, o.pool_img, S.pool_img);
     if (S.train && c->train_labels)
       std::memcpy(slot->host + o.labels, c->train_labels, (S.q_ptr.size() - 1) * 4);
     CUDA_TRY(cudaMemcpyAsync(slot->dev, slot->host, o.total, cudaMemcpyHostToDevice, st));
@@ -425,7 +429,7 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
   // ---- K3 node evaluation
   NodeCtx nc;
   nc.md = c->md; nc.tb = c->tb; nc.arena = arena; nc.scores = scores_seg[0]; nc.mbuf = c->mbuf;
-  nc.pooled = c->pooled; nc.pool_pitch = c->Kp;
+  nc.pooled = c->pooled; nc.pool_pitch = c->Kp; nc.pool_att = c->pool_att;
   const int NQ = (int)S.q_ptr.size() - 1;
   // several segments: question q writes row q % N of segment q / N; one segment: row q (the
   // per-module entry point numbers its call rows beyond the bound batch size)
@@ -502,6 +506,18 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
       hattr[0].val.programmaticStreamSerializationAllowed = 1;
       hc.attrs = hattr;
       hc.numAttrs = c->use_pdl ? 1 : 0;
+      {   // pooled features: one CTA per (root row, 128-channel chunk)
+        const int HWp = (c->HW + 3) & ~3;
+        cudaLaunchConfig_t pc = hc;
+        const int quads = c->md.feat_pitch / 4;
+        pc.gridDim = dim3((unsigned)S.num_pool_rows, (unsigned)((quads + kPoolQuads - 1) / kPoolQuads));
+        pc.blockDim = dim3(kPoolQuads * kPoolSlices);
+        pc.dynamicSmemBytes = (size_t)(HWp + 4 * kPoolQuads * kPoolSlices) * sizeof(float);
+        CUDA_TRY(cudaLaunchKernelEx(&pc, pool_kernel, nc,
+                                    reinterpret_cast<const int32_t*>(d + o.pool_img), HWp));
+        ++c->launches;
+        prof_mark(c, "pool_kernel", st);
+      }
       const HeadWork* d_hw = reinterpret_cast<const HeadWork*>(d + o.head_work);
       const int32_t* d_hl = reinterpret_cast<const int32_t*>(d + o.head_list);
       if (c->head_nn == 16) CUDA_TRY(cudaLaunchKernelEx(&hc, head_kernel<16>, nc, d_nodes, d_hw, d_hl));
@@ -638,7 +654,8 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
   CUDA_TRY(cudaMalloc(&c->scores_tmp,
                       (size_t)cfg->max_batch * TT * cfg->num_choices * sizeof(float)));
   CUDA_TRY(cudaMalloc(&c->pooled, (size_t)2 * NB * c->Kp * sizeof(float)));
-  c->head_nn = head_nodes_per_cta(c->Dk);
+  CUDA_TRY(cudaMalloc(&c->pool_att, (size_t)2 * NB * ((c->HW + 3) & ~3) * sizeof(float)));
+  c->head_nn = head_nodes_per_cta(c->Dk, c->Mp);
   c->head_smem_bytes = head_smem_layout(c->head_nn, c->Kp, c->Mp).total * (int)sizeof(float);
   if (cfg->family == N2NMN_VQA || (cfg->D % 4) != 0) {
     CUDA_TRY(cudaMalloc(&c->feat_aug, (size_t)NB * c->HW * c->Kp * sizeof(float)));
@@ -650,7 +667,7 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
     c->table_cap = nodes * (sizeof(NodeRec) + 4 * 6) + (nodes / 8 + 8) * sizeof(TextGroup) +
                    tiles * (TT / kMaxProjNodesPerPass + 1 + NUM_PROJ_SETS) * sizeof(ProjWork) +
                    (size_t)NB * (12 + 4 * NUM_PROJ_SETS) + nodes * (4 + 2 * sizeof(BwdEntryHost)) +
-                   (size_t)NB * (4 + sizeof(HeadWork)) + 4096;
+                   (size_t)NB * (4 + 8 + sizeof(HeadWork)) + 4096;
     for (int i = 0; i < kTableSlots; ++i) {
       CUDA_TRY(cudaMallocHost(&c->slots[i].host, c->table_cap));
       CUDA_TRY(cudaMalloc(&c->slots[i].dev, c->table_cap));
@@ -728,7 +745,7 @@ int n2nmn_destroy(n2nmn_ctx* c) {
   cudaFree(c->wbuf);
   for (int s = 0; s < NUM_PROJ_SETS; ++s) { cudaFree(c->proj_wt[s]); cudaFree(c->proj_bias[s]); }
   cudaFree(c->feat_aug); cudaFree(c->tb.tau); cudaFree(c->arena); cudaFree(c->mbuf);
-  cudaFree(c->pooled);
+  cudaFree(c->pooled); cudaFree(c->pool_att);
   cudaFree(c->dscores); cudaFree(c->per_sample); cudaFree(c->dtau); cudaFree(c->dmap); cudaFree(c->dstencil);
   cudaFree(c->d_segs); cudaFree(c->d_sumsq);
   cudaFree(c->scores_tmp); cudaFree(c->e2e_feat); cudaFree(c->e2e_wv); cudaFree(c->e2e_scores);

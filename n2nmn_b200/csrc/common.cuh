@@ -95,11 +95,16 @@ struct ProjWork { int32_t row0[2], seg[2], pass[2], set, pad; };
 // the same type (Describe or SameProperty), listed in head_list[first .. first+count).
 struct HeadWork { int32_t first, count, op, pad; };
 constexpr int kHeadNodesMax = 16;
-// Root nodes per head-kernel CTA: their pooled feature rows (Kp floats each) are staged in shared
-// memory, <= 72 KB of it. 16 for D <= 1024, 8 for the VQA grid (D = 2050), else 4.
-__host__ __device__ inline int head_nodes_per_cta(int Dk) {
+// Root nodes per head-kernel CTA: their pooled feature rows (Kp floats each, kept as a TF32 hi and
+// a lo plane), the two fc_att outputs [nn][Mp] and 16 KB of scratch share <= 160 KB of shared
+// memory (head_smem_layout). 16 for CLEVR, 8 for the stress grid, 4 for VQA.
+__host__ __device__ inline int head_smem_floats(int nn, int pitch, int Mp) {
+  return 2 * nn * (pitch + 4) + 2 * nn * Mp + 8 * kHeadNodesMax * 32;
+}
+__host__ __device__ inline int head_nodes_per_cta(int Dk, int Mp) {
   const int kp = (Dk + 31) / 32 * 32;
-  return (16 * kp * 4 <= 72 * 1024) ? 16 : (8 * kp * 4 <= 72 * 1024) ? 8 : 4;
+  return (head_smem_floats(16, kp, Mp) * 4 <= 160 * 1024) ? 16
+         : (head_smem_floats(8, kp, Mp) * 4 <= 160 * 1024) ? 8 : 4;
 }
 
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization

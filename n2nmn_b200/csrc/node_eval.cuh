@@ -24,8 +24,12 @@ struct NodeCtx {
   float* scores_seg[kMaxSeg];
   int score_rows;      // score rows per segment (a huge value when there is one segment)
   const float* mbuf;   // [mslots][HW][Mp]
-  float* pooled;       // [rows][pool_pitch]: pooled feature vectors of Describe / SameProperty
-  int pool_pitch;      //   roots (schedules with pooled_direct: tree kernel -> head kernel)
+  // schedules with pooled_direct (Describe / SameProperty roots): tree kernel -> pool_att
+  // [rows][HWp] softmaxed attention weights -> pool kernel -> pooled [rows][pool_pitch] feature
+  // vectors -> head kernel -> scores
+  float* pool_att;
+  float* pooled;
+  int pool_pitch;
 };
 
 // score row of question / call row q (numbered across the segments)

@@ -166,7 +166,7 @@ int finalize_schedule(const SchedShape& shp, int images_per_seg, HostSchedule* o
   S.train = train;
   if (train) S.pooled_direct = false;
   S.num_pool_rows = 0;
-  S.head_work.clear(); S.head_list.clear();
+  S.head_work.clear(); S.head_list.clear(); S.pool_img.clear();
   S.entries.clear();
   S.node_entry.assign(train ? num_nodes : 0, -1);
   auto entry = [&](int node, int set, int b) {
@@ -186,17 +186,21 @@ int finalize_schedule(const SchedShape& shp, int images_per_seg, HostSchedule* o
         r.aux = want(PS_FSP_IMG, r.b); r.aux2 = want(PS_FSP_ATT, r.b);
         entry(i, PS_FSP_IMG, r.b); entry(i, PS_FSP_ATT, r.b); break;
       case OP_DESCRIBE:
-        if (S.pooled_direct) { r.aux = S.num_pool_rows++; break; }
+        if (S.pooled_direct) { r.aux = S.num_pool_rows++; S.pool_img.push_back(r.b); break; }
         r.aux = want(PS_DESC_ATT, r.b); entry(i, PS_DESC_ATT, r.b); break;
       case OP_SAME_PROPERTY:
-        if (S.pooled_direct) { r.aux = S.num_pool_rows++; r.aux2 = S.num_pool_rows++; break; }
+        if (S.pooled_direct) {
+          r.aux = S.num_pool_rows++; r.aux2 = S.num_pool_rows++;
+          S.pool_img.push_back(r.b); S.pool_img.push_back(r.b);
+          break;
+        }
         r.aux = want(PS_SP_ATT0, r.b); r.aux2 = want(PS_SP_ATT1, r.b);
         entry(i, PS_SP_ATT0, r.b); entry(i, PS_SP_ATT1, r.b); break;
       default: break;
     }
   }
   if (S.pooled_direct) {   // head-kernel work: chunks of root nodes of one type
-    const int per = head_nodes_per_cta(shp.Dk);
+    const int per = head_nodes_per_cta(shp.Dk, shp.Mp);
     for (int op : {(int)OP_DESCRIBE, (int)OP_SAME_PROPERTY}) {
       int open = -1;
       for (int i = 0; i < num_nodes; ++i) {

@@ -602,60 +602,15 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
         __syncthreads();
         if (threadIdx.x == 0) N2NMN_STAMP(2, 27);
         if (kDirect) {
-          // f = Σ_p s_p·X_b[p,:] (reduce_sum(image_feat_grid * att_softmax, [1,2]),
-          // nmn3_modules.py:432-440, 482-487): one pass over the image's feature rows, both
-          // attention inputs of SameProperty share it. Threads = (channel quad, pixel slice).
+          // evaluation: hand the (already softmaxed) attention weights to the pooling kernel
+          // (head_kernel.cuh: f = Σ_p s_p·X_b[p,:], then fc_att / l2norm / fc_eltwise batched over
+          // many root nodes); this question is done
           if (co.rank == 0) {
-            const int seg = nd.b / md.N;
-            const float* __restrict__ X =
-                md.feat_seg[seg] + (size_t)(nd.b - seg * md.N) * HW * md.feat_pitch;
-            const int quads = md.feat_pitch >> 2;
-            const int Qn = min(quads, (int)blockDim.x), slices = blockDim.x / Qn;
-            const int q = threadIdx.x % Qn, sl = threadIdx.x / Qn;
-            float* f0 = c.pooled + (size_t)nd.aux * c.pool_pitch;
-            float* f1 = two ? c.pooled + (size_t)nd.aux2 * c.pool_pitch : nullptr;
-            for (int qb = q; qb < quads; qb += Qn) {
-              float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
-              if (sl < slices) {
-                const float4* xp = reinterpret_cast<const float4*>(X) + qb;
-#pragma unroll 8
-                for (int p = sl; p < HW; p += slices) {
-                  const float4 x = __ldg(xp + (size_t)p * quads);
-                  const float w0 = s.a0[p];
-                  A.x = fmaf(w0, x.x, A.x); A.y = fmaf(w0, x.y, A.y);
-                  A.z = fmaf(w0, x.z, A.z); A.w = fmaf(w0, x.w, A.w);
-                  if (two) {
-                    const float w1 = s.a1[p];
-                    B.x = fmaf(w1, x.x, B.x); B.y = fmaf(w1, x.y, B.y);
-                    B.z = fmaf(w1, x.z, B.z); B.w = fmaf(w1, x.w, B.w);
-                  }
-                }
-              }
-              if (slices == 1) {
-                if (sl == 0) {
-                  reinterpret_cast<float4*>(f0)[qb] = A;
-                  if (two) reinterpret_cast<float4*>(f1)[qb] = B;
-                }
-              } else {   // quads <= blockDim: one round; pixel slices meet in shared memory
-                float4* sc4 = reinterpret_cast<float4*>(s.scratch);
-                __syncthreads();
-                if (sl < slices) { sc4[sl * Qn + q] = A; if (two) sc4[(slices + sl) * Qn + q] = B; }
-                __syncthreads();
-                if (sl == 0) {
-                  for (int j = 1; j < slices; ++j) {
-                    const float4 t = sc4[j * Qn + q];
-                    A.x += t.x; A.y += t.y; A.z += t.z; A.w += t.w;
-                  }
-                  reinterpret_cast<float4*>(f0)[qb] = A;
-                } else if (two && sl == 1) {
-                  float4 Bs = sc4[slices * Qn + q];
-                  for (int j = 1; j < slices; ++j) {
-                    const float4 t = sc4[(slices + j) * Qn + q];
-                    Bs.x += t.x; Bs.y += t.y; Bs.z += t.z; Bs.w += t.w;
-                  }
-                  reinterpret_cast<float4*>(f1)[qb] = Bs;
-                }
-              }
+            float* w0 = c.pool_att + (size_t)nd.aux * L.HWp;
+            for (int p = threadIdx.x; p < HW; p += blockDim.x) w0[p] = s.a0[p];
+            if (two) {
+              float* w1 = c.pool_att + (size_t)nd.aux2 * L.HWp;
+              for (int p = threadIdx.x; p < HW; p += blockDim.x) w1[p] = s.a1[p];
             }
           }
           break;

@@ -402,3 +402,59 @@ def test_config5_stress_20x20x1024_depth16():
     depths = [synth.layout_depth(asm, tokens[:, i]) for i in range(12)]
     assert max(depths) >= 12
     _check_family_batch('clevr', 12, 20, 20, 1024, 40, 28, tokens)
+
+
+# ---- BASELINE configs 4 and 5 at their REAL batch sizes: several N-tiles per
+#      work item (Mp = 1024), multi-tile persistent CTA pairs, the reference's 2048(+2) channels
+def _real_size_case(family, N, H, Wd, D, T, C, tokens, seed, group=0):
+    from n2nmn_b200 import weights as wts
+    from n2nmn_b200.executor import ExecutorPool
+    feat, word_vecs = synth.make_inputs(N, H, Wd, D, T, seed=seed)
+    W = wts.init_weights(family, H, Wd, D, C, seed=9, bias_std=0.1)
+    ex = make_executor(family, feat, word_vecs, C, W, max_batch=N, max_T=T)
+    cb = ex.compile_tokens(tokens)
+    scores, arena = ex.run(cb, return_att=True)
+    torch.cuda.synchronize()
+    ref_s, ref_att, valid = _oracle_scores(family, feat, word_vecs, C, W, tokens)
+    assert cb.validity.tolist() == valid.tolist()
+    scores_np, arena = scores.cpu().numpy(), arena.cpu().numpy()
+    err_s = float(np.max(np.abs(scores_np - ref_s)))
+    err_a = 0.0
+    for i, (op, t, b, depth, in0, in1) in enumerate(cb.nodes()):
+        if (b, t) in ref_att:
+            err_a = max(err_a, float(np.max(np.abs(arena[i] - ref_att[(b, t)]))))
+    print(family, 'N', N, 'D', D, 'nodes', cb.info['num_nodes'], 'depth', cb.info['max_depth'],
+          'scores err', err_s, 'att err', err_a, 'max |score|', float(np.abs(ref_s).max()))
+    assert err_s <= 1e-3 and err_a <= 1e-3
+    if group:   # the same batch three times through the pool's dynamic batching: same numbers
+        f, w = torch.from_numpy(feat).cuda(), torch.from_numpy(word_vecs).cuda()
+        del ex
+        pool = ExecutorPool(family, f, w, C, Assembler(synth.vocab_file(family)), weights=W,
+                            num_streams=2, max_batch=N, max_T=T, max_group=group)
+        pool.begin()
+        outs = [pool.submit(f, w, tokens)[0] for _ in range(3)]
+        pool.end()
+        torch.cuda.synchronize()
+        for o in outs:
+            assert float(np.max(np.abs(o.cpu().numpy() - scores_np))) <= 2e-5
+
+
+def test_config4_vqa_batch128_14x14x512():
+    asm = Assembler(synth.vocab_file('vqa'))
+    tokens = synth.histogram_tokens(asm, synth.VQA_LAYOUTS, 128, 13, seed=41)
+    _real_size_case('vqa', 128, 14, 14, 512, 13, 3001, tokens, seed=940, group=3)
+
+
+def test_config4_vqa_batch128_reference_depth_2048():
+    """The reference's own VQA feature depth: res5c 2048 channels + 2 coordinate channels."""
+    asm = Assembler(synth.vocab_file('vqa'))
+    tokens = synth.histogram_tokens(asm, synth.VQA_LAYOUTS, 128, 13, seed=42)
+    _real_size_case('vqa', 128, 14, 14, 2048, 13, 3001, tokens, seed=941)
+
+
+def test_config5_stress_batch128_20x20x1024_depth16():
+    asm = Assembler(synth.vocab_file('clevr'))
+    base = synth.random_valid_tokens(asm, 16, 40, seed=21, ans_weight=0.08, min_depth=8,
+                                     max_depth=16)
+    tokens = np.ascontiguousarray(base[:, np.random.RandomState(5).randint(0, 16, size=128)])
+    _real_size_case('clevr', 128, 20, 20, 1024, 40, 28, tokens, seed=942, group=2)
