@@ -23,6 +23,7 @@
 #ifndef N2NMN_B200_H_
 #define N2NMN_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -309,6 +310,11 @@ int n2nmn_set_proj_ctas(n2nmn_ctx* ctx, int max_ctas);
  * ceil((Mp/64) / n) blocks of 64 output columns. 0 (the default) = one CTA per column block
  * (shortest kernel); 1 = one CTA per group (least SM-time). Tuning only: results are identical. */
 int n2nmn_set_text_ctas_per_group(n2nmn_ctx* ctx, int n);
+
+/* CRC-32C (Castagnoli) of a host buffer, continuing from `crc` (0 to start): the checksum of the
+ * TensorFlow checkpoint format (tf.train.Saver, exp_clevr/eval_clevr.py:90-91) that
+ * n2nmn_b200/checkpoint.py reads and writes. Host only. */
+uint32_t n2nmn_crc32c(const void* data, size_t n, uint32_t crc);
 
 /* Per-launch device time of the last n2nmn_run_schedule in microseconds (CUDA events recorded
  * around every launch when enabled). names/us arrays of length >= capacity. */

@@ -92,6 +92,7 @@ SIGNATURES = {
     'n2nmn_get_launch_times': (C.c_int, [_P, C.POINTER(C.c_char_p), C.POINTER(C.c_float),
                                          C.c_int]),
     'n2nmn_launch_count': (C.c_int64, [_P]),
+    'n2nmn_crc32c': (C.c_uint32, [_P, C.c_size_t, C.c_uint32]),
 }
 
 
