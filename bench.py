@@ -330,11 +330,17 @@ def run_reference_arm(args, rank, world):
             steps = i + 1      # bounded sample (big workloads: seconds per batch)
             break
     el = time.perf_counter() - t0
-    qps = steps * B / el
+    # The CPU arm's step time is bimodal on the many-core box (median 7.6 ms, mean 14-17 ms: a few
+    # steps of > 100 ms, allocator / thread-pool hiccups of the CPU libraries), which made the
+    # baseline differ by 20 % between two runs of the same command. The MEDIAN step is what is
+    # reported: it is the stable figure and the one that favours the reference.
+    med = float(np.median(per))
+    qps = B / med
     line = {
         'impl': 'reference', 'metric': wl['metric'], 'value': qps, 'unit': UNIT,
         'n_gpus': args.gpus, 'steps': steps, 'warmup': args.warmup,
-        'ms_per_step': 1e3 * el / steps, 'median_ms_per_step': 1e3 * float(np.median(per)),
+        'ms_per_step': 1e3 * med, 'mean_ms_per_step': 1e3 * el / steps,
+        'median_ms_per_step': 1e3 * med, 'value_from_mean': steps * B / el,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
         'config': {'workload': workload_title(wl, layouts), 'global_batch': B},

@@ -106,14 +106,15 @@ struct n2nmn_ctx {
   int N = 0, T = 0;
   float* feat_aug = nullptr;   // ctx-owned re-pitched / coordinate-augmented copy
   // workspaces
-  TextBufs tb = {nullptr, nullptr, nullptr};
+  TextBufs tb = {nullptr, nullptr, nullptr, nullptr};
   int text_rows_cap = 0;
   float* arena = nullptr;
   int arena_slots = 0;
   float* mbuf = nullptr;
   int mbuf_slots = 0;
   float* pooled = nullptr;     // [2*QB][Kp] pooled feature vectors of Describe / SameProperty roots
-  float* pool_att = nullptr;   // [2*QB][HWp] their softmaxed attention weights
+  float* pool_att = nullptr;   // [2*QB][HWp] input maps of the answer roots (softmaxed for those)
+  float* conv_quad = nullptr;  // [quad_rows][Mp] Transform quadratic-form matrix (common.cuh)
   int head_nn = 16;            // root nodes per head-kernel CTA
   int head_smem_bytes = 0;
   float* scores_tmp = nullptr;
@@ -365,7 +366,8 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
     dim3 grid(c->text_ctas_per_group > 0 ? std::min(c->text_ctas_per_group, n_cblk) : n_cblk,
               (unsigned)S.groups.size());
     const size_t smem = (size_t)(kTextRowsPerCta * c->cfg.text_dim +
-                                 8 * kTextRowsPerCta * kTextCols) * sizeof(float);
+                                 8 * kTextRowsPerCta * kTextCols +
+                                 2 * kTextRowsPerCta * c->Mp) * sizeof(float);
     TextSetRows tsr;
     for (int i = 0; i <= NUM_TEXT_SETS; ++i) tsr.start[i] = S.text_set_start[i];
     text_proj_kernel<<<grid, 256, smem, st>>>(
@@ -462,7 +464,7 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
     const int slots = std::max(1, S.max_stack);
     lc.dynamicSmemBytes = sizeof(float) * (size_t)tree_smem_layout(
         c->cfg.H, c->cfg.W, c->Mp, c->cfg.kernel_size, c->cfg.map_dim, c->cfg.num_choices,
-        slots).total;
+        slots, S.pooled_direct).total;
     lc.stream = st;
     cudaLaunchAttribute attr[2];
     int na = 0;
@@ -506,11 +508,11 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
       hattr[0].val.programmaticStreamSerializationAllowed = 1;
       hc.attrs = hattr;
       hc.numAttrs = c->use_pdl ? 1 : 0;
-      {   // pooled features: one CTA per (root row, 128-channel chunk)
+      if (S.num_feat_rows > 0) {   // pooled features: one CTA per (root row, 128-channel chunk)
         const int HWp = (c->HW + 3) & ~3;
         cudaLaunchConfig_t pc = hc;
         const int quads = c->md.feat_pitch / 4;
-        pc.gridDim = dim3((unsigned)S.num_pool_rows, (unsigned)((quads + kPoolQuads - 1) / kPoolQuads));
+        pc.gridDim = dim3((unsigned)S.num_feat_rows, (unsigned)((quads + kPoolQuads - 1) / kPoolQuads));
         pc.blockDim = dim3(kPoolQuads * kPoolSlices);
         pc.dynamicSmemBytes = (size_t)(HWp + 4 * kPoolQuads * kPoolSlices) * sizeof(float);
         CUDA_TRY(cudaLaunchKernelEx(&pc, pool_kernel, nc,
@@ -655,6 +657,17 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
                       (size_t)cfg->max_batch * TT * cfg->num_choices * sizeof(float)));
   CUDA_TRY(cudaMalloc(&c->pooled, (size_t)2 * NB * c->Kp * sizeof(float)));
   CUDA_TRY(cudaMalloc(&c->pool_att, (size_t)2 * NB * ((c->HW + 3) & ~3) * sizeof(float)));
+  if (c->cfg.family != N2NMN_VQA) {
+    const int ks = c->cfg.kernel_size;
+    CUDA_TRY(cudaMalloc(&c->conv_quad, (size_t)quad_rows(ks) * c->Mp * sizeof(float)));
+    CUDA_TRY(cudaMemset(c->conv_quad, 0, (size_t)quad_rows(ks) * c->Mp * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c->tb.tq, (size_t)c->text_rows_cap * quad_pitch(ks) * sizeof(float)));
+    md.conv_quad = c->conv_quad;
+    if (quad_pitch(ks) > 3 * c->Mp)
+      return fail(N2NMN_ERR_ARG, "kernel_size too large for this map_dim");
+  }
+  if (2 * (c->HW + 2) * kHeadNodesMax > head_smem_floats(c->head_nn, c->Kp, c->Mp) - 8 * kHeadNodesMax * 32)
+    return fail(N2NMN_ERR_ARG, "grid too large for the answer-head kernel");
   c->head_nn = head_nodes_per_cta(c->Dk, c->Mp);
   c->head_smem_bytes = head_smem_layout(c->head_nn, c->Kp, c->Mp).total * (int)sizeof(float);
   if (cfg->family == N2NMN_VQA || (cfg->D % 4) != 0) {
@@ -745,7 +758,7 @@ int n2nmn_destroy(n2nmn_ctx* c) {
   cudaFree(c->wbuf);
   for (int s = 0; s < NUM_PROJ_SETS; ++s) { cudaFree(c->proj_wt[s]); cudaFree(c->proj_bias[s]); }
   cudaFree(c->feat_aug); cudaFree(c->tb.tau); cudaFree(c->arena); cudaFree(c->mbuf);
-  cudaFree(c->pooled); cudaFree(c->pool_att);
+  cudaFree(c->pooled); cudaFree(c->pool_att); cudaFree(c->conv_quad); cudaFree(c->tb.tq);
   cudaFree(c->dscores); cudaFree(c->per_sample); cudaFree(c->dtau); cudaFree(c->dmap); cudaFree(c->dstencil);
   cudaFree(c->d_segs); cudaFree(c->d_sumsq);
   cudaFree(c->scores_tmp); cudaFree(c->e2e_feat); cudaFree(c->e2e_wv); cudaFree(c->e2e_scores);
@@ -794,6 +807,13 @@ int n2nmn_set_weight(n2nmn_ctx* c, const char* name, const float* src, const int
     } else if (v.kind == VK_PROJ_B) {
       pad_copy_kernel<<<(c->Mp + 255) / 256, 256, 0, st>>>(c->wbuf + v.offset, c->cfg.map_dim,
                                                            c->proj_bias[v.set], c->Mp);
+    }
+    if (c->conv_quad && (v.slot == &c->md.conv_k || v.slot == &c->md.conv_b ||
+                         v.slot == &c->md.elt_w[ES_TRANSFORM])) {
+      // the Transform quadratic-form matrix depends on these three variables
+      conv_quad_kernel<<<quad_rows(c->cfg.kernel_size), 256, 0, st>>>(
+          c->md.conv_k, c->md.conv_b, c->md.elt_w[ES_TRANSFORM], c->cfg.kernel_size,
+          c->cfg.map_dim, c->Mp, c->conv_quad);
     }
     CUDA_TRY(cudaGetLastError());
     v.loaded = true;

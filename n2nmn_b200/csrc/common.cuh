@@ -69,6 +69,8 @@ struct DevModel {
   const float* elt_b[NUM_ELT_SETS];    // [1]
   const float* conv_k;                 // conv_maps [k*k][Mp] (row pitch Mp, zero padded)
   const float* conv_b;                 // [M]
+  // Transform as a quadratic form (quad_rows(ksize) rows x Mp, see conv_quad_kernel in prep.cuh)
+  const float* conv_quad;
   const float* out_w[NUM_OUT_SETS];    // fc_eltwise [M][C]
   const float* out_b[NUM_OUT_SETS];
   const float* sc_w[NUM_SCORE_SETS];   // fc_scores [L][C]
@@ -80,7 +82,24 @@ struct TextBufs {
   float* tau;    // t·W + b
   float* tauw;   // tau ∘ conv_eltwise weights of the consuming module (or tau)
   float* tau2;   // tau²
+  float* tq;     // Transform rows only: [rows][quad_pitch] coefficients (u, Q) of the node
 };
+
+// TransformModule (models_clevr/nmn3_modules.py:185-216) as a quadratic form. With the extended
+// window w̃ = [the k·k taps of the zero-padded input around the pixel, 1] and the extended filter
+// bank K̃ = [conv_maps taps ; conv_maps bias] (n = k·k + 1 rows of M channels):
+//     conv output  A_c = Σ_i w̃_i K̃_ic
+//     numerator    Σ_c A_c τ_c w2_c     = Σ_i w̃_i u_i,          u_i  = Σ_c K̃_ic w2_c · τ_c
+//     denominator  Σ_c (A_c τ_c)²       = Σ_{i<=j} w̃_i w̃_j Q_ij, Q_ij = Σ_c (2-δ_ij) K̃_ic K̃_jc · τ_c²
+// so a node costs n + n(n+1)/2 dot products over the channels (done once, batched over the nodes,
+// in the text kernel against the precomputed matrix `conv_quad`) plus n + n(n+1)/2 FMAs per
+// pixel, instead of k·k·M FMAs per pixel: 7x less arithmetic at k = 5, M = 250, no filter bank
+// in shared memory, and exact fp32 (the round-1 stencil ran on TF32 mma fragments).
+__host__ __device__ inline int quad_n(int ksize) { return ksize * ksize + 1; }
+__host__ __device__ inline int quad_rows(int ksize) {
+  return quad_n(ksize) + quad_n(ksize) * (quad_n(ksize) + 1) / 2;
+}
+__host__ __device__ inline int quad_pitch(int ksize) { return (quad_rows(ksize) + 3) & ~3; }
 
 // Host-compiled launch tables (built by schedule.cpp, consumed by the kernels).
 struct TextGroup { int32_t set, start, count, pad; };   // <= kTextRowsPerCta rows of one text set

@@ -208,7 +208,8 @@ head_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes,
             const HeadWork* __restrict__ work, const int32_t* __restrict__ list) {
   extern __shared__ __align__(16) float head_smem[];
   const DevModel& md = c.md;
-  const int M = md.M, Mp = md.Mp, C = md.C, Dk = md.Dk;
+  const int M = md.M, Mp = md.Mp, C = md.C, Dk = md.Dk, HW = md.HW;
+  const int HWp = (HW + 3) & ~3;
   const float* __restrict__ pooled = c.pooled;
   const int pool_pitch = c.pool_pitch;
   const HeadSmem L = head_smem_layout(NN, pool_pitch, Mp);
@@ -217,82 +218,117 @@ head_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes,
   float* phi1 = phi0 + NN * Mp;
   float* scratch = phi1 + NN * Mp;
   __shared__ int s_node[kHeadNodesMax];
-  __shared__ const float* s_rowp[2][kHeadNodesMax];   // pooled rows of the chunk's nodes
+  __shared__ const float* s_rowp[2][kHeadNodesMax];   // input rows of the chunk's nodes
   __shared__ const float* s_taup[kHeadNodesMax];
   __shared__ float* s_outp[kHeadNodesMax];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   const HeadWork wk = work[blockIdx.x];   // launch tables: uploaded before any kernel of the step
   const int cnt = wk.count;
-  const bool two = (wk.op == OP_SAME_PROPERTY);
+  const bool feat = (wk.op == OP_DESCRIBE || wk.op == OP_SAME_PROPERTY);
+  const bool two = (wk.op == OP_SAME_PROPERTY || wk.op == OP_EQUAL_NUM ||
+                    wk.op == OP_MORE_NUM || wk.op == OP_LESS_NUM);
   if (threadIdx.x < kHeadNodesMax)
     s_node[threadIdx.x] = threadIdx.x < cnt ? list[wk.first + threadIdx.x] : -1;
   __syncthreads();
   if (threadIdx.x < cnt) {   // node records -> pointers (one dependent round trip, not one per use)
     const NodeRec nd = nodes[s_node[threadIdx.x]];
-    s_rowp[0][threadIdx.x] = pooled + (size_t)nd.aux * pool_pitch;
-    s_rowp[1][threadIdx.x] = pooled + (size_t)(two ? nd.aux2 : nd.aux) * pool_pitch;
-    s_taup[threadIdx.x] = c.tb.tau + (size_t)nd.text * Mp;
+    const float* base = feat ? pooled : c.pool_att;
+    const size_t pitch = feat ? (size_t)pool_pitch : (size_t)HWp;
+    s_rowp[0][threadIdx.x] = base + (size_t)nd.aux * pitch;
+    s_rowp[1][threadIdx.x] = base + (size_t)(two ? nd.aux2 : nd.aux) * pitch;
+    s_taup[threadIdx.x] = feat ? c.tb.tau + (size_t)nd.text * Mp : nullptr;
     s_outp[threadIdx.x] = score_row(c, nd.out);
   }
-  pdl_wait();            // the pooled rows come from the pool kernel, tau from the text kernel
+  pdl_wait();            // inputs come from the pool / tree kernel, tau from the text kernel
   __syncthreads();
 
-  for (int which = 0; which < (two ? 2 : 1); ++which) {
-    // ---- the chunk's pooled rows -> shared memory (unused rows = 0)
-    for (int i = threadIdx.x; i < NN * (pool_pitch >> 2); i += kHeadThreads) {
-      const int n = i / (pool_pitch >> 2), q = i - n * (pool_pitch >> 2);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n < cnt && 4 * q < md.feat_pitch)   // (columns beyond the feature pitch: zeros)
-        v = __ldg(reinterpret_cast<const float4*>(s_rowp[which][n]) + q);
-      uint4 hi, lo;
-      split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
-      split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
-      reinterpret_cast<uint4*>(Fs + n * (pool_pitch + 4))[q] = hi;
-      reinterpret_cast<uint4*>(Fs + (NN + n) * (pool_pitch + 4))[q] = lo;
-    }
-    __syncthreads();
-    const int set = two ? (which ? PS_SP_ATT1 : PS_SP_ATT0) : PS_DESC_ATT;
-    head_fc_att<NN>(Fs, pool_pitch + 4, Dk, md.proj_w[set], M, Mp, md.proj_b[set],
-                    which ? phi1 : phi0);
-    __syncthreads();
-  }
-
-  // ---- e = τ∘φ0(∘φ1), l2_normalize over the M channels (nmn3_modules.py:448, 491): a warp per node
-  for (int n = warp; n < cnt; n += kHeadThreads / 32) {
-    const float* tau = s_taup[n];
-    float ss = 0.f;
-    for (int ch = lane; ch < Mp; ch += 32) {
-      float e = 0.f;
-      if (ch < M) {
-        e = tau[ch] * phi0[n * Mp + ch];
-        if (two) e *= phi1[n * Mp + ch];
+  const float* fin;       // [cnt][fpitch] input of the final fc, fL values each
+  int fpitch, fL;
+  const float* __restrict__ Wo;
+  const float* __restrict__ bo;
+  if (feat) {
+    for (int which = 0; which < (two ? 2 : 1); ++which) {
+      // ---- the chunk's pooled rows -> shared memory as TF32 hi / lo planes (unused rows = 0)
+      for (int i = threadIdx.x; i < NN * (pool_pitch >> 2); i += kHeadThreads) {
+        const int n = i / (pool_pitch >> 2), q = i - n * (pool_pitch >> 2);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n < cnt && 4 * q < md.feat_pitch)   // (columns beyond the feature pitch: zeros)
+          v = __ldg(reinterpret_cast<const float4*>(s_rowp[which][n]) + q);
+        uint4 hi, lo;
+        split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
+        split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+        reinterpret_cast<uint4*>(Fs + n * (pool_pitch + 4))[q] = hi;
+        reinterpret_cast<uint4*>(Fs + (NN + n) * (pool_pitch + 4))[q] = lo;
       }
-      phi0[n * Mp + ch] = e;
-      ss = fmaf(e, e, ss);
+      __syncthreads();
+      const int set = two ? (which ? PS_SP_ATT1 : PS_SP_ATT0) : PS_DESC_ATT;
+      head_fc_att<NN>(Fs, pool_pitch + 4, Dk, md.proj_w[set], M, Mp, md.proj_b[set],
+                      which ? phi1 : phi0);
+      __syncthreads();
     }
-    ss = warp_sum(ss);
-    const float inv = rsqrtf(fmaxf(ss, kEps));
-    for (int ch = lane; ch < Mp; ch += 32) phi0[n * Mp + ch] *= inv;
+    // ---- e = τ∘φ0(∘φ1), l2_normalize over the M channels (nmn3_modules.py:448, 491)
+    for (int n = warp; n < cnt; n += kHeadThreads / 32) {
+      const float* tau = s_taup[n];
+      float ss = 0.f;
+      for (int ch = lane; ch < Mp; ch += 32) {
+        float e = 0.f;
+        if (ch < M) {
+          e = tau[ch] * phi0[n * Mp + ch];
+          if (two) e *= phi1[n * Mp + ch];
+        }
+        phi0[n * Mp + ch] = e;
+        ss = fmaf(e, e, ss);
+      }
+      ss = warp_sum(ss);
+      const float inv = rsqrtf(fmaxf(ss, kEps));
+      for (int ch = lane; ch < Mp; ch += 32) phi0[n * Mp + ch] *= inv;
+    }
+    const int os = two ? OS_SAMEPROP : OS_DESCRIBE;
+    fin = phi0; fpitch = Mp; fL = M; Wo = md.out_w[os]; bo = md.out_b[os];
+  } else {
+    // ---- Exist / Count / EqualNum / MoreNum / LessNum (nmn3_modules.py:258-400; SHAPES Answer):
+    //      z = [min, mean, max] or [att(HW), min, max] (x2) from the root's input maps
+    float* z = Fs;
+    const int zp = (2 * (HW + 2) + 3) & ~3;
+    const bool exist = (wk.op == OP_EXIST);
+    for (int n = warp; n < cnt; n += kHeadThreads / 32) {
+      for (int which = 0; which < (two ? 2 : 1); ++which) {
+        const float* a = s_rowp[which][n];
+        float* zo = z + n * zp + which * (HW + 2);
+        float mn = INFINITY, mx = -INFINITY, sm = 0.f;
+        for (int p = lane; p < HW; p += 32) {
+          const float v = __ldg(a + p);
+          if (!exist) zo[p] = v;
+          mn = fminf(mn, v); mx = fmaxf(mx, v); sm += v;
+        }
+        mn = warp_min(mn); mx = warp_max(mx); sm = warp_sum(sm);
+        if (lane == 0) {
+          if (exist) { zo[0] = mn; zo[1] = sm / (float)HW; zo[2] = mx; }
+          else { zo[HW] = mn; zo[HW + 1] = mx; }
+        }
+      }
+    }
+    const int set = exist ? SS_EXIST : (wk.op == OP_COUNT) ? SS_COUNT
+                  : (wk.op == OP_EQUAL_NUM) ? SS_EQUAL : (wk.op == OP_MORE_NUM) ? SS_MORE : SS_LESS;
+    fin = z; fpitch = zp; fL = exist ? 3 : (two ? 2 * (HW + 2) : HW + 2);
+    Wo = md.sc_w[set]; bo = md.sc_b[set];
   }
   __syncthreads();
 
-  // ---- scores = ê·W_out + b_out (fc_eltwise)
-  const int os = two ? OS_SAMEPROP : OS_DESCRIBE;
-  const float* __restrict__ Wo = md.out_w[os];
-  const float* __restrict__ bo = md.out_b[os];
+  // ---- scores = in·W + b (fc_eltwise / fc_scores)
   if (C <= 32) {
-    // warp w < 8 takes the channels k ≡ w (mod 8), lane = class; partial sums meet in `scratch`
+    // warp w < 8 takes the rows k ≡ w (mod 8), lane = class; partial sums meet in `scratch`
     if (warp < 8) {
       float acc[NN];
 #pragma unroll
       for (int n = 0; n < NN; ++n) acc[n] = 0.f;
       if (lane < C) {
 #pragma unroll 4
-        for (int k = warp; k < M; k += 8) {
+        for (int k = warp; k < fL; k += 8) {
           const float w = __ldg(Wo + (size_t)k * C + lane);
 #pragma unroll
-          for (int n = 0; n < NN; ++n) acc[n] = fmaf(phi0[n * Mp + k], w, acc[n]);
+          for (int n = 0; n < NN; ++n) acc[n] = fmaf(fin[n * fpitch + k], w, acc[n]);
         }
       }
 #pragma unroll
@@ -314,10 +350,10 @@ head_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes,
 #pragma unroll
       for (int n = 0; n < NN; ++n) acc[n] = 0.f;
 #pragma unroll 16
-      for (int k = 0; k < M; ++k) {
+      for (int k = 0; k < fL; ++k) {
         const float w = __ldg(Wo + (size_t)k * C + cl);
 #pragma unroll
-        for (int n = 0; n < NN; ++n) acc[n] = fmaf(phi0[n * Mp + k], w, acc[n]);
+        for (int n = 0; n < NN; ++n) acc[n] = fmaf(fin[n * fpitch + k], w, acc[n]);
       }
       const float b = bo[cl];
 #pragma unroll

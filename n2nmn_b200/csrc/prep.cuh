@@ -37,6 +37,34 @@ __global__ void pitch_rows_kernel(const float* __restrict__ src, int rows, int M
     dst[(size_t)r * Mp + c] = (c < M) ? src[(size_t)r * M + c] : 0.f;
 }
 
+// conv_quad [quad_rows(ks)][Mp] (common.cuh: Transform as a quadratic form): rows 0..n-1 =
+// K̃_i ∘ w2, then one row per pair i <= j = (2-δ_ij) K̃_i ∘ K̃_j, with K̃ = [conv_maps taps (row
+// pitch Mp) ; conv_maps bias]. One CTA per row. Re-run whenever one of the three variables changes.
+__global__ void conv_quad_kernel(const float* __restrict__ conv_k, const float* __restrict__ conv_b,
+                                 const float* __restrict__ w2, int ks, int M, int Mp,
+                                 float* __restrict__ out) {
+  const int n = ks * ks + 1, r = blockIdx.x;
+  int i = r, j = -1;
+  if (r >= n) {                        // pair index -> (i, j), i <= j
+    int idx = r - n;
+    i = 0;
+    while (idx >= n - i) { idx -= n - i; ++i; }
+    j = i + idx;
+  }
+  for (int c = threadIdx.x; c < Mp; c += blockDim.x) {
+    float v = 0.f;
+    if (c < M) {
+      const float ki = (i < n - 1) ? conv_k[(size_t)i * Mp + c] : conv_b[c];
+      if (j < 0) v = ki * w2[c];
+      else {
+        const float kj = (j < n - 1) ? conv_k[(size_t)j * Mp + c] : conv_b[c];
+        v = ki * kj * (i == j ? 1.f : 2.f);
+      }
+    }
+    out[(size_t)r * Mp + c] = v;
+  }
+}
+
 // add_spatial_coordinate_map (models_vqa/nmn3_modules.py:11-31): dst[r, :] =
 // [src[r, 0:D], x, y, 0...] with x = linspace(-1,1,W)[col], y = linspace(-1,1,H)[row]; also used
 // (with_coords = 0) to re-pitch feature grids whose channel count is not a multiple of 4.

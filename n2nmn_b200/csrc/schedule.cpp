@@ -165,8 +165,24 @@ int finalize_schedule(const SchedShape& shp, int images_per_seg, HostSchedule* o
   };
   S.train = train;
   if (train) S.pooled_direct = false;
-  S.num_pool_rows = 0;
+  S.num_pool_rows = 0; S.num_feat_rows = 0;
   S.head_work.clear(); S.head_list.clear(); S.pool_img.clear();
+  if (S.pooled_direct) {
+    // rows of the root-input buffer: first the roots that pool image features (Describe: 1 row,
+    // SameProperty: 2 — the pool kernel's grid covers exactly these), then the other answer roots
+    for (int pass = 0; pass < 2; ++pass)
+      for (int i = 0; i < num_nodes; ++i) {
+        NodeRec& r = S.nodes[i];
+        const bool feat = (r.op == OP_DESCRIBE || r.op == OP_SAME_PROPERTY);
+        if (r.op < OP_EXIST || feat != (pass == 0)) continue;
+        const bool two = (r.op == OP_SAME_PROPERTY || r.op == OP_EQUAL_NUM ||
+                          r.op == OP_MORE_NUM || r.op == OP_LESS_NUM);
+        r.aux = S.num_pool_rows++;
+        r.aux2 = two ? S.num_pool_rows++ : -1;
+        if (feat) { S.pool_img.push_back(r.b); if (two) S.pool_img.push_back(r.b); }
+      }
+    S.num_feat_rows = (int)S.pool_img.size();
+  }
   S.entries.clear();
   S.node_entry.assign(train ? num_nodes : 0, -1);
   auto entry = [&](int node, int set, int b) {
@@ -186,14 +202,10 @@ int finalize_schedule(const SchedShape& shp, int images_per_seg, HostSchedule* o
         r.aux = want(PS_FSP_IMG, r.b); r.aux2 = want(PS_FSP_ATT, r.b);
         entry(i, PS_FSP_IMG, r.b); entry(i, PS_FSP_ATT, r.b); break;
       case OP_DESCRIBE:
-        if (S.pooled_direct) { r.aux = S.num_pool_rows++; S.pool_img.push_back(r.b); break; }
+        if (S.pooled_direct) break;
         r.aux = want(PS_DESC_ATT, r.b); entry(i, PS_DESC_ATT, r.b); break;
       case OP_SAME_PROPERTY:
-        if (S.pooled_direct) {
-          r.aux = S.num_pool_rows++; r.aux2 = S.num_pool_rows++;
-          S.pool_img.push_back(r.b); S.pool_img.push_back(r.b);
-          break;
-        }
+        if (S.pooled_direct) break;
         r.aux = want(PS_SP_ATT0, r.b); r.aux2 = want(PS_SP_ATT1, r.b);
         entry(i, PS_SP_ATT0, r.b); entry(i, PS_SP_ATT1, r.b); break;
       default: break;
@@ -201,7 +213,7 @@ int finalize_schedule(const SchedShape& shp, int images_per_seg, HostSchedule* o
   }
   if (S.pooled_direct) {   // head-kernel work: chunks of root nodes of one type
     const int per = head_nodes_per_cta(shp.Dk, shp.Mp);
-    for (int op : {(int)OP_DESCRIBE, (int)OP_SAME_PROPERTY}) {
+    for (int op = OP_EXIST; op < NUM_OPS; ++op) {
       int open = -1;
       for (int i = 0; i < num_nodes; ++i) {
         if (S.nodes[i].op != op) continue;

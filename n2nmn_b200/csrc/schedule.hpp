@@ -37,7 +37,8 @@ struct HostSchedule {
   // their pooled feature vectors Σ_p s_p·X[p,:] and a batched head kernel finishes them
   // (head_kernel.cuh). Requested by the caller before finalize_schedule; never with `train`.
   bool pooled_direct = false;
-  int num_pool_rows = 0;               // rows of the pooled-feature buffer in use
+  int num_pool_rows = 0;               // rows of the root-input buffer in use
+  int num_feat_rows = 0;               // the first rows: roots that pool image features
   std::vector<int32_t> pool_img;       // per row: image index (across the segments)
   std::vector<HeadWork> head_work;     // one entry per CTA of the head kernel
   std::vector<int32_t> head_list;      // node ids, grouped by head_work
@@ -66,7 +67,8 @@ struct HostSchedule {
     text_b.clear(); groups.clear(); work.clear(); img_ptr.clear(); node_text.clear();
     node_out.clear(); mslot.clear(); wave_ptr.clear(); wave_nodes.clear();
     entries.clear(); node_entry.clear(); text_set_start.clear(); train = false;
-    pooled_direct = false; num_pool_rows = 0; head_work.clear(); head_list.clear();
+    pooled_direct = false; num_pool_rows = 0; num_feat_rows = 0; head_work.clear();
+    head_list.clear();
     pool_img.clear();
     for (int k = 0; k < 3; ++k) kbytes[k] = kflops[k] = 0;
     per_node_bytes = per_node_flops = 0;

@@ -11,7 +11,10 @@
 // 16 (column quads) x 16 (K slices) grid: every thread streams ~Dt/16 float4 weight rows with all
 // loads independent (the kernel is latency-bound, so memory-level parallelism is what matters),
 // keeps 8x4 accumulators, and the 16 K slices are reduced through shared memory.
-// Also emits tau∘w_eltwise and tau² so the consumers' epilogues are pure FMAs.
+// Also emits tau∘w_eltwise and tau² so the consumers' epilogues are pure FMAs, and — for the
+// rows of TransformModule — the node's quadratic-form coefficients (common.cuh) as a second small
+// product [8 rows x M] x [M x quad_rows] against md.conv_quad; a Transform group is therefore
+// always handled by ONE CTA (it needs the complete tau rows).
 // Weights are stored with row pitch Mp (zero padded), so padded columns come out as exact zeros.
 #pragma once
 #include "common.cuh"
@@ -36,6 +39,7 @@ text_proj_kernel(DevModel md, TextBufs tb, TextSetRows rows,
   const int Dt = md.Dt, M = md.M, Mp = md.Mp;
   float* s_x = s_dyn;                                 // [8][Dt]
   float* s_red = s_dyn + kTextRowsPerCta * Dt;        // [8 warps][8 rows][64 cols]
+  float* s_tau = s_red + 8 * kTextRowsPerCta * kTextCols;   // [8][Mp] tau, then [8][Mp] tau²
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tx = lane & 15;                    // column quad inside the CTA's 64 columns
   const int ky = warp * 2 + (lane >> 4);       // K slice 0..15
@@ -54,6 +58,10 @@ text_proj_kernel(DevModel md, TextBufs tb, TextSetRows rows,
     g.start = rows.start[set] + gi * kTextRowsPerCta;
     g.count = min(kTextRowsPerCta, rows.start[set + 1] - g.start);
   }
+  // a Transform group: one CTA walks every column block (it needs whole tau rows afterwards)
+  const bool quad = (g.set == TS_TRANSFORM) && md.conv_quad != nullptr;
+  if (quad && blockIdx.x != 0) return;
+  const int cb_step = quad ? 1 : gridDim.x;
   const float* __restrict__ wbase = md.txt_w[g.set] + c0;
   const int es = (g.set == TS_FIND) ? ES_FIND : (g.set == TS_FSP) ? ES_FSP
                : (g.set == TS_TRANSFORM) ? ES_TRANSFORM : -1;
@@ -97,7 +105,7 @@ text_proj_kernel(DevModel md, TextBufs tb, TextSetRows rows,
   }
   __syncthreads();
   if (threadIdx.x == 0) N2NMN_STAMP(0, 3);
-  for (; cblk < n_cblk; cblk += gridDim.x) {
+  for (; cblk < n_cblk; cblk += cb_step) {
   c0 = cblk * kTextCols + tx * 4;
   const float* __restrict__ wb = md.txt_w[g.set] + c0;
   // (4) 8 x 4 accumulators per thread
@@ -153,8 +161,31 @@ text_proj_kernel(DevModel md, TextBufs tb, TextSetRows rows,
     tb.tau[idx] = v;
     tb.tauw[idx] = v * w2;
     tb.tau2[idx] = v * v;
+    if (quad) { s_tau[r * Mp + c] = v; s_tau[(kTextRowsPerCta + r) * Mp + c] = v * v; }
   }
   __syncthreads();   // s_red is reused by the next column block
+  }
+  if (quad) {
+    // (u, Q) of the group's Transform nodes: out[r][o] = Σ_c conv_quad[o][c] · (o < n ? tau : tau²)[r][c]
+    const int nq = quad_rows(md.ksize), n1 = quad_n(md.ksize), qp = quad_pitch(md.ksize);
+    for (int o = threadIdx.x; o < nq; o += blockDim.x) {
+      const float4* __restrict__ krow = reinterpret_cast<const float4*>(md.conv_quad + (size_t)o * Mp);
+      const float* tv = s_tau + (o < n1 ? 0 : kTextRowsPerCta * Mp);
+      float acc[kTextRowsPerCta];
+#pragma unroll
+      for (int r = 0; r < kTextRowsPerCta; ++r) acc[r] = 0.f;
+#pragma unroll 4
+      for (int c4 = 0; c4 < (Mp >> 2); ++c4) {
+        const float4 k4 = __ldg(krow + c4);
+#pragma unroll
+        for (int r = 0; r < kTextRowsPerCta; ++r) {
+          const float4 t4 = *reinterpret_cast<const float4*>(tv + r * Mp + 4 * c4);
+          acc[r] = fmaf(k4.x, t4.x, acc[r]); acc[r] = fmaf(k4.y, t4.y, acc[r]);
+          acc[r] = fmaf(k4.z, t4.z, acc[r]); acc[r] = fmaf(k4.w, t4.w, acc[r]);
+        }
+      }
+      for (int r = 0; r < g.count; ++r) tb.tq[(size_t)(g.start + r) * qp + o] = acc[r];
+    }
   }
   if (threadIdx.x == 0) N2NMN_STAMP(0, 5);
 }
