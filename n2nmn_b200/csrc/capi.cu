@@ -360,22 +360,35 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
 
   c->ev_used = 0;
   prof_mark(c, "begin", st);
-  // ---- K1 text projections
+  // ---- K1 text projections (+ the quadratic-form coefficients of the Transform nodes)
   if (!S.groups.empty()) {
-    const int n_cblk = c->Mp / kTextCols;
-    dim3 grid(c->text_ctas_per_group > 0 ? std::min(c->text_ctas_per_group, n_cblk) : n_cblk,
-              (unsigned)S.groups.size());
-    const size_t smem = (size_t)(kTextRowsPerCta * c->cfg.text_dim +
-                                 8 * kTextRowsPerCta * kTextCols +
-                                 2 * kTextRowsPerCta * c->Mp) * sizeof(float);
+    dim3 grid((unsigned)(c->Mp / kTextCols), (unsigned)S.groups.size());
     TextSetRows tsr;
     for (int i = 0; i <= NUM_TEXT_SETS; ++i) tsr.start[i] = S.text_set_start[i];
-    text_proj_kernel<<<grid, 256, smem, st>>>(
+    text_proj_kernel<<<grid, 256, 0, st>>>(
         c->md, c->tb, tsr,
         reinterpret_cast<const int32_t*>(d + o.text_t),
         reinterpret_cast<const int32_t*>(d + o.text_b));
     ++c->launches;
     prof_mark(c, "text_proj_kernel", st);
+    const int tr0 = S.text_set_start[TS_TRANSFORM];
+    const int trn = S.text_set_start[TS_TRANSFORM + 1] - tr0;
+    if (trn > 0 && c->conv_quad) {
+      cudaLaunchConfig_t qc;
+      std::memset(&qc, 0, sizeof(qc));
+      qc.gridDim = dim3((unsigned)((quad_pitch(c->cfg.kernel_size) + kTextCols - 1) / kTextCols),
+                        (unsigned)((trn + kTileRows - 1) / kTileRows));
+      qc.blockDim = dim3(256);
+      qc.stream = st;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      qa[0].val.programmaticStreamSerializationAllowed = 1;
+      qc.attrs = qa;
+      qc.numAttrs = c->use_pdl ? 1 : 0;
+      CUDA_TRY(cudaLaunchKernelEx(&qc, quad_kernel, c->md, c->tb, tr0, trn));
+      ++c->launches;
+      prof_mark(c, "quad_kernel", st);
+    }
   }
   // ---- K2 conv_image contraction with fused Find / stored FindSameProperty maps
   if (!S.work.empty()) {
@@ -659,8 +672,8 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
   CUDA_TRY(cudaMalloc(&c->pool_att, (size_t)2 * NB * ((c->HW + 3) & ~3) * sizeof(float)));
   if (c->cfg.family != N2NMN_VQA) {
     const int ks = c->cfg.kernel_size;
-    CUDA_TRY(cudaMalloc(&c->conv_quad, (size_t)quad_rows(ks) * c->Mp * sizeof(float)));
-    CUDA_TRY(cudaMemset(c->conv_quad, 0, (size_t)quad_rows(ks) * c->Mp * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c->conv_quad, (size_t)quad_pitch(ks) * c->Mp * sizeof(float)));
+    CUDA_TRY(cudaMemset(c->conv_quad, 0, (size_t)quad_pitch(ks) * c->Mp * sizeof(float)));
     CUDA_TRY(cudaMalloc(&c->tb.tq, (size_t)c->text_rows_cap * quad_pitch(ks) * sizeof(float)));
     md.conv_quad = c->conv_quad;
     if (quad_pitch(ks) > 3 * c->Mp)
@@ -811,7 +824,7 @@ int n2nmn_set_weight(n2nmn_ctx* c, const char* name, const float* src, const int
     if (c->conv_quad && (v.slot == &c->md.conv_k || v.slot == &c->md.conv_b ||
                          v.slot == &c->md.elt_w[ES_TRANSFORM])) {
       // the Transform quadratic-form matrix depends on these three variables
-      conv_quad_kernel<<<quad_rows(c->cfg.kernel_size), 256, 0, st>>>(
+      conv_quad_kernel<<<quad_pitch(c->cfg.kernel_size), 256, 0, st>>>(
           c->md.conv_k, c->md.conv_b, c->md.elt_w[ES_TRANSFORM], c->cfg.kernel_size,
           c->cfg.map_dim, c->Mp, c->conv_quad);
     }

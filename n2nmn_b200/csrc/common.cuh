@@ -69,7 +69,7 @@ struct DevModel {
   const float* elt_b[NUM_ELT_SETS];    // [1]
   const float* conv_k;                 // conv_maps [k*k][Mp] (row pitch Mp, zero padded)
   const float* conv_b;                 // [M]
-  // Transform as a quadratic form (quad_rows(ksize) rows x Mp, see conv_quad_kernel in prep.cuh)
+  // Transform as a quadratic form: [Mp][quad_pitch(ksize)] (conv_quad_kernel in prep.cuh)
   const float* conv_quad;
   const float* out_w[NUM_OUT_SETS];    // fc_eltwise [M][C]
   const float* out_b[NUM_OUT_SETS];
@@ -95,15 +95,19 @@ struct TextBufs {
 // in the text kernel against the precomputed matrix `conv_quad`) plus n + n(n+1)/2 FMAs per
 // pixel, instead of k·k·M FMAs per pixel: 7x less arithmetic at k = 5, M = 250, no filter bank
 // in shared memory, and exact fp32 (the round-1 stencil ran on TF32 mma fragments).
+// Coefficient row of a node: u[0..n), zero padding up to quad_u_pitch (a multiple of 4: a column
+// quad of the coefficient product is then either all-u or all-Q), then the upper triangle of Q row
+// by row; quad_pitch floats in all.
 __host__ __device__ inline int quad_n(int ksize) { return ksize * ksize + 1; }
+__host__ __device__ inline int quad_u_pitch(int ksize) { return (quad_n(ksize) + 3) & ~3; }
 __host__ __device__ inline int quad_rows(int ksize) {
-  return quad_n(ksize) + quad_n(ksize) * (quad_n(ksize) + 1) / 2;
+  return quad_u_pitch(ksize) + quad_n(ksize) * (quad_n(ksize) + 1) / 2;
 }
 __host__ __device__ inline int quad_pitch(int ksize) { return (quad_rows(ksize) + 3) & ~3; }
 
 // Host-compiled launch tables (built by schedule.cpp, consumed by the kernels).
 struct TextGroup { int32_t set, start, count, pad; };   // <= kTextRowsPerCta rows of one text set
-constexpr int kTextRowsPerCta = 8;
+constexpr int kTextRowsPerCta = 64;
 // One work item of the contraction kernel = a PAIR of 128-row tiles of the same weight set, one per
 // CTA of a cta_group::2 pair (the tiles share nothing but the weight matrix, so they may come from
 // different images, passes or segments). row0 = first row inside the segment's [N*HW] row axis;

@@ -37,23 +37,27 @@ __global__ void pitch_rows_kernel(const float* __restrict__ src, int rows, int M
     dst[(size_t)r * Mp + c] = (c < M) ? src[(size_t)r * M + c] : 0.f;
 }
 
-// conv_quad [quad_rows(ks)][Mp] (common.cuh: Transform as a quadratic form): rows 0..n-1 =
-// K̃_i ∘ w2, then one row per pair i <= j = (2-δ_ij) K̃_i ∘ K̃_j, with K̃ = [conv_maps taps (row
-// pitch Mp) ; conv_maps bias]. One CTA per row. Re-run whenever one of the three variables changes.
+// conv_quad^T [Mp][quad_pitch] (common.cuh: Transform as a quadratic form), the B operand of
+// quad_kernel (text_proj.cuh): column o < n: K̃_o ∘ w2; columns [n, quad_u_pitch): zero; then one
+// column per pair i <= j: (2-δ_ij) K̃_i ∘ K̃_j, with K̃ = [conv_maps taps (row pitch Mp) ;
+// conv_maps bias]. One CTA per output column. Re-run whenever one of the three variables changes.
 __global__ void conv_quad_kernel(const float* __restrict__ conv_k, const float* __restrict__ conv_b,
                                  const float* __restrict__ w2, int ks, int M, int Mp,
                                  float* __restrict__ out) {
-  const int n = ks * ks + 1, r = blockIdx.x;
-  int i = r, j = -1;
-  if (r >= n) {                        // pair index -> (i, j), i <= j
-    int idx = r - n;
+  const int n = quad_n(ks), nu = quad_u_pitch(ks), qp = quad_pitch(ks), o = blockIdx.x;
+  int i = o, j = -1;
+  bool zero = false;
+  if (o >= n && o < nu) zero = true;
+  if (o >= nu) {                        // pair index -> (i, j), i <= j
+    int idx = o - nu;
     i = 0;
-    while (idx >= n - i) { idx -= n - i; ++i; }
+    while (i < n && idx >= n - i) { idx -= n - i; ++i; }
     j = i + idx;
+    if (i >= n) zero = true;           // padding columns beyond the last pair
   }
   for (int c = threadIdx.x; c < Mp; c += blockDim.x) {
     float v = 0.f;
-    if (c < M) {
+    if (c < M && !zero) {
       const float ki = (i < n - 1) ? conv_k[(size_t)i * Mp + c] : conv_b[c];
       if (j < 0) v = ki * w2[c];
       else {
@@ -61,7 +65,7 @@ __global__ void conv_quad_kernel(const float* __restrict__ conv_k, const float* 
         v = ki * kj * (i == j ? 1.f : 2.f);
       }
     }
-    out[(size_t)r * Mp + c] = v;
+    out[(size_t)c * qp + o] = v;
   }
 }
 

@@ -1,52 +1,122 @@
-// K1: text projection for every node that takes a text vector.
+// K1: text projection for every node that takes a text vector, and the quadratic-form
+// coefficients of the Transform nodes.
 //   tau[r, :] = word_vecs[t_r, b_r, :] · W_txt[set] + b_txt[set]
 // (fc('fc_text') / fc('text_fc'): models_clevr/nmn3_modules.py:104,167,209,429,478 through
 //  util/cnn.py:116). The gather of _slice_word_vecs (nmn3_modules.py:53-57) is folded into the
-// load: row (t*N + b) of the time-major word_vecs.
+// load: row (t*N + b) of the segment's time-major word_vecs.
 //
-// One CTA = up to 8 nodes of ONE weight set x the 64-column blocks blockIdx.x, blockIdx.x +
-// gridDim.x, ... (gridDim.x = Mp/64: one block per CTA, shortest kernel; gridDim.x = 1: one CTA
-// per node group walks all column blocks and gathers its word vectors once — fewer, longer CTAs,
-// less SM-time, used when many batches are in flight). The 256 threads form a
-// 16 (column quads) x 16 (K slices) grid: every thread streams ~Dt/16 float4 weight rows with all
-// loads independent (the kernel is latency-bound, so memory-level parallelism is what matters),
-// keeps 8x4 accumulators, and the 16 K slices are reduced through shared memory.
-// Also emits tau∘w_eltwise and tau² so the consumers' epilogues are pure FMAs, and — for the
-// rows of TransformModule — the node's quadratic-form coefficients (common.cuh) as a second small
-// product [8 rows x M] x [M x quad_rows] against md.conv_quad; a Transform group is therefore
-// always handled by ONE CTA (it needs the complete tau rows).
+// Both are small dense products  C[r, c] = Σ_k A[r, k] · B[k, c]  with a few hundred to a few
+// thousand rows per launch, done exactly in fp32 on the CUDA cores as one tiled kernel:
+//   CTA tile 64 rows x 64 columns, K in chunks of 32 staged through shared memory (the next chunk
+//   is in registers while the current one is multiplied), 256 threads = 16 column quads x 16 row
+//   quads, 4 x 4 accumulators each: 2 shared-memory loads per 16 FMAs.
+// Round 1 gave every group of 8 rows its own CTA, which streamed the whole weight matrix from L2
+// with a handful of loads in flight: ~1000 SM-cycles per row against ~600 of FMA issue at peak.
+//   text_proj_kernel : A = gathered word vectors (K = Dt), B = W_txt [Dt][Mp]; emits tau,
+//                      tau∘w_eltwise and tau² so the consumers' epilogues are pure FMAs.
+//   quad_kernel      : A = tau (first n outputs) or tau² (the rest) of the Transform rows, K = Mp,
+//                      B = conv_quad^T [Mp][quad_pitch] (common.cuh); emits (u, Q) per node.
 // Weights are stored with row pitch Mp (zero padded), so padded columns come out as exact zeros.
 #pragma once
 #include "common.cuh"
 
 namespace n2nmn {
 
-constexpr int kTextCols = 64;   // output columns per CTA
+constexpr int kTextCols = 64;    // output columns per CTA
+constexpr int kTileK = 32;       // K per shared-memory chunk
+constexpr int kTileRows = kTextRowsPerCta;   // 64 rows per CTA
+static_assert(kTextRowsPerCta == 64, "the tile kernel is written for 64-row groups");
 
-constexpr int kTextKIter = 20;   // K rows per thread per chunk (16 slices x 20 = 320 >= Dt=300)
-
-// Rows of each text weight set, by value: a CTA finds its group without touching global memory,
-// so its weight loads can start immediately.
+// Rows of each text weight set, by value: a CTA finds its group without touching global memory.
 struct TextSetRows { int32_t start[NUM_TEXT_SETS + 1]; };
 
+// One 64 x 64 output tile. a_row(r) -> pointer to row r of A (or nullptr: zeros), K valid values
+// per row; B row pitch ldb; sq_from_col: columns >= this use A² instead of A (quad kernel).
+// acc[i][j] = C[4*ty + i][c0 + 4*tx + j].
+template <class ARow>
+__device__ __forceinline__ void tile_gemm_64x64(ARow a_row, int K, const float* __restrict__ B,
+                                                int ldb, int c0, int ncols, int sq_from_col,
+                                                float (&acc)[4][4]) {
+  __shared__ __align__(16) float As[2][kTileK][kTileRows + 4];   // [k][row], padded
+  __shared__ __align__(16) float Bs[2][kTileK][kTextCols];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  // loader roles: A: thread -> (row = tid / 4, k-quads (tid % 4) and +4); B: (k = tid / 8 ... )
+  const int ar = threadIdx.x >> 2, aq = threadIdx.x & 3;          // 64 rows x 4 threads
+  const int bk = threadIdx.x >> 4, bq = threadIdx.x & 15;         // 16 k-rows x 16 col quads
+  const float* arow = a_row(ar);
+  const bool a_vec = arow != nullptr && (reinterpret_cast<uintptr_t>(arow) & 15) == 0;
+  const bool bcol_ok = c0 + 4 * bq < ncols;
+  float4 ra[2], rb[2];
+  auto load_chunk = [&](int k0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k = k0 + 4 * (aq + 4 * h);
+      ra[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (arow != nullptr) {
+        if (k + 3 < K && a_vec) ra[h] = __ldg(reinterpret_cast<const float4*>(arow + k));
+        else {
+          if (k < K) ra[h].x = __ldg(arow + k);
+          if (k + 1 < K) ra[h].y = __ldg(arow + k + 1);
+          if (k + 2 < K) ra[h].z = __ldg(arow + k + 2);
+          if (k + 3 < K) ra[h].w = __ldg(arow + k + 3);
+        }
+      }
+      const int kb = k0 + bk + 16 * h;
+      rb[h] = (kb < K && bcol_ok)
+                  ? __ldg(reinterpret_cast<const float4*>(B + (size_t)kb * ldb + c0) + bq)
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto store_chunk = [&](int buf) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int kk = 4 * (aq + 4 * h);
+      As[buf][kk][ar] = ra[h].x; As[buf][kk + 1][ar] = ra[h].y;
+      As[buf][kk + 2][ar] = ra[h].z; As[buf][kk + 3][ar] = ra[h].w;
+      *reinterpret_cast<float4*>(&Bs[buf][bk + 16 * h][4 * bq]) = rb[h];
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const bool sq = c0 + 4 * tx >= sq_from_col;
+  const int nchunks = (K + kTileK - 1) / kTileK;
+  load_chunk(0);
+  store_chunk(0);
+  __syncthreads();
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nchunks) load_chunk((ch + 1) * kTileK);   // in flight during the FMAs below
+#pragma unroll
+    for (int k = 0; k < kTileK; ++k) {
+      float4 a = *reinterpret_cast<const float4*>(&As[buf][k][4 * ty]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][4 * tx]);
+      if (sq) { a.x *= a.x; a.y *= a.y; a.z *= a.z; a.w *= a.w; }
+      acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
+      acc[0][2] = fmaf(a.x, b.z, acc[0][2]); acc[0][3] = fmaf(a.x, b.w, acc[0][3]);
+      acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
+      acc[1][2] = fmaf(a.y, b.z, acc[1][2]); acc[1][3] = fmaf(a.y, b.w, acc[1][3]);
+      acc[2][0] = fmaf(a.z, b.x, acc[2][0]); acc[2][1] = fmaf(a.z, b.y, acc[2][1]);
+      acc[2][2] = fmaf(a.z, b.z, acc[2][2]); acc[2][3] = fmaf(a.z, b.w, acc[2][3]);
+      acc[3][0] = fmaf(a.w, b.x, acc[3][0]); acc[3][1] = fmaf(a.w, b.y, acc[3][1]);
+      acc[3][2] = fmaf(a.w, b.z, acc[3][2]); acc[3][3] = fmaf(a.w, b.w, acc[3][3]);
+    }
+    if (ch + 1 < nchunks) {
+      store_chunk(buf ^ 1);     // the other buffer: its readers finished before the last barrier
+      __syncthreads();
+    }
+  }
+}
+
+// grid = (Mp / 64, groups); one group = <= 64 text rows of ONE weight set (schedule.cpp)
 __global__ void __launch_bounds__(256)
 text_proj_kernel(DevModel md, TextBufs tb, TextSetRows rows,
                  const int32_t* __restrict__ text_t, const int32_t* __restrict__ text_b) {
-  extern __shared__ float s_dyn[];
-  __shared__ const float* s_src[kTextRowsPerCta];
   pdl_trigger();   // the contraction kernel only needs our output in its epilogue
   if (threadIdx.x == 0) N2NMN_STAMP(0, 0);
-  const int Dt = md.Dt, M = md.M, Mp = md.Mp;
-  float* s_x = s_dyn;                                 // [8][Dt]
-  float* s_red = s_dyn + kTextRowsPerCta * Dt;        // [8 warps][8 rows][64 cols]
-  float* s_tau = s_red + 8 * kTextRowsPerCta * kTextCols;   // [8][Mp] tau, then [8][Mp] tau²
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tx = lane & 15;                    // column quad inside the CTA's 64 columns
-  const int ky = warp * 2 + (lane >> 4);       // K slice 0..15
-  const int n_cblk = Mp / kTextCols;
-  int cblk = blockIdx.x;
-  int c0 = cblk * kTextCols + tx * 4;
-  TextGroup g;   // blockIdx.y-th group of <= 8 rows, groups never straddle weight sets
+  const int M = md.M, Mp = md.Mp;
+  TextGroup g;   // blockIdx.y-th group, groups never straddle weight sets
   {
     int gi = blockIdx.y, set = 0;
     for (; set < NUM_TEXT_SETS; ++set) {
@@ -58,136 +128,69 @@ text_proj_kernel(DevModel md, TextBufs tb, TextSetRows rows,
     g.start = rows.start[set] + gi * kTextRowsPerCta;
     g.count = min(kTextRowsPerCta, rows.start[set + 1] - g.start);
   }
-  // a Transform group: one CTA walks every column block (it needs whole tau rows afterwards)
-  const bool quad = (g.set == TS_TRANSFORM) && md.conv_quad != nullptr;
-  if (quad && blockIdx.x != 0) return;
-  const int cb_step = quad ? 1 : gridDim.x;
-  const float* __restrict__ wbase = md.txt_w[g.set] + c0;
   const int es = (g.set == TS_FIND) ? ES_FIND : (g.set == TS_FSP) ? ES_FSP
                : (g.set == TS_TRANSFORM) ? ES_TRANSFORM : -1;
-
-  // (1) this thread's weight rows of the first chunk: independent of everything else, so the
-  //     loads fly while the word vectors are being gathered
-  float4 w[kTextKIter];
-#pragma unroll
-  for (int j = 0; j < kTextKIter; ++j) {
-    const int k = ky + 16 * j;
-    w[j] = (k < Dt) ? __ldg(reinterpret_cast<const float4*>(wbase + (size_t)k * Mp))
-                    : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  if (threadIdx.x == 0) N2NMN_STAMP(0, 1);
-  // (2) source rows of the group's nodes in the time-major word_vecs: row t*N + b of the segment
-  if (threadIdx.x < kTextRowsPerCta) {
-    const int r = threadIdx.x;
-    s_src[r] = (r < g.count) ? word_vec_row(md, text_t[g.start + r], text_b[g.start + r]) : nullptr;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) N2NMN_STAMP(0, 2);
-  // (3) gather the word vectors (all loads of a thread are independent)
-  constexpr int kGather = 10;   // 8 rows x 300 words / 256 threads = 9.4 loads per thread
-  for (int i0 = 0; i0 < kTextRowsPerCta * Dt; i0 += kGather * 256) {
-    float xv[kGather];
-#pragma unroll
-    for (int u = 0; u < kGather; ++u) {
-      const int i = i0 + u * 256 + threadIdx.x;
-      xv[u] = 0.f;
-      if (i < kTextRowsPerCta * Dt) {
-        const int r = i / Dt, k = i - r * Dt;
-        const float* src = s_src[r];
-        if (src != nullptr) xv[u] = __ldg(src + k);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kGather; ++u) {
-      const int i = i0 + u * 256 + threadIdx.x;
-      if (i < kTextRowsPerCta * Dt) s_x[i] = xv[u];
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) N2NMN_STAMP(0, 3);
-  for (; cblk < n_cblk; cblk += cb_step) {
-  c0 = cblk * kTextCols + tx * 4;
-  const float* __restrict__ wb = md.txt_w[g.set] + c0;
-  // (4) 8 x 4 accumulators per thread
-  float4 acc[kTextRowsPerCta];
-#pragma unroll
-  for (int r = 0; r < kTextRowsPerCta; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int kb = 0; kb < Dt; kb += 16 * kTextKIter) {
-    if (kb > 0 || cblk != (int)blockIdx.x) {   // chunk / column block not prefetched above
-#pragma unroll
-      for (int j = 0; j < kTextKIter; ++j) {
-        const int k = kb + ky + 16 * j;
-        w[j] = (k < Dt) ? __ldg(reinterpret_cast<const float4*>(wb + (size_t)k * Mp))
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < kTextKIter; ++j) {
-      const int k = kb + ky + 16 * j;
-      if (k < Dt) {
-#pragma unroll
-        for (int r = 0; r < kTextRowsPerCta; ++r) {
-          const float x = s_x[r * Dt + k];
-          acc[r].x = fmaf(x, w[j].x, acc[r].x); acc[r].y = fmaf(x, w[j].y, acc[r].y);
-          acc[r].z = fmaf(x, w[j].z, acc[r].z); acc[r].w = fmaf(x, w[j].w, acc[r].w);
-        }
-      }
-    }
-  }
+  const int c0 = blockIdx.x * kTextCols;
+  auto a_row = [&](int r) -> const float* {
+    return r < g.count ? word_vec_row(md, text_t[g.start + r], text_b[g.start + r]) : nullptr;
+  };
+  float acc[4][4];
+  tile_gemm_64x64(a_row, md.Dt, md.txt_w[g.set], Mp, c0, Mp, 1 << 30, acc);
   if (threadIdx.x == 0) N2NMN_STAMP(0, 4);
-  // the two K slices inside a warp, then the 8 warps through shared memory
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int c = c0 + 4 * tx;
+  float bias[4], w2[4];
 #pragma unroll
-  for (int r = 0; r < kTextRowsPerCta; ++r) {
-    acc[r].x += __shfl_xor_sync(0xffffffffu, acc[r].x, 16);
-    acc[r].y += __shfl_xor_sync(0xffffffffu, acc[r].y, 16);
-    acc[r].z += __shfl_xor_sync(0xffffffffu, acc[r].z, 16);
-    acc[r].w += __shfl_xor_sync(0xffffffffu, acc[r].w, 16);
-    if (lane < 16)
-      *reinterpret_cast<float4*>(s_red + ((warp * kTextRowsPerCta + r) * kTextCols + tx * 4)) =
-          acc[r];
+  for (int j = 0; j < 4; ++j) {
+    const bool live = c + j < M;
+    bias[j] = live ? md.txt_b[g.set][c + j] : 0.f;
+    w2[j] = (live && es >= 0) ? md.elt_w[es][c + j] : 1.f;
   }
-  __syncthreads();
-  for (int o = threadIdx.x; o < kTextRowsPerCta * kTextCols; o += blockDim.x) {
-    const int r = o / kTextCols, cc = o - r * kTextCols;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 4 * ty + i;
     if (r >= g.count) continue;
-    const int c = cblk * kTextCols + cc;
-    float v = 0.f;
+    float4 v, vw, v2;
+    float* pv = &v.x; float* pw = &vw.x; float* p2 = &v2.x;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) v += s_red[(w * kTextRowsPerCta + r) * kTextCols + cc];
-    const bool live = c < M;
-    v = live ? v + md.txt_b[g.set][c] : 0.f;
-    const float w2 = (live && es >= 0) ? md.elt_w[es][c] : 1.f;
-    const size_t idx = (size_t)(g.start + r) * Mp + c;
-    tb.tau[idx] = v;
-    tb.tauw[idx] = v * w2;
-    tb.tau2[idx] = v * v;
-    if (quad) { s_tau[r * Mp + c] = v; s_tau[(kTextRowsPerCta + r) * Mp + c] = v * v; }
-  }
-  __syncthreads();   // s_red is reused by the next column block
-  }
-  if (quad) {
-    // (u, Q) of the group's Transform nodes: out[r][o] = Σ_c conv_quad[o][c] · (o < n ? tau : tau²)[r][c]
-    const int nq = quad_rows(md.ksize), n1 = quad_n(md.ksize), qp = quad_pitch(md.ksize);
-    for (int o = threadIdx.x; o < nq; o += blockDim.x) {
-      const float4* __restrict__ krow = reinterpret_cast<const float4*>(md.conv_quad + (size_t)o * Mp);
-      const float* tv = s_tau + (o < n1 ? 0 : kTextRowsPerCta * Mp);
-      float acc[kTextRowsPerCta];
-#pragma unroll
-      for (int r = 0; r < kTextRowsPerCta; ++r) acc[r] = 0.f;
-#pragma unroll 4
-      for (int c4 = 0; c4 < (Mp >> 2); ++c4) {
-        const float4 k4 = __ldg(krow + c4);
-#pragma unroll
-        for (int r = 0; r < kTextRowsPerCta; ++r) {
-          const float4 t4 = *reinterpret_cast<const float4*>(tv + r * Mp + 4 * c4);
-          acc[r] = fmaf(k4.x, t4.x, acc[r]); acc[r] = fmaf(k4.y, t4.y, acc[r]);
-          acc[r] = fmaf(k4.z, t4.z, acc[r]); acc[r] = fmaf(k4.w, t4.w, acc[r]);
-        }
-      }
-      for (int r = 0; r < g.count; ++r) tb.tq[(size_t)(g.start + r) * qp + o] = acc[r];
+    for (int j = 0; j < 4; ++j) {
+      const float t = (c + j < M) ? acc[i][j] + bias[j] : 0.f;
+      pv[j] = t; pw[j] = t * w2[j]; p2[j] = t * t;
     }
+    const size_t idx = (size_t)(g.start + r) * Mp + c;
+    *reinterpret_cast<float4*>(tb.tau + idx) = v;
+    *reinterpret_cast<float4*>(tb.tauw + idx) = vw;
+    *reinterpret_cast<float4*>(tb.tau2 + idx) = v2;
   }
   if (threadIdx.x == 0) N2NMN_STAMP(0, 5);
+}
+
+// (u, Q) of the Transform nodes (common.cuh): tq[row, o] = Σ_c (o < n ? tau : tau²)[row, c] ·
+// conv_quad^T[c, o] for the text rows [row0, row0 + nrows) of the Transform weight set.
+// grid = (ceil(quad_pitch / 64), ceil(nrows / 64)).
+__global__ void __launch_bounds__(256)
+quad_kernel(DevModel md, TextBufs tb, int row0, int nrows) {
+  pdl_trigger();
+  pdl_wait();      // tau comes from the text kernel
+  const int Mp = md.Mp, qp = quad_pitch(md.ksize);
+  const int r0 = row0 + blockIdx.y * kTileRows, cnt = min(kTileRows, row0 + nrows - r0);
+  const int c0 = blockIdx.x * kTextCols;
+  auto a_row = [&](int r) -> const float* {
+    return r < cnt ? tb.tau + (size_t)(r0 + r) * Mp : nullptr;
+  };
+  float acc[4][4];
+  // columns [0, n) are u (pairs with tau), padded to a multiple of 4; the rest is Q (tau²)
+  tile_gemm_64x64(a_row, Mp, md.conv_quad, qp, c0, qp, quad_u_pitch(md.ksize), acc);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int c = c0 + 4 * tx;
+  if (c >= qp) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 4 * ty + i;
+    if (r < cnt)
+      *reinterpret_cast<float4*>(tb.tq + (size_t)(r0 + r) * qp + c) =
+          make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  }
 }
 
 }  // namespace n2nmn

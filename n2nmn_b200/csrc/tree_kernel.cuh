@@ -126,7 +126,7 @@ __device__ __forceinline__ void transform_quad(const float* pad, const float* q,
     float num = 0.f, den = 0.f;
 #pragma unroll
     for (int i = 0; i < N; ++i) num = fmaf(w[i], q[i], num);
-    int idx = N;
+    int idx = (N + 3) & ~3;   // quad_u_pitch
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       float row = 0.f;
