@@ -360,16 +360,25 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
 
   c->ev_used = 0;
   prof_mark(c, "begin", st);
+  // Programmatic dependent launch is only used behind a producer whose grid fits in ONE wave.
+  // Measured (tools/dbg_group.py, r2): with a 512-CTA tree kernel (444 resident) in front of the
+  // pool / head kernels, the consumers' griddepcontrol.wait returned before the second wave of
+  // producer CTAs had run — exactly the questions >= 444 came out wrong. Behind a single-wave
+  // producer (every CTA resident from the start) the chain has been exact since round 1.
+  int prev_ctas = 1 << 30;
+  auto pdl_ok = [&]() { return c->use_pdl && prev_ctas <= c->num_sms; };
   // ---- K1 text projections (+ the quadratic-form coefficients of the Transform nodes)
   if (!S.groups.empty()) {
     dim3 grid((unsigned)(c->Mp / kTextCols), (unsigned)S.groups.size());
     TextSetRows tsr;
     for (int i = 0; i <= NUM_TEXT_SETS; ++i) tsr.start[i] = S.text_set_start[i];
-    text_proj_kernel<<<grid, 256, 0, st>>>(
+    const size_t tsm = (size_t)tile_smem_floats(c->cfg.text_dim) * sizeof(float) + 64 * sizeof(void*);
+    text_proj_kernel<<<grid, 256, tsm, st>>>(
         c->md, c->tb, tsr,
         reinterpret_cast<const int32_t*>(d + o.text_t),
         reinterpret_cast<const int32_t*>(d + o.text_b));
     ++c->launches;
+    prev_ctas = (int)(grid.x * grid.y);
     prof_mark(c, "text_proj_kernel", st);
     const int tr0 = S.text_set_start[TS_TRANSFORM];
     const int trn = S.text_set_start[TS_TRANSFORM + 1] - tr0;
@@ -379,14 +388,16 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
       qc.gridDim = dim3((unsigned)((quad_pitch(c->cfg.kernel_size) + kTextCols - 1) / kTextCols),
                         (unsigned)((trn + kTileRows - 1) / kTileRows));
       qc.blockDim = dim3(256);
+      qc.dynamicSmemBytes = (size_t)tile_smem_floats(c->Mp) * sizeof(float) + 64 * sizeof(void*);
       qc.stream = st;
       cudaLaunchAttribute qa[1];
       qa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       qa[0].val.programmaticStreamSerializationAllowed = 1;
       qc.attrs = qa;
-      qc.numAttrs = c->use_pdl ? 1 : 0;
+      qc.numAttrs = pdl_ok() ? 1 : 0;
       CUDA_TRY(cudaLaunchKernelEx(&qc, quad_kernel, c->md, c->tb, tr0, trn));
       ++c->launches;
+      prev_ctas = std::max(prev_ctas, (int)(qc.gridDim.x * qc.gridDim.y));   // text AND quad feed proj
       prof_mark(c, "quad_kernel", st);
     }
   }
@@ -422,6 +433,7 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
     if (c->cfg.flags & N2NMN_FLAG_PROJ_FP32_SIMT) {
       const size_t smem = (size_t)(kSimtRows * kSimtKChunk + kSimtRows * c->Mp) * sizeof(float);
       proj_simt_kernel<<<2 * p.num_work, 256, smem, st>>>(p);
+      prev_ctas = 2 * p.num_work;
       prof_mark(c, "proj_simt_kernel", st);
     } else {
       cudaLaunchConfig_t lc;
@@ -434,9 +446,10 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
       attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[0].val.programmaticStreamSerializationAllowed = 1;
       lc.attrs = attr;
-      lc.numAttrs = c->use_pdl ? 1 : 0;
+      lc.numAttrs = pdl_ok() ? 1 : 0;
       if (S.train) CUDA_TRY(cudaLaunchKernelEx(&lc, proj_umma_kernel<true>, c->tmaps, p));
       else CUDA_TRY(cudaLaunchKernelEx(&lc, proj_umma_kernel<false>, c->tmaps, p));
+      prev_ctas = 2 * pairs;
       prof_mark(c, "proj_umma_kernel", st);
     }
     ++c->launches;
@@ -488,7 +501,7 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
       attr[na].val.clusterDim.z = 1;
       ++na;
     }
-    if (c->use_pdl) {
+    if (pdl_ok()) {
       attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[na].val.programmaticStreamSerializationAllowed = 1;
       ++na;
@@ -520,7 +533,8 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
       hattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       hattr[0].val.programmaticStreamSerializationAllowed = 1;
       hc.attrs = hattr;
-      hc.numAttrs = c->use_pdl ? 1 : 0;
+      prev_ctas = NQ * cs;          // the tree kernel's grid
+      hc.numAttrs = pdl_ok() ? 1 : 0;
       if (S.num_feat_rows > 0) {   // pooled features: one CTA per (root row, 128-channel chunk)
         const int HWp = (c->HW + 3) & ~3;
         cudaLaunchConfig_t pc = hc;
@@ -531,6 +545,8 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
         CUDA_TRY(cudaLaunchKernelEx(&pc, pool_kernel, nc,
                                     reinterpret_cast<const int32_t*>(d + o.pool_img), HWp));
         ++c->launches;
+        prev_ctas = (int)(pc.gridDim.x * pc.gridDim.y);
+        hc.numAttrs = pdl_ok() ? 1 : 0;
         prof_mark(c, "pool_kernel", st);
       }
       const HeadWork* d_hw = reinterpret_cast<const HeadWork*>(d + o.head_work);
@@ -720,6 +736,15 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
                                 c->tree_smem_bytes));
   CUDA_TRY(cudaFuncSetAttribute(tree_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 c->tree_smem_bytes));
+  {
+    const int tsm = tile_smem_floats(cfg->text_dim) * (int)sizeof(float) + 64 * (int)sizeof(void*);
+    const int qsm = tile_smem_floats(c->Mp) * (int)sizeof(float) + 64 * (int)sizeof(void*);
+    if (tsm > 220 * 1024 || (c->conv_quad && qsm > 220 * 1024))
+      return fail(N2NMN_ERR_ARG, "text_dim / map_dim too large for the text tile kernel");
+    CUDA_TRY(cudaFuncSetAttribute(text_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+    CUDA_TRY(cudaFuncSetAttribute(quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  std::max(qsm, 48 * 1024)));
+  }
   CUDA_TRY(cudaFuncSetAttribute(head_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 head_smem_layout(16, c->Kp, c->Mp).total * (int)sizeof(float) <=
                                         200 * 1024

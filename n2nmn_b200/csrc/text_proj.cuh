@@ -7,9 +7,9 @@
 //
 // Both are small dense products  C[r, c] = Σ_k A[r, k] · B[k, c]  with a few hundred to a few
 // thousand rows per launch, done exactly in fp32 on the CUDA cores as one tiled kernel:
-//   CTA tile 64 rows x 64 columns, K in chunks of 32 staged through shared memory (the next chunk
-//   is in registers while the current one is multiplied), 256 threads = 16 column quads x 16 row
-//   quads, 4 x 4 accumulators each: 2 shared-memory loads per 16 FMAs.
+//   CTA tile 64 rows x 64 columns with the whole K extent of both operands staged in shared
+//   memory by cp.async, 256 threads = 16 column quads x 16 row quads, 4 x 4 accumulators each:
+//   8 shared-memory loads per 64 FMAs.
 // Round 1 gave every group of 8 rows its own CTA, which streamed the whole weight matrix from L2
 // with a handful of loads in flight: ~1000 SM-cycles per row against ~600 of FMA issue at peak.
 //   text_proj_kernel : A = gathered word vectors (K = Dt), B = W_txt [Dt][Mp]; emits tau,
@@ -23,89 +23,109 @@
 namespace n2nmn {
 
 constexpr int kTextCols = 64;    // output columns per CTA
-constexpr int kTileK = 32;       // K per shared-memory chunk
 constexpr int kTileRows = kTextRowsPerCta;   // 64 rows per CTA
 static_assert(kTextRowsPerCta == 64, "the tile kernel is written for 64-row groups");
 
 // Rows of each text weight set, by value: a CTA finds its group without touching global memory.
 struct TextSetRows { int32_t start[NUM_TEXT_SETS + 1]; };
 
-// One 64 x 64 output tile. a_row(r) -> pointer to row r of A (or nullptr: zeros), K valid values
-// per row; B row pitch ldb; sq_from_col: columns >= this use A² instead of A (quad kernel).
-// acc[i][j] = C[4*ty + i][c0 + 4*tx + j].
+// cp.async helpers (16-byte copies global -> shared, completion by commit groups)
+__device__ __forceinline__ void tp_cp16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+               ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void tp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kTileKBlock = 320;   // K extent staged at a time (Dt = 300 and Mp = 256 in one pass)
+__host__ __device__ inline int tile_a_pitch(int K) {   // floats; 16-byte rows
+  return ((K < kTileKBlock ? K : kTileKBlock) + 3) & ~3;
+}
+__host__ __device__ inline int tile_smem_floats(int K) {
+  return kTileRows * tile_a_pitch(K) + tile_a_pitch(K) * kTextCols;
+}
+
+// One 64 x 64 output tile. The whole A tile [64][K] and B tile [K][64] are brought into shared
+// memory with cp.async in TWO commit groups (first / second half of K): every load of the tile is
+// in flight at once (the launch has at most a CTA or two per SM, so nothing else hides the
+// latency), and the FMAs of the first half run under the second half's loads.
+// a_row(r) -> pointer to row r of A (or nullptr: zeros), K valid values per row; B row pitch ldb;
+// sq_from_col: columns >= this use A² instead of A (quad kernel).
+// acc[i][j] = C[4*ty + i][c0 + 4*tx + j]. smem: tile_smem_floats(K) floats + 64 pointers.
 template <class ARow>
-__device__ __forceinline__ void tile_gemm_64x64(ARow a_row, int K, const float* __restrict__ B,
-                                                int ldb, int c0, int ncols, int sq_from_col,
-                                                float (&acc)[4][4]) {
-  __shared__ __align__(16) float As[2][kTileK][kTileRows + 4];   // [k][row], padded
-  __shared__ __align__(16) float Bs[2][kTileK][kTextCols];
+__device__ __forceinline__ void tile_gemm_64x64(float* smem, ARow a_row, int Ktot,
+                                                const float* __restrict__ Btot, int ldb, int c0,
+                                                int ncols, int sq_from_col, float (&acc)[4][4]) {
+  const int P = tile_a_pitch(Ktot);
+  float* As = smem;                      // [64][P]
+  float* Bs = smem + kTileRows * P;      // [P][64]
+  const float** s_ap = reinterpret_cast<const float**>(Bs + P * kTextCols);   // [64]
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  // loader roles: A: thread -> (row = tid / 4, k-quads (tid % 4) and +4); B: (k = tid / 8 ... )
-  const int ar = threadIdx.x >> 2, aq = threadIdx.x & 3;          // 64 rows x 4 threads
-  const int bk = threadIdx.x >> 4, bq = threadIdx.x & 15;         // 16 k-rows x 16 col quads
-  const float* arow = a_row(ar);
-  const bool a_vec = arow != nullptr && (reinterpret_cast<uintptr_t>(arow) & 15) == 0;
-  const bool bcol_ok = c0 + 4 * bq < ncols;
-  float4 ra[2], rb[2];
-  auto load_chunk = [&](int k0) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int k = k0 + 4 * (aq + 4 * h);
-      ra[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (arow != nullptr) {
-        if (k + 3 < K && a_vec) ra[h] = __ldg(reinterpret_cast<const float4*>(arow + k));
-        else {
-          if (k < K) ra[h].x = __ldg(arow + k);
-          if (k + 1 < K) ra[h].y = __ldg(arow + k + 1);
-          if (k + 2 < K) ra[h].z = __ldg(arow + k + 2);
-          if (k + 3 < K) ra[h].w = __ldg(arow + k + 3);
-        }
-      }
-      const int kb = k0 + bk + 16 * h;
-      rb[h] = (kb < K && bcol_ok)
-                  ? __ldg(reinterpret_cast<const float4*>(B + (size_t)kb * ldb + c0) + bq)
-                  : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  auto store_chunk = [&](int buf) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int kk = 4 * (aq + 4 * h);
-      As[buf][kk][ar] = ra[h].x; As[buf][kk + 1][ar] = ra[h].y;
-      As[buf][kk + 2][ar] = ra[h].z; As[buf][kk + 3][ar] = ra[h].w;
-      *reinterpret_cast<float4*>(&Bs[buf][bk + 16 * h][4 * bq]) = rb[h];
-    }
-  };
+  if (threadIdx.x < kTileRows) s_ap[threadIdx.x] = a_row(threadIdx.x);
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const bool sq = c0 + 4 * tx >= sq_from_col;
-  const int nchunks = (K + kTileK - 1) / kTileK;
-  load_chunk(0);
-  store_chunk(0);
-  __syncthreads();
-  for (int ch = 0; ch < nchunks; ++ch) {
-    const int buf = ch & 1;
-    if (ch + 1 < nchunks) load_chunk((ch + 1) * kTileK);   // in flight during the FMAs below
+  for (int kb0 = 0; kb0 < Ktot; kb0 += kTileKBlock) {   // (one pass unless K > kTileKBlock)
+  const int K = min(kTileKBlock, Ktot - kb0), K4 = (K + 3) & ~3;
+  const float* __restrict__ B = Btot + (size_t)kb0 * ldb;
+  __syncthreads();                        // s_ap visible / the previous pass is done with smem
+  const int Kh = ((K4 / 2) + 3) & ~3;    // first half: k in [0, Kh)
+  const int qa = P >> 2;                 // 16-byte quads per A row
+  for (int half = 0; half < 2; ++half) {
+    const int k_lo = half ? Kh : 0, k_hi = half ? K4 : Kh;
+    for (int i = threadIdx.x; i < kTileRows * qa; i += blockDim.x) {
+      const int r = i / qa, k = 4 * (i - r * qa);
+      if (k < k_lo || k >= k_hi) continue;
+      const float* src = s_ap[r] ? s_ap[r] + kb0 : nullptr;
+      float* dst = As + r * P + k;
+      if (src != nullptr && k + 3 < K && ((reinterpret_cast<uintptr_t>(src + k) & 15) == 0)) {
+        tp_cp16(dst, src + k);
+      } else {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src != nullptr) {
+          if (k < K) v.x = __ldg(src + k);
+          if (k + 1 < K) v.y = __ldg(src + k + 1);
+          if (k + 2 < K) v.z = __ldg(src + k + 2);
+          if (k + 3 < K) v.w = __ldg(src + k + 3);
+        }
+        *reinterpret_cast<float4*>(dst) = v;
+      }
+    }
+    for (int i = threadIdx.x; i < (k_hi - k_lo) * (kTextCols / 4); i += blockDim.x) {
+      const int k = k_lo + i / (kTextCols / 4), q = i % (kTextCols / 4);
+      float* dst = Bs + k * kTextCols + 4 * q;
+      if (k < K && c0 + 4 * q < ncols) tp_cp16(dst, B + (size_t)k * ldb + c0 + 4 * q);
+      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    tp_commit();
+  }
+  for (int half = 0; half < 2; ++half) {
+    if (half == 0) tp_wait<1>(); else tp_wait<0>();
+    __syncthreads();
+    const int k_lo = half ? Kh : 0, k_hi = half ? K4 : Kh;
+#pragma unroll 2
+    for (int k = k_lo; k < k_hi; k += 4) {
+      float4 a[4], b[4];
 #pragma unroll
-    for (int k = 0; k < kTileK; ++k) {
-      float4 a = *reinterpret_cast<const float4*>(&As[buf][k][4 * ty]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][4 * tx]);
-      if (sq) { a.x *= a.x; a.y *= a.y; a.z *= a.z; a.w *= a.w; }
-      acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
-      acc[0][2] = fmaf(a.x, b.z, acc[0][2]); acc[0][3] = fmaf(a.x, b.w, acc[0][3]);
-      acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
-      acc[1][2] = fmaf(a.y, b.z, acc[1][2]); acc[1][3] = fmaf(a.y, b.w, acc[1][3]);
-      acc[2][0] = fmaf(a.z, b.x, acc[2][0]); acc[2][1] = fmaf(a.z, b.y, acc[2][1]);
-      acc[2][2] = fmaf(a.z, b.z, acc[2][2]); acc[2][3] = fmaf(a.z, b.w, acc[2][3]);
-      acc[3][0] = fmaf(a.w, b.x, acc[3][0]); acc[3][1] = fmaf(a.w, b.y, acc[3][1]);
-      acc[3][2] = fmaf(a.w, b.z, acc[3][2]); acc[3][3] = fmaf(a.w, b.w, acc[3][3]);
+      for (int i = 0; i < 4; ++i) {
+        a[i] = *reinterpret_cast<const float4*>(As + (4 * ty + i) * P + k);
+        b[i] = *reinterpret_cast<const float4*>(Bs + (k + i) * kTextCols + 4 * tx);
+        if (sq) { a[i].x *= a[i].x; a[i].y *= a[i].y; a[i].z *= a[i].z; a[i].w *= a[i].w; }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float ak[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          acc[i][0] = fmaf(ak[kk], b[kk].x, acc[i][0]); acc[i][1] = fmaf(ak[kk], b[kk].y, acc[i][1]);
+          acc[i][2] = fmaf(ak[kk], b[kk].z, acc[i][2]); acc[i][3] = fmaf(ak[kk], b[kk].w, acc[i][3]);
+        }
+      }
     }
-    if (ch + 1 < nchunks) {
-      store_chunk(buf ^ 1);     // the other buffer: its readers finished before the last barrier
-      __syncthreads();
-    }
+  }
   }
 }
 
@@ -134,8 +154,9 @@ text_proj_kernel(DevModel md, TextBufs tb, TextSetRows rows,
   auto a_row = [&](int r) -> const float* {
     return r < g.count ? word_vec_row(md, text_t[g.start + r], text_b[g.start + r]) : nullptr;
   };
+  extern __shared__ __align__(16) float tile_smem[];
   float acc[4][4];
-  tile_gemm_64x64(a_row, md.Dt, md.txt_w[g.set], Mp, c0, Mp, 1 << 30, acc);
+  tile_gemm_64x64(tile_smem, a_row, md.Dt, md.txt_w[g.set], Mp, c0, Mp, 1 << 30, acc);
   if (threadIdx.x == 0) N2NMN_STAMP(0, 4);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int c = c0 + 4 * tx;
@@ -178,9 +199,10 @@ quad_kernel(DevModel md, TextBufs tb, int row0, int nrows) {
   auto a_row = [&](int r) -> const float* {
     return r < cnt ? tb.tau + (size_t)(r0 + r) * Mp : nullptr;
   };
+  extern __shared__ __align__(16) float tile_smem[];
   float acc[4][4];
   // columns [0, n) are u (pairs with tau), padded to a multiple of 4; the rest is Q (tau²)
-  tile_gemm_64x64(a_row, Mp, md.conv_quad, qp, c0, qp, quad_u_pitch(md.ksize), acc);
+  tile_gemm_64x64(tile_smem, a_row, Mp, md.conv_quad, qp, c0, qp, quad_u_pitch(md.ksize), acc);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int c = c0 + 4 * tx;
   if (c >= qp) return;
