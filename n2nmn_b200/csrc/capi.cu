@@ -360,13 +360,9 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
 
   c->ev_used = 0;
   prof_mark(c, "begin", st);
-  // Programmatic dependent launch is only used behind a producer whose grid fits in ONE wave.
-  // Measured (tools/dbg_group.py, r2): with a 512-CTA tree kernel (444 resident) in front of the
-  // pool / head kernels, the consumers' griddepcontrol.wait returned before the second wave of
-  // producer CTAs had run — exactly the questions >= 444 came out wrong. Behind a single-wave
-  // producer (every CTA resident from the start) the chain has been exact since round 1.
-  int prev_ctas = 1 << 30;
-  auto pdl_ok = [&]() { return c->use_pdl && prev_ctas <= c->num_sms; };
+  // every kernel of the step after the first is a programmatic dependent launch of its
+  // predecessor (each calls griddepcontrol.wait before it touches the predecessor's output)
+  auto pdl_ok = [&]() { return c->use_pdl; };
   // ---- K1 text projections (+ the quadratic-form coefficients of the Transform nodes)
   if (!S.groups.empty()) {
     dim3 grid((unsigned)(c->Mp / kTextCols), (unsigned)S.groups.size());
@@ -378,7 +374,6 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
         reinterpret_cast<const int32_t*>(d + o.text_t),
         reinterpret_cast<const int32_t*>(d + o.text_b));
     ++c->launches;
-    prev_ctas = (int)(grid.x * grid.y);
     prof_mark(c, "text_proj_kernel", st);
     const int tr0 = S.text_set_start[TS_TRANSFORM];
     const int trn = S.text_set_start[TS_TRANSFORM + 1] - tr0;
@@ -397,7 +392,6 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
       qc.numAttrs = pdl_ok() ? 1 : 0;
       CUDA_TRY(cudaLaunchKernelEx(&qc, quad_kernel, c->md, c->tb, tr0, trn));
       ++c->launches;
-      prev_ctas = std::max(prev_ctas, (int)(qc.gridDim.x * qc.gridDim.y));   // text AND quad feed proj
       prof_mark(c, "quad_kernel", st);
     }
   }
@@ -433,7 +427,6 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
     if (c->cfg.flags & N2NMN_FLAG_PROJ_FP32_SIMT) {
       const size_t smem = (size_t)(kSimtRows * kSimtKChunk + kSimtRows * c->Mp) * sizeof(float);
       proj_simt_kernel<<<2 * p.num_work, 256, smem, st>>>(p);
-      prev_ctas = 2 * p.num_work;
       prof_mark(c, "proj_simt_kernel", st);
     } else {
       cudaLaunchConfig_t lc;
@@ -449,7 +442,6 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
       lc.numAttrs = pdl_ok() ? 1 : 0;
       if (S.train) CUDA_TRY(cudaLaunchKernelEx(&lc, proj_umma_kernel<true>, c->tmaps, p));
       else CUDA_TRY(cudaLaunchKernelEx(&lc, proj_umma_kernel<false>, c->tmaps, p));
-      prev_ctas = 2 * pairs;
       prof_mark(c, "proj_umma_kernel", st);
     }
     ++c->launches;
@@ -533,7 +525,6 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
       hattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       hattr[0].val.programmaticStreamSerializationAllowed = 1;
       hc.attrs = hattr;
-      prev_ctas = NQ * cs;          // the tree kernel's grid
       hc.numAttrs = pdl_ok() ? 1 : 0;
       if (S.num_feat_rows > 0) {   // pooled features: one CTA per (root row, 128-channel chunk)
         const int HWp = (c->HW + 3) & ~3;
@@ -545,8 +536,6 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
         CUDA_TRY(cudaLaunchKernelEx(&pc, pool_kernel, nc,
                                     reinterpret_cast<const int32_t*>(d + o.pool_img), HWp));
         ++c->launches;
-        prev_ctas = (int)(pc.gridDim.x * pc.gridDim.y);
-        hc.numAttrs = pdl_ok() ? 1 : 0;
         prof_mark(c, "pool_kernel", st);
       }
       const HeadWork* d_hw = reinterpret_cast<const HeadWork*>(d + o.head_work);

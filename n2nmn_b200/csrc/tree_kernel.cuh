@@ -209,6 +209,11 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
   // ---- the attention arena, stored maps and text projections come from the preceding kernels
   if (threadIdx.x == 0) N2NMN_STAMP(2, 1);
   pdl_wait();
+  // the node records staged above are read by every thread below. (A CTA of the first wave sits in
+  // pdl_wait long enough for the writes to land; a CTA that starts after the predecessor has
+  // finished does not — without this barrier the questions of the second wave read stale records:
+  // tools/dbg_group.py, r2.)
+  __syncthreads();
   if (threadIdx.x == 0) N2NMN_STAMP(2, 2);
   if (beg == end) {   // invalid layout: zeros(num_choices) (models_clevr/nmn3_model.py:144-155)
     if (co.rank == 0)
