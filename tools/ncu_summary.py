@@ -10,9 +10,11 @@ import sys
 tag = sys.argv[1]
 out = open('profiles/%s.md' % tag, 'w')
 out.write('# ncu summary %s\n\n' % tag)
-out.write('Command: `bash tools/gpu_prof.sh %s` (bench.py --steps 30 --warmup 10 under '
-          '`ncu --metrics gpu__time_duration.sum --clock-control none`, then `--set full` on the '
-          'three hot kernels). Per-launch times are cold-cache and serialised: compare shares.\n\n' % tag)
+out.write('Command: `bash tools/gpu_prof.sh %s` (launch list: bench.py under `ncu --metrics '
+          'gpu__time_duration.sum --clock-control none`, the pool batching 8 batches per launch '
+          'set; `--set full`: one set of launches of `GB_ONLY=8 tools/group_bench.py`, i.e. '
+          'n2nmn_forward_group over 8 batches). Per-launch times are cold-cache and serialised: '
+          'compare shares.\n\n' % tag)
 rows = [r for r in csv.reader(open('gpurun_out/launches_%s.csv' % tag)) if len(r) > 5]
 hdr = [i for i, r in enumerate(rows) if r[0] == 'ID'][0]
 h, data = rows[hdr], rows[hdr + 1:]
