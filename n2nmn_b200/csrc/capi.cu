@@ -369,7 +369,7 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
     TextSetRows tsr;
     for (int i = 0; i <= NUM_TEXT_SETS; ++i) tsr.start[i] = S.text_set_start[i];
     const size_t tsm = (size_t)tile_smem_floats(c->cfg.text_dim) * sizeof(float) + 64 * sizeof(void*);
-    text_proj_kernel<<<grid, 256, tsm, st>>>(
+    text_proj_kernel<<<grid, kTileThreads, tsm, st>>>(
         c->md, c->tb, tsr,
         reinterpret_cast<const int32_t*>(d + o.text_t),
         reinterpret_cast<const int32_t*>(d + o.text_b));
@@ -382,7 +382,7 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
       std::memset(&qc, 0, sizeof(qc));
       qc.gridDim = dim3((unsigned)((quad_pitch(c->cfg.kernel_size) + kTextCols - 1) / kTextCols),
                         (unsigned)((trn + kTileRows - 1) / kTileRows));
-      qc.blockDim = dim3(256);
+      qc.blockDim = dim3(kTileThreads);
       qc.dynamicSmemBytes = (size_t)tile_smem_floats(c->Mp) * sizeof(float) + 64 * sizeof(void*);
       qc.stream = st;
       cudaLaunchAttribute qa[1];

@@ -8,8 +8,10 @@
 // Both are small dense products  C[r, c] = Σ_k A[r, k] · B[k, c]  with a few hundred to a few
 // thousand rows per launch, done exactly in fp32 on the CUDA cores as one tiled kernel:
 //   CTA tile 64 rows x 64 columns with the whole K extent of both operands staged in shared
-//   memory by cp.async, 256 threads = 16 column quads x 16 row quads, 4 x 4 accumulators each:
-//   8 shared-memory loads per 64 FMAs.
+//   memory by cp.async, 512 threads = 16 column quads x 32 row pairs, 2 x 4 accumulators each
+//   (a launch has at most one CTA per SM, so the warps that hide the shared-memory latency have
+//   to come from inside the CTA: ncu r2f showed 12 % warp occupancy and 42 K cycles per tile with
+//   256 threads x 4 x 4).
 // Round 1 gave every group of 8 rows its own CTA, which streamed the whole weight matrix from L2
 // with a handful of loads in flight: ~1000 SM-cycles per row against ~600 of FMA issue at peak.
 //   text_proj_kernel : A = gathered word vectors (K = Dt), B = W_txt [Dt][Mp]; emits tau,
@@ -24,6 +26,7 @@ namespace n2nmn {
 
 constexpr int kTextCols = 64;    // output columns per CTA
 constexpr int kTileRows = kTextRowsPerCta;   // 64 rows per CTA
+constexpr int kTileThreads = 512;
 static_assert(kTextRowsPerCta == 64, "the tile kernel is written for 64-row groups");
 
 // Rows of each text weight set, by value: a CTA finds its group without touching global memory.
@@ -52,11 +55,11 @@ __host__ __device__ inline int tile_smem_floats(int K) {
 // latency), and the FMAs of the first half run under the second half's loads.
 // a_row(r) -> pointer to row r of A (or nullptr: zeros), K valid values per row; B row pitch ldb;
 // sq_from_col: columns >= this use A² instead of A (quad kernel).
-// acc[i][j] = C[4*ty + i][c0 + 4*tx + j]. smem: tile_smem_floats(K) floats + 64 pointers.
+// acc[i][j] = C[2*ty + i][c0 + 4*tx + j]. smem: tile_smem_floats(K) floats + 64 pointers.
 template <class ARow>
 __device__ __forceinline__ void tile_gemm_64x64(float* smem, ARow a_row, int Ktot,
                                                 const float* __restrict__ Btot, int ldb, int c0,
-                                                int ncols, int sq_from_col, float (&acc)[4][4]) {
+                                                int ncols, int sq_from_col, float (&acc)[2][4]) {
   const int P = tile_a_pitch(Ktot);
   float* As = smem;                      // [64][P]
   float* Bs = smem + kTileRows * P;      // [P][64]
@@ -64,7 +67,7 @@ __device__ __forceinline__ void tile_gemm_64x64(float* smem, ARow a_row, int Kto
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   if (threadIdx.x < kTileRows) s_ap[threadIdx.x] = a_row(threadIdx.x);
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const bool sq = c0 + 4 * tx >= sq_from_col;
@@ -108,15 +111,17 @@ __device__ __forceinline__ void tile_gemm_64x64(float* smem, ARow a_row, int Kto
     const int k_lo = half ? Kh : 0, k_hi = half ? K4 : Kh;
 #pragma unroll 2
     for (int k = k_lo; k < k_hi; k += 4) {
-      float4 a[4], b[4];
+      float4 a[2], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        a[i] = *reinterpret_cast<const float4*>(As + (4 * ty + i) * P + k);
+      for (int i = 0; i < 4; ++i)
         b[i] = *reinterpret_cast<const float4*>(Bs + (k + i) * kTextCols + 4 * tx);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        a[i] = *reinterpret_cast<const float4*>(As + (2 * ty + i) * P + k);
         if (sq) { a[i].x *= a[i].x; a[i].y *= a[i].y; a[i].z *= a[i].z; a[i].w *= a[i].w; }
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 2; ++i) {
         const float ak[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
@@ -130,7 +135,7 @@ __device__ __forceinline__ void tile_gemm_64x64(float* smem, ARow a_row, int Kto
 }
 
 // grid = (Mp / 64, groups); one group = <= 64 text rows of ONE weight set (schedule.cpp)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kTileThreads)
 text_proj_kernel(DevModel md, TextBufs tb, TextSetRows rows,
                  const int32_t* __restrict__ text_t, const int32_t* __restrict__ text_b) {
   pdl_trigger();   // the contraction kernel only needs our output in its epilogue
@@ -155,7 +160,7 @@ text_proj_kernel(DevModel md, TextBufs tb, TextSetRows rows,
     return r < g.count ? word_vec_row(md, text_t[g.start + r], text_b[g.start + r]) : nullptr;
   };
   extern __shared__ __align__(16) float tile_smem[];
-  float acc[4][4];
+  float acc[2][4];
   tile_gemm_64x64(tile_smem, a_row, md.Dt, md.txt_w[g.set], Mp, c0, Mp, 1 << 30, acc);
   if (threadIdx.x == 0) N2NMN_STAMP(0, 4);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -168,8 +173,8 @@ text_proj_kernel(DevModel md, TextBufs tb, TextSetRows rows,
     w2[j] = (live && es >= 0) ? md.elt_w[es][c + j] : 1.f;
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = 4 * ty + i;
+  for (int i = 0; i < 2; ++i) {
+    const int r = 2 * ty + i;
     if (r >= g.count) continue;
     float4 v, vw, v2;
     float* pv = &v.x; float* pw = &vw.x; float* p2 = &v2.x;
@@ -189,7 +194,7 @@ text_proj_kernel(DevModel md, TextBufs tb, TextSetRows rows,
 // (u, Q) of the Transform nodes (common.cuh): tq[row, o] = Σ_c (o < n ? tau : tau²)[row, c] ·
 // conv_quad^T[c, o] for the text rows [row0, row0 + nrows) of the Transform weight set.
 // grid = (ceil(quad_pitch / 64), ceil(nrows / 64)).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kTileThreads)
 quad_kernel(DevModel md, TextBufs tb, int row0, int nrows) {
   pdl_trigger();
   pdl_wait();      // tau comes from the text kernel
@@ -200,15 +205,15 @@ quad_kernel(DevModel md, TextBufs tb, int row0, int nrows) {
     return r < cnt ? tb.tau + (size_t)(r0 + r) * Mp : nullptr;
   };
   extern __shared__ __align__(16) float tile_smem[];
-  float acc[4][4];
+  float acc[2][4];
   // columns [0, n) are u (pairs with tau), padded to a multiple of 4; the rest is Q (tau²)
   tile_gemm_64x64(tile_smem, a_row, Mp, md.conv_quad, qp, c0, qp, quad_u_pitch(md.ksize), acc);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int c = c0 + 4 * tx;
   if (c >= qp) return;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = 4 * ty + i;
+  for (int i = 0; i < 2; ++i) {
+    const int r = 2 * ty + i;
     if (r < cnt)
       *reinterpret_cast<float4*>(tb.tq + (size_t)(r0 + r) * qp + c) =
           make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
