@@ -323,6 +323,60 @@ int n2nmn_get_launch_times(n2nmn_ctx* ctx, const char** names, float* us, int ca
 /* Count of kernel launches issued by this ctx since creation. */
 int64_t n2nmn_launch_count(const n2nmn_ctx* ctx);
 
+/* ---- (f1) attentional seq2seq layout generator --------------------------------------------
+ * Replaces `AttentionSeq2Seq` (models_clevr/nmn3_netgen_att.py:46-322; the VQA / SHAPES copies
+ * are the same code) in its inference configuration (no dropout; greedy decoding under the
+ * Assembler's validity masks, or teacher forcing): the encoder LSTM stack under dynamic_rnn
+ * (:73-120) and the raw_rnn attention decoder (:122-322). Sampling (`decoder_sampling`) and the
+ * backward pass are not provided. */
+typedef struct n2nmn_seq2seq n2nmn_seq2seq;
+typedef struct n2nmn_seq2seq_config {
+  int32_t abi_version;     /* N2NMN_ABI_VERSION */
+  int32_t num_vocab_txt;   /* nmn3_netgen_att.py:48-52 constructor arguments */
+  int32_t embed_dim_txt;
+  int32_t num_vocab_nmn;   /* <= 64 */
+  int32_t embed_dim_nmn;
+  int32_t lstm_dim;        /* multiple of 16 */
+  int32_t num_layers;      /* <= 4 */
+  int32_t T_encoder;       /* capacity, <= 128 */
+  int32_t T_decoder;       /* decoding steps (fixed, as in the reference) */
+  int32_t max_batch;
+  int32_t device;
+  int32_t flags;           /* 0 */
+} n2nmn_seq2seq_config;
+
+int n2nmn_seq2seq_create(const n2nmn_seq2seq_config* cfg, n2nmn_seq2seq** out);
+int n2nmn_seq2seq_destroy(n2nmn_seq2seq* s);
+/* Variables under the reference's `encoder_decoder/` scope, names relative to it, e.g.
+ * "encoder/lstm/multi_rnn_cell/cell_0/basic_lstm_cell/weights" (TF 1.0 BasicLSTMCell:
+ * [input+units, 4*units], gate order i, j, f, o). */
+int n2nmn_seq2seq_num_variables(const n2nmn_seq2seq* s);
+int n2nmn_seq2seq_variable_info(const n2nmn_seq2seq* s, int index, const char** name,
+                                int64_t shape[4], int* ndim);
+/* src_dev: device pointer, TF layout (what tf.train.Saver stores). */
+int n2nmn_seq2seq_set_weight(n2nmn_seq2seq* s, const char* name, const float* src_dev,
+                             const int64_t* shape, int ndim, void* stream);
+/* The Assembler's decoding-state tables (models_clevr/nmn3_assembler.py:150-222), HOST int32:
+ * P [V][3], W [3][V][4], b [V][4] — `_get_valid_tokens` (nmn3_netgen_att.py:8-11) and
+ * `_update_decoding_state` (:13-15). Synchronises the stream. */
+int n2nmn_seq2seq_set_assembler(n2nmn_seq2seq* s, const int32_t* P, const int32_t* W,
+                                const int32_t* b, void* stream);
+/* One batch, everything device-resident and time-major as in the reference:
+ *   input_seq_dev [T_enc][N] int32, seq_len_dev [N] int32,
+ *   gt_layout_dev [T_decoder][N] int32 or NULL (NULL = greedy; non-NULL = `use_gt_layout`),
+ *   tokens_dev [T_decoder][N] int32        -> predicted_tokens (:307)
+ *   token_probs_dev [T_decoder][N]         -> token_probs (:308); Σ_t log = log_seq_prob
+ *   neg_entropy_dev [N]                    -> neg_entropy (:309)
+ *   word_vecs_dev [T_decoder][N][embed_dim_txt] -> word_vecs (:312)
+ *   atts_dev [T_decoder][T_enc][N] or NULL -> atts (:311)
+ * All work is enqueued on `stream`. */
+int n2nmn_seq2seq_forward(n2nmn_seq2seq* s, const int32_t* input_seq_dev,
+                          const int32_t* seq_len_dev, int T_enc, int N,
+                          const int32_t* gt_layout_dev, int32_t* tokens_dev,
+                          float* token_probs_dev, float* neg_entropy_dev, float* word_vecs_dev,
+                          float* atts_dev, void* stream);
+int64_t n2nmn_seq2seq_launch_count(const n2nmn_seq2seq* s);
+
 #ifdef __cplusplus
 }
 #endif

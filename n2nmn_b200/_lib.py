@@ -23,6 +23,12 @@ class Config(C.Structure):
         'num_choices', 'max_batch', 'max_T', 'device', 'flags', 'max_group')]
 
 
+class Seq2SeqConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        'abi_version', 'num_vocab_txt', 'embed_dim_txt', 'num_vocab_nmn', 'embed_dim_nmn',
+        'lstm_dim', 'num_layers', 'T_encoder', 'T_decoder', 'max_batch', 'device', 'flags')]
+
+
 class SchedInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         'num_questions', 'num_valid', 'num_nodes', 'max_depth', 'num_text_nodes',
@@ -35,6 +41,15 @@ class SchedInfo(C.Structure):
 _P = C.c_void_p
 _I32P = C.POINTER(C.c_int32)
 SIGNATURES = {
+    'n2nmn_seq2seq_create': (C.c_int, [C.POINTER(Seq2SeqConfig), C.POINTER(_P)]),
+    'n2nmn_seq2seq_destroy': (C.c_int, [_P]),
+    'n2nmn_seq2seq_num_variables': (C.c_int, [_P]),
+    'n2nmn_seq2seq_variable_info': (C.c_int, [_P, C.c_int, C.POINTER(C.c_char_p),
+                                              C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
+    'n2nmn_seq2seq_set_weight': (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int, _P]),
+    'n2nmn_seq2seq_set_assembler': (C.c_int, [_P, _I32P, _I32P, _I32P, _P]),
+    'n2nmn_seq2seq_forward': (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
+    'n2nmn_seq2seq_launch_count': (C.c_int64, [_P]),
     'n2nmn_create': (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
     'n2nmn_destroy': (C.c_int, [_P]),
     'n2nmn_last_error': (C.c_char_p, []),

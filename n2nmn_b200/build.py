@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libn2nmn_b200.so')
-SOURCES = ['capi.cu', 'schedule.cpp', 'pool.cpp', 'util.cpp']
+SOURCES = ['capi.cu', 'seq2seq.cu', 'schedule.cpp', 'pool.cpp', 'util.cpp']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC', '--shared', '-x', 'cu', '-Xptxas', '-v']

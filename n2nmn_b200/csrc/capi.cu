@@ -562,6 +562,10 @@ int check_ready(n2nmn_ctx* c) {
 }  // namespace
 
 // ================================================================================== C ABI
+namespace n2nmn {
+int fail_with(int code, const std::string& msg) { return fail(code, msg); }   // other TUs
+}
+
 extern "C" {
 
 const char* n2nmn_last_error(void) { return g_err.c_str(); }

@@ -1,0 +1,122 @@
+"""GPU parity of the seq2seq layout generator through the C ABI:
+  * against the goldens produced by executing the reference's nmn3_netgen_att.py on the TF shim
+    (tests/golden/golden_seq2seq.npz): greedy decoding under the validity masks and teacher
+    forcing;
+  * against the numpy oracle at the reference's real CLEVR sizes (exp_clevr/train_clevr_*.py:
+    T_encoder 45, T_decoder 20 (here 10..20), embed 300, lstm 512, 2 layers, batch 64), ragged
+    lengths including 1 and T_encoder.
+Tolerance: tokens bit-exact; probabilities, entropies, attention maps and word vectors 2e-5
+absolute (fp32 everywhere; only the summation order differs)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from n2nmn_b200 import synth
+from n2nmn_b200.assembler import Assembler
+from oracle import seq2seq_oracle as so
+
+pytestmark = pytest.mark.gpu
+Z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'golden_seq2seq.npz'))
+ATOL = 2e-5
+
+
+def golden_weights():
+    return {k[2 + len('encoder_decoder/'):]: Z[k] for k in Z.files if k.startswith('w:')}
+
+
+def make(asm, w, T_enc, N, T_dec, V_txt, E_txt, E_nmn, L, layers):
+    from n2nmn_b200.seq2seq import AttentionSeq2Seq
+    return AttentionSeq2Seq(None, None, T_dec, V_txt, E_txt, asm.num_vocab_nmn, E_nmn, L, layers,
+                            asm, T_encoder=T_enc, max_batch=N, weights=w, device='cuda:0')
+
+
+def check(out, tokens, probs, nent, wv, atts, atol=ATOL):
+    torch.cuda.synchronize()
+    g = [o.cpu().numpy() for o in out]
+    assert np.array_equal(g[0], tokens)
+    np.testing.assert_allclose(g[1], probs, atol=atol)
+    np.testing.assert_allclose(g[2], nent, atol=10 * atol)
+    np.testing.assert_allclose(g[3], wv, atol=atol)
+    np.testing.assert_allclose(g[4], atts, atol=atol)
+
+
+def test_matches_reference_goldens():
+    N, T_enc, T_dec, V_txt, E_txt, E_nmn, L, layers, seed = [int(v) for v in Z['cfg']]
+    asm = Assembler(synth.vocab_file('clevr'))
+    s = make(asm, golden_weights(), T_enc, N, T_dec, V_txt, E_txt, E_nmn, L, layers)
+    out = s.forward(Z['input_seq'], Z['seq_length'])
+    check(out, Z['greedy_predicted_tokens'], Z['greedy_token_probs'], Z['greedy_neg_entropy'],
+          Z['greedy_word_vecs'], Z['greedy_atts'])
+    lsp = s.log_seq_prob.cpu().numpy()
+    np.testing.assert_allclose(lsp, np.log(Z['greedy_token_probs']).sum(0), atol=1e-4)
+    out = s.forward(Z['input_seq'], Z['seq_length'], True, Z['gt_layout'])
+    check(out, Z['gt_layout'], Z['gt_token_probs'], Z['gt_neg_entropy'], Z['gt_word_vecs'],
+          Z['gt_atts'])
+    # the first call again: nothing of the forced run may leak into the next batch
+    out = s.forward(Z['input_seq'], Z['seq_length'])
+    check(out, Z['greedy_predicted_tokens'], Z['greedy_token_probs'], Z['greedy_neg_entropy'],
+          Z['greedy_word_vecs'], Z['greedy_atts'])
+
+
+def random_weights(rng, V_txt, E_txt, V_nmn, E_nmn, L, layers, scale=1.0):
+    w = {}
+
+    def u(*shape, a):
+        return rng.uniform(-a, a, size=shape).astype(np.float32)
+    w['encoder/embedding_mat'] = u(V_txt, E_txt, a=0.5 * scale)
+    w['decoder/embedding_mat'] = u(V_nmn, E_nmn, a=0.5 * scale)
+    w['decoder/go_embedding'] = u(1, E_nmn, a=0.5 * scale)
+    for side, E in (('encoder', E_txt), ('decoder', E_nmn)):
+        for l in range(layers):
+            n_in = (E if l == 0 else L) + L
+            p = '%s/lstm/multi_rnn_cell/cell_%d/basic_lstm_cell/' % (side, l)
+            w[p + 'weights'] = u(n_in, 4 * L, a=scale * (3.0 / n_in) ** 0.5)
+            w[p + 'biases'] = u(4 * L, a=0.1)
+    w['encoder/encoder_h_transform/weights'] = u(L, L, a=scale * (3.0 / L) ** 0.5)
+    w['encoder/encoder_h_transform/biases'] = u(L, a=0.1)
+    w['decoder/att_prediction/weights'] = u(L, L, a=scale * (3.0 / L) ** 0.5)
+    w['decoder/att_prediction/biases'] = u(L, a=0.1)
+    w['decoder/att_prediction/v'] = u(L, a=scale * (3.0 / L) ** 0.5 * 4)
+    w['decoder/token_prediction/weights'] = u(2 * L, V_nmn, a=scale * (3.0 / L) ** 0.5 * 4)
+    w['decoder/token_prediction/biases'] = u(V_nmn, a=0.1)
+    return w
+
+
+@pytest.mark.parametrize('N,T_enc,T_dec,L,layers', [(64, 45, 20, 512, 2), (37, 26, 13, 208, 1),
+                                                     (1, 5, 10, 64, 3)])
+def test_matches_oracle_at_reference_sizes(N, T_enc, T_dec, L, layers):
+    rng = np.random.RandomState(1000 + N)
+    asm = Assembler(synth.vocab_file('clevr'))
+    V_nmn = len(asm.module_names)
+    V_txt, E_txt, E_nmn = 90, 300, 300
+    w = random_weights(rng, V_txt, E_txt, V_nmn, E_nmn, L, layers)
+    seq = rng.randint(0, V_txt, size=(T_enc, N)).astype(np.int32)
+    lens = rng.randint(1, T_enc + 1, size=N).astype(np.int32)
+    lens[0] = T_enc
+    lens[-1] = 1
+    s = make(asm, w, T_enc, N, T_dec, V_txt, E_txt, E_nmn, L, layers)
+    _, dec = so.run(w, seq, lens, T_dec, layers, asm.P, asm.W, asm.b)
+    out = s.forward(seq, lens)
+    check(out, *dec)
+    assert asm.assemble(out[0].cpu().numpy())[1].all()
+    gt = dec[0][:, ::-1].copy()      # some other valid layouts as the forced ones
+    _, dec = so.run(w, seq, lens, T_dec, layers, asm.P, asm.W, asm.b, use_gt_layout=True,
+                    gt_layout=gt)
+    out = s.forward(seq, lens, True, gt)
+    check(out, *dec)
+
+
+def test_errors_are_loud():
+    from n2nmn_b200 import _lib
+    asm = Assembler(synth.vocab_file('clevr'))
+    N, T_enc, T_dec, V_txt, E_txt, E_nmn, L, layers, seed = [int(v) for v in Z['cfg']]
+    s = make(asm, None, T_enc, N, T_dec, V_txt, E_txt, E_nmn, L, layers)
+    with pytest.raises(_lib.N2NMNError):          # weights not set
+        s.forward(Z['input_seq'], Z['seq_length'])
+    s.set_weights(golden_weights())
+    with pytest.raises(_lib.N2NMNError):          # over capacity
+        s.forward(np.zeros((T_enc + 1, N), np.int32), Z['seq_length'])
+    with pytest.raises(KeyError):
+        s.set_weights({'encoder/embedding_mat': Z['w:encoder_decoder/encoder/embedding_mat']})
