@@ -79,6 +79,8 @@ def parse_args():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--wave', action='store_true', help='depth-bucketed wave executor')
     ap.add_argument('--no-train', action='store_true', help='skip the train-step measurement')
+    ap.add_argument('--no-seq2seq', action='store_true',
+                    help='skip the layout-generator (seq2seq, SURVEY §8 f1) measurement')
     ap.add_argument('--no-other-sets', action='store_true',
                     help='skip the random / deep layout sets reported beside the expert mix')
     ap.add_argument('--no-other-configs', action='store_true',
@@ -350,7 +352,67 @@ def run_reference_arm(args, rank, world):
         'e2e': {'value': qps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
+    if args.config == 'clevr' and not args.no_seq2seq:
+        line['cpu_baseline']['layout_generator'] = seq2seq_cpu_port(asm, B)
     print(json.dumps(line), flush=True)
+
+
+SEQ2SEQ = dict(T_encoder=45, T_decoder=20, num_vocab_txt=90, embed_dim=300, lstm_dim=512,
+               num_layers=2)   # exp_clevr/train_clevr_gt_layout.py:22-40
+
+
+def seq2seq_inputs(B, seed=0):
+    rng = np.random.RandomState(seed)
+    seq = rng.randint(0, SEQ2SEQ['num_vocab_txt'], size=(SEQ2SEQ['T_encoder'], B)).astype(np.int32)
+    lens = rng.randint(5, SEQ2SEQ['T_encoder'] + 1, size=B).astype(np.int32)
+    return seq, lens
+
+
+def seq2seq_measure(torch, asm, dev, B, reps=30):
+    from n2nmn_b200.seq2seq import AttentionSeq2Seq
+    from n2nmn_b200.weights import init_seq2seq_weights
+    c = SEQ2SEQ
+    w = init_seq2seq_weights(c['num_vocab_txt'], c['embed_dim'], asm.num_vocab_nmn, c['embed_dim'],
+                             c['lstm_dim'], c['num_layers'])
+    s = AttentionSeq2Seq(None, None, c['T_decoder'], c['num_vocab_txt'], c['embed_dim'],
+                         asm.num_vocab_nmn, c['embed_dim'], c['lstm_dim'], c['num_layers'], asm,
+                         T_encoder=c['T_encoder'], max_batch=B, weights=w, device=dev)
+    seq, lens = seq2seq_inputs(B)
+    seq, lens = torch.from_numpy(seq).to(dev), torch.from_numpy(lens).to(dev)
+    for _ in range(5):
+        s.forward(seq, lens)
+    torch.cuda.synchronize()
+    n0 = s.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        s.forward(seq, lens)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {'what': 'AttentionSeq2Seq forward (encoder LSTM x%d, attention decoder, greedy), '
+                    'N=%d T_encoder=%d T_decoder=%d lstm_dim=%d; fp32 via 3xTF32 mma.sync'
+                    % (c['num_layers'], B, c['T_encoder'], c['T_decoder'], c['lstm_dim']),
+            'ms_per_batch': ms, 'questions_per_sec': B / (ms * 1e-3),
+            'gpu_launches_per_batch': (s.launch_count() - n0) // reps, 'reps': reps}
+
+
+def seq2seq_cpu_port(asm, B):
+    """The numpy restatement of the layout generator, timed once (cpu_baseline leg only)."""
+    from oracle import seq2seq_oracle as so
+    from n2nmn_b200.weights import init_seq2seq_weights
+    c = SEQ2SEQ
+    w = init_seq2seq_weights(c['num_vocab_txt'], c['embed_dim'], asm.num_vocab_nmn, c['embed_dim'],
+                             c['lstm_dim'], c['num_layers'])
+    seq, lens = seq2seq_inputs(B)
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        so.run(w, seq, lens, c['T_decoder'], c['num_layers'], asm.P, asm.W, asm.b)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {'ms_per_batch': 1e3 * best, 'questions_per_sec': B / best, 'kind': 'port (numpy/BLAS)',
+            'sample': '1 batch of %d questions, best of 2' % B}
 
 
 # =========================================================================== GPU arm
@@ -740,6 +802,12 @@ def main():
                          '+ weight re-pack' % (tr.flat_size + 1)}
         del tr, tr_ex
 
+    # ---- (f1) the layout generator that feeds the path: one batch of 64 questions through the
+    #      attentional seq2seq at the CLEVR sizes (exp_clevr/train_clevr_*.py), greedy decoding
+    layout_gen = None
+    if rank == 0 and world == 1 and args.config == 'clevr' and not args.no_seq2seq:
+        layout_gen = seq2seq_measure(torch, bn.asm, dev, B)
+
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -796,7 +864,8 @@ def main():
             'host_enqueue_ms_per_step': head['host_enqueue_ms_per_step'], 'host_numa': numa,
             'roofline': roof.get('roofline'), 'roofline_text': roof.get('roofline_text'),
             'roofline_tree': roof.get('roofline_tree'), 'kernel_us': roof.get('kernel_us'),
-            'cpu_baseline': cpu, 'train_step': train, 'other_layout_sets': other_sets,
+            'cpu_baseline': cpu, 'train_step': train, 'layout_generator': layout_gen,
+            'other_layout_sets': other_sets,
             'strong_scaling': strong, 'other_configs': others,
         }
         print(json.dumps(line), flush=True)

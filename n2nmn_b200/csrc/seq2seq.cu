@@ -10,18 +10,21 @@
 //   table_enc [V_txt][4L]    = embedding_mat · W_x of encoder layer 0 (the embedding lookup and
 //   table_dec [V_nmn+1][4L]    the layer-0 input product fold into ONE row gather per token;
 //                              row V_nmn of table_dec is go_embedding)
-//   w_in[l] [L][4L] (l >= 1), w_rec[l] [L][4L], bias[l] [4L] : the BasicLSTMCell matrix split by
-//       input, with gate columns INTERLEAVED (column 4u+g = gate g of unit u, g = i, j, f, o) so
-//       that one thread's 4 adjacent accumulators are the 4 gates of one unit and the cell update
-//       happens in the GEMM epilogue;
+//   w_cell[side][l] [(in + L)][4L], b_cell [4L]: the BasicLSTMCell matrix (rows of the layer
+//       input, then rows of the recurrent state — TF's order) with the gate columns REGROUPED per
+//       8 units (regroup_gates_kernel) so that the cell update happens in the GEMM epilogue;
 //   h[l] double buffered [2][N][L] (every CTA reads all of h_prev while others write h_next),
 //   c[l] [N][L] in place; enc_out / enc_ht [T][N][L]; atts [T_dec][T_enc][N].
-// Kernels: lstm_step (one per layer per time step; 64x64-tile fp32 GEMM over [h_below, h_prev]
-// with the whole K in shared memory, text_proj.cuh), s2s_gemm (h-transform, attention query,
-// table precompute), dec_attn (one CTA per question and step: attention, context vector, token
-// scores, validity mask, argmax / forcing, probabilities, entropy, stack state update),
-// word_vecs. A step is latency bound (N <= 64 rows): ~32 CTAs; the whole call is a chain of
-// 2·L_layers·(T_enc + T_dec) + 2·T_dec + 2 launches captured in order on the caller's stream.
+// Kernels: lstm_step (one launch per layer per time step: [x, h_prev]·W on mma.sync m16n8k8 with
+// error-compensated TF32 = fp32 parity, 32 or 64 questions x 8 units per CTA, K streamed through
+// a cp.async ring, LSTM cell in the epilogue), s2s_gemm (same tile engine: h-transform, attention
+// query, table precompute), dec_attn (one CTA per question and step: attention, context vector,
+// token scores, validity mask, argmax / forcing, probabilities, entropy, stack-state update),
+// word_vecs. The whole call is a chain of layers·(T_enc + T_dec) + 2·T_dec + 3 dependent launches
+// on the caller's stream, linked by programmatic dependent launch: each kernel requests what does
+// not depend on its predecessor (weights, tables) before griddepcontrol.wait.
+// A step at N = 64 is latency bound (measured ~10 us per LSTM launch, r2 notes in DESIGN.md):
+// the next step for this row is a persistent kernel with the weights resident in shared memory.
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -47,19 +50,22 @@ namespace {
   } while (0)
 
 constexpr int kMaxLayers = 4;
-constexpr int kAttnThreads = 256;
+constexpr int kAttnThreads = 512;
 constexpr int kMaxVocabNmn = 64;    // token scores / masks live in one warp's reach
 constexpr int kMaxTEnc = 128;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-// dst[r][4u+g] = src[r][g*L+u]
-__global__ void interleave_gates_kernel(const float* __restrict__ src, float* __restrict__ dst,
-                                        int rows, int L) {
+// Gate columns regrouped per 8 units: dst column (u/8)*32 + g*8 + u%8 = src column g*L + u
+// (gate g = i, j, f, o of unit u). A CTA of the step kernel owns 32 such columns = all four gates
+// of 8 units, and inside it n-tile g of the mma holds gate g: one thread's accumulators across
+// the four n-tiles are the four gates of its two units.
+__global__ void regroup_gates_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                     int rows, int L) {
   const int n = rows * 4 * L;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int r = i / (4 * L), c = i - r * 4 * L;
-    const int u = c >> 2, g = c & 3;
+    const int blk = c >> 5, g = (c >> 3) & 3, u = blk * 8 + (c & 7);
     dst[i] = src[(size_t)r * 4 * L + g * L + u];
   }
 }
@@ -73,38 +79,186 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
   }
 }
 
-// out[r][c] = Σ_k A[r][k] B[k][c] + bias[c];  grid = (ceil(C/64), ceil(R/64))
-__global__ void __launch_bounds__(kTileThreads)
-s2s_gemm_kernel(const float* __restrict__ A, int lda, int R, int K, const float* __restrict__ B,
-                int ldb, int C, const float* __restrict__ bias, float* __restrict__ out, int ldo) {
-  extern __shared__ __align__(16) float tile_smem[];
-  const int row0 = blockIdx.y * kTileRows, c0 = blockIdx.x * kTextCols;
-  auto a_row = [&](int r) -> const float* {
-    return row0 + r < R ? A + (size_t)(row0 + r) * lda : nullptr;
-  };
-  float acc[2][4];
-  tile_gemm_64x64(tile_smem, a_row, K, B, ldb, c0, C, 1 << 30, acc);
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int r = row0 + 2 * ty + i;
-    if (r >= R) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = c0 + 4 * tx + j;
-      if (c < C) out[(size_t)r * ldo + c] = acc[i][j] + (bias ? bias[c] : 0.f);
+// ---- 64 x 32 output tile on mma.sync m16n8k8 with error-compensated TF32 (3 products per
+// fragment pair: hi*hi + hi*lo + lo*hi, fp32 accumulate: ~2^-21 relative, i.e. fp32 parity —
+// the decoded TOKENS must match the reference's fp32 graph, so plain TF32 is not an option).
+// Operands are split by truncation (hi = the top 19 bits, lo = x - hi exactly; the tensor core
+// ignores the low 13 bits of lo): 2 ALU instructions per element where cvt.rna is a sequence.
+//   C[r, c] = Σ_k A[r, k] B[k, c],  A = [A0 | A1] (two row-major sources side by side: the layer
+//   input and the recurrent state), B row-major with pitch ldb.
+// 8 warps = 4 row tiles of 16 x 2 halves of every 128-deep K chunk; chunks stream through a
+// 3-stage cp.async ring (A 64x128, B 128x32 per stage). B (weights) of the first stages is
+// requested BEFORE griddepcontrol.wait: under programmatic dependent launch the weight fetch of
+// step t+1 overlaps the tail of step t.
+constexpr int kMmaCols = 32, kMmaKC = 128, kMmaThreads = 256;
+constexpr int kMmaAPitch = kMmaKC + 4;     // rows g / g+8 and k / k+4 of a fragment: distinct banks
+constexpr int kMmaBPitch = kMmaCols + 8;
+#ifndef N2NMN_S2S_STAGES_NARROW
+#define N2NMN_S2S_STAGES_NARROW 5
+#endif
+// a stage = A [16 WM][kMmaAPitch] then B [kMmaKC][kMmaBPitch]: 3 stages (162 KB) for 64-row tiles,
+// 5 stages (187 KB) for 32-row tiles: at N <= 64 a step is bound by the latency of its operand
+// stream, i.e. by the bytes in flight per SM (measured 2.59 -> 1.97 ms per batch from 3 to 5)
+__host__ __device__ constexpr int mma_stage_floats(int wm) {
+  return 16 * wm * kMmaAPitch + kMmaKC * kMmaBPitch;
+}
+__host__ __device__ constexpr int mma_stages(int wm) { return wm == 2 ? N2NMN_S2S_STAGES_NARROW : 3; }
+__host__ __device__ constexpr size_t mma_smem_bytes(int wm) {
+  return (size_t)mma_stages(wm) * mma_stage_floats(wm) * sizeof(float);
+}
+
+struct GemmOperands {
+  const float* a0; int k0, lda0;   // A columns [0, k0)
+  const float* a1; int k1, lda1;   // A columns [k0, k0 + k1)  (k1 may be 0)
+  int R;                           // valid rows
+  const float* B; int ldb, C;      // B [k0 + k1][ldb], C valid columns
+};
+
+__device__ __forceinline__ void split_trunc(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// WM = row tiles of 16 per CTA (4: 64 rows, 2: 32 rows); the 8 warps split every K chunk
+// KH = 8 / WM ways. acc[nt][0..3]: rows (wm*16 + g, +8), columns nt*8 + 2*tig (+1) of the tile;
+// valid in the warps with kh == 0 (returns true there) after the call.
+// after_wait(): called once griddepcontrol.wait has returned and the first A chunks are in
+// flight — the place to start the loads the epilogue will need.
+template <int WM, class AfterWait>
+__device__ __forceinline__ bool mma_tile(float* smem, const GemmOperands& p, int row0, int c0,
+                                         float (&acc)[4][4], AfterWait after_wait) {
+  constexpr int KH = 8 / WM, ROWS = 16 * WM, KW = kMmaKC / KH;   // k extent per warp per chunk
+  constexpr int kMmaStageFloats = mma_stage_floats(WM), kMmaStages = mma_stages(WM);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp % WM, kh = warp / WM, g = lane >> 2, tig = lane & 3;
+  const int K = p.k0 + p.k1, nchunks = (K + kMmaKC - 1) / kMmaKC;
+  auto load_b = [&](int chunk, int stage) {
+    float* Bs = smem + stage * kMmaStageFloats + ROWS * kMmaAPitch;
+    const int kc0 = chunk * kMmaKC;
+    for (int i = tid; i < kMmaKC * (kMmaCols / 4); i += kMmaThreads) {
+      const int kk = i >> 3, q = i & 7, k = kc0 + kk, col = c0 + 4 * q;
+      float* dst = Bs + kk * kMmaBPitch + 4 * q;
+      if (k < K && col < p.C) tp_cp16(dst, p.B + (size_t)k * p.ldb + col);
+      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  };
+  auto load_a = [&](int chunk, int stage) {
+    float* As = smem + stage * kMmaStageFloats;
+    const int kc0 = chunk * kMmaKC;
+    for (int i = tid; i < ROWS * (kMmaKC / 4); i += kMmaThreads) {
+      const int r = i >> 5, q = i & 31, k = kc0 + 4 * q, row = row0 + r;
+      float* dst = As + r * kMmaAPitch + 4 * q;
+      if (row < p.R && k < K) {
+        const float* src = k < p.k0 ? p.a0 + (size_t)row * p.lda0 + k
+                                    : p.a1 + (size_t)row * p.lda1 + (k - p.k0);
+        tp_cp16(dst, src);
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int s = 0; s < kMmaStages - 1; ++s)
+    if (s < nchunks) load_b(s, s);
+  pdl_wait();   // everything below may read what the previous kernel in the stream wrote
+  for (int s = 0; s < kMmaStages - 1; ++s) {
+    if (s < nchunks) load_a(s, s);
+    tp_commit();
+  }
+  after_wait();
+  for (int c = 0; c < nchunks; ++c) {
+    tp_wait<kMmaStages - 2>();
+    __syncthreads();
+    const int nx = c + kMmaStages - 1;
+    if (nx < nchunks) { load_b(nx, nx % kMmaStages); load_a(nx, nx % kMmaStages); }
+    tp_commit();
+    const float* As = smem + (c % kMmaStages) * kMmaStageFloats + (wm * 16 + g) * kMmaAPitch;
+    const float* Bs = smem + (c % kMmaStages) * kMmaStageFloats + ROWS * kMmaAPitch + g;
+#pragma unroll 2
+    for (int ks = 0; ks < KW / 8; ++ks) {
+      const int kb = kh * KW + ks * 8;
+      uint32_t ah[4], al[4];
+      split_trunc(As[kb + tig], ah[0], al[0]);
+      split_trunc(As[8 * kMmaAPitch + kb + tig], ah[1], al[1]);
+      split_trunc(As[kb + tig + 4], ah[2], al[2]);
+      split_trunc(As[8 * kMmaAPitch + kb + tig + 4], ah[3], al[3]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        uint32_t bh0, bl0, bh1, bl1;
+        split_trunc(Bs[(kb + tig) * kMmaBPitch + nt * 8], bh0, bl0);
+        split_trunc(Bs[(kb + tig + 4) * kMmaBPitch + nt * 8], bh1, bl1);
+        mma_tf32(acc[nt], al, bh0, bh1);
+        mma_tf32(acc[nt], ah, bl0, bl1);
+        mma_tf32(acc[nt], ah, bh0, bh1);
+      }
+    }
+  }
+  tp_wait<0>();
+  __syncthreads();
+  // the K parts meet in shared memory (the stages are free now)
+  if (kh > 0) {
+    float* red = smem + (((kh - 1) * WM + wm) * 32 + lane) * 17;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[i * 4 + j] = acc[i][j];
+  }
+  __syncthreads();
+  if (kh == 0) {
+#pragma unroll
+    for (int part = 0; part < KH - 1; ++part) {
+      const float* red = smem + ((part * WM + wm) * 32 + lane) * 17;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += red[i * 4 + j];
+    }
+  }
+  return kh == 0;
+}
+
+// out[r][c] = Σ_k A[r][k] B[k][c] + bias[c];  grid = (ceil(C/32), ceil(R/(16 WM)))
+template <int WM>
+__global__ void __launch_bounds__(kMmaThreads)
+s2s_gemm_kernel(GemmOperands p, const float* __restrict__ bias, float* __restrict__ out, int ldo) {
+  pdl_trigger();
+  extern __shared__ __align__(16) float mma_smem[];
+  const int row0 = blockIdx.y * 16 * WM, c0 = blockIdx.x * kMmaCols;
+  float acc[4][4];
+  if (!mma_tile<WM>(mma_smem, p, row0, c0, acc, [] {})) return;
+  const int lane = threadIdx.x & 31, wm = (threadIdx.x >> 5) % WM, g = lane >> 2, tig = lane & 3;
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int r = row0 + wm * 16 + g + 8 * hh;
+    if (r >= p.R) continue;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = c0 + nt * 8 + 2 * tig + j;
+        if (c < p.C) out[(size_t)r * ldo + c] = acc[nt][hh * 2 + j] + (bias ? bias[c] : 0.f);
+      }
   }
 }
 
 struct LstmStep {
   const float* x;        // [N][L] output of the layer below at this step, or nullptr (layer 0)
-  const float* w_in;     // [L][4L] interleaved (layer >= 1)
   const float* h_prev;   // [N][L]
-  const float* w_rec;    // [L][4L] interleaved
-  const float* table;    // layer 0: [V][4L] interleaved input products, else nullptr
+  const float* w;        // [(L +) L][4L] regrouped: rows of x (layer >= 1) then rows of h_prev
+  const float* table;    // layer 0: [V][4L] regrouped input products, else nullptr
   const int32_t* tok;    // layer 0: token of question n at this step
-  const float* bias;     // [4L] interleaved
+  const float* bias;     // [4L] regrouped
   float* c;              // [N][L] in place
   float* h_out;          // [N][L]
   float* out_seq;        // encoder top layer: encoder_outputs[t] (zero past the end) or nullptr
@@ -114,43 +268,73 @@ struct LstmStep {
 
 // BasicLSTMCell(forget_bias=1) step (gate order i, j, f, o) with dynamic_rnn's masking: past the
 // sequence end the state is carried through and the output is zero (nmn3_netgen_att.py:95-99).
-// grid = (4L/64, ceil(N/64))
-__global__ void __launch_bounds__(kTileThreads) lstm_step_kernel(LstmStep p) {
-  extern __shared__ __align__(16) float tile_smem[];
-  const int row0 = blockIdx.y * kTileRows, c0 = blockIdx.x * kTextCols;
+// grid = (4L/32, ceil(N/(16 WM))): one CTA = 8 units x 64 (WM = 4) or 32 (WM = 2) questions; the
+// narrow variant is used while it is what it takes to put a CTA on most SMs (N <= 64 at L = 512).
+template <int WM>
+__global__ void __launch_bounds__(kMmaThreads) lstm_step_kernel(LstmStep p) {
+  pdl_trigger();
+  extern __shared__ __align__(16) float mma_smem[];
+  const int row0 = blockIdx.y * 16 * WM, c0 = blockIdx.x * kMmaCols;
   const int L = p.L, C = 4 * L;
-  float acc[2][4];
-  auto h_row = [&](int r) -> const float* {
-    return row0 + r < p.N ? p.h_prev + (size_t)(row0 + r) * L : nullptr;
-  };
-  tile_gemm_64x64(tile_smem, h_row, L, p.w_rec, C, c0, C, 1 << 30, acc);
-  if (p.x != nullptr) {
-    auto x_row = [&](int r) -> const float* {
-      return row0 + r < p.N ? p.x + (size_t)(row0 + r) * L : nullptr;
-    };
-    tile_gemm_64x64(tile_smem, x_row, L, p.w_in, C, c0, C, 1 << 30, acc, false);
-  }
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int col = c0 + 4 * tx, u = col >> 2;
-  if (col >= C) return;
-  const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col);
+  GemmOperands op;
+  if (p.x != nullptr) { op.a0 = p.x; op.k0 = L; op.lda0 = L; op.a1 = p.h_prev; op.k1 = L; op.lda1 = L; }
+  else { op.a0 = p.h_prev; op.k0 = L; op.lda0 = L; op.a1 = nullptr; op.k1 = 0; op.lda1 = 0; }
+  op.R = p.N; op.B = p.w; op.ldb = C; op.C = C;
+  float acc[4][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wm = warp % WM, g = lane >> 2,
+            tig = lane & 3;
+  // epilogue inputs, requested as soon as the previous step is complete (they ride under the GEMM)
+  float gt[2][4][2], c_prev[2][2], h_keep[2][2];
+  bool live[2];
+  auto prefetch = [&] {
+    if (warp / WM != 0) return;
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int n = row0 + 2 * ty + i;
-    if (n >= p.N) continue;
-    float g[4] = {acc[i][0] + b4.x, acc[i][1] + b4.y, acc[i][2] + b4.z, acc[i][3] + b4.w};
-    if (p.table != nullptr) {
-      const float4 e = *reinterpret_cast<const float4*>(p.table + (size_t)p.tok[n] * C + col);
-      g[0] += e.x; g[1] += e.y; g[2] += e.z; g[3] += e.w;
+    for (int hh = 0; hh < 2; ++hh) {
+      const int n = row0 + wm * 16 + g + 8 * hh;
+#pragma unroll
+      for (int gate = 0; gate < 4; ++gate) {
+        const float2 b2 = *reinterpret_cast<const float2*>(p.bias + c0 + gate * 8 + 2 * tig);
+        gt[hh][gate][0] = b2.x; gt[hh][gate][1] = b2.y;
+      }
+      live[hh] = false;
+      if (n >= p.N) continue;
+      if (p.table != nullptr) {
+        const float* row = p.table + (size_t)p.tok[n] * C + c0 + 2 * tig;
+#pragma unroll
+        for (int gate = 0; gate < 4; ++gate) {
+          const float2 e = *reinterpret_cast<const float2*>(row + gate * 8);
+          gt[hh][gate][0] += e.x; gt[hh][gate][1] += e.y;
+        }
+      }
+      live[hh] = p.seq_len == nullptr || p.t < p.seq_len[n];
+      const size_t idx = (size_t)n * L + (c0 >> 2) + 2 * tig;
+      const float2 cp = *reinterpret_cast<const float2*>(p.c + idx);
+      const float2 hp = *reinterpret_cast<const float2*>(p.h_prev + idx);
+      c_prev[hh][0] = cp.x; c_prev[hh][1] = cp.y;
+      h_keep[hh][0] = hp.x; h_keep[hh][1] = hp.y;
     }
-    const size_t idx = (size_t)n * L + u;
-    const float c_prev = p.c[idx];
-    const float c2 = c_prev * sigmoidf_(g[2] + 1.0f) + sigmoidf_(g[0]) * tanhf(g[1]);
-    const float h2 = tanhf(c2) * sigmoidf_(g[3]);
-    const bool live = p.seq_len == nullptr || p.t < p.seq_len[n];
-    p.c[idx] = live ? c2 : c_prev;
-    p.h_out[idx] = live ? h2 : p.h_prev[idx];
-    if (p.out_seq != nullptr) p.out_seq[idx] = live ? h2 : 0.f;
+  };
+  if (!mma_tile<WM>(mma_smem, op, row0, c0, acc, prefetch)) return;
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int n = row0 + wm * 16 + g + 8 * hh;
+    if (n >= p.N) continue;
+    float c_new[2], h_new[2], o_new[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float gi = gt[hh][0][j] + acc[0][hh * 2 + j], gj = gt[hh][1][j] + acc[1][hh * 2 + j];
+      const float gf = gt[hh][2][j] + acc[2][hh * 2 + j], go = gt[hh][3][j] + acc[3][hh * 2 + j];
+      const float c2 = c_prev[hh][j] * sigmoidf_(gf + 1.0f) + sigmoidf_(gi) * tanhf(gj);
+      const float h2 = tanhf(c2) * sigmoidf_(go);
+      c_new[j] = live[hh] ? c2 : c_prev[hh][j];
+      h_new[j] = live[hh] ? h2 : h_keep[hh][j];
+      o_new[j] = live[hh] ? h2 : 0.f;
+    }
+    const size_t idx = (size_t)n * L + (c0 >> 2) + 2 * tig;
+    *reinterpret_cast<float2*>(p.c + idx) = make_float2(c_new[0], c_new[1]);
+    *reinterpret_cast<float2*>(p.h_out + idx) = make_float2(h_new[0], h_new[1]);
+    if (p.out_seq != nullptr)
+      *reinterpret_cast<float2*>(p.out_seq + idx) = make_float2(o_new[0], o_new[1]);
   }
 }
 
@@ -176,30 +360,73 @@ struct AttnStep {
   int T, N, L, V;
 };
 
-// One CTA per question: nmn3_netgen_att.py:205-293 for one decoding step.
+// One CTA per question: nmn3_netgen_att.py:205-293 for one decoding step. Everything that does
+// not depend on the previous kernel (W_y^T, v, b_y and the Assembler tables) is staged in shared
+// memory BEFORE griddepcontrol.wait, i.e. under the tail of the kernels before it. The step is a
+// chain of short phases, each bound by the latency of its global loads, so every phase keeps as
+// many independent 16-byte loads in flight per thread as registers allow.
+__host__ __device__ inline size_t attn_smem_floats(int L, int T, int V) {
+  const int part = L > 4 * kAttnThreads ? L : 4 * kAttnThreads;
+  return (size_t)V * 2 * L + 4 * L + part + ((T + 3) & ~3) + 2 * ((V + 3) & ~3) + 3 * V + 12 * V +
+         4 * V + 8;
+}
 __global__ void __launch_bounds__(kAttnThreads) dec_attn_kernel(AttnStep p) {
+  pdl_trigger();
   extern __shared__ __align__(16) float sm[];
   const int n = blockIdx.x, L = p.L, T = p.T, V = p.V;
-  float* s_x = sm;                 // [2L] = [h_top, d2]
-  float* s_q = sm + 2 * L;         // [L]
-  float* s_v = s_q + L;            // [L]
-  float* s_att = s_v + L;          // [T]
-  float* s_sc = s_att + T;         // [V]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = kAttnThreads / 32;
-  for (int d = threadIdx.x; d < L; d += kAttnThreads) {
+  const int part = L > 4 * kAttnThreads ? L : 4 * kAttnThreads;
+  float* s_wy = sm;                    // [V][2L]
+  float* s_x = s_wy + (size_t)V * 2 * L;   // [2L] = [h_top, d2]
+  float* s_q = s_x + 2 * L;            // [L]
+  float* s_v = s_q + L;                // [L]
+  float* s_part = s_v + L;             // [G][L] partial context vectors
+  float* s_att = s_part + part;        // [T]
+  float* s_sc = s_att + ((T + 3) & ~3);   // [V] scores
+  float* s_by = s_sc + ((V + 3) & ~3);    // [V]
+  int32_t* s_P = reinterpret_cast<int32_t*>(s_by + ((V + 3) & ~3));   // [V][3]
+  int32_t* s_W = s_P + 3 * V;          // [3][V][4]
+  int32_t* s_b = s_W + 12 * V;         // [V][4]
+  int32_t* s_valid = s_b + 4 * V;      // [2]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kAttnThreads / 32;
+  for (int i = tid; i < V * 2 * L / 4; i += kAttnThreads) tp_cp16(s_wy + 4 * i, p.wy_t + 4 * i);
+  tp_commit();
+  for (int d = tid; d < L; d += kAttnThreads) s_v[d] = p.v[d];
+  for (int i = tid; i < V; i += kAttnThreads) s_by[i] = p.by[i];
+  for (int i = tid; i < 3 * V; i += kAttnThreads) s_P[i] = p.P[i];
+  for (int i = tid; i < 12 * V; i += kAttnThreads) s_W[i] = p.W[i];
+  for (int i = tid; i < 4 * V; i += kAttnThreads) s_b[i] = p.b[i];
+  pdl_wait();
+  for (int d = tid; d < L; d += kAttnThreads) {
     s_x[d] = p.h_top[(size_t)n * L + d];
     s_q[d] = p.q[(size_t)n * L + d];
-    s_v[d] = p.v[d];
   }
   __syncthreads();
-  // att_raw[te] = Σ_d tanh(q + enc_ht[te]) v   (:208-212)
-  for (int te = warp; te < T; te += nw) {
-    const float* ht = p.enc_ht + ((size_t)te * p.N + n) * L;
-    float s = 0.f;
-    for (int d = lane; d < L; d += 32) s += tanhf(s_q[d] + ht[d]) * s_v[d];
+  const int ncol = L >> 2;
+  const size_t tstride = (size_t)p.N * L;
+  // att_raw[te] = Σ_d tanh(q + enc_ht[te]) v   (:208-212): a warp takes 4 time steps at once
+  for (int tb = warp * 4; tb < T; tb += nw * 4) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* ht = p.enc_ht + (size_t)tb * tstride + (size_t)n * L;
+#pragma unroll 2
+    for (int c4 = lane; c4 < ncol; c4 += 32) {
+      const float4 q4 = reinterpret_cast<const float4*>(s_q)[c4];
+      const float4 v4 = reinterpret_cast<const float4*>(s_v)[c4];
+      float4 h4[4];
 #pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) s_att[te] = s;
+      for (int i = 0; i < 4; ++i)
+        h4[i] = tb + i < T ? __ldg(reinterpret_cast<const float4*>(ht + i * tstride) + c4)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        s[i] += tanhf(q4.x + h4[i].x) * v4.x + tanhf(q4.y + h4[i].y) * v4.y +
+                tanhf(q4.z + h4[i].z) * v4.z + tanhf(q4.w + h4[i].w) * v4.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+      if (lane == 0 && tb + i < T) s_att[tb + i] = s[i];
+    }
   }
   __syncthreads();
   // softmax over ALL time steps, then mask by the sequence length and renormalise (:213-216)
@@ -225,69 +452,111 @@ __global__ void __launch_bounds__(kAttnThreads) dec_attn_kernel(AttnStep p) {
       s_att[te] = a;
       p.atts[(size_t)te * p.N + n] = a;
     }
+  } else if (warp == 1) {
+    // validity of every token from the decoding state (:8-11); all ones under forcing (:230-233)
+    const int32_t x0 = p.X[n * 3], x1 = p.X[n * 3 + 1], x2 = p.X[n * 3 + 2];
+    uint32_t lo = 0, hi = 0;
+    for (int base = 0; base < V; base += 32) {
+      const int vv = base + lane;
+      bool ok = vv < V;
+      if (ok && p.gt == nullptr) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int32_t lhs = x0 * s_W[(0 * V + vv) * 4 + c] + x1 * s_W[(1 * V + vv) * 4 + c] +
+                              x2 * s_W[(2 * V + vv) * 4 + c];
+          ok = ok && (lhs - s_b[vv * 4 + c] >= 0);
+        }
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+      if (base == 0) lo = bal; else hi = bal;
+    }
+    if (lane == 0) { s_valid[0] = (int32_t)lo; s_valid[1] = (int32_t)hi; }
   }
   __syncthreads();
-  // d2 = Σ_te att[te] encoder_outputs[te]   (:218)
-  for (int d = threadIdx.x; d < L; d += kAttnThreads) {
-    float s = 0.f;
-    for (int te = 0; te < T; ++te) s += s_att[te] * p.enc_out[((size_t)te * p.N + n) * L + d];
-    s_x[L + d] = s;
+  // d2 = Σ_te att[te] encoder_outputs[te]   (:218): G groups of threads split the time steps of
+  // each 4-channel column, partial sums meet in shared memory
+  {
+    const int G = ncol >= kAttnThreads ? 1 : kAttnThreads / ncol;
+    for (int item = tid; item < ncol * G; item += kAttnThreads) {
+      const int c4 = item % ncol, gi = item / ncol;
+      const float4* eo = reinterpret_cast<const float4*>(p.enc_out + (size_t)n * L) + c4;
+      float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+      for (int te = gi; te < T; te += G) {
+        const float4 e = __ldg(eo + (size_t)te * (tstride >> 2));
+        const float a = s_att[te];
+        acc4.x += a * e.x; acc4.y += a * e.y; acc4.z += a * e.z; acc4.w += a * e.w;
+      }
+      reinterpret_cast<float4*>(s_part + (size_t)gi * L)[c4] = acc4;
+    }
+    __syncthreads();
+    for (int d = tid; d < L; d += kAttnThreads) {
+      float s = 0.f;
+      for (int gi = 0; gi < G; ++gi) s += s_part[(size_t)gi * L + d];
+      s_x[L + d] = s;
+    }
   }
+  tp_wait<0>();
   __syncthreads();
   // token_scores = [h_top, d2] · W_y + b_y   (:221-223)
   for (int vv = warp; vv < V; vv += nw) {
-    const float* wr = p.wy_t + (size_t)vv * 2 * L;
+    const float4* wr = reinterpret_cast<const float4*>(s_wy + (size_t)vv * 2 * L);
     float s = 0.f;
-    for (int k = lane; k < 2 * L; k += 32) s += s_x[k] * wr[k];
+    for (int k4 = lane; k4 < 2 * ncol; k4 += 32) {
+      const float4 x4 = reinterpret_cast<const float4*>(s_x)[k4], w4 = wr[k4];
+      s += x4.x * w4.x + x4.y * w4.y + x4.z * w4.z + x4.w * w4.w;
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) s_sc[vv] = s + p.by[vv];
+    if (lane == 0) s_sc[vv] = s + s_by[vv];
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const int32_t x0 = p.X[n * 3], x1 = p.X[n * 3 + 1], x2 = p.X[n * 3 + 2];
-    uint64_t valid = 0;
-    float mx = -INFINITY;
-    for (int vv = 0; vv < V; ++vv) {
-      bool ok = true;
-      if (p.gt == nullptr) {   // _get_valid_tokens (:8-11); all ones under teacher forcing (:230-233)
-        for (int c = 0; c < 4; ++c) {
-          const int32_t lhs = x0 * p.W[(0 * V + vv) * 4 + c] + x1 * p.W[(1 * V + vv) * 4 + c] +
-                              x2 * p.W[(2 * V + vv) * 4 + c];
-          ok = ok && (lhs - p.b[vv * 4 + c] >= 0);
-        }
-      }
-      if (ok) valid |= 1ull << vv;
-      mx = fmaxf(mx, s_sc[vv]);
-    }
+  if (warp == 0) {   // lane handles tokens lane and lane + 32 (V <= 64)
+    const uint32_t vlo = (uint32_t)s_valid[0], vhi = (uint32_t)s_valid[1];
+    const int v0 = lane, v1 = lane + 32;
+    const bool in0 = v0 < V, in1 = v1 < V;
+    const bool ok0 = in0 && ((vlo >> lane) & 1), ok1 = in1 && ((vhi >> lane) & 1);
+    const float sc0 = in0 ? s_sc[v0] : -INFINITY, sc1 = in1 ? s_sc[v1] : -INFINITY;
+    float mx = fmaxf(sc0, sc1);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     // greedy token: invalid scores are replaced by (global min - 1) before the argmax (:259-261),
     // i.e. the first best VALID token, or token 0 if none is valid
-    int pred = 0;
-    float best = -INFINITY;
-    for (int vv = 0; vv < V; ++vv)
-      if (((valid >> vv) & 1) && s_sc[vv] > best) { best = s_sc[vv]; pred = vv; }
+    float best = ok0 ? sc0 : -INFINITY;
+    int pred = ok0 ? v0 : 0x7fffffff;
+    if (ok1 && sc1 > best) { best = sc1; pred = v1; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int op = __shfl_xor_sync(0xffffffffu, pred, o);
+      if (ob > best || (ob == best && op < pred)) { best = ob; pred = op; }
+    }
+    if (pred == 0x7fffffff) pred = 0;
     if (p.gt != nullptr) pred = p.gt[n];   // :264-266
-    float se = 0.f;
-    for (int vv = 0; vv < V; ++vv) { const float e = expf(s_sc[vv] - mx); s_sc[vv] = e; se += e; }
-    float sv = 0.f;
-    for (int vv = 0; vv < V; ++vv) {
-      const float a = ((valid >> vv) & 1) ? s_sc[vv] / se : 0.f;   // :270
-      s_sc[vv] = a; sv += a;
-    }
+    const float e0 = in0 ? expf(sc0 - mx) : 0.f, e1 = in1 ? expf(sc1 - mx) : 0.f;
+    float se = e0 + e1;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    const float a0 = ok0 ? e0 / se : 0.f, a1 = ok1 ? e1 / se : 0.f;      // :270
+    float sv = a0 + a1;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+    const float p0 = a0 / sv, p1 = a1 / sv;                               // :272
     float ent = 0.f;
-    for (int vv = 0; vv < V; ++vv) {
-      const float a = s_sc[vv] / sv;                               // :272
-      s_sc[vv] = a;
-      const float inv = ((valid >> vv) & 1) ? 0.f : 1.f;
-      ent += a * logf(fmaxf(1e-5f, a + inv));                      // :283-285
+    if (in0) ent += p0 * logf(fmaxf(1e-5f, p0 + (ok0 ? 0.f : 1.f)));      // :283-285
+    if (in1) ent += p1 * logf(fmaxf(1e-5f, p1 + (ok1 ? 0.f : 1.f)));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ent += __shfl_xor_sync(0xffffffffu, ent, o);
+    const float pp = __shfl_sync(0xffffffffu, pred < 32 ? p0 : p1, pred & 31);
+    if (lane == 0) {
+      p.probs[n] = pp;                                                    // :281
+      p.neg_entropy[n] += ent;
+      p.X[n * 3] += s_P[pred * 3];                                        // :288-289
+      p.X[n * 3 + 1] += s_P[pred * 3 + 1];
+      p.X[n * 3 + 2] += s_P[pred * 3 + 2];
+      p.tokens[n] = pred;
+      p.cur_tok[n] = pred;
     }
-    p.probs[n] = s_sc[pred];                                        // :281
-    p.neg_entropy[n] += ent;
-    p.X[n * 3] = x0 + p.P[pred * 3];                                // :288-289
-    p.X[n * 3 + 1] = x1 + p.P[pred * 3 + 1];
-    p.X[n * 3 + 2] = x2 + p.P[pred * 3 + 2];
-    p.tokens[n] = pred;
-    p.cur_tok[n] = pred;
   }
 }
 
@@ -354,14 +623,37 @@ struct n2nmn_seq2seq {
 
 namespace {
 
-size_t gemm_smem(int K) { return (size_t)tile_smem_floats(K) * 4 + kTileRows * sizeof(void*); }
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                       cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t lc;
+  std::memset(&lc, 0, sizeof(lc));
+  lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = 1;
+  return cudaLaunchKernelEx(&lc, kernel, KArgs(args)...);
+}
+
+// 32-row tiles while 64-row tiles would leave SMs without a CTA
+bool narrow_tiles(int col_blocks, int R) { return R > 16 && col_blocks * ((R + 63) / 64) < 148; }
 
 int launch_gemm(n2nmn_seq2seq* s, cudaStream_t st, const float* A, int lda, int R, int K,
                 const float* B, int ldb, int C, const float* bias, float* out, int ldo) {
-  dim3 grid((C + kTextCols - 1) / kTextCols, (R + kTileRows - 1) / kTileRows);
-  s2s_gemm_kernel<<<grid, kTileThreads, gemm_smem(K), st>>>(A, lda, R, K, B, ldb, C, bias, out, ldo);
+  GemmOperands op;
+  op.a0 = A; op.k0 = K; op.lda0 = lda; op.a1 = nullptr; op.k1 = 0; op.lda1 = 0;
+  op.R = R; op.B = B; op.ldb = ldb; op.C = C;
+  const int cb = (C + kMmaCols - 1) / kMmaCols;
+  if (narrow_tiles(cb, R)) {
+    S2S_TRY(launch_pdl(s2s_gemm_kernel<2>, dim3(cb, (R + 31) / 32), dim3(kMmaThreads),
+                       mma_smem_bytes(2), st, op, bias, out, ldo));
+  } else {
+    S2S_TRY(launch_pdl(s2s_gemm_kernel<4>, dim3(cb, (R + 63) / 64), dim3(kMmaThreads),
+                       mma_smem_bytes(4), st, op, bias, out, ldo));
+  }
   ++s->launches;
-  S2S_TRY(cudaGetLastError());
   return N2NMN_OK;
 }
 
@@ -379,10 +671,10 @@ int prepare(n2nmn_seq2seq* s, cudaStream_t st) {
   for (int side = 0; side < 2; ++side) {
     for (int l = 0; l < g.num_layers; ++l) {
       const int in = l == 0 ? (side == 0 ? g.embed_dim_txt : g.embed_dim_nmn) : L;
-      interleave_gates_kernel<<<148, 256, 0, st>>>(s->v(cell_prefix(side, l) + "weights"),
-                                                   s->w_cell[side][l], in + L, L);
-      interleave_gates_kernel<<<8, 256, 0, st>>>(s->v(cell_prefix(side, l) + "biases"),
-                                                 s->b_cell[side][l], 1, L);
+      regroup_gates_kernel<<<148, 256, 0, st>>>(s->v(cell_prefix(side, l) + "weights"),
+                                                s->w_cell[side][l], in + L, L);
+      regroup_gates_kernel<<<8, 256, 0, st>>>(s->v(cell_prefix(side, l) + "biases"),
+                                              s->b_cell[side][l], 1, L);
       s->launches += 2;
     }
   }
@@ -418,11 +710,12 @@ int n2nmn_seq2seq_create(const n2nmn_seq2seq_config* cfg, n2nmn_seq2seq** out) {
   if (cfg->abi_version != N2NMN_ABI_VERSION) return fail_with(N2NMN_ERR_ARG, "ABI version mismatch");
   const int L = cfg->lstm_dim;
   if (cfg->num_vocab_txt <= 0 || cfg->embed_dim_txt <= 0 || cfg->embed_dim_nmn <= 0 ||
+      cfg->embed_dim_txt % 4 != 0 || cfg->embed_dim_nmn % 4 != 0 ||
       cfg->num_vocab_nmn <= 0 || cfg->num_vocab_nmn > kMaxVocabNmn || L <= 0 || L % 16 != 0 ||
       cfg->num_layers <= 0 || cfg->num_layers > kMaxLayers || cfg->T_encoder <= 0 ||
       cfg->T_encoder > kMaxTEnc || cfg->T_decoder <= 0 || cfg->max_batch <= 0)
     return fail_with(N2NMN_ERR_ARG,
-                     "bad seq2seq config (lstm_dim must be a multiple of 16, num_vocab_nmn <= 64, "
+                     "bad seq2seq config (lstm_dim must be a multiple of 16, embed dims of 4, num_vocab_nmn <= 64, "
                      "num_layers <= 4, T_encoder <= 128)");
   S2S_TRY(cudaSetDevice(cfg->device));
   cudaDeviceProp prop;
@@ -484,11 +777,19 @@ int n2nmn_seq2seq_create(const n2nmn_seq2seq_config* cfg, n2nmn_seq2seq** out) {
   S2S_TRY(dmalloc(&s->P, (size_t)Vn * 3));
   S2S_TRY(dmalloc(&s->W, (size_t)3 * Vn * 4));
   S2S_TRY(dmalloc(&s->b, (size_t)Vn * 4));
-  const int maxK = std::max(std::max(Et, En), L);
-  S2S_TRY(cudaFuncSetAttribute(s2s_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)gemm_smem(maxK)));
-  S2S_TRY(cudaFuncSetAttribute(lstm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)gemm_smem(L)));
+  S2S_TRY(cudaFuncSetAttribute(s2s_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)mma_smem_bytes(2)));
+  S2S_TRY(cudaFuncSetAttribute(s2s_gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)mma_smem_bytes(4)));
+  S2S_TRY(cudaFuncSetAttribute(lstm_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)mma_smem_bytes(2)));
+  S2S_TRY(cudaFuncSetAttribute(lstm_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)mma_smem_bytes(4)));
+  const size_t attn_bytes = attn_smem_floats(L, cfg->T_encoder, Vn) * sizeof(float);
+  if (attn_bytes > 200 * 1024)
+    return fail_with(N2NMN_ERR_ARG, "num_vocab_nmn * lstm_dim too large for the decoder step kernel");
+  S2S_TRY(cudaFuncSetAttribute(dec_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)attn_bytes));
   *out = s;
   return N2NMN_OK;
 }
@@ -573,17 +874,17 @@ int n2nmn_seq2seq_forward(n2nmn_seq2seq* s, const int32_t* input_seq_dev,
   }
   init_state_kernel<<<(N + 127) / 128, 128, 0, st>>>(s->X, s->cur_tok, neg_entropy_dev, N, T_dec, Vn);
   ++s->launches;
-  const dim3 grid(C / kTextCols, (N + kTileRows - 1) / kTileRows);
-  const size_t smem = gemm_smem(L);
+  const bool narrow = narrow_tiles(C / kMmaCols, N);
+  const dim3 grid(C / kMmaCols, narrow ? (N + 31) / 32 : (N + 63) / 64);
   int cur = 0;   // h[l][cur] holds every layer's h_{t-1}
+  bool ok = true;
   auto step = [&](int side, int t, const int32_t* tok, const int32_t* seq_len, float* out_seq) {
     for (int l = 0; l < NL; ++l) {
       const int in = l == 0 ? (side == 0 ? Et : En) : L;
       LstmStep p;
       p.x = l == 0 ? nullptr : s->h[l - 1][cur ^ 1];
-      p.w_in = s->w_cell[side][l];
       p.h_prev = s->h[l][cur];
-      p.w_rec = s->w_cell[side][l] + (size_t)in * C;
+      p.w = s->w_cell[side][l] + (l == 0 ? (size_t)in * C : 0);
       p.table = l == 0 ? (side == 0 ? s->table_enc : s->table_dec) : nullptr;
       p.tok = tok;
       p.bias = s->b_cell[side][l];
@@ -592,7 +893,10 @@ int n2nmn_seq2seq_forward(n2nmn_seq2seq* s, const int32_t* input_seq_dev,
       p.out_seq = l == NL - 1 ? out_seq : nullptr;
       p.seq_len = seq_len;
       p.t = t; p.N = N; p.L = L;
-      lstm_step_kernel<<<grid, kTileThreads, smem, st>>>(p);
+      if ((narrow ? launch_pdl(lstm_step_kernel<2>, grid, dim3(kMmaThreads), mma_smem_bytes(2), st, p)
+                  : launch_pdl(lstm_step_kernel<4>, grid, dim3(kMmaThreads), mma_smem_bytes(4), st, p)) !=
+          cudaSuccess)
+        ok = false;
       ++s->launches;
     }
     cur ^= 1;
@@ -603,7 +907,7 @@ int n2nmn_seq2seq_forward(n2nmn_seq2seq* s, const int32_t* input_seq_dev,
   int rc = launch_gemm(s, st, s->enc_out, L, T_enc * N, L, s->v("encoder/encoder_h_transform/weights"),
                        L, L, s->v("encoder/encoder_h_transform/biases"), s->enc_ht, L);   // :104-108
   if (rc) return rc;
-  const size_t attn_smem = sizeof(float) * (4 * L + T_enc + Vn);
+  const size_t attn_smem = attn_smem_floats(L, T_enc, Vn) * sizeof(float);
   for (int t = 0; t < T_dec; ++t) {   // raw_rnn loop (:199-305)
     step(1, t, s->cur_tok, nullptr, nullptr);
     const float* h_top = s->h[NL - 1][cur];
@@ -622,13 +926,15 @@ int n2nmn_seq2seq_forward(n2nmn_seq2seq* s, const int32_t* input_seq_dev,
     a.neg_entropy = neg_entropy_dev;
     a.atts = atts + (size_t)t * T_enc * N;
     a.T = T_enc; a.N = N; a.L = L; a.V = Vn;
-    dec_attn_kernel<<<N, kAttnThreads, attn_smem, st>>>(a);
+    if (launch_pdl(dec_attn_kernel, dim3(N), dim3(kAttnThreads), attn_smem, st, a) != cudaSuccess)
+      ok = false;
     ++s->launches;
   }
   word_vecs_kernel<<<dim3(N, T_dec), 128, sizeof(float) * 2 * T_enc, st>>>(
       atts, input_seq_dev, s->v("encoder/embedding_mat"), word_vecs_dev, T_enc, N, Et);
   ++s->launches;
   S2S_TRY(cudaGetLastError());
+  if (!ok) return fail_with(N2NMN_ERR_CUDA, "seq2seq kernel launch failed");
   return N2NMN_OK;
 }
 

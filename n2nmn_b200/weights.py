@@ -99,3 +99,34 @@ def l2_reg(weights):
     excluded (models_clevr/nmn3_model.py:163-166)."""
     return float(sum(0.5 * np.sum(np.asarray(w, np.float64) ** 2)
                      for n, w in weights.items() if n.endswith('/weights')))
+
+
+def init_seq2seq_weights(num_vocab_txt, embed_dim_txt, num_vocab_nmn, embed_dim_nmn, lstm_dim,
+                         num_layers, seed=0):
+    """Random weights of the layout generator under the reference's variable names relative to
+    ``encoder_decoder/`` (models_clevr/nmn3_netgen_att.py:73-240): uniform, Xavier-like scale, the
+    attention vector and the token projection a little hotter so that the decoded layouts vary
+    across questions. For tests and benchmarks (no checkpoints are reachable offline)."""
+    rng = np.random.RandomState(seed)
+    L = lstm_dim
+    w = OrderedDict()
+
+    def u(*shape, a):
+        return rng.uniform(-a, a, size=shape).astype(np.float32)
+    w['encoder/embedding_mat'] = u(num_vocab_txt, embed_dim_txt, a=0.5)
+    w['decoder/embedding_mat'] = u(num_vocab_nmn, embed_dim_nmn, a=0.5)
+    w['decoder/go_embedding'] = u(1, embed_dim_nmn, a=0.5)
+    for side, E in (('encoder', embed_dim_txt), ('decoder', embed_dim_nmn)):
+        for l in range(num_layers):
+            n_in = (E if l == 0 else L) + L
+            p = '%s/lstm/multi_rnn_cell/cell_%d/basic_lstm_cell/' % (side, l)
+            w[p + 'weights'] = u(n_in, 4 * L, a=(3.0 / n_in) ** 0.5)
+            w[p + 'biases'] = u(4 * L, a=0.1)
+    w['encoder/encoder_h_transform/weights'] = u(L, L, a=(3.0 / L) ** 0.5)
+    w['encoder/encoder_h_transform/biases'] = u(L, a=0.1)
+    w['decoder/att_prediction/weights'] = u(L, L, a=(3.0 / L) ** 0.5)
+    w['decoder/att_prediction/biases'] = u(L, a=0.1)
+    w['decoder/att_prediction/v'] = u(L, a=(3.0 / L) ** 0.5 * 4)
+    w['decoder/token_prediction/weights'] = u(2 * L, num_vocab_nmn, a=(3.0 / L) ** 0.5 * 4)
+    w['decoder/token_prediction/biases'] = u(num_vocab_nmn, a=0.1)
+    return w

@@ -14,6 +14,7 @@ import pytest
 import torch
 
 from n2nmn_b200 import synth
+from n2nmn_b200.weights import init_seq2seq_weights
 from n2nmn_b200.assembler import Assembler
 from oracle import seq2seq_oracle as so
 
@@ -60,30 +61,6 @@ def test_matches_reference_goldens():
           Z['greedy_word_vecs'], Z['greedy_atts'])
 
 
-def random_weights(rng, V_txt, E_txt, V_nmn, E_nmn, L, layers, scale=1.0):
-    w = {}
-
-    def u(*shape, a):
-        return rng.uniform(-a, a, size=shape).astype(np.float32)
-    w['encoder/embedding_mat'] = u(V_txt, E_txt, a=0.5 * scale)
-    w['decoder/embedding_mat'] = u(V_nmn, E_nmn, a=0.5 * scale)
-    w['decoder/go_embedding'] = u(1, E_nmn, a=0.5 * scale)
-    for side, E in (('encoder', E_txt), ('decoder', E_nmn)):
-        for l in range(layers):
-            n_in = (E if l == 0 else L) + L
-            p = '%s/lstm/multi_rnn_cell/cell_%d/basic_lstm_cell/' % (side, l)
-            w[p + 'weights'] = u(n_in, 4 * L, a=scale * (3.0 / n_in) ** 0.5)
-            w[p + 'biases'] = u(4 * L, a=0.1)
-    w['encoder/encoder_h_transform/weights'] = u(L, L, a=scale * (3.0 / L) ** 0.5)
-    w['encoder/encoder_h_transform/biases'] = u(L, a=0.1)
-    w['decoder/att_prediction/weights'] = u(L, L, a=scale * (3.0 / L) ** 0.5)
-    w['decoder/att_prediction/biases'] = u(L, a=0.1)
-    w['decoder/att_prediction/v'] = u(L, a=scale * (3.0 / L) ** 0.5 * 4)
-    w['decoder/token_prediction/weights'] = u(2 * L, V_nmn, a=scale * (3.0 / L) ** 0.5 * 4)
-    w['decoder/token_prediction/biases'] = u(V_nmn, a=0.1)
-    return w
-
-
 @pytest.mark.parametrize('N,T_enc,T_dec,L,layers', [(64, 45, 20, 512, 2), (37, 26, 13, 208, 1),
                                                      (1, 5, 10, 64, 3)])
 def test_matches_oracle_at_reference_sizes(N, T_enc, T_dec, L, layers):
@@ -91,7 +68,7 @@ def test_matches_oracle_at_reference_sizes(N, T_enc, T_dec, L, layers):
     asm = Assembler(synth.vocab_file('clevr'))
     V_nmn = len(asm.module_names)
     V_txt, E_txt, E_nmn = 90, 300, 300
-    w = random_weights(rng, V_txt, E_txt, V_nmn, E_nmn, L, layers)
+    w = init_seq2seq_weights(V_txt, E_txt, V_nmn, E_nmn, L, layers, seed=2000 + N)
     seq = rng.randint(0, V_txt, size=(T_enc, N)).astype(np.int32)
     lens = rng.randint(1, T_enc + 1, size=N).astype(np.int32)
     lens[0] = T_enc

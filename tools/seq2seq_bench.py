@@ -1,16 +1,16 @@
 """Device time of one seq2seq forward (CLEVR sizes) with CUDA events; prints questions/s."""
-import sys, time
+import sys
 import numpy as np, torch
 sys.path.insert(0, '.')
 from n2nmn_b200 import synth
 from n2nmn_b200.assembler import Assembler
 from n2nmn_b200.seq2seq import AttentionSeq2Seq
-from tests.test_gpu_seq2seq import random_weights
+from n2nmn_b200.weights import init_seq2seq_weights
 
 N, T_enc, T_dec, L, layers, V_txt, E = 64, 45, 20, 512, 2, 90, 300
 asm = Assembler(synth.vocab_file('clevr'))
 rng = np.random.RandomState(0)
-w = random_weights(rng, V_txt, E, asm.num_vocab_nmn, E, L, layers)
+w = init_seq2seq_weights(V_txt, E, asm.num_vocab_nmn, E, L, layers)
 s = AttentionSeq2Seq(None, None, T_dec, V_txt, E, asm.num_vocab_nmn, E, L, layers, asm,
                      T_encoder=T_enc, max_batch=N, weights=w, device='cuda:0')
 seq = torch.from_numpy(rng.randint(0, V_txt, size=(T_enc, N)).astype(np.int32)).cuda()
@@ -28,8 +28,3 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / R
 print('seq2seq forward N=%d T_enc=%d T_dec=%d L=%d: %.3f ms/batch, %.0f questions/s, %d launches/batch'
       % (N, T_enc, T_dec, L, ms, N / ms * 1e3, (s.launch_count() - n0) // R))
-if '--cpu' in sys.argv:
-    from oracle import seq2seq_oracle as so
-    t = time.time()
-    so.run(w, seq.cpu().numpy(), lens.cpu().numpy(), T_dec, layers, asm.P, asm.W, asm.b)
-    print('numpy oracle: %.1f ms/batch' % ((time.time() - t) * 1e3))
