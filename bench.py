@@ -784,14 +784,15 @@ def main():
         tlab = [np.random.RandomState(11 + i).randint(0, C, size=B) for i in range(P)]
         lsp = torch.full((B,), -2.0, device=dev)
         for i in range(5):
-            tr.train_step(bn.feats[i % P], twv[i % P], ttok[i % P], tlab[i % P], log_seq_prob=lsp)
+            tr.train_step(bn.feats[i % P], twv[i % P], ttok[i % P], tlab[i % P], log_seq_prob=lsp,
+                          sync=False)
         k_tr = max(50, min(args.steps, 200))
         bn.barrier()
         t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0e.record()
         for i in range(k_tr):
             out = tr.train_step(bn.feats[i % P], twv[i % P], ttok[i % P], tlab[i % P],
-                                log_seq_prob=lsp)
+                                log_seq_prob=lsp, sync=False)
         t1e.record()
         bn.barrier()
         tms = bn.allmax(t0e.elapsed_time(t1e))

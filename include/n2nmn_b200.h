@@ -292,6 +292,26 @@ int n2nmn_adam_step(n2nmn_ctx* ctx, float* wflat_dev, float* gflat_dev, float* m
                     int step, float lr, float beta1, float beta2, float eps, float max_norm,
                     float weight_decay, void* stream);
 
+/* The rest of the policy-search step after the (optional) all-reduce, with nothing read back by
+ * the host (exp_clevr/train_clevr_rl_gt_layout.py:119-139):
+ *   avg_sample_loss = loss_sum / (N*world); coeff_i = (loss_i - baseline) / (N*world) (the
+ *   stop_gradient factor of the policy-gradient loss, :123-124); pg = Σ coeff_i*log_seq_prob_i;
+ *   baseline EMA (:120-122); g = g/world + weight_decay*w; l2_reg; per-tensor clip; Adam; re-pack.
+ * loss_sum_dev: ONE float, Σ of the per-sample losses over all ranks (loss_dev[0] of
+ * n2nmn_train_backward, summed by the all-reduce); per_sample_dev [N] this rank's losses
+ * (loss_dev + 1); log_seq_prob_dev [N] or NULL; state_in/out_dev: 4 floats {baseline,
+ * avg_sample_loss, policy_gradient_loss, l2_reg} (only [0] of state_in is read; in and out may
+ * alias); coeff_dev [N] or NULL. */
+int n2nmn_train_finish(n2nmn_ctx* ctx, float* wflat_dev, float* gflat_dev, float* m_dev,
+                       float* v_dev, int step, float lr, float beta1, float beta2, float eps,
+                       float max_norm, float weight_decay, const float* loss_sum_dev,
+                       const float* per_sample_dev, const float* log_seq_prob_dev, int N, int world,
+                       float baseline_decay, const float* state_in_dev, float* state_out_dev,
+                       float* coeff_dev, void* stream);
+/* Factor applied to d_word_vecs by n2nmn_train_backward (the one gradient that is not
+ * all-reduced): 1/world_size in data-parallel training. Default 1. */
+int n2nmn_set_grad_scale(n2nmn_ctx* ctx, float scale);
+
 /* CTAs per question in the layout-executor kernel: 1, 2, 4 or 8 thread-block clusters; 0 (the
  * default) picks from the batch size so that one batch alone spreads over the SMs (lowest latency
  * of a single batch). Callers that keep several batches in flight on different streams get more

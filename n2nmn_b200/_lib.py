@@ -100,6 +100,10 @@ SIGNATURES = {
                                        C.c_float, _P, _P, _P, _P, _P, _P]),
     'n2nmn_adam_step': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_float, C.c_float, C.c_float,
                                   C.c_float, C.c_float, C.c_float, _P]),
+    'n2nmn_train_finish': (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_float, C.c_float, C.c_float,
+                                     C.c_float, C.c_float, C.c_float, _P, _P, _P, C.c_int, C.c_int,
+                                     C.c_float, _P, _P, _P, _P]),
+    'n2nmn_set_grad_scale': (C.c_int, [_P, C.c_float]),
     'n2nmn_set_tree_cluster': (C.c_int, [_P, C.c_int]),
     'n2nmn_set_proj_ctas': (C.c_int, [_P, C.c_int]),
     'n2nmn_set_text_ctas_per_group': (C.c_int, [_P, C.c_int]),

@@ -628,7 +628,7 @@ text_wgrad_kernel(DevModel md, const float* __restrict__ dtau, const int32_t* __
 __global__ void __launch_bounds__(256)
 text_xgrad_kernel(DevModel md, const float* __restrict__ dtau, const int32_t* __restrict__ text_t,
                   const int32_t* __restrict__ text_b, const int32_t* __restrict__ set_start,
-                  float* __restrict__ dword) {
+                  float* __restrict__ dword, float scale) {
   extern __shared__ float sdt[];
   const int r = blockIdx.x;
   int set = 0;
@@ -643,7 +643,7 @@ text_xgrad_kernel(DevModel md, const float* __restrict__ dtau, const int32_t* __
     float acc = 0.f;
     for (int ch = lane; ch < M; ch += 32) acc = fmaf(w[ch], sdt[ch], acc);
     acc = warp_sum(acc);
-    if (lane == 0) dst[k] = acc;
+    if (lane == 0) dst[k] = acc * scale;
   }
 }
 
@@ -838,19 +838,61 @@ feat_grad_mma_kernel(DevModel md, const float* __restrict__ dmap,
 // ---- optimiser ---------------------------------------------------------------------------------
 struct VarSeg { int offset, count, decay; };   // decay = 1 for ".../weights" variables
 
-// g += wd*w for weights variables, then Σ g² per variable.
+// g = g*gscale + wd*w for weights variables (gscale = 1/world after the all-reduce), then Σ g² per
+// variable; l2 (optional) += Σ tf.nn.l2_loss(w) over the weights variables (nmn3_model.py:163-166).
 __global__ void grad_norm_kernel(const float* __restrict__ w, float* __restrict__ g,
-                                 const VarSeg* __restrict__ segs, float weight_decay,
-                                 float* __restrict__ sumsq) {
+                                 const VarSeg* __restrict__ segs, float weight_decay, float gscale,
+                                 float* __restrict__ sumsq, float* __restrict__ l2) {
   const VarSeg s = segs[blockIdx.y];
-  float acc = 0.f;
+  float acc = 0.f, wsq = 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s.count; i += gridDim.x * blockDim.x) {
-    float gv = g[s.offset + i];
-    if (s.decay) { gv = fmaf(weight_decay, w[s.offset + i], gv); g[s.offset + i] = gv; }
+    float gv = g[s.offset + i] * gscale;
+    if (s.decay) {
+      const float wv = w[s.offset + i];
+      gv = fmaf(weight_decay, wv, gv);
+      wsq = fmaf(wv, wv, wsq);
+    }
+    if (s.decay || gscale != 1.f) g[s.offset + i] = gv;
     acc = fmaf(gv, gv, acc);
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0 && acc != 0.f) atomicAdd(sumsq + blockIdx.y, acc);
+  if (l2 != nullptr && s.decay) {
+    wsq = warp_sum(wsq);
+    if ((threadIdx.x & 31) == 0 && wsq != 0.f) atomicAdd(l2, 0.5f * wsq);
+  }
+}
+
+// The scalar part of the policy-search step (exp_clevr/train_clevr_rl_gt_layout.py:119-124) on
+// the device, one block: avg = Σ loss / (N·world); coeff_i = (loss_i - baseline) / (N·world) (the
+// stop_gradient factor of the policy-gradient loss); pg = Σ coeff_i·log_seq_prob_i; baseline EMA.
+// state_out = {new baseline, avg_sample_loss, policy_gradient_loss, l2_reg (zeroed here, summed by
+// grad_norm_kernel)}.
+__global__ void train_scalars_kernel(const float* __restrict__ loss_sum,
+                                     const float* __restrict__ per_sample,
+                                     const float* __restrict__ log_seq_prob, int N, int world,
+                                     float baseline_decay, const float* __restrict__ state_in,
+                                     float* __restrict__ state_out, float* __restrict__ coeff) {
+  __shared__ float red[32];
+  const float inv = 1.f / ((float)N * (float)world);
+  const float avg = loss_sum[0] * inv, base = state_in[0];
+  float pg = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float cf = (per_sample[i] - base) * inv;
+    if (coeff != nullptr) coeff[i] = cf;
+    if (log_seq_prob != nullptr) pg = fmaf(cf, log_seq_prob[i], pg);
+  }
+  pg = warp_sum(pg);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = pg;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    state_out[0] = base + (1.f - baseline_decay) * (avg - base);
+    state_out[1] = avg;
+    state_out[2] = t;
+    state_out[3] = 0.f;
+  }
 }
 
 // tf.clip_by_norm per tensor, then Adam (TF: lr_t = lr*sqrt(1-b2^t)/(1-b1^t)).

@@ -145,6 +145,10 @@ struct n2nmn_ctx {
   int dmap_entries = 0;
   VarSeg* d_segs = nullptr;
   float* d_sumsq = nullptr;
+  RepackSeg* d_repack = nullptr;           // fused re-pack tables (n2nmn_load_flat_weights)
+  ProjRepack proj_repack;
+  int proj_repack_sets = 0;
+  float dword_scale = 1.f;                 // n2nmn_set_grad_scale
   GradOffsets go;
   std::vector<int64_t> flat_offset;
   int64_t flat_size = 0;
@@ -1268,12 +1272,48 @@ int n2nmn_flat_offset(const n2nmn_ctx* c, int index, int64_t* offset, int64_t* c
 
 int n2nmn_load_flat_weights(n2nmn_ctx* c, const float* wflat_dev, void* stream) {
   if (!c || !wflat_dev) return fail(N2NMN_ERR_ARG, "null argument");
-  for (size_t i = 0; i < c->vars.size(); ++i) {
-    const Variable& v = c->vars[i];
-    if (int rc = n2nmn_set_weight(c, v.name.c_str(), wflat_dev + c->flat_offset[i], v.shape.data(),
-                                  (int)v.shape.size(), stream))
-      return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nv = (int)c->vars.size();
+  if (!c->d_repack) {   // what n2nmn_set_weight does per variable, as device tables
+    std::vector<RepackSeg> segs(nv);
+    ProjRepack& pr = c->proj_repack;
+    for (int s = 0; s < NUM_PROJ_SETS; ++s) { pr.w_off[s] = pr.b_off[s] = -1; pr.wt[s] = pr.bias[s] = nullptr; }
+    c->proj_repack_sets = 0;
+    for (int i = 0; i < nv; ++i) {
+      const Variable& v = c->vars[i];
+      segs[i].src_off = (int)c->flat_offset[i];
+      segs[i].count = (int)v.count;
+      segs[i].cols = (int)v.shape.back();
+      segs[i].kind = v.kind == VK_PITCHED ? 1 : 0;
+      segs[i].dst_off = (long long)v.offset;
+      if (v.kind == VK_PROJ_W) {
+        pr.w_off[v.set] = (int)c->flat_offset[i];
+        pr.wt[v.set] = c->proj_wt[v.set];
+        pr.bias[v.set] = c->proj_bias[v.set];
+        pr.set_of_z[c->proj_repack_sets++] = v.set;
+      } else if (v.kind == VK_PROJ_B) {
+        pr.b_off[v.set] = (int)c->flat_offset[i];
+      }
+    }
+    CUDA_TRY(cudaMalloc(&c->d_repack, nv * sizeof(RepackSeg)));
+    CUDA_TRY(cudaMemcpy(c->d_repack, segs.data(), nv * sizeof(RepackSeg), cudaMemcpyHostToDevice));
   }
+  repack_all_kernel<<<dim3(16, nv), 256, 0, st>>>(wflat_dev, c->d_repack, c->wbuf, c->Mp);
+  ++c->launches;
+  if (c->proj_repack_sets > 0) {
+    dim3 grid((c->Kp + 31) / 32, (c->Mp + 31) / 32, c->proj_repack_sets), block(32, 8);
+    proj_repack_kernel<<<grid, block, 0, st>>>(wflat_dev, c->proj_repack, c->Dk, c->cfg.map_dim,
+                                               c->Kp, c->Mp);
+    ++c->launches;
+  }
+  if (c->conv_quad) {
+    conv_quad_kernel<<<quad_pitch(c->cfg.kernel_size), 256, 0, st>>>(
+        c->md.conv_k, c->md.conv_b, c->md.elt_w[ES_TRANSFORM], c->cfg.kernel_size, c->cfg.map_dim,
+        c->Mp, c->conv_quad);
+    ++c->launches;
+  }
+  CUDA_TRY(cudaGetLastError());
+  for (Variable& v : c->vars) v.loaded = true;
   return 0;
 }
 
@@ -1363,7 +1403,7 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
     ++c->launches;
     if (dword_dev) {
       text_xgrad_kernel<<<rows, 256, c->Mp * sizeof(float), st>>>(c->md, c->dtau, d_tt, d_tb, d_ss,
-                                                                 dword_dev);
+                                                                 dword_dev, c->dword_scale);
       ++c->launches;
     }
   }
@@ -1388,11 +1428,10 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
   return 0;
 }
 
-int n2nmn_adam_step(n2nmn_ctx* c, float* wflat, float* gflat, float* m, float* v, int step,
-                    float lr, float beta1, float beta2, float eps, float max_norm,
-                    float weight_decay, void* stream) {
-  if (!c || !wflat || !gflat || !m || !v || step < 1) return fail(N2NMN_ERR_ARG, "bad argument");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+namespace {
+int adam_impl(n2nmn_ctx* c, float* wflat, float* gflat, float* m, float* v, int step, float lr,
+              float beta1, float beta2, float eps, float max_norm, float weight_decay, float gscale,
+              float* l2_dev, cudaStream_t st) {
   const int nv = (int)c->vars.size();
   if (!c->d_segs) {
     std::vector<VarSeg> segs(nv);
@@ -1408,14 +1447,47 @@ int n2nmn_adam_step(n2nmn_ctx* c, float* wflat, float* gflat, float* m, float* v
   }
   CUDA_TRY(cudaMemsetAsync(c->d_sumsq, 0, nv * sizeof(float), st));
   dim3 grid(32, nv);
-  grad_norm_kernel<<<grid, 256, 0, st>>>(wflat, gflat, c->d_segs, weight_decay, c->d_sumsq);
+  grad_norm_kernel<<<grid, 256, 0, st>>>(wflat, gflat, c->d_segs, weight_decay, gscale, c->d_sumsq,
+                                         l2_dev);
   const double lr_t = (double)lr * std::sqrt(1.0 - std::pow((double)beta2, step)) /
                       (1.0 - std::pow((double)beta1, step));
   adam_clip_kernel<<<grid, 256, 0, st>>>(wflat, gflat, m, v, c->d_segs, c->d_sumsq, (float)lr_t,
                                          beta1, beta2, eps, max_norm);
   c->launches += 2;
   CUDA_TRY(cudaGetLastError());
-  return n2nmn_load_flat_weights(c, wflat, stream);
+  return n2nmn_load_flat_weights(c, wflat, st);
+}
+}  // namespace
+
+int n2nmn_adam_step(n2nmn_ctx* c, float* wflat, float* gflat, float* m, float* v, int step,
+                    float lr, float beta1, float beta2, float eps, float max_norm,
+                    float weight_decay, void* stream) {
+  if (!c || !wflat || !gflat || !m || !v || step < 1) return fail(N2NMN_ERR_ARG, "bad argument");
+  return adam_impl(c, wflat, gflat, m, v, step, lr, beta1, beta2, eps, max_norm, weight_decay, 1.f,
+                   nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int n2nmn_train_finish(n2nmn_ctx* c, float* wflat, float* gflat, float* m, float* v, int step,
+                       float lr, float beta1, float beta2, float eps, float max_norm,
+                       float weight_decay, const float* loss_sum_dev, const float* per_sample_dev,
+                       const float* log_seq_prob_dev, int N, int world, float baseline_decay,
+                       const float* state_in_dev, float* state_out_dev, float* coeff_dev,
+                       void* stream) {
+  if (!c || !wflat || !gflat || !m || !v || step < 1 || !loss_sum_dev || !per_sample_dev ||
+      !state_in_dev || !state_out_dev || N <= 0 || world <= 0)
+    return fail(N2NMN_ERR_ARG, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  train_scalars_kernel<<<1, 256, 0, st>>>(loss_sum_dev, per_sample_dev, log_seq_prob_dev, N, world,
+                                          baseline_decay, state_in_dev, state_out_dev, coeff_dev);
+  ++c->launches;
+  return adam_impl(c, wflat, gflat, m, v, step, lr, beta1, beta2, eps, max_norm, weight_decay,
+                   1.f / (float)world, state_out_dev + 3, st);
+}
+
+int n2nmn_set_grad_scale(n2nmn_ctx* c, float scale) {
+  if (!c) return fail(N2NMN_ERR_ARG, "null context");
+  c->dword_scale = scale;
+  return 0;
 }
 
 #if defined(N2NMN_EXP_TIMELINE)

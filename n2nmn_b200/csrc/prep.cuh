@@ -37,6 +37,57 @@ __global__ void pitch_rows_kernel(const float* __restrict__ src, int rows, int M
     dst[(size_t)r * Mp + c] = (c < M) ? src[(size_t)r * M + c] : 0.f;
 }
 
+// ---- all variables from one flat buffer in two launches (after every optimiser step) ------------
+// kind 0: plain copy of `count` floats; kind 1: [rows][cols] -> [rows][pitch] zero padded.
+struct RepackSeg { int src_off, count, cols, kind; long long dst_off; };
+// grid = (16, variables)
+__global__ void repack_all_kernel(const float* __restrict__ wflat, const RepackSeg* __restrict__ segs,
+                                  float* __restrict__ wbuf, int pitch) {
+  const RepackSeg s = segs[blockIdx.y];
+  const float* src = wflat + s.src_off;
+  float* dst = wbuf + s.dst_off;
+  if (s.kind == 0) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s.count; i += gridDim.x * blockDim.x)
+      dst[i] = src[i];
+  } else {
+    const int rows = s.count / s.cols, n = rows * pitch;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const int r = i / pitch, cidx = i - r * pitch;
+      dst[i] = cidx < s.cols ? src[(size_t)r * s.cols + cidx] : 0.f;
+    }
+  }
+}
+// The K-major padded copies of the conv_image / fc_att weights (tcgen05 B operand) and their padded
+// biases, every projection set in one launch: grid = (Kp/32, Mp/32, sets), block (32, 8).
+struct ProjRepack {
+  int w_off[NUM_PROJ_SETS], b_off[NUM_PROJ_SETS];   // offsets in the flat buffer (-1: set not owned)
+  float* wt[NUM_PROJ_SETS];
+  float* bias[NUM_PROJ_SETS];
+  int set_of_z[NUM_PROJ_SETS];
+};
+__global__ void proj_repack_kernel(const float* __restrict__ wflat, ProjRepack pr, int K, int M,
+                                   int Kp, int Mp) {
+  __shared__ float tile[32][33];
+  const int set = pr.set_of_z[blockIdx.z];
+  const float* W = wflat + pr.w_off[set];
+  float* Wt = pr.wt[set];
+  const int k0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, m = m0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < K && m < M) ? W[(size_t)k * M + m] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int m = m0 + i, k = k0 + threadIdx.x;
+    if (m < Mp && k < Kp) Wt[(size_t)m * Kp + k] = tile[threadIdx.x][i];
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && pr.b_off[set] >= 0) {
+    const float* b = wflat + pr.b_off[set];
+    for (int i = threadIdx.y * 32 + threadIdx.x; i < Mp; i += 32 * blockDim.y)
+      pr.bias[set][i] = i < M ? b[i] : 0.f;
+  }
+}
+
 // conv_quad^T [Mp][quad_pitch] (common.cuh: Transform as a quadratic form), the B operand of
 // quad_kernel (text_proj.cuh): column o < n: K̃_o ∘ w2; columns [n, quad_u_pitch): zero; then one
 // column per pair i <= j: (2-δ_ij) K̃_i ∘ K̃_j, with K̃ = [conv_maps taps (row pitch Mp) ;

@@ -1,21 +1,30 @@
-#!/usr/bin/env python
-"""Six train steps on one CLEVR batch (profiling target of tools/gpu_train_prof.sh)."""
-import sys, numpy as np, torch
-import os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+"""Runs a few policy-search train steps (CLEVR B=64, T=10) for the profiler / a timing print."""
+import sys
+import numpy as np, torch
+sys.path.insert(0, '.')
 from n2nmn_b200 import synth, weights as wts
 from n2nmn_b200.assembler import Assembler
 from n2nmn_b200.executor import LayoutExecutor
 from n2nmn_b200.trainer import ModuleNetTrainer
-B, H, W, D, T, C = 64, 10, 15, 512, 10, 28
+
+B, T, C = 64, 10, 28
 asm = Assembler(synth.vocab_file('clevr'))
-weights = wts.init_weights('clevr', H, W, D, C, seed=0, bias_std=0.1)
-f, w = synth.make_inputs(B, H, W, D, T, seed=1)
-f, w = torch.from_numpy(f).cuda(), torch.from_numpy(w).cuda()
-ex = LayoutExecutor('clevr', f, w, C, asm, weights=weights, max_batch=B, max_T=T)
+feat, wv = synth.make_inputs(B, 10, 15, 512, T, seed=1)
+W = wts.init_weights('clevr', 10, 15, 512, C, seed=0, bias_std=0.1)
+ex = LayoutExecutor('clevr', torch.from_numpy(feat).cuda(), torch.from_numpy(wv).cuda(), C, asm,
+                    weights=W, max_batch=B, max_T=T)
 tr = ModuleNetTrainer(ex)
 tok = synth.expert_mix_tokens(asm, B, T)
-lab = np.random.RandomState(0).randint(0, C, size=B)
-for i in range(6):
-    tr.train_step(f, w, tok, lab)
+lab = np.random.RandomState(3).randint(0, C, size=B)
+lsp = torch.full((B,), -2.0, device='cuda')
+f, w = torch.from_numpy(feat).cuda(), torch.from_numpy(wv).cuda()
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+for _ in range(5):
+    tr.train_step(f, w, tok, lab, log_seq_prob=lsp, sync=False)
 torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(n):
+    tr.train_step(f, w, tok, lab, log_seq_prob=lsp, sync=False)
+e1.record(); torch.cuda.synchronize()
+print('train step: %.3f ms' % (e0.elapsed_time(e1) / n))
