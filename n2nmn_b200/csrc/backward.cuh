@@ -835,6 +835,245 @@ feat_grad_mma_kernel(DevModel md, const float* __restrict__ dmap,
   flush(cur_set);
 }
 
+// ---- C[k][c] += Σ_p X[p][k]·B[p][c]: the weight-gradient contraction of every "X·W + b" layer ----
+// (feature-side layers: p = the pixels of one B map, X = that image's feature grid; text layers:
+// p = the text rows of one weight set, X = the gathered word vectors). Default path; the CUDA-core
+// kernels above stay as the exact-fp32 verification path (N2NMN_FLAG_PROJ_FP32_SIMT).
+//   CTA tile 128 (k) x 64 (c), 8 warps of 32 x 32 on mma.sync m16n8k8 TF32 (fp32 accumulate), the
+//   contraction index streamed 32 rows at a time through a 4-stage cp.async ring: both operands
+//   are stored exactly as they lie in memory ([p][k] and [p][c], padded pitches 136 / 72 make the
+//   transposed fragment reads conflict-free), so no register staging and no transposition pass.
+//   Operands are rounded to TF32 at fragment-load time by adding half an ulp (the tensor core
+//   ignores the low 13 bits): one integer add per element where cvt.rna is an instruction sequence.
+//   Round 1's kernel staged 64 x 64 tiles through registers with two barriers per 32 rows and 16
+//   MMAs per warp between them: 178 us for 3.6 GFLOP (2.4 % of the TF32 peak).
+// Segments [blockIdx.z * segs_per_cta, ...) are walked by one CTA and flushed with atomics when the
+// weight set changes; CTAs with blockIdx.x == 0 also sum the columns of B (the bias gradient).
+constexpr int kXtbM = 128, kXtbN = 64, kXtbP = 32, kXtbStages = 4, kXtbThreads = 256;
+constexpr int kXtbXPitch = kXtbM + 8, kXtbBPitch = kXtbN + 8;
+constexpr int kXtbStageFloats = kXtbP * (kXtbXPitch + kXtbBPitch);
+constexpr size_t kXtbSmemBytes = (size_t)kXtbStages * kXtbStageFloats * sizeof(float);
+
+__device__ __forceinline__ uint32_t tf32_round_bits(float x) { return __float_as_uint(x) + 0x1000u; }
+
+struct FeatGradSrc {   // segment = one B map (entry)
+  DevModel md; const float* dmap; const BwdEntry* entries; int n; float* gflat; GradOffsets go;
+  __device__ int num_segs() const { return n; }
+  __device__ int rows(int) const { return md.HW; }
+  __device__ int set(int sg) const { return entries[sg].set; }
+  __device__ const float* x_row(int sg, int p) const {
+    return md.feat + ((size_t)entries[sg].b * md.HW + p) * md.feat_pitch;
+  }
+  __device__ const float* b_row(int sg, int p) const { return dmap + ((size_t)sg * md.HW + p) * md.Mp; }
+  __device__ int kdim() const { return md.Dk; }
+  __device__ float* w_out(int st) const { return gflat + go.proj_w[st]; }
+  __device__ float* b_out(int st) const { return gflat + go.proj_b[st]; }
+};
+struct TextGradSrc {   // segment = one text weight set
+  DevModel md; const float* dtau; const int32_t* text_t; const int32_t* text_b;
+  const int32_t* set_start; float* gflat; GradOffsets go;
+  __device__ int num_segs() const { return NUM_TEXT_SETS; }
+  __device__ int rows(int sg) const { return set_start[sg + 1] - set_start[sg]; }
+  __device__ int set(int sg) const { return sg; }
+  __device__ const float* x_row(int sg, int p) const {
+    const int r = set_start[sg] + p;
+    return word_vec_row(md, text_t[r], text_b[r]);
+  }
+  __device__ const float* b_row(int sg, int p) const { return dtau + (size_t)(set_start[sg] + p) * md.Mp; }
+  __device__ int kdim() const { return md.Dt; }
+  __device__ float* w_out(int st) const { return gflat + go.txt_w[st]; }
+  __device__ float* b_out(int st) const { return gflat + go.txt_b[st]; }
+};
+
+template <class Src>
+__global__ void __launch_bounds__(kXtbThreads) xtb_mma_kernel(const Src src, int segs_per_cta) {
+  extern __shared__ __align__(16) float xsm[];
+  const int k0 = blockIdx.x * kXtbM, c0 = blockIdx.y * kXtbN;
+  const int s0 = blockIdx.z * segs_per_cta, s1 = min(src.num_segs(), s0 + segs_per_cta);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3, wm = warp & 3, wn = warp >> 2;
+  const int Kd = src.kdim(), M = src.md.M, Mp = src.md.Mp;
+  const bool bias_cta = blockIdx.x == 0;
+  struct It { int seg, p0; };
+  auto settle = [&](It& it) { while (it.seg < s1 && it.p0 >= src.rows(it.seg)) { ++it.seg; it.p0 = 0; } };
+  auto load = [&](const It& it, int stage) {
+    float* xs = xsm + stage * kXtbStageFloats;
+    float* bs = xs + kXtbP * kXtbXPitch;
+    const int rows = src.rows(it.seg);
+    for (int i = tid; i < kXtbP * (kXtbM / 4); i += kXtbThreads) {
+      const int r = i >> 5, q = i & 31, p = it.p0 + r, k = k0 + 4 * q;
+      float* dst = xs + r * kXtbXPitch + 4 * q;
+      if (p < rows && k < Kd) tp_cp16(dst, src.x_row(it.seg, p) + k);
+      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int i = tid; i < kXtbP * (kXtbN / 4); i += kXtbThreads) {
+      const int r = i >> 4, q = i & 15, p = it.p0 + r, cc = c0 + 4 * q;
+      float* dst = bs + r * kXtbBPitch + 4 * q;
+      if (p < rows && cc < Mp) tp_cp16(dst, src.b_row(it.seg, p) + cc);
+      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  float acc[2][4][4], bsum = 0.f;
+  auto zero = [&] {
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[mi][ni][i] = 0.f;
+    bsum = 0.f;
+  };
+  auto flush = [&](int st) {
+    float* W = src.w_out(st);
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int k = k0 + wm * 32 + mi * 16 + g + ((i & 2) ? 8 : 0);
+          const int ch = c0 + wn * 32 + ni * 8 + 2 * t + (i & 1);
+          const float v = acc[mi][ni][i];
+          if (k < Kd && ch < M && v != 0.f) atomicAdd(W + (size_t)k * M + ch, v);
+        }
+    const int ch = c0 + (tid & (kXtbN - 1));
+    if (bias_cta && ch < M && bsum != 0.f) atomicAdd(src.b_out(st) + ch, bsum);
+  };
+  It ld{s0, 0}, cp{s0, 0};
+  settle(ld); settle(cp);
+  for (int s = 0; s < kXtbStages - 1; ++s) {
+    if (ld.seg < s1) { load(ld, s); ld.p0 += kXtbP; settle(ld); }
+    tp_commit();
+  }
+  int cur_set = -1, step = 0;
+  zero();
+  while (cp.seg < s1) {
+    const int st = src.set(cp.seg);
+    if (st != cur_set) {
+      if (cur_set >= 0) flush(cur_set);
+      zero();
+      cur_set = st;
+    }
+    tp_wait<kXtbStages - 2>();
+    __syncthreads();
+    if (ld.seg < s1) { load(ld, (step + kXtbStages - 1) % kXtbStages); ld.p0 += kXtbP; settle(ld); }
+    tp_commit();
+    const float* xs = xsm + (step % kXtbStages) * kXtbStageFloats;
+    const float* bs = xs + kXtbP * kXtbXPitch;
+#pragma unroll
+    for (int ks = 0; ks < kXtbP / 8; ++ks) {
+      uint32_t a[2][4], b[4][2];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const float* xa = xs + (8 * ks + t) * kXtbXPitch + wm * 32 + mi * 16 + g;
+        a[mi][0] = tf32_round_bits(xa[0]);
+        a[mi][1] = tf32_round_bits(xa[8]);
+        a[mi][2] = tf32_round_bits(xa[4 * kXtbXPitch]);
+        a[mi][3] = tf32_round_bits(xa[4 * kXtbXPitch + 8]);
+      }
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const float* ba = bs + (8 * ks + t) * kXtbBPitch + wn * 32 + ni * 8 + g;
+        b[ni][0] = tf32_round_bits(ba[0]);
+        b[ni][1] = tf32_round_bits(ba[4 * kXtbBPitch]);
+      }
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+          asm volatile(
+              "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+              "{%8,%9}, {%0,%1,%2,%3};"
+              : "+f"(acc[mi][ni][0]), "+f"(acc[mi][ni][1]), "+f"(acc[mi][ni][2]), "+f"(acc[mi][ni][3])
+              : "r"(a[mi][0]), "r"(a[mi][1]), "r"(a[mi][2]), "r"(a[mi][3]), "r"(b[ni][0]), "r"(b[ni][1]));
+    }
+    if (bias_cta) {   // column sums of B from the unrounded values: 4 row groups of 8 per column
+      const float* bc = bs + (tid >> 6) * 8 * kXtbBPitch + (tid & (kXtbN - 1));
+#pragma unroll
+      for (int r = 0; r < 8; ++r) bsum += bc[r * kXtbBPitch];
+    }
+    cp.p0 += kXtbP; settle(cp);
+    ++step;
+  }
+  if (cur_set >= 0) flush(cur_set);
+}
+
+// d(word_vecs)[t, b, :] = scale · dtau[row, :] · W_set^T on the same fragments: A = 64 text rows of
+// one weight set (groups as in text_proj_kernel), B = 64 rows k of W_set [Dt][Mp], both K-major
+// (channel contiguous) exactly as stored. grid = (ceil(Dt/64), groups).
+constexpr int kXgThreads = 256, kXgKC = 256;
+constexpr int kXgPitch = kXgKC + 4;
+constexpr size_t kXgSmemBytes = (size_t)2 * 64 * kXgPitch * sizeof(float);
+__global__ void __launch_bounds__(kXgThreads)
+text_xgrad_mma_kernel(DevModel md, const float* __restrict__ dtau, const int32_t* __restrict__ text_t,
+                      const int32_t* __restrict__ text_b, TextSetRows rows, float* __restrict__ dword,
+                      float scale) {
+  extern __shared__ __align__(16) float gsm[];
+  float* As = gsm;                    // [64 rows][kXgPitch]
+  float* Ws = gsm + 64 * kXgPitch;    // [64 k][kXgPitch]
+  int set = 0, gi = blockIdx.y, r0, cnt;
+  for (; set < NUM_TEXT_SETS; ++set) {
+    const int ng = (rows.start[set + 1] - rows.start[set] + 63) / 64;
+    if (gi < ng) break;
+    gi -= ng;
+  }
+  r0 = rows.start[set] + gi * 64;
+  cnt = min(64, rows.start[set + 1] - r0);
+  const int k0 = blockIdx.x * 64, Dt = md.Dt, Mp = md.Mp;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3, wm = warp & 3, wn = warp >> 2;
+  float acc[4][4];
+#pragma unroll
+  for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[ni][i] = 0.f;
+  const float* W = md.txt_w[set];
+  for (int cb = 0; cb < Mp; cb += kXgKC) {
+    const int kc = min(kXgKC, Mp - cb), q4 = kc >> 2;
+    __syncthreads();
+    for (int i = tid; i < 64 * q4; i += kXgThreads) {
+      const int r = i / q4, q = i - r * q4;
+      float* da = As + r * kXgPitch + 4 * q;
+      float* dw = Ws + r * kXgPitch + 4 * q;
+      if (r < cnt) tp_cp16(da, dtau + (size_t)(r0 + r) * Mp + cb + 4 * q);
+      else *reinterpret_cast<float4*>(da) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + r < Dt) tp_cp16(dw, W + (size_t)(k0 + r) * Mp + cb + 4 * q);
+      else *reinterpret_cast<float4*>(dw) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    tp_commit();
+    tp_wait<0>();
+    __syncthreads();
+    for (int ks = 0; ks < kc / 8; ++ks) {
+      const float* aa = As + (wm * 16 + g) * kXgPitch + 8 * ks + t;
+      uint32_t a[4] = {tf32_round_bits(aa[0]), tf32_round_bits(aa[8 * kXgPitch]),
+                       tf32_round_bits(aa[4]), tf32_round_bits(aa[8 * kXgPitch + 4])};
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const float* wa = Ws + (wn * 32 + ni * 8 + g) * kXgPitch + 8 * ks + t;
+        const uint32_t b0 = tf32_round_bits(wa[0]), b1 = tf32_round_bits(wa[4]);
+        asm volatile(
+            "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+            "{%8,%9}, {%0,%1,%2,%3};"
+            : "+f"(acc[ni][0]), "+f"(acc[ni][1]), "+f"(acc[ni][2]), "+f"(acc[ni][3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+      }
+    }
+  }
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int r = wm * 16 + g + 8 * hh;
+    if (r >= cnt) continue;
+    float* dst = dword + ((size_t)text_t[r0 + r] * md.N + text_b[r0 + r]) * Dt;
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int k = k0 + wn * 32 + ni * 8 + 2 * t + j;
+        if (k < Dt) dst[k] = acc[ni][hh * 2 + j] * scale;
+      }
+  }
+}
+
 // ---- optimiser ---------------------------------------------------------------------------------
 struct VarSeg { int offset, count, decay; };   // decay = 1 for ".../weights" variables
 

@@ -1347,6 +1347,12 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
                                   (int)(L.total * sizeof(float))));
     CUDA_TRY(cudaFuncSetAttribute(tree_bwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(L.total * sizeof(float))));
+    CUDA_TRY(cudaFuncSetAttribute(xtb_mma_kernel<FeatGradSrc>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kXtbSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(xtb_mma_kernel<TextGradSrc>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kXtbSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(text_xgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kXgSmemBytes));
   }
   n2nmn_sched* sc = &c->step_sched;
   sc->uid = g_uid++;
@@ -1398,30 +1404,53 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
     const int32_t* d_tt = reinterpret_cast<const int32_t*>(d + o.text_t);
     const int32_t* d_tb = reinterpret_cast<const int32_t*>(d + o.text_b);
     const int32_t* d_ss = reinterpret_cast<const int32_t*>(d + o.text_set_start);
-    dim3 g1((c->cfg.text_dim + 7) / 8, NUM_TEXT_SETS);
-    text_wgrad_kernel<<<g1, 256, 0, st>>>(c->md, c->dtau, d_tt, d_tb, d_ss, gflat_dev, c->go);
+    const bool exact = (c->cfg.flags & N2NMN_FLAG_PROJ_FP32_SIMT) != 0;
+    if (exact) {
+      dim3 g1((c->cfg.text_dim + 7) / 8, NUM_TEXT_SETS);
+      text_wgrad_kernel<<<g1, 256, 0, st>>>(c->md, c->dtau, d_tt, d_tb, d_ss, gflat_dev, c->go);
+    } else {
+      TextGradSrc ts{c->md, c->dtau, d_tt, d_tb, d_ss, gflat_dev, c->go};
+      dim3 g1((c->cfg.text_dim + kXtbM - 1) / kXtbM, (c->cfg.map_dim + kXtbN - 1) / kXtbN,
+              NUM_TEXT_SETS);
+      xtb_mma_kernel<TextGradSrc><<<g1, kXtbThreads, kXtbSmemBytes, st>>>(ts, 1);
+    }
     ++c->launches;
     if (dword_dev) {
-      text_xgrad_kernel<<<rows, 256, c->Mp * sizeof(float), st>>>(c->md, c->dtau, d_tt, d_tb, d_ss,
-                                                                 dword_dev, c->dword_scale);
+      if (exact) {
+        text_xgrad_kernel<<<rows, 256, c->Mp * sizeof(float), st>>>(c->md, c->dtau, d_tt, d_tb, d_ss,
+                                                                   dword_dev, c->dword_scale);
+      } else {
+        TextSetRows tsr;
+        int groups = 0;
+        for (int i = 0; i <= NUM_TEXT_SETS; ++i) tsr.start[i] = S.text_set_start[i];
+        for (int i = 0; i < NUM_TEXT_SETS; ++i) groups += (tsr.start[i + 1] - tsr.start[i] + 63) / 64;
+        dim3 g3((c->cfg.text_dim + 63) / 64, groups);
+        text_xgrad_mma_kernel<<<g3, kXgThreads, kXgSmemBytes, st>>>(c->md, c->dtau, d_tt, d_tb, tsr,
+                                                                    dword_dev, c->dword_scale);
+      }
       ++c->launches;
     }
   }
   // ---- feature-side layers: dW_set = Σ X^T·B
   const int ne = (int)S.entries.size();
   if (ne > 0) {
-    const int chunks = std::min(ne, 16);
-    const int per = (ne + chunks - 1) / chunks;
-    dim3 g2((c->Dk + kFgTile - 1) / kFgTile, (c->cfg.map_dim + kFgTile - 1) / kFgTile,
-            (ne + per - 1) / per);
-    if (c->cfg.flags & N2NMN_FLAG_PROJ_FP32_SIMT)
-      feat_grad_kernel<<<g2, 256, 0, st>>>(c->md, c->dmap,
-                                         reinterpret_cast<const BwdEntry*>(d + o.entries), ne, per,
-                                         gflat_dev, c->go);
-    else
-      feat_grad_mma_kernel<<<g2, 256, 0, st>>>(c->md, c->dmap,
-                                         reinterpret_cast<const BwdEntry*>(d + o.entries), ne, per,
-                                         gflat_dev, c->go);
+    const BwdEntry* d_ent = reinterpret_cast<const BwdEntry*>(d + o.entries);
+    if (c->cfg.flags & N2NMN_FLAG_PROJ_FP32_SIMT) {
+      const int chunks = std::min(ne, 16);
+      const int per = (ne + chunks - 1) / chunks;
+      dim3 g2((c->Dk + kFgTile - 1) / kFgTile, (c->cfg.map_dim + kFgTile - 1) / kFgTile,
+              (ne + per - 1) / per);
+      feat_grad_kernel<<<g2, 256, 0, st>>>(c->md, c->dmap, d_ent, ne, per, gflat_dev, c->go);
+    } else {
+      // two CTAs per SM (106 KB of ring each): ~296 CTAs over (Dk/128) x (M/64) tiles
+      const int tiles = ((c->Dk + kXtbM - 1) / kXtbM) * ((c->cfg.map_dim + kXtbN - 1) / kXtbN);
+      const int chunks = std::max(1, std::min(ne, (2 * 148 + tiles - 1) / tiles));
+      const int per = (ne + chunks - 1) / chunks;
+      FeatGradSrc fs{c->md, c->dmap, d_ent, ne, gflat_dev, c->go};
+      dim3 g2((c->Dk + kXtbM - 1) / kXtbM, (c->cfg.map_dim + kXtbN - 1) / kXtbN,
+              (ne + per - 1) / per);
+      xtb_mma_kernel<FeatGradSrc><<<g2, kXtbThreads, kXtbSmemBytes, st>>>(fs, per);
+    }
     ++c->launches;
   }
   CUDA_TRY(cudaGetLastError());
