@@ -44,9 +44,9 @@ struct BwdCtx {
   float* gflat;           // flat gradient buffer (zero-initialised)
   float* dtau;            // [text rows][Mp]
   float* dmap;            // [entries][HW][Mp]
-  float* dstencil;        // [NQ][HW][Mp] scratch: d(conv_maps output) of the Transform being walked
+  float* dstencil;        // [nodes][HW][Mp] scratch: d(conv_maps output) of a Transform node
+  float* gmap;            // [nodes][HWp] d loss / d(attention map of the node), zero-initialised
   GradOffsets go;
-  int max_nodes_q;        // capacity of the per-question gradient stack in shared memory
 };
 
 // ---- loss ------------------------------------------------------------------------------------
@@ -125,12 +125,11 @@ __device__ __forceinline__ void head_backward(const float* z, int L, const float
 struct BwdSmem {
   int HWp, g, pad, k, vec, z, total;
 };
-__host__ __device__ inline BwdSmem bwd_smem_layout(int H, int W, int Mp, int ksize, int C,
-                                                   int max_nodes_q) {
+__host__ __device__ inline BwdSmem bwd_smem_layout(int H, int W, int Mp, int ksize, int C) {
   BwdSmem s;
   const int HW = H * W;
   s.HWp = (HW + 3) & ~3;
-  s.g = max_nodes_q * s.HWp;
+  s.g = 0;
   s.pad = ((H + ksize - 1) * (W + ksize - 1) + 3) & ~3;
   s.k = 2 * ksize * ksize * Mp;          // filter bank + its gradient
   s.vec = 10 * Mp;
@@ -139,17 +138,23 @@ __host__ __device__ inline BwdSmem bwd_smem_layout(int H, int W, int Mp, int ksi
   return s;
 }
 
-// One CTA per question, nodes in reverse order.
+constexpr int kBwdSlices = 6;   // CTAs per splittable node (25 of the 150 CLEVR pixels each)
+
+// One CTA per NODE, one launch per depth level from the roots down (bwd_nodes lists the nodes by
+// depth): the gradient maps travel between the levels through c.gmap (a node's map feeds exactly
+// one parent, so its gradient row has one writer, and that writer ran in an earlier launch).
+// Round 1 walked a question's nodes inside one CTA: 64 CTAs on 148 SMs and the longest question
+// (~10 dependent modules, each bound by its own reductions) set the time: 360 us.
 template <int KS>
 __global__ void __launch_bounds__(kNodeThreads)
 tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
-                const int32_t* __restrict__ q_ptr, const int32_t* __restrict__ node_entry) {
+                const int32_t* __restrict__ bwd_nodes, int first,
+                const int32_t* __restrict__ node_entry) {
   extern __shared__ __align__(16) float bsm[];
   const DevModel& md = c.md;
   const int HW = md.HW, Mp = md.Mp, M = md.M, C = md.C, Hh = md.H, Ww = md.W;
-  const BwdSmem L = bwd_smem_layout(Hh, Ww, Mp, md.ksize, C, c.max_nodes_q);
-  float* gst = bsm;                       // [nodes of the question][HWp] gradient maps
-  float* a0 = gst + L.g;                  // forward inputs / scratch maps
+  const BwdSmem L = bwd_smem_layout(Hh, Ww, Mp, md.ksize, C);
+  float* a0 = bsm;                        // forward inputs / scratch maps
   float* a1 = a0 + L.HWp;
   float* da = a1 + L.HWp;
   float* db_ = da + L.HWp;
@@ -160,22 +165,24 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
   float* v = dks + KS * KS * Mp;          // 10 vectors of Mp
   float* zb = v + 10 * Mp;                // z, dz, g(C)
   float* red = zb + L.z;
-  const int q = blockIdx.x;
-  const int beg = q_ptr[q], end = q_ptr[q + 1];
-  if (beg == end) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int zlen = (2 * (HW + 2) + 3) & ~3;
   float* z = zb;
   float* dz = zb + zlen;
   float* gsc = dz + zlen;
-  for (int i = threadIdx.x; i < (end - beg) * L.HWp; i += blockDim.x) gst[i] = 0.f;
-  __syncthreads();
-
-  for (int i = end - 1; i >= beg; --i) {
+  {
+    const int i = bwd_nodes[first + blockIdx.x];
     const NodeRec nd = nodes[i];
-    float* g = gst + (i - beg) * L.HWp;                       // d loss / d this node's map
-    float* gin0 = (nd.in0 >= 0) ? gst + (nd.in0 - beg) * L.HWp : nullptr;
-    float* gin1 = (nd.in1 >= 0) ? gst + (nd.in1 - beg) * L.HWp : nullptr;
+    // gridDim.y CTAs share the pixels of a node whose per-pixel work is independent (Find, Filter,
+    // Transform: what they accumulate over pixels goes out through atomics); the others run in
+    // slice 0 alone
+    const bool split = (nd.op == OP_FIND || nd.op == OP_FILTER || nd.op == OP_TRANSFORM);
+    const int slice = blockIdx.y, ns = split ? (int)gridDim.y : 1;
+    if (slice >= ns) return;
+    const int p_lo = (HW * slice) / ns, p_hi = (HW * (slice + 1)) / ns;
+    float* g = c.gmap + (size_t)i * L.HWp;                    // d loss / d this node's map
+    float* gin0 = (nd.in0 >= 0) ? c.gmap + (size_t)nd.in0 * L.HWp : nullptr;
+    float* gin1 = (nd.in1 >= 0) ? c.gmap + (size_t)nd.in1 * L.HWp : nullptr;
     const float* fin0 = (nd.in0 >= 0) ? c.arena + (size_t)nd.in0 * HW : nullptr;
     const float* fin1 = (nd.in1 >= 0) ? c.arena + (size_t)nd.in1 * HW : nullptr;
     const float* fout = c.arena + (size_t)i * HW;             // this node's forward map
@@ -326,7 +333,7 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
           // out = min(a, find): gradient to `a` where out == a (ties included), else to find
           for (int p = threadIdx.x; p < HW; p += blockDim.x) {
             const bool to_a = (fout[p] == fin0[p]);
-            if (to_a) { gin0[p] += g[p]; gm[p] = 0.f; } else { gm[p] = g[p]; }
+            if (to_a) { if (slice == 0) gin0[p] += g[p]; gm[p] = 0.f; } else { gm[p] = g[p]; }
           }
         } else {
           for (int p = threadIdx.x; p < HW; p += blockDim.x) gm[p] = g[p];
@@ -367,7 +374,7 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
         float dcoef_r[kCh], dw2_r[kCh];
 #pragma unroll
         for (int k = 0; k < kCh; ++k) { dcoef_r[k] = 0.f; dw2_r[k] = 0.f; }
-        for (int p = warp; p < HW; p += nwarps) {
+        for (int p = p_lo + warp; p < p_hi; p += nwarps) {
           const float gp = gm[p];
           const float* mrow = mimg + (size_t)p * Mp;
           float mv[kCh];
@@ -417,7 +424,8 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
         float* dtau = c.dtau + (size_t)nd.text * Mp;
         for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
           if (ch < M) atomicAdd(c.gflat + c.go.elt_w[es] + ch, dw2[ch]);
-          dtau[ch] = (ch < M) ? (fsp ? dcoef[ch] * phi[ch] : dcoef[ch]) : 0.f;
+          if (ns > 1) { if (ch < M) atomicAdd(dtau + ch, dcoef[ch]); }   // dtau is zero-initialised
+          else dtau[ch] = (ch < M) ? (fsp ? dcoef[ch] * phi[ch] : dcoef[ch]) : 0.f;
         }
         if (fsp) {
           // dphi = dcoef∘tau -> second B map (s_p*dphi) and the softmax backward into input_0
@@ -468,11 +476,11 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
         float db2 = 0.f;
         constexpr int kMaxCh = 16;   // conv Transform exists for Mp <= 512 (CLEVR 256, SHAPES 512)
         const int nj = Mp >> 5;
-        float* dA_all = c.dstencil + (size_t)q * HW * Mp;
+        float* dA_all = c.dstencil + (size_t)(first + blockIdx.x) * HW * Mp;
         float dtau_r[kMaxCh], dw2_r[kMaxCh], dbk_r[kMaxCh];
 #pragma unroll
         for (int j = 0; j < kMaxCh; ++j) { dtau_r[j] = 0.f; dw2_r[j] = 0.f; dbk_r[j] = 0.f; }
-        for (int p = warp; p < HW; p += nwarps) {
+        for (int p = p_lo + warp; p < p_hi; p += nwarps) {
           const int y = p / Ww, x = p - y * Ww;
           const float gp = g[p];
           float A[kMaxCh];
@@ -551,9 +559,9 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
           float acc[KS * KS];
 #pragma unroll
           for (int t = 0; t < KS * KS; ++t) acc[t] = 0.f;
-          int y = 0, x = 0;
+          int y = p_lo / Ww, x = p_lo - y * Ww;
 #pragma unroll 2
-          for (int p = 0; p < HW; ++p, ++x) {
+          for (int p = p_lo; p < p_hi; ++p, ++x) {
             if (x == Ww) { x = 0; ++y; }
             const float d = dA_all[(size_t)p * Mp + ch];
 #pragma unroll
@@ -569,7 +577,7 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
         __syncthreads();
         float* dtau = c.dtau + (size_t)nd.text * Mp;
         for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
-          dtau[ch] = dtauv[ch];
+          if (ns > 1) { if (ch < M) atomicAdd(dtau + ch, dtauv[ch]); } else dtau[ch] = dtauv[ch];
           if (ch < M) {
             atomicAdd(c.gflat + c.go.elt_w[ES_TRANSFORM] + ch, dw2v[ch]);
             atomicAdd(c.gflat + c.go.conv_b + ch, dbkv[ch]);
@@ -581,7 +589,8 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
         }
         for (int p = threadIdx.x; p < HW; p += blockDim.x) {
           const int y = p / Ww, x = p - y * Ww;
-          gin0[p] += dpad[(y + R) * PW + x + R];
+          const float dv = dpad[(y + R) * PW + x + R];
+          if (ns > 1) { if (dv != 0.f) atomicAdd(gin0 + p, dv); } else gin0[p] += dv;
         }
         break;
       }

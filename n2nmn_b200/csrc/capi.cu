@@ -69,7 +69,7 @@ struct TableSlot {
 
 struct TableOffsets {
   size_t nodes, q_ptr, text_t, text_b, groups, work, img_ptr, node_text, node_out, mslot,
-      wave_nodes, node_entry, entries, text_set_start, labels, head_work, head_list, pool_img,
+      wave_nodes, bwd_nodes, node_entry, entries, text_set_start, labels, head_work, head_list, pool_img,
       total;
 };
 
@@ -141,7 +141,8 @@ struct n2nmn_ctx {
   float* per_sample = nullptr;
   float* dtau = nullptr;
   float* dmap = nullptr;
-  float* dstencil = nullptr;   // [max_batch][HW][Mp] scratch of the Transform backward
+  float* dstencil = nullptr;
+  float* gmap = nullptr;   // [max_batch][HW][Mp] scratch of the Transform backward
   int dmap_entries = 0;
   VarSeg* d_segs = nullptr;
   float* d_sumsq = nullptr;
@@ -276,6 +277,7 @@ TableOffsets table_offsets(const HostSchedule& S) {
   o.node_out = take(S.node_out.size() * 4);
   o.mslot = take(S.mslot.size() * 4);
   o.wave_nodes = take(S.wave_nodes.size() * 4);
+  o.bwd_nodes = take(S.bwd_nodes.size() * 4);
   o.node_entry = take(S.node_entry.size() * 4);
   o.entries = take(S.entries.size() * sizeof(BwdEntryHost));
   o.text_set_start = take(S.text_set_start.size() * 4);
@@ -345,6 +347,7 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
     put(slot->host, o.node_out, S.node_out);
     put(slot->host, o.mslot, S.mslot);
     put(slot->host, o.wave_nodes, S.wave_nodes);
+    put(slot->host, o.bwd_nodes, S.bwd_nodes);
     put(slot->host, o.node_entry, S.node_entry);
     put(slot->host, o.entries, S.entries);
     put(slot->host, o.text_set_start, S.text_set_start);
@@ -705,7 +708,7 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
     const size_t tiles = (size_t)c->G * (((size_t)cfg->max_batch * c->HW + 127) / 128 + 1);
     c->table_cap = nodes * (sizeof(NodeRec) + 4 * 6) + (nodes / 8 + 8) * sizeof(TextGroup) +
                    tiles * (TT / kMaxProjNodesPerPass + 1 + NUM_PROJ_SETS) * sizeof(ProjWork) +
-                   (size_t)NB * (12 + 4 * NUM_PROJ_SETS) + nodes * (4 + 2 * sizeof(BwdEntryHost)) +
+                   (size_t)NB * (12 + 4 * NUM_PROJ_SETS) + nodes * (8 + 2 * sizeof(BwdEntryHost)) +
                    (size_t)NB * (4 + 8 + sizeof(HeadWork)) + 4096;
     for (int i = 0; i < kTableSlots; ++i) {
       CUDA_TRY(cudaMallocHost(&c->slots[i].host, c->table_cap));
@@ -794,7 +797,7 @@ int n2nmn_destroy(n2nmn_ctx* c) {
   for (int s = 0; s < NUM_PROJ_SETS; ++s) { cudaFree(c->proj_wt[s]); cudaFree(c->proj_bias[s]); }
   cudaFree(c->feat_aug); cudaFree(c->tb.tau); cudaFree(c->arena); cudaFree(c->mbuf);
   cudaFree(c->pooled); cudaFree(c->pool_att); cudaFree(c->conv_quad); cudaFree(c->tb.tq);
-  cudaFree(c->dscores); cudaFree(c->per_sample); cudaFree(c->dtau); cudaFree(c->dmap); cudaFree(c->dstencil);
+  cudaFree(c->dscores); cudaFree(c->per_sample); cudaFree(c->dtau); cudaFree(c->dmap); cudaFree(c->dstencil); cudaFree(c->gmap);
   cudaFree(c->d_segs); cudaFree(c->d_sumsq);
   cudaFree(c->scores_tmp); cudaFree(c->e2e_feat); cudaFree(c->e2e_wv); cudaFree(c->e2e_scores);
   for (int i = 0; i < kTableSlots; ++i) {
@@ -1341,8 +1344,9 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
     CUDA_TRY(cudaMalloc(&c->dtau, (size_t)c->text_rows_cap * c->Mp * sizeof(float)));
     c->dmap_entries = NB * TT;
     CUDA_TRY(cudaMalloc(&c->dmap, (size_t)c->dmap_entries * c->HW * c->Mp * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&c->dstencil, (size_t)c->cfg.max_batch * c->HW * c->Mp * sizeof(float)));
-    const BwdSmem L = bwd_smem_layout(c->cfg.H, c->cfg.W, c->Mp, c->cfg.kernel_size, C, TT);
+    CUDA_TRY(cudaMalloc(&c->dstencil, (size_t)c->dmap_entries * c->HW * c->Mp * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c->gmap, (size_t)c->arena_slots * ((c->HW + 3) & ~3) * sizeof(float)));
+    const BwdSmem L = bwd_smem_layout(c->cfg.H, c->cfg.W, c->Mp, c->cfg.kernel_size, C);
     CUDA_TRY(cudaFuncSetAttribute(tree_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(L.total * sizeof(float))));
     CUDA_TRY(cudaFuncSetAttribute(tree_bwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1359,9 +1363,19 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
   const char* err = nullptr;
   if (int rc = compile_schedule(c->shp, tokens, T, N, vocab_ops, num_vocab, &sc->hs, &err, true))
     return fail(rc, err ? err : "compile_schedule failed");
+  {   // every node bucketed by depth (leaves = 1): the backward runs one launch per level, top down
+    HostSchedule& W = sc->hs;
+    W.bwd_ptr.assign(W.max_depth + 2, 0);
+    for (size_t i = 0; i < W.nodes.size(); ++i) ++W.bwd_ptr[W.depth[i] + 1];
+    for (int dd = 0; dd <= W.max_depth; ++dd) W.bwd_ptr[dd + 1] += W.bwd_ptr[dd];
+    W.bwd_nodes.assign(W.nodes.size(), 0);
+    std::vector<int32_t> fill(W.bwd_ptr.begin(), W.bwd_ptr.end() - 1);
+    for (size_t i = 0; i < W.nodes.size(); ++i) W.bwd_nodes[fill[W.depth[i]]++] = (int32_t)i;
+  }
   const HostSchedule& S = sc->hs;
   if (validity_out) std::memcpy(validity_out, S.validity.data(), N);
-  if ((int)S.nodes.size() > c->arena_slots || (int)S.entries.size() > c->dmap_entries)
+  if ((int)S.nodes.size() > c->arena_slots || (int)S.entries.size() > c->dmap_entries ||
+      (int)S.nodes.size() > c->dmap_entries)
     return fail(N2NMN_ERR_CAPACITY, "too many nodes for the context");
   if (S.max_stack > c->stack_cap)
     return fail(N2NMN_ERR_CAPACITY, "layout too deep for the training path");
@@ -1389,15 +1403,23 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
   BwdCtx bc;
   bc.md = c->md; bc.tb = c->tb; bc.arena = c->arena; bc.scores = scores_dev;
   bc.dscores = c->dscores; bc.mbuf = c->mbuf; bc.gflat = gflat_dev; bc.dtau = c->dtau;
-  bc.dmap = c->dmap; bc.dstencil = c->dstencil; bc.go = c->go; bc.max_nodes_q = TT;
-  const BwdSmem L = bwd_smem_layout(c->cfg.H, c->cfg.W, c->Mp, c->cfg.kernel_size, C, TT);
+  bc.dmap = c->dmap; bc.dstencil = c->dstencil; bc.gmap = c->gmap; bc.go = c->go;
+  const BwdSmem L = bwd_smem_layout(c->cfg.H, c->cfg.W, c->Mp, c->cfg.kernel_size, C);
   const size_t bsm = L.total * sizeof(float);
   const int32_t* d_entry = reinterpret_cast<const int32_t*>(d + o.node_entry);
-  if (c->cfg.kernel_size != 5)
-    tree_bwd_kernel<3><<<N, kNodeThreads, bsm, st>>>(bc, d_nodes, d_qptr, d_entry);
-  else
-    tree_bwd_kernel<5><<<N, kNodeThreads, bsm, st>>>(bc, d_nodes, d_qptr, d_entry);
-  ++c->launches;
+  const int32_t* d_bwd = reinterpret_cast<const int32_t*>(d + o.bwd_nodes);
+  CUDA_TRY(cudaMemsetAsync(c->gmap, 0, S.nodes.size() * (size_t)L.HWp * sizeof(float), st));
+  CUDA_TRY(cudaMemsetAsync(c->dtau, 0, S.text_t.size() * (size_t)c->Mp * sizeof(float), st));
+  for (int dd = S.max_depth; dd >= 1; --dd) {
+    const int first = S.bwd_ptr[dd], cnt = S.bwd_ptr[dd + 1] - first;
+    if (cnt <= 0) continue;
+    const dim3 grid(cnt, kBwdSlices);
+    if (c->cfg.kernel_size != 5)
+      tree_bwd_kernel<3><<<grid, kNodeThreads, bsm, st>>>(bc, d_nodes, d_bwd, first, d_entry);
+    else
+      tree_bwd_kernel<5><<<grid, kNodeThreads, bsm, st>>>(bc, d_nodes, d_bwd, first, d_entry);
+    ++c->launches;
+  }
   // ---- text layers
   const int rows = (int)S.text_t.size();
   if (rows > 0) {
