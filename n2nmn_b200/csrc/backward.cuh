@@ -145,8 +145,11 @@ constexpr int kBwdSlices = 6;   // CTAs per splittable node (25 of the 150 CLEVR
 // one parent, so its gradient row has one writer, and that writer ran in an earlier launch).
 // Round 1 walked a question's nodes inside one CTA: 64 CTAs on 148 SMs and the longest question
 // (~10 dependent modules, each bound by its own reductions) set the time: 360 us.
-template <int KS>
-__global__ void __launch_bounds__(kNodeThreads)
+// Two instantiations: kTransform = true handles every op (the stencil backward of Transform keeps
+// ~170 registers busy: one CTA per SM) and runs the levels that contain Transform nodes; false
+// leaves the Transform body out (128 registers, two CTAs per SM) and runs the other levels.
+template <int KS, bool kTransform>
+__global__ void __launch_bounds__(kNodeThreads, kTransform ? 1 : 2)
 tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
                 const int32_t* __restrict__ bwd_nodes, int first,
                 const int32_t* __restrict__ node_entry) {
@@ -452,7 +455,7 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
         }
         break;
       }
-      case OP_TRANSFORM: {
+      case OP_TRANSFORM: if constexpr (kTransform) {
         // A = conv(a)+bK ; e = A∘tau ; out = l2norm(e)·w2 + b2
         const int PW = Ww + KS - 1, PH = Hh + KS - 1, R = (KS - 1) / 2;
         float* tauv = v; float* w2v = v + Mp; float* bkv = v + 2 * Mp; float* dtauv = v + 3 * Mp;
@@ -593,7 +596,7 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
           if (ns > 1) { if (dv != 0.f) atomicAdd(gin0 + p, dv); } else gin0[p] += dv;
         }
         break;
-      }
+      } else break;
       default: break;
     }
     __syncthreads();
@@ -934,16 +937,24 @@ __global__ void __launch_bounds__(kXtbThreads) xtb_mma_kernel(const Src src, int
   };
   auto flush = [&](int st) {
     float* W = src.w_out(st);
+    const bool pair_ok = (M & 1) == 0 && (reinterpret_cast<uintptr_t>(W) & 7) == 0;
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int k = k0 + wm * 32 + mi * 16 + g + ((i & 2) ? 8 : 0);
-          const int ch = c0 + wn * 32 + ni * 8 + 2 * t + (i & 1);
-          const float v = acc[mi][ni][i];
-          if (k < Kd && ch < M && v != 0.f) atomicAdd(W + (size_t)k * M + ch, v);
+        for (int hh = 0; hh < 2; ++hh) {
+          const int k = k0 + wm * 32 + mi * 16 + g + 8 * hh;
+          const int ch = c0 + wn * 32 + ni * 8 + 2 * t;
+          const float v0 = acc[mi][ni][2 * hh], v1 = acc[mi][ni][2 * hh + 1];
+          if (k >= Kd || ch >= M) continue;
+          float* dst = W + (size_t)k * M + ch;
+          if (pair_ok && ch + 1 < M) {   // one 8-byte reduction for the two adjacent channels
+            if (v0 != 0.f || v1 != 0.f) atomicAdd(reinterpret_cast<float2*>(dst), make_float2(v0, v1));
+          } else {
+            if (v0 != 0.f) atomicAdd(dst, v0);
+            if (ch + 1 < M && v1 != 0.f) atomicAdd(dst + 1, v1);
+          }
         }
     const int ch = c0 + (tid & (kXtbN - 1));
     if (bias_cta && ch < M && bsum != 0.f) atomicAdd(src.b_out(st) + ch, bsum);

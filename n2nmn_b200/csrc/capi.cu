@@ -1347,10 +1347,13 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
     CUDA_TRY(cudaMalloc(&c->dstencil, (size_t)c->dmap_entries * c->HW * c->Mp * sizeof(float)));
     CUDA_TRY(cudaMalloc(&c->gmap, (size_t)c->arena_slots * ((c->HW + 3) & ~3) * sizeof(float)));
     const BwdSmem L = bwd_smem_layout(c->cfg.H, c->cfg.W, c->Mp, c->cfg.kernel_size, C);
-    CUDA_TRY(cudaFuncSetAttribute(tree_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(L.total * sizeof(float))));
-    CUDA_TRY(cudaFuncSetAttribute(tree_bwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(L.total * sizeof(float))));
+    const int bwd_smem = (int)(L.total * sizeof(float));
+    CUDA_TRY(cudaFuncSetAttribute(tree_bwd_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem));
+    CUDA_TRY(cudaFuncSetAttribute(tree_bwd_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem));
+    CUDA_TRY(cudaFuncSetAttribute(tree_bwd_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem));
+    CUDA_TRY(cudaFuncSetAttribute(tree_bwd_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem));
+    CUDA_TRY(cudaFuncSetAttribute(tree_bwd_kernel<3, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_TRY(cudaFuncSetAttribute(tree_bwd_kernel<5, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CUDA_TRY(cudaFuncSetAttribute(xtb_mma_kernel<FeatGradSrc>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kXtbSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(xtb_mma_kernel<TextGradSrc>,
@@ -1365,12 +1368,15 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
     return fail(rc, err ? err : "compile_schedule failed");
   {   // every node bucketed by depth (leaves = 1): the backward runs one launch per level, top down
     HostSchedule& W = sc->hs;
-    W.bwd_ptr.assign(W.max_depth + 2, 0);
-    for (size_t i = 0; i < W.nodes.size(); ++i) ++W.bwd_ptr[W.depth[i] + 1];
-    for (int dd = 0; dd <= W.max_depth; ++dd) W.bwd_ptr[dd + 1] += W.bwd_ptr[dd];
+    // bucket 2*depth: the level's nodes other than Transform, 2*depth + 1: its Transform nodes
+    const int nb = 2 * (W.max_depth + 1);
+    W.bwd_ptr.assign(nb + 1, 0);
+    auto bucket = [&](size_t i) { return 2 * W.depth[i] + (W.nodes[i].op == OP_TRANSFORM ? 1 : 0); };
+    for (size_t i = 0; i < W.nodes.size(); ++i) ++W.bwd_ptr[bucket(i) + 1];
+    for (int b = 0; b < nb; ++b) W.bwd_ptr[b + 1] += W.bwd_ptr[b];
     W.bwd_nodes.assign(W.nodes.size(), 0);
     std::vector<int32_t> fill(W.bwd_ptr.begin(), W.bwd_ptr.end() - 1);
-    for (size_t i = 0; i < W.nodes.size(); ++i) W.bwd_nodes[fill[W.depth[i]]++] = (int32_t)i;
+    for (size_t i = 0; i < W.nodes.size(); ++i) W.bwd_nodes[fill[bucket(i)]++] = (int32_t)i;
   }
   const HostSchedule& S = sc->hs;
   if (validity_out) std::memcpy(validity_out, S.validity.data(), N);
@@ -1410,14 +1416,21 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
   const int32_t* d_bwd = reinterpret_cast<const int32_t*>(d + o.bwd_nodes);
   CUDA_TRY(cudaMemsetAsync(c->gmap, 0, S.nodes.size() * (size_t)L.HWp * sizeof(float), st));
   CUDA_TRY(cudaMemsetAsync(c->dtau, 0, S.text_t.size() * (size_t)c->Mp * sizeof(float), st));
+  // a level's nodes are listed [others | Transform nodes]; a level with Transform nodes runs the
+  // full instantiation over all of them (one CTA per SM), a level without the lighter one
   for (int dd = S.max_depth; dd >= 1; --dd) {
-    const int first = S.bwd_ptr[dd], cnt = S.bwd_ptr[dd + 1] - first;
+    const int first = S.bwd_ptr[2 * dd], cnt = S.bwd_ptr[2 * dd + 2] - first;
     if (cnt <= 0) continue;
+    const bool has_tr = S.bwd_ptr[2 * dd + 2] > S.bwd_ptr[2 * dd + 1];
     const dim3 grid(cnt, kBwdSlices);
-    if (c->cfg.kernel_size != 5)
-      tree_bwd_kernel<3><<<grid, kNodeThreads, bsm, st>>>(bc, d_nodes, d_bwd, first, d_entry);
-    else
-      tree_bwd_kernel<5><<<grid, kNodeThreads, bsm, st>>>(bc, d_nodes, d_bwd, first, d_entry);
+    const bool k5 = c->cfg.kernel_size == 5;
+    if (has_tr) {
+      if (k5) tree_bwd_kernel<5, true><<<grid, kNodeThreads, bsm, st>>>(bc, d_nodes, d_bwd, first, d_entry);
+      else tree_bwd_kernel<3, true><<<grid, kNodeThreads, bsm, st>>>(bc, d_nodes, d_bwd, first, d_entry);
+    } else {
+      if (k5) tree_bwd_kernel<5, false><<<grid, kNodeThreads, bsm, st>>>(bc, d_nodes, d_bwd, first, d_entry);
+      else tree_bwd_kernel<3, false><<<grid, kNodeThreads, bsm, st>>>(bc, d_nodes, d_bwd, first, d_entry);
+    }
     ++c->launches;
   }
   // ---- text layers
