@@ -46,6 +46,7 @@ struct BwdCtx {
   float* dmap;            // [entries][HW][Mp]
   float* dstencil;        // [nodes][HW][Mp] scratch: d(conv_maps output) of a Transform node
   float* gmap;            // [nodes][HWp] d loss / d(attention map of the node), zero-initialised
+  const float* phi;       // [score rows][2][Mp] attended features of the Describe-type roots (forward)
   GradOffsets go;
 };
 
@@ -138,7 +139,7 @@ __host__ __device__ inline BwdSmem bwd_smem_layout(int H, int W, int Mp, int ksi
   return s;
 }
 
-constexpr int kBwdSlices = 6;   // CTAs per splittable node (25 of the 150 CLEVR pixels each)
+constexpr int kBwdSlicesMax = 8;   // CTAs per splittable node (>= 19 of the 150 CLEVR pixels each)
 
 // One CTA per NODE, one launch per depth level from the roots down (bwd_nodes lists the nodes by
 // depth): the gradient maps travel between the levels through c.gmap (a node's map feeds exactly
@@ -177,9 +178,10 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
     const int i = bwd_nodes[first + blockIdx.x];
     const NodeRec nd = nodes[i];
     // gridDim.y CTAs share the pixels of a node whose per-pixel work is independent (Find, Filter,
-    // Transform: what they accumulate over pixels goes out through atomics); the others run in
-    // slice 0 alone
-    const bool split = (nd.op == OP_FIND || nd.op == OP_FILTER || nd.op == OP_TRANSFORM);
+    // Transform: what they accumulate over pixels goes out through atomics; Describe and
+    // SameProperty: slice 0 emits the per-node results); the others run in slice 0 alone
+    const bool split = (nd.op == OP_FIND || nd.op == OP_FILTER || nd.op == OP_TRANSFORM ||
+                        nd.op == OP_DESCRIBE || nd.op == OP_SAME_PROPERTY);
     const int slice = blockIdx.y, ns = split ? (int)gridDim.y : 1;
     if (slice >= ns) return;
     const int p_lo = (HW * slice) / ns, p_hi = (HW * (slice + 1)) / ns;
@@ -239,6 +241,9 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
       }
       case OP_DESCRIBE: case OP_SAME_PROPERTY: {
         // forward: s = softmax(a); phi = Σ_p s_p G[p]; e = tau∘phi (∘phi1); ê = e/n; scores = ê·Wout+b
+        // phi comes from the forward pass (c.phi); every slice redoes the channel-vector part
+        // (a few thousand FMAs) and takes its share of the pixels for the B maps and the softmax
+        // backward, whose Σ_p s_p ds_p term is dphi·phi in closed form.
         const bool two = (nd.op == OP_SAME_PROPERTY);
         const int os = two ? OS_SAMEPROP : OS_DESCRIBE;
         float* phi0 = v; float* phi1 = v + Mp; float* e = v + 2 * Mp; float* de = v + 3 * Mp;
@@ -251,15 +256,9 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
         const float* G0 = c.mbuf + (size_t)nd.aux * HW * Mp;
         const float* G1 = two ? c.mbuf + (size_t)nd.aux2 * HW * Mp : nullptr;
         const float* tau = c.tb.tau + (size_t)nd.text * Mp;
+        const float* ph = c.phi + (size_t)nd.out * 2 * Mp;
         for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
-          float p0 = 0.f, p1 = 0.f;
-          if (ch < M) {
-#pragma unroll 8
-            for (int p = 0; p < HW; ++p) {
-              p0 = fmaf(a0[p], G0[(size_t)p * Mp + ch], p0);
-              if (two) p1 = fmaf(a1[p], G1[(size_t)p * Mp + ch], p1);
-            }
-          }
+          const float p0 = ch < M ? ph[ch] : 0.f, p1 = (two && ch < M) ? ph[Mp + ch] : 0.f;
           phi0[ch] = p0; phi1[ch] = p1;
           e[ch] = (ch < M) ? (two ? p0 * tau[ch] * p1 : tau[ch] * p0) : 0.f;
         }
@@ -268,22 +267,24 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
         for (int ch = threadIdx.x; ch < M; ch += blockDim.x) ss = fmaf(e[ch], e[ch], ss);
         ss = block_reduce<0>(ss, red);
         const float inv = rsqrtf(fmaxf(ss, kEps));
-        // dê = Wout·g ; head weight grads with ê
+        // dê = Wout·g ; head weight grads with ê (slice 0)
         float dot = 0.f;
         for (int ch = threadIdx.x; ch < M; ch += blockDim.x) {
           const float eh = e[ch] * inv;
           float acc = 0.f;
           for (int cc = 0; cc < C; ++cc) {
             acc = fmaf(md.out_w[os][(size_t)ch * C + cc], gsc[cc], acc);
-            atomicAdd(c.gflat + c.go.out_w[os] + (size_t)ch * C + cc, eh * gsc[cc]);
+            if (slice == 0) atomicAdd(c.gflat + c.go.out_w[os] + (size_t)ch * C + cc, eh * gsc[cc]);
           }
           de[ch] = acc;            // holds dê for now
           dot = fmaf(eh, acc, dot);
         }
-        for (int cc = threadIdx.x; cc < C; cc += blockDim.x) atomicAdd(c.gflat + c.go.out_b[os] + cc, gsc[cc]);
+        if (slice == 0)
+          for (int cc = threadIdx.x; cc < C; cc += blockDim.x) atomicAdd(c.gflat + c.go.out_b[os] + cc, gsc[cc]);
         dot = block_reduce<0>(dot, red);
         if (!(ss > kEps)) dot = 0.f;
         float* dtau = c.dtau + (size_t)nd.text * Mp;
+        float sd0 = 0.f, sd1 = 0.f;   // Σ_ch dphi·phi = Σ_p s_p ds_p
         for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
           float d = 0.f, dt = 0.f, d0 = 0.f, d1 = 0.f;
           if (ch < M) {
@@ -291,8 +292,12 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
             if (two) { dt = d * phi0[ch] * phi1[ch]; d0 = d * tau[ch] * phi1[ch]; d1 = d * tau[ch] * phi0[ch]; }
             else { dt = d * phi0[ch]; d0 = d * tau[ch]; }
           }
-          dtau[ch] = dt; dphi0[ch] = d0; dphi1[ch] = d1;
+          if (slice == 0) dtau[ch] = dt;
+          dphi0[ch] = d0; dphi1[ch] = d1;
+          sd0 = fmaf(d0, phi0[ch], sd0); sd1 = fmaf(d1, phi1[ch], sd1);
         }
+        sd0 = block_reduce<0>(sd0, red);
+        sd1 = block_reduce<0>(sd1, red);
         __syncthreads();
         // B maps: dG[p,:] = s_p * dphi ; input gradients through the softmax
         const int ent = node_entry[i];
@@ -300,9 +305,10 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
           const float* G = which ? G1 : G0;
           const float* sft = which ? a1 : a0;
           const float* dphi = which ? dphi1 : dphi0;
+          const float sd = which ? sd1 : sd0;
           float* B = c.dmap + (size_t)(ent + which) * HW * Mp;
-          float* ds = which ? db_ : da;
-          for (int p = warp; p < HW; p += nwarps) {
+          float* gi = which ? gin1 : gin0;
+          for (int p = p_lo + warp; p < p_hi; p += nwarps) {
             float acc = 0.f;
             const float sp = sft[p];
             for (int ch = lane; ch < Mp; ch += 32) {
@@ -311,15 +317,8 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
               B[(size_t)p * Mp + ch] = sp * dp;
             }
             acc = warp_sum(acc);
-            if (lane == 0) ds[p] = acc;
+            if (lane == 0) gi[p] += sp * (acc - sd);
           }
-          __syncthreads();
-          float sd = 0.f;
-          for (int p = threadIdx.x; p < HW; p += blockDim.x) sd = fmaf(sft[p], ds[p], sd);
-          sd = block_reduce<0>(sd, red);
-          float* gi = which ? gin1 : gin0;
-          for (int p = threadIdx.x; p < HW; p += blockDim.x) gi[p] += sft[p] * (ds[p] - sd);
-          __syncthreads();
         }
         break;
       }

@@ -142,7 +142,8 @@ struct n2nmn_ctx {
   float* dtau = nullptr;
   float* dmap = nullptr;
   float* dstencil = nullptr;
-  float* gmap = nullptr;   // [max_batch][HW][Mp] scratch of the Transform backward
+  float* gmap = nullptr;
+  float* phi_buf = nullptr;   // [max_batch][HW][Mp] scratch of the Transform backward
   int dmap_entries = 0;
   VarSeg* d_segs = nullptr;
   float* d_sumsq = nullptr;
@@ -457,6 +458,7 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
   NodeCtx nc;
   nc.md = c->md; nc.tb = c->tb; nc.arena = arena; nc.scores = scores_seg[0]; nc.mbuf = c->mbuf;
   nc.pooled = c->pooled; nc.pool_pitch = c->Kp; nc.pool_att = c->pool_att;
+  nc.phi_out = S.train ? c->phi_buf : nullptr;
   const int NQ = (int)S.q_ptr.size() - 1;
   // several segments: question q writes row q % N of segment q / N; one segment: row q (the
   // per-module entry point numbers its call rows beyond the bound batch size)
@@ -797,7 +799,7 @@ int n2nmn_destroy(n2nmn_ctx* c) {
   for (int s = 0; s < NUM_PROJ_SETS; ++s) { cudaFree(c->proj_wt[s]); cudaFree(c->proj_bias[s]); }
   cudaFree(c->feat_aug); cudaFree(c->tb.tau); cudaFree(c->arena); cudaFree(c->mbuf);
   cudaFree(c->pooled); cudaFree(c->pool_att); cudaFree(c->conv_quad); cudaFree(c->tb.tq);
-  cudaFree(c->dscores); cudaFree(c->per_sample); cudaFree(c->dtau); cudaFree(c->dmap); cudaFree(c->dstencil); cudaFree(c->gmap);
+  cudaFree(c->dscores); cudaFree(c->per_sample); cudaFree(c->dtau); cudaFree(c->dmap); cudaFree(c->dstencil); cudaFree(c->gmap); cudaFree(c->phi_buf);
   cudaFree(c->d_segs); cudaFree(c->d_sumsq);
   cudaFree(c->scores_tmp); cudaFree(c->e2e_feat); cudaFree(c->e2e_wv); cudaFree(c->e2e_scores);
   for (int i = 0; i < kTableSlots; ++i) {
@@ -1346,6 +1348,7 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
     CUDA_TRY(cudaMalloc(&c->dmap, (size_t)c->dmap_entries * c->HW * c->Mp * sizeof(float)));
     CUDA_TRY(cudaMalloc(&c->dstencil, (size_t)c->dmap_entries * c->HW * c->Mp * sizeof(float)));
     CUDA_TRY(cudaMalloc(&c->gmap, (size_t)c->arena_slots * ((c->HW + 3) & ~3) * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c->phi_buf, (size_t)NB * 2 * c->Mp * sizeof(float)));
     const BwdSmem L = bwd_smem_layout(c->cfg.H, c->cfg.W, c->Mp, c->cfg.kernel_size, C);
     const int bwd_smem = (int)(L.total * sizeof(float));
     CUDA_TRY(cudaFuncSetAttribute(tree_bwd_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem));
@@ -1409,7 +1412,7 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
   BwdCtx bc;
   bc.md = c->md; bc.tb = c->tb; bc.arena = c->arena; bc.scores = scores_dev;
   bc.dscores = c->dscores; bc.mbuf = c->mbuf; bc.gflat = gflat_dev; bc.dtau = c->dtau;
-  bc.dmap = c->dmap; bc.dstencil = c->dstencil; bc.gmap = c->gmap; bc.go = c->go;
+  bc.dmap = c->dmap; bc.dstencil = c->dstencil; bc.gmap = c->gmap; bc.phi = c->phi_buf; bc.go = c->go;
   const BwdSmem L = bwd_smem_layout(c->cfg.H, c->cfg.W, c->Mp, c->cfg.kernel_size, C);
   const size_t bsm = L.total * sizeof(float);
   const int32_t* d_entry = reinterpret_cast<const int32_t*>(d + o.node_entry);
@@ -1421,8 +1424,13 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
   for (int dd = S.max_depth; dd >= 1; --dd) {
     const int first = S.bwd_ptr[2 * dd], cnt = S.bwd_ptr[2 * dd + 2] - first;
     if (cnt <= 0) continue;
-    const bool has_tr = S.bwd_ptr[2 * dd + 2] > S.bwd_ptr[2 * dd + 1];
-    const dim3 grid(cnt, kBwdSlices);
+    const int n_tr = S.bwd_ptr[2 * dd + 2] - S.bwd_ptr[2 * dd + 1];
+    const bool has_tr = n_tr > 0;
+    // CTAs per splittable node: as many as keep the level's heavy CTAs within one wave of the
+    // SMs (148 at one CTA per SM with Transform nodes, 296 without)
+    const int slices = has_tr ? std::max(3, std::min(kBwdSlicesMax, 148 / n_tr))
+                              : std::max(2, std::min(6, 296 / cnt));
+    const dim3 grid(cnt, slices);
     const bool k5 = c->cfg.kernel_size == 5;
     if (has_tr) {
       if (k5) tree_bwd_kernel<5, true><<<grid, kNodeThreads, bsm, st>>>(bc, d_nodes, d_bwd, first, d_entry);

@@ -30,6 +30,9 @@ struct NodeCtx {
   float* pool_att;
   float* pooled;
   int pool_pitch;
+  // training: the attended feature vectors phi of the Describe / SameProperty roots, kept for the
+  // backward pass, [score row][2][Mp] (nullptr outside training)
+  float* phi_out;
 };
 
 // score row of question / call row q (numbered across the segments)

@@ -441,6 +441,14 @@ tree_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes, const int32_t* _
         if (co.rank == 0) {   // the tail is tiny: one CTA finishes it
           sum_partials(co, part, nullptr, s.v0, M, Mp);
           if (two) sum_partials(co, part + Mp, nullptr, s.v1, M, Mp);
+          if (c.phi_out != nullptr) {
+            __syncthreads();
+            float* ph = c.phi_out + (size_t)nd.out * 2 * Mp;
+            for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
+              ph[ch] = ch < M ? s.v0[ch] : 0.f;
+              ph[Mp + ch] = (two && ch < M) ? s.v1[ch] : 0.f;
+            }
+          }
           float ss = 0.f;
           for (int ch = threadIdx.x; ch < M; ch += blockDim.x) {
             const float e = two ? s.v0[ch] * tau[ch] * s.v1[ch] : tau[ch] * s.v0[ch];
