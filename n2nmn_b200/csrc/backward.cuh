@@ -1153,12 +1153,19 @@ __global__ void train_scalars_kernel(const float* __restrict__ loss_sum,
   }
 }
 
-// tf.clip_by_norm per tensor, then Adam (TF: lr_t = lr*sqrt(1-b2^t)/(1-b1^t)).
+// tf.clip_by_norm per tensor, then Adam (TF: lr_t = lr*sqrt(1-b2^t)/(1-b1^t)). The new value also
+// goes straight to the variable's place in the context's weight buffer (plain or row-pitched copy,
+// prep.cuh RepackSeg): the re-pack pass after the step only has the K-major tcgen05 copies and the
+// Transform quadratic form left to do.
 __global__ void adam_clip_kernel(float* __restrict__ w, const float* __restrict__ g,
                                  float* __restrict__ m, float* __restrict__ v,
                                  const VarSeg* __restrict__ segs, const float* __restrict__ sumsq,
-                                 float lr_t, float b1, float b2, float eps, float max_norm) {
+                                 float lr_t, float b1, float b2, float eps, float max_norm,
+                                 const RepackSeg* __restrict__ rp, float* __restrict__ wbuf,
+                                 int pitch) {
   const VarSeg s = segs[blockIdx.y];
+  const RepackSeg r = rp[blockIdx.y];
+  float* dst = wbuf + r.dst_off;
   const float nrm = sqrtf(sumsq[blockIdx.y]);
   const float scale = (nrm > max_norm) ? max_norm / nrm : 1.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s.count; i += gridDim.x * blockDim.x) {
@@ -1167,7 +1174,10 @@ __global__ void adam_clip_kernel(float* __restrict__ w, const float* __restrict_
     const float mv = b1 * m[o] + (1.f - b1) * gv;
     const float vv = b2 * v[o] + (1.f - b2) * gv * gv;
     m[o] = mv; v[o] = vv;
-    w[o] -= lr_t * mv / (sqrtf(vv) + eps);
+    const float wn = w[o] - lr_t * mv / (sqrtf(vv) + eps);
+    w[o] = wn;
+    if (r.kind == 0) dst[i] = wn;
+    else { const int row = i / r.cols; dst[(size_t)row * pitch + (i - row * r.cols)] = wn; }
   }
 }
 

@@ -1275,9 +1275,8 @@ int n2nmn_flat_offset(const n2nmn_ctx* c, int index, int64_t* offset, int64_t* c
   return 0;
 }
 
-int n2nmn_load_flat_weights(n2nmn_ctx* c, const float* wflat_dev, void* stream) {
-  if (!c || !wflat_dev) return fail(N2NMN_ERR_ARG, "null argument");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+namespace {
+int ensure_repack_tables(n2nmn_ctx* c) {
   const int nv = (int)c->vars.size();
   if (!c->d_repack) {   // what n2nmn_set_weight does per variable, as device tables
     std::vector<RepackSeg> segs(nv);
@@ -1303,8 +1302,11 @@ int n2nmn_load_flat_weights(n2nmn_ctx* c, const float* wflat_dev, void* stream) 
     CUDA_TRY(cudaMalloc(&c->d_repack, nv * sizeof(RepackSeg)));
     CUDA_TRY(cudaMemcpy(c->d_repack, segs.data(), nv * sizeof(RepackSeg), cudaMemcpyHostToDevice));
   }
-  repack_all_kernel<<<dim3(16, nv), 256, 0, st>>>(wflat_dev, c->d_repack, c->wbuf, c->Mp);
-  ++c->launches;
+  return 0;
+}
+
+// the derived copies: K-major padded projection weights / biases and the Transform quadratic form
+int repack_derived(n2nmn_ctx* c, const float* wflat_dev, cudaStream_t st) {
   if (c->proj_repack_sets > 0) {
     dim3 grid((c->Kp + 31) / 32, (c->Mp + 31) / 32, c->proj_repack_sets), block(32, 8);
     proj_repack_kernel<<<grid, block, 0, st>>>(wflat_dev, c->proj_repack, c->Dk, c->cfg.map_dim,
@@ -1320,6 +1322,17 @@ int n2nmn_load_flat_weights(n2nmn_ctx* c, const float* wflat_dev, void* stream) 
   CUDA_TRY(cudaGetLastError());
   for (Variable& v : c->vars) v.loaded = true;
   return 0;
+}
+}  // namespace
+
+int n2nmn_load_flat_weights(n2nmn_ctx* c, const float* wflat_dev, void* stream) {
+  if (!c || !wflat_dev) return fail(N2NMN_ERR_ARG, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = ensure_repack_tables(c)) return rc;
+  repack_all_kernel<<<dim3(16, (unsigned)c->vars.size()), 256, 0, st>>>(wflat_dev, c->d_repack,
+                                                                        c->wbuf, c->Mp);
+  ++c->launches;
+  return repack_derived(c, wflat_dev, st);
 }
 
 int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_dev,
@@ -1371,10 +1384,11 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
     return fail(rc, err ? err : "compile_schedule failed");
   {   // every node bucketed by depth (leaves = 1): the backward runs one launch per level, top down
     HostSchedule& W = sc->hs;
-    // bucket 2*depth: the level's nodes other than Transform, 2*depth + 1: its Transform nodes
+    // bucket 2*depth: the level's Transform nodes (the long CTAs: scheduled first), 2*depth + 1:
+    // its other nodes
     const int nb = 2 * (W.max_depth + 1);
     W.bwd_ptr.assign(nb + 1, 0);
-    auto bucket = [&](size_t i) { return 2 * W.depth[i] + (W.nodes[i].op == OP_TRANSFORM ? 1 : 0); };
+    auto bucket = [&](size_t i) { return 2 * W.depth[i] + (W.nodes[i].op == OP_TRANSFORM ? 0 : 1); };
     for (size_t i = 0; i < W.nodes.size(); ++i) ++W.bwd_ptr[bucket(i) + 1];
     for (int b = 0; b < nb; ++b) W.bwd_ptr[b + 1] += W.bwd_ptr[b];
     W.bwd_nodes.assign(W.nodes.size(), 0);
@@ -1419,12 +1433,12 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
   const int32_t* d_bwd = reinterpret_cast<const int32_t*>(d + o.bwd_nodes);
   CUDA_TRY(cudaMemsetAsync(c->gmap, 0, S.nodes.size() * (size_t)L.HWp * sizeof(float), st));
   CUDA_TRY(cudaMemsetAsync(c->dtau, 0, S.text_t.size() * (size_t)c->Mp * sizeof(float), st));
-  // a level's nodes are listed [others | Transform nodes]; a level with Transform nodes runs the
+  // a level's nodes are listed [Transform nodes | others]; a level with Transform nodes runs the
   // full instantiation over all of them (one CTA per SM), a level without the lighter one
   for (int dd = S.max_depth; dd >= 1; --dd) {
     const int first = S.bwd_ptr[2 * dd], cnt = S.bwd_ptr[2 * dd + 2] - first;
     if (cnt <= 0) continue;
-    const int n_tr = S.bwd_ptr[2 * dd + 2] - S.bwd_ptr[2 * dd + 1];
+    const int n_tr = S.bwd_ptr[2 * dd + 1] - S.bwd_ptr[2 * dd];
     const bool has_tr = n_tr > 0;
     // CTAs per splittable node: as many as keep the level's heavy CTAs within one wave of the
     // SMs (148 at one CTA per SM with Transform nodes, 296 without)
@@ -1523,11 +1537,12 @@ int adam_impl(n2nmn_ctx* c, float* wflat, float* gflat, float* m, float* v, int 
                                          l2_dev);
   const double lr_t = (double)lr * std::sqrt(1.0 - std::pow((double)beta2, step)) /
                       (1.0 - std::pow((double)beta1, step));
+  if (int rc = ensure_repack_tables(c)) return rc;
   adam_clip_kernel<<<grid, 256, 0, st>>>(wflat, gflat, m, v, c->d_segs, c->d_sumsq, (float)lr_t,
-                                         beta1, beta2, eps, max_norm);
+                                         beta1, beta2, eps, max_norm, c->d_repack, c->wbuf, c->Mp);
   c->launches += 2;
   CUDA_TRY(cudaGetLastError());
-  return n2nmn_load_flat_weights(c, wflat, st);
+  return repack_derived(c, wflat, st);
 }
 }  // namespace
 
