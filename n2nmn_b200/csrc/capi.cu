@@ -143,7 +143,13 @@ struct n2nmn_ctx {
   float* dmap = nullptr;
   float* dstencil = nullptr;
   float* gmap = nullptr;
-  float* phi_buf = nullptr;   // [max_batch][HW][Mp] scratch of the Transform backward
+  float* phi_buf = nullptr;
+  // many-class answer heads (C > 32): ê rows + score-row addresses of the roots of a launch, and
+  // the fc_eltwise matrices with rows pitched to a multiple of 4 floats (cp.async alignment)
+  float* ehat = nullptr;
+  float** ehat_dst = nullptr;
+  float* out_wp[NUM_OUT_SETS] = {};
+  int Cp = 0;   // [max_batch][HW][Mp] scratch of the Transform backward
   int dmap_entries = 0;
   VarSeg* d_segs = nullptr;
   float* d_sumsq = nullptr;
@@ -459,6 +465,7 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
   nc.md = c->md; nc.tb = c->tb; nc.arena = arena; nc.scores = scores_seg[0]; nc.mbuf = c->mbuf;
   nc.pooled = c->pooled; nc.pool_pitch = c->Kp; nc.pool_att = c->pool_att;
   nc.phi_out = S.train ? c->phi_buf : nullptr;
+  nc.ehat = c->ehat; nc.ehat_dst = c->ehat_dst;
   const int NQ = (int)S.q_ptr.size() - 1;
   // several segments: question q writes row q % N of segment q / N; one segment: row q (the
   // per-module entry point numbers its call rows beyond the bound batch size)
@@ -554,6 +561,32 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
       else CUDA_TRY(cudaLaunchKernelEx(&hc, head_kernel<4>, nc, d_nodes, d_hw, d_hl));
       ++c->launches;
       prof_mark(c, "head_kernel", st);
+      if (c->ehat) {   // fc_eltwise of the Describe-type roots as one GEMM per weight set
+        for (int op : {OP_DESCRIBE, OP_SAME_PROPERTY}) {
+          int r0 = 1 << 30, r1 = 0;
+          for (const HeadWork& w : S.head_work)
+            if (w.op == op) { r0 = std::min(r0, (int)w.first); r1 = std::max(r1, (int)(w.first + w.count)); }
+          if (r1 <= r0) continue;
+          const int os = op == OP_DESCRIBE ? OS_DESCRIBE : OS_SAMEPROP;
+          if (!c->out_wp[os]) return fail(N2NMN_ERR_STATE, "answer-head weights not packed");
+          GemmOperands gp;
+          gp.a0 = c->ehat + (size_t)r0 * c->Mp; gp.k0 = c->cfg.map_dim; gp.lda0 = c->Mp;
+          gp.a1 = nullptr; gp.k1 = 0; gp.lda1 = 0;
+          gp.R = r1 - r0; gp.B = c->out_wp[os]; gp.ldb = c->Cp; gp.C = c->cfg.num_choices;
+          cudaLaunchConfig_t gc = hc;
+          const bool narrow = gp.R <= 32;
+          gc.gridDim = dim3((unsigned)((gp.C + kMmaCols - 1) / kMmaCols),
+                            (unsigned)(narrow ? (gp.R + 31) / 32 : (gp.R + 63) / 64));
+          gc.blockDim = dim3(kMmaThreads);
+          gc.dynamicSmemBytes = mma_smem_bytes(narrow ? 2 : 4);
+          if (narrow) CUDA_TRY(cudaLaunchKernelEx(&gc, head_tail_gemm_kernel<2>, gp, c->md.out_b[os],
+                                                  (float* const*)c->ehat_dst, r0));
+          else CUDA_TRY(cudaLaunchKernelEx(&gc, head_tail_gemm_kernel<4>, gp, c->md.out_b[os],
+                                           (float* const*)c->ehat_dst, r0));
+          ++c->launches;
+          prof_mark(c, "head_tail_gemm_kernel", st);
+        }
+      }
     }
   }
   CUDA_TRY(cudaGetLastError());
@@ -699,6 +732,21 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
   }
   if (2 * (c->HW + 2) * kHeadNodesMax > head_smem_floats(c->head_nn, c->Kp, c->Mp) - 8 * kHeadNodesMax * 32)
     return fail(N2NMN_ERR_ARG, "grid too large for the answer-head kernel");
+  if (cfg->num_choices > 32) {
+    c->Cp = round_up(cfg->num_choices, 4);
+    CUDA_TRY(cudaMalloc(&c->ehat, (size_t)NB * c->Mp * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c->ehat_dst, (size_t)NB * sizeof(float*)));
+    for (const Variable& v : c->vars)
+      for (int os = 0; os < NUM_OUT_SETS; ++os)
+        if (v.slot == &md.out_w[os]) {
+          CUDA_TRY(cudaMalloc(&c->out_wp[os], (size_t)cfg->map_dim * c->Cp * sizeof(float)));
+          CUDA_TRY(cudaMemset(c->out_wp[os], 0, (size_t)cfg->map_dim * c->Cp * sizeof(float)));
+        }
+    CUDA_TRY(cudaFuncSetAttribute(head_tail_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)mma_smem_bytes(2)));
+    CUDA_TRY(cudaFuncSetAttribute(head_tail_gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)mma_smem_bytes(4)));
+  }
   c->head_nn = head_nodes_per_cta(c->Dk, c->Mp);
   c->head_smem_bytes = head_smem_layout(c->head_nn, c->Kp, c->Mp).total * (int)sizeof(float);
   if (cfg->family == N2NMN_VQA || (cfg->D % 4) != 0) {
@@ -800,6 +848,8 @@ int n2nmn_destroy(n2nmn_ctx* c) {
   cudaFree(c->feat_aug); cudaFree(c->tb.tau); cudaFree(c->arena); cudaFree(c->mbuf);
   cudaFree(c->pooled); cudaFree(c->pool_att); cudaFree(c->conv_quad); cudaFree(c->tb.tq);
   cudaFree(c->dscores); cudaFree(c->per_sample); cudaFree(c->dtau); cudaFree(c->dmap); cudaFree(c->dstencil); cudaFree(c->gmap); cudaFree(c->phi_buf);
+  cudaFree(c->ehat); cudaFree(c->ehat_dst);
+  for (int os = 0; os < NUM_OUT_SETS; ++os) cudaFree(c->out_wp[os]);
   cudaFree(c->d_segs); cudaFree(c->d_sumsq);
   cudaFree(c->scores_tmp); cudaFree(c->e2e_feat); cudaFree(c->e2e_wv); cudaFree(c->e2e_scores);
   for (int i = 0; i < kTableSlots; ++i) {
@@ -848,6 +898,10 @@ int n2nmn_set_weight(n2nmn_ctx* c, const char* name, const float* src, const int
       pad_copy_kernel<<<(c->Mp + 255) / 256, 256, 0, st>>>(c->wbuf + v.offset, c->cfg.map_dim,
                                                            c->proj_bias[v.set], c->Mp);
     }
+    for (int os = 0; os < NUM_OUT_SETS; ++os)
+      if (v.slot == &c->md.out_w[os] && c->out_wp[os])
+        pitch_rows_kernel<<<(unsigned)c->cfg.map_dim, 256, 0, st>>>(src, c->cfg.map_dim,
+                                                                   c->cfg.num_choices, c->out_wp[os], c->Cp);
     if (c->conv_quad && (v.slot == &c->md.conv_k || v.slot == &c->md.conv_b ||
                          v.slot == &c->md.elt_w[ES_TRANSFORM])) {
       // the Transform quadratic-form matrix depends on these three variables
@@ -1307,6 +1361,13 @@ int ensure_repack_tables(n2nmn_ctx* c) {
 
 // the derived copies: K-major padded projection weights / biases and the Transform quadratic form
 int repack_derived(n2nmn_ctx* c, const float* wflat_dev, cudaStream_t st) {
+  for (size_t i = 0; i < c->vars.size(); ++i)
+    for (int os = 0; os < NUM_OUT_SETS; ++os)
+      if (c->vars[i].slot == &c->md.out_w[os] && c->out_wp[os]) {
+        pitch_rows_kernel<<<(unsigned)c->cfg.map_dim, 256, 0, st>>>(
+            wflat_dev + c->flat_offset[i], c->cfg.map_dim, c->cfg.num_choices, c->out_wp[os], c->Cp);
+        ++c->launches;
+      }
   if (c->proj_repack_sets > 0) {
     dim3 grid((c->Kp + 31) / 32, (c->Mp + 31) / 32, c->proj_repack_sets), block(32, 8);
     proj_repack_kernel<<<grid, block, 0, st>>>(wflat_dev, c->proj_repack, c->Dk, c->cfg.map_dim,

@@ -33,6 +33,11 @@ struct NodeCtx {
   // training: the attended feature vectors phi of the Describe / SameProperty roots, kept for the
   // backward pass, [score row][2][Mp] (nullptr outside training)
   float* phi_out;
+  // answer heads with many classes (VQA: 3001): head_kernel leaves the normalised vector ê of
+  // root r (its position in the head list) in ehat[r][Mp] and the address of its score row in
+  // ehat_dst[r]; head_tail_gemm_kernel does the fc_eltwise product as one GEMM (nullptr otherwise)
+  float* ehat;
+  float** ehat_dst;
 };
 
 // score row of question / call row q (numbered across the segments)
