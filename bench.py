@@ -796,7 +796,30 @@ def main():
         t1e.record()
         bn.barrier()
         tms = bn.allmax(t0e.elapsed_time(t1e))
-        train = {'questions_per_sec': world * B * k_tr / (tms * 1e-3),
+        # per-kernel device times of the step (library profiling mode: CUDA events around every
+        # launch group) and the roofline of the backward weight-gradient contraction
+        tr_ex.set_profiling(True)
+        acc = {}
+        n_prof = 10
+        for i in range(n_prof):
+            tr.train_step(bn.feats[i % P], twv[i % P], ttok[i % P], tlab[i % P], log_seq_prob=lsp,
+                          sync=False)
+            torch.cuda.synchronize()
+            for name, us in tr_ex.launch_times():
+                acc[name] = acc.get(name, 0.0) + us / n_prof
+        tr_ex.set_profiling(False)
+        gflops = tr_ex.last_step_info().get('bwd_gemm_flops', 0)
+        tf32_peak = pk['bf16_tflops'] / 2
+        troof = None
+        if gflops and acc.get('feat_grad_kernel'):
+            tfs = gflops / (acc['feat_grad_kernel'] * 1e-6) / 1e12
+            troof = {'kernel': 'xtb_mma_kernel<FeatGradSrc> (dW = sum X^T B, mma.sync TF32)',
+                     'bound': 'tensor', 'achieved': tfs, 'peak': tf32_peak, 'unit': 'TFLOP/s',
+                     'frac': tfs / tf32_peak, 'avg_launch_us': acc['feat_grad_kernel'],
+                     'flops_per_launch': gflops,
+                     'peak_source': pk['source'] + '; TF32 peak taken as bf16 burst / 2'}
+        train = {'questions_per_sec': world * B * k_tr / (tms * 1e-3), 'kernel_us': acc,
+                 'roofline': troof,
                  'ms_per_step': tms / k_tr, 'steps': k_tr, 'global_batch': B * world,
                  'T_decoder': T_TRAIN, 'last_avg_sample_loss': float(out['avg_sample_loss']),
                  'what': 'fwd + bwd + all-reduce(flat grads, %d floats) + per-tensor clip + Adam '

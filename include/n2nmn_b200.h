@@ -174,6 +174,9 @@ typedef struct n2nmn_sched_info {
    * [0] text projection kernel, [1] conv_image contraction kernel, [2] node kernel(s) */
   int64_t kernel_bytes[3];
   int64_t kernel_flops[3];
+  /* training schedules: 2 * (B maps) * HW * Dk * map_dim, the weight-gradient contraction of the
+   * feature-side layers (xtb_mma_kernel<FeatGradSrc>); 0 otherwise */
+  int64_t bwd_gemm_flops;
 } n2nmn_sched_info;
 int n2nmn_sched_get_info(const n2nmn_sched* sched, n2nmn_sched_info* info);
 /* Node table in (question, token) order: op, time_idx, batch_idx, depth, in0, in1 (node ids or

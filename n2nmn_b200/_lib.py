@@ -34,7 +34,8 @@ class SchedInfo(C.Structure):
         'num_questions', 'num_valid', 'num_nodes', 'max_depth', 'num_text_nodes',
         'num_find_nodes', 'num_proj_tiles', 'num_launches')] + [
         ('algorithmic_bytes', C.c_int64), ('algorithmic_flops', C.c_int64),
-        ('kernel_bytes', C.c_int64 * 3), ('kernel_flops', C.c_int64 * 3)]
+        ('kernel_bytes', C.c_int64 * 3), ('kernel_flops', C.c_int64 * 3),
+        ('bwd_gemm_flops', C.c_int64)]
 
 
 # every symbol declared in include/n2nmn_b200.h: name -> (restype, argtypes)

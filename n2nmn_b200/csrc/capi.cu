@@ -1094,6 +1094,8 @@ int n2nmn_sched_get_info(const n2nmn_sched* s, n2nmn_sched_info* info) {
   info->algorithmic_bytes = S.per_node_bytes;
   info->algorithmic_flops = S.per_node_flops;
   for (int k = 0; k < 3; ++k) { info->kernel_bytes[k] = S.kbytes[k]; info->kernel_flops[k] = S.kflops[k]; }
+  info->bwd_gemm_flops = S.train ? 2ll * (int64_t)S.entries.size() * s->shp.H * s->shp.W *
+                                       s->shp.Dk * s->shp.M : 0;
   return 0;
 }
 
@@ -1483,6 +1485,7 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
                                            d_qptr, N, C, invalid_expr_loss, c->dscores,
                                            loss_dev + 1, loss_dev);
   ++c->launches;
+  prof_mark(c, "loss_kernel", st);
   // ---- reverse tree walk
   BwdCtx bc;
   bc.md = c->md; bc.tb = c->tb; bc.arena = c->arena; bc.scores = scores_dev;
@@ -1516,6 +1519,7 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
     }
     ++c->launches;
   }
+  prof_mark(c, "tree_bwd_kernel", st);
   // ---- text layers
   const int rows = (int)S.text_t.size();
   if (rows > 0) {
@@ -1548,6 +1552,7 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
       }
       ++c->launches;
     }
+    prof_mark(c, "text_grad_kernels", st);
   }
   // ---- feature-side layers: dW_set = Σ X^T·B
   const int ne = (int)S.entries.size();
@@ -1570,6 +1575,7 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
       xtb_mma_kernel<FeatGradSrc><<<g2, kXtbThreads, kXtbSmemBytes, st>>>(fs, per);
     }
     ++c->launches;
+    prof_mark(c, "feat_grad_kernel", st);
   }
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -1603,7 +1609,10 @@ int adam_impl(n2nmn_ctx* c, float* wflat, float* gflat, float* m, float* v, int 
                                          beta1, beta2, eps, max_norm, c->d_repack, c->wbuf, c->Mp);
   c->launches += 2;
   CUDA_TRY(cudaGetLastError());
-  return repack_derived(c, wflat, st);
+  prof_mark(c, "clip_adam_kernels", st);
+  const int rc = repack_derived(c, wflat, st);
+  prof_mark(c, "repack_kernels", st);
+  return rc;
 }
 }  // namespace
 
