@@ -365,8 +365,13 @@ typedef struct n2nmn_seq2seq_config {
   int32_t T_decoder;       /* decoding steps (fixed, as in the reference) */
   int32_t max_batch;
   int32_t device;
-  int32_t flags;           /* 0 */
+  int32_t flags;           /* N2NMN_SEQ2SEQ_FLAG_* */
 } n2nmn_seq2seq_config;
+/* LSTM / attention-query / h-transform products as ONE TF32 pass (operands rounded to 10-bit
+ * mantissas, fp32 accumulate) instead of the default error-compensated three passes (fp32
+ * parity). ~1e-3-level differences in probabilities; a decoded token can differ from the fp32
+ * result when two scores are within that distance. */
+#define N2NMN_SEQ2SEQ_FLAG_TF32 1
 
 int n2nmn_seq2seq_create(const n2nmn_seq2seq_config* cfg, n2nmn_seq2seq** out);
 int n2nmn_seq2seq_destroy(n2nmn_seq2seq* s);

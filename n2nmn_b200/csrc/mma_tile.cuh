@@ -60,7 +60,9 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 // valid in the warps with kh == 0 (returns true there) after the call.
 // after_wait(): called once griddepcontrol.wait has returned and the first A chunks are in
 // flight — the place to start the loads the epilogue will need.
-template <int WM, class AfterWait>
+// kExact = true: three products per fragment pair (fp32 parity); false: one TF32 product with the
+// operands rounded to nearest (add half an ulp; the tensor core drops the low 13 bits).
+template <int WM, bool kExact = true, class AfterWait>
 __device__ __forceinline__ bool mma_tile(float* smem, const GemmOperands& p, int row0, int c0,
                                          float (&acc)[4][4], AfterWait after_wait) {
   constexpr int KH = 8 / WM, ROWS = 16 * WM, KW = kMmaKC / KH;   // k extent per warp per chunk
@@ -116,19 +118,30 @@ __device__ __forceinline__ bool mma_tile(float* smem, const GemmOperands& p, int
 #pragma unroll 2
     for (int ks = 0; ks < KW / 8; ++ks) {
       const int kb = kh * KW + ks * 8;
-      uint32_t ah[4], al[4];
-      split_trunc(As[kb + tig], ah[0], al[0]);
-      split_trunc(As[8 * kMmaAPitch + kb + tig], ah[1], al[1]);
-      split_trunc(As[kb + tig + 4], ah[2], al[2]);
-      split_trunc(As[8 * kMmaAPitch + kb + tig + 4], ah[3], al[3]);
+      if constexpr (kExact) {
+        uint32_t ah[4], al[4];
+        split_trunc(As[kb + tig], ah[0], al[0]);
+        split_trunc(As[8 * kMmaAPitch + kb + tig], ah[1], al[1]);
+        split_trunc(As[kb + tig + 4], ah[2], al[2]);
+        split_trunc(As[8 * kMmaAPitch + kb + tig + 4], ah[3], al[3]);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        uint32_t bh0, bl0, bh1, bl1;
-        split_trunc(Bs[(kb + tig) * kMmaBPitch + nt * 8], bh0, bl0);
-        split_trunc(Bs[(kb + tig + 4) * kMmaBPitch + nt * 8], bh1, bl1);
-        mma_tf32(acc[nt], al, bh0, bh1);
-        mma_tf32(acc[nt], ah, bl0, bl1);
-        mma_tf32(acc[nt], ah, bh0, bh1);
+        for (int nt = 0; nt < 4; ++nt) {
+          uint32_t bh0, bl0, bh1, bl1;
+          split_trunc(Bs[(kb + tig) * kMmaBPitch + nt * 8], bh0, bl0);
+          split_trunc(Bs[(kb + tig + 4) * kMmaBPitch + nt * 8], bh1, bl1);
+          mma_tf32(acc[nt], al, bh0, bh1);
+          mma_tf32(acc[nt], ah, bl0, bl1);
+          mma_tf32(acc[nt], ah, bh0, bh1);
+        }
+      } else {
+        const uint32_t a[4] = {__float_as_uint(As[kb + tig]) + 0x1000u,
+                               __float_as_uint(As[8 * kMmaAPitch + kb + tig]) + 0x1000u,
+                               __float_as_uint(As[kb + tig + 4]) + 0x1000u,
+                               __float_as_uint(As[8 * kMmaAPitch + kb + tig + 4]) + 0x1000u};
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+          mma_tf32(acc[nt], a, __float_as_uint(Bs[(kb + tig) * kMmaBPitch + nt * 8]) + 0x1000u,
+                   __float_as_uint(Bs[(kb + tig + 4) * kMmaBPitch + nt * 8]) + 0x1000u);
       }
     }
   }

@@ -80,14 +80,14 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
 }
 
 // out[r][c] = Σ_k A[r][k] B[k][c] + bias[c];  grid = (ceil(C/32), ceil(R/(16 WM)))
-template <int WM>
+template <int WM, bool kExact>
 __global__ void __launch_bounds__(kMmaThreads)
 s2s_gemm_kernel(GemmOperands p, const float* __restrict__ bias, float* __restrict__ out, int ldo) {
   pdl_trigger();
   extern __shared__ __align__(16) float mma_smem[];
   const int row0 = blockIdx.y * 16 * WM, c0 = blockIdx.x * kMmaCols;
   float acc[4][4];
-  if (!mma_tile<WM>(mma_smem, p, row0, c0, acc, [] {})) return;
+  if (!mma_tile<WM, kExact>(mma_smem, p, row0, c0, acc, [] {})) return;
   const int lane = threadIdx.x & 31, wm = (threadIdx.x >> 5) % WM, g = lane >> 2, tig = lane & 3;
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
@@ -121,7 +121,7 @@ struct LstmStep {
 // sequence end the state is carried through and the output is zero (nmn3_netgen_att.py:95-99).
 // grid = (4L/32, ceil(N/(16 WM))): one CTA = 8 units x 64 (WM = 4) or 32 (WM = 2) questions; the
 // narrow variant is used while it is what it takes to put a CTA on most SMs (N <= 64 at L = 512).
-template <int WM>
+template <int WM, bool kExact>
 __global__ void __launch_bounds__(kMmaThreads) lstm_step_kernel(LstmStep p) {
   pdl_trigger();
   extern __shared__ __align__(16) float mma_smem[];
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kMmaThreads) lstm_step_kernel(LstmStep p) {
       h_keep[hh][0] = hp.x; h_keep[hh][1] = hp.y;
     }
   };
-  if (!mma_tile<WM>(mma_smem, op, row0, c0, acc, prefetch)) return;
+  if (!mma_tile<WM, kExact>(mma_smem, op, row0, c0, acc, prefetch)) return;
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
     const int n = row0 + wm * 16 + g + 8 * hh;
@@ -492,17 +492,20 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 bool narrow_tiles(int col_blocks, int R) { return R > 16 && col_blocks * ((R + 63) / 64) < 148; }
 
 int launch_gemm(n2nmn_seq2seq* s, cudaStream_t st, const float* A, int lda, int R, int K,
-                const float* B, int ldb, int C, const float* bias, float* out, int ldo) {
+                const float* B, int ldb, int C, const float* bias, float* out, int ldo,
+                bool force_exact = false) {
   GemmOperands op;
   op.a0 = A; op.k0 = K; op.lda0 = lda; op.a1 = nullptr; op.k1 = 0; op.lda1 = 0;
   op.R = R; op.B = B; op.ldb = ldb; op.C = C;
   const int cb = (C + kMmaCols - 1) / kMmaCols;
+  const bool exact = !(s->cfg.flags & N2NMN_SEQ2SEQ_FLAG_TF32) || force_exact;
+  const dim3 gn(cb, (R + 31) / 32), gw(cb, (R + 63) / 64), blk(kMmaThreads);
   if (narrow_tiles(cb, R)) {
-    S2S_TRY(launch_pdl(s2s_gemm_kernel<2>, dim3(cb, (R + 31) / 32), dim3(kMmaThreads),
-                       mma_smem_bytes(2), st, op, bias, out, ldo));
+    if (exact) S2S_TRY(launch_pdl(s2s_gemm_kernel<2, true>, gn, blk, mma_smem_bytes(2), st, op, bias, out, ldo));
+    else S2S_TRY(launch_pdl(s2s_gemm_kernel<2, false>, gn, blk, mma_smem_bytes(2), st, op, bias, out, ldo));
   } else {
-    S2S_TRY(launch_pdl(s2s_gemm_kernel<4>, dim3(cb, (R + 63) / 64), dim3(kMmaThreads),
-                       mma_smem_bytes(4), st, op, bias, out, ldo));
+    if (exact) S2S_TRY(launch_pdl(s2s_gemm_kernel<4, true>, gw, blk, mma_smem_bytes(4), st, op, bias, out, ldo));
+    else S2S_TRY(launch_pdl(s2s_gemm_kernel<4, false>, gw, blk, mma_smem_bytes(4), st, op, bias, out, ldo));
   }
   ++s->launches;
   return N2NMN_OK;
@@ -536,10 +539,10 @@ int prepare(n2nmn_seq2seq* s, cudaStream_t st) {
                           s->v("decoder/go_embedding"), sizeof(float) * g.embed_dim_nmn,
                           cudaMemcpyDeviceToDevice, st));
   int rc = launch_gemm(s, st, s->v("encoder/embedding_mat"), g.embed_dim_txt, g.num_vocab_txt,
-                       g.embed_dim_txt, s->w_cell[0][0], C, C, nullptr, s->table_enc, C);
+                       g.embed_dim_txt, s->w_cell[0][0], C, C, nullptr, s->table_enc, C, true);
   if (rc) return rc;
   rc = launch_gemm(s, st, s->dec_rows, g.embed_dim_nmn, g.num_vocab_nmn + 1, g.embed_dim_nmn,
-                   s->w_cell[1][0], C, C, nullptr, s->table_dec, C);
+                   s->w_cell[1][0], C, C, nullptr, s->table_dec, C, true);
   if (rc) return rc;
   transpose_kernel<<<64, 256, 0, st>>>(s->v("decoder/token_prediction/weights"), s->wy_t, 2 * L,
                                        g.num_vocab_nmn);
@@ -628,14 +631,17 @@ int n2nmn_seq2seq_create(const n2nmn_seq2seq_config* cfg, n2nmn_seq2seq** out) {
   S2S_TRY(dmalloc(&s->P, (size_t)Vn * 3));
   S2S_TRY(dmalloc(&s->W, (size_t)3 * Vn * 4));
   S2S_TRY(dmalloc(&s->b, (size_t)Vn * 4));
-  S2S_TRY(cudaFuncSetAttribute(s2s_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)mma_smem_bytes(2)));
-  S2S_TRY(cudaFuncSetAttribute(s2s_gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)mma_smem_bytes(4)));
-  S2S_TRY(cudaFuncSetAttribute(lstm_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)mma_smem_bytes(2)));
-  S2S_TRY(cudaFuncSetAttribute(lstm_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)mma_smem_bytes(4)));
+  auto opt_in = [](auto kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  };
+  S2S_TRY(opt_in(s2s_gemm_kernel<2, true>, mma_smem_bytes(2)));
+  S2S_TRY(opt_in(s2s_gemm_kernel<2, false>, mma_smem_bytes(2)));
+  S2S_TRY(opt_in(s2s_gemm_kernel<4, true>, mma_smem_bytes(4)));
+  S2S_TRY(opt_in(s2s_gemm_kernel<4, false>, mma_smem_bytes(4)));
+  S2S_TRY(opt_in(lstm_step_kernel<2, true>, mma_smem_bytes(2)));
+  S2S_TRY(opt_in(lstm_step_kernel<2, false>, mma_smem_bytes(2)));
+  S2S_TRY(opt_in(lstm_step_kernel<4, true>, mma_smem_bytes(4)));
+  S2S_TRY(opt_in(lstm_step_kernel<4, false>, mma_smem_bytes(4)));
   const size_t attn_bytes = attn_smem_floats(L, cfg->T_encoder, Vn) * sizeof(float);
   if (attn_bytes > 200 * 1024)
     return fail_with(N2NMN_ERR_ARG, "num_vocab_nmn * lstm_dim too large for the decoder step kernel");
@@ -729,6 +735,7 @@ int n2nmn_seq2seq_forward(n2nmn_seq2seq* s, const int32_t* input_seq_dev,
   const dim3 grid(C / kMmaCols, narrow ? (N + 31) / 32 : (N + 63) / 64);
   int cur = 0;   // h[l][cur] holds every layer's h_{t-1}
   bool ok = true;
+  const bool exact = !(g.flags & N2NMN_SEQ2SEQ_FLAG_TF32);
   auto step = [&](int side, int t, const int32_t* tok, const int32_t* seq_len, float* out_seq) {
     for (int l = 0; l < NL; ++l) {
       const int in = l == 0 ? (side == 0 ? Et : En) : L;
@@ -744,10 +751,12 @@ int n2nmn_seq2seq_forward(n2nmn_seq2seq* s, const int32_t* input_seq_dev,
       p.out_seq = l == NL - 1 ? out_seq : nullptr;
       p.seq_len = seq_len;
       p.t = t; p.N = N; p.L = L;
-      if ((narrow ? launch_pdl(lstm_step_kernel<2>, grid, dim3(kMmaThreads), mma_smem_bytes(2), st, p)
-                  : launch_pdl(lstm_step_kernel<4>, grid, dim3(kMmaThreads), mma_smem_bytes(4), st, p)) !=
-          cudaSuccess)
-        ok = false;
+      cudaError_t le;
+      if (exact) le = narrow ? launch_pdl(lstm_step_kernel<2, true>, grid, dim3(kMmaThreads), mma_smem_bytes(2), st, p)
+                             : launch_pdl(lstm_step_kernel<4, true>, grid, dim3(kMmaThreads), mma_smem_bytes(4), st, p);
+      else le = narrow ? launch_pdl(lstm_step_kernel<2, false>, grid, dim3(kMmaThreads), mma_smem_bytes(2), st, p)
+                       : launch_pdl(lstm_step_kernel<4, false>, grid, dim3(kMmaThreads), mma_smem_bytes(4), st, p);
+      if (le != cudaSuccess) ok = false;
       ++s->launches;
     }
     cur ^= 1;

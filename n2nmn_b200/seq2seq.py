@@ -9,6 +9,11 @@ attribute names after a forward are the reference's: ``predicted_tokens`` [T_dec
 ``token_probs`` [T_decoder, N], ``neg_entropy`` [N], ``word_vecs`` [T_decoder, N, embed_dim_txt],
 ``atts`` [T_decoder, T_encoder, N, 1]; ``log_seq_prob`` as nmn3_model.py:45 computes it.
 PyTorch only owns the device buffers; there is no CPU path.
+
+`precision='fp32'` (default): every matrix product with fp32 parity (error-compensated TF32 on the
+tensor cores); `'tf32'`: one TF32 pass (13 % faster at batch 64, where the step is latency bound),
+probabilities within ~1e-3, a token may
+differ when two scores are that close.
 """
 from __future__ import annotations
 
@@ -26,7 +31,7 @@ class AttentionSeq2Seq:
                  num_vocab_nmn, embed_dim_nmn, lstm_dim, num_layers, assembler,
                  encoder_dropout=False, decoder_dropout=False, decoder_sampling=False,
                  use_gt_layout=None, gt_layout_batch=None, scope='encoder_decoder', reuse=None,
-                 T_encoder=None, max_batch=None, device=None, weights=None):
+                 T_encoder=None, max_batch=None, device=None, weights=None, precision='fp32'):
         if encoder_dropout or decoder_dropout:
             raise NotImplementedError('dropout is a training-time option; the B200 seq2seq is the '
                                       'inference configuration')
@@ -53,7 +58,7 @@ class AttentionSeq2Seq:
         cfg = _lib.Seq2SeqConfig(_lib.ABI_VERSION, self.encoder_num_vocab, self.encoder_embed_dim,
                                  self.decoder_num_vocab, self.decoder_embed_dim, self.lstm_dim,
                                  self.num_layers, self.T_encoder, self.T_decoder, self.max_batch,
-                                 self.device.index or 0, 0)
+                                 self.device.index or 0, {'fp32': 0, 'tf32': 1}[precision])
         h = C.c_void_p()
         check(self._L.n2nmn_seq2seq_create(C.byref(cfg), C.byref(h)))
         self._h = h

@@ -27,10 +27,11 @@ def golden_weights():
     return {k[2 + len('encoder_decoder/'):]: Z[k] for k in Z.files if k.startswith('w:')}
 
 
-def make(asm, w, T_enc, N, T_dec, V_txt, E_txt, E_nmn, L, layers):
+def make(asm, w, T_enc, N, T_dec, V_txt, E_txt, E_nmn, L, layers, precision='fp32'):
     from n2nmn_b200.seq2seq import AttentionSeq2Seq
     return AttentionSeq2Seq(None, None, T_dec, V_txt, E_txt, asm.num_vocab_nmn, E_nmn, L, layers,
-                            asm, T_encoder=T_enc, max_batch=N, weights=w, device='cuda:0')
+                            asm, T_encoder=T_enc, max_batch=N, weights=w, device='cuda:0',
+                            precision=precision)
 
 
 def check(out, tokens, probs, nent, wv, atts, atol=ATOL):
@@ -83,6 +84,30 @@ def test_matches_oracle_at_reference_sizes(N, T_enc, T_dec, L, layers):
                     gt_layout=gt)
     out = s.forward(seq, lens, True, gt)
     check(out, *dec)
+
+
+def test_single_pass_tf32_option_stays_within_1e_3():
+    """precision='tf32' (one TF32 pass per product): teacher-forced probabilities, attention maps
+    and word vectors within 2e-3 of the fp32 oracle at the CLEVR sizes; greedy tokens agree on
+    >= 97 % of the positions (a flip needs two scores within the TF32 error)."""
+    N, T_enc, T_dec, L, layers = 64, 45, 20, 512, 2
+    rng = np.random.RandomState(77)
+    asm = Assembler(synth.vocab_file('clevr'))
+    V_nmn, V_txt, E = asm.num_vocab_nmn, 90, 300
+    w = init_seq2seq_weights(V_txt, E, V_nmn, E, L, layers, seed=5)
+    seq = rng.randint(0, V_txt, size=(T_enc, N)).astype(np.int32)
+    lens = rng.randint(3, T_enc + 1, size=N).astype(np.int32)
+    s = make(asm, w, T_enc, N, T_dec, V_txt, E, E, L, layers, precision='tf32')
+    _, dec = so.run(w, seq, lens, T_dec, layers, asm.P, asm.W, asm.b)
+    out = s.forward(seq, lens)
+    torch.cuda.synchronize()
+    agree = float((out[0].cpu().numpy() == dec[0]).mean())
+    assert agree >= 0.97, agree
+    assert asm.assemble(out[0].cpu().numpy())[1].all()
+    _, decf = so.run(w, seq, lens, T_dec, layers, asm.P, asm.W, asm.b, use_gt_layout=True,
+                     gt_layout=dec[0])
+    out = s.forward(seq, lens, True, dec[0])
+    check(out, *decf, atol=2e-3)
 
 
 def test_errors_are_loud():

@@ -12,7 +12,8 @@ asm = Assembler(synth.vocab_file('clevr'))
 rng = np.random.RandomState(0)
 w = init_seq2seq_weights(V_txt, E, asm.num_vocab_nmn, E, L, layers)
 s = AttentionSeq2Seq(None, None, T_dec, V_txt, E, asm.num_vocab_nmn, E, L, layers, asm,
-                     T_encoder=T_enc, max_batch=N, weights=w, device='cuda:0')
+                     T_encoder=T_enc, max_batch=N, weights=w, device='cuda:0',
+                     precision='tf32' if '--tf32' in sys.argv else 'fp32')
 seq = torch.from_numpy(rng.randint(0, V_txt, size=(T_enc, N)).astype(np.int32)).cuda()
 lens = torch.from_numpy(rng.randint(5, T_enc + 1, size=N).astype(np.int32)).cuda()
 for _ in range(5):
