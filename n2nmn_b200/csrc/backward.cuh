@@ -3,18 +3,22 @@
 // w.r.t. word_vecs, following TF 1.0's registered gradients (ties of tf.minimum/maximum go to
 // input_0; reduce_min/max split ties equally; l2_normalize takes the constant branch below eps).
 //
-// Structure (the forward got the tuning; here only the measured hot spots were restructured — see
-// the notes at the Find pixel loop, the stencil's butterfly and feat_grad_kernel):
+// Structure (DESIGN.md §4b has the measured history):
 //   loss_kernel      : softmax cross-entropy, validity select, d(loss)/d(scores)
-//   tree_bwd_kernel  : one CTA per question walks its nodes in REVERSE Reverse-Polish order with
-//                      the gradient maps in shared memory; recomputes each module's forward
+//   tree_bwd_kernel  : reverse walk, ONE CTA PER NODE and one launch per depth level from the
+//                      roots down; gradient maps travel through a global [nodes][HW] buffer (a map
+//                      has one consumer, so one writer); recomputes each module's forward
 //                      intermediates from the saved attention maps / stored tensor-core maps and
 //                      emits (a) small weight gradients by atomics, (b) d(tau) per text row,
 //                      (c) one [HW, Mp] "B map" per feature-side layer use (dm for conv_image,
-//                      s_p*dphi for the fc_att layers)
-//   text_bwd_kernel  : d(fc_text weights) = Σ t^T dtau, d(word_vecs) = dtau · W^T
-//   feat_grad_kernel : d(W_set) = Σ_entries X_b^T · B_entry, d(b_set) = Σ rows of B  (every
-//                      feature-side layer is "X·W + b" per image, so they all share this GEMM)
+//                      s_p*dphi for the fc_att layers). Nodes with independent per-pixel work are
+//                      split over several CTAs by pixel ranges.
+//   xtb_mma_kernel   : C[k,c] += Σ_p X[p,k]·B[p,c] on mma.sync TF32 fragments: the weight gradient
+//                      of every "X·W + b" layer — d(W_set) = Σ_entries X_b^T · B_entry for the
+//                      feature-side layers, d(fc_text W) = Σ t^T dtau for the text layers
+//   text_xgrad_mma_kernel : d(word_vecs) = dtau · W^T
+//   feat_grad_kernel / text_wgrad_kernel / text_xgrad_kernel : the same three products in exact
+//                      fp32 on the CUDA cores (verification path, N2NMN_FLAG_PROJ_FP32_SIMT)
 //   adam kernels     : weight decay, per-tensor clip_by_norm, Adam (train_clevr_rl_gt_layout.py:
 //                      126-139)
 #pragma once
@@ -738,109 +742,6 @@ feat_grad_kernel(DevModel md, const float* __restrict__ dmap, const BwdEntry* __
       if (ty == 0)
 #pragma unroll
         for (int j = 0; j < 4; ++j) bsum[j] += bv[j];
-    }
-  }
-  flush(cur_set);
-}
-
-// Same contraction on the tensor cores (TF32 mma.sync fragments, fp32 accumulate): the default; the
-// CUDA-core kernel above is the exact-fp32 verification path. One CTA = a 64 (features) x 64
-// (channels) tile of dW; warp w owns the 16-feature row block w%4 and the four 8-channel column
-// blocks of half w/4. Operands are rounded to TF32 when they are written to shared memory; the bias
-// gradient (column sums of B) is accumulated from the unrounded values in registers.
-__device__ __forceinline__ float fg_round_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-constexpr int kFgPitch = kFgTile + 8;   // 72: (8t + g) mod 32 is a bijection -> conflict-free frags
-__global__ void __launch_bounds__(256)
-feat_grad_mma_kernel(DevModel md, const float* __restrict__ dmap,
-                     const BwdEntry* __restrict__ entries, int num_entries, int entries_per_cta,
-                     float* __restrict__ gflat, GradOffsets go) {
-  __shared__ __align__(16) float xs[kFgRows][kFgPitch];
-  __shared__ __align__(16) float bs[kFgRows][kFgPitch];
-  const int k0 = blockIdx.x * kFgTile, c0 = blockIdx.y * kFgTile;
-  const int e0 = blockIdx.z * entries_per_cta, e1 = min(num_entries, e0 + entries_per_cta);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane >> 2, t = lane & 3, mi = warp & 3, half = warp >> 2;
-  const int HW = md.HW, Mp = md.Mp, M = md.M, Dk = md.Dk;
-  int cur_set = -1;
-  float acc[4][4], bsum = 0.f;
-  auto flush = [&](int set) {
-    if (set < 0) return;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int k = k0 + mi * 16 + g + ((i & 2) ? 8 : 0);
-        const int ch = c0 + (half * 4 + j) * 8 + 2 * t + (i & 1);
-        if (k < Dk && ch < M && acc[j][i] != 0.f)
-          atomicAdd(gflat + go.proj_w[set] + (size_t)k * M + ch, acc[j][i]);
-      }
-    const int ch = c0 + (threadIdx.x & (kFgTile - 1));
-    if (blockIdx.x == 0 && ch < M && bsum != 0.f) atomicAdd(gflat + go.proj_b[set] + ch, bsum);
-  };
-  constexpr int kPer = kFgRows * kFgTile / 256;   // 8 elements of each operand per thread
-  const int chunks_per_entry = (HW + kFgRows - 1) / kFgRows;
-  const int n_steps = (e1 - e0) * chunks_per_entry;
-  float xr[kPer], br[kPer];
-  auto fetch = [&](int step) {
-    const int e = e0 + step / chunks_per_entry, p0 = (step % chunks_per_entry) * kFgRows;
-    const float* X = md.feat + (size_t)entries[e].b * HW * md.feat_pitch;
-    const float* B = dmap + (size_t)e * HW * Mp;
-#pragma unroll
-    for (int u = 0; u < kPer; ++u) {
-      const int idx = threadIdx.x + u * 256;
-      const int r = idx / kFgTile, cc = idx - r * kFgTile, p = p0 + r;
-      xr[u] = (p < HW && k0 + cc < Dk) ? X[(size_t)p * md.feat_pitch + k0 + cc] : 0.f;
-      br[u] = (p < HW && c0 + cc < Mp) ? B[(size_t)p * Mp + c0 + cc] : 0.f;
-    }
-  };
-  if (n_steps > 0) fetch(0);
-  for (int step = 0; step < n_steps; ++step) {
-    const int e = e0 + step / chunks_per_entry;
-    if (step % chunks_per_entry == 0) {
-      const int set = entries[e].set;
-      if (set != cur_set) {
-        flush(cur_set);
-        cur_set = set;
-        bsum = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
-      }
-    }
-    __syncthreads();   // the previous step's readers are done with xs / bs
-#pragma unroll
-    for (int u = 0; u < kPer; ++u) {
-      const int idx = threadIdx.x + u * 256;
-      const int r = idx / kFgTile, cc = idx - r * kFgTile;
-      xs[r][cc] = fg_round_tf32(xr[u]);
-      bs[r][cc] = fg_round_tf32(br[u]);
-      bsum += br[u];   // this thread always holds column threadIdx.x % 64
-    }
-    __syncthreads();
-    if (step + 1 < n_steps) fetch(step + 1);
-#pragma unroll
-    for (int ks = 0; ks < kFgRows / 8; ++ks) {
-      uint32_t a[4];
-      a[0] = __float_as_uint(xs[8 * ks + t][mi * 16 + g]);
-      a[1] = __float_as_uint(xs[8 * ks + t][mi * 16 + g + 8]);
-      a[2] = __float_as_uint(xs[8 * ks + t + 4][mi * 16 + g]);
-      a[3] = __float_as_uint(xs[8 * ks + t + 4][mi * 16 + g + 8]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int n0 = (half * 4 + j) * 8;
-        const uint32_t b0 = __float_as_uint(bs[8 * ks + t][n0 + g]);
-        const uint32_t b1 = __float_as_uint(bs[8 * ks + t + 4][n0 + g]);
-        asm volatile(
-            "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
-            "{%8,%9}, {%0,%1,%2,%3};"
-            : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])
-            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-      }
     }
   }
   flush(cur_set);
