@@ -379,11 +379,10 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
   auto pdl_ok = [&]() { return c->use_pdl; };
   // ---- K1 text projections (+ the quadratic-form coefficients of the Transform nodes)
   if (!S.groups.empty()) {
-    dim3 grid((unsigned)(c->Mp / kTextCols), (unsigned)S.groups.size());
+    dim3 grid((unsigned)(c->Mp / kMmaCols), (unsigned)S.groups.size());
     TextSetRows tsr;
     for (int i = 0; i <= NUM_TEXT_SETS; ++i) tsr.start[i] = S.text_set_start[i];
-    const size_t tsm = (size_t)tile_smem_floats(c->cfg.text_dim) * sizeof(float) + 64 * sizeof(void*);
-    text_proj_kernel<<<grid, kTileThreads, tsm, st>>>(
+    text_proj_kernel<<<grid, kMmaThreads, mma_smem_bytes(4, kTextStages), st>>>(
         c->md, c->tb, tsr,
         reinterpret_cast<const int32_t*>(d + o.text_t),
         reinterpret_cast<const int32_t*>(d + o.text_b));
@@ -394,10 +393,10 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
     if (trn > 0 && c->conv_quad) {
       cudaLaunchConfig_t qc;
       std::memset(&qc, 0, sizeof(qc));
-      qc.gridDim = dim3((unsigned)((quad_pitch(c->cfg.kernel_size) + kTextCols - 1) / kTextCols),
-                        (unsigned)((trn + kTileRows - 1) / kTileRows));
-      qc.blockDim = dim3(kTileThreads);
-      qc.dynamicSmemBytes = (size_t)tile_smem_floats(c->Mp) * sizeof(float) + 64 * sizeof(void*);
+      const int qcols = quad_pitch(c->cfg.kernel_size) - quad_u_pitch(c->cfg.kernel_size);
+      qc.gridDim = dim3((unsigned)(1 + (qcols + kMmaCols - 1) / kMmaCols), (unsigned)((trn + 63) / 64));
+      qc.blockDim = dim3(kMmaThreads);
+      qc.dynamicSmemBytes = mma_smem_bytes(4, kTextStages);
       qc.stream = st;
       cudaLaunchAttribute qa[1];
       qa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -787,13 +786,14 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
   CUDA_TRY(cudaFuncSetAttribute(tree_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 c->tree_smem_bytes));
   {
-    const int tsm = tile_smem_floats(cfg->text_dim) * (int)sizeof(float) + 64 * (int)sizeof(void*);
-    const int qsm = tile_smem_floats(c->Mp) * (int)sizeof(float) + 64 * (int)sizeof(void*);
-    if (tsm > 220 * 1024 || (c->conv_quad && qsm > 220 * 1024))
-      return fail(N2NMN_ERR_ARG, "text_dim / map_dim too large for the text tile kernel");
-    CUDA_TRY(cudaFuncSetAttribute(text_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+    if (cfg->text_dim % 4 != 0)
+      return fail(N2NMN_ERR_ARG, "text_dim must be a multiple of 4 (16-byte word-vector rows)");
+    CUDA_TRY(cudaFuncSetAttribute(text_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)mma_smem_bytes(4, kTextStages)));
     CUDA_TRY(cudaFuncSetAttribute(quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  std::max(qsm, 48 * 1024)));
+                                  (int)mma_smem_bytes(4, kTextStages)));
+    CUDA_TRY(cudaFuncSetAttribute(text_proj_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_TRY(cudaFuncSetAttribute(quad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   }
   CUDA_TRY(cudaFuncSetAttribute(head_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 head_smem_layout(16, c->Kp, c->Mp).total * (int)sizeof(float) <=

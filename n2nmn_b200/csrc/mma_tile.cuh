@@ -31,8 +31,8 @@ __host__ __device__ constexpr int mma_stage_floats(int wm) {
   return 16 * wm * kMmaAPitch + kMmaKC * kMmaBPitch;
 }
 __host__ __device__ constexpr int mma_stages(int wm) { return wm == 2 ? N2NMN_S2S_STAGES_NARROW : 3; }
-__host__ __device__ constexpr size_t mma_smem_bytes(int wm) {
-  return (size_t)mma_stages(wm) * mma_stage_floats(wm) * sizeof(float);
+__host__ __device__ constexpr size_t mma_smem_bytes(int wm, int stages = 0) {
+  return (size_t)(stages > 0 ? stages : mma_stages(wm)) * mma_stage_floats(wm) * sizeof(float);
 }
 
 struct GemmOperands {
@@ -40,6 +40,9 @@ struct GemmOperands {
   const float* a1; int k1, lda1;   // A columns [k0, k0 + k1)  (k1 may be 0)
   int R;                           // valid rows
   const float* B; int ldb, C;      // B [k0 + k1][ldb], C valid columns
+  // gathered A (text projection): pointer to the K-contiguous data of each of the tile's rows
+  // (nullptr = a row of zeros), indexed by the row inside the tile; a0 / a1 / R are then unused
+  const float* const* a_rows = nullptr;
 };
 
 __device__ __forceinline__ void split_trunc(float x, uint32_t& hi, uint32_t& lo) {
@@ -62,11 +65,13 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 // flight — the place to start the loads the epilogue will need.
 // kExact = true: three products per fragment pair (fp32 parity); false: one TF32 product with the
 // operands rounded to nearest (add half an ulp; the tensor core drops the low 13 bits).
-template <int WM, bool kExact = true, class AfterWait>
+// ST = ring depth (default: mma_stages(WM)); short-K callers (text projection: 3 chunks) take 2
+// stages so that two CTAs share an SM. K-steps entirely beyond K are skipped.
+template <int WM, bool kExact = true, int ST = 0, class AfterWait>
 __device__ __forceinline__ bool mma_tile(float* smem, const GemmOperands& p, int row0, int c0,
                                          float (&acc)[4][4], AfterWait after_wait) {
   constexpr int KH = 8 / WM, ROWS = 16 * WM, KW = kMmaKC / KH;   // k extent per warp per chunk
-  constexpr int kMmaStageFloats = mma_stage_floats(WM), kMmaStages = mma_stages(WM);
+  constexpr int kMmaStageFloats = mma_stage_floats(WM), kMmaStages = ST > 0 ? ST : mma_stages(WM);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp % WM, kh = warp / WM, g = lane >> 2, tig = lane & 3;
   const int K = p.k0 + p.k1, nchunks = (K + kMmaKC - 1) / kMmaKC;
@@ -86,7 +91,11 @@ __device__ __forceinline__ bool mma_tile(float* smem, const GemmOperands& p, int
     for (int i = tid; i < ROWS * (kMmaKC / 4); i += kMmaThreads) {
       const int r = i >> 5, q = i & 31, k = kc0 + 4 * q, row = row0 + r;
       float* dst = As + r * kMmaAPitch + 4 * q;
-      if (row < p.R && k < K) {
+      if (p.a_rows != nullptr) {
+        const float* base = p.a_rows[r];
+        if (base != nullptr && k < K) tp_cp16(dst, base + k);
+        else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else if (row < p.R && k < K) {
         const float* src = k < p.k0 ? p.a0 + (size_t)row * p.lda0 + k
                                     : p.a1 + (size_t)row * p.lda1 + (k - p.k0);
         tp_cp16(dst, src);
@@ -118,6 +127,7 @@ __device__ __forceinline__ bool mma_tile(float* smem, const GemmOperands& p, int
 #pragma unroll 2
     for (int ks = 0; ks < KW / 8; ++ks) {
       const int kb = kh * KW + ks * 8;
+      if (c * kMmaKC + kb >= K) break;   // (zero-filled beyond K: nothing to add)
       if constexpr (kExact) {
         uint32_t ah[4], al[4];
         split_trunc(As[kb + tig], ah[0], al[0]);
