@@ -24,6 +24,7 @@
 #include "tree_kernel.cuh"
 #include "head_kernel.cuh"
 #include "backward.cuh"
+#include "wgrad_umma.cuh"
 
 using namespace n2nmn;
 
@@ -69,7 +70,7 @@ struct TableSlot {
 
 struct TableOffsets {
   size_t nodes, q_ptr, text_t, text_b, groups, work, img_ptr, node_text, node_out, mslot,
-      wave_nodes, bwd_nodes, node_entry, entries, text_set_start, labels, head_work, head_list, pool_img,
+      wave_nodes, bwd_nodes, entry_order, node_entry, entries, text_set_start, labels, head_work, head_list, pool_img,
       total;
 };
 
@@ -144,6 +145,8 @@ struct n2nmn_ctx {
   float* dstencil = nullptr;
   float* gmap = nullptr;
   float* phi_buf = nullptr;
+  WgradMaps wg_maps;                       // tcgen05 weight-gradient kernel (wgrad_umma.cuh)
+  bool wg_ok = false;                      // shapes fit it (Mp == 256, Dk % 128 == 0, no re-pitch)
   // many-class answer heads (C > 32): ê rows + score-row addresses of the roots of a launch, and
   // the fc_eltwise matrices with rows pitched to a multiple of 4 floats (cp.async alignment)
   float* ehat = nullptr;
@@ -269,6 +272,24 @@ int encode_2d(n2nmn_ctx* c, CUtensorMap* map, const float* base, uint64_t inner,
   return 0;
 }
 
+// (inner, mid, outer) fp32 tensor, box (box_inner, box_mid, 1), 128-byte swizzle with 32-byte
+// atoms (the MN-major operand layout of 4-byte tensor-core operands), zero fill.
+int encode_3d(n2nmn_ctx* c, CUtensorMap* map, const float* base, uint64_t inner, uint64_t mid,
+              uint64_t outer, uint64_t mid_pitch_elems, uint64_t outer_pitch_elems,
+              uint32_t box_inner, uint32_t box_mid) {
+  cuuint64_t dims[3] = {inner, mid, outer};
+  cuuint64_t strides[2] = {mid_pitch_elems * sizeof(float), outer_pitch_elems * sizeof(float)};
+  cuuint32_t box[3] = {box_inner, box_mid, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = c->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims,
+                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(N2NMN_ERR_CUDA, "cuTensorMapEncodeTiled (3d) failed with CUresult " + std::to_string(r));
+  return 0;
+}
+
 TableOffsets table_offsets(const HostSchedule& S) {
   TableOffsets o;
   size_t off = 0;
@@ -285,6 +306,7 @@ TableOffsets table_offsets(const HostSchedule& S) {
   o.mslot = take(S.mslot.size() * 4);
   o.wave_nodes = take(S.wave_nodes.size() * 4);
   o.bwd_nodes = take(S.bwd_nodes.size() * 4);
+  o.entry_order = take(S.entry_order.size() * 4);
   o.node_entry = take(S.node_entry.size() * 4);
   o.entries = take(S.entries.size() * sizeof(BwdEntryHost));
   o.text_set_start = take(S.text_set_start.size() * 4);
@@ -355,6 +377,7 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
     put(slot->host, o.mslot, S.mslot);
     put(slot->host, o.wave_nodes, S.wave_nodes);
     put(slot->host, o.bwd_nodes, S.bwd_nodes);
+    put(slot->host, o.entry_order, S.entry_order);
     put(slot->host, o.node_entry, S.node_entry);
     put(slot->host, o.entries, S.entries);
     put(slot->host, o.text_set_start, S.text_set_start);
@@ -757,7 +780,7 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
     const size_t tiles = (size_t)c->G * (((size_t)cfg->max_batch * c->HW + 127) / 128 + 1);
     c->table_cap = nodes * (sizeof(NodeRec) + 4 * 6) + (nodes / 8 + 8) * sizeof(TextGroup) +
                    tiles * (TT / kMaxProjNodesPerPass + 1 + NUM_PROJ_SETS) * sizeof(ProjWork) +
-                   (size_t)NB * (12 + 4 * NUM_PROJ_SETS) + nodes * (8 + 2 * sizeof(BwdEntryHost)) +
+                   (size_t)NB * (12 + 4 * NUM_PROJ_SETS) + nodes * (16 + 2 * sizeof(BwdEntryHost)) +
                    (size_t)NB * (4 + 8 + sizeof(HeadWork)) + 4096;
     for (int i = 0; i < kTableSlots; ++i) {
       CUDA_TRY(cudaMallocHost(&c->slots[i].host, c->table_cap));
@@ -1425,6 +1448,14 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
     CUDA_TRY(cudaMalloc(&c->dstencil, (size_t)c->dmap_entries * c->HW * c->Mp * sizeof(float)));
     CUDA_TRY(cudaMalloc(&c->gmap, (size_t)c->arena_slots * ((c->HW + 3) & ~3) * sizeof(float)));
     CUDA_TRY(cudaMalloc(&c->phi_buf, (size_t)NB * 2 * c->Mp * sizeof(float)));
+    c->wg_ok = c->Mp == kWgN && c->Dk % kWgM == 0 && !c->feat_aug;
+    if (c->wg_ok) {
+      if (int rc = encode_3d(c, &c->wg_maps.b, c->dmap, c->Mp, c->HW, c->dmap_entries, c->Mp,
+                             (uint64_t)c->HW * c->Mp, 32, kWgP))
+        return rc;
+      CUDA_TRY(cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)kWgSmemBytes));
+    }
     const BwdSmem L = bwd_smem_layout(c->cfg.H, c->cfg.W, c->Mp, c->cfg.kernel_size, C);
     const int bwd_smem = (int)(L.total * sizeof(float));
     CUDA_TRY(cudaFuncSetAttribute(tree_bwd_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem));
@@ -1457,6 +1488,10 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
     W.bwd_nodes.assign(W.nodes.size(), 0);
     std::vector<int32_t> fill(W.bwd_ptr.begin(), W.bwd_ptr.end() - 1);
     for (size_t i = 0; i < W.nodes.size(); ++i) W.bwd_nodes[fill[bucket(i)]++] = (int32_t)i;
+    W.entry_order.resize(W.entries.size());
+    for (size_t i = 0; i < W.entries.size(); ++i) W.entry_order[i] = (int32_t)i;
+    std::stable_sort(W.entry_order.begin(), W.entry_order.end(),
+                     [&](int32_t a, int32_t b) { return W.entries[a].set < W.entries[b].set; });
   }
   const HostSchedule& S = sc->hs;
   if (validity_out) std::memcpy(validity_out, S.validity.data(), N);
@@ -1564,6 +1599,23 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
       dim3 g2((c->Dk + kFgTile - 1) / kFgTile, (c->cfg.map_dim + kFgTile - 1) / kFgTile,
               (ne + per - 1) / per);
       feat_grad_kernel<<<g2, 256, 0, st>>>(c->md, c->dmap, d_ent, ne, per, gflat_dev, c->go);
+    } else if (c->wg_ok && !std::getenv("N2NMN_WGRAD_MMA_SYNC")) {
+      // tcgen05, both operands MN-major straight from the feature grid and the B maps
+      if (int rc = encode_3d(c, &c->wg_maps.x, c->md.feat, c->Dk, c->HW, N, c->md.feat_pitch,
+                             (uint64_t)c->HW * c->md.feat_pitch, 32, kWgP))
+        return rc;
+      const int slabs = c->Dk / kWgM;
+      const int chunks = std::max(1, std::min(ne, 148 / slabs));
+      WgradParams wp;
+      wp.entries = d_ent;
+      wp.order = reinterpret_cast<const int32_t*>(d + o.entry_order);
+      wp.num_entries = ne; wp.per_cta = (ne + chunks - 1) / chunks;
+      wp.HW = c->HW; wp.Dk = c->Dk; wp.M = c->cfg.map_dim; wp.gflat = gflat_dev; wp.go = c->go;
+      dim3 gw(slabs, (ne + wp.per_cta - 1) / wp.per_cta);
+      wgrad_umma_kernel<<<gw, kWgThreads, kWgSmemBytes, st>>>(c->wg_maps, wp);
+      bmap_colsum_kernel<<<ne, 256, 0, st>>>(c->dmap, d_ent, c->HW, c->cfg.map_dim, c->Mp, gflat_dev,
+                                             c->go);
+      ++c->launches;
     } else {
       // two CTAs per SM (106 KB of ring each): ~296 CTAs over (Dk/128) x (M/64) tiles
       const int tiles = ((c->Dk + kXtbM - 1) / kXtbM) * ((c->cfg.map_dim + kXtbN - 1) / kXtbN);

@@ -64,6 +64,31 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 3D tile load (box along dims 0..2 of the tensor map), same completion mechanism.
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1,
+                                            int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(smem_u32(bar))
+      : "memory");
+}
+// mbarrier wait that gives up: a protocol bug then ends in a trap (launch error) instead of a hung
+// GPU. Used by kernels under development and kept where the wait is not on the hot path.
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return;
+    if (spin > (1u << 24)) __trap();
+  }
+}
+
 // ---- TMEM -----------------------------------------------------------------------------------
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {  // whole warp
@@ -104,6 +129,29 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
        | (2u << 10)                              // B format: TF32
        | (static_cast<uint32_t>(N >> 3) << 17)   // N / 8
        | (static_cast<uint32_t>(M >> 4) << 24);  // M / 16
+}
+// MN-major operands (the contraction index is the SLOW one in memory: X[p][k], B[p][c] with p the
+// contraction). For 4-byte elements the only MN-major layout the tensor core accepts is
+// SWIZZLE_128B_BASE32B (layout type 1; cutlass sm100_common.inl: "for mn-major tf32 operands,
+// SW128_32B is the only available smem layout" — with the plain SWIZZLE_128B type the instruction
+// runs and returns zeros): 32-element (128-byte) runs along M/N, one run per K index, 4 K indices =
+// one 512-byte atom whose 32-byte chunks are XORed with the K index (Swizzle<2,5,2>); atoms of
+// successive K groups are SBO (512) apart, successive 32-element blocks along M/N are LBO apart.
+// A TMA box [K rows][32 elements] with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes exactly one
+// such block. Checked element by element with tools/exp/umma_mn_test.cu.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                            uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;                        // version
+  d |= static_cast<uint64_t>(1) << 61;                        // SWIZZLE_128B_BASE32B
+  return d;
+}
+// kind::tf32 instruction descriptor with A and B MN-major (bits 15 / 16).
+__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {
+  return make_idesc_tf32(M, N) | (1u << 15) | (1u << 16);
 }
 // D[tmem] (+)= A[smem] · B[smem]^T ; issued by one thread.
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,

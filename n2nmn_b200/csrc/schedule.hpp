@@ -46,6 +46,7 @@ struct HostSchedule {
   std::vector<int32_t> wave_ptr;      // [max_depth+2], wave d = [wave_ptr[d], wave_ptr[d+1])
   std::vector<int32_t> wave_nodes;
   std::vector<int32_t> bwd_ptr, bwd_nodes;   // training: ALL nodes bucketed by depth (capi.cu)
+  std::vector<int32_t> entry_order;          // training: B-map entries sorted by weight set
   // training schedules only: one [HW,Mp] gradient map per feature-side layer use
   bool train = false;
   std::vector<BwdEntryHost> entries;
@@ -66,7 +67,7 @@ struct HostSchedule {
     num_seg = 1;
     validity.clear(); nodes.clear(); depth.clear(); q_ptr.clear(); text_t.clear();
     text_b.clear(); groups.clear(); work.clear(); img_ptr.clear(); node_text.clear();
-    node_out.clear(); mslot.clear(); wave_ptr.clear(); wave_nodes.clear(); bwd_ptr.clear(); bwd_nodes.clear();
+    node_out.clear(); mslot.clear(); wave_ptr.clear(); wave_nodes.clear(); bwd_ptr.clear(); bwd_nodes.clear(); entry_order.clear();
     entries.clear(); node_entry.clear(); text_set_start.clear(); train = false;
     pooled_direct = false; num_pool_rows = 0; num_feat_rows = 0; head_work.clear();
     head_list.clear();

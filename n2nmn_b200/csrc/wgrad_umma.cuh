@@ -1,0 +1,212 @@
+// Weight gradient of the feature-side layers on the 5th-gen tensor cores:
+//   dW_set[k, c] += Σ_entries Σ_p X_b[p, k] · B_entry[p, c]        (backward.cuh, FeatGradSrc)
+// as tcgen05.mma kind::tf32 with BOTH operands MN-major: the contraction index p (pixels) is the
+// slow index of X [p][k] and of the B maps [p][c], which is exactly how the forward pass and the
+// reverse walk leave them in memory — no transposed copy of either. TMA boxes of 32 pixels x 32
+// elements (128 bytes, SWIZZLE_128B_ATOM_32B) are the canonical MN-major blocks of 4-byte
+// operands (ptx_sm100.cuh; the layout was established with tools/exp/umma_mn_test.cu); pixels
+// beyond H·W are zero-filled by the tensor maps (3-D: element, pixel, image / entry).
+//   CTA = one 128-feature slab of k x all 256 channels x a chunk of the entries (sorted by weight
+//   set by the host): M = 128, N = 256, K = 8 per instruction, 4 instructions per 32-pixel stage,
+//   4-stage ring of 48 KB; the accumulator (128 lanes x 256 fp32 columns of TMEM) is flushed with
+//   float2 reductions when the weight set changes and at the end.
+//   warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = flush.
+// Operands are the fp32 bits read as TF32 (as in the forward contraction); fp32 accumulate.
+#pragma once
+#include <cstdio>
+#include "backward.cuh"
+#include "ptx_sm100.cuh"
+
+namespace n2nmn {
+
+constexpr int kWgM = 128, kWgN = 256, kWgP = 32, kWgStages = 4, kWgThreads = 192;
+constexpr int kWgBlockBytes = kWgP * 128;                 // one [32 pixels][32 elements] box
+constexpr int kWgABytes = (kWgM / 32) * kWgBlockBytes;    // 16 KB
+constexpr int kWgBBytes = (kWgN / 32) * kWgBlockBytes;    // 32 KB
+constexpr int kWgStageBytes = kWgABytes + kWgBBytes;
+constexpr size_t kWgSmemBytes = (size_t)kWgStages * kWgStageBytes + 256;
+
+struct WgradMaps {
+  CUtensorMap x;   // features  (k: Dk, p: HW, image: N)      box (32, 32, 1)
+  CUtensorMap b;   // B maps    (c: Mp, p: HW, entry: E_cap)  box (32, 32, 1)
+};
+struct WgradParams {
+  const BwdEntry* entries;     // [num_entries] {set, image}
+  const int32_t* order;        // entry indices sorted by weight set
+  int num_entries, per_cta, HW, Dk, M;
+  float* gflat;
+  GradOffsets go;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_umma_kernel(const __grid_constant__ WgradMaps tm, const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t wg_smem[];
+  if ((ptx::smem_u32(wg_smem) & 1023u) != 0) __trap();
+  uint64_t* full = reinterpret_cast<uint64_t*>(wg_smem + kWgStages * kWgStageBytes);
+  uint64_t* empty = full + kWgStages;
+  uint64_t* tmem_full = empty + kWgStages;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * kWgM;
+  const int e0 = blockIdx.y * p.per_cta, e1 = min(p.num_entries, e0 + p.per_cta);
+  const int stages_per_entry = (p.HW + kWgP - 1) / kWgP;
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tensormap(&tm.x);
+    ptx::prefetch_tensormap(&tm.b);
+    for (int s = 0; s < kWgStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    ptx::mbar_init(tmem_full, 1);
+    ptx::mbar_init(tmem_empty, 4);    // one arrive per flush warp
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<kWgN>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================= TMA producer
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = e0; i < e1; ++i) {
+        const int e = p.order[i], img = p.entries[e].b;
+        for (int ps = 0; ps < stages_per_entry; ++ps) {
+          ptx::mbar_wait_bounded(&empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[stage], kWgStageBytes);
+          uint8_t* sa = wg_smem + stage * kWgStageBytes;
+          uint8_t* sb = sa + kWgABytes;
+          for (int j = 0; j < kWgM / 32; ++j)
+            ptx::tma_load_3d(sa + j * kWgBlockBytes, &tm.x, k0 + 32 * j, ps * kWgP, img, &full[stage]);
+          for (int j = 0; j < kWgN / 32; ++j)
+            ptx::tma_load_3d(sb + j * kWgBlockBytes, &tm.b, 32 * j, ps * kWgP, e, &full[stage]);
+          if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer
+    if (ptx::elect_one()) {
+#if defined(N2NMN_EXP_WG_IDESC)
+      constexpr uint32_t idesc = ptx::make_idesc_tf32(kWgM, kWgN) | (N2NMN_EXP_WG_IDESC);
+#else
+      constexpr uint32_t idesc = ptx::make_idesc_tf32_mn(kWgM, kWgN);
+#endif
+      int stage = 0, cur_set = -1;
+      uint32_t phase = 0, flushes = 0;
+      for (int i = e0; i < e1; ++i) {
+        const int set = p.entries[p.order[i]].set;
+        bool fresh = false;
+        if (set != cur_set) {
+          if (cur_set >= 0) {
+            ptx::umma_commit(tmem_full);                        // accumulator of the old set ready
+            ptx::mbar_wait_bounded(tmem_empty, flushes & 1);    // ... and drained
+            ++flushes;
+            ptx::tc_fence_after();
+          }
+          cur_set = set;
+          fresh = true;
+        }
+        for (int ps = 0; ps < stages_per_entry; ++ps) {
+          ptx::mbar_wait_bounded(&full[stage], phase);
+          ptx::tc_fence_after();
+#if defined(N2NMN_EXP_WGDBG)
+          if (blockIdx.x == 0 && blockIdx.y == 0 && i == e0 && ps == 0) {
+            const float* fa = reinterpret_cast<const float*>(wg_smem + stage * kWgStageBytes);
+            const float* fb = fa + kWgABytes / 4;
+            printf("wgdbg e=%d img=%d set=%d A[0..3]=%g %g %g %g A[row1]=%g %g B[0..3]=%g %g %g %g B[blk1]=%g\n",
+                   p.order[i], p.entries[p.order[i]].b, set, fa[0], fa[1], fa[2], fa[3], fa[32], fa[33],
+                   fb[0], fb[1], fb[2], fb[3], fb[1024]);
+          }
+#endif
+          const uint32_t a_addr = ptx::smem_u32(wg_smem + stage * kWgStageBytes);
+          const uint32_t b_addr = a_addr + kWgABytes;
+#pragma unroll
+          for (int j = 0; j < kWgP / 8; ++j) {   // 8 pixels = two 512-byte atoms per block
+            const uint64_t da = ptx::make_smem_desc_sw128_mn(a_addr + j * 1024, kWgBlockBytes, 512);
+            const uint64_t db = ptx::make_smem_desc_sw128_mn(b_addr + j * 1024, kWgBlockBytes, 512);
+            ptx::umma_tf32(tmem_d, da, db, idesc, !(fresh && ps == 0 && j == 0));
+          }
+          ptx::umma_commit(&empty[stage]);
+          if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (cur_set >= 0) ptx::umma_commit(tmem_full);
+    }
+  } else {
+    // ================================================================= flush warps (TMEM -> gflat)
+    const int quarter = warp & 3;                 // the TMEM lane quarter this warp may read
+    const int k = k0 + quarter * 32 + lane;       // feature row of this lane
+    int cur_set = -1;
+    uint32_t flushes = 0;
+    auto flush = [&](int set) {
+      ptx::mbar_wait_bounded(tmem_full, flushes & 1);
+      ptx::tc_fence_after();
+      float* W = p.gflat + p.go.proj_w[set];
+      for (int cb = 0; cb < kWgN; cb += 32) {
+        float v[32];
+        ptx::tmem_ld_32x32b_x32(tmem_d + (static_cast<uint32_t>(quarter * 32) << 16) + cb, v);
+#if defined(N2NMN_EXP_WGDBG)
+        if (blockIdx.x == 0 && blockIdx.y == 0 && cb == 0 && lane < 2 && quarter == 0)
+          printf("wgdbg flush set=%d lane=%d v=%g %g %g %g tmem=%x\n", set, lane, v[0], v[1], v[2], v[3], tmem_d);
+#endif
+        if (k < p.Dk) {
+          float* dst = W + (size_t)k * p.M + cb;
+          const bool pair_ok = (p.M & 1) == 0 && (reinterpret_cast<uintptr_t>(W) & 7) == 0;
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            if (pair_ok && cb + c + 1 < p.M) {
+              if (v[c] != 0.f || v[c + 1] != 0.f)
+                atomicAdd(reinterpret_cast<float2*>(dst + c), make_float2(v[c], v[c + 1]));
+            } else {
+              if (cb + c < p.M && v[c] != 0.f) atomicAdd(dst + c, v[c]);
+              if (!pair_ok && cb + c + 1 < p.M && v[c + 1] != 0.f) atomicAdd(dst + c + 1, v[c + 1]);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tmem_empty);
+      ++flushes;
+    };
+    for (int i = e0; i < e1; ++i) {
+      const int set = p.entries[p.order[i]].set;
+      if (set != cur_set) {
+        if (cur_set >= 0) flush(cur_set);
+        cur_set = set;
+      }
+    }
+    if (cur_set >= 0) flush(cur_set);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kWgN>(tmem_d);
+  }
+}
+
+// Bias gradient of the same layers: db_set[c] += Σ_p B_entry[p, c]. One CTA per B map.
+__global__ void __launch_bounds__(256)
+bmap_colsum_kernel(const float* __restrict__ dmap, const BwdEntry* __restrict__ entries, int HW,
+                   int M, int Mp, float* __restrict__ gflat, GradOffsets go) {
+  const int e = blockIdx.x;
+  const float* B = dmap + (size_t)e * HW * Mp;
+  float* dst = gflat + go.proj_b[entries[e].set];
+  for (int c = threadIdx.x; c < M; c += blockDim.x) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int p = 0;
+    for (; p + 3 < HW; p += 4) {
+      s0 += B[(size_t)p * Mp + c]; s1 += B[(size_t)(p + 1) * Mp + c];
+      s2 += B[(size_t)(p + 2) * Mp + c]; s3 += B[(size_t)(p + 3) * Mp + c];
+    }
+    for (; p < HW; ++p) s0 += B[(size_t)p * Mp + c];
+    const float s = (s0 + s1) + (s2 + s3);
+    if (s != 0.f) atomicAdd(dst + c, s);
+  }
+}
+
+}  // namespace n2nmn
