@@ -1613,7 +1613,7 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
       wp.HW = c->HW; wp.Dk = c->Dk; wp.M = c->cfg.map_dim; wp.gflat = gflat_dev; wp.go = c->go;
       dim3 gw(slabs, (ne + wp.per_cta - 1) / wp.per_cta);
       wgrad_umma_kernel<<<gw, kWgThreads, kWgSmemBytes, st>>>(c->wg_maps, wp);
-      bmap_colsum_kernel<<<ne, 256, 0, st>>>(c->dmap, d_ent, c->HW, c->cfg.map_dim, c->Mp, gflat_dev,
+      bmap_colsum_kernel<<<ne, 1024, 0, st>>>(c->dmap, d_ent, c->HW, c->cfg.map_dim, c->Mp, gflat_dev,
                                              c->go);
       ++c->launches;
     } else {
