@@ -813,7 +813,8 @@ def main():
         troof = None
         if gflops and acc.get('feat_grad_kernel'):
             tfs = gflops / (acc['feat_grad_kernel'] * 1e-6) / 1e12
-            troof = {'kernel': 'xtb_mma_kernel<FeatGradSrc> (dW = sum X^T B, mma.sync TF32)',
+            troof = {'kernel': 'wgrad_umma_kernel (dW = sum X^T B: tcgen05 kind::tf32, both operands '
+                               'MN-major via TMA)',
                      'bound': 'tensor', 'achieved': tfs, 'peak': tf32_peak, 'unit': 'TFLOP/s',
                      'frac': tfs / tf32_peak, 'avg_launch_us': acc['feat_grad_kernel'],
                      'flops_per_launch': gflops,

@@ -272,21 +272,23 @@ int encode_2d(n2nmn_ctx* c, CUtensorMap* map, const float* base, uint64_t inner,
   return 0;
 }
 
-// (inner, mid, outer) fp32 tensor, box (box_inner, box_mid, 1), 128-byte swizzle with 32-byte
-// atoms (the MN-major operand layout of 4-byte tensor-core operands), zero fill.
-int encode_3d(n2nmn_ctx* c, CUtensorMap* map, const float* base, uint64_t inner, uint64_t mid,
-              uint64_t outer, uint64_t mid_pitch_elems, uint64_t outer_pitch_elems,
-              uint32_t box_inner, uint32_t box_mid) {
-  cuuint64_t dims[3] = {inner, mid, outer};
-  cuuint64_t strides[2] = {mid_pitch_elems * sizeof(float), outer_pitch_elems * sizeof(float)};
-  cuuint32_t box[3] = {box_inner, box_mid, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = c->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims,
+// [outer][rows][row_pitch] fp32 viewed as (32 elements, rows, blocks of 32 elements, outer) with box
+// (32, box_rows, box_blocks, 1): 128-byte swizzle with 32-byte atoms (the MN-major operand layout
+// of 4-byte tensor-core operands), rows beyond `rows` zero-filled.
+int encode_mn_blocks(n2nmn_ctx* c, CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows,
+                     uint64_t outer, uint64_t row_pitch_elems, uint32_t box_rows,
+                     uint32_t box_blocks) {
+  cuuint64_t dims[4] = {32, rows, cols / 32, outer};
+  cuuint64_t strides[3] = {row_pitch_elems * sizeof(float), 32 * sizeof(float),
+                           rows * row_pitch_elems * sizeof(float)};
+  cuuint32_t box[4] = {32, box_rows, box_blocks, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = c->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims,
                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return fail(N2NMN_ERR_CUDA, "cuTensorMapEncodeTiled (3d) failed with CUresult " + std::to_string(r));
+    return fail(N2NMN_ERR_CUDA, "cuTensorMapEncodeTiled (4d) failed with CUresult " + std::to_string(r));
   return 0;
 }
 
@@ -1450,8 +1452,8 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
     CUDA_TRY(cudaMalloc(&c->phi_buf, (size_t)NB * 2 * c->Mp * sizeof(float)));
     c->wg_ok = c->Mp == kWgN && c->Dk % kWgM == 0 && !c->feat_aug;
     if (c->wg_ok) {
-      if (int rc = encode_3d(c, &c->wg_maps.b, c->dmap, c->Mp, c->HW, c->dmap_entries, c->Mp,
-                             (uint64_t)c->HW * c->Mp, 32, kWgP))
+      if (int rc = encode_mn_blocks(c, &c->wg_maps.b, c->dmap, c->Mp, c->HW, c->dmap_entries, c->Mp,
+                                    kWgP, kWgN / 32))
         return rc;
       CUDA_TRY(cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)kWgSmemBytes));
@@ -1601,8 +1603,8 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
       feat_grad_kernel<<<g2, 256, 0, st>>>(c->md, c->dmap, d_ent, ne, per, gflat_dev, c->go);
     } else if (c->wg_ok && !std::getenv("N2NMN_WGRAD_MMA_SYNC")) {
       // tcgen05, both operands MN-major straight from the feature grid and the B maps
-      if (int rc = encode_3d(c, &c->wg_maps.x, c->md.feat, c->Dk, c->HW, N, c->md.feat_pitch,
-                             (uint64_t)c->HW * c->md.feat_pitch, 32, kWgP))
+      if (int rc = encode_mn_blocks(c, &c->wg_maps.x, c->md.feat, c->Dk, c->HW, N, c->md.feat_pitch,
+                                    kWgP, kWgM / 32))
         return rc;
       const int slabs = c->Dk / kWgM;
       const int chunks = std::max(1, std::min(ne, 148 / slabs));
@@ -1613,9 +1615,14 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
       wp.HW = c->HW; wp.Dk = c->Dk; wp.M = c->cfg.map_dim; wp.gflat = gflat_dev; wp.go = c->go;
       dim3 gw(slabs, (ne + wp.per_cta - 1) / wp.per_cta);
       wgrad_umma_kernel<<<gw, kWgThreads, kWgSmemBytes, st>>>(c->wg_maps, wp);
+      prof_mark(c, "feat_grad_kernel", st);
       bmap_colsum_kernel<<<ne, 1024, 0, st>>>(c->dmap, d_ent, c->HW, c->cfg.map_dim, c->Mp, gflat_dev,
                                              c->go);
       ++c->launches;
+      ++c->launches;
+      prof_mark(c, "bias_grad_kernel", st);
+      CUDA_TRY(cudaGetLastError());
+      return 0;
     } else {
       // two CTAs per SM (106 KB of ring each): ~296 CTAs over (Dk/128) x (M/64) tiles
       const int tiles = ((c->Dk + kXtbM - 1) / kXtbM) * ((c->cfg.map_dim + kXtbN - 1) / kXtbN);

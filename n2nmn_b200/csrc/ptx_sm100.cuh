@@ -74,6 +74,15 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1,
+                                            int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
 // mbarrier wait that gives up: a protocol bug then ends in a trap (launch error) instead of a hung
 // GPU. Used by kernels under development and kept where the wait is not on the hot path.
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {

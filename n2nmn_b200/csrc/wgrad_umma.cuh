@@ -26,9 +26,12 @@ constexpr int kWgBBytes = (kWgN / 32) * kWgBlockBytes;    // 32 KB
 constexpr int kWgStageBytes = kWgABytes + kWgBBytes;
 constexpr size_t kWgSmemBytes = (size_t)kWgStages * kWgStageBytes + 256;
 
+// 4-D views with the 32-element blocks as their own dimension, so that ONE box per operand and
+// stage lands as [block][pixel][32 elements] = the canonical layout (12 boxes of 4 KB per stage
+// from 3-D maps kept the single producer thread busier than the tensor core).
 struct WgradMaps {
-  CUtensorMap x;   // features  (k: Dk, p: HW, image: N)      box (32, 32, 1)
-  CUtensorMap b;   // B maps    (c: Mp, p: HW, entry: E_cap)  box (32, 32, 1)
+  CUtensorMap x;   // features (32, p: HW, k/32: Dk/32, image: N)       box (32, 32, 4, 1)
+  CUtensorMap b;   // B maps   (32, p: HW, c/32: Mp/32, entry: E_cap)   box (32, 32, 8, 1)
 };
 struct WgradParams {
   const BwdEntry* entries;     // [num_entries] {set, image}
@@ -78,10 +81,9 @@ wgrad_umma_kernel(const __grid_constant__ WgradMaps tm, const WgradParams p) {
           ptx::mbar_arrive_expect_tx(&full[stage], kWgStageBytes);
           uint8_t* sa = wg_smem + stage * kWgStageBytes;
           uint8_t* sb = sa + kWgABytes;
-          for (int j = 0; j < kWgM / 32; ++j)
-            ptx::tma_load_3d(sa + j * kWgBlockBytes, &tm.x, k0 + 32 * j, ps * kWgP, img, &full[stage]);
-          for (int j = 0; j < kWgN / 32; ++j)
-            ptx::tma_load_3d(sb + j * kWgBlockBytes, &tm.b, 32 * j, ps * kWgP, e, &full[stage]);
+          // one box per operand: (32 elements, 32 pixels, 4 or 8 element blocks, 1 image / entry)
+          ptx::tma_load_4d(sa, &tm.x, 0, ps * kWgP, k0 / 32, img, &full[stage]);
+          ptx::tma_load_4d(sb, &tm.b, 0, ps * kWgP, 0, e, &full[stage]);
           if (++stage == kWgStages) { stage = 0; phase ^= 1; }
         }
       }
