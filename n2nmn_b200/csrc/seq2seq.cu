@@ -20,11 +20,13 @@
 // a cp.async ring, LSTM cell in the epilogue), s2s_gemm (same tile engine: h-transform, attention
 // query, table precompute), dec_attn (one CTA per question and step: attention, context vector,
 // token scores, validity mask, argmax / forcing, probabilities, entropy, stack-state update),
-// word_vecs. The whole call is a chain of layers·(T_enc + T_dec) + 2·T_dec + 3 dependent launches
-// on the caller's stream, linked by programmatic dependent launch: each kernel requests what does
-// not depend on its predecessor (weights, tables) before griddepcontrol.wait.
-// A step at N = 64 is latency bound (measured ~10 us per LSTM launch, r2 notes in DESIGN.md):
-// the next step for this row is a persistent kernel with the weights resident in shared memory.
+// word_vecs. The whole call is a chain of (T_enc + layers - 1) + layers·T_dec + 2·T_dec + 3
+// dependent launches on the caller's stream (the encoder layers run as a wavefront), linked by
+// programmatic dependent launch: each kernel requests what does not depend on its predecessor
+// (weights, tables) before griddepcontrol.wait.
+// At N = 64 an LSTM launch costs the issue time of its mma.sync instructions (three passes for fp32
+// parity): the next step for this row is a persistent tcgen05 kernel with the
+// weights resident in shared memory.
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -121,9 +123,17 @@ struct LstmStep {
 // sequence end the state is carried through and the output is zero (nmn3_netgen_att.py:95-99).
 // grid = (4L/32, ceil(N/(16 WM))): one CTA = 8 units x 64 (WM = 4) or 32 (WM = 2) questions; the
 // narrow variant is used while it is what it takes to put a CTA on most SMs (N <= 64 at L = 512).
-template <int WM, bool kExact>
-__global__ void __launch_bounds__(kMmaThreads) lstm_step_kernel(LstmStep p) {
+// The encoder runs as a WAVEFRONT: layer l of time step t and layer l-1 of step t+1 only depend on
+// the previous launch, so one launch carries up to kMaxLayers steps (blockIdx.z = layer; a slot with
+// N == 0 is idle) and the encoder takes T + layers - 1 launches instead of T * layers. With the
+// 3-stage ring two CTAs share an SM, which keeps as many bytes in flight as the 5-stage ring of
+// the single-step launches.
+struct LstmWave { LstmStep s[kMaxLayers]; };
+template <int WM, bool kExact, int ST>
+__global__ void __launch_bounds__(kMmaThreads) lstm_step_kernel(const LstmWave wave) {
   pdl_trigger();
+  const LstmStep& p = wave.s[blockIdx.z];
+  if (p.N == 0) return;
   extern __shared__ __align__(16) float mma_smem[];
   const int row0 = blockIdx.y * 16 * WM, c0 = blockIdx.x * kMmaCols;
   const int L = p.L, C = 4 * L;
@@ -165,7 +175,7 @@ __global__ void __launch_bounds__(kMmaThreads) lstm_step_kernel(LstmStep p) {
       h_keep[hh][0] = hp.x; h_keep[hh][1] = hp.y;
     }
   };
-  if (!mma_tile<WM, kExact>(mma_smem, op, row0, c0, acc, prefetch)) return;
+  if (!mma_tile<WM, kExact, ST>(mma_smem, op, row0, c0, acc, prefetch)) return;
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
     const int n = row0 + wm * 16 + g + 8 * hh;
@@ -638,10 +648,14 @@ int n2nmn_seq2seq_create(const n2nmn_seq2seq_config* cfg, n2nmn_seq2seq** out) {
   S2S_TRY(opt_in(s2s_gemm_kernel<2, false>, mma_smem_bytes(2)));
   S2S_TRY(opt_in(s2s_gemm_kernel<4, true>, mma_smem_bytes(4)));
   S2S_TRY(opt_in(s2s_gemm_kernel<4, false>, mma_smem_bytes(4)));
-  S2S_TRY(opt_in(lstm_step_kernel<2, true>, mma_smem_bytes(2)));
-  S2S_TRY(opt_in(lstm_step_kernel<2, false>, mma_smem_bytes(2)));
-  S2S_TRY(opt_in(lstm_step_kernel<4, true>, mma_smem_bytes(4)));
-  S2S_TRY(opt_in(lstm_step_kernel<4, false>, mma_smem_bytes(4)));
+  S2S_TRY(opt_in(lstm_step_kernel<2, true, 5>, mma_smem_bytes(2, 5)));
+  S2S_TRY(opt_in(lstm_step_kernel<2, false, 5>, mma_smem_bytes(2, 5)));
+  S2S_TRY(opt_in(lstm_step_kernel<2, true, 3>, mma_smem_bytes(2, 3)));
+  S2S_TRY(opt_in(lstm_step_kernel<2, false, 3>, mma_smem_bytes(2, 3)));
+  S2S_TRY(opt_in(lstm_step_kernel<4, true, 3>, mma_smem_bytes(4, 3)));
+  S2S_TRY(opt_in(lstm_step_kernel<4, false, 3>, mma_smem_bytes(4, 3)));
+  S2S_TRY(cudaFuncSetAttribute(lstm_step_kernel<2, true, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  S2S_TRY(cudaFuncSetAttribute(lstm_step_kernel<2, false, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   const size_t attn_bytes = attn_smem_floats(L, cfg->T_encoder, Vn) * sizeof(float);
   if (attn_bytes > 200 * 1024)
     return fail_with(N2NMN_ERR_ARG, "num_vocab_nmn * lstm_dim too large for the decoder step kernel");
@@ -736,40 +750,71 @@ int n2nmn_seq2seq_forward(n2nmn_seq2seq* s, const int32_t* input_seq_dev,
   int cur = 0;   // h[l][cur] holds every layer's h_{t-1}
   bool ok = true;
   const bool exact = !(g.flags & N2NMN_SEQ2SEQ_FLAG_TF32);
-  auto step = [&](int side, int t, const int32_t* tok, const int32_t* seq_len, float* out_seq) {
+  // one LSTM cell evaluation: layer l of `side` at step t; `par` = parity of the h buffer that
+  // holds the layer's previous state (its own and the layer below's run in lock step)
+  auto cell = [&](int side, int l, int t, int par, const int32_t* tok, const int32_t* seq_len,
+                  float* out_seq) {
+    const int in = l == 0 ? (side == 0 ? Et : En) : L;
+    LstmStep p;
+    p.x = l == 0 ? nullptr : s->h[l - 1][par ^ 1];
+    p.h_prev = s->h[l][par];
+    p.w = s->w_cell[side][l] + (l == 0 ? (size_t)in * C : 0);
+    p.table = l == 0 ? (side == 0 ? s->table_enc : s->table_dec) : nullptr;
+    p.tok = tok;
+    p.bias = s->b_cell[side][l];
+    p.c = s->c[l];
+    p.h_out = s->h[l][par ^ 1];
+    p.out_seq = l == NL - 1 ? out_seq : nullptr;
+    p.seq_len = seq_len;
+    p.t = t; p.N = N; p.L = L;
+    return p;
+  };
+  auto launch_wave = [&](const LstmWave& w, int nz, bool shared_sm) {
+    const dim3 g3(grid.x, grid.y, nz), blk(kMmaThreads);
+    cudaError_t le;
+    if (!narrow) {
+      le = exact ? launch_pdl(lstm_step_kernel<4, true, 3>, g3, blk, mma_smem_bytes(4, 3), st, w)
+                 : launch_pdl(lstm_step_kernel<4, false, 3>, g3, blk, mma_smem_bytes(4, 3), st, w);
+    } else if (shared_sm) {
+      le = exact ? launch_pdl(lstm_step_kernel<2, true, 3>, g3, blk, mma_smem_bytes(2, 3), st, w)
+                 : launch_pdl(lstm_step_kernel<2, false, 3>, g3, blk, mma_smem_bytes(2, 3), st, w);
+    } else {
+      le = exact ? launch_pdl(lstm_step_kernel<2, true, 5>, g3, blk, mma_smem_bytes(2, 5), st, w)
+                 : launch_pdl(lstm_step_kernel<2, false, 5>, g3, blk, mma_smem_bytes(2, 5), st, w);
+    }
+    if (le != cudaSuccess) ok = false;
+    ++s->launches;
+  };
+  // encoder, dynamic_rnn (:95-99): tick k runs layer l at step t = k - l
+  for (int k = 0; k < T_enc + NL - 1; ++k) {
+    LstmWave w;
+    std::memset(&w, 0, sizeof(w));
     for (int l = 0; l < NL; ++l) {
-      const int in = l == 0 ? (side == 0 ? Et : En) : L;
-      LstmStep p;
-      p.x = l == 0 ? nullptr : s->h[l - 1][cur ^ 1];
-      p.h_prev = s->h[l][cur];
-      p.w = s->w_cell[side][l] + (l == 0 ? (size_t)in * C : 0);
-      p.table = l == 0 ? (side == 0 ? s->table_enc : s->table_dec) : nullptr;
-      p.tok = tok;
-      p.bias = s->b_cell[side][l];
-      p.c = s->c[l];
-      p.h_out = s->h[l][cur ^ 1];
-      p.out_seq = l == NL - 1 ? out_seq : nullptr;
-      p.seq_len = seq_len;
-      p.t = t; p.N = N; p.L = L;
-      cudaError_t le;
-      if (exact) le = narrow ? launch_pdl(lstm_step_kernel<2, true>, grid, dim3(kMmaThreads), mma_smem_bytes(2), st, p)
-                             : launch_pdl(lstm_step_kernel<4, true>, grid, dim3(kMmaThreads), mma_smem_bytes(4), st, p);
-      else le = narrow ? launch_pdl(lstm_step_kernel<2, false>, grid, dim3(kMmaThreads), mma_smem_bytes(2), st, p)
-                       : launch_pdl(lstm_step_kernel<4, false>, grid, dim3(kMmaThreads), mma_smem_bytes(4), st, p);
-      if (le != cudaSuccess) ok = false;
-      ++s->launches;
+      const int t = k - l;
+      if (t < 0 || t >= T_enc) continue;    // idle slot (N = 0)
+      w.s[l] = cell(0, l, t, t & 1, input_seq_dev + (size_t)t * N, seq_len_dev,
+                    s->enc_out + (size_t)t * N * L);
+    }
+    launch_wave(w, NL, NL > 1);
+  }
+  cur = T_enc & 1;
+  // decoder step: the layers of one step depend on each other, one launch each
+  auto step = [&](int t, const int32_t* tok) {
+    for (int l = 0; l < NL; ++l) {
+      LstmWave w;
+      std::memset(&w, 0, sizeof(w));
+      w.s[0] = cell(1, l, t, cur, tok, nullptr, nullptr);
+      launch_wave(w, 1, false);
     }
     cur ^= 1;
   };
-  for (int t = 0; t < T_enc; ++t)   // dynamic_rnn (:95-99)
-    step(0, t, input_seq_dev + (size_t)t * N, seq_len_dev, s->enc_out + (size_t)t * N * L);
   S2S_TRY(cudaGetLastError());
   int rc = launch_gemm(s, st, s->enc_out, L, T_enc * N, L, s->v("encoder/encoder_h_transform/weights"),
                        L, L, s->v("encoder/encoder_h_transform/biases"), s->enc_ht, L);   // :104-108
   if (rc) return rc;
   const size_t attn_smem = attn_smem_floats(L, T_enc, Vn) * sizeof(float);
   for (int t = 0; t < T_dec; ++t) {   // raw_rnn loop (:199-305)
-    step(1, t, s->cur_tok, nullptr, nullptr);
+    step(t, s->cur_tok);
     const float* h_top = s->h[NL - 1][cur];
     rc = launch_gemm(s, st, h_top, L, N, L, s->v("decoder/att_prediction/weights"), L, L,
                      s->v("decoder/att_prediction/biases"), s->q, L);
