@@ -25,6 +25,7 @@
 #include "head_kernel.cuh"
 #include "backward.cuh"
 #include "wgrad_umma.cuh"
+#include "head_tail_umma.cuh"
 
 using namespace n2nmn;
 
@@ -152,7 +153,13 @@ struct n2nmn_ctx {
   float* ehat = nullptr;
   float** ehat_dst = nullptr;
   float* out_wp[NUM_OUT_SETS] = {};
-  int Cp = 0;   // [max_batch][HW][Mp] scratch of the Transform backward
+  int Cp = 0;
+  // ... and its tcgen05 form (head_tail_umma.cuh): remainder plane of ê, W_outᵀ planes, maps
+  float* ehat_lo = nullptr;
+  float* out_wt_hi[NUM_OUT_SETS] = {};
+  float* out_wt_lo[NUM_OUT_SETS] = {};
+  HeadTailMaps ht_maps[NUM_OUT_SETS];
+  int Cpad = 0;   // [max_batch][HW][Mp] scratch of the Transform backward
   int dmap_entries = 0;
   VarSeg* d_segs = nullptr;
   float* d_sumsq = nullptr;
@@ -489,7 +496,7 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
   nc.md = c->md; nc.tb = c->tb; nc.arena = arena; nc.scores = scores_seg[0]; nc.mbuf = c->mbuf;
   nc.pooled = c->pooled; nc.pool_pitch = c->Kp; nc.pool_att = c->pool_att;
   nc.phi_out = S.train ? c->phi_buf : nullptr;
-  nc.ehat = c->ehat; nc.ehat_dst = c->ehat_dst;
+  nc.ehat = c->ehat; nc.ehat_lo = c->ehat_lo; nc.ehat_dst = c->ehat_dst;
   const int NQ = (int)S.q_ptr.size() - 1;
   // several segments: question q writes row q % N of segment q / N; one segment: row q (the
   // per-module entry point numbers its call rows beyond the bound batch size)
@@ -593,6 +600,18 @@ int run_tables(n2nmn_ctx* c, n2nmn_sched* sc, float* const* scores_seg, float* a
           if (r1 <= r0) continue;
           const int os = op == OP_DESCRIBE ? OS_DESCRIBE : OS_SAMEPROP;
           if (!c->out_wp[os]) return fail(N2NMN_ERR_STATE, "answer-head weights not packed");
+          if (c->ehat_lo && c->out_wt_hi[os] && !std::getenv("N2NMN_TAIL_MMA_SYNC")) {
+            cudaLaunchConfig_t tc = hc;
+            tc.gridDim = dim3((unsigned)(c->Cpad / kHtN), (unsigned)((r1 - r0 + kHtM - 1) / kHtM));
+            tc.blockDim = dim3(kHtThreads);
+            tc.dynamicSmemBytes = kHtSmemBytes;
+            CUDA_TRY(cudaLaunchKernelEx(&tc, head_tail_umma_kernel, c->ht_maps[os], c->md.out_b[os],
+                                        (float* const*)c->ehat_dst, r0, r1 - r0,
+                                        (int)c->cfg.num_choices, (int)c->cfg.map_dim));
+            ++c->launches;
+            prof_mark(c, "head_tail_gemm_kernel", st);
+            continue;
+          }
           GemmOperands gp;
           gp.a0 = c->ehat + (size_t)r0 * c->Mp; gp.k0 = c->cfg.map_dim; gp.lda0 = c->Mp;
           gp.a1 = nullptr; gp.k1 = 0; gp.lda1 = 0;
@@ -760,12 +779,26 @@ int n2nmn_create(const n2nmn_config* cfg, n2nmn_ctx** out) {
     c->Cp = round_up(cfg->num_choices, 4);
     CUDA_TRY(cudaMalloc(&c->ehat, (size_t)NB * c->Mp * sizeof(float)));
     CUDA_TRY(cudaMalloc(&c->ehat_dst, (size_t)NB * sizeof(float*)));
+    c->Cpad = round_up(cfg->num_choices, kHtN);
+    CUDA_TRY(cudaMalloc(&c->ehat_lo, (size_t)NB * c->Mp * sizeof(float)));
     for (const Variable& v : c->vars)
       for (int os = 0; os < NUM_OUT_SETS; ++os)
         if (v.slot == &md.out_w[os]) {
           CUDA_TRY(cudaMalloc(&c->out_wp[os], (size_t)cfg->map_dim * c->Cp * sizeof(float)));
           CUDA_TRY(cudaMemset(c->out_wp[os], 0, (size_t)cfg->map_dim * c->Cp * sizeof(float)));
+          const size_t wt = (size_t)c->Cpad * c->Mp * sizeof(float);
+          CUDA_TRY(cudaMalloc(&c->out_wt_hi[os], wt));
+          CUDA_TRY(cudaMalloc(&c->out_wt_lo[os], wt));
+          CUDA_TRY(cudaMemset(c->out_wt_hi[os], 0, wt));
+          CUDA_TRY(cudaMemset(c->out_wt_lo[os], 0, wt));
+          HeadTailMaps& hm = c->ht_maps[os];
+          if (int rc = encode_2d(c, &hm.a_hi, c->ehat, c->Mp, NB, c->Mp, kHtK, kHtM)) return rc;
+          if (int rc = encode_2d(c, &hm.a_lo, c->ehat_lo, c->Mp, NB, c->Mp, kHtK, kHtM)) return rc;
+          if (int rc = encode_2d(c, &hm.b_hi, c->out_wt_hi[os], c->Mp, c->Cpad, c->Mp, kHtK, kHtN)) return rc;
+          if (int rc = encode_2d(c, &hm.b_lo, c->out_wt_lo[os], c->Mp, c->Cpad, c->Mp, kHtK, kHtN)) return rc;
         }
+    CUDA_TRY(cudaFuncSetAttribute(head_tail_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kHtSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(head_tail_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)mma_smem_bytes(2)));
     CUDA_TRY(cudaFuncSetAttribute(head_tail_gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -873,8 +906,10 @@ int n2nmn_destroy(n2nmn_ctx* c) {
   cudaFree(c->feat_aug); cudaFree(c->tb.tau); cudaFree(c->arena); cudaFree(c->mbuf);
   cudaFree(c->pooled); cudaFree(c->pool_att); cudaFree(c->conv_quad); cudaFree(c->tb.tq);
   cudaFree(c->dscores); cudaFree(c->per_sample); cudaFree(c->dtau); cudaFree(c->dmap); cudaFree(c->dstencil); cudaFree(c->gmap); cudaFree(c->phi_buf);
-  cudaFree(c->ehat); cudaFree(c->ehat_dst);
-  for (int os = 0; os < NUM_OUT_SETS; ++os) cudaFree(c->out_wp[os]);
+  cudaFree(c->ehat); cudaFree(c->ehat_dst); cudaFree(c->ehat_lo);
+  for (int os = 0; os < NUM_OUT_SETS; ++os) {
+    cudaFree(c->out_wp[os]); cudaFree(c->out_wt_hi[os]); cudaFree(c->out_wt_lo[os]);
+  }
   cudaFree(c->d_segs); cudaFree(c->d_sumsq);
   cudaFree(c->scores_tmp); cudaFree(c->e2e_feat); cudaFree(c->e2e_wv); cudaFree(c->e2e_scores);
   for (int i = 0; i < kTableSlots; ++i) {
@@ -924,9 +959,14 @@ int n2nmn_set_weight(n2nmn_ctx* c, const char* name, const float* src, const int
                                                            c->proj_bias[v.set], c->Mp);
     }
     for (int os = 0; os < NUM_OUT_SETS; ++os)
-      if (v.slot == &c->md.out_w[os] && c->out_wp[os])
+      if (v.slot == &c->md.out_w[os] && c->out_wp[os]) {
         pitch_rows_kernel<<<(unsigned)c->cfg.map_dim, 256, 0, st>>>(src, c->cfg.map_dim,
                                                                    c->cfg.num_choices, c->out_wp[os], c->Cp);
+        if (c->out_wt_hi[os])
+          out_wt_split_kernel<<<dim3((c->Cpad + 31) / 32, (c->Mp + 31) / 32), dim3(32, 8), 0, st>>>(
+              src, c->cfg.map_dim, c->cfg.num_choices, c->out_wt_hi[os], c->out_wt_lo[os], c->Mp,
+              c->Cpad);
+      }
     if (c->conv_quad && (v.slot == &c->md.conv_k || v.slot == &c->md.conv_b ||
                          v.slot == &c->md.elt_w[ES_TRANSFORM])) {
       // the Transform quadratic-form matrix depends on these three variables
@@ -1393,6 +1433,10 @@ int repack_derived(n2nmn_ctx* c, const float* wflat_dev, cudaStream_t st) {
       if (c->vars[i].slot == &c->md.out_w[os] && c->out_wp[os]) {
         pitch_rows_kernel<<<(unsigned)c->cfg.map_dim, 256, 0, st>>>(
             wflat_dev + c->flat_offset[i], c->cfg.map_dim, c->cfg.num_choices, c->out_wp[os], c->Cp);
+        if (c->out_wt_hi[os])
+          out_wt_split_kernel<<<dim3((c->Cpad + 31) / 32, (c->Mp + 31) / 32), dim3(32, 8), 0, st>>>(
+              wflat_dev + c->flat_offset[i], c->cfg.map_dim, c->cfg.num_choices, c->out_wt_hi[os],
+              c->out_wt_lo[os], c->Mp, c->Cpad);
         ++c->launches;
       }
   if (c->proj_repack_sets > 0) {

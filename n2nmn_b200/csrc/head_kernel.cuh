@@ -291,7 +291,11 @@ head_kernel(const NodeCtx c, const NodeRec* __restrict__ nodes,
       __syncthreads();
       for (int i = threadIdx.x; i < cnt * Mp; i += kHeadThreads) {
         const int n = i / Mp, ch = i - n * Mp;
-        c.ehat[(size_t)(wk.first + n) * Mp + ch] = phi0[n * Mp + ch];
+        const float v = phi0[n * Mp + ch];
+        c.ehat[(size_t)(wk.first + n) * Mp + ch] = v;
+        if (c.ehat_lo != nullptr)
+          c.ehat_lo[(size_t)(wk.first + n) * Mp + ch] =
+              v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
       }
       if (threadIdx.x < cnt) c.ehat_dst[wk.first + threadIdx.x] = s_outp[threadIdx.x];
       return;
