@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(kNodeThreads, kTransform ? 1 : 2)
 tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
                 const int32_t* __restrict__ bwd_nodes, int first,
                 const int32_t* __restrict__ node_entry) {
+  pdl_trigger();
   extern __shared__ __align__(16) float bsm[];
   const DevModel& md = c.md;
   const int HW = md.HW, Mp = md.Mp, M = md.M, C = md.C, Hh = md.H, Ww = md.W;
@@ -188,6 +189,14 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
                         nd.op == OP_DESCRIBE || nd.op == OP_SAME_PROPERTY);
     const int slice = blockIdx.y, ns = split ? (int)gridDim.y : 1;
     if (slice >= ns) return;
+    // The levels are chained with programmatic dependent launch: what does not depend on the level
+    // above (the node record, the Transform filter bank — 25 KB per CTA, the top stall of the
+    // Transform levels when it was staged after the wait) is fetched before griddepcontrol.wait.
+    if constexpr (kTransform) {
+      if (nd.op == OP_TRANSFORM)
+        for (int j = threadIdx.x; j < KS * KS * Mp; j += blockDim.x) ks[j] = md.conv_k[j];
+    }
+    pdl_wait();
     const int p_lo = (HW * slice) / ns, p_hi = (HW * (slice + 1)) / ns;
     float* g = c.gmap + (size_t)i * L.HWp;                    // d loss / d this node's map
     float* gin0 = (nd.in0 >= 0) ? c.gmap + (size_t)nd.in0 * L.HWp : nullptr;
@@ -465,7 +474,7 @@ tree_bwd_kernel(const BwdCtx c, const NodeRec* __restrict__ nodes,
         float* dw2v = v + 4 * Mp; float* dbkv = v + 5 * Mp;
         const float* tau = c.tb.tau + (size_t)nd.text * Mp;
         for (int j = threadIdx.x; j < PH * PW; j += blockDim.x) { pad[j] = 0.f; dpad[j] = 0.f; }
-        for (int j = threadIdx.x; j < KS * KS * Mp; j += blockDim.x) ks[j] = md.conv_k[j];
+        // (ks, the filter bank, was staged before the dependency wait)
         for (int ch = threadIdx.x; ch < Mp; ch += blockDim.x) {
           const bool live = ch < M;
           tauv[ch] = live ? tau[ch] : 0.f;

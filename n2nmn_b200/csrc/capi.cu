@@ -1589,14 +1589,24 @@ int n2nmn_train_backward(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
     // SMs (148 at one CTA per SM with Transform nodes, 296 without)
     const int slices = has_tr ? std::max(3, std::min(kBwdSlicesMax, 148 / n_tr))
                               : std::max(2, std::min(6, 296 / cnt));
-    const dim3 grid(cnt, slices);
+    cudaLaunchConfig_t bl;
+    std::memset(&bl, 0, sizeof(bl));
+    bl.gridDim = dim3(cnt, slices);
+    bl.blockDim = dim3(kNodeThreads);
+    bl.dynamicSmemBytes = bsm;
+    bl.stream = st;
+    cudaLaunchAttribute battr[1];
+    battr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    battr[0].val.programmaticStreamSerializationAllowed = 1;
+    bl.attrs = battr;
+    bl.numAttrs = c->use_pdl ? 1 : 0;
     const bool k5 = c->cfg.kernel_size == 5;
     if (has_tr) {
-      if (k5) tree_bwd_kernel<5, true><<<grid, kNodeThreads, bsm, st>>>(bc, d_nodes, d_bwd, first, d_entry);
-      else tree_bwd_kernel<3, true><<<grid, kNodeThreads, bsm, st>>>(bc, d_nodes, d_bwd, first, d_entry);
+      if (k5) CUDA_TRY(cudaLaunchKernelEx(&bl, tree_bwd_kernel<5, true>, bc, d_nodes, d_bwd, first, d_entry));
+      else CUDA_TRY(cudaLaunchKernelEx(&bl, tree_bwd_kernel<3, true>, bc, d_nodes, d_bwd, first, d_entry));
     } else {
-      if (k5) tree_bwd_kernel<5, false><<<grid, kNodeThreads, bsm, st>>>(bc, d_nodes, d_bwd, first, d_entry);
-      else tree_bwd_kernel<3, false><<<grid, kNodeThreads, bsm, st>>>(bc, d_nodes, d_bwd, first, d_entry);
+      if (k5) CUDA_TRY(cudaLaunchKernelEx(&bl, tree_bwd_kernel<5, false>, bc, d_nodes, d_bwd, first, d_entry));
+      else CUDA_TRY(cudaLaunchKernelEx(&bl, tree_bwd_kernel<3, false>, bc, d_nodes, d_bwd, first, d_entry));
     }
     ++c->launches;
   }
