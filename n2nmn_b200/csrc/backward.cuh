@@ -1011,23 +1011,42 @@ struct VarSeg { int offset, count, decay; };   // decay = 1 for ".../weights" va
 __global__ void grad_norm_kernel(const float* __restrict__ w, float* __restrict__ g,
                                  const VarSeg* __restrict__ segs, float weight_decay, float gscale,
                                  float* __restrict__ sumsq, float* __restrict__ l2) {
+  __shared__ float red[2][8];
   const VarSeg s = segs[blockIdx.y];
   float acc = 0.f, wsq = 0.f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s.count; i += gridDim.x * blockDim.x) {
-    float gv = g[s.offset + i] * gscale;
+  const bool touch = s.decay || gscale != 1.f;
+  // variables start on 16-byte boundaries of the flat buffers (offsets are multiples of 4 floats)
+  const int n4 = s.count >> 2;
+  float4* g4 = reinterpret_cast<float4*>(g + s.offset);
+  const float4* w4 = reinterpret_cast<const float4*>(w + s.offset);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    float4 gv = g4[i];
+    gv.x *= gscale; gv.y *= gscale; gv.z *= gscale; gv.w *= gscale;
     if (s.decay) {
-      const float wv = w[s.offset + i];
-      gv = fmaf(weight_decay, wv, gv);
-      wsq = fmaf(wv, wv, wsq);
+      const float4 wv = w4[i];
+      gv.x = fmaf(weight_decay, wv.x, gv.x); gv.y = fmaf(weight_decay, wv.y, gv.y);
+      gv.z = fmaf(weight_decay, wv.z, gv.z); gv.w = fmaf(weight_decay, wv.w, gv.w);
+      wsq += wv.x * wv.x + wv.y * wv.y + wv.z * wv.z + wv.w * wv.w;
     }
-    if (s.decay || gscale != 1.f) g[s.offset + i] = gv;
+    if (touch) g4[i] = gv;
+    acc += gv.x * gv.x + gv.y * gv.y + gv.z * gv.z + gv.w * gv.w;
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < (s.count & 3)) {   // tail of a count not divisible by 4
+    const int i = s.offset + 4 * n4 + threadIdx.x;
+    float gv = g[i] * gscale;
+    if (s.decay) { const float wv = w[i]; gv = fmaf(weight_decay, wv, gv); wsq = fmaf(wv, wv, wsq); }
+    if (touch) g[i] = gv;
     acc = fmaf(gv, gv, acc);
   }
   acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0 && acc != 0.f) atomicAdd(sumsq + blockIdx.y, acc);
-  if (l2 != nullptr && s.decay) {
-    wsq = warp_sum(wsq);
-    if ((threadIdx.x & 31) == 0 && wsq != 0.f) atomicAdd(l2, 0.5f * wsq);
+  wsq = warp_sum(wsq);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = acc; red[1][threadIdx.x >> 5] = wsq; }
+  __syncthreads();
+  if (threadIdx.x == 0) {   // one reduction per CTA (44 addresses take them all)
+    float a = 0.f, q = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += red[0][i]; q += red[1][i]; }
+    if (a != 0.f) atomicAdd(sumsq + blockIdx.y, a);
+    if (l2 != nullptr && s.decay && q != 0.f) atomicAdd(l2, 0.5f * q);
   }
 }
 
@@ -1078,16 +1097,36 @@ __global__ void adam_clip_kernel(float* __restrict__ w, const float* __restrict_
   float* dst = wbuf + r.dst_off;
   const float nrm = sqrtf(sumsq[blockIdx.y]);
   const float scale = (nrm > max_norm) ? max_norm / nrm : 1.f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s.count; i += gridDim.x * blockDim.x) {
-    const int o = s.offset + i;
-    const float gv = g[o] * scale;
-    const float mv = b1 * m[o] + (1.f - b1) * gv;
-    const float vv = b2 * v[o] + (1.f - b2) * gv * gv;
-    m[o] = mv; v[o] = vv;
-    const float wn = w[o] - lr_t * mv / (sqrtf(vv) + eps);
-    w[o] = wn;
+  auto step = [&](float wv, float gv, float& mv, float& vv) {
+    gv *= scale;
+    mv = b1 * mv + (1.f - b1) * gv;
+    vv = b2 * vv + (1.f - b2) * gv * gv;
+    return wv - lr_t * mv / (sqrtf(vv) + eps);
+  };
+  auto put = [&](int i, float wn) {   // the packed copy: plain or row-pitched
     if (r.kind == 0) dst[i] = wn;
     else { const int row = i / r.cols; dst[(size_t)row * pitch + (i - row * r.cols)] = wn; }
+  };
+  const int n4 = s.count >> 2;
+  float4* w4 = reinterpret_cast<float4*>(w + s.offset);
+  float4* m4 = reinterpret_cast<float4*>(m + s.offset);
+  float4* v4 = reinterpret_cast<float4*>(v + s.offset);
+  const float4* g4 = reinterpret_cast<const float4*>(g + s.offset);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    float4 wv = w4[i], mv = m4[i], vv = v4[i];
+    const float4 gv = g4[i];
+    wv.x = step(wv.x, gv.x, mv.x, vv.x); wv.y = step(wv.y, gv.y, mv.y, vv.y);
+    wv.z = step(wv.z, gv.z, mv.z, vv.z); wv.w = step(wv.w, gv.w, mv.w, vv.w);
+    w4[i] = wv; m4[i] = mv; v4[i] = vv;
+    if (r.kind == 0) reinterpret_cast<float4*>(dst)[i] = wv;   // (dst_off: 16-byte aligned slots)
+    else { put(4 * i, wv.x); put(4 * i + 1, wv.y); put(4 * i + 2, wv.z); put(4 * i + 3, wv.w); }
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < (s.count & 3)) {
+    const int i = 4 * n4 + threadIdx.x, o = s.offset + i;
+    float mv = m[o], vv = v[o];
+    const float wn = step(w[o], g[o], mv, vv);
+    m[o] = mv; v[o] = vv; w[o] = wn;
+    put(i, wn);
   }
 }
 
