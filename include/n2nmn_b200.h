@@ -329,9 +329,9 @@ int n2nmn_set_tree_cluster(n2nmn_ctx* ctx, int ctas_per_question);
  * identical. */
 int n2nmn_set_proj_ctas(n2nmn_ctx* ctx, int max_ctas);
 
-/* CTAs per group of 8 text nodes in the text-projection kernel: each CTA then walks
- * ceil((Mp/64) / n) blocks of 64 output columns. 0 (the default) = one CTA per column block
- * (shortest kernel); 1 = one CTA per group (least SM-time). Tuning only: results are identical. */
+/* Retired tuning knob of the round-1 text-projection kernel (CTAs per group of 8 text rows). The
+ * text projection is a tiled GEMM now (64 rows x 32 columns per CTA, csrc/text_proj.cuh); the value
+ * is accepted and ignored, the entry point stays for ABI-2 callers. */
 int n2nmn_set_text_ctas_per_group(n2nmn_ctx* ctx, int n);
 
 /* CRC-32C (Castagnoli) of a host buffer, continuing from `crc` (0 to start): the checksum of the

@@ -269,7 +269,7 @@ class LayoutExecutor:
         _lib.check(self._lib.n2nmn_set_proj_ctas(self.modules._h, int(max_ctas)))
 
     def set_text_ctas_per_group(self, n):
-        """CTAs per group of 8 text nodes in the text kernel (0 = one per column block)."""
+        """Retired knob of the round-1 text kernel: accepted and ignored (see the header)."""
         _lib.check(self._lib.n2nmn_set_text_ctas_per_group(self.modules._h, int(n)))
 
     # -- profiling ------------------------------------------------------------------------------
