@@ -24,14 +24,15 @@ constexpr int kWgBlockBytes = kWgP * 128;                 // one [32 pixels][32 
 constexpr int kWgABytes = (kWgM / 32) * kWgBlockBytes;    // 16 KB
 constexpr int kWgBBytes = (kWgN / 32) * kWgBlockBytes;    // 32 KB
 constexpr int kWgStageBytes = kWgABytes + kWgBBytes;
-constexpr size_t kWgSmemBytes = (size_t)kWgStages * kWgStageBytes + 256;
+constexpr int kWgFlushFloats = 4 * 32 * 33;   // per flush warp: a 32 x 32 transpose tile (pitch 33)
+constexpr size_t kWgSmemBytes = (size_t)kWgStages * kWgStageBytes + 256 + kWgFlushFloats * sizeof(float);
 
 // 4-D views with the 32-element blocks as their own dimension, so that ONE box per operand and
 // stage lands as [block][pixel][32 elements] = the canonical layout (12 boxes of 4 KB per stage
 // from 3-D maps kept the single producer thread busier than the tensor core).
 struct WgradMaps {
-  CUtensorMap x;   // features (32, p: HW, k/32: Dk/32, image: N)       box (32, 32, 4, 1)
-  CUtensorMap b;   // B maps   (32, p: HW, c/32: Mp/32, entry: E_cap)   box (32, 32, 8, 1)
+  CUtensorMap x;    // features (32, p: HW, k/32: Dk/32, image: N)       box (32, 32, 4, 1)
+  CUtensorMap b;    // B maps   (32, p: HW, c/32: Mp/32, entry: E_cap)   box (32, 32, 8, 1)
 };
 struct WgradParams {
   const BwdEntry* entries;     // [num_entries] {set, image}
@@ -41,6 +42,9 @@ struct WgradParams {
   GradOffsets go;
 };
 
+// (A 4-CTA cluster variant that multicast the B stage to the four feature slabs — a quarter of the
+// B-map traffic — was built and measured: no faster, 36.8 vs 32.7 us; the kernel was bound by the
+// reductions of its flush, see below, not by operand traffic. Removed.)
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_umma_kernel(const __grid_constant__ WgradMaps tm, const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t wg_smem[];
@@ -50,6 +54,7 @@ wgrad_umma_kernel(const __grid_constant__ WgradMaps tm, const WgradParams p) {
   uint64_t* tmem_full = empty + kWgStages;
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  float* s_flush = reinterpret_cast<float*>(wg_smem + kWgStages * kWgStageBytes + 256);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * kWgM;
   const int e0 = blockIdx.y * p.per_cta, e1 = min(p.num_entries, e0 + p.per_cta);
@@ -58,7 +63,10 @@ wgrad_umma_kernel(const __grid_constant__ WgradMaps tm, const WgradParams p) {
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tensormap(&tm.x);
     ptx::prefetch_tensormap(&tm.b);
-    for (int s = 0; s < kWgStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kWgStages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
     ptx::mbar_init(tmem_full, 1);
     ptx::mbar_init(tmem_empty, 4);    // one arrive per flush warp
     ptx::fence_barrier_init();
@@ -140,32 +148,38 @@ wgrad_umma_kernel(const __grid_constant__ WgradMaps tm, const WgradParams p) {
   } else {
     // ================================================================= flush warps (TMEM -> gflat)
     const int quarter = warp & 3;                 // the TMEM lane quarter this warp may read
-    const int k = k0 + quarter * 32 + lane;       // feature row of this lane
+    float* tile = s_flush + quarter * 32 * 33;
     int cur_set = -1;
     uint32_t flushes = 0;
+    // TMEM hands a lane one ROW (feature) and 32 columns; reductions issued that way touch 32
+    // different lines per instruction and the L2's reduction rate set the kernel's time (23 of 33
+    // us: the time did not move with the number of entry chunks). Each 32 x 32 chunk therefore goes
+    // through a transpose tile so that half a warp covers 128 contiguous bytes of one row.
     auto flush = [&](int set) {
       ptx::mbar_wait_bounded(tmem_full, flushes & 1);
       ptx::tc_fence_after();
       float* W = p.gflat + p.go.proj_w[set];
+      const bool pair_ok = (p.M & 1) == 0 && (reinterpret_cast<uintptr_t>(W) & 7) == 0;
+      const int sub = lane >> 4, c2 = 2 * (lane & 15);
       for (int cb = 0; cb < kWgN; cb += 32) {
         float v[32];
         ptx::tmem_ld_32x32b_x32(tmem_d + (static_cast<uint32_t>(quarter * 32) << 16) + cb, v);
-#if defined(N2NMN_EXP_WGDBG)
-        if (blockIdx.x == 0 && blockIdx.y == 0 && cb == 0 && lane < 2 && quarter == 0)
-          printf("wgdbg flush set=%d lane=%d v=%g %g %g %g tmem=%x\n", set, lane, v[0], v[1], v[2], v[3], tmem_d);
-#endif
-        if (k < p.Dk) {
-          float* dst = W + (size_t)k * p.M + cb;
-          const bool pair_ok = (p.M & 1) == 0 && (reinterpret_cast<uintptr_t>(W) & 7) == 0;
+        __syncwarp();
 #pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            if (pair_ok && cb + c + 1 < p.M) {
-              if (v[c] != 0.f || v[c + 1] != 0.f)
-                atomicAdd(reinterpret_cast<float2*>(dst + c), make_float2(v[c], v[c + 1]));
-            } else {
-              if (cb + c < p.M && v[c] != 0.f) atomicAdd(dst + c, v[c]);
-              if (!pair_ok && cb + c + 1 < p.M && v[c + 1] != 0.f) atomicAdd(dst + c + 1, v[c + 1]);
-            }
+        for (int c = 0; c < 32; ++c) tile[lane * 33 + c] = v[c];
+        __syncwarp();
+        const int col = cb + c2;
+#pragma unroll 4
+        for (int rr = 0; rr < 32; rr += 2) {
+          const int row = rr + sub, k = k0 + quarter * 32 + row;
+          const float a = tile[row * 33 + c2], b = tile[row * 33 + c2 + 1];
+          if (k >= p.Dk) continue;
+          float* dst = W + (size_t)k * p.M + col;
+          if (pair_ok && col + 1 < p.M) {
+            if (a != 0.f || b != 0.f) atomicAdd(reinterpret_cast<float2*>(dst), make_float2(a, b));
+          } else {
+            if (col < p.M && a != 0.f) atomicAdd(dst, a);
+            if (col + 1 < p.M && b != 0.f) atomicAdd(dst + 1, b);
           }
         }
       }
