@@ -108,15 +108,18 @@ def peaks():
                 source='fallback (B200_PROFILING.md)')
 
 
-def ncu_traffic(kernel):
+def ncu_traffic(kernel, batches_per_launch):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
-    `ncu --set full` capture of this same command (profiles/ncu_traffic.json), or None."""
+    `ncu --set full` capture of this same command (profiles/ncu_traffic.json); None when there
+    is no capture or it was taken with another number of batches per launch."""
     p = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
     if not os.path.exists(p):
         return None
     with open(p) as f:
         d = json.load(f).get(kernel)
-    return None if not d else d['dram_read_bytes'] + d['dram_write_bytes']
+    if not d or d.get('batches_per_launch', 8) != batches_per_launch:
+        return None
+    return d['dram_read_bytes'] + d['dram_write_bytes']
 
 
 def workload_title(wl, layouts):
@@ -566,7 +569,7 @@ class Bench:
         algorithmic bytes / flops per launch of each of the three kernels."""
         ex, acc, nb, nf = self.ex, {}, np.zeros(3), np.zeros(3)
         G = self.pool.max_group
-        outs = self.outs[:G]
+        outs = [self.outs[g % self.nout] for g in range(G)] if G > self.nout else self.outs[:G]
 
         def run(i):
             idx = [(i * G + g) % self.P for g in range(G)]
@@ -604,7 +607,8 @@ class Bench:
                 'kernel': proj, 'bound': bound, 'achieved': gbs if bound == 'hbm' else tfs,
                 'peak': pk['hbm_gbs'] if bound == 'hbm' else tf32_peak,
                 'unit': 'GB/s' if bound == 'hbm' else 'TFLOP/s', 'frac': max(hf, tf),
-                'traffic': ncu_traffic(proj) if self.wl is WORKLOADS['clevr'] else None,
+                'traffic': (ncu_traffic(proj, self.pool.max_group) if self.wl is WORKLOADS['clevr']
+                            else None),
                 'hbm_frac': hf, 'tensor_frac_of_tf32_peak': tf, 'avg_launch_us': kus[proj],
                 'algorithmic_bytes_per_launch': nb[1], 'flops_per_launch': nf[1],
                 'peak_source': pk['source'] + '; TF32 peak taken as bf16 burst / 2',

@@ -94,7 +94,7 @@ typedef struct n2nmn_config {
   int32_t flags;         /* enum n2nmn_flags */
   int32_t max_group;     /* capacity: independent batches (each <= max_batch questions) that one
                           * n2nmn_forward_group call may evaluate with one set of launches;
-                          * 0 or 1 = none, at most 8. Workspaces scale with it. */
+                          * 0 or 1 = none, at most 16. Workspaces scale with it. */
 } n2nmn_config;
 
 /* Replaces `Modules.__init__` (models_clevr/nmn3_modules.py:12-47): allocates the context,

@@ -11,7 +11,10 @@ constexpr int kMaxProjNodesPerPass = 8;
 // One launch may cover several independent batches ("segments": separate feature / word-vector /
 // score buffers of identical shape) so that the kernels see enough work per launch. Images and
 // questions are numbered across the segments: g = seg * N + b.
-constexpr int kMaxSeg = 8;
+#ifndef N2NMN_MAX_SEG
+#define N2NMN_MAX_SEG 16
+#endif
+constexpr int kMaxSeg = N2NMN_MAX_SEG;
 
 // Opcodes mirror enum n2nmn_op in include/n2nmn_b200.h.
 enum Op : int {

@@ -55,7 +55,10 @@ struct Worker {
 // step is ~10 us of host work, a futex wake-up is 50-100 us, so a sleeping worker turns a short
 // burst of submissions (the driver's --steps 20) into a measurement of wake-up latency.
 constexpr int kSpinMicros = 300;
-constexpr int kMaxGroup = 8;
+#ifndef N2NMN_MAX_SEG
+#define N2NMN_MAX_SEG 16
+#endif
+constexpr int kMaxGroup = N2NMN_MAX_SEG;   // = kMaxSeg of the kernels (common.cuh)
 
 inline void cpu_relax() {
 #if defined(__x86_64__) || defined(__i386__)

@@ -278,21 +278,21 @@ def test_forward_group_equals_separate_batches(N):
     W = wts.init_weights('clevr', H, Wd, D, C, seed=16, bias_std=0.1)
     asm = Assembler(synth.vocab_file('clevr'))
     items = []
-    for i in range(8):
+    for i in range(16):
         f, w = synth.make_inputs(N, H, Wd, D, T, seed=400 + i)
         tok = synth.random_valid_tokens(asm, N, T, seed=500 + i)
         items.append((torch.from_numpy(f).cuda(), torch.from_numpy(w).cuda(), tok))
     items[3][2][:, 0] = asm.name2idx_dict['_Find']      # never terminates: invalid -> zero row
     for flags in (0, _lib.FLAG_PROJ_FP32_SIMT):
         ex = make_executor('clevr', items[0][0].cpu().numpy(), items[0][1].cpu().numpy(), C, W,
-                           flags=flags, max_batch=N, max_T=T, max_group=8)
+                           flags=flags, max_batch=N, max_T=T, max_group=16)
         ex.set_tree_cluster(1)   # (the automatic cluster size depends on the question count, and
         single = []              #  a different split of a reduction changes its rounding)
         for f, w, tok in items:
             sc, v = ex.forward_device(f, w, tok)
             single.append((sc.cpu().numpy().copy(), v.copy()))
         assert not single[3][1][0] and not single[3][0][0].any()
-        for G in (1, 2, 3, 8):
+        for G in (1, 2, 3, 8, 16):
             outs, valids = ex.forward_group([x[0] for x in items[:G]], [x[1] for x in items[:G]],
                                             [x[2] for x in items[:G]])
             torch.cuda.synchronize()
@@ -379,7 +379,7 @@ def test_pool_narrow_mode_other_families(family, H, Wd, D, T, C, layouts):
     pool = ExecutorPool(family, items[0][0], items[0][1], C, asm, weights=W, num_streams=12,
                         max_batch=N, max_T=T)
     assert (pool.tree_cluster, pool.proj_ctas, pool.text_ctas_per_group) == (1, 0, 1)
-    assert pool.max_group == 8
+    assert pool.max_group == max(1, min(16, 1024 // N))
     pool.begin()
     outs = [pool.submit(f, w, tok)[0] for f, w, tok in items]
     pool.end()

@@ -10,7 +10,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -s 60 -c 120 -
     --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 40 --warmup 10 --min-seconds 0.02 --trials 1 \
     --no-cpu-baseline --no-e2e --no-train --no-other-configs --no-other-sets > gpurun_out/ncu_launch_$TAG.log 2>&1
 echo "launch list rc=$?"
-GB_ONLY=8 GB_ITERS=4 ncu --set full --clock-control none --import-source on -k "$K" -s 24 -c 6 \
+GB_ONLY=16 GB_ITERS=4 ncu --set full --clock-control none --import-source on -k "$K" -s 24 -c 6 \
     -o gpurun_out/prof_$TAG -f python tools/group_bench.py > gpurun_out/ncu_full_$TAG.log 2>&1
 echo "full rc=$?"
 ls -la gpurun_out | tail -5

@@ -27,13 +27,13 @@ for i in range(P):
         t = synth.expert_mix_tokens(asm, B, T)
         toks.append(np.ascontiguousarray(t[:, np.random.RandomState(i).permutation(B)]))
 ex = LayoutExecutor('clevr', feats[0], wvs[0], C, asm, weights=weights, max_batch=B, max_T=T,
-                    max_group=8)
+                    max_group=int(os.environ.get('GB_MAXG', 16)))
 ex.set_tree_cluster(int(os.environ.get('GB_CLUSTER', 1)))
 ex.set_text_ctas_per_group(int(os.environ.get('GB_TEXT', 1)))
 only = os.environ.get('GB_ONLY')
 iters = int(os.environ.get('GB_ITERS', 40))
 pk_tf32, pk_hbm = 840.25, 6581.6
-for G in ([int(only)] if only else [1, 2, 4, 8]):
+for G in ([int(only)] if only else [1, 2, 4, 8, 16]):
     def run(i):
         idx = [(i * G + g) % P for g in range(G)]
         return ex.forward_group([feats[j] for j in idx], [wvs[j] for j in idx], [toks[j] for j in idx])

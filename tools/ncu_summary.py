@@ -8,13 +8,14 @@ import subprocess
 import sys
 
 tag = sys.argv[1]
+group = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 out = open('profiles/%s.md' % tag, 'w')
 out.write('# ncu summary %s\n\n' % tag)
 out.write('Command: `bash tools/gpu_prof.sh %s` (launch list: bench.py under `ncu --metrics '
-          'gpu__time_duration.sum --clock-control none`, the pool batching 8 batches per launch '
-          'set; `--set full`: one set of launches of `GB_ONLY=8 tools/group_bench.py`, i.e. '
-          'n2nmn_forward_group over 8 batches). Per-launch times are cold-cache and serialised: '
-          'compare shares.\n\n' % tag)
+          'gpu__time_duration.sum --clock-control none`, the pool batching %d batches per launch '
+          'set; `--set full`: one set of launches of `GB_ONLY=%d tools/group_bench.py`, i.e. '
+          'n2nmn_forward_group over %d batches). Per-launch times are cold-cache and serialised: '
+          'compare shares.\n\n' % (tag, group, group, group))
 rows = [r for r in csv.reader(open('gpurun_out/launches_%s.csv' % tag)) if len(r) > 5]
 hdr = [i for i, r in enumerate(rows) if r[0] == 'ID'][0]
 h, data = rows[hdr], rows[hdr + 1:]
@@ -55,7 +56,8 @@ import json
 if traffic:   # a launch-list-only run keeps the previous --set full figures
   json.dump({k: {'dram_read_bytes': sum(x[0] for x in v) / len(v),
                'dram_write_bytes': sum(x[1] for x in v) / len(v), 'launches': len(v),
-               'capture': 'profiles/%s.md' % tag} for k, v in traffic.items()},
+               'batches_per_launch': group, 'capture': 'profiles/%s.md' % tag}
+             for k, v in traffic.items()},
           open('profiles/ncu_traffic.json', 'w'), indent=1)
 out.close()
 print(open('profiles/%s.md' % tag).read())
