@@ -629,12 +629,15 @@ class Bench:
                             'share_of_step': kus[name] / total}
         return out
 
-    def e2e(self, steps, min_seconds):
+    def e2e(self, steps, min_seconds, feat_f16=False):
         """Pinned host features + word vectors -> H2D -> kernels -> D2H scores, every step, through
-        ExecutorPool (n2nmn_forward_host_async per step); wall clock + final synchronize."""
+        ExecutorPool (n2nmn_forward_host_async per step); wall clock + final synchronize.
+        feat_f16: the feature grids are stored as fp16 on the host (a secondary number: not the
+        reference's fp32 feed; n2nmn_forward_group_host_f16_async widens them on the device)."""
         torch = self.torch
         hp = int(min(self.P, max(2, math.ceil(1.2 * L2_BYTES / self.batch_bytes)), 8))
-        hf = [self.feats[i].cpu().pin_memory() for i in range(hp)]
+        hf = [(self.feats[i].half() if feat_f16 else self.feats[i]).cpu().pin_memory()
+              for i in range(hp)]
         hw = [self.wvs[i].cpu().pin_memory() for i in range(hp)]
         # one score buffer per host batch: steps that share a buffer have identical inputs
         hs = [torch.empty((self.B, self.wl['C']), dtype=torch.float32).pin_memory()
@@ -665,13 +668,19 @@ class Bench:
         chk, _ = self.ex.forward_device(self.feats[idx[last]], self.wvs[idx[last]],
                                         self.tok(idx[last]))
         torch.cuda.synchronize()
-        assert torch.equal(hs[idx[last]], chk.cpu()), 'e2e scores differ from the device path'
-        h2d = int(hf[0].numel() * 4 + hw[0].numel() * 4)
+        diff = float((hs[idx[last]] - chk.cpu()).abs().max())
+        if feat_f16:
+            assert diff <= 1e-3, 'fp16-feature e2e scores differ from the fp32 feed by %g' % diff
+        else:
+            assert diff == 0.0, 'e2e scores differ from the device path'
+        h2d = int(hf[0].numel() * hf[0].element_size() + hw[0].numel() * 4)
         d2h = int(hs[0].numel() * 4)
         n = reps * k
         return {'value': self.world * self.B * n / el, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'steps': n, 'timed_region_s': el,
                 'bound': 'pcie', 'achieved_h2d_gbs_per_gpu': h2d * n / el / 1e9,
+                'host_feature_dtype': 'f16' if feat_f16 else 'f32',
+                'max_abs_score_diff_vs_f32_device_path': diff,
                 'how': 'ExecutorPool.submit_block(host_io): pinned host features+word_vecs -> '
                        'async H2D -> C++ layout compile -> kernels -> async D2H scores, %d '
                        'streams, every step; wall clock around the loop + final synchronize, '
@@ -755,6 +764,8 @@ def main():
 
     # ---- e2e: host (pinned) buffers in, host scores out, every step, through the public API
     e2e = None if args.no_e2e else bn.e2e(args.steps, 0.4)
+    # secondary: the same with an fp16 feature store on the host (half the PCIe bytes)
+    e2e_f16 = None if (args.no_e2e or args.config != 'clevr') else bn.e2e(args.steps, 0.4, True)
 
     # ---- strong scaling point: the SAME global batch split over the ranks
     strong = None
@@ -889,7 +900,8 @@ def main():
                             'executor': 'wave' if args.wave else 'tree',
                             'nodes_per_batch': info['num_nodes'], 'max_depth': info['max_depth']},
                            **pool_cfg),
-            'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
+            'clocks': clocks, 'e2e': e2e, 'e2e_f16_host_features': e2e_f16,
+            'gpu_launches': int(launches),
             'host_enqueue_ms_per_step': head['host_enqueue_ms_per_step'], 'host_numa': numa,
             'roofline': roof.get('roofline'), 'roofline_text': roof.get('roofline_text'),
             'roofline_tree': roof.get('roofline_tree'), 'kernel_us': roof.get('kernel_us'),

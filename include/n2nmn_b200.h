@@ -240,11 +240,27 @@ int n2nmn_forward_host_async(n2nmn_ctx* ctx, const float* feat_host, const float
                              int num_vocab, float* scores_host, uint8_t* validity_out,
                              void* stream);
 
+/* n2nmn_forward_group_host_async with the feature grids stored as IEEE fp16 on the host
+ * (feat_host_f16[i]: [N][H][W][D] half, pinned): half the PCIe bytes of the fp32 feed, which is
+ * what bounds the end-to-end rate (21.2 MB per CLEVR batch of 64). The grids are widened to fp32 on
+ * the device (one pass over the staged copy) before the same kernels run; the contraction reads
+ * 10-bit mantissas either way, so the outputs move by <= 1e-4 against the fp32 feed at the CLEVR
+ * sizes (tests/test_gpu_parity.py), inside the 1e-3 bar. N*H*W*D must be a multiple of 8. No
+ * reference counterpart: the reference feeds fp32 `image_feat_batch` (eval_clevr.py:120-123). */
+int n2nmn_forward_group_host_f16_async(n2nmn_ctx* ctx, int num_batches,
+                                       const uint16_t* const* feat_host_f16,
+                                       const float* const* word_vecs_host,
+                                       const int32_t* const* tokens_host, int T, int N,
+                                       const int32_t* vocab_ops, int num_vocab,
+                                       float* const* scores_host, uint8_t* const* validity_out,
+                                       void* stream);
+
 /* ---- several batches in flight -------------------------------------------------------------------
  * One worker thread per (context, stream) pair; n2nmn_pool_submit copies the token matrix into a
  * job for worker `slot` and returns. A worker takes up to n2nmn_max_group(ctx) queued jobs of
  * identical shape at a time and runs them as ONE n2nmn_forward_group (host_io == 0: device
- * pointers) or n2nmn_forward_group_host_async (host_io != 0: pinned host pointers) on its stream:
+ * pointers), n2nmn_forward_group_host_async (host_io == 1: pinned host pointers) or
+ * n2nmn_forward_group_host_f16_async (host_io == 2: `feat` points to fp16 grids) on its stream:
  * dynamic batching of whatever the caller has queued, never waiting for more.
  * n2nmn_pool_wait blocks until every submitted batch has been ENQUEUED (not finished) and returns
  * the first error; `validity_out` arrays are valid after it. The contexts must outlive the pool
@@ -348,10 +364,10 @@ int64_t n2nmn_launch_count(const n2nmn_ctx* ctx);
 
 /* ---- (f1) attentional seq2seq layout generator --------------------------------------------
  * Replaces `AttentionSeq2Seq` (models_clevr/nmn3_netgen_att.py:46-322; the VQA / SHAPES copies
- * are the same code) in its inference configuration (no dropout; greedy decoding under the
- * Assembler's validity masks, or teacher forcing): the encoder LSTM stack under dynamic_rnn
- * (:73-120) and the raw_rnn attention decoder (:122-322). Sampling (`decoder_sampling`) and the
- * backward pass are not provided. */
+ * are the same code) without dropout: greedy decoding under the Assembler's validity masks,
+ * `decoder_sampling` (n2nmn_seq2seq_set_sampling) or teacher forcing: the encoder LSTM stack
+ * under dynamic_rnn (:73-120) and the raw_rnn attention decoder (:122-322). The backward pass is
+ * not provided. */
 typedef struct n2nmn_seq2seq n2nmn_seq2seq;
 typedef struct n2nmn_seq2seq_config {
   int32_t abi_version;     /* N2NMN_ABI_VERSION */
@@ -403,6 +419,13 @@ int n2nmn_seq2seq_forward(n2nmn_seq2seq* s, const int32_t* input_seq_dev,
                           const int32_t* gt_layout_dev, int32_t* tokens_dev,
                           float* token_probs_dev, float* neg_entropy_dev, float* word_vecs_dev,
                           float* atts_dev, void* stream);
+/* `decoder_sampling=True` (nmn3_netgen_att.py:234-256) for the following forward calls:
+ * uniforms_dev [T_decoder][N] fp32 in [0,1) (N = the forward call's N; must stay valid until the
+ * forward's work has run), one number per decoding step and question. The token is drawn from
+ * softmax(token_scores - 50·invalid) by inverse CDF in vocabulary order (`tf.multinomial`'s
+ * distribution; TF's generator itself is not reproducible outside TF) and replaced by the greedy
+ * token if it is invalid (:241-256). NULL = back to greedy decoding. gt_layout_dev still wins. */
+int n2nmn_seq2seq_set_sampling(n2nmn_seq2seq* s, const float* uniforms_dev);
 int64_t n2nmn_seq2seq_launch_count(const n2nmn_seq2seq* s);
 
 #ifdef __cplusplus

@@ -50,6 +50,7 @@ SIGNATURES = {
     'n2nmn_seq2seq_set_weight': (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int, _P]),
     'n2nmn_seq2seq_set_assembler': (C.c_int, [_P, _I32P, _I32P, _I32P, _P]),
     'n2nmn_seq2seq_forward': (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
+    'n2nmn_seq2seq_set_sampling': (C.c_int, [_P, _P]),
     'n2nmn_seq2seq_launch_count': (C.c_int64, [_P]),
     'n2nmn_create': (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
     'n2nmn_destroy': (C.c_int, [_P]),
@@ -78,6 +79,8 @@ SIGNATURES = {
                                       _P, _P]),
     'n2nmn_forward_group_host_async': (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P,
                                                  C.c_int, _P, _P, _P]),
+    'n2nmn_forward_group_host_f16_async': (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P,
+                                                     C.c_int, _P, _P, _P]),
     'n2nmn_max_group': (C.c_int, [_P]),
     'n2nmn_last_step_info': (C.c_int, [_P, C.POINTER(SchedInfo)]),
     'n2nmn_forward_host': (C.c_int, [_P, _P, _P, _I32P, C.c_int, C.c_int, _I32P, C.c_int, _P,

@@ -174,6 +174,7 @@ struct n2nmn_ctx {
   float* e2e_feat = nullptr;
   float* e2e_wv = nullptr;
   float* e2e_scores = nullptr;
+  uint16_t* e2e_feat_f16 = nullptr;   // fp16 staging of host features (host_f16 path)
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t> ev;
@@ -912,6 +913,7 @@ int n2nmn_destroy(n2nmn_ctx* c) {
   }
   cudaFree(c->d_segs); cudaFree(c->d_sumsq);
   cudaFree(c->scores_tmp); cudaFree(c->e2e_feat); cudaFree(c->e2e_wv); cudaFree(c->e2e_scores);
+  cudaFree(c->e2e_feat_f16);
   for (int i = 0; i < kTableSlots; ++i) {
     cudaFreeHost(c->slots[i].host); cudaFree(c->slots[i].dev);
     if (c->slots[i].last_use) cudaEventDestroy(c->slots[i].last_use);
@@ -1314,10 +1316,10 @@ int n2nmn_forward_tokens(n2nmn_ctx* c, const float* feat_dev, const float* wv_de
 namespace {
 // Host-buffer variant of n2nmn_forward_group: H2D of every batch's features and word vectors into
 // context-owned staging, the kernels, D2H of every batch's scores — all enqueued on `stream`.
-int forward_host_impl(n2nmn_ctx* c, int nb, const float* const* feat_host,
+int forward_host_impl(n2nmn_ctx* c, int nb, const void* const* feat_host,
                       const float* const* wv_host, const int32_t* const* tokens, int T, int N,
                       const int32_t* vocab_ops, int num_vocab, float* const* scores_host,
-                      uint8_t* const* validity_out, void* stream, bool sync) {
+                      uint8_t* const* validity_out, void* stream, bool sync, bool feat_f16 = false) {
   if (!c || !feat_host || !wv_host || !tokens || !scores_host || nb <= 0)
     return fail(N2NMN_ERR_ARG, "null argument");
   if (nb > c->G) return fail(N2NMN_ERR_CAPACITY, "too many batches for one group");
@@ -1336,14 +1338,34 @@ int forward_host_impl(n2nmn_ctx* c, int nb, const float* const* feat_host,
     CUDA_TRY(cudaMalloc(&c->e2e_wv, c->G * wcap * sizeof(float)));
     CUDA_TRY(cudaMalloc(&c->e2e_scores, c->G * scap * sizeof(float)));
   }
+  if (feat_f16 && (fbytes / sizeof(float)) % 8 != 0)
+    return fail(N2NMN_ERR_ARG, "fp16 host features need N*H*W*D to be a multiple of 8");
+  const size_t fcap16 = (fcap + 7) & ~(size_t)7;   // fp16 staging slots stay 16-byte aligned
+  if (feat_f16 && !c->e2e_feat_f16)
+    CUDA_TRY(cudaMalloc(&c->e2e_feat_f16, c->G * fcap16 * sizeof(uint16_t)));
   const float* fd[kMaxSeg];
   const float* wd[kMaxSeg];
   float* sd[kMaxSeg];
   for (int i = 0; i < nb; ++i) {
     if (!feat_host[i] || !wv_host[i] || !scores_host[i]) return fail(N2NMN_ERR_ARG, "null argument");
     fd[i] = c->e2e_feat + i * fcap; wd[i] = c->e2e_wv + i * wcap; sd[i] = c->e2e_scores + i * scap;
-    CUDA_TRY(cudaMemcpyAsync(c->e2e_feat + i * fcap, feat_host[i], fbytes, cudaMemcpyHostToDevice, st));
+    if (feat_f16)
+      CUDA_TRY(cudaMemcpyAsync(c->e2e_feat_f16 + i * fcap16, feat_host[i], fbytes / 2,
+                               cudaMemcpyHostToDevice, st));
+    else
+      CUDA_TRY(cudaMemcpyAsync(c->e2e_feat + i * fcap, feat_host[i], fbytes, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(c->e2e_wv + i * wcap, wv_host[i], wbytes, cudaMemcpyHostToDevice, st));
+  }
+  if (feat_f16) {   // widen every staged grid to the fp32 layout the kernels read
+    const size_t cnt = fbytes / sizeof(float);
+    for (int i = 0; i < nb; ++i) {
+      const size_t n8 = (cnt + 7) / 8;
+      widen_f16_kernel<<<(unsigned)std::min<size_t>((n8 + 255) / 256, 148 * 8), 256, 0, st>>>(
+          reinterpret_cast<const uint4*>(c->e2e_feat_f16 + i * fcap16),
+          reinterpret_cast<float4*>(c->e2e_feat + i * fcap), n8);
+      ++c->launches;
+    }
+    CUDA_TRY(cudaGetLastError());
   }
   int rc = n2nmn_forward_group(c, nb, fd, wd, tokens, T, N, vocab_ops, num_vocab, sd, validity_out,
                                stream);
@@ -1363,7 +1385,7 @@ int forward_host_impl(n2nmn_ctx* c, int nb, const float* const* feat_host,
 int n2nmn_forward_host(n2nmn_ctx* c, const float* feat_host, const float* wv_host,
                        const int32_t* tokens, int T, int N, const int32_t* vocab_ops,
                        int num_vocab, float* scores_host, uint8_t* validity_out, void* stream) {
-  return forward_host_impl(c, 1, &feat_host, &wv_host, &tokens, T, N, vocab_ops, num_vocab,
+  return forward_host_impl(c, 1, reinterpret_cast<const void* const*>(&feat_host), &wv_host, &tokens, T, N, vocab_ops, num_vocab,
                            &scores_host, validity_out ? &validity_out : nullptr, stream, true);
 }
 
@@ -1371,7 +1393,7 @@ int n2nmn_forward_host_async(n2nmn_ctx* c, const float* feat_host, const float* 
                              const int32_t* tokens, int T, int N, const int32_t* vocab_ops,
                              int num_vocab, float* scores_host, uint8_t* validity_out,
                              void* stream) {
-  return forward_host_impl(c, 1, &feat_host, &wv_host, &tokens, T, N, vocab_ops, num_vocab,
+  return forward_host_impl(c, 1, reinterpret_cast<const void* const*>(&feat_host), &wv_host, &tokens, T, N, vocab_ops, num_vocab,
                            &scores_host, validity_out ? &validity_out : nullptr, stream, false);
 }
 
@@ -1380,8 +1402,20 @@ int n2nmn_forward_group_host_async(n2nmn_ctx* c, int num_batches, const float* c
                                    int T, int N, const int32_t* vocab_ops, int num_vocab,
                                    float* const* scores_host, uint8_t* const* validity_out,
                                    void* stream) {
-  return forward_host_impl(c, num_batches, feat_host, wv_host, tokens, T, N, vocab_ops, num_vocab,
-                           scores_host, validity_out, stream, false);
+  return forward_host_impl(c, num_batches, reinterpret_cast<const void* const*>(feat_host), wv_host,
+                           tokens, T, N, vocab_ops, num_vocab, scores_host, validity_out, stream,
+                           false);
+}
+
+int n2nmn_forward_group_host_f16_async(n2nmn_ctx* c, int num_batches,
+                                       const uint16_t* const* feat_host_f16,
+                                       const float* const* wv_host, const int32_t* const* tokens,
+                                       int T, int N, const int32_t* vocab_ops, int num_vocab,
+                                       float* const* scores_host, uint8_t* const* validity_out,
+                                       void* stream) {
+  return forward_host_impl(c, num_batches, reinterpret_cast<const void* const*>(feat_host_f16),
+                           wv_host, tokens, T, N, vocab_ops, num_vocab, scores_host, validity_out,
+                           stream, false, true);
 }
 
 int n2nmn_max_group(const n2nmn_ctx* c) { return c ? c->G : 0; }

@@ -100,7 +100,11 @@ void run_group(n2nmn_pool* p, Worker* w, std::vector<Job>& js) {
   }
   const Job& j0 = js[0];
   int rc;
-  if (j0.host_io)
+  if (j0.host_io == 2)
+    rc = n2nmn_forward_group_host_f16_async(w->ctx, n, reinterpret_cast<const uint16_t* const*>(feat),
+                                            wv, tok, j0.T, j0.N, p->vocab.data(),
+                                            (int)p->vocab.size(), scores, valid, w->stream);
+  else if (j0.host_io)
     rc = n2nmn_forward_group_host_async(w->ctx, n, feat, wv, tok, j0.T, j0.N, p->vocab.data(),
                                         (int)p->vocab.size(), scores, valid, w->stream);
   else

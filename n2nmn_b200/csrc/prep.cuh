@@ -1,6 +1,8 @@
 // One-off data-layout kernels: weight repacking at n2nmn_set_weight time and the VQA
 // coordinate-channel augmentation at bind time.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace n2nmn {
@@ -35,6 +37,22 @@ __global__ void pitch_rows_kernel(const float* __restrict__ src, int rows, int M
   if (r >= rows) return;
   for (int c = threadIdx.x; c < Mp; c += blockDim.x)
     dst[(size_t)r * Mp + c] = (c < M) ? src[(size_t)r * M + c] : 0.f;
+}
+
+// Feature grids that travel over PCIe as IEEE fp16 (n2nmn_forward_group_host_f16_async): widen to
+// the fp32 layout every kernel reads. 8 values per thread: one 16-byte load, two 16-byte stores.
+// n8 = count / 8 (the staging buffers are padded to a multiple of 8).
+__global__ void widen_f16_kernel(const uint4* __restrict__ src, float4* __restrict__ dst,
+                                 size_t n8) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = src[i];
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+    const float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
+    const float2 c = __half22float2(h[2]), d = __half22float2(h[3]);
+    dst[2 * i] = make_float4(a.x, a.y, b.x, b.y);
+    dst[2 * i + 1] = make_float4(c.x, c.y, d.x, d.y);
+  }
 }
 
 // ---- all variables from one flat buffer in two launches (after every optimiser step) ------------

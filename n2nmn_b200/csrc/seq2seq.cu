@@ -213,6 +213,7 @@ struct AttnStep {
   const int32_t* b;       // [V][4]
   int32_t* X;             // [N][3] decoding state (nmn3_netgen_att.py:288-293)
   const int32_t* gt;      // [N] this step's ground-truth tokens or nullptr
+  const float* u;         // [N] this step's uniform numbers (decoder_sampling) or nullptr
   int32_t* tokens;        // [N] this step's predicted tokens (row t of predicted_tokens)
   int32_t* cur_tok;       // [N] input token of the next step
   float* probs;           // [N] row t of token_probs
@@ -393,6 +394,28 @@ __global__ void __launch_bounds__(kAttnThreads) dec_attn_kernel(AttnStep p) {
       if (ob > best || (ob == best && op < pred)) { best = ob; pred = op; }
     }
     if (pred == 0x7fffffff) pred = 0;
+    if (p.u != nullptr) {
+      // decoder_sampling (:234-256): one draw from softmax(scores - 50·invalid) by inverse CDF
+      // over the tokens in vocabulary order — the first token whose cumulative probability
+      // exceeds u — kept when it is valid, else the greedy token above
+      const float z0 = in0 ? sc0 - (ok0 ? 0.f : 50.f) : -INFINITY;
+      const float z1 = in1 ? sc1 - (ok1 ? 0.f : 50.f) : -INFINITY;
+      float zm = fmaxf(z0, z1);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) zm = fmaxf(zm, __shfl_xor_sync(0xffffffffu, zm, o));
+      float c0 = in0 ? expf(z0 - zm) : 0.f, c1 = in1 ? expf(z1 - zm) : 0.f;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {   // inclusive scans over the lanes
+        const float t0 = __shfl_up_sync(0xffffffffu, c0, o), t1 = __shfl_up_sync(0xffffffffu, c1, o);
+        if (lane >= o) { c0 += t0; c1 += t1; }
+      }
+      c1 += __shfl_sync(0xffffffffu, c0, 31);
+      const float thr = p.u[n] * __shfl_sync(0xffffffffu, c1, 31);
+      const uint32_t m0 = __ballot_sync(0xffffffffu, in0 && c0 > thr);
+      const uint32_t m1 = __ballot_sync(0xffffffffu, in1 && c1 > thr);
+      const int samp = m0 ? __ffs(m0) - 1 : (m1 ? 31 + __ffs(m1) : V - 1);
+      if (((samp < 32 ? vlo >> samp : vhi >> (samp - 32)) & 1u) != 0u) pred = samp;
+    }
     if (p.gt != nullptr) pred = p.gt[n];   // :264-266
     const float e0 = in0 ? expf(sc0 - mx) : 0.f, e1 = in1 ? expf(sc1 - mx) : 0.f;
     float se = e0 + e1;
@@ -464,6 +487,7 @@ struct n2nmn_seq2seq {
   n2nmn_seq2seq_config cfg;
   std::vector<S2SVar> vars;
   bool dirty = true, tables_set = false;
+  const float* sample_u = nullptr;   // [T_decoder][N] uniforms of the following forward calls
   // derived weights
   float *table_enc = nullptr, *table_dec = nullptr, *dec_rows = nullptr;   // dec_rows = [emb; go]
   float* w_cell[2][kMaxLayers] = {};   // interleaved full matrices [(in+L)][4L]
@@ -825,6 +849,7 @@ int n2nmn_seq2seq_forward(n2nmn_seq2seq* s, const int32_t* input_seq_dev,
     a.wy_t = s->wy_t; a.by = s->v("decoder/token_prediction/biases");
     a.seq_len = seq_len_dev; a.P = s->P; a.W = s->W; a.b = s->b; a.X = s->X;
     a.gt = gt_layout_dev ? gt_layout_dev + (size_t)t * N : nullptr;
+    a.u = s->sample_u ? s->sample_u + (size_t)t * N : nullptr;
     a.tokens = tokens_dev + (size_t)t * N;
     a.cur_tok = s->cur_tok;
     a.probs = token_probs_dev + (size_t)t * N;
@@ -840,6 +865,12 @@ int n2nmn_seq2seq_forward(n2nmn_seq2seq* s, const int32_t* input_seq_dev,
   ++s->launches;
   S2S_TRY(cudaGetLastError());
   if (!ok) return fail_with(N2NMN_ERR_CUDA, "seq2seq kernel launch failed");
+  return N2NMN_OK;
+}
+
+int n2nmn_seq2seq_set_sampling(n2nmn_seq2seq* s, const float* uniforms_dev) {
+  if (!s) return fail_with(N2NMN_ERR_ARG, "null argument");
+  s->sample_u = uniforms_dev;
   return N2NMN_OK;
 }
 

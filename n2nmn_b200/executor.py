@@ -420,14 +420,18 @@ class ExecutorPool:
         """End-to-end step from pinned HOST tensors: H2D of the batch's features and word
         vectors, the forward pass, and D2H of the scores, all enqueued by the slot's worker on
         the slot's stream (copy engines overlap the other slots' kernels). `scores_host` and the
-        returned validity are valid after end() + a stream/device synchronise."""
+        returned validity are valid after end() + a stream/device synchronise. `feat_host` may be
+        a float16 tensor (a feature store kept in half precision: half the PCIe bytes; widened
+        on the device, n2nmn_forward_group_host_f16_async)."""
         k = (self._i // self.max_group) % len(self.executors)
         self._i += 1
         tok = self._tokens(layout_tokens)
         for t in (feat_host, word_vecs_host, scores_host):
-            assert (not t.is_cuda) and t.is_contiguous() and t.dtype == torch.float32
+            assert (not t.is_cuda) and t.is_contiguous()
+        assert word_vecs_host.dtype == torch.float32 and scores_host.dtype == torch.float32
+        assert feat_host.dtype in (torch.float32, torch.float16)
         valid = self._submit(k, feat_host.data_ptr(), word_vecs_host.data_ptr(), tok,
-                             scores_host.data_ptr(), 1)
+                             scores_host.data_ptr(), 2 if feat_host.dtype == torch.float16 else 1)
         self._keep.append((feat_host, word_vecs_host, scores_host))
         return scores_host, valid, self.streams[k]
 
@@ -440,17 +444,21 @@ class ExecutorPool:
         """Pre-marshal a list of same-shape batches for submit_block(): pointer arrays for ONE
         FFI call (n2nmn_pool_submit_many). The tensors/arrays must stay alive and unchanged for as
         long as the block is used; the block keeps references. `outs` device tensors (host_io:
-        pinned host tensors; then feats / word_vecs are pinned host tensors too)."""
+        pinned host tensors; then feats / word_vecs are pinned host tensors too, and the feature
+        grids may be float16 — all of them or none)."""
         toks = [self._tokens(t) for t in tokens]
         n = len(toks)
         T, N = toks[0].shape
         assert all(t.shape == (T, N) for t in toks)
+        f16 = bool(host_io) and feats[0].dtype == torch.float16
         for f, w, o in zip(feats, word_vecs, outs):
             for t in (f, w, o):
-                assert t.is_contiguous() and t.dtype == torch.float32 and t.is_cuda != bool(host_io)
+                assert t.is_contiguous() and t.is_cuda != bool(host_io)
+            assert w.dtype == torch.float32 and o.dtype == torch.float32
+            assert f.dtype == (torch.float16 if f16 else torch.float32)
         valid = np.empty((n, N), np.uint8)
         arr = lambda ptrs: (C.c_void_p * n)(*ptrs)
-        return {'n': n, 'T': T, 'N': N, 'host_io': int(bool(host_io)), 'valid': valid,
+        return {'n': n, 'T': T, 'N': N, 'host_io': 2 if f16 else int(bool(host_io)), 'valid': valid,
                 'feat': arr([f.data_ptr() for f in feats]),
                 'wv': arr([w.data_ptr() for w in word_vecs]),
                 'tok': arr([t.ctypes.data for t in toks]),

@@ -1,7 +1,9 @@
 """Host-side mirror of the reference's layout generator ``AttentionSeq2Seq``
 (models_clevr/nmn3_netgen_att.py:46-322; models_vqa/ and models_shapes/ carry the same file) over
-the C ABI (`n2nmn_seq2seq_*`, include/n2nmn_b200.h). Inference configuration only: dropout off,
-greedy decoding under the Assembler's validity masks or teacher forcing (`use_gt_layout`).
+the C ABI (`n2nmn_seq2seq_*`, include/n2nmn_b200.h). Forward pass without dropout: greedy decoding
+under the Assembler's validity masks, `decoder_sampling=True` (one draw per step from the masked
+token distribution, nmn3_netgen_att.py:234-256; the uniform numbers come from `torch.rand` on the
+device or from the caller, `forward(..., sample_uniforms=)`) or teacher forcing (`use_gt_layout`).
 
 The reference builds a TF graph whose placeholders are fed per batch; here the constructor takes
 the shapes (and optionally the first batch) and ``forward`` / ``__call__`` runs a batch. The
@@ -35,8 +37,7 @@ class AttentionSeq2Seq:
         if encoder_dropout or decoder_dropout:
             raise NotImplementedError('dropout is a training-time option; the B200 seq2seq is the '
                                       'inference configuration')
-        if decoder_sampling:
-            raise NotImplementedError('decoder_sampling (policy-gradient training) is not provided')
+        self.decoder_sampling = bool(decoder_sampling)
         self.T_decoder = int(T_decoder)
         self.encoder_num_vocab, self.encoder_embed_dim = int(num_vocab_txt), int(embed_dim_txt)
         self.decoder_num_vocab, self.decoder_embed_dim = int(num_vocab_nmn), int(embed_dim_nmn)
@@ -122,9 +123,12 @@ class AttentionSeq2Seq:
                                                        shp, len(shape), self._stream()))
                 torch.cuda.current_stream(self.device).synchronize()   # t may be a temporary
 
-    def forward(self, input_seq_batch, seq_length_batch, use_gt_layout=None, gt_layout_batch=None):
+    def forward(self, input_seq_batch, seq_length_batch, use_gt_layout=None, gt_layout_batch=None,
+                sample_uniforms=None):
         """input_seq_batch [T_enc, N] int, seq_length_batch [N] int (device or host);
-        gt_layout_batch [T_decoder, N] with use_gt_layout truthy = teacher forcing."""
+        gt_layout_batch [T_decoder, N] with use_gt_layout truthy = teacher forcing;
+        sample_uniforms [T_decoder, N] in [0, 1): the numbers the sampled decoding consumes
+        (decoder_sampling=True; default `torch.rand` on the device, i.e. torch's generator)."""
         dev = self.device
 
         def i32(x):
@@ -141,19 +145,31 @@ class AttentionSeq2Seq:
             gt = i32(gt_layout_batch)
             if gt.shape != (self.T_decoder, N):
                 raise ValueError('gt_layout_batch must be [T_decoder, N]')
+        u = None
+        if self.decoder_sampling or sample_uniforms is not None:
+            if sample_uniforms is None:
+                u = torch.rand((self.T_decoder, N), dtype=torch.float32, device=dev)
+            else:
+                u = (sample_uniforms if isinstance(sample_uniforms, torch.Tensor) else
+                     torch.as_tensor(np.asarray(sample_uniforms, np.float32)))
+                u = u.to(dev, torch.float32).contiguous()
+                if u.shape != (self.T_decoder, N):
+                    raise ValueError('sample_uniforms must be [T_decoder, N]')
         tokens = torch.empty((self.T_decoder, N), dtype=torch.int32, device=dev)
         probs = torch.empty((self.T_decoder, N), dtype=torch.float32, device=dev)
         ent = torch.empty((N,), dtype=torch.float32, device=dev)
         wv = torch.empty((self.T_decoder, N, self.encoder_embed_dim), dtype=torch.float32, device=dev)
         atts = torch.empty((self.T_decoder, T, N, 1), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
+            check(self._L.n2nmn_seq2seq_set_sampling(
+                self._h, C.c_void_p(u.data_ptr()) if u is not None else None))
             check(self._L.n2nmn_seq2seq_forward(
                 self._h, C.c_void_p(seq.data_ptr()), C.c_void_p(lens.data_ptr()), T, N,
                 C.c_void_p(gt.data_ptr()) if gt is not None else None,
                 C.c_void_p(tokens.data_ptr()), C.c_void_p(probs.data_ptr()),
                 C.c_void_p(ent.data_ptr()), C.c_void_p(wv.data_ptr()), C.c_void_p(atts.data_ptr()),
                 self._stream()))
-        self._keep = (seq, lens, gt)   # alive until the stream has consumed them
+        self._keep = (seq, lens, gt, u)   # alive until the stream has consumed them
         self.predicted_tokens, self.token_probs, self.neg_entropy = tokens, probs, ent
         self.word_vecs, self.atts = wv, atts
         self.log_seq_prob = torch.log(probs).sum(0)          # nmn3_model.py:45

@@ -1,7 +1,8 @@
 """CPU ORACLE (test infrastructure, not product code) — numpy restatement of the attentional
 seq2seq layout generator ``AttentionSeq2Seq`` (models_clevr/nmn3_netgen_att.py:46-322; the VQA
-copy is identical), inference configuration: no dropout, greedy decoding under the validity masks
-or teacher forcing with ground-truth layouts.
+copy is identical) without dropout: greedy decoding under the validity masks, teacher forcing
+with ground-truth layouts, or sampling (decoder_sampling=True, :234-256) with caller-supplied
+uniform numbers (inverse-CDF; TF's own multinomial generator is not reproducible outside TF).
 
 Pinned against golden vectors produced by executing the reference file itself on the numpy TF shim
 (tests/golden/make_golden_seq2seq.py -> golden_seq2seq.npz); the TF-op semantics it relies on
@@ -60,10 +61,15 @@ def encode(w, input_seq, seq_length, num_layers):
     return emb, outs, state, ht, not_finished
 
 
-def decode(w, enc, T_dec, num_layers, P, W, b, use_gt_layout=False, gt_layout=None):
-    """_build_decoder (nmn3_netgen_att.py:122-322), greedy (decoder_sampling=False) or teacher
-    forced. Returns predicted_tokens [T_dec,N] int32, token_probs [T_dec,N], neg_entropy [N],
-    word_vecs [T_dec,N,E], atts [T_dec,T_enc,N,1]."""
+def decode(w, enc, T_dec, num_layers, P, W, b, use_gt_layout=False, gt_layout=None,
+           sample_uniforms=None, margins=None):
+    """_build_decoder (nmn3_netgen_att.py:122-322), greedy (decoder_sampling=False), sampled
+    (`sample_uniforms` [T_dec,N] in [0,1): token = first class whose cumulative probability under
+    softmax(scores - 50·invalid) exceeds u, greedy fallback if that token is invalid, :234-256) or
+    teacher forced. Returns predicted_tokens [T_dec,N] int32, token_probs [T_dec,N], neg_entropy
+    [N], word_vecs [T_dec,N,E], atts [T_dec,T_enc,N,1]. `margins` (a list) receives, per step, the
+    distance of u from the nearest CDF boundary — how far a draw is from flipping under another
+    summation order."""
     emb, outs, state, ht, not_finished = enc
     N = emb.shape[1]
     V = w['decoder/embedding_mat'].shape[0]
@@ -97,6 +103,15 @@ def decode(w, enc, T_dec, num_layers, P, W, b, use_gt_layout=False, gt_layout=No
         vm = valid.astype(np.float32)
         masked = np.where(valid, scores, scores.min() - 1)                                # :259-261
         pred = np.argmax(masked, axis=1).astype(np.int32)
+        if sample_uniforms is not None:
+            z = scores.astype(np.float64) - (1.0 - vm) * 50.0                             # :235
+            q = np.exp(z - z.max(axis=1, keepdims=True))
+            cdf = np.cumsum(q, axis=1) / q.sum(axis=1, keepdims=True)
+            u = np.asarray(sample_uniforms[t], np.float64)
+            samp = np.minimum((cdf <= u[:, None]).sum(axis=1), V - 1)                     # :238-239
+            pred = np.where(valid[np.arange(N), samp], samp, pred).astype(np.int32)       # :244-256
+            if margins is not None:
+                margins.append(np.abs(cdf[:, :-1] - u[:, None]).min(axis=1))
         if use_gt_layout:
             pred = gt_layout[t].astype(np.int32)                                          # :264-266
         es = np.exp(scores - scores.max(axis=1, keepdims=True))
@@ -113,7 +128,7 @@ def decode(w, enc, T_dec, num_layers, P, W, b, use_gt_layout=False, gt_layout=No
 
 
 def run(w, input_seq, seq_length, T_dec, num_layers, P, W, b, use_gt_layout=False,
-        gt_layout=None):
+        gt_layout=None, sample_uniforms=None, margins=None):
     enc = encode(w, np.asarray(input_seq), np.asarray(seq_length), num_layers)
     return enc, decode(w, enc, T_dec, num_layers, np.asarray(P), np.asarray(W), np.asarray(b),
-                       use_gt_layout, gt_layout)
+                       use_gt_layout, gt_layout, sample_uniforms, margins)

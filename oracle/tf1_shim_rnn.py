@@ -131,8 +131,31 @@ def _reduce(fn):
     return r
 
 
+_UNIFORMS = []
+
+
+def set_sampling_uniforms(u):
+    """Uniform numbers in [0, 1) that the shim's `tf.multinomial` consumes, one row [N] per call
+    (= per decoding step of nmn3_netgen_att.py:236-238)."""
+    _UNIFORMS[:] = [np.asarray(r, np.float64) for r in u]
+
+
+def multinomial(logits, num_samples):
+    """`tf.multinomial(logits, 1)` as inverse-CDF sampling from softmax(logits) with the next row
+    of set_sampling_uniforms(): the first class whose cumulative probability exceeds u (TF's own
+    generator is not reproducible outside TF; the distribution is the same)."""
+    assert num_samples == 1
+    z = np.asarray(logits, np.float64)
+    q = np.exp(z - z.max(axis=1, keepdims=True))
+    cdf = np.cumsum(q, axis=1)
+    u = _UNIFORMS.pop(0)
+    tok = (cdf <= (u * cdf[:, -1])[:, None]).sum(axis=1)
+    return _t(np.minimum(tok, z.shape[1] - 1).astype(np.int64)[:, None])
+
+
 def install_rnn(tf):
     """Adds the seq2seq symbols to the fake module returned by tf1_shim.install()."""
+    tf.multinomial = multinomial
     tf.newaxis = None
     tf.convert_to_tensor = lambda v, dtype=None, **k: (
         v if isinstance(v, np.ndarray) else

@@ -267,6 +267,53 @@ def test_executor_pool_threads_match_single_context():
         pool.end()
 
 
+def test_fp16_host_feature_store_matches_device_path_and_oracle():
+    """n2nmn_forward_group_host_f16_async (pool.submit_host with float16 features): bit-identical
+    to the device path fed the same fp16-rounded values as fp32 (the widening is exact), and within
+    1e-3 of the oracle on the ORIGINAL fp32 features at the BASELINE batch (measured ~1e-4)."""
+    from n2nmn_b200 import weights as wts
+    from n2nmn_b200.executor import ExecutorPool
+    N, H, Wd, D, T, C = 64, 10, 15, 512, 20, 28
+    W = wts.init_weights('clevr', H, Wd, D, C, seed=0, bias_std=0.1)
+    asm = Assembler(synth.vocab_file('clevr'))
+    items = []
+    for i in range(5):
+        f, w = synth.make_inputs(N, H, Wd, D, T, seed=1234 + i)
+        tok = (synth.expert_mix_tokens(asm, N, T) if i % 2 == 0 else
+               synth.random_valid_tokens(asm, N, T, seed=7 + i))
+        items.append((f, w, tok))
+    pool = ExecutorPool('clevr', torch.from_numpy(items[0][0]).cuda(),
+                        torch.from_numpy(items[0][1]).cuda(), C, asm, weights=W, num_streams=2,
+                        max_group=3)
+    hf = [torch.from_numpy(f).half().pin_memory() for f, _, _ in items]
+    hw = [torch.from_numpy(w).pin_memory() for _, w, _ in items]
+    hs = [torch.empty((N, C)).pin_memory() for _ in items]
+    pool.begin()
+    valids = [pool.submit_host(f, w, t[2], o)[1] for f, w, t, o in zip(hf, hw, items, hs)]
+    pool.end()
+    torch.cuda.synchronize()
+    ex = pool.executors[0]
+    for (f, w, tok), h16, got, valid in zip(items, hf, hs, valids):
+        want, v = ex.forward_device(h16.float().cuda(), torch.from_numpy(w).cuda(), tok)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(got.numpy(), want.cpu().numpy())
+        assert valid.all() and valid.tolist() == v.tolist()
+    ref_s, _, _ = _oracle_scores('clevr', items[0][0], items[0][1], C, W, items[0][2])
+    err = float(np.max(np.abs(hs[0].numpy() - ref_s)))
+    print('fp16 feature store vs fp32 oracle: max |d scores| = %.3g' % err)
+    assert err <= 1e-3
+    # the same through a pre-marshalled block (n2nmn_pool_submit_many, host_io = 2)
+    hs2 = [torch.empty((N, C)).pin_memory() for _ in items]
+    blk = pool.make_block(hf, hw, [x[2] for x in items], hs2, host_io=True)
+    assert blk['host_io'] == 2
+    pool.begin()
+    pool.submit_block(blk)
+    pool.end()
+    torch.cuda.synchronize()
+    for a, b in zip(hs, hs2):
+        np.testing.assert_array_equal(a.numpy(), b.numpy())
+
+
 @pytest.mark.parametrize('N', [1, 2, 5, 64])
 def test_forward_group_equals_separate_batches(N):
     """n2nmn_forward_group: G independent batches in one set of launches give bit-identical scores

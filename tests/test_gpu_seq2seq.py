@@ -86,6 +86,55 @@ def test_matches_oracle_at_reference_sizes(N, T_enc, T_dec, L, layers):
     check(out, *dec)
 
 
+def test_sampled_decoding_matches_reference_goldens_and_oracle():
+    """decoder_sampling=True (nmn3_netgen_att.py:234-256): with the golden's uniform numbers the
+    tokens of the reference file (run on the shim's inverse-CDF tf.multinomial) bit-exactly; at
+    the CLEVR sizes against the oracle, with draws whose distance from the nearest CDF boundary
+    (> 1e-4, asserted) is far above the fp32 difference between a warp scan and a cumsum."""
+    from n2nmn_b200.seq2seq import AttentionSeq2Seq
+    N, T_enc, T_dec, V_txt, E_txt, E_nmn, L, layers, seed = [int(v) for v in Z['cfg']]
+    asm = Assembler(synth.vocab_file('clevr'))
+    s = AttentionSeq2Seq(None, None, T_dec, V_txt, E_txt, asm.num_vocab_nmn, E_nmn, L, layers, asm,
+                         T_encoder=T_enc, max_batch=N, weights=golden_weights(), device='cuda:0',
+                         decoder_sampling=True)
+    out = s.forward(Z['input_seq'], Z['seq_length'], sample_uniforms=Z['sample_uniforms'])
+    check(out, Z['sample_predicted_tokens'], Z['sample_token_probs'], Z['sample_neg_entropy'],
+          Z['sample_word_vecs'], Z['sample_atts'])
+    # teacher forcing wins over sampling (:264-266); torch.rand draws give valid layouts
+    out = s.forward(Z['input_seq'], Z['seq_length'], True, Z['gt_layout'],
+                    sample_uniforms=Z['sample_uniforms'])
+    check(out, Z['gt_layout'], Z['gt_token_probs'], Z['gt_neg_entropy'], Z['gt_word_vecs'],
+          Z['gt_atts'])
+    torch.manual_seed(5)
+    drawn = set()
+    for _ in range(4):
+        tok = s.forward(Z['input_seq'], Z['seq_length'])[0].cpu().numpy()
+        assert asm.assemble(tok)[1].all()
+        drawn.add(tok.tobytes())
+    assert len(drawn) > 1
+    # a greedy generator is not disturbed by an earlier sampling one (the pointer is per context)
+    g = make(asm, golden_weights(), T_enc, N, T_dec, V_txt, E_txt, E_nmn, L, layers)
+    check(g.forward(Z['input_seq'], Z['seq_length']), Z['greedy_predicted_tokens'],
+          Z['greedy_token_probs'], Z['greedy_neg_entropy'], Z['greedy_word_vecs'], Z['greedy_atts'])
+    for (N, T_enc, T_dec, L, layers, useed) in [(64, 45, 20, 512, 2, 3065), (37, 26, 13, 208, 1, 3037)]:
+        rng = np.random.RandomState(1000 + N)
+        V_nmn, V_txt, E = len(asm.module_names), 90, 300
+        w = init_seq2seq_weights(V_txt, E, V_nmn, E, L, layers, seed=2000 + N)
+        seq = rng.randint(0, V_txt, size=(T_enc, N)).astype(np.int32)
+        lens = rng.randint(1, T_enc + 1, size=N).astype(np.int32)
+        lens[0], lens[-1] = T_enc, 1
+        u = np.random.RandomState(useed).random_sample((T_dec, N)).astype(np.float32)
+        margins = []
+        _, dec = so.run(w, seq, lens, T_dec, layers, asm.P, asm.W, asm.b, sample_uniforms=u,
+                        margins=margins)
+        assert np.min(margins) > 1e-4
+        s = AttentionSeq2Seq(None, None, T_dec, V_txt, E, V_nmn, E, L, layers, asm, T_encoder=T_enc,
+                             max_batch=N, weights=w, device='cuda:0', decoder_sampling=True)
+        out = s.forward(seq, lens, sample_uniforms=u)
+        check(out, *dec)
+        assert asm.assemble(out[0].cpu().numpy())[1].all()
+
+
 def test_single_pass_tf32_option_stays_within_1e_3():
     """precision='tf32' (one TF32 pass per product): teacher-forced probabilities, attention maps
     and word vectors within 2e-3 of the fp32 oracle at the CLEVR sizes; greedy tokens agree on

@@ -39,3 +39,22 @@ def test_encoder_and_both_decoding_modes_match_reference():
     np.testing.assert_allclose(dec[1], Z['gt_token_probs'], atol=2e-6)
     np.testing.assert_allclose(dec[2], Z['gt_neg_entropy'], atol=1e-5)
     np.testing.assert_allclose(dec[3], Z['gt_word_vecs'], atol=2e-6)
+
+
+def test_sampled_decoding_matches_reference():
+    """decoder_sampling=True (nmn3_netgen_att.py:234-256) with the golden's uniform numbers: the
+    reference file itself ran on the shim's inverse-CDF `tf.multinomial`."""
+    N, T_enc, T_dec, V_txt, E_txt, E_nmn, L, layers, seed = [int(v) for v in Z['cfg']]
+    asm = Assembler(synth.vocab_file('clevr'))
+    margins = []
+    _, dec = so.run(golden_weights(), Z['input_seq'], Z['seq_length'], T_dec, layers, asm.P, asm.W,
+                    asm.b, sample_uniforms=Z['sample_uniforms'], margins=margins)
+    assert np.array_equal(dec[0], Z['sample_predicted_tokens'])
+    assert (dec[0] != Z['greedy_predicted_tokens']).any()
+    np.testing.assert_allclose(dec[1], Z['sample_token_probs'], atol=2e-6)
+    np.testing.assert_allclose(dec[2], Z['sample_neg_entropy'], atol=1e-5)
+    np.testing.assert_allclose(dec[3], Z['sample_word_vecs'], atol=2e-6)
+    np.testing.assert_allclose(dec[4], Z['sample_atts'], atol=2e-6)
+    assert asm.assemble(dec[0])[1].all()
+    # no draw sits close enough to a CDF boundary for an fp32 scan (the GPU) to flip it
+    assert np.min(margins) > 2e-5, np.min(margins)
