@@ -71,6 +71,20 @@ def test_batch_loader_matches_reference(tmp_path):
     assert imdb[2]['gt_layout_tokens'].count('_Filter') == 5
 
 
+def test_batch_loader_fp16_feature_store(tmp_path):
+    """feature_dtype='float16': the same batch with the grids rounded to half precision."""
+    path, params = _write_imdb(tmp_path)
+    imdb = data.load_imdb(path)
+    ids = G['loader']['cases'][0]['sample_ids']
+    b32 = data.ClevrBatchLoader(imdb, params).load_one_batch(ids)
+    b16 = data.ClevrBatchLoader(imdb, dict(params, feature_dtype='float16')).load_one_batch(ids)
+    assert b16['image_feat_batch'].dtype == np.float16
+    assert np.array_equal(b16['image_feat_batch'], b32['image_feat_batch'].astype(np.float16))
+    assert b16['input_seq_batch'].tolist() == b32['input_seq_batch'].tolist()
+    with pytest.raises(ValueError):
+        data.ClevrBatchLoader(imdb, dict(params, feature_dtype='int8'))
+
+
 def test_data_reader_one_pass_order_and_short_last_batch(tmp_path):
     path, params = _write_imdb(tmp_path)
     rd = data.DataReader(path, shuffle=False, one_pass=True, prefetch_num=2, num_workers=3, **params)
