@@ -5,8 +5,10 @@ backward, clip, Adam — on the GPU.
 
 Scope: the reference trains the seq2seq layout generator and the module network jointly. Here
 the layout generator has no backward pass, so it is FROZEN: it supplies the layout
-tokens (teacher forced with the ground-truth layouts as in train_clevr_gt_layout.py, or decoded
-greedily) and the attended word vectors; the module network is what learns. Per iteration the
+tokens (teacher forced with the ground-truth layouts as in train_clevr_gt_layout.py, decoded
+greedily, or sampled — `AttentionSeq2Seq(decoder_sampling=True)` as the policy-search script
+does, with its `log_seq_prob` fed to the REINFORCE bookkeeping through `log_seq_prob_fn`) and the
+attended word vectors; the module network is what learns. Per iteration the
 loop returns/logs the reference's quantities (loss, accuracy cur/avg, validity, :197-213) and
 writes snapshots in the TensorFlow checkpoint format under the reference's variable names
 (`snapshot_saver.save`, :216-219) every `snapshot_interval` iterations.
