@@ -37,6 +37,10 @@ if ROOT not in sys.path:
 
 TEXT_DIM = 300
 UNIT = 'questions/s'
+# mma.sync.m16n8k8.tf32 issues once per ~36 cycles per SM sub-partition on this part (measured:
+# tools/ubench/mma_tf32.cu): 4 x 2048 flop / 36 clk x 148 SMs x 1.965 GHz. The
+# ceiling of every mma.sync kernel here (the fp32-parity text / quad products run 3 passes).
+MMA_SYNC_TF32_TFLOPS = 4 * 2048 / 36.0 * 148 * 1.965e9 / 1e12
 
 # BASELINE.json configs made concrete. `clevr` is the configuration the
 # metric is quoted on; the others are reported beside it (`other_configs`) or with --config.
@@ -569,6 +573,10 @@ class Bench:
         algorithmic bytes / flops per launch of each of the three kernels."""
         ex, acc, nb, nf = self.ex, {}, np.zeros(3), np.zeros(3)
         G = self.pool.max_group
+        name2idx = self.asm.name2idx_dict
+        pooled_w = {name2idx[k]: v for k, v in (('_Describe', 1), ('_SameProperty', 2))
+                    if k in name2idx}
+        self.pooled_roots = 0.0     # mean pooled answer roots per launch (pool_kernel's work)
         outs = [self.outs[g % self.nout] for g in range(G)] if G > self.nout else self.outs[:G]
 
         def run(i):
@@ -583,6 +591,9 @@ class Bench:
             for name, us in ex.launch_times():
                 acc.setdefault(name, []).append(us)
             info = ex.last_step_info()
+            for g in range(G):
+                tk = self.tok((i * G + g) % self.P)
+                self.pooled_roots += sum(w * int((tk == t).sum()) for t, w in pooled_w.items()) / n
             nb += np.array(info['kernel_bytes'], float)
             nf += np.array(info['kernel_flops'], float)
         ex.set_profiling(False)
@@ -627,6 +638,34 @@ class Bench:
                             'algorithmic_bytes_per_launch': nb[k], 'flops_per_launch': nf[k],
                             'batches_per_launch': self.pool.max_group,
                             'share_of_step': kus[name] / total}
+        try:    # derived figures; never allowed to cost the line
+            if self.wl is WORKLOADS['clevr'] and 'roofline_text' in out:
+                # the text kernel's governing limit is the mma.sync issue rate, not HBM: three
+                # error-compensated TF32 passes over [rows, 304] x [304, 256] (K, M padded)
+                r = out['roofline_text']
+                rows = nf[0] / (2.0 * TEXT_DIM * 250)
+                issued = 3 * 2.0 * rows * 304 * 256
+                tf = issued / (r['avg_launch_us'] * 1e-6) / 1e12
+                r['issue_rate'] = {'bound': 'mma.sync issue rate (fp32-parity 3xTF32)',
+                                   'issued_flops_per_launch': issued, 'achieved': tf,
+                                   'peak': MMA_SYNC_TF32_TFLOPS, 'unit': 'TFLOP/s',
+                                   'frac': tf / MMA_SYNC_TF32_TFLOPS, 'rows_per_launch': rows}
+            if self.wl['family'] == 'clevr' and 'pool_kernel' in kus and self.pooled_roots > 0:
+                b = self.pooled_roots * self.wl['H'] * self.wl['W'] * self.wl['D'] * 4.0
+                gbs = b / (kus['pool_kernel'] * 1e-6) / 1e9
+                out['roofline_pool'] = {
+                    'kernel': 'pool_kernel', 'bound': 'hbm', 'achieved': gbs,
+                    'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / pk['hbm_gbs'],
+                    'avg_launch_us': kus['pool_kernel'], 'algorithmic_bytes_per_launch': b,
+                    'pooled_roots_per_launch': self.pooled_roots,
+                    'traffic': ncu_traffic('pool_kernel', self.pool.max_group),
+                    'batches_per_launch': self.pool.max_group,
+                    'share_of_step': kus['pool_kernel'] / total,
+                    'note': 'algorithmic = one H*W*D feature grid per pooled root (Describe 1, '
+                            'SameProperty 2); grids the contraction has just read are partly '
+                            'served from L2 (traffic = DRAM bytes of the ncu capture)'}
+        except Exception as e:   # noqa: BLE001
+            out['roofline_derived_error'] = repr(e)
         return out
 
     def e2e(self, steps, min_seconds, feat_f16=False):
@@ -904,7 +943,8 @@ def main():
             'gpu_launches': int(launches),
             'host_enqueue_ms_per_step': head['host_enqueue_ms_per_step'], 'host_numa': numa,
             'roofline': roof.get('roofline'), 'roofline_text': roof.get('roofline_text'),
-            'roofline_tree': roof.get('roofline_tree'), 'kernel_us': roof.get('kernel_us'),
+            'roofline_tree': roof.get('roofline_tree'), 'roofline_pool': roof.get('roofline_pool'),
+            'kernel_us': roof.get('kernel_us'),
             'cpu_baseline': cpu, 'train_step': train, 'layout_generator': layout_gen,
             'other_layout_sets': other_sets,
             'strong_scaling': strong, 'other_configs': others,
