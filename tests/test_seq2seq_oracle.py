@@ -58,3 +58,44 @@ def test_sampled_decoding_matches_reference():
     assert asm.assemble(dec[0])[1].all()
     # no draw sits close enough to a CDF boundary for an fp32 scan (the GPU) to flip it
     assert np.min(margins) > 2e-5, np.min(margins)
+
+
+def test_encoder_matches_torch_lstm_independently():
+    """Independent pin of the restated TF semantics (BasicLSTMCell gate order i,j,f,o with
+    forget_bias 1; dynamic_rnn: zero output and carried state past the sequence end): the oracle's
+    encoder against torch.nn.LSTM over packed sequences, weights mapped TF -> torch
+    (rows [x; h] -> weight_ih / weight_hh, gates i,j,f,o -> i,f,g,o, +1 on the forget bias)."""
+    import torch
+    from n2nmn_b200.weights import init_seq2seq_weights
+    rng = np.random.RandomState(5)
+    V_txt, E, L, layers, T, N = 30, 20, 24, 2, 9, 7
+    w = init_seq2seq_weights(V_txt, E, 15, 12, L, layers, seed=3)
+    for k in list(w):       # biases are zero-initialised: make them count
+        if k.endswith('biases'):
+            w[k] = (0.2 * rng.standard_normal(w[k].shape)).astype(np.float32)
+    seq = rng.randint(0, V_txt, size=(T, N)).astype(np.int32)
+    lens = rng.randint(1, T + 1, size=N).astype(np.int32)
+    lens[0], lens[1] = T, 1
+    emb, outs, state, ht, nf = so.encode(w, seq, lens, layers)
+
+    lstm = torch.nn.LSTM(E, L, num_layers=layers)
+    perm = np.concatenate([np.arange(0, L), np.arange(2 * L, 3 * L), np.arange(L, 2 * L),
+                           np.arange(3 * L, 4 * L)])           # TF i,j,f,o -> torch i,f,g,o
+    with torch.no_grad():
+        for l in range(layers):
+            W, b = so._cell_vars(w, 'encoder', l)
+            nin = E if l == 0 else L
+            b = b.copy()
+            b[2 * L:3 * L] += 1.0                                # forget_bias
+            getattr(lstm, 'weight_ih_l%d' % l).copy_(torch.from_numpy(W[:nin, perm].T.copy()))
+            getattr(lstm, 'weight_hh_l%d' % l).copy_(torch.from_numpy(W[nin:, perm].T.copy()))
+            getattr(lstm, 'bias_ih_l%d' % l).copy_(torch.from_numpy(b[perm]))
+            getattr(lstm, 'bias_hh_l%d' % l).zero_()
+        packed = torch.nn.utils.rnn.pack_padded_sequence(
+            torch.from_numpy(emb), torch.from_numpy(lens.astype(np.int64)), enforce_sorted=False)
+        y, (hn, cn) = lstm(packed)
+        y, _ = torch.nn.utils.rnn.pad_packed_sequence(y, total_length=T)
+    np.testing.assert_allclose(outs, y.numpy(), atol=2e-6)
+    for l in range(layers):
+        np.testing.assert_allclose(state[l][0], cn[l].numpy(), atol=2e-6)
+        np.testing.assert_allclose(state[l][1], hn[l].numpy(), atol=2e-6)
