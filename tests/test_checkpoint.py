@@ -64,6 +64,27 @@ def test_snappy_blocks_and_prefix_compression():
     assert blk[0:3] == bytes([0, 11, 1]) and blk[15:18] == bytes([11, 5, 2])   # shared prefix 11
 
 
+def test_snappy_decoder_against_an_independent_encoder():
+    """TensorFlow compresses index blocks with Snappy: the decoder here against streams written by
+    the Snappy library itself (through pyarrow's codec) — variable-name-like text with long runs
+    (overlapping copies), > 60-byte literals (multi-byte literal lengths), random bytes, empty."""
+    pa = pytest.importorskip('pyarrow')
+    if not pa.Codec.is_available('snappy'):
+        pytest.skip('pyarrow without snappy')
+    codec = pa.Codec('snappy')
+    rng = np.random.RandomState(0)
+    names = [('neural_module_network/layout_execution/module_variables/%s/%s/%s%s' % (m, l, k, a))
+             .encode() for m in ('FindModule', 'TransformModule', 'DescribeModule')
+             for l in ('conv_image', 'fc_text', 'fc_att') for k in ('weights', 'biases')
+             for a in ('', '/Adam', '/Adam_1')]
+    cases = [b'', b'a', b'ab' * 5000, b''.join(names), bytes(rng.randint(0, 256, 70000, dtype=np.uint8)),
+             b'\x00' * 100000, b''.join(names) * 40 + bytes(rng.randint(0, 4, 3000, dtype=np.uint8))]
+    for raw in cases:
+        comp = codec.compress(raw, asbytes=True)
+        assert ck._snappy_decompress(comp) == raw
+    assert len(codec.compress(cases[2], asbytes=True)) < 600      # it really compressed
+
+
 def test_import_export_module_weights(tmp_path):
     from n2nmn_b200 import weights as wts
     W = wts.init_weights('clevr', 10, 15, 512, 28, seed=3, bias_std=0.1)
