@@ -222,16 +222,26 @@ class ClevrBatchLoader:
 class DataReader:
     """DataReader (util/clevr_train/data_reader.py:87-143): `batches()` yields dicts from a bounded
     prefetch queue; order is the imdb order, or a fresh permutation per epoch with `shuffle`;
-    the last batch of a pass may be short; `one_pass` ends the generator after one epoch."""
+    the last batch of a pass may be short; `one_pass` ends the generator after one epoch.
+    `rank` / `world` (not in the reference, which is single-device): this reader serves one rank of
+    a data-parallel job — every epoch's order (the same on all ranks: a common `seed` is required
+    with `shuffle`) is dealt round-robin, rank r taking questions r, r+world, … of it, so the ranks
+    see disjoint questions and, up to one, equally many."""
 
     def __init__(self, imdb_file, shuffle=True, one_pass=False, prefetch_num=8, num_workers=4,
-                 pinned=False, seed=None, **kwargs):
+                 pinned=False, seed=None, rank=0, world=1, **kwargs):
         self.imdb = load_imdb(imdb_file) if isinstance(imdb_file, str) else imdb_file
         self.shuffle, self.one_pass = shuffle, one_pass
         self.data_params = kwargs
         self.batch_size = kwargs['batch_size']
         self.batch_loader = ClevrBatchLoader(self.imdb, kwargs, pinned=pinned,
                                              num_buffers=prefetch_num + num_workers + 2)
+        if not 0 <= rank < world:
+            raise ValueError('rank must be in [0, world)')
+        if world > 1 and shuffle and seed is None:
+            raise ValueError('a data-parallel reader needs a common seed (the ranks must draw the '
+                             'same permutation to get disjoint shards)')
+        self.rank, self.world = int(rank), int(world)
         self._rng = np.random.RandomState(seed)
         self._q = queue.Queue(maxsize=prefetch_num)
         self._workers = max(1, num_workers)
@@ -240,7 +250,8 @@ class DataReader:
 
     def _epoch_order(self):
         n = len(self.imdb)
-        return self._rng.permutation(n) if self.shuffle else np.arange(n)
+        order = self._rng.permutation(n) if self.shuffle else np.arange(n)
+        return order[self.rank::self.world]
 
     def _produce(self):
         """Loader threads work on consecutive batches of the epoch; results enter the queue in

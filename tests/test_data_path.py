@@ -99,6 +99,22 @@ def test_data_reader_one_pass_order_and_short_last_batch(tmp_path):
         data.DataReader('imdb.json', **params)
 
 
+def test_data_reader_rank_shards_are_disjoint_and_cover_the_epoch(tmp_path):
+    path, params = _write_imdb(tmp_path)
+    seen = []
+    for r in range(2):
+        rd = data.DataReader(path, shuffle=True, one_pass=True, seed=11, rank=r, world=2,
+                             **dict(params, batch_size=2))
+        seen.append([p for b in rd.batches() for p in b['image_path_list']])
+    assert not set(seen[0]) & set(seen[1])
+    assert sorted(seen[0] + seen[1]) == ['img_%d.png' % i for i in range(5)]
+    assert abs(len(seen[0]) - len(seen[1])) <= 1
+    with pytest.raises(ValueError):
+        data.DataReader(path, shuffle=True, rank=0, world=2, **params)      # no common seed
+    with pytest.raises(ValueError):
+        data.DataReader(path, shuffle=False, rank=2, world=2, **params)
+
+
 def test_vocab_dict_unknown_words(tmp_path):
     f = tmp_path / 'v.txt'
     f.write_text('a\nb\n')
