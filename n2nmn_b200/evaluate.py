@@ -71,6 +71,39 @@ def evaluate_split(pool, batches, assembler, answer_word_list, tst_image_set, sa
     return res
 
 
+def merge_rank_results(results, tst_image_set=None):
+    """One result from the per-rank results of a data-parallel evaluation (rank r evaluated
+    questions r, r+world, … of the split: `DataReader(..., shuffle=False, rank=r, world=world)`):
+    counts summed, accuracies recomputed, `output_answers` interleaved back into the split's
+    order, so the prediction file is the one a single process writes."""
+    world = len(results)
+    n = sum(r['num_questions'] for r in results)
+    answers = [None] * n
+    for r, res in enumerate(results):
+        if len(res['output_answers']) != len(range(r, n, world)):
+            raise ValueError('rank %d evaluated %d questions, expected %d of %d dealt round-robin'
+                             % (r, len(res['output_answers']), len(range(r, n, world)), n))
+        answers[r::world] = res['output_answers']
+    out = dict(split=tst_image_set or results[0]['split'], num_questions=n,
+               output_answers=answers)
+    for k in ('answer_correct', 'layout_correct', 'layout_valid'):
+        out[k] = sum(r[k] for r in results)
+    out['answer_accuracy'] = out['answer_correct'] / max(n, 1)
+    out['layout_accuracy'] = out['layout_correct'] / max(n, 1)
+    out['layout_validity'] = out['layout_valid'] / max(n, 1)
+    return out
+
+
+def gather_rank_results(res, group=None):
+    """All ranks call this after `evaluate_split` on their shard (no collective on the data path:
+    this is the optional gather of SURVEY.md §8e, a few KB per rank); every rank returns the
+    merged result."""
+    import torch.distributed as dist
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, res, group=group)
+    return merge_rank_results(parts)
+
+
 def accuracy_lines(res):
     """The four lines eval_clevr.py:140-151 prints and writes."""
     n = res['num_questions']

@@ -116,3 +116,26 @@ def test_eval_writers(tmp_path):
     j = tmp_path / 'vqa.json'
     ev.write_vqa_prediction_file(str(j), [11, 12], ['cat', 'no'])
     assert j.read_text() == '[{"question_id":\n11,\n"answer":\n"cat"},\n{"question_id":\n12,\n"answer":\n"no"}]'
+
+
+def test_merge_rank_results_restores_split_order():
+    """Data-parallel evaluation: per-rank results (round-robin deal of the split) merge into the
+    single-process result, prediction lines back in split order."""
+    from n2nmn_b200 import evaluate as ev
+    answers = ['a%d' % i for i in range(7)]
+    world = 3
+    parts = []
+    for r in range(world):
+        mine = answers[r::world]
+        parts.append(dict(split='val', num_questions=len(mine), answer_correct=r + 1,
+                          layout_correct=len(mine), layout_valid=len(mine) - (r == 0),
+                          answer_accuracy=0.0, layout_accuracy=0.0, layout_validity=0.0,
+                          output_answers=mine))
+    res = ev.merge_rank_results(parts)
+    assert res['output_answers'] == answers and res['num_questions'] == 7
+    assert (res['answer_correct'], res['layout_correct'], res['layout_valid']) == (6, 7, 6)
+    assert abs(res['answer_accuracy'] - 6 / 7) < 1e-12 and res['split'] == 'val'
+    parts[1]['output_answers'] = parts[1]['output_answers'][:-1]
+    parts[1]['num_questions'] -= 1
+    with pytest.raises(ValueError):          # not a round-robin deal of one split
+        ev.merge_rank_results(parts)
