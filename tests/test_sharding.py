@@ -145,3 +145,26 @@ def test_two_rank_balanced_shards_match_single_process(tmp_path):
     want = np.concatenate([_flat(g, sorted(g)), [avg]])
     np.testing.assert_allclose(got['flat'], want, rtol=1e-4, atol=1e-7)
     np.testing.assert_allclose(got['scores'], scores, rtol=0, atol=1e-5)
+
+
+def _gather_worker(rank, world, port, out):
+    from n2nmn_b200 import evaluate as ev
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    answers = ['w%d' % i for i in range(9)][rank::world]
+    res = dict(split='val', num_questions=len(answers), answer_correct=len(answers) - rank,
+               layout_correct=len(answers), layout_valid=len(answers), answer_accuracy=0.0,
+               layout_accuracy=0.0, layout_validity=0.0, output_answers=answers)
+    merged = ev.gather_rank_results(res)
+    if rank == 1:                      # every rank holds the merged result
+        np.save(out, merged, allow_pickle=True)
+    dist.destroy_process_group()
+
+
+def test_two_rank_eval_results_gather(tmp_path):
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    out = str(tmp_path / 'r1.npy')
+    mp.spawn(_gather_worker, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out, allow_pickle=True).item()
+    assert got['output_answers'] == ['w%d' % i for i in range(9)]
+    assert got['num_questions'] == 9 and got['answer_correct'] == 5 + 3
