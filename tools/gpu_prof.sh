@@ -1,7 +1,7 @@
 #!/bin/bash
-# ncu launch list of bench.py + full capture of the forward kernels as launched for a group of 8
+# ncu launch list of bench.py + full capture of the forward kernels as launched for a group of 16
 # batches (tools/group_bench.py). Numbers printed under ncu are never bench values; this only
-# produces the inputs of tools/ncu_summary.py -> profiles/<tag>.md.
+# produces the inputs of tools/ncu_summary.py <tag> 16 -> profiles/<tag>.md.
 set +e
 mkdir -p gpurun_out
 TAG=${1:-r2}
